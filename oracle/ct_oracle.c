@@ -1,0 +1,444 @@
+/* oracle/ct_oracle.c -- plain-C CPU restatement of CobbleTrace's per-pixel ray/scene
+ * intersection + shading path.  TEST INFRASTRUCTURE ONLY (see ct_oracle.h): the product
+ * never links or calls this.  Parity: PINNED against oracle/_ref (the compiled reference).
+ *
+ * The reference's arithmetic is mixed: v3_t is double (mymath.h:24-28) but
+ * DotProduct / Magnitude / V3ByIndex return float (mymath.h:229,213,179) and most scalars
+ * of the hot path are float.  Every such rounding point is written out explicitly below as
+ * a (float) cast of a double expression.  Build with -ffp-contract=off, no -ffast-math.
+ *
+ * Citations are file:line in /root/reference.
+ */
+#include "ct_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define RAY_T_INIT 1e30f            /* ray_t.t of primary and shadow rays, raythread.cpp:508,304 */
+static const float FINF = 4294967296.0f;          /* raythread.cpp:58 */
+#define BACKGROUND 0x333333u        /* raythread.cpp:59 */
+
+/* mymath.h:11-17 -- macros, NOT fminf/fmaxf: with a NaN operand the comparison is false
+ * and the SECOND operand is returned. */
+#define MACRO_MIN(a, b) (((a) < (b)) ? (a) : (b))
+#define MACRO_MAX(a, b) (((a) > (b)) ? (a) : (b))
+
+typedef struct { double x, y, z; } vec3;
+
+static inline vec3 v_sub(vec3 a, vec3 b) { vec3 r = {a.x - b.x, a.y - b.y, a.z - b.z}; return r; }   /* mymath.h:147 */
+static inline vec3 v_add(vec3 a, vec3 b) { vec3 r = {a.x + b.x, a.y + b.y, a.z + b.z}; return r; }   /* mymath.h:129 */
+static inline vec3 v_scale(double s, vec3 a) { vec3 r = {s * a.x, s * a.y, s * a.z}; return r; }     /* mymath.h:47 */
+static inline vec3 v_neg(vec3 a) { vec3 r = {-a.x, -a.y, -a.z}; return r; }                          /* mymath.h:118 */
+static inline vec3 v_cross(vec3 a, vec3 b) {                                                         /* mymath.h:234 */
+    vec3 r = {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+    return r;
+}
+/* mymath.h:229 -- double sum, left to right, rounded to float on return */
+static inline float v_dot(vec3 a, vec3 b) { return (float)(a.x * b.x + a.y * b.y + a.z * b.z); }
+/* mymath.h:213 -- double sqrt, rounded to float on return */
+static inline float v_mag(vec3 a) { return (float)sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+static inline vec3 v_load(const double *p) { vec3 r = {p[0], p[1], p[2]}; return r; }
+
+typedef struct { vec3 org, dir; float t; } ray;   /* ray_t, scenefile.h:104-108 */
+
+typedef struct {
+    const ct_oracle_scene *s;
+    ct_oracle_counters c;
+} ctx;
+
+/* ---- bvh.cpp:147-163 IntersectTriangle -------------------------------------------- */
+static int intersect_triangle(ray *r, const double *tri) {
+    vec3 p1 = v_load(tri), p2 = v_load(tri + 3), p3 = v_load(tri + 6);
+    vec3 edge1 = v_sub(p2, p1);
+    vec3 edge2 = v_sub(p3, p1);
+    vec3 h = v_cross(r->dir, edge2);
+    float a = v_dot(edge1, h);
+    if (a > -0.0001f && a < 0.0001f) return 0;
+    float f = 1 / a;
+    vec3 sv = v_sub(r->org, p1);
+    float u = f * v_dot(sv, h);
+    if (u < 0 || u > 1) return 0;
+    vec3 q = v_cross(sv, edge1);
+    float v = f * v_dot(r->dir, q);
+    if (v < 0 || u + v > 1) return 0;
+    float t = f * v_dot(edge2, q);
+    if (t > 0.0001f) r->t = MACRO_MIN(r->t, t);
+    return 1;   /* true whatever the sign/size of t */
+}
+
+/* ---- bvh.cpp:165-179 IntersectAABB -------------------------------------------------- */
+static int intersect_aabb(const ray *r, const double *bmin, const double *bmax) {
+    float tx1 = (float)((bmin[0] - r->org.x) / r->dir.x);
+    float tx2 = (float)((bmax[0] - r->org.x) / r->dir.x);
+    float tmin = MACRO_MIN(tx1, tx2);
+    float tmax = MACRO_MAX(tx1, tx2);
+    float ty1 = (float)((bmin[1] - r->org.y) / r->dir.y);
+    float ty2 = (float)((bmax[1] - r->org.y) / r->dir.y);
+    tmin = MACRO_MAX(tmin, MACRO_MIN(ty1, ty2));
+    tmax = MACRO_MIN(tmax, MACRO_MAX(ty1, ty2));
+    float tz1 = (float)((bmin[2] - r->org.z) / r->dir.z);
+    float tz2 = (float)((bmax[2] - r->org.z) / r->dir.z);
+    tmin = MACRO_MAX(tmin, MACRO_MIN(tz1, tz2));
+    tmax = MACRO_MIN(tmax, MACRO_MAX(tz1, tz2));
+    return tmax >= tmin && tmin < r->t && tmax > 0;
+}
+
+/* ---- bvh.cpp:198-222 IntersectBVHClosest (recursive, left child first, no ordering) -- */
+static void bvh_closest(ctx *cx, ray *r, uint32_t node, float *tclosest, uint32_t *closest_index) {
+    const ct_oracle_scene *s = cx->s;
+    cx->c.box_tests++;
+    if (!intersect_aabb(r, s->node_min + 3 * (size_t)node, s->node_max + 3 * (size_t)node)) return;
+    uint32_t count = s->node_count[node];
+    if (count > 0) {
+        uint32_t first = s->node_first[node];
+        for (uint32_t i = 0; i < count; i++) {
+            uint32_t k = s->tri_index[first + i];
+            cx->c.tri_tests++;
+            int hit = intersect_triangle(r, s->tri + 9 * (size_t)k);
+            if (hit && r->t != RAY_T_INIT && r->t < *tclosest) {
+                *closest_index = k;
+                *tclosest = r->t;
+            }
+        }
+    } else {
+        bvh_closest(cx, r, s->node_left[node], tclosest, closest_index);
+        bvh_closest(cx, r, s->node_left[node] + 1, tclosest, closest_index);
+    }
+}
+
+/* ---- raythread.cpp:197-227 ClosestIntersection (tmin/tmax are ignored there too) ------ */
+static int closest_intersection(ctx *cx, ray r, float *tclosest, uint32_t *closest_index) {
+    *tclosest = FINF;
+    *closest_index = 0;
+    bvh_closest(cx, &r, 0, tclosest, closest_index);
+    return r.t != RAY_T_INIT;
+}
+
+/* ---- raythread.cpp:270-273 ReflectRay: 2.0*normal*Dot(normal,ray) - ray ---------------- */
+static vec3 reflect_ray(vec3 rv, vec3 normal) {
+    double d = (double)v_dot(normal, rv);
+    vec3 two_n = v_scale(2.0, normal);
+    return v_sub(v_scale(d, two_n), rv);
+}
+
+/* ---- raythread.cpp:275-327 ComputeLighting --------------------------------------------- */
+static float compute_lighting(ctx *cx, vec3 position, vec3 normal, vec3 view, int specular) {
+    const ct_oracle_scene *s = cx->s;
+    float intensity = 0.0f;
+    for (uint32_t i = 0; i < s->n_lights; i++) {
+        float li = s->light_intensity[i];
+        vec3 light_ray;
+        switch (s->light_type[i]) {
+        case CT_ORACLE_LT_AMBIENT:
+            intensity += li;
+            continue;
+        case CT_ORACLE_LT_POINT:
+            light_ray = v_sub(v_load(s->light_pos + 3 * i), position);
+            break;
+        default: /* directional */
+            light_ray = v_load(s->light_dir + 3 * i);
+            break;
+        }
+        /* shadow check :304 -- full closest traversal from the surface point, no offset, no t<=1 test */
+        ray sr = {position, light_ray, RAY_T_INIT};
+        float tc; uint32_t idx;
+        cx->c.rays_shadow++;
+        if (closest_intersection(cx, sr, &tc, &idx)) continue;
+
+        float n_dot_l = v_dot(normal, light_ray);                       /* :310 */
+        if (n_dot_l > 0) intensity += li * n_dot_l / (v_mag(normal) * v_mag(light_ray));   /* all float :312 */
+
+        if (specular != -1) {                                           /* :316 */
+            vec3 refl = reflect_ray(light_ray, normal);
+            float r_dot_v = v_dot(refl, view);
+            if (r_dot_v > 0) {
+                /* :320-321  pow(float,int) is the double pow; the product is double and the
+                 * += rounds (double)intensity + product back to float. */
+                float q = r_dot_v / (v_mag(refl) * v_mag(view));
+                intensity = (float)((double)intensity + (double)li * pow((double)q, (double)specular));
+            }
+        }
+    }
+    return intensity;
+}
+
+/* ---- color.h ------------------------------------------------------------------------------ */
+typedef struct { float h, s, v; } hsv;
+
+static hsv color_to_hsv(uint32_t color) {      /* color.h:114-120 + RgbToHsv :49-75 */
+    float r = (float)(color & 0xff) / 0xff, g = (float)((color >> 8) & 0xff) / 0xff, b = (float)((color >> 16) & 0xff) / 0xff;
+    float gb_max = MACRO_MAX(g, b), gb_min = MACRO_MIN(g, b);
+    float max_c = MACRO_MAX(r, gb_max);
+    float min_c = MACRO_MIN(r, gb_min);
+    float delta = max_c - min_c;
+    hsv o;
+    o.v = max_c;
+    if (max_c != 0.0) {
+        o.s = delta / max_c;
+    } else {
+        o.s = 0.0f; o.h = -1; return o;
+    }
+    if (r == max_c) o.h = (g - b) / delta;
+    else if (g == max_c) o.h = 2 + (b - r) / delta;
+    else o.h = 4 + (r - g) / delta;
+    o.h = (float)((double)o.h * 60.0);
+    if (o.h < 0) o.h = (float)((double)o.h + 360.0);
+    return o;
+}
+
+static uint8_t to_u8(float x) { return (uint8_t)(int)x; }   /* float -> uint8_t argument conversion (truncation) */
+
+static uint32_t hsv_to_color(hsv c) {          /* color.h:122-126 + HsvToRgb :18-45 */
+    float r, g, b;
+    if (c.s == 0) {
+        r = g = b = c.v;
+    } else {
+        c.h = (float)((double)c.h / 60.0);
+        int i = (int)floor((double)c.h);
+        float f = c.h - i;
+        float aa = c.v * (1 - c.s);
+        float bb = c.v * (1 - (c.s * f));
+        float cc = c.v * (1 - (c.s * (1 - f)));
+        r = g = b = 0; /* the reference leaves them uninitialised for i outside 0..5 (color.h:35-42) */
+        switch (i) {
+        case 0: r = c.v; g = cc;  b = aa;  break;
+        case 1: r = bb;  g = c.v; b = aa;  break;
+        case 2: r = aa;  g = c.v; b = cc;  break;
+        case 3: r = aa;  g = bb;  b = c.v; break;
+        case 4: r = cc;  g = aa;  b = c.v; break;
+        case 5: r = c.v; g = aa;  b = bb;  break;
+        }
+    }
+    float r255 = r * 0xff, g255 = g * 0xff, b255 = b * 0xff;
+    uint8_t R = to_u8(MACRO_MIN(r255, 0xff)), G = to_u8(MACRO_MIN(g255, 0xff)), B = to_u8(MACRO_MIN(b255, 0xff));
+    return ((uint32_t)B << 16) | ((uint32_t)G << 8) | R;     /* 0x00BBGGRR color.h:77-80 */
+}
+
+uint32_t ct_oracle_shade_color(uint32_t material_color, float intensity) {
+    hsv c = color_to_hsv(material_color);
+    c.v = intensity;                              /* raythread.cpp:365 */
+    return hsv_to_color(c);
+}
+
+/* raythread.cpp:375-379: per channel local*(1-r) + reflected*r in double, truncated to uint8_t */
+uint32_t ct_oracle_blend(uint32_t lc, uint32_t rc, float reflection) {
+    double wl = (double)(1 - reflection), wr = (double)reflection;
+    uint32_t out = 0;
+    for (int sh = 0; sh <= 16; sh += 8) {
+        double l = (double)((lc >> sh) & 0xff), r = (double)((rc >> sh) & 0xff);
+        double c = wl * l + wr * r;
+        out |= (uint32_t)(uint8_t)(int)c << sh;
+    }
+    return out;
+}
+
+/* ---- raythread.cpp:353-386 TraceRay ------------------------------------------------------------ */
+static uint32_t trace_ray(ctx *cx, ray r, int depth) {
+    const ct_oracle_scene *s = cx->s;
+    float tclosest; uint32_t idx;
+    if (!closest_intersection(cx, r, &tclosest, &idx)) return BACKGROUND;
+    const double *tri = s->tri + 9 * (size_t)idx;
+    vec3 position = v_add(r.org, v_scale((double)tclosest, r.dir));                 /* :360 */
+    /* NormalOfSceneObject :336-346: raw cross product, flipped to face the viewer */
+    vec3 n = v_cross(v_sub(v_load(tri + 3), v_load(tri)), v_sub(v_load(tri + 6), v_load(tri)));
+    float d = v_dot(n, r.dir);
+    vec3 normal = (d < 0) ? n : v_neg(n);
+    float intensity = compute_lighting(cx, position, normal, v_neg(r.dir), s->mat_specular[idx]);
+    uint32_t local = ct_oracle_shade_color(s->mat_color[idx], intensity);
+    float reflection = s->mat_reflection[idx];
+    if (depth <= 0 || reflection <= 0) return local;                                 /* :369 */
+    vec3 rdir = reflect_ray(v_neg(r.dir), normal);                                   /* :372 */
+    ray rr = {position, rdir, 0.0f};                                                 /* :373 -- t = 0 (sic) */
+    cx->c.rays_reflection++;
+    uint32_t reflected = trace_ray(cx, rr, depth - 1);
+    return ct_oracle_blend(local, reflected, reflection);
+}
+
+/* ---- pixel loop, raythread.cpp:452-510 + CanvasToViewport :186-194 + CanvasPutPixel :176-184 --- */
+typedef struct {
+    ctx cx;
+    int W, H, y0, y1, max_depth, flags;
+    uint32_t *frame;
+    ct_oracle_hit *hits;
+} job;
+
+static void *render_rows(void *arg) {
+    job *j = (job *)arg;
+    const ct_oracle_scene *s = j->cx.s;
+    int W = j->W, H = j->H;
+    float half = (float)(H / 2);                 /* :454 float width = bitmap->height/2 (int division) */
+    int x_lo = (int)-half, x_hi = (int)half;
+    if (j->flags & CT_ORACLE_WIDE) { x_lo = -(W / 2); x_hi = W - W / 2; }
+    float sx = 1.0f / (float)H, sy = 1.0f / (float)H;   /* :189-192 viewport {1,1,1} :554, float quotient */
+    vec3 cam = v_load(s->cam_pos);
+    const double *m = s->cam_rot;
+    for (int x = x_lo; x < x_hi; x++) {
+        for (int y = j->y0; y < j->y1; y++) {
+            double vx = (double)(float)x * (double)sx, vy = (double)(float)y * (double)sy, vz = 1.0;
+            vec3 dir;                                  /* v3_t * m3x3_t, mymath.h:68-75 */
+            dir.x = vx * m[0] + vy * m[3] + vz * m[6];
+            dir.y = vx * m[1] + vy * m[4] + vz * m[7];
+            dir.z = vx * m[2] + vy * m[5] + vz * m[8];
+            int col = x + W / 2, row = H / 2 - y;      /* :181-182 */
+            int stored = !(row < 0 || row >= H || col < 0 || col >= W);   /* draw2d.h:11-14 */
+            ray r = {cam, dir, RAY_T_INIT};
+            j->cx.c.rays_primary++;
+            if (j->hits && stored) {
+                ctx tmp = { s, {0, 0, 0, 0, 0} };
+                ct_oracle_hit *h = &j->hits[(size_t)row * W + col];
+                h->found = (uint32_t)closest_intersection(&tmp, r, &h->t, &h->index);
+            }
+            uint32_t color = trace_ray(&j->cx, r, j->max_depth);
+            if (stored) j->frame[(size_t)row * W + col] = color;
+        }
+    }
+    return NULL;
+}
+
+int ct_oracle_render(const ct_oracle_scene *s, int W, int H, int y_start, int y_end, int max_depth, int flags,
+                     uint32_t *frame, ct_oracle_hit *hits, ct_oracle_counters *counters, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    int rows = y_end - y_start;
+    if (rows <= 0) return 0;
+    if (n_threads > rows) n_threads = rows;
+    if (hits) for (size_t i = 0; i < (size_t)W * H; i++) if (0) hits[i].found = 0; /* caller pre-fills */
+    job *jobs = (job *)calloc((size_t)n_threads, sizeof(job));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    for (int i = 0; i < n_threads; i++) {
+        jobs[i].cx.s = s;
+        jobs[i].W = W; jobs[i].H = H; jobs[i].max_depth = max_depth; jobs[i].flags = flags;
+        jobs[i].y0 = y_start + (int)((long long)rows * i / n_threads);
+        jobs[i].y1 = y_start + (int)((long long)rows * (i + 1) / n_threads);
+        jobs[i].frame = frame; jobs[i].hits = hits;
+        if (n_threads == 1) render_rows(&jobs[i]);
+        else pthread_create(&th[i], NULL, render_rows, &jobs[i]);
+    }
+    ct_oracle_counters total = {0, 0, 0, 0, 0};
+    for (int i = 0; i < n_threads; i++) {
+        if (n_threads > 1) pthread_join(th[i], NULL);
+        total.rays_primary += jobs[i].cx.c.rays_primary;
+        total.rays_shadow += jobs[i].cx.c.rays_shadow;
+        total.rays_reflection += jobs[i].cx.c.rays_reflection;
+        total.box_tests += jobs[i].cx.c.box_tests;
+        total.tri_tests += jobs[i].cx.c.tri_tests;
+    }
+    if (counters) *counters = total;
+    free(jobs); free(th);
+    return 0;
+}
+
+/* ---- raythread.cpp:564-572 camera matrix (double cos/sin of float angles) ----------------------- */
+void ct_oracle_camera_rotation(float yaw, float pitch, float roll, double o[9]) {
+    double cy = cos(yaw), sy = sin(yaw), cp = cos(pitch), sp = sin(pitch), cr = cos(roll), sr = sin(roll);
+    o[0] = cy * cp;  o[1] = cy * sp * sr - sy * cr;  o[2] = cy * sp * cr + sy * sr;
+    o[3] = sy * cp;  o[4] = sy * sp * sr + cy * cr;  o[5] = sy * sp * cr - cy * sr;
+    o[6] = -sy;      o[7] = cp * sr;                 o[8] = cp * cr;
+}
+
+/* ---- single-call KAT entry points ------------------------------------------------------------------- */
+int ct_oracle_intersect_triangle(const double org[3], const double dir[3], float *ray_t, const double tri[9]) {
+    ray r = {v_load(org), v_load(dir), *ray_t};
+    int hit = intersect_triangle(&r, tri);
+    *ray_t = r.t;
+    return hit;
+}
+
+int ct_oracle_intersect_aabb(const double org[3], const double dir[3], float ray_t, const double bmin[3], const double bmax[3]) {
+    ray r = {v_load(org), v_load(dir), ray_t};
+    return intersect_aabb(&r, bmin, bmax);
+}
+
+int ct_oracle_closest(const ct_oracle_scene *s, const double org[3], const double dir[3], float ray_t0,
+                      uint32_t *index, float *tclosest) {
+    ctx cx = { s, {0, 0, 0, 0, 0} };
+    ray r = {v_load(org), v_load(dir), ray_t0};
+    *tclosest = FINF;
+    *index = 0;
+    bvh_closest(&cx, &r, 0, tclosest, index);
+    return r.t != RAY_T_INIT;
+}
+
+/* ---- bvh.cpp:16-120 build: midpoint split on the longest axis, leaves <= 2 or unsplittable -------- */
+typedef struct {
+    uint32_t n_tri, used;
+    const double *tri;
+    double *centroid;       /* n_tri x 3, BuildBVH :112 */
+    double *nmin, *nmax;
+    uint32_t *left, *first, *count, *index;
+} builder;
+
+static inline float by_axis_f(const double *v, int axis) { return (float)v[axis]; }   /* V3ByIndex mymath.h:179 returns float */
+
+static void update_bounds(builder *b, uint32_t node) {                                   /* bvh.cpp:30-49 */
+    double *mn = b->nmin + 3 * (size_t)node, *mx = b->nmax + 3 * (size_t)node;
+    for (int a = 0; a < 3; a++) { mn[a] = (double)1e30f; mx[a] = (double)-1e30f; }
+    uint32_t first = b->first[node];
+    for (uint32_t i = 0; i < b->count[node]; i++) {
+        const double *t = b->tri + 9 * (size_t)b->index[first + i];
+        for (int p = 0; p < 3; p++)
+            for (int a = 0; a < 3; a++) mn[a] = MACRO_MIN(mn[a], t[3 * p + a]);
+        for (int p = 0; p < 3; p++)
+            for (int a = 0; a < 3; a++) mx[a] = MACRO_MAX(mx[a], t[3 * p + a]);
+    }
+}
+
+static void subdivide(builder *b, uint32_t node) {                                       /* bvh.cpp:51-106 */
+    if (b->count[node] <= 2) return;
+    double ext[3];
+    for (int a = 0; a < 3; a++) ext[a] = b->nmax[3 * (size_t)node + a] - b->nmin[3 * (size_t)node + a];
+    int axis = 0;
+    if (ext[1] > ext[0]) axis = 1;
+    if (ext[2] > by_axis_f(ext, axis)) axis = 2;            /* double vs float-rounded compare :64 */
+    float split = by_axis_f(b->nmin + 3 * (size_t)node, axis) + by_axis_f(ext, axis) * 0.5f;   /* :67 */
+    int i = (int)b->first[node];
+    int j = i + (int)b->count[node] - 1;
+    while (i <= j) {
+        if (by_axis_f(b->centroid + 3 * (size_t)b->index[i], axis) < split) {
+            i++;
+        } else {
+            uint32_t t = b->index[i];
+            b->index[i] = b->index[j];
+            b->index[j--] = t;
+        }
+    }
+    uint32_t left_count = (uint32_t)i - b->first[node];
+    if (left_count == 0 || left_count == b->count[node]) return;
+    uint32_t l = b->used++, r = b->used++;
+    b->left[node] = l;
+    b->first[l] = b->first[node];
+    b->count[l] = left_count;
+    b->first[r] = (uint32_t)i;
+    b->count[r] = b->count[node] - left_count;
+    b->count[node] = 0;
+    update_bounds(b, l);
+    update_bounds(b, r);
+    subdivide(b, l);
+    subdivide(b, r);
+}
+
+uint32_t ct_oracle_build_bvh(uint32_t n_tri, const double *tri, double *node_min, double *node_max,
+                             uint32_t *node_left, uint32_t *node_first, uint32_t *node_count, uint32_t *tri_index) {
+    builder b;
+    b.n_tri = n_tri; b.tri = tri; b.used = 1;
+    b.nmin = node_min; b.nmax = node_max; b.left = node_left; b.first = node_first; b.count = node_count; b.index = tri_index;
+    size_t n_nodes = n_tri ? 2 * (size_t)n_tri - 1 : 1;
+    memset(node_min, 0, n_nodes * 3 * sizeof(double));
+    memset(node_max, 0, n_nodes * 3 * sizeof(double));
+    memset(node_left, 0, n_nodes * sizeof(uint32_t));
+    memset(node_first, 0, n_nodes * sizeof(uint32_t));
+    memset(node_count, 0, n_nodes * sizeof(uint32_t));
+    b.centroid = (double *)malloc(sizeof(double) * 3 * (size_t)(n_tri ? n_tri : 1));
+    double third = (double)0.3333f;                         /* :112  (p1+p2+p3) * 0.3333f */
+    for (uint32_t k = 0; k < n_tri; k++) {
+        tri_index[k] = k;                                   /* :24-26 */
+        const double *t = tri + 9 * (size_t)k;
+        for (int a = 0; a < 3; a++) b.centroid[3 * (size_t)k + a] = third * ((t[a] + t[3 + a]) + t[6 + a]);
+    }
+    node_left[0] = 0; node_first[0] = 0; node_count[0] = n_tri;
+    update_bounds(&b, 0);
+    subdivide(&b, 0);
+    free(b.centroid);
+    return b.used;
+}
