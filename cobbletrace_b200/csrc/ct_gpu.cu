@@ -1,0 +1,854 @@
+// ct_gpu.cu -- sm_100a wavefront renderer behind the C ABI in include/ct_gpu.h.
+//
+// Replaces the worker half of the reference's boss/worker (raythread.cpp:437-543
+// RayTracePartition -> TraceRay :353 -> ClosestIntersection :197 -> bvh.cpp:198
+// IntersectBVHClosest / ComputeLighting :275).  Not a port: the recursive per-pixel CPU loop
+// becomes a wavefront of persistent-warp kernels over SoA path state in HBM:
+//
+//   k_primary   raygen (CanvasToViewport :186) + closest-hit DFS            -> hit records
+//   k_shade     NormalOfSceneObject :329 + ComputeLighting :275 (any-hit shadow rays with early
+//               exit) + HsvToColor; emits the reflection ray (:372-373) into the next queue
+//   k_bounce    the reference's degenerate t=0 reflection rays (:373): first barycentric
+//               pass in DFS order                               -> hit records
+//   k_resolve   unwinds the per-pixel blend chain (:375-379) and stores 0x00BBGGRR pixels
+//
+// Arithmetic is the reference's mixed fp64/fp32, reproduced exactly (ct_exact.cuh).
+// No tensor cores: the path has no dense contraction.  No CPU fallback.
+#include "../../include/ct_gpu.h"
+#include "ct_exact.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace {
+
+using namespace ct;
+
+constexpr int kStackMax = 96;        // DFS stack entries per ray (tree depth limit, checked at upload)
+constexpr int kMaxDevices = 16;
+constexpr int kBlockThreads = 128;   // 4 warps per CTA
+constexpr uint32_t kNoPos = 0xffffffffu;
+
+// ---- device-side scene layout (SoA arrays in HBM, uploaded once) -----------------------------------
+struct __align__(16) DevNode {       // 64 B: one node = two 32-B sectors
+    double bmin[3];
+    double bmax[3];
+    uint32_t left, first, count, pad;
+};
+struct __align__(16) DevTri {        // 80 B, stored in LEAF order (position = slot in bvh indexes[])
+    double p1[3], e1[3], e2[3];      // e1 = p2-p1, e2 = p3-p1 (bvh.cpp:148-149, raythread.cpp:337-338)
+    uint32_t orig, pad;              // original triangle id (= closestIndex of the reference)
+};
+struct DevLight { int32_t type; float intensity; double pos[3]; double dir[3]; };
+
+struct DevSched {                    // zeroed at the start of every tile render
+    uint32_t work[32];               // dynamic-fetch cursors, one per launch of the tile
+    uint32_t queue_count[16];        // paths alive at depth d (d >= 1)
+};
+struct DevTotals {                   // running ray / test counters (never reset by a tile)
+    unsigned long long rays_primary, rays_shadow, rays_reflection, box_tests, tri_tests;
+};
+
+struct Params {
+    const DevNode *nodes;
+    const DevTri *tris;
+    const ct_material *materials;    // by original id
+    const DevLight *lights;
+    uint32_t n_lights, n_tri;
+    uint32_t pos_of_tri0;            // leaf position of original triangle 0 (closestIndex default, raythread.cpp:205)
+    double cam[3], rot[9];
+    float vp_w, vp_h, vp_d;
+    int W, H, max_depth;
+    uint32_t background;
+    // tile
+    int x_lo, n_x, y_lo, n_y;        // canvas x in [x_lo, x_lo+n_x), y in [y_lo, y_lo+n_y)
+    int blocks_x;                    // ceil(n_x / 8): pixel blocks of 8x4 per warp
+    uint32_t n_slots;                // blocks_x * ceil(n_y/4) * 32
+    uint32_t cap;                    // capacity of every per-slot array
+    // per-slot path state
+    float *hit0_t; uint32_t *hit0_pos;           // depth-0 hit (pos = kNoPos-1.. see below)
+    float *hitb_t; uint32_t *hitb_pos;           // depth>=1 hits, by queue slot
+    double *ray_buf[2];                          // depth>=1 rays: 6 doubles per queue slot, ping-pong
+    uint32_t *path_slot[2];                      // queue slot -> depth-0 slot, ping-pong
+    uint32_t *stack_color; float *stack_refl;    // [depth][slot]
+    uint8_t *term_level;                         // [slot] level at which the chain ended
+    uint32_t *fb;                                // W*H
+    uint32_t *dbg_found, *dbg_index; float *dbg_t;   // optional (CT_FLAG_KEEP_HITS), framebuffer layout
+    DevSched *sched;
+    DevTotals *tot;
+};
+
+struct LocalCount { uint32_t box = 0, tri = 0; };
+
+CT_DEV V3 ld3(const double *p) { return {p[0], p[1], p[2]}; }
+
+CT_DEV void load_node(const DevNode *nodes, uint32_t i, DevNode &n) {
+    const double2 *p = reinterpret_cast<const double2 *>(nodes + i);
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    uint4 m = __ldg(reinterpret_cast<const uint4 *>(p + 3));
+    n.bmin[0] = a.x; n.bmin[1] = a.y; n.bmin[2] = b.x;
+    n.bmax[0] = b.y; n.bmax[1] = c.x; n.bmax[2] = c.y;
+    n.left = m.x; n.first = m.y; n.count = m.z;
+}
+
+CT_DEV void load_tri(const DevTri *tris, uint32_t pos, V3 &p1, V3 &e1, V3 &e2) {
+    const double2 *p = reinterpret_cast<const double2 *>(tris + pos);
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    double e = __ldg(reinterpret_cast<const double *>(p + 4));
+    p1 = {a.x, a.y, b.x};
+    e1 = {b.y, c.x, c.y};
+    e2 = {d.x, d.y, e};
+}
+
+enum TraverseMode { kClosest, kAnyHit, kFirstLine };
+
+// IntersectBVHClosest (bvh.cpp:198-222) as an explicit-stack DFS: left child first, right child
+// pushed, boxes tested at visit time against the CURRENT ray.t -- the reference's exact visit order,
+// so box/triangle test counts equal the reference's.
+//   kClosest   general semantics (any initial ray.t).
+//   kAnyHit    shadow rays (ray.t = 1e30f): `found` is all that is used (raythread.cpp:306), so stop at
+//              the first triangle that lowers ray.t, i.e. bary pass and 1e-4 < t < 1e30.
+//   kFirstLine reflection rays (ray.t = 0, raythread.cpp:373): ray.t never changes, the first bary
+//              pass in DFS order becomes closestIndex with tclosest = 0, so stop there.
+// Returns: kAnyHit -> occluded; others -> ray.t != 1e30f ("found").
+template <TraverseMode MODE, bool COUNT>
+CT_DEV bool traverse(const Params &P, Ray &r, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    uint32_t stack[kStackMax];
+    int sp = 0;
+    uint32_t node = 0;
+    tclosest = kFinf;          // raythread.cpp:204
+    closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
+    while (true) {
+        DevNode nd;
+        load_node(P.nodes, node, nd);
+        if (COUNT) lc.box++;
+        if (intersect_aabb(r, nd.bmin, nd.bmax)) {
+            if (nd.count > 0) {
+                for (uint32_t i = 0; i < nd.count; i++) {
+                    uint32_t pos = nd.first + i;
+                    V3 p1, e1, e2;
+                    load_tri(P.tris, pos, p1, e1, e2);
+                    if (COUNT) lc.tri++;
+                    float t;
+                    if (intersect_triangle(r, p1, e1, e2, &t)) {
+                        if (MODE == kAnyHit) {
+                            if (t > kEps && t < kRayTInit) return true;
+                        } else if (MODE == kFirstLine) {
+                            closest_pos = pos; tclosest = 0.0f;
+                            return true;
+                        } else {
+                            if (t > kEps) r.t = macro_min(r.t, t);                     // bvh.cpp:161
+                            if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
+                                closest_pos = pos; tclosest = r.t;
+                            }
+                        }
+                    }
+                }
+            } else {
+                stack[sp++] = nd.left + 1;
+                node = nd.left;
+                continue;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    if (MODE == kAnyHit) return false;
+    return r.t != kRayTInit;
+}
+
+// Primary ray of canvas pixel (x,y): CanvasToViewport (raythread.cpp:186-194) * camera.rotation (mymath.h:68-75)
+CT_DEV Ray primary_ray(const Params &P, int x, int y) {
+    float hh = (float)P.H;                                  // "Keep it square": both scales use bitmap->height
+    double sx = (double)__fdiv_rn(P.vp_w, hh), sy = (double)__fdiv_rn(P.vp_h, hh);
+    double vx = __dmul_rn((double)(float)x, sx), vy = __dmul_rn((double)(float)y, sy), vz = (double)P.vp_d;
+    Ray r;
+    r.o = {P.cam[0], P.cam[1], P.cam[2]};
+    r.d.x = __dadd_rn(__dadd_rn(__dmul_rn(vx, P.rot[0]), __dmul_rn(vy, P.rot[3])), __dmul_rn(vz, P.rot[6]));
+    r.d.y = __dadd_rn(__dadd_rn(__dmul_rn(vx, P.rot[1]), __dmul_rn(vy, P.rot[4])), __dmul_rn(vz, P.rot[7]));
+    r.d.z = __dadd_rn(__dadd_rn(__dmul_rn(vx, P.rot[2]), __dmul_rn(vy, P.rot[5])), __dmul_rn(vz, P.rot[8]));
+    r.t = kRayTInit;
+    ray_finish(r);
+    return r;
+}
+
+// slot -> canvas pixel.  A warp owns an 8x4 pixel block (coherent rays); returns false for padding lanes
+// and for pixels PutPixel would drop (draw2d.h:11-14), which are not traced at all.
+CT_DEV bool slot_pixel(const Params &P, uint32_t slot, int &x, int &y, int &fb_index) {
+    uint32_t blk = slot >> 5, lane = slot & 31u;
+    int bx = (int)(blk % (uint32_t)P.blocks_x), by = (int)(blk / (uint32_t)P.blocks_x);
+    int ix = bx * 8 + (int)(lane & 7u), iy = by * 4 + (int)(lane >> 3);
+    if (ix >= P.n_x || iy >= P.n_y) return false;
+    x = P.x_lo + ix; y = P.y_lo + iy;
+    int col = x + P.W / 2, row = P.H / 2 - y;               // CanvasPutPixel raythread.cpp:181-182
+    if (row < 0 || row >= P.H || col < 0 || col >= P.W) return false;
+    fb_index = row * P.W + col;
+    return true;
+}
+
+CT_DEV uint32_t warp_fetch(uint32_t *cursor) {               // persistent warps pull 32 slots at a time
+    uint32_t base = 0;
+    if ((threadIdx.x & 31u) == 0) base = atomicAdd(cursor, 32u);
+    return __shfl_sync(0xffffffffu, base, 0);
+}
+
+CT_DEV void warp_add(unsigned long long *dst, uint32_t v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads) k_primary(const __grid_constant__ Params P, int work_idx) {
+    LocalCount lc;
+    uint32_t n_rays = 0;
+    while (true) {
+        uint32_t base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= P.n_slots) break;
+        uint32_t slot = base + (threadIdx.x & 31u);
+        int x, y, fbi;
+        if (!slot_pixel(P, slot, x, y, fbi)) continue;
+        Ray r = primary_ray(P, x, y);
+        float tc; uint32_t pos;
+        bool found = traverse<kClosest, COUNT>(P, r, tc, pos, lc);
+        n_rays++;
+        P.hit0_t[slot] = tc;
+        P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
+        if (P.dbg_found) {
+            P.dbg_found[fbi] = found ? 1u : 0u;
+            P.dbg_index[fbi] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
+            P.dbg_t[fbi] = tc;
+        }
+    }
+    warp_add(&P.tot->rays_primary, n_rays);
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
+}
+
+// TraceRay body after the closest hit (raythread.cpp:359-373) for the paths alive at `depth`.
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__ Params P, int depth, int work_idx) {
+    LocalCount lc;
+    uint32_t n_shadow = 0, n_refl = 0;
+    const uint32_t n = depth == 0 ? P.n_slots : P.sched->queue_count[depth];
+    const int cur = depth & 1, nxt = cur ^ 1;
+    while (true) {
+        uint32_t base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= n) break;
+        uint32_t q = base + (threadIdx.x & 31u);
+        bool active = q < n;
+        uint32_t slot = q; int fbi = 0;
+        Ray r; float tc = 0.0f; uint32_t pos = kNoPos;
+        if (active) {
+            if (depth == 0) {
+                int x, y;
+                active = slot_pixel(P, slot, x, y, fbi);
+                if (active) { r = primary_ray(P, x, y); tc = P.hit0_t[slot]; pos = P.hit0_pos[slot]; }
+            } else {
+                slot = P.path_slot[cur][q];
+                const double2 *rb = reinterpret_cast<const double2 *>(P.ray_buf[cur] + 6ull * q);
+                double2 a = rb[0], b = rb[1], c = rb[2];
+                r.o = {a.x, a.y, b.x}; r.d = {b.y, c.x, c.y};
+                tc = P.hitb_t[q]; pos = P.hitb_pos[q];
+            }
+        }
+        bool emit = false;
+        V3 position = {0, 0, 0}, rdir = {0, 0, 0};
+        if (active) {
+            uint32_t *sc = P.stack_color + (size_t)depth * P.cap + slot;
+            if (pos == kNoPos) {                                           // miss (depth 0 only): raythread.cpp:385
+                if (depth == 0) P.fb[fbi] = P.background;
+                *sc = P.background;
+                P.term_level[slot] = (uint8_t)depth;
+            } else {
+                V3 p1, e1, e2;
+                load_tri(P.tris, pos, p1, e1, e2);
+                const ct_material mat = P.materials[P.tris[pos].orig];
+                position = vadd(r.o, vscale((double)tc, r.d));              // :360
+                V3 nn = vcross(e1, e2);                                     // NormalOfSceneObject :337-339
+                float dd = vdot(nn, r.d);
+                V3 normal = (dd < 0.0f) ? nn : vneg(nn);                    // :341-345
+                V3 view = vneg(r.d);
+                // ---- ComputeLighting :275-327, lights in file order, fp32 accumulator
+                float intensity = 0.0f;
+                for (uint32_t i = 0; i < P.n_lights; i++) {
+                    const DevLight &L = P.lights[i];
+                    float li = L.intensity;
+                    if (L.type == CT_LIGHT_AMBIENT) { intensity = __fadd_rn(intensity, li); continue; }
+                    V3 lray = (L.type == CT_LIGHT_POINT) ? vsub(ld3(L.pos), position) : ld3(L.dir);
+                    Ray sr; sr.o = position; sr.d = lray; sr.t = kRayTInit;  // :304 no offset, no t<=1 test
+                    ray_finish(sr);
+                    float stc; uint32_t spos;
+                    n_shadow++;
+                    if (traverse<kAnyHit, COUNT>(P, sr, stc, spos, lc)) continue;
+                    float ndl = vdot(normal, lray);                          // :310
+                    if (ndl > 0.0f)
+                        intensity = __fadd_rn(intensity, __fdiv_rn(__fmul_rn(li, ndl), __fmul_rn(vmag(normal), vmag(lray))));
+                    if (mat.specular != -1) {                                // :316
+                        V3 refl = reflect_ray(lray, normal);
+                        float rdv = vdot(refl, view);
+                        if (rdv > 0.0f) {                                    // :319-321 double pow, += rounds to float
+                            float qv = __fdiv_rn(rdv, __fmul_rn(vmag(refl), vmag(view)));
+                            double term = __dmul_rn((double)li, pow((double)qv, (double)mat.specular));
+                            intensity = __double2float_rn(__dadd_rn((double)intensity, term));
+                        }
+                    }
+                }
+                uint32_t local = shade_color(mat.color, intensity);
+                *sc = local;
+                int remaining = P.max_depth - depth;                        // recursionDepth of this TraceRay call
+                if (remaining <= 0 || !(mat.reflection > 0.0f)) {           // :369  (reflection <= 0, NaN-safe)
+                    P.term_level[slot] = (uint8_t)depth;
+                    if (depth == 0) P.fb[fbi] = local;
+                } else {
+                    P.stack_refl[(size_t)depth * P.cap + slot] = mat.reflection;
+                    rdir = reflect_ray(view, normal);                        // :372
+                    emit = true;
+                }
+            }
+        }
+        // warp-aggregated append of the reflection rays to the next queue
+        uint32_t mask = __ballot_sync(0xffffffffu, emit);
+        if (mask) {
+            uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1, qbase = 0;
+            if (lane == leader) qbase = atomicAdd(&P.sched->queue_count[depth + 1], (uint32_t)__popc(mask));
+            qbase = __shfl_sync(0xffffffffu, qbase, leader);
+            if (emit) {
+                uint32_t nq = qbase + __popc(mask & ((1u << lane) - 1u));
+                double2 *rb = reinterpret_cast<double2 *>(P.ray_buf[nxt] + 6ull * nq);
+                rb[0] = make_double2(position.x, position.y);
+                rb[1] = make_double2(position.z, rdir.x);
+                rb[2] = make_double2(rdir.y, rdir.z);
+                P.path_slot[nxt][nq] = slot;
+                n_refl++;
+            }
+        }
+    }
+    warp_add(&P.tot->rays_shadow, n_shadow);
+    warp_add(&P.tot->rays_reflection, n_refl);
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
+}
+
+// Closest "hit" of the reflection rays {position, reflected, t = 0} (raythread.cpp:373).
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads) k_bounce(const __grid_constant__ Params P, int depth, int work_idx) {
+    LocalCount lc;
+    const uint32_t n = P.sched->queue_count[depth];
+    const int cur = depth & 1;
+    while (true) {
+        uint32_t base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= n) break;
+        uint32_t q = base + (threadIdx.x & 31u);
+        if (q >= n) continue;
+        const double2 *rb = reinterpret_cast<const double2 *>(P.ray_buf[cur] + 6ull * q);
+        double2 a = rb[0], b = rb[1], c = rb[2];
+        Ray r;
+        r.o = {a.x, a.y, b.x}; r.d = {b.y, c.x, c.y}; r.t = 0.0f;
+        ray_finish(r);
+        float tc; uint32_t pos;
+        traverse<kFirstLine, COUNT>(P, r, tc, pos, lc);      // found is always true: 0 != 1e30f (:227)
+        P.hitb_t[q] = tc;
+        P.hitb_pos[q] = (pos == kNoPos) ? P.pos_of_tri0 : pos;
+    }
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
+}
+
+// Unwind TraceRay's recursion (raythread.cpp:375-379) for pixels whose chain went past depth 0.
+__global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Params P) {
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < P.n_slots; slot += gridDim.x * blockDim.x) {
+        int x, y, fbi;
+        if (!slot_pixel(P, slot, x, y, fbi)) continue;
+        int lvl = P.term_level[slot];
+        if (lvl == 0) continue;                              // already stored by k_shade
+        uint32_t color = P.stack_color[(size_t)lvl * P.cap + slot];
+        for (int d = lvl - 1; d >= 0; d--)
+            color = blend_color(P.stack_color[(size_t)d * P.cap + slot], color, P.stack_refl[(size_t)d * P.cap + slot]);
+        P.fb[fbi] = color;
+    }
+}
+
+// ---- KAT kernels -----------------------------------------------------------------------------------------
+__global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, const double *org, const double *dir,
+                                const float *t0, uint32_t *found, uint32_t *index, float *tclosest) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r;
+    r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = t0[i];
+    ray_finish(r);
+    LocalCount lc; float tc; uint32_t pos; bool f;
+    if (r.t == 0.0f) f = traverse<kFirstLine, false>(P, r, tc, pos, lc);
+    else f = traverse<kClosest, false>(P, r, tc, pos, lc);
+    if (found) found[i] = f ? 1u : 0u;
+    if (index) index[i] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
+    if (tclosest) tclosest[i] = tc;
+}
+
+__global__ void k_debug_primitives(uint32_t n, const double *org, const double *dir, float *ray_t, const double *tri,
+                                   const double *bmin, const double *bmax, uint32_t *tri_hit, uint32_t *box_hit) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r;
+    r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = ray_t[i];
+    ray_finish(r);
+    double mn[3] = {bmin[3ull * i], bmin[3ull * i + 1], bmin[3ull * i + 2]};
+    double mx[3] = {bmax[3ull * i], bmax[3ull * i + 1], bmax[3ull * i + 2]};
+    box_hit[i] = intersect_aabb(r, mn, mx) ? 1u : 0u;
+    V3 p1 = ld3(tri + 9ull * i), p2 = ld3(tri + 9ull * i + 3), p3 = ld3(tri + 9ull * i + 6);
+    float t;
+    bool hit = intersect_triangle(r, p1, vsub(p2, p1), vsub(p3, p1), &t);
+    if (hit && t > kEps) r.t = macro_min(r.t, t);
+    tri_hit[i] = hit ? 1u : 0u;
+    ray_t[i] = r.t;
+}
+
+// ==== host side of the ABI ===================================================================================
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? CT_ERR_OOM : CT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceState {
+    bool loaded = false;
+    Params p{};
+    uint32_t flags = 0;
+    bool any_reflective = false;
+    int n_sm = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    std::vector<void *> allocs;
+    ct_ray_counters snapshot{};      // totals at the end of the previous counted tile
+    // rows rendered so far (framebuffer rows), for readback clipping
+    int col_lo = 0, col_hi = 0;
+};
+
+DeviceState g_dev[kMaxDevices];
+std::mutex g_mutex;
+
+int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return fail(CT_ERR_NO_DEVICE, "no CUDA device available (%s): this library has no CPU fallback",
+                                                 e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    if (device < 0 || device >= n || device >= kMaxDevices) return fail(CT_ERR_NO_DEVICE, "device %d out of range (0..%d)", device, n - 1);
+    CU(cudaSetDevice(device));
+    return CT_OK;
+}
+
+void free_device(DeviceState &s) {
+    for (void *p : s.allocs) cudaFree(p);
+    s.allocs.clear();
+    if (s.ev0) cudaEventDestroy(s.ev0);
+    if (s.ev1) cudaEventDestroy(s.ev1);
+    if (s.own_stream) cudaStreamDestroy(s.own_stream);
+    s = DeviceState{};
+}
+
+template <typename T>
+int dev_alloc(DeviceState &s, T **out, size_t count, bool zero = false) {
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(CT_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    s.allocs.push_back(p);
+    if (zero) CU(cudaMemset(p, 0, bytes));
+    *out = static_cast<T *>(p);
+    return CT_OK;
+}
+
+#define TRY(expr) do { int rc_ = (expr); if (rc_ != CT_OK) return rc_; } while (0)
+
+// depth of the reference's DFS (stack entries needed) -- iterative to survive degenerate trees
+int bvh_depth(const ct_bvh_node *nodes, uint32_t n_nodes, uint32_t n_tri, bool *ok) {
+    std::vector<std::pair<uint32_t, int>> st;
+    st.push_back({0u, 1});
+    int best = 0;
+    size_t visited = 0;
+    *ok = true;
+    while (!st.empty()) {
+        auto [i, d] = st.back();
+        st.pop_back();
+        if (i >= n_nodes || ++visited > (size_t)n_nodes) { *ok = false; return 0; }
+        best = std::max(best, d);
+        const ct_bvh_node &nd = nodes[i];
+        if (nd.triangle_count == 0) {
+            st.push_back({nd.left_node, d + 1});
+            st.push_back({nd.left_node + 1, d + 1});
+        } else if ((uint64_t)nd.first_triangle_index + nd.triangle_count > n_tri) {
+            *ok = false; return 0;
+        }
+    }
+    return best;
+}
+
+int launch_grid(const DeviceState &s, int blocks_per_sm) { return s.n_sm * blocks_per_sm; }
+
+int read_totals(DeviceState &s, ct_ray_counters *out) {   // synchronises the stream
+    DevTotals h;
+    CU(cudaMemcpyAsync(&h, s.p.tot, sizeof h, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    out->rays_primary = h.rays_primary; out->rays_shadow = h.rays_shadow; out->rays_reflection = h.rays_reflection;
+    out->box_tests = h.box_tests; out->tri_tests = h.tri_tests;
+    return CT_OK;
+}
+
+}  // namespace
+
+// ==== exported C ABI ==========================================================================================
+extern "C" {
+
+int ct_gpu_abi_version(void) { return CT_GPU_ABI_VERSION; }
+
+const char *ct_gpu_last_error(void) { return g_err; }
+
+int ct_gpu_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(CT_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
+    if (!d || d->struct_size != sizeof(ct_scene_desc)) return fail(CT_ERR_INVALID, "ct_scene_desc missing or struct_size != %zu", sizeof(ct_scene_desc));
+    if (d->n_triangles == 0 || !d->triangles || !d->materials) return fail(CT_ERR_INVALID, "scene has no triangles");
+    if (d->triangle_stride < 72 || d->triangle_stride % 8) return fail(CT_ERR_INVALID, "triangle_stride must be >= 72 and a multiple of 8");
+    if (d->n_nodes == 0 || !d->nodes || !d->tri_indexes) return fail(CT_ERR_INVALID, "scene has no BVH (build it with the reference's BuildBVH or ct_host_build_bvh)");
+    if (d->n_lights && !d->lights) return fail(CT_ERR_INVALID, "n_lights > 0 but lights == NULL");
+    if (d->width <= 0 || d->height <= 0 || (int64_t)d->width * d->height > (1ll << 30)) return fail(CT_ERR_INVALID, "bad frame size %dx%d", d->width, d->height);
+    if (d->max_depth < 0 || d->max_depth > 15) return fail(CT_ERR_LIMIT, "max_depth %d outside 0..15", d->max_depth);
+    bool ok = true;
+    int depth = bvh_depth(d->nodes, d->n_nodes, d->n_triangles, &ok);
+    if (!ok) return fail(CT_ERR_INVALID, "BVH is malformed (child or triangle range out of bounds, or a cycle)");
+    if (depth > kStackMax) return fail(CT_ERR_LIMIT, "BVH depth %d exceeds the device traversal stack (%d)", depth, kStackMax);
+    TRY(check_device(device));
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceState &s = g_dev[device];
+    free_device(s);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    s.n_sm = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
+    s.stream = s.own_stream;
+    CU(cudaEventCreate(&s.ev0));
+    CU(cudaEventCreate(&s.ev1));
+    s.flags = d->flags;
+
+    Params &p = s.p;
+    p.n_tri = d->n_triangles; p.n_lights = d->n_lights;
+    // nodes: reference layout -> device layout (same 64 B, pad zeroed)
+    std::vector<DevNode> nodes(d->n_nodes);
+    for (uint32_t i = 0; i < d->n_nodes; i++) {
+        const ct_bvh_node &n = d->nodes[i];
+        for (int a = 0; a < 3; a++) { nodes[i].bmin[a] = n.aabb_min[a]; nodes[i].bmax[a] = n.aabb_max[a]; }
+        nodes[i].left = n.left_node; nodes[i].first = n.first_triangle_index; nodes[i].count = n.triangle_count; nodes[i].pad = 0;
+    }
+    // triangles in leaf order with precomputed edges
+    std::vector<DevTri> tris(d->n_triangles);
+    uint32_t pos0 = kNoPos;
+    const unsigned char *tbase = static_cast<const unsigned char *>(d->triangles);
+    for (uint32_t pos = 0; pos < d->n_triangles; pos++) {
+        uint32_t k = d->tri_indexes[pos];
+        if (k >= d->n_triangles) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes[%u] = %u out of range", pos, k); }
+        if (k == 0) pos0 = pos;
+        double v[9];
+        memcpy(v, tbase + (size_t)k * d->triangle_stride, sizeof v);
+        for (int a = 0; a < 3; a++) {
+            tris[pos].p1[a] = v[a];
+            tris[pos].e1[a] = v[3 + a] - v[a];
+            tris[pos].e2[a] = v[6 + a] - v[a];
+        }
+        tris[pos].orig = k; tris[pos].pad = 0;
+        if (d->materials[k].reflection > 0.0f) s.any_reflective = true;
+    }
+    if (pos0 == kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes is not a permutation (triangle 0 missing)"); }
+    p.pos_of_tri0 = pos0;
+    std::vector<DevLight> lights(std::max<uint32_t>(d->n_lights, 1));
+    for (uint32_t i = 0; i < d->n_lights; i++) {
+        lights[i].type = d->lights[i].type; lights[i].intensity = d->lights[i].intensity;
+        for (int a = 0; a < 3; a++) { lights[i].pos[a] = d->lights[i].position[a]; lights[i].dir[a] = d->lights[i].direction[a]; }
+    }
+    DevNode *dn; DevTri *dt; ct_material *dm; DevLight *dl;
+    TRY(dev_alloc(s, &dn, nodes.size())); TRY(dev_alloc(s, &dt, tris.size()));
+    TRY(dev_alloc(s, &dm, d->n_triangles)); TRY(dev_alloc(s, &dl, lights.size()));
+    CU(cudaMemcpy(dn, nodes.data(), nodes.size() * sizeof(DevNode), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dt, tris.data(), tris.size() * sizeof(DevTri), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dm, d->materials, (size_t)d->n_triangles * sizeof(ct_material), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dl, lights.data(), lights.size() * sizeof(DevLight), cudaMemcpyHostToDevice));
+    p.nodes = dn; p.tris = dt; p.materials = dm; p.lights = dl;
+
+    memcpy(p.cam, d->camera_position, sizeof p.cam);
+    memcpy(p.rot, d->camera_rotation, sizeof p.rot);
+    p.vp_w = d->viewport[0]; p.vp_h = d->viewport[1]; p.vp_d = d->viewport[2];
+    p.W = d->width; p.H = d->height; p.max_depth = d->max_depth; p.background = d->background;
+
+    // x range: the reference's centred square (raythread.cpp:454-455) or the whole width
+    int half = d->height / 2;
+    int x_lo = -half, n_x = 2 * half;
+    if (d->flags & CT_FLAG_WIDE) { x_lo = -(d->width / 2); n_x = d->width; }
+    p.x_lo = x_lo; p.n_x = n_x;
+    p.blocks_x = (n_x + 7) / 8;
+    s.col_lo = std::max(0, x_lo + d->width / 2);
+    s.col_hi = std::min(d->width, x_lo + n_x + d->width / 2);
+    int rows_max = 2 * half + 1;
+    p.cap = (uint32_t)p.blocks_x * (uint32_t)((rows_max + 3) / 4) * 32u;
+
+    const int levels = s.any_reflective ? d->max_depth + 1 : 1;
+    TRY(dev_alloc(s, &p.hit0_t, p.cap)); TRY(dev_alloc(s, &p.hit0_pos, p.cap));
+    TRY(dev_alloc(s, &p.stack_color, (size_t)p.cap * levels));
+    TRY(dev_alloc(s, &p.term_level, p.cap, true));
+    if (levels > 1) {
+        TRY(dev_alloc(s, &p.hitb_t, p.cap)); TRY(dev_alloc(s, &p.hitb_pos, p.cap));
+        TRY(dev_alloc(s, &p.stack_refl, (size_t)p.cap * levels));
+        for (int b = 0; b < 2; b++) { TRY(dev_alloc(s, &p.ray_buf[b], (size_t)p.cap * 6)); TRY(dev_alloc(s, &p.path_slot[b], p.cap)); }
+    }
+    TRY(dev_alloc(s, &p.fb, (size_t)d->width * d->height, true));       // calloc'd like cobbletrace.cpp:57
+    if (d->flags & CT_FLAG_KEEP_HITS) {
+        size_t npx = (size_t)d->width * d->height;
+        TRY(dev_alloc(s, &p.dbg_found, npx)); TRY(dev_alloc(s, &p.dbg_index, npx, true)); TRY(dev_alloc(s, &p.dbg_t, npx, true));
+        CU(cudaMemset(p.dbg_found, 0xff, npx * sizeof(uint32_t)));
+    }
+    TRY(dev_alloc(s, &p.sched, 1, true));
+    TRY(dev_alloc(s, &p.tot, 1, true));
+    s.loaded = true;
+    return CT_OK;
+}
+
+int ct_gpu_set_camera(int device, const double position[3], const double rotation[9]) {
+    if (!position || !rotation) return fail(CT_ERR_INVALID, "NULL camera");
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    memcpy(s.p.cam, position, sizeof s.p.cam);
+    memcpy(s.p.rot, rotation, sizeof s.p.rot);
+    return CT_OK;
+}
+
+int ct_gpu_set_stream(int device, void *cuda_stream) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    CU(cudaStreamSynchronize(s.stream));
+    s.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s.own_stream;
+    return CT_OK;
+}
+
+int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *counters) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    int half = s.p.H / 2;
+    // rows outside [-half+?, half] can never be stored (draw2d.h:11): clip so no ray is wasted on them
+    int y0 = std::max(y_start, half - (s.p.H - 1)), y1 = std::min(y_end, half + 1);
+    if (y1 <= y0) { if (counters) memset(counters, 0, sizeof *counters); return CT_OK; }
+    Params p = s.p;
+    p.y_lo = y0; p.n_y = y1 - y0;
+    p.n_slots = (uint32_t)p.blocks_x * (uint32_t)((p.n_y + 3) / 4) * 32u;
+    if (p.n_slots > p.cap) return fail(CT_ERR_INVALID, "tile [%d,%d) larger than the frame", y_start, y_end);
+    const bool count = (s.flags & CT_FLAG_COUNT_TESTS) != 0;
+    const int depth_max = s.any_reflective ? p.max_depth : 0;
+    Params pk = p; pk.max_depth = depth_max;   // with no reflective material the recursion never goes past depth 0 (:369)
+    cudaStream_t st = s.stream;
+    CU(cudaMemsetAsync(p.sched, 0, sizeof(DevSched), st));
+    CU(cudaEventRecord(s.ev0, st));
+    const int grid = launch_grid(s, 8);
+    int work = 0;
+    if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(pk, work++);
+    else k_primary<false><<<grid, kBlockThreads, 0, st>>>(pk, work++);
+    for (int d = 0; d <= depth_max; d++) {
+        if (d > 0) {
+            if (count) k_bounce<true><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
+            else k_bounce<false><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
+        }
+        if (count) k_shade<true><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
+        else k_shade<false><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
+    }
+    if (depth_max > 0) k_resolve<<<s.n_sm * 4, 256, 0, st>>>(pk);
+    CU(cudaEventRecord(s.ev1, st));
+    CU(cudaGetLastError());
+    s.timed = true;
+    if (counters) {
+        ct_ray_counters now;
+        TRY(read_totals(s, &now));
+        counters->rays_primary = now.rays_primary - s.snapshot.rays_primary;
+        counters->rays_shadow = now.rays_shadow - s.snapshot.rays_shadow;
+        counters->rays_reflection = now.rays_reflection - s.snapshot.rays_reflection;
+        counters->box_tests = now.box_tests - s.snapshot.box_tests;
+        counters->tri_tests = now.tri_tests - s.snapshot.tri_tests;
+        s.snapshot = now;
+    }
+    return CT_OK;
+}
+
+int ct_gpu_sync(int device) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    CU(cudaStreamSynchronize(s.stream));
+    return CT_OK;
+}
+
+int ct_gpu_last_tile_ms(int device, float *ms) {
+    if (!ms) return fail(CT_ERR_INVALID, "NULL ms");
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded || !s.timed) return fail(CT_ERR_NO_SCENE, "no tile rendered on device %d", device);
+    CU(cudaEventSynchronize(s.ev1));
+    CU(cudaEventElapsedTime(ms, s.ev0, s.ev1));
+    return CT_OK;
+}
+
+int ct_gpu_get_counters(int device, ct_ray_counters *out, int reset) {
+    if (!out) return fail(CT_ERR_INVALID, "NULL out");
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    TRY(read_totals(s, out));
+    if (reset) {
+        CU(cudaMemset(s.p.tot, 0, sizeof(DevTotals)));
+        s.snapshot = ct_ray_counters{};
+    }
+    return CT_OK;
+}
+
+int ct_gpu_readback(int device, uint32_t *dst, int dst_stride_pixels, int row_start, int row_end) {
+    if (!dst) return fail(CT_ERR_INVALID, "NULL dst");
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    const Params &p = s.p;
+    // Row 0 corresponds to y = H/2, which the reference's loops never reach (y < yEnd <= H/2): never written.
+    int r0 = std::max(row_start, 1), r1 = std::min(row_end, p.H);
+    int cols = s.col_hi - s.col_lo;
+    if (dst_stride_pixels < p.W) return fail(CT_ERR_INVALID, "dst stride %d < width %d", dst_stride_pixels, p.W);
+    CU(cudaStreamSynchronize(s.stream));
+    if (r1 <= r0 || cols <= 0) return CT_OK;
+    CU(cudaMemcpy2D(dst + (size_t)r0 * dst_stride_pixels + s.col_lo, (size_t)dst_stride_pixels * 4,
+                    p.fb + (size_t)r0 * p.W + s.col_lo, (size_t)p.W * 4, (size_t)cols * 4, (size_t)(r1 - r0),
+                    cudaMemcpyDeviceToHost));
+    return CT_OK;
+}
+
+int ct_gpu_readback_hits(int device, uint32_t *found, uint32_t *index, float *t, int stride_pixels, int row_start, int row_end) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    const Params &p = s.p;
+    if (!p.dbg_found) return fail(CT_ERR_INVALID, "scene was uploaded without CT_FLAG_KEEP_HITS");
+    if (stride_pixels < p.W) return fail(CT_ERR_INVALID, "stride %d < width %d", stride_pixels, p.W);
+    int r0 = std::max(row_start, 0), r1 = std::min(row_end, p.H);
+    CU(cudaStreamSynchronize(s.stream));
+    if (r1 <= r0) return CT_OK;
+    size_t rows = (size_t)(r1 - r0);
+    if (found) CU(cudaMemcpy2D(found + (size_t)r0 * stride_pixels, (size_t)stride_pixels * 4, p.dbg_found + (size_t)r0 * p.W, (size_t)p.W * 4, (size_t)p.W * 4, rows, cudaMemcpyDeviceToHost));
+    if (index) CU(cudaMemcpy2D(index + (size_t)r0 * stride_pixels, (size_t)stride_pixels * 4, p.dbg_index + (size_t)r0 * p.W, (size_t)p.W * 4, (size_t)p.W * 4, rows, cudaMemcpyDeviceToHost));
+    if (t) CU(cudaMemcpy2D(t + (size_t)r0 * stride_pixels, (size_t)stride_pixels * 4, p.dbg_t + (size_t)r0 * p.W, (size_t)p.W * 4, (size_t)p.W * 4, rows, cudaMemcpyDeviceToHost));
+    return CT_OK;
+}
+
+int ct_gpu_framebuffer(int device, void **device_ptr, int *width, int *height) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    if (device_ptr) *device_ptr = s.p.fb;
+    if (width) *width = s.p.W;
+    if (height) *height = s.p.H;
+    return CT_OK;
+}
+
+int ct_gpu_gather_rows(int src_device, int dst_device, int row_start, int row_end) {
+    TRY(check_device(dst_device));
+    TRY(check_device(src_device));
+    DeviceState &a = g_dev[src_device], &b = g_dev[dst_device];
+    if (!a.loaded || !b.loaded) return fail(CT_ERR_NO_SCENE, "both devices need an uploaded scene");
+    if (a.p.W != b.p.W || a.p.H != b.p.H) return fail(CT_ERR_INVALID, "frame sizes differ between devices");
+    int r0 = std::max(row_start, 0), r1 = std::min(row_end, a.p.H);
+    if (r1 <= r0 || src_device == dst_device) return CT_OK;
+    size_t off = (size_t)r0 * a.p.W, bytes = (size_t)(r1 - r0) * a.p.W * 4;
+    CU(cudaMemcpyPeerAsync(b.p.fb + off, dst_device, a.p.fb + off, src_device, bytes, a.stream));
+    return CT_OK;
+}
+
+int ct_gpu_debug_closest(int device, uint32_t n, const double *origins, const double *directions, const float *t0,
+                         uint32_t *found, uint32_t *index, float *tclosest) {
+    if (!origins || !directions || !t0) return fail(CT_ERR_INVALID, "NULL ray arrays");
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    if (n == 0) return CT_OK;
+    double *d_o = nullptr, *d_d = nullptr; float *d_t0 = nullptr, *d_tc = nullptr; uint32_t *d_f = nullptr, *d_i = nullptr;
+    int rc = CT_OK;
+    auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_t0); cudaFree(d_tc); cudaFree(d_f); cudaFree(d_i); };
+#define CUX(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(CT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+    CUX(cudaMalloc(&d_o, 24ull * n)); CUX(cudaMalloc(&d_d, 24ull * n)); CUX(cudaMalloc(&d_t0, 4ull * n));
+    CUX(cudaMalloc(&d_tc, 4ull * n)); CUX(cudaMalloc(&d_f, 4ull * n)); CUX(cudaMalloc(&d_i, 4ull * n));
+    CUX(cudaMemcpy(d_o, origins, 24ull * n, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(d_d, directions, 24ull * n, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(d_t0, t0, 4ull * n, cudaMemcpyHostToDevice));
+    CUX(cudaStreamSynchronize(s.stream));
+    k_debug_closest<<<(n + 127) / 128, 128, 0, s.stream>>>(s.p, n, d_o, d_d, d_t0, d_f, d_i, d_tc);
+    CUX(cudaGetLastError());
+    CUX(cudaStreamSynchronize(s.stream));
+    if (found) CUX(cudaMemcpy(found, d_f, 4ull * n, cudaMemcpyDeviceToHost));
+    if (index) CUX(cudaMemcpy(index, d_i, 4ull * n, cudaMemcpyDeviceToHost));
+    if (tclosest) CUX(cudaMemcpy(tclosest, d_tc, 4ull * n, cudaMemcpyDeviceToHost));
+    cleanup();
+    return CT_OK;
+}
+
+int ct_gpu_debug_primitives(int device, uint32_t n, const double *origins, const double *directions, float *ray_t,
+                            const double *tri, const double *bmin, const double *bmax, uint32_t *tri_hit, uint32_t *box_hit) {
+    if (!origins || !directions || !ray_t || !tri || !bmin || !bmax || !tri_hit || !box_hit) return fail(CT_ERR_INVALID, "NULL array");
+    TRY(check_device(device));
+    if (n == 0) return CT_OK;
+    double *d_o = nullptr, *d_d = nullptr, *d_tri = nullptr, *d_mn = nullptr, *d_mx = nullptr; float *d_t = nullptr; uint32_t *d_th = nullptr, *d_bh = nullptr;
+    int rc = CT_OK;
+    auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_tri); cudaFree(d_mn); cudaFree(d_mx); cudaFree(d_t); cudaFree(d_th); cudaFree(d_bh); };
+    CUX(cudaMalloc(&d_o, 24ull * n)); CUX(cudaMalloc(&d_d, 24ull * n)); CUX(cudaMalloc(&d_tri, 72ull * n));
+    CUX(cudaMalloc(&d_mn, 24ull * n)); CUX(cudaMalloc(&d_mx, 24ull * n)); CUX(cudaMalloc(&d_t, 4ull * n));
+    CUX(cudaMalloc(&d_th, 4ull * n)); CUX(cudaMalloc(&d_bh, 4ull * n));
+    CUX(cudaMemcpy(d_o, origins, 24ull * n, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(d_d, directions, 24ull * n, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(d_tri, tri, 72ull * n, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(d_mn, bmin, 24ull * n, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(d_mx, bmax, 24ull * n, cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(d_t, ray_t, 4ull * n, cudaMemcpyHostToDevice));
+    k_debug_primitives<<<(n + 127) / 128, 128>>>(n, d_o, d_d, d_t, d_tri, d_mn, d_mx, d_th, d_bh);
+    CUX(cudaGetLastError());
+    CUX(cudaDeviceSynchronize());
+    CUX(cudaMemcpy(ray_t, d_t, 4ull * n, cudaMemcpyDeviceToHost));
+    CUX(cudaMemcpy(tri_hit, d_th, 4ull * n, cudaMemcpyDeviceToHost));
+    CUX(cudaMemcpy(box_hit, d_bh, 4ull * n, cudaMemcpyDeviceToHost));
+    cleanup();
+#undef CUX
+    return CT_OK;
+}
+
+int ct_gpu_shutdown(int device) {
+    if (device < 0 || device >= kMaxDevices) return fail(CT_ERR_NO_DEVICE, "device %d out of range", device);
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceState &s = g_dev[device];
+    if (s.loaded || !s.allocs.empty()) {
+        cudaSetDevice(device);
+        cudaDeviceSynchronize();
+        free_device(s);
+    }
+    return CT_OK;
+}
+
+}  // extern "C"

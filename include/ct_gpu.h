@@ -1,0 +1,177 @@
+/* include/ct_gpu.h -- C ABI of the B200 renderer that sits behind CobbleTrace's boss/worker
+ * entry point (reference raythread.cpp:641 RayThread).
+ *
+ * Everything is plain C: POD structs, pointers and sizes.  Every function returns 0 on
+ * success or a negative ct_status; nothing calls exit() (the reference's workers do:
+ * raythread.cpp:591,608).  ct_gpu_last_error() gives a message for the calling thread.
+ * The library copies at upload and never keeps a host pointer past the call that received
+ * it.  There is no CPU fallback: without a CUDA device every compute call fails with
+ * CT_ERR_NO_DEVICE.
+ *
+ * Struct layouts deliberately equal the reference's in-memory layouts on x86-64
+ * (sizeof checked in SURVEY 8: bvh_node_t 64, light_t 56, material_t 12), so a binding
+ * can pass the reference's own arrays without repacking; see INTEGRATION.md.
+ *
+ * Threading: one host thread per device at a time.  Work is asynchronous on one CUDA
+ * stream per device; ct_gpu_readback(_hits), ct_gpu_get_counters and ct_gpu_sync are the
+ * synchronisation points that replace the reference's WS_FINISHED polling
+ * (raythread.cpp:657-661).
+ */
+#ifndef CT_GPU_H
+#define CT_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CT_GPU_ABI_VERSION 1
+
+typedef enum ct_status {
+    CT_OK = 0,
+    CT_ERR_INVALID = -1,      /* bad argument / descriptor */
+    CT_ERR_NO_DEVICE = -2,    /* no CUDA device, or device index out of range */
+    CT_ERR_CUDA = -3,         /* a CUDA runtime call failed (see ct_gpu_last_error) */
+    CT_ERR_NO_SCENE = -4,     /* render/readback before a successful upload */
+    CT_ERR_LIMIT = -5,        /* scene exceeds a device-side limit (BVH depth, counts) */
+    CT_ERR_OOM = -6           /* device allocation failed */
+} ct_status;
+
+/* == bvh_node_t, reference bvh.h:5-11 (two v3_t of double, three uint32, 4 bytes tail padding) */
+typedef struct ct_bvh_node {
+    double aabb_min[3];
+    double aabb_max[3];
+    uint32_t left_node;             /* children are left_node and left_node+1 (bvh.cpp:89-97) */
+    uint32_t first_triangle_index;  /* into tri_indexes */
+    uint32_t triangle_count;        /* 0 = interior (bvh.cpp:99) */
+    uint32_t _pad;
+} ct_bvh_node;
+
+/* == material_t, reference scenefile.h:25-29 */
+typedef struct ct_material {
+    uint32_t color;      /* 0x00BBGGRR, color.h:77-80 */
+    int32_t specular;    /* -1 disables the specular term (raythread.cpp:316) */
+    float reflection;    /* <= 0 stops recursion (raythread.cpp:369) */
+} ct_material;
+
+/* == light_t, reference scenefile.h:61-66; type values == lightType_t scenefile.h:13 */
+enum { CT_LIGHT_POINT = 0, CT_LIGHT_DIRECTIONAL = 1, CT_LIGHT_AMBIENT = 2 };
+typedef struct ct_light {
+    int32_t type;
+    float intensity;
+    double position[3];
+    double direction[3];
+} ct_light;
+
+enum {
+    CT_FLAG_WIDE = 1u,        /* trace x in [-W/2, W/2) instead of the reference's centred HxH square
+                                 (raythread.cpp:454-455 "Keep it square"); SURVEY f2 */
+    CT_FLAG_KEEP_HITS = 2u,   /* keep the primary-ray hit records for ct_gpu_readback_hits */
+    CT_FLAG_COUNT_TESTS = 4u  /* count box / triangle tests (slower; for roofline accounting) */
+};
+
+/* What RayThread hands its workers (display_partition_t raythread.cpp:69-78 + bvh_state_t bvh.h:19-25). */
+typedef struct ct_scene_desc {
+    uint32_t struct_size;           /* = sizeof(ct_scene_desc) */
+    uint32_t flags;                 /* CT_FLAG_* */
+
+    uint32_t n_triangles;           /* bvh_state_t.triangles.size */
+    uint32_t triangle_stride;       /* bytes between triangles: 96 for the reference's triangle_t
+                                       (scenefile.h:36-41, 4 x v3_t), 72 for packed p1,p2,p3 */
+    const void *triangles;          /* each: 9 doubles p1,p2,p3 at offset 0 (GetSceneTriangles order, raythread.cpp:621) */
+    const ct_material *materials;   /* per triangle k: objects[triangleLookup.indexes[k]].material (raythread.cpp:211) */
+
+    uint32_t n_nodes;               /* bvh_state_t.nodesUsed */
+    uint32_t n_lights;              /* lightStack.index */
+    const ct_bvh_node *nodes;       /* bvh_state_t.bvhNodes, root = node 0 */
+    const uint32_t *tri_indexes;    /* bvh_state_t.triangles.indexes (permutation, n_triangles) */
+    const ct_light *lights;         /* lightStack.lights, file order (order is part of the result: fp32 accumulation) */
+
+    double camera_position[3];      /* camera_t scenefile.h:68-71 */
+    double camera_rotation[9];      /* rotation.data[i][j] row-major (raythread.cpp:564-572) */
+    float viewport[3];              /* width,height,d -- the reference always passes {1,1,1} (raythread.cpp:554) */
+
+    int32_t width, height;          /* bitmapSettings_t environment.h:7-12 */
+    int32_t max_depth;              /* recursion depth; the reference's literal is 10 (raythread.cpp:508) */
+    uint32_t background;            /* 0x333333 (raythread.cpp:59) */
+} ct_scene_desc;
+
+/* Rays are counted by kind: primary = pixels traced, shadow = one per non-ambient light
+ * per shaded point (raythread.cpp:304), reflection = recursive TraceRay calls (raythread.cpp:373). */
+typedef struct ct_ray_counters {
+    uint64_t rays_primary, rays_shadow, rays_reflection;
+    uint64_t box_tests, tri_tests;  /* only with CT_FLAG_COUNT_TESTS, else 0 */
+} ct_ray_counters;
+
+int ct_gpu_abi_version(void);
+int ct_gpu_device_count(void);                 /* >= 0, or negative ct_status */
+const char *ct_gpu_last_error(void);
+
+/* Replaces RayThread's first-call initialisation hand-off (raythread.cpp:647-654): copies the scene and
+ * the BVH built by the reference's BuildBVH (bvh.cpp:108) to `device` as SoA arrays and allocates the
+ * device framebuffer (zero-filled, like cobbletrace.cpp:57).  Re-uploading replaces the previous scene. */
+int ct_gpu_upload_scene(int device, const ct_scene_desc *desc);
+
+/* Replaces the camera half of HandleUpdates (raythread.cpp:557-572) for an already uploaded scene. */
+int ct_gpu_set_camera(int device, const double position[3], const double rotation[9]);
+
+/* Optional: launch on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead of
+ * the library's own; pass NULL to go back. */
+int ct_gpu_set_stream(int device, void *cuda_stream);
+
+/* Replaces one worker's RayTracePartition pass (raythread.cpp:437-543) over canvas rows
+ * y in [y_start, y_end) -- the same half-open range as display_partition_t.yStart/yEnd
+ * (raythread.cpp:580-581) -- for all x.  Asynchronous.  If `counters` is non-NULL the call
+ * synchronises and returns this tile's ray counts. */
+int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *counters);
+
+/* Blocks until all submitted tiles are done, then copies framebuffer rows [row_start,row_end) into
+ * dst (bitmap->memory, row stride in pixels).  Only pixels the tracer covers are written: the centred
+ * square's columns (all columns with CT_FLAG_WIDE), and never a row the reference never writes
+ * (row 0) -- everything else in dst is left untouched, as the reference leaves it. */
+int ct_gpu_readback(int device, uint32_t *dst, int dst_stride_pixels, int row_start, int row_end);
+
+/* Debug/parity export (needs CT_FLAG_KEEP_HITS): primary-ray hit records in framebuffer layout.
+ * found: 1/0, or 0xFFFFFFFF where no ray was traced.  Any pointer may be NULL. */
+int ct_gpu_readback_hits(int device, uint32_t *found, uint32_t *index, float *t, int stride_pixels,
+                         int row_start, int row_end);
+
+/* Accumulated counters since upload / last reset (synchronises). */
+int ct_gpu_get_counters(int device, ct_ray_counters *out, int reset);
+
+/* Device time in ms spent in the kernels of the most recent ct_gpu_render_tile (CUDA events on the
+ * launching stream; synchronises). */
+int ct_gpu_last_tile_ms(int device, float *ms);
+
+int ct_gpu_sync(int device);
+
+/* Device framebuffer access for multi-GPU gathers done by the host framework (NCCL / peer copies):
+ * pointer to row-major uint32 pixels, stride = width. Valid until the next upload/shutdown. */
+int ct_gpu_framebuffer(int device, void **device_ptr, int *width, int *height);
+
+/* In-process multi-GPU gather (north_star "cudaMemcpyPeer" path): copy framebuffer rows
+ * [row_start,row_end) of src_device into dst_device's framebuffer over NVLink.  Both devices must hold
+ * an uploaded scene of the same frame size.  Asynchronous on src_device's stream. */
+int ct_gpu_gather_rows(int src_device, int dst_device, int row_start, int row_end);
+
+/* Known-answer-test entry: ClosestIntersection (raythread.cpp:197-227) for n arbitrary rays through the
+ * uploaded scene.  origins/directions: n x 3 doubles; t0: initial ray_t.t per ray (1e30f primary/shadow,
+ * 0 for the reference's reflection rays, raythread.cpp:373).  Outputs may be NULL. */
+int ct_gpu_debug_closest(int device, uint32_t n, const double *origins, const double *directions, const float *t0,
+                         uint32_t *found, uint32_t *index, float *tclosest);
+
+/* Known-answer-test entry for the two primitives (bvh.cpp:147 IntersectTriangle, :165 IntersectAABB):
+ * n independent (ray, triangle, box) cases.  tri: n x 9, bmin/bmax: n x 3.  ray_t is in/out. */
+int ct_gpu_debug_primitives(int device, uint32_t n, const double *origins, const double *directions, float *ray_t,
+                            const double *tri, const double *bmin, const double *bmax,
+                            uint32_t *tri_hit, uint32_t *box_hit);
+
+/* Frees everything held for `device` (the reference never frees; this makes the library re-entrant). */
+int ct_gpu_shutdown(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CT_GPU_H */
