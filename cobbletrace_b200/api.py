@@ -24,7 +24,7 @@ REFERENCE_MAX_DEPTH = 10   # raythread.cpp:508
 ABI_SYMBOLS = [
     "ct_gpu_abi_version", "ct_gpu_device_count", "ct_gpu_last_error", "ct_gpu_upload_scene", "ct_gpu_set_camera",
     "ct_gpu_set_stream", "ct_gpu_render_tile", "ct_gpu_readback", "ct_gpu_readback_hits", "ct_gpu_get_counters",
-    "ct_gpu_last_tile_ms", "ct_gpu_sync", "ct_gpu_framebuffer", "ct_gpu_gather_rows", "ct_gpu_debug_closest",
+    "ct_gpu_last_tile_ms", "ct_gpu_sync", "ct_gpu_throttle", "ct_gpu_framebuffer", "ct_gpu_gather_rows", "ct_gpu_debug_closest",
     "ct_gpu_debug_primitives", "ct_gpu_shutdown",
 ]
 
@@ -96,6 +96,7 @@ def load_library(path: Optional[str] = None):
     L.ct_gpu_get_counters.argtypes = [C.c_int, C.POINTER(RayCounters), C.c_int]
     L.ct_gpu_last_tile_ms.argtypes = [C.c_int, C.POINTER(C.c_float)]
     L.ct_gpu_sync.argtypes = [C.c_int]
+    L.ct_gpu_throttle.argtypes = [C.c_int, C.c_int]
     L.ct_gpu_framebuffer.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ct_gpu_gather_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.ct_gpu_debug_closest.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp]
@@ -171,7 +172,9 @@ class GpuRenderer:
     # -- ct_gpu_render_tile ---------------------------------------------------------------------------
     def full_range(self):
         half = self.height // 2
-        return -half, half       # HandleUpdates raythread.cpp:574-581 with one partition
+        # HandleUpdates raythread.cpp:574-581 with a thread count that divides H: yStart = -(H/2),
+        # yEnd = yStart + N * (H/N) = yStart + H  (H/2 for even H; odd H also reaches row 0)
+        return -half, -half + self.height
 
     def render_tile(self, y_start: Optional[int] = None, y_end: Optional[int] = None, counters: bool = False):
         if y_start is None:

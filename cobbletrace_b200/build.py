@@ -64,7 +64,10 @@ def build_host(force: bool = False) -> str:
     deps = srcs + _glob(hdir, (".h", ".hpp")) + [os.path.join(ROOT, "include", "ct_gpu.h"), os.path.join(ROOT, "include", "ct_host.h")]
     if not force and _newer(HOST_LIB, deps):
         return HOST_LIB
-    cmd = [os.environ.get("CXX", "g++")] + GXX_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", HOST_LIB] + srcs + ["-ldl"]
+    # Deliberately the PATH g++ and not $CXX: this image exports CXX=/opt/gcc/bin/g++, whose libstdc++.so link
+    # dangles, so it silently links libstdc++.a into the .so -- a second C++ runtime next to the one torch
+    # loads, and exceptions thrown inside the library then crash the process.
+    cmd = [shutil.which("g++") or "g++"] + GXX_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", HOST_LIB] + srcs + ["-ldl"]
     subprocess.check_call(cmd, cwd=ROOT)
     return HOST_LIB
 

@@ -431,6 +431,9 @@ struct DeviceState {
     int n_sm = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t tile_done[8] = {};   // ring: completion of the last 8 submitted tiles (ct_gpu_throttle)
+    unsigned long long tiles_submitted = 0;
+    int row_lo = 0, row_hi = 0;      // hull of framebuffer rows rendered since upload (readback clips to it)
     bool timed = false;
     std::vector<void *> allocs;
     ct_ray_counters snapshot{};      // totals at the end of the previous counted tile
@@ -456,6 +459,7 @@ void free_device(DeviceState &s) {
     s.allocs.clear();
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
+    for (cudaEvent_t e : s.tile_done) if (e) cudaEventDestroy(e);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
     s = DeviceState{};
 }
@@ -547,6 +551,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     s.stream = s.own_stream;
     CU(cudaEventCreate(&s.ev0));
     CU(cudaEventCreate(&s.ev1));
+    for (cudaEvent_t &e : s.tile_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     s.flags = d->flags;
 
     Params &p = s.p;
@@ -680,8 +685,15 @@ int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *coun
     }
     if (depth_max > 0) k_resolve<<<s.n_sm * 4, 256, 0, st>>>(pk);
     CU(cudaEventRecord(s.ev1, st));
+    CU(cudaEventRecord(s.tile_done[s.tiles_submitted % 8], st));
+    s.tiles_submitted++;
     CU(cudaGetLastError());
     s.timed = true;
+    {   // framebuffer rows this tile writes: row = H/2 - y
+        int lo = half - (y1 - 1), hi = half - y0 + 1;
+        if (s.row_hi <= s.row_lo) { s.row_lo = lo; s.row_hi = hi; }
+        else { s.row_lo = std::min(s.row_lo, lo); s.row_hi = std::max(s.row_hi, hi); }
+    }
     if (counters) {
         ct_ray_counters now;
         TRY(read_totals(s, &now));
@@ -700,6 +712,16 @@ int ct_gpu_sync(int device) {
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     CU(cudaStreamSynchronize(s.stream));
+    return CT_OK;
+}
+
+int ct_gpu_throttle(int device, int max_in_flight) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    if (max_in_flight <= 0) { CU(cudaStreamSynchronize(s.stream)); return CT_OK; }
+    unsigned long long keep = (unsigned long long)std::min(max_in_flight, 7);
+    if (s.tiles_submitted > keep) CU(cudaEventSynchronize(s.tile_done[(s.tiles_submitted - keep - 1) % 8]));
     return CT_OK;
 }
 
@@ -732,8 +754,9 @@ int ct_gpu_readback(int device, uint32_t *dst, int dst_stride_pixels, int row_st
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     const Params &p = s.p;
-    // Row 0 corresponds to y = H/2, which the reference's loops never reach (y < yEnd <= H/2): never written.
-    int r0 = std::max(row_start, 1), r1 = std::min(row_end, p.H);
+    // Only rows some tile has rendered are copied: e.g. row 0 (y = H/2) is never reached by the reference's
+    // loops (y < yEnd <= H/2) and so stays untouched in dst here as well.
+    int r0 = std::max(row_start, s.row_lo), r1 = std::min(row_end, s.row_hi);
     int cols = s.col_hi - s.col_lo;
     if (dst_stride_pixels < p.W) return fail(CT_ERR_INVALID, "dst stride %d < width %d", dst_stride_pixels, p.W);
     CU(cudaStreamSynchronize(s.stream));

@@ -1,0 +1,240 @@
+// ct_boss.cpp -- the boss half of RayThread (raythread.cpp:641-666 + HandleUpdates :546-594), with the
+// SDL worker threads replaced by ct_gpu_render_tile calls.
+//
+// Differences from the reference, all deliberate:
+//   * the static split `yStep = H / numberOfThreads` (:576, loses H % N rows) becomes dynamic tile
+//     stealing: row tiles are handed out by an atomic counter -- process-local for the GPUs this process
+//     drives (one host thread per GPU), or a POSIX shared-memory counter when one process per GPU is
+//     used (torchrun): load balance follows the image content, no row is ever dropped;
+//   * completion is a stream synchronisation, not polling of `status` flags (:657-661);
+//   * finished tiles of GPUs other than devices[0] are copied to devices[0] over NVLink
+//     (ct_gpu_gather_rows -> cudaMemcpyPeerAsync) before the single readback.
+// libct_gpu.so is loaded with dlopen so this library also loads on machines without CUDA; rendering
+// then fails loudly (there is no CPU path).
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "ct_scene.hpp"
+
+namespace cth {
+
+struct GpuApi {
+    void *handle = nullptr;
+    int (*abi_version)() = nullptr;
+    const char *(*last_error)() = nullptr;
+    int (*upload_scene)(int, const ct_scene_desc *) = nullptr;
+    int (*set_camera)(int, const double *, const double *) = nullptr;
+    int (*render_tile)(int, int, int, ct_ray_counters *) = nullptr;
+    int (*throttle)(int, int) = nullptr;
+    int (*readback)(int, uint32_t *, int, int, int) = nullptr;
+    int (*get_counters)(int, ct_ray_counters *, int) = nullptr;
+    int (*sync)(int) = nullptr;
+    int (*gather_rows)(int, int, int, int) = nullptr;
+    int (*shutdown)(int) = nullptr;
+
+    void load(const std::string &path) {
+        handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!handle) throw std::runtime_error(std::string("cannot load the CUDA renderer (no CPU fallback): ") + dlerror());
+        auto sym = [&](const char *name) {
+            void *p = dlsym(handle, name);
+            if (!p) throw std::runtime_error(std::string("libct_gpu.so lacks symbol ") + name);
+            return p;
+        };
+        abi_version = (int (*)())sym("ct_gpu_abi_version");
+        last_error = (const char *(*)())sym("ct_gpu_last_error");
+        upload_scene = (int (*)(int, const ct_scene_desc *))sym("ct_gpu_upload_scene");
+        set_camera = (int (*)(int, const double *, const double *))sym("ct_gpu_set_camera");
+        render_tile = (int (*)(int, int, int, ct_ray_counters *))sym("ct_gpu_render_tile");
+        throttle = (int (*)(int, int))sym("ct_gpu_throttle");
+        readback = (int (*)(int, uint32_t *, int, int, int))sym("ct_gpu_readback");
+        get_counters = (int (*)(int, ct_ray_counters *, int))sym("ct_gpu_get_counters");
+        sync = (int (*)(int))sym("ct_gpu_sync");
+        gather_rows = (int (*)(int, int, int, int))sym("ct_gpu_gather_rows");
+        shutdown = (int (*)(int))sym("ct_gpu_shutdown");
+        if (abi_version() != CT_GPU_ABI_VERSION) throw std::runtime_error("libct_gpu.so ABI version mismatch");
+    }
+    void check(int rc, const char *what) const {
+        if (rc < 0) throw std::runtime_error(std::string(what) + ": " + last_error());
+    }
+};
+
+struct TileCounter {               // hands out tile numbers 0,1,2,... to whoever asks first
+    std::atomic<int32_t> local{0};
+    int32_t *shared = nullptr;     // mmap'd, shared by all processes of the job
+    std::string shm_name;
+    int fd = -1;
+
+    void open_shared(const std::string &name) {
+        shm_name = name[0] == '/' ? name : "/" + name;
+        fd = shm_open(shm_name.c_str(), O_CREAT | O_RDWR, 0600);
+        if (fd < 0) throw std::runtime_error("shm_open(" + shm_name + ") failed");
+        if (ftruncate(fd, 64) != 0) throw std::runtime_error("ftruncate on shared tile counter failed");
+        void *p = mmap(nullptr, 64, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (p == MAP_FAILED) throw std::runtime_error("mmap of shared tile counter failed");
+        shared = static_cast<int32_t *>(p);
+    }
+    int32_t next() { return shared ? __atomic_fetch_add(shared, 1, __ATOMIC_RELAXED) : local.fetch_add(1, std::memory_order_relaxed); }
+    void reset() { if (shared) __atomic_store_n(shared, 0, __ATOMIC_SEQ_CST); else local.store(0); }
+    ~TileCounter() {
+        if (shared) munmap(shared, 64);
+        if (fd >= 0) close(fd);
+    }
+};
+
+struct Boss {
+    Scene *scene = nullptr;
+    ct_host_boss_config cfg{};
+    GpuApi gpu;
+    TileCounter counter;
+    int tile_rows = 0, n_tiles = 0, y_lo = 0, y_hi = 0;
+    std::vector<std::vector<std::pair<int, int>>> tiles_by_dev;   // last frame
+    std::string error;
+};
+
+static std::string default_gpu_library() {
+    Dl_info info;
+    if (dladdr((void *)&default_gpu_library, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t k = p.find_last_of('/');
+        return (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/libct_gpu.so";
+    }
+    return "libct_gpu.so";
+}
+
+Boss *boss_create(Scene *scene, const ct_host_boss_config *cfg) {
+    if (!scene || !cfg || cfg->struct_size != sizeof(ct_host_boss_config)) throw std::runtime_error("bad boss config (struct_size)");
+    if (cfg->n_devices < 1 || cfg->n_devices > 16) throw std::runtime_error("n_devices must be 1..16");
+    if (cfg->width <= 0 || cfg->height <= 0) throw std::runtime_error("bad bitmap size");
+    auto *b = new Boss();
+    try {
+        b->scene = scene;
+        b->cfg = *cfg;
+        b->gpu.load(cfg->gpu_library && cfg->gpu_library[0] ? cfg->gpu_library : default_gpu_library());
+        if (scene->nodes.empty()) build_bvh(*scene);                               // raythread.cpp:650-651
+        ct_scene_desc d;
+        if (ct_host_fill_desc(reinterpret_cast<ct_host_scene *>(scene), cfg->width, cfg->height, cfg->max_depth, cfg->flags, &d) != 0)
+            throw std::runtime_error(ct_host_last_error());
+        for (int i = 0; i < cfg->n_devices; i++) b->gpu.check(b->gpu.upload_scene(cfg->devices[i], &d), "ct_gpu_upload_scene");
+        const bool shared = cfg->shared_counter_name && cfg->shared_counter_name[0];
+        if (shared) b->counter.open_shared(cfg->shared_counter_name);
+        // canvas rows the reference's loops cover when the thread count divides H (raythread.cpp:574-581):
+        // y in [-(H/2), -(H/2) + H)
+        const int half = cfg->height / 2;
+        b->y_lo = -half; b->y_hi = -half + cfg->height;
+        const int total_devices = shared ? std::max(1, cfg->world_size) * cfg->n_devices : cfg->n_devices;
+        int rows = cfg->tile_rows;
+        if (rows <= 0) {
+            if (total_devices == 1) rows = b->y_hi - b->y_lo;                        // one tile: whole frame in flight
+            else rows = std::max(8, ((b->y_hi - b->y_lo) / (total_devices * 8) + 3) / 4 * 4);
+        }
+        b->tile_rows = rows;
+        b->n_tiles = (b->y_hi - b->y_lo + rows - 1) / rows;
+        b->tiles_by_dev.resize(cfg->n_devices);
+    } catch (...) {
+        delete b;
+        throw;
+    }
+    return b;
+}
+
+void boss_set_camera(Boss *b, const double pos[3], float yaw, float pitch, float roll) {
+    double rot[9];
+    camera_rotation(yaw, pitch, roll, rot);
+    b->scene->cam_pos = {pos[0], pos[1], pos[2]};
+    memcpy(b->scene->cam_rot, rot, sizeof rot);
+    for (int i = 0; i < b->cfg.n_devices; i++) b->gpu.check(b->gpu.set_camera(b->cfg.devices[i], pos, rot), "ct_gpu_set_camera");
+}
+
+void boss_reset_counter(Boss *b) { b->counter.reset(); }
+
+void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int nd = b->cfg.n_devices;
+    const bool shared = b->counter.shared != nullptr;
+    if (!shared) b->counter.reset();
+    for (auto &v : b->tiles_by_dev) v.clear();
+    std::vector<std::string> errs(nd);
+    auto worker = [&](int k) {
+        try {
+            const int dev = b->cfg.devices[k];
+            while (true) {
+                int t = b->counter.next();
+                if (t >= b->n_tiles) break;
+                int y0 = b->y_lo + t * b->tile_rows, y1 = std::min(b->y_hi, y0 + b->tile_rows);
+                b->gpu.check(b->gpu.render_tile(dev, y0, y1, nullptr), "ct_gpu_render_tile");
+                b->tiles_by_dev[k].push_back({y0, y1});
+                // keep at most two tiles in flight per GPU so that stealing follows real progress
+                b->gpu.check(b->gpu.throttle(dev, 1), "ct_gpu_throttle");
+            }
+            // finished tiles -> devices[0] over NVLink
+            if (k != 0) {
+                const int H = b->cfg.height, half = H / 2;
+                for (auto [y0, y1] : b->tiles_by_dev[k])
+                    b->gpu.check(b->gpu.gather_rows(dev, b->cfg.devices[0], half - (y1 - 1), half - y0 + 1), "ct_gpu_gather_rows");
+            }
+            b->gpu.check(b->gpu.sync(dev), "ct_gpu_sync");
+        } catch (const std::exception &e) {
+            errs[k] = e.what();
+        }
+    };
+    if (nd == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nd; k++) th.emplace_back(worker, k);
+        for (auto &t : th) t.join();
+    }
+    for (auto &e : errs) if (!e.empty()) throw std::runtime_error(e);
+    if (bitmap) {
+        const int H = b->cfg.height, half = H / 2;
+        if (!shared) {
+            b->gpu.check(b->gpu.readback(b->cfg.devices[0], bitmap, stride, 0, H), "ct_gpu_readback");
+        } else {
+            for (int k = 0; k < nd; k++)
+                for (auto [y0, y1] : b->tiles_by_dev[k])
+                    b->gpu.check(b->gpu.readback(b->cfg.devices[0], bitmap, stride, half - (y1 - 1), half - y0 + 1), "ct_gpu_readback");
+        }
+    }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int k = 0; k < nd; k++) {
+            ct_ray_counters c;
+            b->gpu.check(b->gpu.get_counters(b->cfg.devices[k], &c, 1), "ct_gpu_get_counters");
+            stats->rays.rays_primary += c.rays_primary; stats->rays.rays_shadow += c.rays_shadow;
+            stats->rays.rays_reflection += c.rays_reflection; stats->rays.box_tests += c.box_tests; stats->rays.tri_tests += c.tri_tests;
+            stats->tiles_mine += (int)b->tiles_by_dev[k].size();
+        }
+        stats->tiles_total = b->n_tiles;
+        stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+}
+
+int boss_tiles(const Boss *b, int32_t *out, int max_tiles) {
+    int n = 0;
+    for (auto &v : b->tiles_by_dev)
+        for (auto [y0, y1] : v) {
+            if (n < max_tiles && out) { out[2 * n] = y0; out[2 * n + 1] = y1; }
+            n++;
+        }
+    return n;
+}
+
+void boss_destroy(Boss *b) {
+    if (!b) return;
+    if (b->gpu.shutdown) for (int i = 0; i < b->cfg.n_devices; i++) b->gpu.shutdown(b->cfg.devices[i]);
+    delete b;
+}
+
+}  // namespace cth

@@ -1,0 +1,158 @@
+// ct_host_api.cpp -- extern "C" surface of include/ct_host.h.
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "ct_scene.hpp"
+
+namespace cth {
+struct Boss;
+Boss *boss_create(Scene *scene, const ct_host_boss_config *cfg);
+void boss_set_camera(Boss *b, const double pos[3], float yaw, float pitch, float roll);
+void boss_reset_counter(Boss *b);
+void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *stats);
+int boss_tiles(const Boss *b, int32_t *out, int max_tiles);
+void boss_destroy(Boss *b);
+}  // namespace cth
+
+namespace {
+thread_local std::string g_err;
+cth::Scene *S(ct_host_scene *s) { return reinterpret_cast<cth::Scene *>(s); }
+const cth::Scene *S(const ct_host_scene *s) { return reinterpret_cast<const cth::Scene *>(s); }
+}  // namespace
+
+extern "C" {
+
+const char *ct_host_last_error(void) { return g_err.c_str(); }
+
+ct_host_scene *ct_host_scene_load(const char *scene_file, const char *base_dir) {
+    if (!scene_file) { g_err = "scene_file is NULL"; return nullptr; }
+    auto *s = new cth::Scene();
+    try {
+        cth::parse_scene_file(scene_file, base_dir ? base_dir : "", *s);
+        if (s->tris.empty()) throw std::runtime_error(std::string(scene_file) + ": scene has no triangles (spheres are ignored by the ray tracer)");
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        delete s;
+        return nullptr;
+    }
+    return reinterpret_cast<ct_host_scene *>(s);
+}
+
+ct_host_scene *ct_host_scene_from_arrays(uint32_t n_tri, const double *tri, const ct_material *materials, uint32_t n_lights,
+                                         const ct_light *lights, const double cam_pos[3], const double cam_rot[9]) {
+    if (!n_tri || !tri || !materials || (n_lights && !lights)) { g_err = "bad arrays"; return nullptr; }
+    auto *s = new cth::Scene();
+    s->tris.resize(n_tri);
+    memcpy(static_cast<void *>(s->tris.data()), tri, (size_t)n_tri * sizeof(cth::Triangle));
+    s->mats.assign(materials, materials + n_tri);
+    s->lights.assign(lights, lights + n_lights);
+    if (cam_pos) s->cam_pos = {cam_pos[0], cam_pos[1], cam_pos[2]};
+    if (cam_rot) memcpy(s->cam_rot, cam_rot, sizeof s->cam_rot);
+    return reinterpret_cast<ct_host_scene *>(s);
+}
+
+void ct_host_scene_free(ct_host_scene *s) { delete S(s); }
+
+uint32_t ct_host_scene_triangle_count(const ct_host_scene *s) { return (uint32_t)S(s)->tris.size(); }
+uint32_t ct_host_scene_sphere_count(const ct_host_scene *s) { return S(s)->n_spheres; }
+const double *ct_host_scene_triangles(const ct_host_scene *s) { return &S(s)->tris.data()->p1.x; }
+const ct_material *ct_host_scene_materials(const ct_host_scene *s) { return S(s)->mats.data(); }
+uint32_t ct_host_scene_light_count(const ct_host_scene *s) { return (uint32_t)S(s)->lights.size(); }
+const ct_light *ct_host_scene_lights(const ct_host_scene *s) { return S(s)->lights.data(); }
+
+void ct_host_scene_camera(const ct_host_scene *s, double pos[3], double rot[9]) {
+    if (pos) { pos[0] = S(s)->cam_pos.x; pos[1] = S(s)->cam_pos.y; pos[2] = S(s)->cam_pos.z; }
+    if (rot) memcpy(rot, S(s)->cam_rot, sizeof S(s)->cam_rot);
+}
+
+void ct_host_scene_set_camera(ct_host_scene *s, const double pos[3], const double rot[9]) {
+    if (pos) S(s)->cam_pos = {pos[0], pos[1], pos[2]};
+    if (rot) memcpy(S(s)->cam_rot, rot, sizeof S(s)->cam_rot);
+}
+
+void ct_host_scene_settings(const ct_host_scene *s, ct_host_settings *out) { if (out) *out = S(s)->settings; }
+
+void ct_host_scene_set_reflection(ct_host_scene *s, float reflection) {
+    for (auto &m : S(s)->mats) m.reflection = reflection;
+}
+
+int ct_host_build_bvh(ct_host_scene *s) {
+    try {
+        if (S(s)->nodes.empty()) cth::build_bvh(*S(s));
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return CT_ERR_INVALID;
+    }
+    return (int)S(s)->nodes.size();
+}
+
+const ct_bvh_node *ct_host_scene_nodes(const ct_host_scene *s, uint32_t *n_nodes) {
+    if (n_nodes) *n_nodes = (uint32_t)S(s)->nodes.size();
+    return S(s)->nodes.data();
+}
+
+const uint32_t *ct_host_scene_tri_indexes(const ct_host_scene *s) { return S(s)->tri_index.data(); }
+
+int ct_host_scene_set_bvh(ct_host_scene *s, uint32_t n_nodes, const ct_bvh_node *nodes, const uint32_t *tri_indexes) {
+    if (!n_nodes || !nodes || !tri_indexes) { g_err = "bad BVH arrays"; return CT_ERR_INVALID; }
+    S(s)->nodes.assign(nodes, nodes + n_nodes);
+    S(s)->tri_index.assign(tri_indexes, tri_indexes + S(s)->tris.size());
+    return CT_OK;
+}
+
+void ct_host_camera_rotation(float yaw, float pitch, float roll, double out[9]) { cth::camera_rotation(yaw, pitch, roll, out); }
+
+int ct_host_fill_desc(const ct_host_scene *s, int width, int height, int max_depth, uint32_t flags, ct_scene_desc *d) {
+    const cth::Scene *sc = S(s);
+    if (!d) { g_err = "NULL desc"; return CT_ERR_INVALID; }
+    if (sc->nodes.empty()) { g_err = "scene has no BVH yet: call ct_host_build_bvh first"; return CT_ERR_INVALID; }
+    memset(d, 0, sizeof *d);
+    d->struct_size = sizeof *d;
+    d->flags = flags;
+    d->n_triangles = (uint32_t)sc->tris.size();
+    d->triangle_stride = sizeof(cth::Triangle);
+    d->triangles = sc->tris.data();
+    d->materials = sc->mats.data();
+    d->n_nodes = (uint32_t)sc->nodes.size();
+    d->n_lights = (uint32_t)sc->lights.size();
+    d->nodes = sc->nodes.data();
+    d->tri_indexes = sc->tri_index.data();
+    d->lights = sc->lights.data();
+    d->camera_position[0] = sc->cam_pos.x; d->camera_position[1] = sc->cam_pos.y; d->camera_position[2] = sc->cam_pos.z;
+    memcpy(d->camera_rotation, sc->cam_rot, sizeof d->camera_rotation);
+    d->viewport[0] = d->viewport[1] = d->viewport[2] = 1.0f;       // raythread.cpp:554
+    d->width = width; d->height = height; d->max_depth = max_depth;
+    d->background = 0x333333u;                                     // raythread.cpp:59
+    return CT_OK;
+}
+
+ct_host_boss *ct_host_boss_create(ct_host_scene *s, const ct_host_boss_config *cfg) {
+    try {
+        return reinterpret_cast<ct_host_boss *>(cth::boss_create(S(s), cfg));
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+#define GUARD(stmt) try { stmt; } catch (const std::exception &e) { g_err = e.what(); return CT_ERR_CUDA; } return CT_OK
+
+int ct_host_boss_set_camera(ct_host_boss *b, const double pos[3], float yaw, float pitch, float roll) {
+    GUARD(cth::boss_set_camera(reinterpret_cast<cth::Boss *>(b), pos, yaw, pitch, roll));
+}
+
+int ct_host_boss_reset_shared_counter(ct_host_boss *b) { GUARD(cth::boss_reset_counter(reinterpret_cast<cth::Boss *>(b))); }
+
+int ct_host_boss_render(ct_host_boss *b, uint32_t *bitmap, int stride_pixels, ct_host_frame_stats *stats) {
+    GUARD(cth::boss_render(reinterpret_cast<cth::Boss *>(b), bitmap, stride_pixels, stats));
+}
+
+int ct_host_boss_tiles(const ct_host_boss *b, int32_t *y_ranges, int max_tiles) {
+    return cth::boss_tiles(reinterpret_cast<const cth::Boss *>(b), y_ranges, max_tiles);
+}
+
+void ct_host_boss_destroy(ct_host_boss *b) { cth::boss_destroy(reinterpret_cast<cth::Boss *>(b)); }
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+"""ctypes binding of include/ct_host.h (libct_host.so): scene ingest, BVH build and the boss loop.
+
+Host code is C++ like the reference's; Python only marshals arrays.  The boss renders through
+libct_gpu.so (dlopen'ed by the C++ side) -- no CPU rendering path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import api
+from .sceneio import FlatScene
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB = os.path.join(PKG, "libct_host.so")
+
+ABI_SYMBOLS = [
+    "ct_host_last_error", "ct_host_scene_load", "ct_host_scene_from_arrays", "ct_host_scene_free",
+    "ct_host_scene_triangle_count", "ct_host_scene_sphere_count", "ct_host_scene_triangles", "ct_host_scene_materials",
+    "ct_host_scene_light_count", "ct_host_scene_lights", "ct_host_scene_camera", "ct_host_scene_set_camera",
+    "ct_host_scene_settings", "ct_host_scene_set_reflection", "ct_host_build_bvh", "ct_host_scene_nodes",
+    "ct_host_scene_tri_indexes", "ct_host_scene_set_bvh", "ct_host_camera_rotation", "ct_host_fill_desc",
+    "ct_host_boss_create", "ct_host_boss_set_camera", "ct_host_boss_render", "ct_host_boss_reset_shared_counter",
+    "ct_host_boss_tiles", "ct_host_boss_destroy",
+]
+
+
+class HostSettings(C.Structure):
+    _fields_ = [("number_of_threads", C.c_int32), ("subsampling", C.c_int32), ("wireframe", C.c_int32), ("supersampling", C.c_int32)]
+
+
+class BossConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("width", C.c_int32), ("height", C.c_int32), ("max_depth", C.c_int32),
+                ("flags", C.c_uint32), ("n_devices", C.c_int32), ("devices", C.c_int32 * 16), ("tile_rows", C.c_int32),
+                ("shared_counter_name", C.c_char_p), ("rank", C.c_int32), ("world_size", C.c_int32), ("gpu_library", C.c_char_p)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("rays", api.RayCounters), ("device_ms_max", C.c_float), ("wall_ms", C.c_double),
+                ("tiles_total", C.c_int32), ("tiles_mine", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(HOST_LIB):
+            raise RuntimeError(f"{HOST_LIB} not found: build it with `python -m cobbletrace_b200.build`")
+        L = C.CDLL(HOST_LIB)
+        vp = C.c_void_p
+        L.ct_host_last_error.restype = C.c_char_p
+        L.ct_host_scene_load.restype = vp; L.ct_host_scene_load.argtypes = [C.c_char_p, C.c_char_p]
+        L.ct_host_scene_from_arrays.restype = vp
+        L.ct_host_scene_from_arrays.argtypes = [C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp]
+        L.ct_host_scene_free.argtypes = [vp]
+        for f in ("ct_host_scene_triangle_count", "ct_host_scene_sphere_count", "ct_host_scene_light_count"):
+            getattr(L, f).restype = C.c_uint32; getattr(L, f).argtypes = [vp]
+        for f in ("ct_host_scene_triangles", "ct_host_scene_materials", "ct_host_scene_lights", "ct_host_scene_tri_indexes"):
+            getattr(L, f).restype = vp; getattr(L, f).argtypes = [vp]
+        L.ct_host_scene_camera.argtypes = [vp, vp, vp]
+        L.ct_host_scene_set_camera.argtypes = [vp, vp, vp]
+        L.ct_host_scene_settings.argtypes = [vp, C.POINTER(HostSettings)]
+        L.ct_host_scene_set_reflection.argtypes = [vp, C.c_float]
+        L.ct_host_build_bvh.argtypes = [vp]
+        L.ct_host_scene_nodes.restype = vp; L.ct_host_scene_nodes.argtypes = [vp, C.POINTER(C.c_uint32)]
+        L.ct_host_scene_set_bvh.argtypes = [vp, C.c_uint32, vp, vp]
+        L.ct_host_camera_rotation.argtypes = [C.c_float, C.c_float, C.c_float, vp]
+        L.ct_host_fill_desc.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(api.SceneDesc)]
+        L.ct_host_boss_create.restype = vp; L.ct_host_boss_create.argtypes = [vp, C.POINTER(BossConfig)]
+        L.ct_host_boss_set_camera.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float]
+        L.ct_host_boss_render.argtypes = [vp, vp, C.c_int, C.POINTER(FrameStats)]
+        L.ct_host_boss_reset_shared_counter.argtypes = [vp]
+        L.ct_host_boss_tiles.argtypes = [vp, vp, C.c_int]
+        L.ct_host_boss_destroy.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _err(L) -> str:
+    return L.ct_host_last_error().decode(errors="replace")
+
+
+def _np_from(ptr, dtype, count):
+    if count == 0:
+        return np.zeros(0, dtype)
+    buf = (C.c_char * (np.dtype(dtype).itemsize * count)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+
+def camera_rotation(yaw: float = 0.0, pitch: float = 0.0, roll: float = 0.0) -> np.ndarray:
+    out = np.zeros(9)
+    load_library().ct_host_camera_rotation(yaw, pitch, roll, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+class HostScene:
+    """Owns a ct_host_scene (C++ cth::Scene)."""
+
+    def __init__(self, handle):
+        self.L = load_library()
+        self.h = handle
+
+    @classmethod
+    def load(cls, scene_file: str, base_dir: Optional[str] = None) -> "HostScene":
+        L = load_library()
+        h = L.ct_host_scene_load(os.fsencode(scene_file), os.fsencode(base_dir) if base_dir else None)
+        if not h:
+            raise RuntimeError("ct_host_scene_load: " + _err(L))
+        return cls(h)
+
+    @classmethod
+    def from_flat(cls, fs: FlatScene) -> "HostScene":
+        L = load_library()
+        tri = np.ascontiguousarray(fs.tri, np.float64)
+        mats = np.zeros(fs.n_tri, api.MAT_DT)
+        mats["color"], mats["specular"], mats["reflection"] = fs.mat_color, fs.mat_specular, fs.mat_reflection
+        lights = np.zeros(max(fs.n_lights, 1), api.LIGHT_DT)
+        if fs.n_lights:
+            lights["type"][:fs.n_lights], lights["intensity"][:fs.n_lights] = fs.light_type, fs.light_intensity
+            lights["pos"][:fs.n_lights], lights["dir"][:fs.n_lights] = fs.light_pos, fs.light_dir
+        pos = np.ascontiguousarray(fs.cam_pos, np.float64); rot = np.ascontiguousarray(fs.cam_rot, np.float64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        h = L.ct_host_scene_from_arrays(fs.n_tri, p(tri), p(mats), fs.n_lights, p(lights), p(pos), p(rot))
+        if not h:
+            raise RuntimeError("ct_host_scene_from_arrays: " + _err(L))
+        s = cls(h)
+        if fs.has_bvh():
+            nodes = api.pack_nodes(fs); idx = np.ascontiguousarray(fs.tri_index, np.uint32)
+            if L.ct_host_scene_set_bvh(h, fs.n_nodes, p(nodes), p(idx)) < 0:
+                raise RuntimeError("ct_host_scene_set_bvh: " + _err(L))
+        return s
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ct_host_scene_free(self.h); self.h = None
+        except Exception:
+            pass
+
+    @property
+    def n_tri(self) -> int:
+        return int(self.L.ct_host_scene_triangle_count(self.h))
+
+    @property
+    def n_spheres(self) -> int:
+        return int(self.L.ct_host_scene_sphere_count(self.h))
+
+    def settings(self) -> dict:
+        s = HostSettings(); self.L.ct_host_scene_settings(self.h, C.byref(s))
+        return dict(numberOfThreads=s.number_of_threads, subsampling=bool(s.subsampling), wireframe=bool(s.wireframe),
+                    supersampling=bool(s.supersampling))
+
+    def set_reflection(self, reflection: float):
+        self.L.ct_host_scene_set_reflection(self.h, reflection)
+
+    def set_camera(self, pos=None, rot=None):
+        p = None if pos is None else np.ascontiguousarray(pos, np.float64)
+        r = None if rot is None else np.ascontiguousarray(rot, np.float64)
+        self.L.ct_host_scene_set_camera(self.h, None if p is None else p.ctypes.data_as(C.c_void_p),
+                                        None if r is None else r.ctypes.data_as(C.c_void_p))
+
+    def build_bvh(self) -> int:
+        n = self.L.ct_host_build_bvh(self.h)
+        if n < 0:
+            raise RuntimeError("ct_host_build_bvh: " + _err(self.L))
+        return n
+
+    def to_flat(self, with_bvh: bool = True) -> FlatScene:
+        L, h = self.L, self.h
+        n, nl = self.n_tri, int(L.ct_host_scene_light_count(h))
+        tri = _np_from(L.ct_host_scene_triangles(h), np.float64, n * 9).reshape(n, 9)
+        mats = _np_from(L.ct_host_scene_materials(h), api.MAT_DT, n)
+        lights = _np_from(L.ct_host_scene_lights(h), api.LIGHT_DT, nl) if nl else np.zeros(0, api.LIGHT_DT)
+        pos = np.zeros(3); rot = np.zeros(9)
+        L.ct_host_scene_camera(h, pos.ctypes.data_as(C.c_void_p), rot.ctypes.data_as(C.c_void_p))
+        fs = FlatScene(tri=tri, mat_color=mats["color"].copy(), mat_specular=mats["specular"].copy(),
+                       mat_reflection=mats["reflection"].copy(), light_type=lights["type"].copy(),
+                       light_intensity=lights["intensity"].copy(), light_pos=lights["pos"].copy().reshape(nl, 3),
+                       light_dir=lights["dir"].copy().reshape(nl, 3), cam_pos=pos, cam_rot=rot)
+        if with_bvh:
+            self.build_bvh()
+            nn = C.c_uint32()
+            nodes = _np_from(L.ct_host_scene_nodes(h, C.byref(nn)), api.NODE_DT, 0) if False else None
+            ptr = L.ct_host_scene_nodes(h, C.byref(nn))
+            nodes = _np_from(ptr, api.NODE_DT, int(nn.value))
+            fs.node_min, fs.node_max = nodes["min"].copy(), nodes["max"].copy()
+            fs.node_left, fs.node_first, fs.node_count = nodes["left"].copy(), nodes["first"].copy(), nodes["count"].copy()
+            fs.tri_index = _np_from(L.ct_host_scene_tri_indexes(h), np.uint32, n)
+        return fs
+
+
+class Boss:
+    """RayThread's boss half over one or more GPUs of this process (ct_host_boss_*)."""
+
+    def __init__(self, scene: HostScene, width: int, height: int, devices: Sequence[int] = (0,), max_depth: int = api.REFERENCE_MAX_DEPTH,
+                 flags: int = 0, tile_rows: int = 0, shared_counter: Optional[str] = None, rank: int = 0, world_size: int = 1):
+        self.L = load_library()
+        self.scene = scene
+        self.width, self.height = width, height
+        cfg = BossConfig()
+        cfg.struct_size = C.sizeof(BossConfig)
+        cfg.width, cfg.height, cfg.max_depth, cfg.flags = width, height, max_depth, flags
+        cfg.n_devices = len(devices)
+        for i, d in enumerate(devices):
+            cfg.devices[i] = d
+        cfg.tile_rows = tile_rows
+        self._name = shared_counter.encode() if shared_counter else None
+        cfg.shared_counter_name = self._name
+        cfg.rank, cfg.world_size = rank, world_size
+        self._gpu = os.fsencode(api.GPU_LIB)
+        cfg.gpu_library = self._gpu
+        self.h = self.L.ct_host_boss_create(scene.h, C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("ct_host_boss_create: " + _err(self.L))
+
+    def set_camera(self, pos, yaw=0.0, pitch=0.0, roll=0.0):
+        p = np.ascontiguousarray(pos, np.float64)
+        if self.L.ct_host_boss_set_camera(self.h, p.ctypes.data_as(C.c_void_p), yaw, pitch, roll) < 0:
+            raise RuntimeError("ct_host_boss_set_camera: " + _err(self.L))
+
+    def reset_shared_counter(self):
+        self.L.ct_host_boss_reset_shared_counter(self.h)
+
+    def render(self, bitmap: Optional[np.ndarray] = None, want_bitmap: bool = True):
+        if bitmap is None and want_bitmap:
+            bitmap = np.zeros((self.height, self.width), np.uint32)
+        st = FrameStats()
+        rc = self.L.ct_host_boss_render(self.h, bitmap.ctypes.data_as(C.c_void_p) if bitmap is not None else None,
+                                        bitmap.shape[1] if bitmap is not None else 0, C.byref(st))
+        if rc < 0:
+            raise RuntimeError("ct_host_boss_render: " + _err(self.L))
+        stats = dict(st.rays.as_dict(), wall_ms=float(st.wall_ms), tiles_total=int(st.tiles_total), tiles_mine=int(st.tiles_mine))
+        return bitmap, stats
+
+    def tiles(self):
+        n = self.L.ct_host_boss_tiles(self.h, None, 0)
+        out = np.zeros((max(n, 1), 2), np.int32)
+        self.L.ct_host_boss_tiles(self.h, out.ctypes.data_as(C.c_void_p), n)
+        return [tuple(map(int, r)) for r in out[:n]]
+
+    def close(self):
+        if self.h:
+            self.L.ct_host_boss_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

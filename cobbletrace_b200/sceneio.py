@@ -22,6 +22,7 @@ from __future__ import annotations
 import dataclasses
 import gzip
 import hashlib
+import lzma
 from typing import Optional
 
 import numpy as np
@@ -90,7 +91,11 @@ class FlatScene:
 
 
 def _open(path: str, mode: str):
-    return gzip.open(path, mode) if str(path).endswith(".gz") else open(path, mode)
+    if str(path).endswith(".gz"):
+        return gzip.open(path, mode)
+    if str(path).endswith(".xz"):
+        return lzma.open(path, mode)
+    return open(path, mode)
 
 
 def load_ctscene(path: str) -> FlatScene:

@@ -147,6 +147,10 @@ int ct_gpu_last_tile_ms(int device, float *ms);
 
 int ct_gpu_sync(int device);
 
+/* Blocks until at most `max_in_flight` of the submitted tiles are unfinished (0 == ct_gpu_sync).  Lets a
+ * boss keep a GPU fed while tile stealing still follows real progress. */
+int ct_gpu_throttle(int device, int max_in_flight);
+
 /* Device framebuffer access for multi-GPU gathers done by the host framework (NCCL / peer copies):
  * pointer to row-major uint32 pixels, stride = width. Valid until the next upload/shutdown. */
 int ct_gpu_framebuffer(int device, void **device_ptr, int *width, int *height);

@@ -329,12 +329,13 @@ int ct_oracle_render(const ct_oracle_scene *s, int W, int H, int y_start, int y_
     return 0;
 }
 
-/* ---- raythread.cpp:564-572 camera matrix (double cos/sin of float angles) ----------------------- */
+/* ---- raythread.cpp:564-572 camera matrix.  The angles are float and <math.h> is the C++ wrapper there, so
+ * cos/sin are the float overloads and the arithmetic is fp32 (checked against oracle/_ref --keys). -------- */
 void ct_oracle_camera_rotation(float yaw, float pitch, float roll, double o[9]) {
-    double cy = cos(yaw), sy = sin(yaw), cp = cos(pitch), sp = sin(pitch), cr = cos(roll), sr = sin(roll);
-    o[0] = cy * cp;  o[1] = cy * sp * sr - sy * cr;  o[2] = cy * sp * cr + sy * sr;
-    o[3] = sy * cp;  o[4] = sy * sp * sr + cy * cr;  o[5] = sy * sp * cr - cy * sr;
-    o[6] = -sy;      o[7] = cp * sr;                 o[8] = cp * cr;
+    float cy = cosf(yaw), sy = sinf(yaw), cp = cosf(pitch), sp = sinf(pitch), cr = cosf(roll), sr = sinf(roll);
+    o[0] = (double)(cy * cp);  o[1] = (double)(cy * sp * sr - sy * cr);  o[2] = (double)(cy * sp * cr + sy * sr);
+    o[3] = (double)(sy * cp);  o[4] = (double)(sy * sp * sr + cy * cr);  o[5] = (double)(sy * sp * cr - cy * sr);
+    o[6] = (double)(-sy);      o[7] = (double)(cp * sr);                 o[8] = (double)(cp * cr);
 }
 
 /* ---- single-call KAT entry points ------------------------------------------------------------------- */

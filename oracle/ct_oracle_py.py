@@ -113,9 +113,9 @@ class OracleScene:
         self.c = s
 
     def render(self, W, H, y_start=None, y_end=None, max_depth=10, flags=0, want_hits=True, n_threads=None):
-        half = H // 2
+        half = H // 2      # HandleUpdates raythread.cpp:574-581 with a thread count dividing H: rows [-(H/2), -(H/2)+H)
         y_start = -half if y_start is None else y_start
-        y_end = half if y_end is None else y_end
+        y_end = -half + H if y_end is None else y_end
         frame = np.zeros((H, W), np.uint32)
         hits = None
         if want_hits:

@@ -25,6 +25,8 @@
 //   --dump-scene F write the flattened scene + BVH (format: see tests/ctscene.py)
 //   --time K       time K frames through the boss/worker, print JSON
 //   --counters     print ray / box-test / triangle-test counters (needs -DCT_COUNT build)
+//   --keys STR     feed STR as key presses to the reference's HandleKeyboard (raythread.cpp:388) before
+//                  the first frame: y/p/r rotate by pi/16, wasd/io move the camera by 0.1
 
 #include <stdint.h>
 #include <stdio.h>
@@ -115,11 +117,47 @@ static void DumpScene(const char *path, scene_t *scene, bvh_state_t *bvh) {
 
 struct hit_record_t { uint32_t found; uint32_t index; float t; };
 
+// --kat IN OUT: known-answer vectors straight from the reference's two primitives (bvh.cpp:147,165).
+// IN : u32 n, then org[n][3] dir[n][3] tri[n][9] bmin[n][3] bmax[n][3] (double), t[n] (float)
+// OUT: tri_hit[n] box_hit[n] (u32), t_out[n] (float)
+extern bool IntersectTriangle(ray_t *ray, triangle_t *triangle);
+extern bool IntersectAABB(ray_t *ray, v3_t bmin, v3_t bmax);
+static int RunKat(const char *in, const char *out) {
+    FILE *f = fopen(in, "rb");
+    if (!f) { fprintf(stderr, "cannot open %s\n", in); return 4; }
+    uint32_t n = 0;
+    if (fread(&n, 4, 1, f) != 1) return 4;
+    double *org = (double *)malloc(24ull * n), *dir = (double *)malloc(24ull * n), *tri = (double *)malloc(72ull * n);
+    double *mn = (double *)malloc(24ull * n), *mx = (double *)malloc(24ull * n);
+    float *t = (float *)malloc(4ull * n);
+    if (fread(org, 24, n, f) != n || fread(dir, 24, n, f) != n || fread(tri, 72, n, f) != n || fread(mn, 24, n, f) != n ||
+        fread(mx, 24, n, f) != n || fread(t, 4, n, f) != n) { fprintf(stderr, "short KAT input\n"); return 4; }
+    fclose(f);
+    uint32_t *th = (uint32_t *)malloc(4ull * n), *bh = (uint32_t *)malloc(4ull * n);
+    for (uint32_t i = 0; i < n; i++) {
+        ray_t ray = {{org[3 * i], org[3 * i + 1], org[3 * i + 2]}, {dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]}, t[i]};
+        v3_t bmin = {mn[3 * i], mn[3 * i + 1], mn[3 * i + 2]}, bmax = {mx[3 * i], mx[3 * i + 1], mx[3 * i + 2]};
+        bh[i] = IntersectAABB(&ray, bmin, bmax) ? 1u : 0u;
+        triangle_t tr = {};
+        tr.p1 = {tri[9 * i], tri[9 * i + 1], tri[9 * i + 2]};
+        tr.p2 = {tri[9 * i + 3], tri[9 * i + 4], tri[9 * i + 5]};
+        tr.p3 = {tri[9 * i + 6], tri[9 * i + 7], tri[9 * i + 8]};
+        th[i] = IntersectTriangle(&ray, &tr) ? 1u : 0u;
+        t[i] = ray.t;
+    }
+    f = fopen(out, "wb");
+    if (!f) return 4;
+    fwrite(th, 4, n, f); fwrite(bh, 4, n, f); fwrite(t, 4, n, f);
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char **argv) {
-    const char *sceneFile = NULL, *dir = NULL, *frameOut = NULL, *hitsOut = NULL, *sceneOut = NULL;
+    const char *sceneFile = NULL, *dir = NULL, *frameOut = NULL, *hitsOut = NULL, *sceneOut = NULL, *keys = NULL;
     int W = 640, H = 640, threads = 8, timeFrames = 0;
     float forceReflection = -1;
     bool counters = false;
+    if (argc == 4 && strcmp(argv[1], "--kat") == 0) return RunKat(argv[2], argv[3]);
     for (int i = 1; i < argc; i++) {
         #define ARG(name) (strcmp(argv[i], name) == 0 && i + 1 < argc)
         if (ARG("--scene")) sceneFile = argv[++i];
@@ -133,6 +171,7 @@ int main(int argc, char **argv) {
         else if (ARG("--hits")) hitsOut = argv[++i];
         else if (ARG("--dump-scene")) sceneOut = argv[++i];
         else if (ARG("--time")) timeFrames = atoi(argv[++i]);
+        else if (ARG("--keys")) keys = argv[++i];       // key presses fed to HandleKeyboard before the first frame
         else if (strcmp(argv[i], "--counters") == 0) counters = true;
         else if (strcmp(argv[i], "--verbose") == 0) ct_sdl_stub_quiet = 0;
         else { fprintf(stderr, "unknown arg %s\n", argv[i]); return 2; }
@@ -185,6 +224,12 @@ int main(int argc, char **argv) {
 
     AllocatePartitions(&scene);
     double ms = RenderFrame(&env, &scene, &bvh, true);
+    if (keys) {
+        // HandleKeyboard is short-circuited on the very first HandleUpdates (static changesMade = true,
+        // raythread.cpp:548,557), so key presses only take effect from the second frame on.
+        for (const char *k = keys; *k; k++) AddEvent(&env.events, {ET_KEY_DOWN, EM_NONE, {0, 0}, (uint32_t)*k});
+        ms = RenderFrame(&env, &scene, &bvh, false);
+    }
 
     if (frameP) WriteFile(frameP, bitmap.memory, (size_t)W * H * 4);
     if (sceneP) DumpScene(sceneP, &scene, &bvh);
@@ -200,8 +245,9 @@ int main(int argc, char **argv) {
         for (size_t i = 0; i < (size_t)W * H; i++) hits[i].found = 0xFFFFFFFFu; // never traced / dropped
         viewport_t vp = {1, 1, 1};
         float width = bitmap.height / 2;
+        for (int part = 0; part < scene.settings.numberOfThreads; part++)   // exactly the rows the workers traced
         for (int x = -width; x < width; x++) {
-            for (int y = -(int)width; y < (int)width; y++) {
+            for (int y = displayPart[part]->yStart; y < displayPart[part]->yEnd; y++) {
                 v3_t direction = CanvasToViewport(&bitmap, vp, {(float)x, (float)y}) * scene.camera.rotation;
                 ray_t ray = {scene.camera.position, direction, 1e30f};
                 float tclosest = FINF;
