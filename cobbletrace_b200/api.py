@@ -16,7 +16,7 @@ from .sceneio import FlatScene
 PKG = os.path.dirname(os.path.abspath(__file__))
 GPU_LIB = os.path.join(PKG, "libct_gpu.so")
 
-CT_FLAG_WIDE, CT_FLAG_KEEP_HITS, CT_FLAG_COUNT_TESTS = 1, 2, 4
+CT_FLAG_WIDE, CT_FLAG_KEEP_HITS, CT_FLAG_COUNT_TESTS, CT_FLAG_STAGE_TIMING = 1, 2, 4, 8
 BACKGROUND = 0x333333      # raythread.cpp:59
 REFERENCE_MAX_DEPTH = 10   # raythread.cpp:508
 
@@ -24,7 +24,7 @@ REFERENCE_MAX_DEPTH = 10   # raythread.cpp:508
 ABI_SYMBOLS = [
     "ct_gpu_abi_version", "ct_gpu_device_count", "ct_gpu_last_error", "ct_gpu_upload_scene", "ct_gpu_set_camera",
     "ct_gpu_set_stream", "ct_gpu_render_tile", "ct_gpu_readback", "ct_gpu_readback_hits", "ct_gpu_get_counters",
-    "ct_gpu_last_tile_ms", "ct_gpu_sync", "ct_gpu_throttle", "ct_gpu_framebuffer", "ct_gpu_gather_rows", "ct_gpu_debug_closest",
+    "ct_gpu_last_tile_ms", "ct_gpu_sync", "ct_gpu_throttle", "ct_gpu_kernel_launches", "ct_gpu_last_tile_stages", "ct_gpu_framebuffer", "ct_gpu_gather_rows", "ct_gpu_debug_closest",
     "ct_gpu_debug_primitives", "ct_gpu_shutdown",
 ]
 
@@ -97,6 +97,8 @@ def load_library(path: Optional[str] = None):
     L.ct_gpu_last_tile_ms.argtypes = [C.c_int, C.POINTER(C.c_float)]
     L.ct_gpu_sync.argtypes = [C.c_int]
     L.ct_gpu_throttle.argtypes = [C.c_int, C.c_int]
+    L.ct_gpu_kernel_launches.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.c_int]
+    L.ct_gpu_last_tile_stages.argtypes = [C.c_int, C.c_int, vp, vp, vp]
     L.ct_gpu_framebuffer.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ct_gpu_gather_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.ct_gpu_debug_closest.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp]
@@ -190,6 +192,17 @@ class GpuRenderer:
         ms = C.c_float()
         _check(self.L, self.L.ct_gpu_last_tile_ms(self.device, C.byref(ms)))
         return float(ms.value)
+
+    def kernel_launches(self, reset: bool = False) -> int:
+        n = C.c_uint64()
+        _check(self.L, self.L.ct_gpu_kernel_launches(self.device, C.byref(n), int(reset)))
+        return int(n.value)
+
+    def last_tile_stages(self):
+        """[(kernel name, depth, ms)] of the last tile (needs CT_FLAG_STAGE_TIMING)."""
+        ms = (C.c_float * 40)(); names = (C.c_char_p * 40)(); depth = (C.c_int * 40)()
+        n = _check(self.L, self.L.ct_gpu_last_tile_stages(self.device, 40, ms, names, depth))
+        return [(names[i].decode(), int(depth[i]), float(ms[i])) for i in range(n)]
 
     def counters(self, reset: bool = False):
         c = RayCounters()

@@ -434,6 +434,11 @@ struct DeviceState {
     cudaEvent_t tile_done[8] = {};   // ring: completion of the last 8 submitted tiles (ct_gpu_throttle)
     unsigned long long tiles_submitted = 0;
     int row_lo = 0, row_hi = 0;      // hull of framebuffer rows rendered since upload (readback clips to it)
+    unsigned long long launches = 0; // kernels launched since upload / reset
+    cudaEvent_t stage_ev[40] = {};   // CT_FLAG_STAGE_TIMING: boundaries between the launches of the last tile
+    const char *stage_name[40] = {};
+    int stage_depth[40] = {};
+    int n_stages = 0;
     bool timed = false;
     std::vector<void *> allocs;
     ct_ray_counters snapshot{};      // totals at the end of the previous counted tile
@@ -460,6 +465,7 @@ void free_device(DeviceState &s) {
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
     for (cudaEvent_t e : s.tile_done) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s.stage_ev) if (e) cudaEventDestroy(e);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
     s = DeviceState{};
 }
@@ -552,6 +558,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     CU(cudaEventCreate(&s.ev0));
     CU(cudaEventCreate(&s.ev1));
     for (cudaEvent_t &e : s.tile_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (d->flags & CT_FLAG_STAGE_TIMING) for (cudaEvent_t &e : s.stage_ev) CU(cudaEventCreate(&e));
     s.flags = d->flags;
 
     Params &p = s.p;
@@ -673,17 +680,33 @@ int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *coun
     CU(cudaEventRecord(s.ev0, st));
     const int grid = launch_grid(s, 8);
     int work = 0;
+    const bool stages = (s.flags & CT_FLAG_STAGE_TIMING) != 0;
+    s.n_stages = 0;
+    auto mark = [&](const char *name, int depth) -> int {          // called after each launch
+        s.launches++;
+        if (!stages) return CT_OK;
+        if (s.n_stages == 0) CU(cudaEventRecord(s.stage_ev[0], st));    // (re-recorded below, before the first launch)
+        s.stage_name[s.n_stages] = name; s.stage_depth[s.n_stages] = depth;
+        s.n_stages++;
+        CU(cudaEventRecord(s.stage_ev[s.n_stages], st));
+        return CT_OK;
+    };
+    if (stages) CU(cudaEventRecord(s.stage_ev[0], st));
     if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(pk, work++);
     else k_primary<false><<<grid, kBlockThreads, 0, st>>>(pk, work++);
+    if (stages) { s.launches++; s.stage_name[0] = "primary"; s.stage_depth[0] = 0; s.n_stages = 1; CU(cudaEventRecord(s.stage_ev[1], st)); }
+    else s.launches++;
     for (int d = 0; d <= depth_max; d++) {
         if (d > 0) {
             if (count) k_bounce<true><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
             else k_bounce<false><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
+            TRY(mark("bounce", d));
         }
         if (count) k_shade<true><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
         else k_shade<false><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
+        TRY(mark("shade", d));
     }
-    if (depth_max > 0) k_resolve<<<s.n_sm * 4, 256, 0, st>>>(pk);
+    if (depth_max > 0) { k_resolve<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("resolve", 0)); }
     CU(cudaEventRecord(s.ev1, st));
     CU(cudaEventRecord(s.tile_done[s.tiles_submitted % 8], st));
     s.tiles_submitted++;
@@ -713,6 +736,30 @@ int ct_gpu_sync(int device) {
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     CU(cudaStreamSynchronize(s.stream));
     return CT_OK;
+}
+
+int ct_gpu_kernel_launches(int device, uint64_t *out, int reset) {
+    if (!out) return fail(CT_ERR_INVALID, "NULL out");
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    *out = s.launches;
+    if (reset) s.launches = 0;
+    return CT_OK;
+}
+
+int ct_gpu_last_tile_stages(int device, int max, float *ms, const char **names, int *depth) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    if (!(s.flags & CT_FLAG_STAGE_TIMING)) return fail(CT_ERR_INVALID, "scene was uploaded without CT_FLAG_STAGE_TIMING");
+    CU(cudaStreamSynchronize(s.stream));
+    for (int i = 0; i < s.n_stages && i < max; i++) {
+        if (ms) CU(cudaEventElapsedTime(&ms[i], s.stage_ev[i], s.stage_ev[i + 1]));
+        if (names) names[i] = s.stage_name[i];
+        if (depth) depth[i] = s.stage_depth[i];
+    }
+    return s.n_stages;
 }
 
 int ct_gpu_throttle(int device, int max_in_flight) {

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "ct_scene.hpp"
+#include "ct_tiles.hpp"
 
 namespace cth {
 
@@ -36,6 +37,8 @@ struct GpuApi {
     const char *(*last_error)() = nullptr;
     int (*upload_scene)(int, const ct_scene_desc *) = nullptr;
     int (*set_camera)(int, const double *, const double *) = nullptr;
+    int (*set_stream)(int, void *) = nullptr;
+    int (*kernel_launches)(int, uint64_t *, int) = nullptr;
     int (*render_tile)(int, int, int, ct_ray_counters *) = nullptr;
     int (*throttle)(int, int) = nullptr;
     int (*readback)(int, uint32_t *, int, int, int) = nullptr;
@@ -56,6 +59,8 @@ struct GpuApi {
         last_error = (const char *(*)())sym("ct_gpu_last_error");
         upload_scene = (int (*)(int, const ct_scene_desc *))sym("ct_gpu_upload_scene");
         set_camera = (int (*)(int, const double *, const double *))sym("ct_gpu_set_camera");
+        set_stream = (int (*)(int, void *))sym("ct_gpu_set_stream");
+        kernel_launches = (int (*)(int, uint64_t *, int))sym("ct_gpu_kernel_launches");
         render_tile = (int (*)(int, int, int, ct_ray_counters *))sym("ct_gpu_render_tile");
         throttle = (int (*)(int, int))sym("ct_gpu_throttle");
         readback = (int (*)(int, uint32_t *, int, int, int))sym("ct_gpu_readback");
@@ -67,29 +72,6 @@ struct GpuApi {
     }
     void check(int rc, const char *what) const {
         if (rc < 0) throw std::runtime_error(std::string(what) + ": " + last_error());
-    }
-};
-
-struct TileCounter {               // hands out tile numbers 0,1,2,... to whoever asks first
-    std::atomic<int32_t> local{0};
-    int32_t *shared = nullptr;     // mmap'd, shared by all processes of the job
-    std::string shm_name;
-    int fd = -1;
-
-    void open_shared(const std::string &name) {
-        shm_name = name[0] == '/' ? name : "/" + name;
-        fd = shm_open(shm_name.c_str(), O_CREAT | O_RDWR, 0600);
-        if (fd < 0) throw std::runtime_error("shm_open(" + shm_name + ") failed");
-        if (ftruncate(fd, 64) != 0) throw std::runtime_error("ftruncate on shared tile counter failed");
-        void *p = mmap(nullptr, 64, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-        if (p == MAP_FAILED) throw std::runtime_error("mmap of shared tile counter failed");
-        shared = static_cast<int32_t *>(p);
-    }
-    int32_t next() { return shared ? __atomic_fetch_add(shared, 1, __ATOMIC_RELAXED) : local.fetch_add(1, std::memory_order_relaxed); }
-    void reset() { if (shared) __atomic_store_n(shared, 0, __ATOMIC_SEQ_CST); else local.store(0); }
-    ~TileCounter() {
-        if (shared) munmap(shared, 64);
-        if (fd >= 0) close(fd);
     }
 };
 
@@ -159,6 +141,11 @@ void boss_set_camera(Boss *b, const double pos[3], float yaw, float pitch, float
 
 void boss_reset_counter(Boss *b) { b->counter.reset(); }
 
+void boss_set_stream(Boss *b, int slot, void *stream) {
+    if (slot < 0 || slot >= b->cfg.n_devices) throw std::runtime_error("device slot out of range");
+    b->gpu.check(b->gpu.set_stream(b->cfg.devices[slot], stream), "ct_gpu_set_stream");
+}
+
 void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *stats) {
     const auto t0 = std::chrono::steady_clock::now();
     const int nd = b->cfg.n_devices;
@@ -215,6 +202,9 @@ void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *sta
             stats->rays.rays_primary += c.rays_primary; stats->rays.rays_shadow += c.rays_shadow;
             stats->rays.rays_reflection += c.rays_reflection; stats->rays.box_tests += c.box_tests; stats->rays.tri_tests += c.tri_tests;
             stats->tiles_mine += (int)b->tiles_by_dev[k].size();
+            uint64_t nl = 0;
+            b->gpu.check(b->gpu.kernel_launches(b->cfg.devices[k], &nl, 1), "ct_gpu_kernel_launches");
+            stats->kernel_launches += nl;
         }
         stats->tiles_total = b->n_tiles;
         stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -5,12 +5,14 @@
 #include <string>
 
 #include "ct_scene.hpp"
+#include "ct_tiles.hpp"
 
 namespace cth {
 struct Boss;
 Boss *boss_create(Scene *scene, const ct_host_boss_config *cfg);
 void boss_set_camera(Boss *b, const double pos[3], float yaw, float pitch, float roll);
 void boss_reset_counter(Boss *b);
+void boss_set_stream(Boss *b, int slot, void *stream);
 void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *stats);
 int boss_tiles(const Boss *b, int32_t *out, int max_tiles);
 void boss_destroy(Boss *b);
@@ -143,6 +145,10 @@ int ct_host_boss_set_camera(ct_host_boss *b, const double pos[3], float yaw, flo
     GUARD(cth::boss_set_camera(reinterpret_cast<cth::Boss *>(b), pos, yaw, pitch, roll));
 }
 
+int ct_host_boss_set_stream(ct_host_boss *b, int device_slot, void *cuda_stream) {
+    GUARD(cth::boss_set_stream(reinterpret_cast<cth::Boss *>(b), device_slot, cuda_stream));
+}
+
 int ct_host_boss_reset_shared_counter(ct_host_boss *b) { GUARD(cth::boss_reset_counter(reinterpret_cast<cth::Boss *>(b))); }
 
 int ct_host_boss_render(ct_host_boss *b, uint32_t *bitmap, int stride_pixels, ct_host_frame_stats *stats) {
@@ -151,6 +157,25 @@ int ct_host_boss_render(ct_host_boss *b, uint32_t *bitmap, int stride_pixels, ct
 
 int ct_host_boss_tiles(const ct_host_boss *b, int32_t *y_ranges, int max_tiles) {
     return cth::boss_tiles(reinterpret_cast<const cth::Boss *>(b), y_ranges, max_tiles);
+}
+
+ct_host_tile_counter *ct_host_tile_counter_open(const char *shared_name) {
+    auto *c = new cth::TileCounter();
+    try {
+        if (shared_name && shared_name[0]) c->open_shared(shared_name);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        delete c;
+        return nullptr;
+    }
+    return reinterpret_cast<ct_host_tile_counter *>(c);
+}
+int32_t ct_host_tile_counter_next(ct_host_tile_counter *c) { return reinterpret_cast<cth::TileCounter *>(c)->next(); }
+void ct_host_tile_counter_reset(ct_host_tile_counter *c) { reinterpret_cast<cth::TileCounter *>(c)->reset(); }
+void ct_host_tile_counter_close(ct_host_tile_counter *c, int unlink_shared) {
+    auto *t = reinterpret_cast<cth::TileCounter *>(c);
+    if (t && unlink_shared && !t->shm_name.empty()) shm_unlink(t->shm_name.c_str());
+    delete t;
 }
 
 void ct_host_boss_destroy(ct_host_boss *b) { cth::boss_destroy(reinterpret_cast<cth::Boss *>(b)); }

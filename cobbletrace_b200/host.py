@@ -23,8 +23,9 @@ ABI_SYMBOLS = [
     "ct_host_scene_light_count", "ct_host_scene_lights", "ct_host_scene_camera", "ct_host_scene_set_camera",
     "ct_host_scene_settings", "ct_host_scene_set_reflection", "ct_host_build_bvh", "ct_host_scene_nodes",
     "ct_host_scene_tri_indexes", "ct_host_scene_set_bvh", "ct_host_camera_rotation", "ct_host_fill_desc",
-    "ct_host_boss_create", "ct_host_boss_set_camera", "ct_host_boss_render", "ct_host_boss_reset_shared_counter",
+    "ct_host_boss_create", "ct_host_boss_set_stream", "ct_host_boss_set_camera", "ct_host_boss_render", "ct_host_boss_reset_shared_counter",
     "ct_host_boss_tiles", "ct_host_boss_destroy",
+    "ct_host_tile_counter_open", "ct_host_tile_counter_next", "ct_host_tile_counter_reset", "ct_host_tile_counter_close",
 ]
 
 
@@ -40,7 +41,7 @@ class BossConfig(C.Structure):
 
 class FrameStats(C.Structure):
     _fields_ = [("rays", api.RayCounters), ("device_ms_max", C.c_float), ("wall_ms", C.c_double),
-                ("tiles_total", C.c_int32), ("tiles_mine", C.c_int32)]
+                ("tiles_total", C.c_int32), ("tiles_mine", C.c_int32), ("kernel_launches", C.c_uint64)]
 
 
 _lib = None
@@ -73,10 +74,15 @@ def load_library():
         L.ct_host_fill_desc.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(api.SceneDesc)]
         L.ct_host_boss_create.restype = vp; L.ct_host_boss_create.argtypes = [vp, C.POINTER(BossConfig)]
         L.ct_host_boss_set_camera.argtypes = [vp, vp, C.c_float, C.c_float, C.c_float]
+        L.ct_host_boss_set_stream.argtypes = [vp, C.c_int, vp]
         L.ct_host_boss_render.argtypes = [vp, vp, C.c_int, C.POINTER(FrameStats)]
         L.ct_host_boss_reset_shared_counter.argtypes = [vp]
         L.ct_host_boss_tiles.argtypes = [vp, vp, C.c_int]
         L.ct_host_boss_destroy.argtypes = [vp]
+        L.ct_host_tile_counter_open.restype = vp; L.ct_host_tile_counter_open.argtypes = [C.c_char_p]
+        L.ct_host_tile_counter_next.restype = C.c_int32; L.ct_host_tile_counter_next.argtypes = [vp]
+        L.ct_host_tile_counter_reset.argtypes = [vp]
+        L.ct_host_tile_counter_close.argtypes = [vp, C.c_int]
         _lib = L
     return _lib
 
@@ -223,6 +229,10 @@ class Boss:
         if self.L.ct_host_boss_set_camera(self.h, p.ctypes.data_as(C.c_void_p), yaw, pitch, roll) < 0:
             raise RuntimeError("ct_host_boss_set_camera: " + _err(self.L))
 
+    def set_stream(self, cuda_stream_ptr, slot: int = 0):
+        if self.L.ct_host_boss_set_stream(self.h, slot, C.c_void_p(cuda_stream_ptr or 0)) < 0:
+            raise RuntimeError("ct_host_boss_set_stream: " + _err(self.L))
+
     def reset_shared_counter(self):
         self.L.ct_host_boss_reset_shared_counter(self.h)
 
@@ -234,7 +244,8 @@ class Boss:
                                         bitmap.shape[1] if bitmap is not None else 0, C.byref(st))
         if rc < 0:
             raise RuntimeError("ct_host_boss_render: " + _err(self.L))
-        stats = dict(st.rays.as_dict(), wall_ms=float(st.wall_ms), tiles_total=int(st.tiles_total), tiles_mine=int(st.tiles_mine))
+        stats = dict(st.rays.as_dict(), wall_ms=float(st.wall_ms), tiles_total=int(st.tiles_total), tiles_mine=int(st.tiles_mine),
+                     kernel_launches=int(st.kernel_launches))
         return bitmap, stats
 
     def tiles(self):
@@ -252,3 +263,23 @@ class Boss:
             self.close()
         except Exception:
             pass
+
+
+class TileCounter:
+    """The dispenser the boss steals tiles from (process-local, or POSIX shm shared by all ranks)."""
+
+    def __init__(self, shared_name: Optional[str] = None):
+        self.L = load_library()
+        self.h = self.L.ct_host_tile_counter_open(shared_name.encode() if shared_name else None)
+        if not self.h:
+            raise RuntimeError("ct_host_tile_counter_open: " + _err(self.L))
+
+    def next(self) -> int:
+        return int(self.L.ct_host_tile_counter_next(self.h))
+
+    def reset(self):
+        self.L.ct_host_tile_counter_reset(self.h)
+
+    def close(self, unlink: bool = False):
+        if self.h:
+            self.L.ct_host_tile_counter_close(self.h, int(unlink)); self.h = None

@@ -1,0 +1,99 @@
+"""One-process-per-GPU plumbing (torch.distributed): the frame is cut into row tiles that the ranks steal
+from a shared counter (C++ boss, ct_host_boss_*), and the finished tiles are gathered to rank 0.
+
+The path has exactly one exchange step -- the gather of 4-byte pixels to GPU 0 -- so that is
+the only collective: point-to-point sends of each rank's own rows into rank 0's framebuffer (NCCL over
+NVLink on GPUs; gloo on CPU for the tests).  Rendering itself needs no communication (scene replicated).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def env_rank() -> Tuple[int, int, int]:
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def init_distributed(backend: str | None = None):
+    rank, local_rank, world = env_rank()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, local_rank, world
+
+
+def shared_counter_name() -> str:
+    """One POSIX shm counter per job (all ranks of a torchrun share MASTER_PORT)."""
+    return f"ct_tiles_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
+
+
+class _CudaArray:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can alias it (no copy)."""
+
+    def __init__(self, ptr: int, shape, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+
+
+def framebuffer_tensor(ptr: int, width: int, height: int, device: int) -> torch.Tensor:
+    """int32 [H, W] tensor aliasing the renderer's device framebuffer (ct_gpu_framebuffer)."""
+    return torch.as_tensor(_CudaArray(ptr, (height, width)), device=torch.device("cuda", device))
+
+
+def tiles_to_rows(tiles: Sequence[Tuple[int, int]], height: int) -> List[Tuple[int, int]]:
+    """canvas-y tile [y0,y1) -> framebuffer rows [r0,r1): row = H/2 - y (raythread.cpp:182)."""
+    half = height // 2
+    return [(max(0, half - (y1 - 1)), min(height, half - y0 + 1)) for y0, y1 in tiles]
+
+
+def exchange_tiles(my_tiles: Sequence[Tuple[int, int]], max_tiles: int, device=None) -> List[List[Tuple[int, int]]]:
+    """all_gather of who rendered which tile (tiny)."""
+    world = dist.get_world_size()
+    buf = torch.full((max_tiles + 1, 2), -1, dtype=torch.int32)
+    buf[0, 0] = len(my_tiles)
+    for i, (a, b) in enumerate(my_tiles):
+        buf[1 + i, 0], buf[1 + i, 1] = a, b
+    if device is not None:
+        buf = buf.to(device)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    res = []
+    for t in out:
+        t = t.cpu()
+        n = int(t[0, 0])
+        res.append([(int(t[1 + i, 0]), int(t[1 + i, 1])) for i in range(n)])
+    return res
+
+
+def gather_rows_to_root(fb: torch.Tensor, tiles_by_rank: Sequence[Sequence[Tuple[int, int]]], root: int = 0) -> int:
+    """Every rank sends the framebuffer rows of the tiles it rendered to `root`, which receives them in place.
+    Returns the number of bytes that crossed into root."""
+    rank = dist.get_rank()
+    H = fb.shape[0]
+    ops, nbytes = [], 0
+    for r, tiles in enumerate(tiles_by_rank):
+        if r == root:
+            continue
+        for r0, r1 in tiles_to_rows(tiles, H):
+            if r1 <= r0:
+                continue
+            view = fb[r0:r1]
+            if rank == r:
+                ops.append(dist.P2POp(dist.isend, view, root))
+            elif rank == root:
+                ops.append(dist.P2POp(dist.irecv, view, r))
+                nbytes += view.numel() * view.element_size()
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return nbytes

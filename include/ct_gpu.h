@@ -69,7 +69,8 @@ enum {
     CT_FLAG_WIDE = 1u,        /* trace x in [-W/2, W/2) instead of the reference's centred HxH square
                                  (raythread.cpp:454-455 "Keep it square"); SURVEY f2 */
     CT_FLAG_KEEP_HITS = 2u,   /* keep the primary-ray hit records for ct_gpu_readback_hits */
-    CT_FLAG_COUNT_TESTS = 4u  /* count box / triangle tests (slower; for roofline accounting) */
+    CT_FLAG_COUNT_TESTS = 4u, /* count box / triangle tests (slower; for roofline accounting) */
+    CT_FLAG_STAGE_TIMING = 8u /* bracket every kernel launch of a tile with CUDA events (profiling passes only) */
 };
 
 /* What RayThread hands its workers (display_partition_t raythread.cpp:69-78 + bvh_state_t bvh.h:19-25). */
@@ -144,6 +145,15 @@ int ct_gpu_get_counters(int device, ct_ray_counters *out, int reset);
 /* Device time in ms spent in the kernels of the most recent ct_gpu_render_tile (CUDA events on the
  * launching stream; synchronises). */
 int ct_gpu_last_tile_ms(int device, float *ms);
+
+/* Number of this library's kernels launched on `device` since upload / last reset (the caller's
+ * "gpu_launches" claim; memsets and copies are not counted). */
+int ct_gpu_kernel_launches(int device, uint64_t *out, int reset);
+
+/* With CT_FLAG_STAGE_TIMING: device time of every kernel of the most recent tile, in launch order.
+ * names[i] points at a static string ("primary", "shade", "bounce", "resolve"); depth[i] is the path depth.
+ * Returns the number of launches (fills at most `max`). Synchronises. */
+int ct_gpu_last_tile_stages(int device, int max, float *ms, const char **names, int *depth);
 
 int ct_gpu_sync(int device);
 

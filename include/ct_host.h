@@ -27,6 +27,7 @@ extern "C" {
 
 typedef struct ct_host_scene ct_host_scene;
 typedef struct ct_host_boss ct_host_boss;
+typedef struct ct_host_tile_counter ct_host_tile_counter;
 
 /* == settings_t, reference scenefile.h:83-88 (defaults from InitSceneData scenefile.cpp:23-26) */
 typedef struct ct_host_settings {
@@ -95,10 +96,14 @@ typedef struct ct_host_frame_stats {
     float device_ms_max;          /* max over this process's devices of summed tile kernel time */
     double wall_ms;               /* dispatch -> bitmap complete */
     int32_t tiles_total, tiles_mine;
+    uint64_t kernel_launches;     /* CUDA kernels launched for this frame by this process */
 } ct_host_frame_stats;
 
 /* RayThread's first-call half (raythread.cpp:647-654): builds the BVH if needed and uploads to every device. */
 ct_host_boss *ct_host_boss_create(ct_host_scene *s, const ct_host_boss_config *cfg);
+/* Launch device k's work on the caller's CUDA stream (cudaStream_t; e.g. the framework's current stream, so
+ * that its events and collectives order with the tiles).  NULL = the library's own stream. */
+int ct_host_boss_set_stream(ct_host_boss *b, int device_slot, void *cuda_stream);
 /* HandleUpdates' camera half (raythread.cpp:557-572). */
 int ct_host_boss_set_camera(ct_host_boss *b, const double pos[3], float yaw, float pitch, float roll);
 /* One frame: dispatch all row tiles (dynamic stealing), wait, gather to devices[0], copy into bitmap
@@ -111,6 +116,13 @@ int ct_host_boss_reset_shared_counter(ct_host_boss *b);
 /* Tiles rendered by this process in the last frame: writes up to max (y_start,y_end) pairs, returns count. */
 int ct_host_boss_tiles(const ct_host_boss *b, int32_t *y_ranges, int max_tiles);
 void ct_host_boss_destroy(ct_host_boss *b);
+
+/* The tile dispenser on its own (what the boss steals from): a process-local atomic (shared_name NULL/"")
+ * or a POSIX shared-memory counter common to all processes that open the same name. */
+ct_host_tile_counter *ct_host_tile_counter_open(const char *shared_name);
+int32_t ct_host_tile_counter_next(ct_host_tile_counter *c);       /* 0,1,2,... each value handed out exactly once */
+void ct_host_tile_counter_reset(ct_host_tile_counter *c);
+void ct_host_tile_counter_close(ct_host_tile_counter *c, int unlink_shared);
 
 #ifdef __cplusplus
 }

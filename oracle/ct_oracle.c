@@ -46,6 +46,7 @@ typedef struct { vec3 org, dir; float t; } ray;   /* ray_t, scenefile.h:104-108 
 typedef struct {
     const ct_oracle_scene *s;
     ct_oracle_counters c;
+    int kind;               /* kind of the ray being traversed: 0 primary, 1 shadow, 2 reflection */
 } ctx;
 
 /* ---- bvh.cpp:147-163 IntersectTriangle -------------------------------------------- */
@@ -89,6 +90,7 @@ static int intersect_aabb(const ray *r, const double *bmin, const double *bmax) 
 static void bvh_closest(ctx *cx, ray *r, uint32_t node, float *tclosest, uint32_t *closest_index) {
     const ct_oracle_scene *s = cx->s;
     cx->c.box_tests++;
+    cx->c.box_tests_kind[cx->kind]++;
     if (!intersect_aabb(r, s->node_min + 3 * (size_t)node, s->node_max + 3 * (size_t)node)) return;
     uint32_t count = s->node_count[node];
     if (count > 0) {
@@ -96,6 +98,7 @@ static void bvh_closest(ctx *cx, ray *r, uint32_t node, float *tclosest, uint32_
         for (uint32_t i = 0; i < count; i++) {
             uint32_t k = s->tri_index[first + i];
             cx->c.tri_tests++;
+            cx->c.tri_tests_kind[cx->kind]++;
             int hit = intersect_triangle(r, s->tri + 9 * (size_t)k);
             if (hit && r->t != RAY_T_INIT && r->t < *tclosest) {
                 *closest_index = k;
@@ -112,7 +115,13 @@ static void bvh_closest(ctx *cx, ray *r, uint32_t node, float *tclosest, uint32_
 static int closest_intersection(ctx *cx, ray r, float *tclosest, uint32_t *closest_index) {
     *tclosest = FINF;
     *closest_index = 0;
+    uint64_t before = cx->c.box_tests;
     bvh_closest(cx, &r, 0, tclosest, closest_index);
+    uint64_t n = cx->c.box_tests - before;
+    int b = 0;
+    while ((n >> (b + 1)) != 0 && b < 31) b++;
+    cx->c.ray_hist[cx->kind][b]++;
+    cx->c.box_hist[cx->kind][b] += n;
     return r.t != RAY_T_INIT;
 }
 
@@ -145,7 +154,11 @@ static float compute_lighting(ctx *cx, vec3 position, vec3 normal, vec3 view, in
         ray sr = {position, light_ray, RAY_T_INIT};
         float tc; uint32_t idx;
         cx->c.rays_shadow++;
-        if (closest_intersection(cx, sr, &tc, &idx)) continue;
+        int kind_saved = cx->kind;
+        cx->kind = 1;
+        int shadowed = closest_intersection(cx, sr, &tc, &idx);
+        cx->kind = kind_saved;
+        if (shadowed) continue;
 
         float n_dot_l = v_dot(normal, light_ray);                       /* :310 */
         if (n_dot_l > 0) intensity += li * n_dot_l / (v_mag(normal) * v_mag(light_ray));   /* all float :312 */
@@ -252,6 +265,7 @@ static uint32_t trace_ray(ctx *cx, ray r, int depth) {
     vec3 rdir = reflect_ray(v_neg(r.dir), normal);                                   /* :372 */
     ray rr = {position, rdir, 0.0f};                                                 /* :373 -- t = 0 (sic) */
     cx->c.rays_reflection++;
+    cx->kind = 2;
     uint32_t reflected = trace_ray(cx, rr, depth - 1);
     return ct_oracle_blend(local, reflected, reflection);
 }
@@ -286,10 +300,11 @@ static void *render_rows(void *arg) {
             ray r = {cam, dir, RAY_T_INIT};
             j->cx.c.rays_primary++;
             if (j->hits && stored) {
-                ctx tmp = { s, {0, 0, 0, 0, 0} };
+                ctx tmp; memset(&tmp, 0, sizeof tmp); tmp.s = s;
                 ct_oracle_hit *h = &j->hits[(size_t)row * W + col];
                 h->found = (uint32_t)closest_intersection(&tmp, r, &h->t, &h->index);
             }
+            j->cx.kind = 0;
             uint32_t color = trace_ray(&j->cx, r, j->max_depth);
             if (stored) j->frame[(size_t)row * W + col] = color;
         }
@@ -315,7 +330,7 @@ int ct_oracle_render(const ct_oracle_scene *s, int W, int H, int y_start, int y_
         if (n_threads == 1) render_rows(&jobs[i]);
         else pthread_create(&th[i], NULL, render_rows, &jobs[i]);
     }
-    ct_oracle_counters total = {0, 0, 0, 0, 0};
+    ct_oracle_counters total; memset(&total, 0, sizeof total);
     for (int i = 0; i < n_threads; i++) {
         if (n_threads > 1) pthread_join(th[i], NULL);
         total.rays_primary += jobs[i].cx.c.rays_primary;
@@ -323,6 +338,14 @@ int ct_oracle_render(const ct_oracle_scene *s, int W, int H, int y_start, int y_
         total.rays_reflection += jobs[i].cx.c.rays_reflection;
         total.box_tests += jobs[i].cx.c.box_tests;
         total.tri_tests += jobs[i].cx.c.tri_tests;
+        for (int k = 0; k < 3; k++) {
+            total.box_tests_kind[k] += jobs[i].cx.c.box_tests_kind[k];
+            total.tri_tests_kind[k] += jobs[i].cx.c.tri_tests_kind[k];
+            for (int b = 0; b < 32; b++) {
+                total.ray_hist[k][b] += jobs[i].cx.c.ray_hist[k][b];
+                total.box_hist[k][b] += jobs[i].cx.c.box_hist[k][b];
+            }
+        }
     }
     if (counters) *counters = total;
     free(jobs); free(th);
@@ -353,7 +376,7 @@ int ct_oracle_intersect_aabb(const double org[3], const double dir[3], float ray
 
 int ct_oracle_closest(const ct_oracle_scene *s, const double org[3], const double dir[3], float ray_t0,
                       uint32_t *index, float *tclosest) {
-    ctx cx = { s, {0, 0, 0, 0, 0} };
+    ctx cx; memset(&cx, 0, sizeof cx); cx.s = s;
     ray r = {v_load(org), v_load(dir), ray_t0};
     *tclosest = FINF;
     *index = 0;

@@ -44,7 +44,10 @@ typedef struct ct_oracle_scene {
 
 typedef struct ct_oracle_counters {
     uint64_t rays_primary, rays_shadow, rays_reflection;
-    uint64_t box_tests, tri_tests;  /* IntersectAABB / IntersectTriangle calls */
+    uint64_t box_tests, tri_tests;  /* IntersectAABB / IntersectTriangle calls, all rays */
+    uint64_t box_tests_kind[3], tri_tests_kind[3];  /* the same split by ray kind: 0 primary, 1 shadow, 2 reflection */
+    uint64_t ray_hist[3][32];       /* rays by floor(log2(box tests of the ray)), per kind: the traversal-length tail */
+    uint64_t box_hist[3][32];       /* box tests spent in each of those buckets */
 } ct_oracle_counters;
 
 typedef struct ct_oracle_hit { uint32_t found, index; float t; } ct_oracle_hit;

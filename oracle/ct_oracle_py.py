@@ -27,10 +27,17 @@ class _Scene(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_reflection", C.c_uint64),
-                ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64)]
+                ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64),
+                ("box_tests_kind", C.c_uint64 * 3), ("tri_tests_kind", C.c_uint64 * 3),
+                ("ray_hist", (C.c_uint64 * 32) * 3), ("box_hist", (C.c_uint64 * 32) * 3)]
 
-    def as_dict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+    def as_dict(self, by_kind=False):
+        d = {k: int(getattr(self, k)) for k, _ in self._fields_[:5]}
+        if by_kind:
+            for i, kind in enumerate(("primary", "shadow", "reflection")):
+                d[f"box_tests_{kind}"] = int(self.box_tests_kind[i]); d[f"tri_tests_{kind}"] = int(self.tri_tests_kind[i])
+                d[f"ray_hist_{kind}"] = [int(x) for x in self.ray_hist[i]]; d[f"box_hist_{kind}"] = [int(x) for x in self.box_hist[i]]
+        return d
 
 
 HIT_DT = np.dtype([("found", "<u4"), ("index", "<u4"), ("t", "<f4")])
@@ -112,7 +119,7 @@ class OracleScene:
         self._keep = keep
         self.c = s
 
-    def render(self, W, H, y_start=None, y_end=None, max_depth=10, flags=0, want_hits=True, n_threads=None):
+    def render(self, W, H, y_start=None, y_end=None, max_depth=10, flags=0, want_hits=True, n_threads=None, by_kind=False):
         half = H // 2      # HandleUpdates raythread.cpp:574-581 with a thread count dividing H: rows [-(H/2), -(H/2)+H)
         y_start = -half if y_start is None else y_start
         y_end = -half + H if y_end is None else y_end
@@ -125,7 +132,7 @@ class OracleScene:
         n_threads = n_threads or min(os.cpu_count() or 1, 32)
         lib().ct_oracle_render(C.byref(self.c), W, H, y_start, y_end, max_depth, flags, _ptr(frame),
                                _ptr(hits) if hits is not None else None, C.byref(ctr), n_threads)
-        return frame, hits, ctr.as_dict()
+        return frame, hits, ctr.as_dict(by_kind)
 
     def closest(self, org, direction, t0=1e30):
         org = np.ascontiguousarray(org, np.float64); direction = np.ascontiguousarray(direction, np.float64)

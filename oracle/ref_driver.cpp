@@ -154,7 +154,7 @@ static int RunKat(const char *in, const char *out) {
 
 int main(int argc, char **argv) {
     const char *sceneFile = NULL, *dir = NULL, *frameOut = NULL, *hitsOut = NULL, *sceneOut = NULL, *keys = NULL;
-    int W = 640, H = 640, threads = 8, timeFrames = 0;
+    int W = 640, H = 640, threads = 8, timeFrames = 0, warmFrames = 0;
     float forceReflection = -1;
     bool counters = false;
     if (argc == 4 && strcmp(argv[1], "--kat") == 0) return RunKat(argv[2], argv[3]);
@@ -171,6 +171,7 @@ int main(int argc, char **argv) {
         else if (ARG("--hits")) hitsOut = argv[++i];
         else if (ARG("--dump-scene")) sceneOut = argv[++i];
         else if (ARG("--time")) timeFrames = atoi(argv[++i]);
+        else if (ARG("--warmup")) warmFrames = atoi(argv[++i]);   // untimed frames before the --time frames
         else if (ARG("--keys")) keys = argv[++i];       // key presses fed to HandleKeyboard before the first frame
         else if (strcmp(argv[i], "--counters") == 0) counters = true;
         else if (strcmp(argv[i], "--verbose") == 0) ct_sdl_stub_quiet = 0;
@@ -267,6 +268,7 @@ int main(int argc, char **argv) {
 
     double best = ms, sum = 0;
     if (timeFrames > 0) {
+        for (int k = 0; k < warmFrames; k++) RenderFrame(&env, &scene, &bvh, false);
         for (int k = 0; k < timeFrames; k++) {
             double m = RenderFrame(&env, &scene, &bvh, false);
             sum += m;
