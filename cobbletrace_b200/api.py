@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "ct_gpu_abi_version", "ct_gpu_device_count", "ct_gpu_last_error", "ct_gpu_upload_scene", "ct_gpu_set_camera",
     "ct_gpu_set_stream", "ct_gpu_render_tile", "ct_gpu_readback", "ct_gpu_readback_hits", "ct_gpu_get_counters",
     "ct_gpu_last_tile_ms", "ct_gpu_sync", "ct_gpu_throttle", "ct_gpu_kernel_launches", "ct_gpu_last_tile_stages", "ct_gpu_framebuffer", "ct_gpu_gather_rows", "ct_gpu_debug_closest",
-    "ct_gpu_debug_primitives", "ct_gpu_shutdown",
+    "ct_gpu_debug_primitives", "ct_gpu_shutdown", "ct_gpu_set_option", "ct_gpu_overflow_stats",
 ]
 
 
@@ -104,6 +104,8 @@ def load_library(path: Optional[str] = None):
     L.ct_gpu_debug_closest.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp]
     L.ct_gpu_debug_primitives.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ct_gpu_shutdown.argtypes = [C.c_int]
+    L.ct_gpu_set_option.argtypes = [C.c_char_p, C.c_longlong]
+    L.ct_gpu_overflow_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     if path == GPU_LIB:
         _lib = L
     return L
@@ -200,8 +202,8 @@ class GpuRenderer:
 
     def last_tile_stages(self):
         """[(kernel name, depth, ms)] of the last tile (needs CT_FLAG_STAGE_TIMING)."""
-        ms = (C.c_float * 40)(); names = (C.c_char_p * 40)(); depth = (C.c_int * 40)()
-        n = _check(self.L, self.L.ct_gpu_last_tile_stages(self.device, 40, ms, names, depth))
+        ms = (C.c_float * 80)(); names = (C.c_char_p * 80)(); depth = (C.c_int * 80)()
+        n = _check(self.L, self.L.ct_gpu_last_tile_stages(self.device, 80, ms, names, depth))
         return [(names[i].decode(), int(depth[i]), float(ms[i])) for i in range(n)]
 
     def counters(self, reset: bool = False):
@@ -251,8 +253,20 @@ class GpuRenderer:
         _check(self.L, self.L.ct_gpu_debug_primitives(self.device, n, _ptr(o), _ptr(d), _ptr(rt), _ptr(tri), _ptr(mn), _ptr(mx), _ptr(th), _ptr(bh)))
         return th, bh, rt
 
+    def overflow_stats(self):
+        """(rays parked for the breadth-first overflow kernel, rays finished in place because the buffer was full)."""
+        a = C.c_uint64(); b = C.c_uint64()
+        _check(self.L, self.L.ct_gpu_overflow_stats(self.device, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def shutdown(self):
         _check(self.L, self.L.ct_gpu_shutdown(self.device))
+
+
+def set_option(name: str, value: int) -> None:
+    """ct_gpu_set_option: library-wide knob applied by the next upload (e.g. "traversal_budget")."""
+    L = load_library()
+    _check(L, L.ct_gpu_set_option(name.encode(), int(value)))
 
 
 def device_count() -> int:

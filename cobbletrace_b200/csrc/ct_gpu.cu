@@ -6,10 +6,17 @@
 // becomes a wavefront of persistent-warp kernels over SoA path state in HBM:
 //
 //   k_primary   raygen (CanvasToViewport :186) + closest-hit DFS            -> hit records
-//   k_shade     NormalOfSceneObject :329 + ComputeLighting :275 (any-hit shadow rays with early
-//               exit) + HsvToColor; emits the reflection ray (:372-373) into the next queue
+//   k_shadow    ComputeLighting's shadow rays (:288-306), one work item per (light, path) in
+//               light-major order (a warp = 32 neighbouring paths, same light); any-hit DFS
+//               with early exit                                              -> occlusion bit masks
+//   k_shade     NormalOfSceneObject :329 + ComputeLighting :275 accumulation (lights in file
+//               order, fp32) + HsvToColor; emits the reflection ray (:372-373) into the next queue
 //   k_bounce    the reference's degenerate t=0 reflection rays (:373): first barycentric
 //               pass in DFS order                               -> hit records
+//   k_overflow  rays whose DFS exceeds a visit budget (e.g. shadow rays cast from a shading point
+//               4.3e9 units away after a reflection "miss": fp32 slab quotients all round to the
+//               same value and EVERY box passes) are parked by k_shadow / k_bounce and traversed
+//               here by the whole grid, breadth first (cooperative launch, one grid.sync per level)
 //   k_resolve   unwinds the per-pixel blend chain (:375-379) and stores 0x00BBGGRR pixels
 //
 // Arithmetic is the reference's mixed fp64/fp32, reproduced exactly (ct_exact.cuh).
@@ -17,6 +24,7 @@
 #include "../../include/ct_gpu.h"
 #include "ct_exact.cuh"
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -26,6 +34,8 @@
 #include <mutex>
 #include <vector>
 
+namespace cg = cooperative_groups;
+
 namespace {
 
 using namespace ct;
@@ -33,7 +43,10 @@ using namespace ct;
 constexpr int kStackMax = 96;        // DFS stack entries per ray (tree depth limit, checked at upload)
 constexpr int kMaxDevices = 16;
 constexpr int kBlockThreads = 128;   // 4 warps per CTA
+constexpr int kOvfThreads = 256;     // k_overflow CTA
+constexpr int kMaxLaunches = 80;     // launches of one tile (work cursors / stage events)
 constexpr uint32_t kNoPos = 0xffffffffu;
+constexpr uint32_t kDefaultBudget = 2048;   // node visits + triangle tests before a ray is parked for k_overflow
 
 // ---- device-side scene layout (SoA arrays in HBM, uploaded once) -----------------------------------
 struct __align__(16) DevNode {       // 64 B: one node = two 32-B sectors
@@ -46,13 +59,23 @@ struct __align__(16) DevTri {        // 80 B, stored in LEAF order (position = s
     uint32_t orig, pad;              // original triangle id (= closestIndex of the reference)
 };
 struct DevLight { int32_t type; float intensity; double pos[3]; double dir[3]; };
+struct DevShadowLight { int32_t type; uint32_t index; double v[3]; };   // non-ambient lights, file order; index = light number
+struct __align__(16) OvfRay {        // a parked ray: 64 B
+    double o[3], d[3];
+    uint32_t target;                 // kAnyHit: word of the occlusion mask; kFirstLine: queue slot of the path
+    uint32_t bit;                    // kAnyHit: bit inside that word
+};
 
 struct DevSched {                    // zeroed at the start of every tile render
-    uint32_t work[32];               // dynamic-fetch cursors, one per launch of the tile
+    unsigned long long work[kMaxLaunches];   // dynamic-fetch cursors, one per launch of the tile
     uint32_t queue_count[16];        // paths alive at depth d (d >= 1)
+    uint32_t ovf_count[40];          // rays parked for the k_overflow launch 2*depth + {0: bounce, 1: shadow}
+    uint32_t bfs_count[3];           // frontier sizes of the breadth-first levels (rotating)
 };
 struct DevTotals {                   // running ray / test counters (never reset by a tile)
     unsigned long long rays_primary, rays_shadow, rays_reflection, box_tests, tri_tests;
+    unsigned long long rays_overflow;    // rays whose DFS ran past the budget
+    unsigned long long rays_in_place;    // ... of which the parking buffer was full: finished by their own thread
 };
 
 struct Params {
@@ -60,8 +83,11 @@ struct Params {
     const DevTri *tris;
     const ct_material *materials;    // by original id
     const DevLight *lights;
-    uint32_t n_lights, n_tri;
+    const DevShadowLight *slights;
+    uint32_t n_lights, n_slights, n_tri, n_nodes;
+    uint32_t occ_words;              // words of occlusion bits per path = ceil(n_lights / 32)
     uint32_t pos_of_tri0;            // leaf position of original triangle 0 (closestIndex default, raythread.cpp:205)
+    uint32_t budget;                 // see kDefaultBudget
     double cam[3], rot[9];
     float vp_w, vp_h, vp_d;
     int W, H, max_depth;
@@ -72,14 +98,19 @@ struct Params {
     uint32_t n_slots;                // blocks_x * ceil(n_y/4) * 32
     uint32_t cap;                    // capacity of every per-slot array
     // per-slot path state
-    float *hit0_t; uint32_t *hit0_pos;           // depth-0 hit (pos = kNoPos-1.. see below)
+    float *hit0_t; uint32_t *hit0_pos;           // depth-0 hit records, by slot (pos = kNoPos: miss)
     float *hitb_t; uint32_t *hitb_pos;           // depth>=1 hits, by queue slot
     double *ray_buf[2];                          // depth>=1 rays: 6 doubles per queue slot, ping-pong
     uint32_t *path_slot[2];                      // queue slot -> depth-0 slot, ping-pong
+    uint32_t *occ;                               // [path][occ_words] shadow-ray verdicts of the current depth, bit i = light i occluded
     uint32_t *stack_color; float *stack_refl;    // [depth][slot]
     uint8_t *term_level;                         // [slot] level at which the chain ended
     uint32_t *fb;                                // W*H
     uint32_t *dbg_found, *dbg_index; float *dbg_t;   // optional (CT_FLAG_KEEP_HITS), framebuffer layout
+    // parked rays + breadth-first frontier
+    OvfRay *ovf; uint32_t ovf_cap;
+    uint2 *frontier[2]; uint32_t frontier_cap;   // items (parked-ray index inside the batch, node)
+    uint32_t *ovf_result; uint32_t ovf_batch_max;
     DevSched *sched;
     DevTotals *tot;
 };
@@ -107,6 +138,7 @@ CT_DEV void load_tri(const DevTri *tris, uint32_t pos, V3 &p1, V3 &e1, V3 &e2) {
 }
 
 enum TraverseMode { kClosest, kAnyHit, kFirstLine };
+enum { kTravMiss = 0, kTravHit = 1, kTravOverBudget = -1 };
 
 // IntersectBVHClosest (bvh.cpp:198-222) as an explicit-stack DFS: left child first, right child
 // pushed, boxes tested at visit time against the CURRENT ray.t -- the reference's exact visit order,
@@ -116,18 +148,22 @@ enum TraverseMode { kClosest, kAnyHit, kFirstLine };
 //              the first triangle that lowers ray.t, i.e. bary pass and 1e-4 < t < 1e30.
 //   kFirstLine reflection rays (ray.t = 0, raythread.cpp:373): ray.t never changes, the first bary
 //              pass in DFS order becomes closestIndex with tclosest = 0, so stop there.
-// Returns: kAnyHit -> occluded; others -> ray.t != 1e30f ("found").
-template <TraverseMode MODE, bool COUNT>
-CT_DEV bool traverse(const Params &P, Ray &r, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+// Returns kTravHit/kTravMiss: kAnyHit -> occluded; others -> ray.t != 1e30f ("found").
+// With BUDGET, gives up with kTravOverBudget after P.budget node visits + triangle tests; the caller parks
+// the ray for k_overflow (both early-exit modes have an order-independent answer, see k_overflow).
+template <TraverseMode MODE, bool COUNT, bool BUDGET>
+CT_DEV int traverse(const Params &P, Ray &r, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
     uint32_t stack[kStackMax];
     int sp = 0;
     uint32_t node = 0;
+    uint32_t spent = 0;
     tclosest = kFinf;          // raythread.cpp:204
     closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
     while (true) {
         DevNode nd;
         load_node(P.nodes, node, nd);
         if (COUNT) lc.box++;
+        if (BUDGET) { spent += 1u + nd.count; if (spent > P.budget) return kTravOverBudget; }
         if (intersect_aabb(r, nd.bmin, nd.bmax)) {
             if (nd.count > 0) {
                 for (uint32_t i = 0; i < nd.count; i++) {
@@ -138,10 +174,10 @@ CT_DEV bool traverse(const Params &P, Ray &r, float &tclosest, uint32_t &closest
                     float t;
                     if (intersect_triangle(r, p1, e1, e2, &t)) {
                         if (MODE == kAnyHit) {
-                            if (t > kEps && t < kRayTInit) return true;
+                            if (t > kEps && t < kRayTInit) return kTravHit;
                         } else if (MODE == kFirstLine) {
                             closest_pos = pos; tclosest = 0.0f;
-                            return true;
+                            return kTravHit;
                         } else {
                             if (t > kEps) r.t = macro_min(r.t, t);                     // bvh.cpp:161
                             if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
@@ -159,8 +195,8 @@ CT_DEV bool traverse(const Params &P, Ray &r, float &tclosest, uint32_t &closest
         if (sp == 0) break;
         node = stack[--sp];
     }
-    if (MODE == kAnyHit) return false;
-    return r.t != kRayTInit;
+    if (MODE == kAnyHit) return kTravMiss;
+    return r.t != kRayTInit ? kTravHit : kTravMiss;
 }
 
 // Primary ray of canvas pixel (x,y): CanvasToViewport (raythread.cpp:186-194) * camera.rotation (mymath.h:68-75)
@@ -174,7 +210,6 @@ CT_DEV Ray primary_ray(const Params &P, int x, int y) {
     r.d.y = __dadd_rn(__dadd_rn(__dmul_rn(vx, P.rot[1]), __dmul_rn(vy, P.rot[4])), __dmul_rn(vz, P.rot[7]));
     r.d.z = __dadd_rn(__dadd_rn(__dmul_rn(vx, P.rot[2]), __dmul_rn(vy, P.rot[5])), __dmul_rn(vz, P.rot[8]));
     r.t = kRayTInit;
-    ray_finish(r);
     return r;
 }
 
@@ -192,9 +227,9 @@ CT_DEV bool slot_pixel(const Params &P, uint32_t slot, int &x, int &y, int &fb_i
     return true;
 }
 
-CT_DEV uint32_t warp_fetch(uint32_t *cursor) {               // persistent warps pull 32 slots at a time
-    uint32_t base = 0;
-    if ((threadIdx.x & 31u) == 0) base = atomicAdd(cursor, 32u);
+CT_DEV unsigned long long warp_fetch(unsigned long long *cursor) {   // persistent warps pull 32 work items at a time
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31u) == 0) base = atomicAdd(cursor, 32ull);
     return __shfl_sync(0xffffffffu, base, 0);
 }
 
@@ -203,22 +238,60 @@ CT_DEV void warp_add(unsigned long long *dst, uint32_t v) {
     if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, (unsigned long long)v);
 }
 
+// The path with queue index q at `depth`: its ray (direction only for depth 0 is regenerated from the pixel),
+// its closest-hit record and its depth-0 slot.  False for padding lanes / untraced pixels.
+CT_DEV bool load_path(const Params &P, int depth, uint32_t q, uint32_t &slot, int &fbi, Ray &r, float &tc, uint32_t &pos) {
+    if (depth == 0) {
+        int x, y;
+        slot = q;
+        if (!slot_pixel(P, q, x, y, fbi)) return false;
+        r = primary_ray(P, x, y);
+        tc = P.hit0_t[q]; pos = P.hit0_pos[q];
+    } else {
+        const int cur = depth & 1;
+        slot = P.path_slot[cur][q];
+        fbi = 0;
+        const double2 *rb = reinterpret_cast<const double2 *>(P.ray_buf[cur] + 6ull * q);
+        double2 a = rb[0], b = rb[1], c = rb[2];
+        r.o = {a.x, a.y, b.x}; r.d = {b.y, c.x, c.y}; r.t = 0.0f;
+        tc = P.hitb_t[q]; pos = P.hitb_pos[q];
+    }
+    return true;
+}
+
+CT_DEV void clear_occ(const Params &P, uint32_t q) {
+    for (uint32_t w = 0; w < P.occ_words; w++) P.occ[(size_t)q * P.occ_words + w] = 0u;
+}
+
+// Park a ray for k_overflow.  False when the buffer is full (the caller then finishes the ray in place).
+CT_DEV bool park_ray(const Params &P, int ovf_idx, const Ray &r, uint32_t target, uint32_t bit) {
+    uint32_t i = atomicAdd(&P.sched->ovf_count[ovf_idx], 1u);
+    if (i >= P.ovf_cap) { atomicAdd(&P.tot->rays_in_place, 1ull); return false; }
+    OvfRay &o = P.ovf[i];
+    o.o[0] = r.o.x; o.o[1] = r.o.y; o.o[2] = r.o.z;
+    o.d[0] = r.d.x; o.d[1] = r.d.y; o.d[2] = r.d.z;
+    o.target = target; o.bit = bit;
+    return true;
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads) k_primary(const __grid_constant__ Params P, int work_idx) {
     LocalCount lc;
     uint32_t n_rays = 0;
     while (true) {
-        uint32_t base = warp_fetch(&P.sched->work[work_idx]);
+        unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
         if (base >= P.n_slots) break;
-        uint32_t slot = base + (threadIdx.x & 31u);
+        uint32_t slot = (uint32_t)base + (threadIdx.x & 31u);
         int x, y, fbi;
         if (!slot_pixel(P, slot, x, y, fbi)) continue;
         Ray r = primary_ray(P, x, y);
+        ray_finish(r);
         float tc; uint32_t pos;
-        bool found = traverse<kClosest, COUNT>(P, r, tc, pos, lc);
+        bool found = traverse<kClosest, COUNT, false>(P, r, tc, pos, lc) == kTravHit;
         n_rays++;
         P.hit0_t[slot] = tc;
         P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
+        if (found) clear_occ(P, slot);
         if (P.dbg_found) {
             P.dbg_found[fbi] = found ? 1u : 0u;
             P.dbg_index[fbi] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
@@ -229,33 +302,58 @@ __global__ void __launch_bounds__(kBlockThreads) k_primary(const __grid_constant
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
 }
 
-// TraceRay body after the closest hit (raythread.cpp:359-373) for the paths alive at `depth`.
+// ComputeLighting's shadow rays (raythread.cpp:288-306) for the paths alive at `depth`.  Work item =
+// (shadow light j, path q), j-major, so the 32 lanes of a warp trace 32 neighbouring shading points towards
+// the same light.  Verdicts go to the per-path occlusion mask read by k_shade.
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__ Params P, int depth, int work_idx) {
+__global__ void __launch_bounds__(kBlockThreads) k_shadow(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
     LocalCount lc;
-    uint32_t n_shadow = 0, n_refl = 0;
+    uint32_t n_shadow = 0, n_parked = 0;
     const uint32_t n = depth == 0 ? P.n_slots : P.sched->queue_count[depth];
-    const int cur = depth & 1, nxt = cur ^ 1;
+    const unsigned long long n_pad = ((unsigned long long)n + 31ull) & ~31ull;
+    const unsigned long long total = n_pad * P.n_slights;
     while (true) {
-        uint32_t base = warp_fetch(&P.sched->work[work_idx]);
-        if (base >= n) break;
-        uint32_t q = base + (threadIdx.x & 31u);
-        bool active = q < n;
-        uint32_t slot = q; int fbi = 0;
-        Ray r; float tc = 0.0f; uint32_t pos = kNoPos;
-        if (active) {
-            if (depth == 0) {
-                int x, y;
-                active = slot_pixel(P, slot, x, y, fbi);
-                if (active) { r = primary_ray(P, x, y); tc = P.hit0_t[slot]; pos = P.hit0_pos[slot]; }
-            } else {
-                slot = P.path_slot[cur][q];
-                const double2 *rb = reinterpret_cast<const double2 *>(P.ray_buf[cur] + 6ull * q);
-                double2 a = rb[0], b = rb[1], c = rb[2];
-                r.o = {a.x, a.y, b.x}; r.d = {b.y, c.x, c.y};
-                tc = P.hitb_t[q]; pos = P.hitb_pos[q];
-            }
+        unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= total) break;
+        uint32_t j = (uint32_t)(base / n_pad);
+        uint32_t q = (uint32_t)(base - (unsigned long long)j * n_pad) + (threadIdx.x & 31u);
+        if (q >= n) continue;
+        uint32_t slot, pos; int fbi; Ray r; float tc;
+        if (!load_path(P, depth, q, slot, fbi, r, tc, pos) || pos == kNoPos) continue;
+        const DevShadowLight &L = P.slights[j];
+        V3 position = vadd(r.o, vscale((double)tc, r.d));                                  // :360
+        V3 lray = (L.type == CT_LIGHT_POINT) ? vsub(ld3(L.v), position) : ld3(L.v);        // :288 / :293
+        Ray sr; sr.o = position; sr.d = lray; sr.t = kRayTInit;                            // :304 no offset, no t<=1 test
+        ray_finish(sr);
+        float stc; uint32_t spos;
+        n_shadow++;
+        uint32_t word = q * P.occ_words + (L.index >> 5), bit = L.index & 31u;
+        int res = traverse<kAnyHit, COUNT, true>(P, sr, stc, spos, lc);
+        if (res == kTravOverBudget) {
+            n_parked++;
+            if (park_ray(P, ovf_idx, sr, word, bit)) continue;
+            res = traverse<kAnyHit, COUNT, false>(P, sr, stc, spos, lc);
         }
+        if (res == kTravHit) atomicOr(&P.occ[word], 1u << bit);
+    }
+    warp_add(&P.tot->rays_shadow, n_shadow);
+    warp_add(&P.tot->rays_overflow, n_parked);
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
+}
+
+// TraceRay body after the closest hit (raythread.cpp:359-373) for the paths alive at `depth`; the shadow
+// verdicts were computed by k_shadow (+ k_overflow).
+__global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__ Params P, int depth, int work_idx) {
+    uint32_t n_refl = 0;
+    const uint32_t n = depth == 0 ? P.n_slots : P.sched->queue_count[depth];
+    const int nxt = (depth & 1) ^ 1;
+    while (true) {
+        unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= n) break;
+        uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
+        uint32_t slot = q, pos = kNoPos; int fbi = 0;
+        Ray r; float tc = 0.0f;
+        bool active = q < n && load_path(P, depth, q, slot, fbi, r, tc, pos);
         bool emit = false;
         V3 position = {0, 0, 0}, rdir = {0, 0, 0};
         if (active) {
@@ -275,16 +373,15 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
                 V3 view = vneg(r.d);
                 // ---- ComputeLighting :275-327, lights in file order, fp32 accumulator
                 float intensity = 0.0f;
+                const uint32_t *occ = P.occ + (size_t)q * P.occ_words;
+                uint32_t occ_word = 0;
                 for (uint32_t i = 0; i < P.n_lights; i++) {
                     const DevLight &L = P.lights[i];
                     float li = L.intensity;
+                    if ((i & 31u) == 0) occ_word = occ[i >> 5];
                     if (L.type == CT_LIGHT_AMBIENT) { intensity = __fadd_rn(intensity, li); continue; }
+                    if ((occ_word >> (i & 31u)) & 1u) continue;              // :306 shadowed
                     V3 lray = (L.type == CT_LIGHT_POINT) ? vsub(ld3(L.pos), position) : ld3(L.dir);
-                    Ray sr; sr.o = position; sr.d = lray; sr.t = kRayTInit;  // :304 no offset, no t<=1 test
-                    ray_finish(sr);
-                    float stc; uint32_t spos;
-                    n_shadow++;
-                    if (traverse<kAnyHit, COUNT>(P, sr, stc, spos, lc)) continue;
                     float ndl = vdot(normal, lray);                          // :310
                     if (ndl > 0.0f)
                         intensity = __fadd_rn(intensity, __fdiv_rn(__fmul_rn(li, ndl), __fmul_rn(vmag(normal), vmag(lray))));
@@ -328,21 +425,20 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
             }
         }
     }
-    warp_add(&P.tot->rays_shadow, n_shadow);
     warp_add(&P.tot->rays_reflection, n_refl);
-    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
 }
 
 // Closest "hit" of the reflection rays {position, reflected, t = 0} (raythread.cpp:373).
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads) k_bounce(const __grid_constant__ Params P, int depth, int work_idx) {
+__global__ void __launch_bounds__(kBlockThreads) k_bounce(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
     LocalCount lc;
+    uint32_t n_parked = 0;
     const uint32_t n = P.sched->queue_count[depth];
     const int cur = depth & 1;
     while (true) {
-        uint32_t base = warp_fetch(&P.sched->work[work_idx]);
+        unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
         if (base >= n) break;
-        uint32_t q = base + (threadIdx.x & 31u);
+        uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
         if (q >= n) continue;
         const double2 *rb = reinterpret_cast<const double2 *>(P.ray_buf[cur] + 6ull * q);
         double2 a = rb[0], b = rb[1], c = rb[2];
@@ -350,9 +446,114 @@ __global__ void __launch_bounds__(kBlockThreads) k_bounce(const __grid_constant_
         r.o = {a.x, a.y, b.x}; r.d = {b.y, c.x, c.y}; r.t = 0.0f;
         ray_finish(r);
         float tc; uint32_t pos;
-        traverse<kFirstLine, COUNT>(P, r, tc, pos, lc);      // found is always true: 0 != 1e30f (:227)
+        clear_occ(P, q);
+        int res = traverse<kFirstLine, COUNT, true>(P, r, tc, pos, lc);      // found is always true: 0 != 1e30f (:227)
+        if (res == kTravOverBudget) {
+            n_parked++;
+            if (park_ray(P, ovf_idx, r, q, 0u)) continue;
+            traverse<kFirstLine, COUNT, false>(P, r, tc, pos, lc);
+        }
         P.hitb_t[q] = tc;
         P.hitb_pos[q] = (pos == kNoPos) ? P.pos_of_tri0 : pos;
+    }
+    warp_add(&P.tot->rays_overflow, n_parked);
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
+}
+
+// Parked rays (see the file header).  Both early-exit modes have an answer that does not depend on the visit
+// order, because ray.t never changes before the exit, so the set of boxes that pass is fixed:
+//   kAnyHit     occluded  <=>  SOME triangle reachable through passing boxes has a bary pass with 1e-4 < t < 1e30;
+//   kFirstLine  closestIndex = the bary-passing reachable triangle that the DFS meets first = the one with the
+//               smallest leaf position (BuildBVH hands the left child the lower part of the parent's index range,
+//               bvh.cpp:70-97, so leaf positions increase along the DFS).
+// The whole grid walks the tree breadth first, a batch of rays at a time: one frontier item = (ray, node), one
+// grid.sync per level, the frontier ping-pongs between two HBM buffers sized for the widest possible level.
+template <TraverseMode MODE, bool COUNT>
+__global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant__ Params P, int ovf_idx) {
+    const uint32_t n = min(P.sched->ovf_count[ovf_idx], P.ovf_cap);
+    if (n == 0) return;                                   // uniform over the grid: nobody reaches a grid.sync
+    cg::grid_group grid = cg::this_grid();
+    LocalCount lc;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t per_ray = P.n_nodes / 2u + 2u;         // widest level of one ray
+    const uint32_t batch = max(1u, min(P.frontier_cap / per_ray, P.ovf_batch_max));
+    volatile uint32_t *cnt = P.sched->bfs_count;
+    for (uint32_t b0 = 0; b0 < n; b0 += batch) {
+        const uint32_t bn = min(batch, n - b0);
+        for (uint32_t i = tid; i < bn; i += n_threads) {
+            P.frontier[0][i] = make_uint2(i, 0u);
+            P.ovf_result[i] = (MODE == kAnyHit) ? 0u : kNoPos;
+        }
+        if (tid == 0) { cnt[0] = bn; cnt[1] = 0u; cnt[2] = 0u; }
+        grid.sync();
+        for (uint32_t level = 0;; level++) {
+            const uint32_t cin = cnt[level % 3u];
+            if (cin == 0) break;
+            if (tid == 0) cnt[(level + 2u) % 3u] = 0u;    // nobody touches this one during this level
+            const uint2 *in = P.frontier[level & 1u];
+            uint2 *out = P.frontier[(level + 1u) & 1u];
+            uint32_t *cout = const_cast<uint32_t *>(&cnt[(level + 1u) % 3u]);
+            for (uint32_t base = tid - lane; base < cin; base += n_threads) {
+                const uint32_t i = base + lane;
+                bool expand = false;
+                uint2 item = make_uint2(0u, 0u);
+                uint32_t left = 0;
+                if (i < cin) {
+                    item = in[i];
+                    volatile uint32_t *res = P.ovf_result + item.x;
+                    if (!(MODE == kAnyHit && *res != 0u)) {
+                        const OvfRay &o = P.ovf[b0 + item.x];
+                        Ray r; r.o = ld3(o.o); r.d = ld3(o.d); r.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
+                        ray_finish(r);
+                        DevNode nd;
+                        load_node(P.nodes, item.y, nd);
+                        if (COUNT) lc.box++;
+                        if (intersect_aabb(r, nd.bmin, nd.bmax)) {
+                            if (nd.count > 0) {
+                                for (uint32_t k = 0; k < nd.count; k++) {
+                                    uint32_t pos = nd.first + k;
+                                    V3 p1, e1, e2;
+                                    load_tri(P.tris, pos, p1, e1, e2);
+                                    if (COUNT) lc.tri++;
+                                    float t;
+                                    if (!intersect_triangle(r, p1, e1, e2, &t)) continue;
+                                    if (MODE == kAnyHit) { if (t > kEps && t < kRayTInit) { *res = 1u; break; } }
+                                    else { atomicMin(P.ovf_result + item.x, pos); break; }   // later positions of this leaf are larger
+                                }
+                            } else {
+                                expand = true; left = nd.left;
+                            }
+                        }
+                    }
+                }
+                uint32_t mask = __ballot_sync(0xffffffffu, expand);
+                if (mask) {
+                    uint32_t leader = __ffs(mask) - 1, obase = 0;
+                    if (lane == leader) obase = atomicAdd(cout, 2u * (uint32_t)__popc(mask));
+                    obase = __shfl_sync(0xffffffffu, obase, leader);
+                    if (expand) {
+                        uint32_t oi = obase + 2u * (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                        if (oi + 1u < P.frontier_cap) {           // cannot trigger: the batch is sized for the widest level
+                            out[oi] = make_uint2(item.x, left);
+                            out[oi + 1u] = make_uint2(item.x, left + 1u);
+                        }
+                    }
+                }
+            }
+            grid.sync();
+        }
+        for (uint32_t i = tid; i < bn; i += n_threads) {
+            const OvfRay &o = P.ovf[b0 + i];
+            uint32_t res = P.ovf_result[i];
+            if (MODE == kAnyHit) {
+                if (res) atomicOr(&P.occ[o.target], 1u << o.bit);
+            } else {
+                P.hitb_t[o.target] = (res == kNoPos) ? kFinf : 0.0f;          // raythread.cpp:204 / first line pass
+                P.hitb_pos[o.target] = (res == kNoPos) ? P.pos_of_tri0 : res;
+            }
+        }
+        grid.sync();                                      // results and frontier are reused by the next batch
     }
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
 }
@@ -380,8 +581,8 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
     r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = t0[i];
     ray_finish(r);
     LocalCount lc; float tc; uint32_t pos; bool f;
-    if (r.t == 0.0f) f = traverse<kFirstLine, false>(P, r, tc, pos, lc);
-    else f = traverse<kClosest, false>(P, r, tc, pos, lc);
+    if (r.t == 0.0f) f = traverse<kFirstLine, false, false>(P, r, tc, pos, lc) == kTravHit;
+    else f = traverse<kClosest, false, false>(P, r, tc, pos, lc) == kTravHit;
     if (found) found[i] = f ? 1u : 0u;
     if (index) index[i] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
     if (tclosest) tclosest[i] = tc;
@@ -435,19 +636,23 @@ struct DeviceState {
     unsigned long long tiles_submitted = 0;
     int row_lo = 0, row_hi = 0;      // hull of framebuffer rows rendered since upload (readback clips to it)
     unsigned long long launches = 0; // kernels launched since upload / reset
-    cudaEvent_t stage_ev[40] = {};   // CT_FLAG_STAGE_TIMING: boundaries between the launches of the last tile
-    const char *stage_name[40] = {};
-    int stage_depth[40] = {};
+    cudaEvent_t stage_ev[kMaxLaunches + 1] = {};   // CT_FLAG_STAGE_TIMING: boundaries between the launches of the last tile
+    const char *stage_name[kMaxLaunches] = {};
+    int stage_depth[kMaxLaunches] = {};
+    bool can_overflow = false;       // some traversal could exceed the visit budget: k_overflow launches are needed
+    int ovf_grid[4] = {};            // co-resident grid of the k_overflow instantiations [mode][count]
     int n_stages = 0;
     bool timed = false;
     std::vector<void *> allocs;
     ct_ray_counters snapshot{};      // totals at the end of the previous counted tile
+    unsigned long long rays_overflow = 0, rays_in_place = 0;   // DevTotals' overflow counters as of the last read_totals
     // rows rendered so far (framebuffer rows), for readback clipping
     int col_lo = 0, col_hi = 0;
 };
 
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mutex;
+long long g_budget_option = 0;       // ct_gpu_set_option("traversal_budget"); 0 = default
 
 int check_device(int device) {
     int n = 0;
@@ -515,6 +720,7 @@ int read_totals(DeviceState &s, ct_ray_counters *out) {   // synchronises the st
     CU(cudaStreamSynchronize(s.stream));
     out->rays_primary = h.rays_primary; out->rays_shadow = h.rays_shadow; out->rays_reflection = h.rays_reflection;
     out->box_tests = h.box_tests; out->tri_tests = h.tri_tests;
+    s.rays_overflow = h.rays_overflow; s.rays_in_place = h.rays_in_place;
     return CT_OK;
 }
 
@@ -559,6 +765,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     CU(cudaEventCreate(&s.ev1));
     for (cudaEvent_t &e : s.tile_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (d->flags & CT_FLAG_STAGE_TIMING) for (cudaEvent_t &e : s.stage_ev) CU(cudaEventCreate(&e));
+    s.p.budget = g_budget_option > 0 ? (uint32_t)std::min<long long>(g_budget_option, 1ll << 30) : kDefaultBudget;
     s.flags = d->flags;
 
     Params &p = s.p;
@@ -595,9 +802,24 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
         lights[i].type = d->lights[i].type; lights[i].intensity = d->lights[i].intensity;
         for (int a = 0; a < 3; a++) { lights[i].pos[a] = d->lights[i].position[a]; lights[i].dir[a] = d->lights[i].direction[a]; }
     }
-    DevNode *dn; DevTri *dt; ct_material *dm; DevLight *dl;
+    std::vector<DevShadowLight> slights;
+    for (uint32_t i = 0; i < d->n_lights; i++) {
+        if (d->lights[i].type == CT_LIGHT_AMBIENT) continue;            // raythread.cpp:284-286: no shadow ray
+        DevShadowLight sl{};
+        sl.type = d->lights[i].type; sl.index = i;
+        const double *v = (sl.type == CT_LIGHT_POINT) ? d->lights[i].position : d->lights[i].direction;   // :288 / :293 (every non-point light is directional)
+        for (int a = 0; a < 3; a++) sl.v[a] = v[a];
+        slights.push_back(sl);
+    }
+    p.n_slights = (uint32_t)slights.size();
+    p.occ_words = std::max<uint32_t>((d->n_lights + 31u) / 32u, 1u);
+    p.n_nodes = d->n_nodes;
+    DevNode *dn; DevTri *dt; ct_material *dm; DevLight *dl; DevShadowLight *dsl;
     TRY(dev_alloc(s, &dn, nodes.size())); TRY(dev_alloc(s, &dt, tris.size()));
     TRY(dev_alloc(s, &dm, d->n_triangles)); TRY(dev_alloc(s, &dl, lights.size()));
+    TRY(dev_alloc(s, &dsl, slights.size()));
+    if (!slights.empty()) CU(cudaMemcpy(dsl, slights.data(), slights.size() * sizeof(DevShadowLight), cudaMemcpyHostToDevice));
+    p.slights = dsl;
     CU(cudaMemcpy(dn, nodes.data(), nodes.size() * sizeof(DevNode), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dt, tris.data(), tris.size() * sizeof(DevTri), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dm, d->materials, (size_t)d->n_triangles * sizeof(ct_material), cudaMemcpyHostToDevice));
@@ -624,6 +846,25 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     TRY(dev_alloc(s, &p.hit0_t, p.cap)); TRY(dev_alloc(s, &p.hit0_pos, p.cap));
     TRY(dev_alloc(s, &p.stack_color, (size_t)p.cap * levels));
     TRY(dev_alloc(s, &p.term_level, p.cap, true));
+    TRY(dev_alloc(s, &p.occ, (size_t)p.cap * p.occ_words, true));
+    // parked rays: only needed when a DFS can run past the budget at all
+    s.can_overflow = (uint64_t)d->n_nodes + d->n_triangles > p.budget;
+    if (s.can_overflow) {
+        p.ovf_cap = 1u << 16;
+        p.ovf_batch_max = 1u << 16;
+        p.frontier_cap = std::max<uint32_t>(1u << 20, 2u * (d->n_nodes / 2u + 2u));
+        TRY(dev_alloc(s, &p.ovf, p.ovf_cap));
+        TRY(dev_alloc(s, &p.ovf_result, p.ovf_batch_max));
+        for (int b = 0; b < 2; b++) TRY(dev_alloc(s, &p.frontier[b], p.frontier_cap));
+        const void *fn[4] = {(const void *)k_overflow<kFirstLine, false>, (const void *)k_overflow<kFirstLine, true>,
+                             (const void *)k_overflow<kAnyHit, false>, (const void *)k_overflow<kAnyHit, true>};
+        for (int i = 0; i < 4; i++) {
+            int per_sm = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn[i], kOvfThreads, 0));
+            if (per_sm < 1) { free_device(s); return fail(CT_ERR_CUDA, "k_overflow does not fit on an SM"); }
+            s.ovf_grid[i] = s.n_sm * std::min(per_sm, 4);
+        }
+    }
     if (levels > 1) {
         TRY(dev_alloc(s, &p.hitb_t, p.cap)); TRY(dev_alloc(s, &p.hitb_pos, p.cap));
         TRY(dev_alloc(s, &p.stack_refl, (size_t)p.cap * levels));
@@ -682,28 +923,40 @@ int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *coun
     int work = 0;
     const bool stages = (s.flags & CT_FLAG_STAGE_TIMING) != 0;
     s.n_stages = 0;
+    if (stages) CU(cudaEventRecord(s.stage_ev[0], st));
     auto mark = [&](const char *name, int depth) -> int {          // called after each launch
         s.launches++;
-        if (!stages) return CT_OK;
-        if (s.n_stages == 0) CU(cudaEventRecord(s.stage_ev[0], st));    // (re-recorded below, before the first launch)
+        if (!stages || s.n_stages >= kMaxLaunches) return CT_OK;
         s.stage_name[s.n_stages] = name; s.stage_depth[s.n_stages] = depth;
         s.n_stages++;
         CU(cudaEventRecord(s.stage_ev[s.n_stages], st));
         return CT_OK;
     };
-    if (stages) CU(cudaEventRecord(s.stage_ev[0], st));
+    auto overflow = [&](int mode_anyhit, int ovf_idx, int depth) -> int {   // parked rays of the launch just made
+        if (!s.can_overflow) return CT_OK;
+        void *args[] = {(void *)&pk, (void *)&ovf_idx};
+        const void *fn = mode_anyhit ? (count ? (const void *)k_overflow<kAnyHit, true> : (const void *)k_overflow<kAnyHit, false>)
+                                     : (count ? (const void *)k_overflow<kFirstLine, true> : (const void *)k_overflow<kFirstLine, false>);
+        CU(cudaLaunchCooperativeKernel(fn, dim3(s.ovf_grid[mode_anyhit * 2 + (count ? 1 : 0)]), dim3(kOvfThreads), args, 0, st));
+        return mark(mode_anyhit ? "overflow_shadow" : "overflow_bounce", depth);
+    };
     if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(pk, work++);
     else k_primary<false><<<grid, kBlockThreads, 0, st>>>(pk, work++);
-    if (stages) { s.launches++; s.stage_name[0] = "primary"; s.stage_depth[0] = 0; s.n_stages = 1; CU(cudaEventRecord(s.stage_ev[1], st)); }
-    else s.launches++;
+    TRY(mark("primary", 0));
     for (int d = 0; d <= depth_max; d++) {
         if (d > 0) {
-            if (count) k_bounce<true><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
-            else k_bounce<false><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
+            if (count) k_bounce<true><<<grid, kBlockThreads, 0, st>>>(pk, d, work++, 2 * d);
+            else k_bounce<false><<<grid, kBlockThreads, 0, st>>>(pk, d, work++, 2 * d);
             TRY(mark("bounce", d));
+            TRY(overflow(0, 2 * d, d));
         }
-        if (count) k_shade<true><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
-        else k_shade<false><<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
+        if (pk.n_slights > 0) {
+            if (count) k_shadow<true><<<grid, kBlockThreads, 0, st>>>(pk, d, work++, 2 * d + 1);
+            else k_shadow<false><<<grid, kBlockThreads, 0, st>>>(pk, d, work++, 2 * d + 1);
+            TRY(mark("shadow", d));
+            TRY(overflow(1, 2 * d + 1, d));
+        }
+        k_shade<<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
         TRY(mark("shade", d));
     }
     if (depth_max > 0) { k_resolve<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("resolve", 0)); }
@@ -727,6 +980,27 @@ int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *coun
         counters->tri_tests = now.tri_tests - s.snapshot.tri_tests;
         s.snapshot = now;
     }
+    return CT_OK;
+}
+
+int ct_gpu_set_option(const char *name, long long value) {
+    if (!name) return fail(CT_ERR_INVALID, "NULL option name");
+    if (!strcmp(name, "traversal_budget")) {
+        if (value < 0) return fail(CT_ERR_INVALID, "traversal_budget must be >= 0 (0 = default)");
+        g_budget_option = value;
+        return CT_OK;
+    }
+    return fail(CT_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int ct_gpu_overflow_stats(int device, uint64_t *parked, uint64_t *finished_in_place) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    ct_ray_counters tmp;
+    TRY(read_totals(s, &tmp));
+    if (parked) *parked = s.rays_overflow;
+    if (finished_in_place) *finished_in_place = s.rays_in_place;
     return CT_OK;
 }
 

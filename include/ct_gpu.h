@@ -151,11 +151,23 @@ int ct_gpu_last_tile_ms(int device, float *ms);
 int ct_gpu_kernel_launches(int device, uint64_t *out, int reset);
 
 /* With CT_FLAG_STAGE_TIMING: device time of every kernel of the most recent tile, in launch order.
- * names[i] points at a static string ("primary", "shade", "bounce", "resolve"); depth[i] is the path depth.
- * Returns the number of launches (fills at most `max`). Synchronises. */
+ * names[i] points at a static string ("primary", "shadow", "shade", "bounce", "overflow_shadow",
+ * "overflow_bounce", "resolve"); depth[i] is the path depth.
+ * Returns the number of launches (fills at most `max`; a tile never has more than 80). Synchronises. */
 int ct_gpu_last_tile_stages(int device, int max, float *ms, const char **names, int *depth);
 
 int ct_gpu_sync(int device);
+
+/* Library-wide tuning knobs, applied by the next ct_gpu_upload_scene.  Names:
+ *   "traversal_budget"  node visits + triangle tests a shadow / reflection ray may spend in its own thread
+ *                       before it is parked and traversed breadth-first by the whole grid (0 = default 2048).
+ *                       Results never depend on it; tests set it to 1 to push every ray through that path. */
+int ct_gpu_set_option(const char *name, long long value);
+
+/* Rays parked so far on `device` since upload (shadow and reflection rays whose DFS ran past the budget, e.g. the
+ * shadow rays of a shading point 2^32 ray lengths away after a reflection miss), and how many
+ * of them found the parking buffer full and were finished by their own thread.  Synchronises. */
+int ct_gpu_overflow_stats(int device, uint64_t *parked, uint64_t *finished_in_place);
 
 /* Blocks until at most `max_in_flight` of the submitted tiles are unfinished (0 == ct_gpu_sync).  Lets a
  * boss keep a GPU fed while tile stealing still follows real progress. */
