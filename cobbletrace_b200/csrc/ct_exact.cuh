@@ -46,7 +46,7 @@ CT_DEV float macro_max(float a, float b) { return (a > b) ? a : b; }
 
 struct Ray {
     V3 o, d;        // ray_t scenefile.h:104-108
-    V3 rd;          // 1/d per axis (correctly rounded), only used by the guarded slab quotient
+    V3 rd;          // 1/d per axis (correctly rounded), only used by box_times' guarded fast path
     float t;
     bool exact_div; // some |d| is so large/small that 1/d is inf/denormal: always divide
 };
@@ -63,39 +63,76 @@ CT_DEV void ray_finish(Ray &r) {
     r.exact_div = odd(r.d.x) || odd(r.d.y) || odd(r.d.z);
 }
 
-// Cold path: the literal (b - o) / d of bvh.cpp:166-175.
-__device__ __noinline__ float slab_quotient_exact(double s, double d) { return __double2float_rn(__ddiv_rn(s, d)); }
+// mymath.h:11-17 on doubles (same NaN behaviour as the float macros).
+CT_DEV double macro_min_d(double a, double b) { return (a < b) ? a : b; }
+CT_DEV double macro_max_d(double a, double b) { return (a > b) ? a : b; }
 
-// float( (b - o) / d ) without an fp64 division on the hot path.
-//   q' = s * fl(1/d) differs from fl(s/d) by at most a few fp64 ulps, so float(q') can differ from the
-//   reference's float only when q' lies within those few ulps of a float rounding boundary (the 29
-//   dropped mantissa bits ~ 0x10000000) or when the float result is subnormal.  Those cases (probability
-//   ~2^-25 per quotient) take the true division; everything else is proven equal.
-CT_DEV float slab_quotient(double b, double o, double d, double rd, bool exact_div) {
-    double s = __dsub_rn(b, o);
-    double q = __dmul_rn(s, rd);
-    uint32_t lo = (uint32_t)__double2loint(q);
-    uint32_t hi = (uint32_t)__double2hiint(q) & 0x7fffffffu;
-    bool near_mid = ((lo & 0x1fffffffu) - 0x0ffffff0u) <= 0x20u;          // dropped bits within +-16 of the midpoint
-    bool tiny = (hi < 0x38200000u) && ((hi | lo) != 0u);                    // |q| < 2^-125 and q != 0
-    if (near_mid | tiny | exact_div) return slab_quotient_exact(s, d);
-    return __double2float_rn(q);
+// Cold path: the literal IntersectAABB arithmetic of bvh.cpp:166-177 -- six fp64 divisions, each rounded to
+// float on assignment, macro min/max in float.
+struct BoxTimes { float tmin, tmax; };
+__device__ __noinline__ BoxTimes box_times_exact(double ox, double oy, double oz, double dx, double dy, double dz,
+                                                 double nx, double ny, double nz, double mx, double my, double mz) {
+    float tx1 = __double2float_rn(__ddiv_rn(__dsub_rn(nx, ox), dx));
+    float tx2 = __double2float_rn(__ddiv_rn(__dsub_rn(mx, ox), dx));
+    float tmin = macro_min(tx1, tx2);
+    float tmax = macro_max(tx1, tx2);
+    float ty1 = __double2float_rn(__ddiv_rn(__dsub_rn(ny, oy), dy));
+    float ty2 = __double2float_rn(__ddiv_rn(__dsub_rn(my, oy), dy));
+    tmin = macro_max(tmin, macro_min(ty1, ty2));
+    tmax = macro_min(tmax, macro_max(ty1, ty2));
+    float tz1 = __double2float_rn(__ddiv_rn(__dsub_rn(nz, oz), dz));
+    float tz2 = __double2float_rn(__ddiv_rn(__dsub_rn(mz, oz), dz));
+    tmin = macro_max(tmin, macro_min(tz1, tz2));
+    tmax = macro_min(tmax, macro_max(tz1, tz2));
+    return {tmin, tmax};
+}
+
+// True when float(x) may differ from float(y) for some y within a few fp64 ulps of x: x sits within +-16 units of
+// a float rounding boundary (the 29 dropped mantissa bits ~ 0x10000000), or x is non-zero with |x| < 2^-125 (float
+// subnormal range, where the boundaries are elsewhere and the fp64 product may itself have lost bits).
+CT_DEV bool float_rounding_unsafe(double x) {
+    uint32_t lo = (uint32_t)__double2loint(x);
+    uint32_t hi = (uint32_t)__double2hiint(x) & 0x7fffffffu;
+    bool near_mid = ((lo & 0x1fffffffu) - 0x0ffffff0u) <= 0x20u;
+    bool tiny = (hi < 0x38200000u) && ((hi | lo) != 0u);
+    return near_mid | tiny;
+}
+
+// The two floats IntersectAABB (bvh.cpp:165-177) compares: tmin and tmax of the slab test, bit-exact (up to
+// the sign of a zero, which no comparison sees).
+//
+// The reference rounds each of the six quotients (b - o)/d to float and then takes macro min/max in float.
+// Rounding to float is monotonic and NaN-preserving, so selecting with the same macros on the unrounded
+// doubles and rounding the two survivors gives the same float VALUES: whenever the double comparison picks
+// a different operand than the float comparison would, the two operands round to the same float.
+// The hot path also replaces the fp64 division by a multiplication with the correctly rounded 1/d: every
+// quotient, and therefore (min/max being monotone selections) each survivor, is then within a few fp64 ulps
+// of the reference's double.  float() of a survivor can differ from the reference only when it lies that
+// close to a float rounding boundary (probability ~2^-24 per test); those cases, and rays whose 1/d leaves the
+// normal range, take box_times_exact().  Everything else is proven equal.
+CT_DEV void box_times(const Ray &r, const double bmin[3], const double bmax[3], float &tmin_f, float &tmax_f) {
+    double x1 = __dmul_rn(__dsub_rn(bmin[0], r.o.x), r.rd.x), x2 = __dmul_rn(__dsub_rn(bmax[0], r.o.x), r.rd.x);
+    double y1 = __dmul_rn(__dsub_rn(bmin[1], r.o.y), r.rd.y), y2 = __dmul_rn(__dsub_rn(bmax[1], r.o.y), r.rd.y);
+    double z1 = __dmul_rn(__dsub_rn(bmin[2], r.o.z), r.rd.z), z2 = __dmul_rn(__dsub_rn(bmax[2], r.o.z), r.rd.z);
+    double tmin = macro_min_d(x1, x2);
+    double tmax = macro_max_d(x1, x2);
+    tmin = macro_max_d(tmin, macro_min_d(y1, y2));
+    tmax = macro_min_d(tmax, macro_max_d(y1, y2));
+    tmin = macro_max_d(tmin, macro_min_d(z1, z2));
+    tmax = macro_min_d(tmax, macro_max_d(z1, z2));
+    if (float_rounding_unsafe(tmin) | float_rounding_unsafe(tmax) | r.exact_div) {
+        BoxTimes e = box_times_exact(r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]);
+        tmin_f = e.tmin; tmax_f = e.tmax;
+        return;
+    }
+    tmin_f = __double2float_rn(tmin);
+    tmax_f = __double2float_rn(tmax);
 }
 
 // IntersectAABB bvh.cpp:165-179.
 CT_DEV bool intersect_aabb(const Ray &r, const double bmin[3], const double bmax[3]) {
-    float tx1 = slab_quotient(bmin[0], r.o.x, r.d.x, r.rd.x, r.exact_div);
-    float tx2 = slab_quotient(bmax[0], r.o.x, r.d.x, r.rd.x, r.exact_div);
-    float tmin = macro_min(tx1, tx2);
-    float tmax = macro_max(tx1, tx2);
-    float ty1 = slab_quotient(bmin[1], r.o.y, r.d.y, r.rd.y, r.exact_div);
-    float ty2 = slab_quotient(bmax[1], r.o.y, r.d.y, r.rd.y, r.exact_div);
-    tmin = macro_max(tmin, macro_min(ty1, ty2));
-    tmax = macro_min(tmax, macro_max(ty1, ty2));
-    float tz1 = slab_quotient(bmin[2], r.o.z, r.d.z, r.rd.z, r.exact_div);
-    float tz2 = slab_quotient(bmax[2], r.o.z, r.d.z, r.rd.z, r.exact_div);
-    tmin = macro_max(tmin, macro_min(tz1, tz2));
-    tmax = macro_min(tmax, macro_max(tz1, tz2));
+    float tmin, tmax;
+    box_times(r, bmin, bmax, tmin, tmax);
     return tmax >= tmin && tmin < r.t && tmax > 0.0f;
 }
 

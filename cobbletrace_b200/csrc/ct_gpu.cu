@@ -140,9 +140,29 @@ CT_DEV void load_tri(const DevTri *tris, uint32_t pos, V3 &p1, V3 &e1, V3 &e2) {
 enum TraverseMode { kClosest, kAnyHit, kFirstLine };
 enum { kTravMiss = 0, kTravHit = 1, kTravOverBudget = -1 };
 
-// IntersectBVHClosest (bvh.cpp:198-222) as an explicit-stack DFS: left child first, right child
-// pushed, boxes tested at visit time against the CURRENT ray.t -- the reference's exact visit order,
-// so box/triangle test counts equal the reference's.
+// A node's two children (bvh.cpp:89-97 allocates them adjacently: left_node, left_node + 1) = 128 contiguous bytes.
+CT_DEV void load_node_pair(const DevNode *nodes, uint32_t left, DevNode &l, DevNode &r) {
+    const double2 *p = reinterpret_cast<const double2 *>(nodes + left);
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    uint4 m = __ldg(reinterpret_cast<const uint4 *>(p + 3));
+    double2 d = __ldg(p + 4), e = __ldg(p + 5), f = __ldg(p + 6);
+    uint4 n = __ldg(reinterpret_cast<const uint4 *>(p + 7));
+    l.bmin[0] = a.x; l.bmin[1] = a.y; l.bmin[2] = b.x;
+    l.bmax[0] = b.y; l.bmax[1] = c.x; l.bmax[2] = c.y;
+    l.left = m.x; l.first = m.y; l.count = m.z;
+    r.bmin[0] = d.x; r.bmin[1] = d.y; r.bmin[2] = e.x;
+    r.bmax[0] = e.y; r.bmax[1] = f.x; r.bmax[2] = f.y;
+    r.left = n.x; r.first = n.y; r.count = n.z;
+}
+
+// IntersectBVHClosest (bvh.cpp:198-222) as an explicit-stack DFS in the reference's visit order (left subtree,
+// then right).  The reference tests a node's box when it VISITS the node; here both children of a passing
+// interior node are fetched and tested together (one 128-byte fetch, two independent slab tests in flight):
+//   * the left child is visited next, so "now" is its visit time;
+//   * the right child's tmin/tmax do not depend on ray.t; of the three accept conditions (bvh.cpp:178) only
+//     `tmin < ray.t` does, and ray.t only ever decreases -- so a right child failing now fails at visit time too
+//     and is dropped, and one that passes now is pushed WITH its tmin and re-checked against the then-current
+//     ray.t when popped.  Same boxes accepted, same triangles tested in the same order, same counts.
 //   kClosest   general semantics (any initial ray.t).
 //   kAnyHit    shadow rays (ray.t = 1e30f): `found` is all that is used (raythread.cpp:306), so stop at
 //              the first triangle that lowers ray.t, i.e. bary pass and 1e-4 < t < 1e30.
@@ -153,47 +173,73 @@ enum { kTravMiss = 0, kTravHit = 1, kTravOverBudget = -1 };
 // the ray for k_overflow (both early-exit modes have an order-independent answer, see k_overflow).
 template <TraverseMode MODE, bool COUNT, bool BUDGET>
 CT_DEV int traverse(const Params &P, Ray &r, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
-    uint32_t stack[kStackMax];
+    // stack entry = the pushed node's payload: (first, count) of a leaf or (left, 0) of an interior node,
+    // plus its slab tmin in kClosest mode
+    uint32_t stk_a[kStackMax], stk_n[kStackMax];
+    float stk_t[MODE == kClosest ? kStackMax : 1];
     int sp = 0;
-    uint32_t node = 0;
     uint32_t spent = 0;
     tclosest = kFinf;          // raythread.cpp:204
     closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
-    while (true) {
-        DevNode nd;
-        load_node(P.nodes, node, nd);
+    uint32_t cur_a, cur_n;     // current (already accepted) node: cur_n > 0 leaf [cur_a, cur_a + cur_n), else children cur_a, cur_a + 1
+    {
+        DevNode root;
+        load_node(P.nodes, 0u, root);
         if (COUNT) lc.box++;
-        if (BUDGET) { spent += 1u + nd.count; if (spent > P.budget) return kTravOverBudget; }
-        if (intersect_aabb(r, nd.bmin, nd.bmax)) {
-            if (nd.count > 0) {
-                for (uint32_t i = 0; i < nd.count; i++) {
-                    uint32_t pos = nd.first + i;
-                    V3 p1, e1, e2;
-                    load_tri(P.tris, pos, p1, e1, e2);
-                    if (COUNT) lc.tri++;
-                    float t;
-                    if (intersect_triangle(r, p1, e1, e2, &t)) {
-                        if (MODE == kAnyHit) {
-                            if (t > kEps && t < kRayTInit) return kTravHit;
-                        } else if (MODE == kFirstLine) {
-                            closest_pos = pos; tclosest = 0.0f;
-                            return kTravHit;
-                        } else {
-                            if (t > kEps) r.t = macro_min(r.t, t);                     // bvh.cpp:161
-                            if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
-                                closest_pos = pos; tclosest = r.t;
-                            }
+        if (!intersect_aabb(r, root.bmin, root.bmax)) return (MODE == kAnyHit || r.t == kRayTInit) ? kTravMiss : kTravHit;
+        cur_n = root.count; cur_a = cur_n ? root.first : root.left;
+        if (BUDGET) spent = 1u + cur_n;
+    }
+    while (true) {
+        if (cur_n > 0) {
+            for (uint32_t i = 0; i < cur_n; i++) {
+                uint32_t pos = cur_a + i;
+                V3 p1, e1, e2;
+                load_tri(P.tris, pos, p1, e1, e2);
+                if (COUNT) lc.tri++;
+                float t;
+                if (intersect_triangle(r, p1, e1, e2, &t)) {
+                    if (MODE == kAnyHit) {
+                        if (t > kEps && t < kRayTInit) return kTravHit;
+                    } else if (MODE == kFirstLine) {
+                        closest_pos = pos; tclosest = 0.0f;
+                        return kTravHit;
+                    } else {
+                        if (t > kEps) r.t = macro_min(r.t, t);                     // bvh.cpp:161
+                        if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
+                            closest_pos = pos; tclosest = r.t;
                         }
                     }
                 }
-            } else {
-                stack[sp++] = nd.left + 1;
-                node = nd.left;
+            }
+        } else {
+            DevNode L, R;
+            load_node_pair(P.nodes, cur_a, L, R);
+            if (COUNT) lc.box += 2;
+            if (BUDGET) { spent += 2u + L.count + R.count; if (spent > P.budget) return kTravOverBudget; }
+            float ln, lx, rn, rx;
+            box_times(r, L.bmin, L.bmax, ln, lx);
+            box_times(r, R.bmin, R.bmax, rn, rx);
+            const bool hit_l = lx >= ln && ln < r.t && lx > 0.0f;              // bvh.cpp:178
+            const bool hit_r = rx >= rn && rn < r.t && rx > 0.0f;
+            const uint32_t ra = R.count ? R.first : R.left;
+            if (hit_l) {
+                if (hit_r) {
+                    stk_a[sp] = ra; stk_n[sp] = R.count;
+                    if (MODE == kClosest) stk_t[sp] = rn;
+                    sp++;
+                }
+                cur_n = L.count; cur_a = cur_n ? L.first : L.left;
                 continue;
             }
+            if (hit_r) { cur_n = R.count; cur_a = ra; continue; }
         }
-        if (sp == 0) break;
-        node = stack[--sp];
+        bool popped = false;
+        while (sp > 0) {
+            --sp;
+            if (MODE != kClosest || stk_t[sp] < r.t) { cur_a = stk_a[sp]; cur_n = stk_n[sp]; popped = true; break; }
+        }
+        if (!popped) break;
     }
     if (MODE == kAnyHit) return kTravMiss;
     return r.t != kRayTInit ? kTravHit : kTravMiss;
