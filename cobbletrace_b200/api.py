@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "ct_gpu_abi_version", "ct_gpu_device_count", "ct_gpu_last_error", "ct_gpu_upload_scene", "ct_gpu_set_camera",
     "ct_gpu_set_stream", "ct_gpu_render_tile", "ct_gpu_readback", "ct_gpu_readback_hits", "ct_gpu_get_counters",
     "ct_gpu_last_tile_ms", "ct_gpu_sync", "ct_gpu_throttle", "ct_gpu_kernel_launches", "ct_gpu_last_tile_stages", "ct_gpu_framebuffer", "ct_gpu_gather_rows", "ct_gpu_debug_closest",
-    "ct_gpu_debug_primitives", "ct_gpu_shutdown", "ct_gpu_set_option", "ct_gpu_overflow_stats",
+    "ct_gpu_debug_primitives", "ct_gpu_debug_filter", "ct_gpu_filter_stats", "ct_gpu_shutdown", "ct_gpu_set_option", "ct_gpu_overflow_stats",
 ]
 
 
@@ -103,6 +103,8 @@ def load_library(path: Optional[str] = None):
     L.ct_gpu_gather_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.ct_gpu_debug_closest.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp]
     L.ct_gpu_debug_primitives.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ct_gpu_debug_filter.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, C.c_double, vp]
+    L.ct_gpu_filter_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.ct_gpu_shutdown.argtypes = [C.c_int]
     L.ct_gpu_set_option.argtypes = [C.c_char_p, C.c_longlong]
     L.ct_gpu_overflow_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -252,6 +254,22 @@ class GpuRenderer:
         th = np.zeros(n, np.uint32); bh = np.zeros(n, np.uint32)
         _check(self.L, self.L.ct_gpu_debug_primitives(self.device, n, _ptr(o), _ptr(d), _ptr(rt), _ptr(tri), _ptr(mn), _ptr(mx), _ptr(th), _ptr(bh)))
         return th, bh, rt
+
+    def debug_filter(self, origins, directions, ray_t, bmin, bmax, bound_scale=1.0):
+        """ct_gpu_debug_filter: verdict codes of the certified fp32 slab filter next to the reference's verdict."""
+        o = np.ascontiguousarray(origins, np.float64); d = np.ascontiguousarray(directions, np.float64)
+        rt = np.ascontiguousarray(ray_t, np.float32)
+        mn = np.ascontiguousarray(bmin, np.float64); mx = np.ascontiguousarray(bmax, np.float64)
+        n = o.shape[0]
+        out = np.zeros(n, np.uint32)
+        _check(self.L, self.L.ct_gpu_debug_filter(self.device, n, _ptr(o), _ptr(d), _ptr(rt), _ptr(mn), _ptr(mx), float(bound_scale), _ptr(out)))
+        return out
+
+    def filter_stats(self):
+        """(box tests, triangle tests) the fp32 filters left to the fp64 arithmetic (needs CT_FLAG_COUNT_TESTS)."""
+        a = C.c_uint64(); b = C.c_uint64()
+        _check(self.L, self.L.ct_gpu_filter_stats(self.device, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def overflow_stats(self):
         """(rays parked for the breadth-first overflow kernel, rays finished in place because the buffer was full)."""

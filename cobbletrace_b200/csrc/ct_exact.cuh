@@ -44,31 +44,59 @@ CT_DEV float vmag(V3 a) {
 CT_DEV float macro_min(float a, float b) { return (a < b) ? a : b; }
 CT_DEV float macro_max(float a, float b) { return (a > b) ? a : b; }
 
+// ---- rays ------------------------------------------------------------------------------------------
+// ray_t (scenefile.h:104-108) plus the per-ray constants of the certified fp32 slab filter (box_filter).
 struct Ray {
-    V3 o, d;        // ray_t scenefile.h:104-108
-    V3 rd;          // 1/d per axis (correctly rounded), only used by box_times' guarded fast path
+    V3 o, d;
     float t;
-    bool exact_div; // some |d| is so large/small that 1/d is inf/denormal: always divide
+    float rdf[3];   // float(1/d)
+    float cl[3];    // round-down float of  -o/d - E   } E = per-axis bound on |filter quotient - reference quotient|,
+    float cu[3];    // round-up   float of  -o/d + E   } see ray_finish
+    bool filt;      // false: some axis cannot be bounded (d == 0, non-finite, absurd magnitudes) -> exact tests only
+    // certified fp32 triangle filter (tri_filter_miss): float copies and magnitudes
+    float of[3], df[3];
+    float cd;       // 2^-17 * max|d_i|, rounded up
+    float om;       // max|o_i|, rounded up
+    bool tfilt;     // false: magnitudes outside the range the filter's error analysis covers
 };
 
-CT_DEV void ray_finish(Ray &r) {
-    r.rd = {__ddiv_rn(1.0, r.d.x), __ddiv_rn(1.0, r.d.y), __ddiv_rn(1.0, r.d.z)};
-    auto odd = [](double d) {
-        uint32_t e = ((uint32_t)__double2hiint(d) >> 20) & 0x7ffu;   // biased exponent
-        // zero/inf/NaN directions are fine (IEEE gives the same inf/NaN quotients both ways);
-        // only finite non-zero d whose reciprocal leaves the normal range needs true division.
-        bool zero = (((uint32_t)__double2hiint(d) & 0x7fffffffu) | (uint32_t)__double2loint(d)) == 0u;
-        return !zero && e != 0x7ffu && (e < 24u || e > 2022u);
-    };
-    r.exact_div = odd(r.d.x) || odd(r.d.y) || odd(r.d.z);
+// Per-ray setup of the slab filter.  bound[k] >= |b| for every node bound b on axis k (computed at upload;
+// +inf when the tree holds non-finite or ill-ordered boxes, which disables the filter).
+//
+// For a node bound b on axis k the reference computes  q_ref = float( fl64( fl64(b - o) / d ) )   (bvh.cpp:166-175).
+// With q* = (b - o)/d in real arithmetic, |q_ref - q*| <= (2^-24 + 2^-51) |q*|.
+// The filter evaluates  y = bf * rdf + c  with  bf = float(b), rdf = float(fl64(1/d)), c ~ fl64(-o * fl64(1/d)):
+//     |bf*rdf - b/d| <= (2 * 2^-24 + 2^-47) |b/d| ,   |c - (-o/d)| <= 2^-51 |o/d|
+// so |y - q_ref| <= 3.01 * 2^-24 * (|b| + |o|) / |d|  <=  E := 2^-22 * (bound + |o|) * |1/d| .
+// cl / cu fold -E / +E into c, rounded DOWN / UP to float, and the filter's FMAs round down / up as well, so
+//     fma_rd(bf, rdf, cl) <= q_ref <= fma_ru(bf, rdf, cu)          for every finite node bound.
+CT_DEV void ray_finish(Ray &r, const double bound[3]) {
+    const double o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z};
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double rd = __ddiv_rn(1.0, d[k]);
+        double c = __dmul_rn(-o[k], rd);
+        double m = __dmul_rn(__dadd_rn(bound[k], fabs(o[k])), fabs(rd));
+        double e = __dmul_rn(m, 0x1p-22);
+        // every quantity must be an ordinary number well inside the float range (rd != 0 rules out d = +-inf, a finite
+        // rd rules out d = 0, NaNs fail the comparisons); tiny E would let float underflow matter
+        ok = ok && (m < 0x1p100) && (fabs(rd) > 0x1p-100) && (e > 0x1p-100);
+        r.rdf[k] = __double2float_rn(rd);
+        r.cl[k] = __double2float_rd(__dsub_rd(c, e));
+        r.cu[k] = __double2float_ru(__dadd_ru(c, e));
+    }
+    r.filt = ok;
+    double dm = fmax(fmax(fabs(d[0]), fabs(d[1])), fabs(d[2])), om = fmax(fmax(fabs(o[0]), fabs(o[1])), fabs(o[2]));
+    r.tfilt = (dm >= 0x1p-20) && (dm <= 0x1p40) && (om <= 0x1p40);          // NaNs fail
+#pragma unroll
+    for (int k = 0; k < 3; k++) { r.of[k] = __double2float_rn(o[k]); r.df[k] = __double2float_rn(d[k]); }
+    r.cd = __double2float_ru(__dmul_ru(dm, 0x1p-17));
+    r.om = __double2float_ru(om);
 }
 
-// mymath.h:11-17 on doubles (same NaN behaviour as the float macros).
-CT_DEV double macro_min_d(double a, double b) { return (a < b) ? a : b; }
-CT_DEV double macro_max_d(double a, double b) { return (a > b) ? a : b; }
-
-// Cold path: the literal IntersectAABB arithmetic of bvh.cpp:166-177 -- six fp64 divisions, each rounded to
-// float on assignment, macro min/max in float.
+// ---- IntersectAABB (bvh.cpp:165-179) -------------------------------------------------------------------
+// Literal arithmetic: six fp64 divisions, each rounded to float on assignment, macro min/max in float.
 struct BoxTimes { float tmin, tmax; };
 __device__ __noinline__ BoxTimes box_times_exact(double ox, double oy, double oz, double dx, double dy, double dz,
                                                  double nx, double ny, double nz, double mx, double my, double mz) {
@@ -87,54 +115,46 @@ __device__ __noinline__ BoxTimes box_times_exact(double ox, double oy, double oz
     return {tmin, tmax};
 }
 
-// True when float(x) may differ from float(y) for some y within a few fp64 ulps of x: x sits within +-16 units of
-// a float rounding boundary (the 29 dropped mantissa bits ~ 0x10000000), or x is non-zero with |x| < 2^-125 (float
-// subnormal range, where the boundaries are elsewhere and the fp64 product may itself have lost bits).
-CT_DEV bool float_rounding_unsafe(double x) {
-    uint32_t lo = (uint32_t)__double2loint(x);
-    uint32_t hi = (uint32_t)__double2hiint(x) & 0x7fffffffu;
-    bool near_mid = ((lo & 0x1fffffffu) - 0x0ffffff0u) <= 0x20u;
-    bool tiny = (hi < 0x38200000u) && ((hi | lo) != 0u);
-    return near_mid | tiny;
+CT_DEV BoxTimes box_times(const Ray &r, const double bmin[3], const double bmax[3]) {
+    return box_times_exact(r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]);
 }
 
-// The two floats IntersectAABB (bvh.cpp:165-177) compares: tmin and tmax of the slab test, bit-exact (up to
-// the sign of a zero, which no comparison sees).
-//
-// The reference rounds each of the six quotients (b - o)/d to float and then takes macro min/max in float.
-// Rounding to float is monotonic and NaN-preserving, so selecting with the same macros on the unrounded
-// doubles and rounding the two survivors gives the same float VALUES: whenever the double comparison picks
-// a different operand than the float comparison would, the two operands round to the same float.
-// The hot path also replaces the fp64 division by a multiplication with the correctly rounded 1/d: every
-// quotient, and therefore (min/max being monotone selections) each survivor, is then within a few fp64 ulps
-// of the reference's double.  float() of a survivor can differ from the reference only when it lies that
-// close to a float rounding boundary (probability ~2^-24 per test); those cases, and rays whose 1/d leaves the
-// normal range, take box_times_exact().  Everything else is proven equal.
-CT_DEV void box_times(const Ray &r, const double bmin[3], const double bmax[3], float &tmin_f, float &tmax_f) {
-    double x1 = __dmul_rn(__dsub_rn(bmin[0], r.o.x), r.rd.x), x2 = __dmul_rn(__dsub_rn(bmax[0], r.o.x), r.rd.x);
-    double y1 = __dmul_rn(__dsub_rn(bmin[1], r.o.y), r.rd.y), y2 = __dmul_rn(__dsub_rn(bmax[1], r.o.y), r.rd.y);
-    double z1 = __dmul_rn(__dsub_rn(bmin[2], r.o.z), r.rd.z), z2 = __dmul_rn(__dsub_rn(bmax[2], r.o.z), r.rd.z);
-    double tmin = macro_min_d(x1, x2);
-    double tmax = macro_max_d(x1, x2);
-    tmin = macro_max_d(tmin, macro_min_d(y1, y2));
-    tmax = macro_min_d(tmax, macro_max_d(y1, y2));
-    tmin = macro_max_d(tmin, macro_min_d(z1, z2));
-    tmax = macro_min_d(tmax, macro_max_d(z1, z2));
-    if (float_rounding_unsafe(tmin) | float_rounding_unsafe(tmax) | r.exact_div) {
-        BoxTimes e = box_times_exact(r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]);
-        tmin_f = e.tmin; tmax_f = e.tmax;
-        return;
+CT_DEV bool box_accept(BoxTimes b, float ray_t) { return b.tmax >= b.tmin && b.tmin < ray_t && b.tmax > 0.0f; }   // bvh.cpp:178
+
+CT_DEV bool intersect_aabb(const Ray &r, const double bmin[3], const double bmax[3]) { return box_accept(box_times(r, bmin, bmax), r.t); }
+
+// Certified fp32 filter for the slab test.  Brackets the reference's float tmin and tmax:
+//     near_lo <= tmin_ref <= near_hi ,   far_lo <= tmax_ref <= far_hi
+// (per axis the reference's min(t1,t2) is the quotient of the bound the ray meets first, because
+// b -> q_ref(b) is monotone; max over axes of brackets brackets the max).  Only valid when r.filt.
+struct BoxBracket { float near_lo, near_hi, far_lo, far_hi; };
+
+CT_DEV BoxBracket box_filter(const Ray &r, const float bmin[3], const float bmax[3]) {
+    float nl[3], nh[3], fl[3], fh[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const bool pos = r.rdf[k] > 0.0f;
+        const float bn = pos ? bmin[k] : bmax[k], bf = pos ? bmax[k] : bmin[k];
+        nl[k] = __fmaf_rd(bn, r.rdf[k], r.cl[k]);
+        nh[k] = __fmaf_ru(bn, r.rdf[k], r.cu[k]);
+        fl[k] = __fmaf_rd(bf, r.rdf[k], r.cl[k]);
+        fh[k] = __fmaf_ru(bf, r.rdf[k], r.cu[k]);
     }
-    tmin_f = __double2float_rn(tmin);
-    tmax_f = __double2float_rn(tmax);
+    BoxBracket b;
+    b.near_lo = fmaxf(fmaxf(nl[0], nl[1]), nl[2]);
+    b.near_hi = fmaxf(fmaxf(nh[0], nh[1]), nh[2]);
+    b.far_lo = fminf(fminf(fl[0], fl[1]), fl[2]);
+    b.far_hi = fminf(fminf(fh[0], fh[1]), fh[2]);
+    return b;
 }
 
-// IntersectAABB bvh.cpp:165-179.
-CT_DEV bool intersect_aabb(const Ray &r, const double bmin[3], const double bmax[3]) {
-    float tmin, tmax;
-    box_times(r, bmin, bmax, tmin, tmax);
-    return tmax >= tmin && tmin < r.t && tmax > 0.0f;
-}
+// Verdicts that follow from the bracket alone (each is true only when certain; both false = undecided).
+//   geometry:  tmax >= tmin && tmax > 0      (independent of ray.t)
+//   distance:  tmin < ray.t
+CT_DEV bool bracket_geom_yes(const BoxBracket &b) { return b.far_lo >= b.near_hi && b.far_lo > 0.0f; }
+CT_DEV bool bracket_geom_no(const BoxBracket &b) { return b.far_hi < b.near_lo || b.far_hi <= 0.0f; }
+CT_DEV bool bracket_t_yes(const BoxBracket &b, float ray_t) { return b.near_hi < ray_t; }
+CT_DEV bool bracket_t_no(const BoxBracket &b, float ray_t) { return b.near_lo >= ray_t; }
 
 // IntersectTriangle bvh.cpp:147-163 with edge1 = p2-p1, edge2 = p3-p1 precomputed at upload (the same
 // two fp64 subtractions the reference redoes per call).  Returns the barycentric verdict; *t_out is
@@ -153,6 +173,61 @@ CT_DEV bool intersect_triangle(const Ray &r, V3 p1, V3 e1, V3 e2, float *t_out) 
     if (v < 0.0f || __fadd_rn(u, v) > 1.0f) return false;
     *t_out = __fmul_rn(f, vdot(e2, q));
     return true;
+}
+
+// Certified fp32 filter in front of IntersectTriangle (bvh.cpp:147-163).  Returns true only when the reference's
+// test CERTAINLY has no effect on the traversal:
+//   * it returns false (|a| < 1e-4, u outside [0,1], v < 0 or u + v > 1), or
+//   * ANY_HIT only (shadow rays): it returns true but with t <= 1e-4, which never lowers ray.t (bvh.cpp:161) --
+//     what a shadow ray leaving a surface sees of the triangle it starts on.
+// Everything else (hits, near misses, out-of-range magnitudes) is left to the exact fp64 test.
+//
+// With A = e1.(d x e2), S = s.(d x e2), Q = d.(s x e1), T = e2.(s x e1), s = o - p1 in real arithmetic, the
+// reference computes u = S/A, v = Q/A, t = T/A up to relative errors below 4.1 * 2^-24 (fp64 products, rounded to
+// float, times float(1/a)).  Evaluating the same determinants in fp32 from float-rounded inputs gives
+//     |A~ - A| <= EA = 2^-17 K1 K2 D        |S~ - S| <= ES = 2^-17 D K2 (O + K3)
+//     |Q~ - Q| <= EQ = 2^-17 D K1 (O + K3)  |T~ - T| <= ET = 2^-17 K1 K2 (O + K3)
+// with K1 = max|e1_i|, K2 = max|e2_i|, K3 = max|p1_i| (stored with the triangle, rounded up), D = max|d_i|,
+// O = max|o_i| (worst case 67 * 2^-24 * magnitude each: input roundings, the float subtraction o - p1, five
+// rounded operations per determinant).  A verdict is certified only with margins of twice these bounds, which
+// also absorbs the reference's own float rounding of u, v, t.  Magnitude limits (r.tfilt,
+// finite K's in [2^-30, 2^30] -- else K1 is stored as NaN and nothing certifies) keep every product in the
+// normal float range; ES, EQ >= 2^-40 keeps the reference's f * S from underflowing to -0.
+// tri: 12 floats p1.xyz, K3, e1.xyz, K1, e2.xyz, K2.
+template <bool ANY_HIT>
+CT_DEV bool tri_filter_miss(const Ray &r, float4 t0, float4 t1, float4 t2) {
+    const float k3 = t0.w, k1 = t1.w, k2 = t2.w;
+    // h = d x e2, q = s x e1
+    const float hx = __fmaf_rn(r.df[1], t2.z, -__fmul_rn(r.df[2], t2.y));
+    const float hy = __fmaf_rn(r.df[2], t2.x, -__fmul_rn(r.df[0], t2.z));
+    const float hz = __fmaf_rn(r.df[0], t2.y, -__fmul_rn(r.df[1], t2.x));
+    const float sx = __fsub_rn(r.of[0], t0.x), sy = __fsub_rn(r.of[1], t0.y), sz = __fsub_rn(r.of[2], t0.z);
+    const float A = __fmaf_rn(t1.x, hx, __fmaf_rn(t1.y, hy, __fmul_rn(t1.z, hz)));
+    const float S = __fmaf_rn(sx, hx, __fmaf_rn(sy, hy, __fmul_rn(sz, hz)));
+    const float qx = __fmaf_rn(sy, t1.z, -__fmul_rn(sz, t1.y));
+    const float qy = __fmaf_rn(sz, t1.x, -__fmul_rn(sx, t1.z));
+    const float qz = __fmaf_rn(sx, t1.y, -__fmul_rn(sy, t1.x));
+    const float Q = __fmaf_rn(r.df[0], qx, __fmaf_rn(r.df[1], qy, __fmul_rn(r.df[2], qz)));
+    const float sig = __fadd_ru(r.om, k3);                       // O + K3
+    const float ea = __fmul_ru(__fmul_ru(k1, k2), r.cd);
+    const float es = fmaxf(__fmul_ru(__fmul_ru(r.cd, k2), sig), 0x1p-40f);
+    const float eq = fmaxf(__fmul_ru(__fmul_ru(r.cd, k1), sig), 0x1p-40f);
+    const float aa = fabsf(A);
+    if (__fadd_ru(aa, ea) < 9.9999e-05f) return true;             // |a| < 1e-4 for certain (bvh.cpp:152)
+    if (!(aa > __fmul_ru(2.0f, ea))) return false;                // sign of a not certain (also NaN K1)
+    const float Ss = A > 0.0f ? S : -S, Qs = A > 0.0f ? Q : -Q;   // S, Q oriented so that u = Ss/|A|, v = Qs/|A|
+    if (Ss < -__fmul_ru(2.0f, es)) return true;                   // u < 0
+    if (Qs < -__fmul_ru(2.0f, eq)) return true;                   // v < 0
+    if (__fsub_rd(Ss, aa) > __fmul_ru(2.0f, __fadd_ru(es, ea))) return true;                                   // u > 1
+    if (__fsub_rd(__fadd_rd(Ss, Qs), aa) > __fmul_ru(2.0f, __fadd_ru(__fadd_ru(es, eq), ea))) return true;      // u + v > 1
+    if (ANY_HIT) {
+        const float T = __fmaf_rn(t2.x, qx, __fmaf_rn(t2.y, qy, __fmul_rn(t2.z, qz)));
+        const float Ts = A > 0.0f ? T : -T;
+        const float et = __fmul_ru(__fmul_ru(__fmul_ru(k1, k2), sig), 0x1p-16f);      // 2 * ET
+        // t <= 1e-4 for certain:  T <= 1e-4 (1 - 2^-20) |A|
+        if (__fadd_ru(Ts, et) <= __fmul_rd(9.9999e-05f, __fsub_rd(aa, ea))) return true;
+    }
+    return false;
 }
 
 // ReflectRay raythread.cpp:270-273: 2.0*normal*Dot(normal,ray) - ray

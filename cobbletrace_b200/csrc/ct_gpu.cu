@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -43,20 +44,31 @@ using namespace ct;
 constexpr int kStackMax = 96;        // DFS stack entries per ray (tree depth limit, checked at upload)
 constexpr int kMaxDevices = 16;
 constexpr int kBlockThreads = 128;   // 4 warps per CTA
+constexpr int kMinBlocks = 6;        // traversal kernels: resident CTAs per SM the register allocation must allow
 constexpr int kOvfThreads = 256;     // k_overflow CTA
 constexpr int kMaxLaunches = 80;     // launches of one tile (work cursors / stage events)
 constexpr uint32_t kNoPos = 0xffffffffu;
 constexpr uint32_t kDefaultBudget = 2048;   // node visits + triangle tests before a ray is parked for k_overflow
 
 // ---- device-side scene layout (SoA arrays in HBM, uploaded once) -----------------------------------
-struct __align__(16) DevNode {       // 64 B: one node = two 32-B sectors
-    double bmin[3];
-    double bmax[3];
-    uint32_t left, first, count, pad;
+// The BVH is stored per INTERIOR node as the pair of its two children (bvh.cpp:89-97 allocates them adjacently
+// and the traversal always needs both).  A child is described by (ref, cnt): cnt > 0 -> leaf holding triangles
+// [ref, ref + cnt) of the leaf-ordered triangle array; cnt == 0 -> interior, ref = its own pair index.
+struct __align__(16) DevPair32 {     // 64 B = two 32-B sectors: what the certified fp32 filter reads
+    float lmin[3], lmax[3], rmin[3], rmax[3];    // float(bounds), round to nearest
+    uint32_t l_ref, l_cnt, r_ref, r_cnt;
+};
+struct __align__(16) DevPair64 {     // 96 B: the reference's fp64 bounds, read only when the filter cannot decide
+    double lmin[3], lmax[3], rmin[3], rmax[3];
 };
 struct __align__(16) DevTri {        // 80 B, stored in LEAF order (position = slot in bvh indexes[])
     double p1[3], e1[3], e2[3];      // e1 = p2-p1, e2 = p3-p1 (bvh.cpp:148-149, raythread.cpp:337-338)
     uint32_t orig, pad;              // original triangle id (= closestIndex of the reference)
+};
+struct __align__(16) DevTri32 {      // 48 B, same order: what the certified fp32 triangle filter reads
+    float p1[3], k3;                 // k3 = max|p1_i| rounded up
+    float e1[3], k1;                 // k1 = max|e1_i| rounded up (NaN: magnitudes outside the filter's range)
+    float e2[3], k2;
 };
 struct DevLight { int32_t type; float intensity; double pos[3]; double dir[3]; };
 struct DevShadowLight { int32_t type; uint32_t index; double v[3]; };   // non-ambient lights, file order; index = light number
@@ -76,15 +88,21 @@ struct DevTotals {                   // running ray / test counters (never reset
     unsigned long long rays_primary, rays_shadow, rays_reflection, box_tests, tri_tests;
     unsigned long long rays_overflow;    // rays whose DFS ran past the budget
     unsigned long long rays_in_place;    // ... of which the parking buffer was full: finished by their own thread
+    unsigned long long box_exact, tri_exact;   // tests the fp32 filters left to the fp64 arithmetic (CT_FLAG_COUNT_TESTS)
 };
 
 struct Params {
-    const DevNode *nodes;
+    const DevPair32 *pairs32;
+    const DevPair64 *pairs64;
+    double root_min[3], root_max[3];     // node 0
+    uint32_t root_ref, root_cnt;
+    double bound[3];                     // >= |b| for every node bound b per axis (+inf disables the filter), see ray_finish
     const DevTri *tris;
+    const DevTri32 *tris32;
     const ct_material *materials;    // by original id
     const DevLight *lights;
     const DevShadowLight *slights;
-    uint32_t n_lights, n_slights, n_tri, n_nodes;
+    uint32_t n_lights, n_slights, n_tri, n_nodes, n_pairs;
     uint32_t occ_words;              // words of occlusion bits per path = ceil(n_lights / 32)
     uint32_t pos_of_tri0;            // leaf position of original triangle 0 (closestIndex default, raythread.cpp:205)
     uint32_t budget;                 // see kDefaultBudget
@@ -115,18 +133,9 @@ struct Params {
     DevTotals *tot;
 };
 
-struct LocalCount { uint32_t box = 0, tri = 0; };
+struct LocalCount { uint32_t box = 0, tri = 0, box_exact = 0, tri_exact = 0; };
 
 CT_DEV V3 ld3(const double *p) { return {p[0], p[1], p[2]}; }
-
-CT_DEV void load_node(const DevNode *nodes, uint32_t i, DevNode &n) {
-    const double2 *p = reinterpret_cast<const double2 *>(nodes + i);
-    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    uint4 m = __ldg(reinterpret_cast<const uint4 *>(p + 3));
-    n.bmin[0] = a.x; n.bmin[1] = a.y; n.bmin[2] = b.x;
-    n.bmax[0] = b.y; n.bmax[1] = c.x; n.bmax[2] = c.y;
-    n.left = m.x; n.first = m.y; n.count = m.z;
-}
 
 CT_DEV void load_tri(const DevTri *tris, uint32_t pos, V3 &p1, V3 &e1, V3 &e2) {
     const double2 *p = reinterpret_cast<const double2 *>(tris + pos);
@@ -137,32 +146,78 @@ CT_DEV void load_tri(const DevTri *tris, uint32_t pos, V3 &p1, V3 &e1, V3 &e2) {
     e2 = {d.x, d.y, e};
 }
 
+CT_DEV void load_pair32(const DevPair32 *pairs, uint32_t pid, DevPair32 &p) {
+    const float4 *q = reinterpret_cast<const float4 *>(pairs + pid);
+    float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    uint4 m = __ldg(reinterpret_cast<const uint4 *>(q + 3));
+    p.lmin[0] = a.x; p.lmin[1] = a.y; p.lmin[2] = a.z; p.lmax[0] = a.w; p.lmax[1] = b.x; p.lmax[2] = b.y;
+    p.rmin[0] = b.z; p.rmin[1] = b.w; p.rmin[2] = c.x; p.rmax[0] = c.y; p.rmax[1] = c.z; p.rmax[2] = c.w;
+    p.l_ref = m.x; p.l_cnt = m.y; p.r_ref = m.z; p.r_cnt = m.w;
+}
+
+// The reference's own slab arithmetic for child `side` (0 left, 1 right) of pair `pid`.  Cold path.
+__device__ __noinline__ BoxTimes exact_child(const DevPair64 *pairs, uint32_t pid, uint32_t side, double ox, double oy, double oz,
+                                             double dx, double dy, double dz) {
+    const double2 *q = reinterpret_cast<const double2 *>(pairs + pid) + 3u * side;
+    double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    return box_times_exact(ox, oy, oz, dx, dy, dz, a.x, a.y, b.x, b.y, c.x, c.y);
+}
+
+// The reference's own triangle arithmetic for the triangle at leaf position `pos`.  Out of line so that the fp64
+// operands only occupy registers while it runs.
+struct TriHit { bool hit; float t; };
+__device__ __noinline__ TriHit tri_exact(const DevTri *tris, uint32_t pos, double ox, double oy, double oz, double dx, double dy, double dz) {
+    V3 p1, e1, e2;
+    load_tri(tris, pos, p1, e1, e2);
+    Ray r;
+    r.o = {ox, oy, oz}; r.d = {dx, dy, dz};
+    TriHit h;
+    h.t = 0.0f;
+    h.hit = intersect_triangle(r, p1, e1, e2, &h.t);
+    return h;
+}
+
+// IntersectTriangle's verdict for the triangle at `pos`: the fp32 filter discards what certainly has no effect,
+// the fp64 arithmetic decides the rest.
+template <bool ANY_HIT, bool COUNT>
+CT_DEV TriHit leaf_triangle(const Params &P, const Ray &r, uint32_t pos, LocalCount &lc) {
+    if (r.tfilt) {
+        const float4 *q = reinterpret_cast<const float4 *>(P.tris32 + pos);
+        if (tri_filter_miss<ANY_HIT>(r, __ldg(q), __ldg(q + 1), __ldg(q + 2))) return {false, 0.0f};
+    }
+    if (COUNT) lc.tri_exact++;
+    return tri_exact(P.tris, pos, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
+}
+
+// IntersectAABB's verdict for one child, bit-exact: the fp32 bracket decides when it can, the fp64 arithmetic
+// otherwise.  On return [near_lo, near_hi] brackets the reference's tmin (collapsed to the exact value when the
+// fp64 path ran), which is what a deferred `tmin < ray.t` re-check needs.
+template <bool COUNT>
+CT_DEV bool child_accept(const Params &P, const Ray &r, uint32_t pid, uint32_t side, const float bmin[3], const float bmax[3],
+                         float &near_lo, float &near_hi, LocalCount &lc) {
+    if (r.filt) {
+        BoxBracket b = box_filter(r, bmin, bmax);
+        near_lo = b.near_lo; near_hi = b.near_hi;
+        if (bracket_geom_no(b) || bracket_t_no(b, r.t)) return false;
+        if (bracket_geom_yes(b) && bracket_t_yes(b, r.t)) return true;
+    }
+    if (COUNT) lc.box_exact++;
+    BoxTimes e = exact_child(P.pairs64, pid, side, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
+    near_lo = near_hi = e.tmin;
+    return box_accept(e, r.t);
+}
+
 enum TraverseMode { kClosest, kAnyHit, kFirstLine };
 enum { kTravMiss = 0, kTravHit = 1, kTravOverBudget = -1 };
 
-// A node's two children (bvh.cpp:89-97 allocates them adjacently: left_node, left_node + 1) = 128 contiguous bytes.
-CT_DEV void load_node_pair(const DevNode *nodes, uint32_t left, DevNode &l, DevNode &r) {
-    const double2 *p = reinterpret_cast<const double2 *>(nodes + left);
-    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    uint4 m = __ldg(reinterpret_cast<const uint4 *>(p + 3));
-    double2 d = __ldg(p + 4), e = __ldg(p + 5), f = __ldg(p + 6);
-    uint4 n = __ldg(reinterpret_cast<const uint4 *>(p + 7));
-    l.bmin[0] = a.x; l.bmin[1] = a.y; l.bmin[2] = b.x;
-    l.bmax[0] = b.y; l.bmax[1] = c.x; l.bmax[2] = c.y;
-    l.left = m.x; l.first = m.y; l.count = m.z;
-    r.bmin[0] = d.x; r.bmin[1] = d.y; r.bmin[2] = e.x;
-    r.bmax[0] = e.y; r.bmax[1] = f.x; r.bmax[2] = f.y;
-    r.left = n.x; r.first = n.y; r.count = n.z;
-}
-
 // IntersectBVHClosest (bvh.cpp:198-222) as an explicit-stack DFS in the reference's visit order (left subtree,
 // then right).  The reference tests a node's box when it VISITS the node; here both children of a passing
-// interior node are fetched and tested together (one 128-byte fetch, two independent slab tests in flight):
+// interior node are fetched and tested together (one 64-byte fetch, two independent slab tests in flight):
 //   * the left child is visited next, so "now" is its visit time;
 //   * the right child's tmin/tmax do not depend on ray.t; of the three accept conditions (bvh.cpp:178) only
 //     `tmin < ray.t` does, and ray.t only ever decreases -- so a right child failing now fails at visit time too
-//     and is dropped, and one that passes now is pushed WITH its tmin and re-checked against the then-current
-//     ray.t when popped.  Same boxes accepted, same triangles tested in the same order, same counts.
+//     and is dropped, and one that passes now is pushed WITH (a bracket of) its tmin and re-checked against the
+//     then-current ray.t when popped.  Same boxes accepted, same triangles tested in the same order, same counts.
 //   kClosest   general semantics (any initial ray.t).
 //   kAnyHit    shadow rays (ray.t = 1e30f): `found` is all that is used (raythread.cpp:306), so stop at
 //              the first triangle that lowers ray.t, i.e. bary pass and 1e-4 < t < 1e30.
@@ -173,32 +228,27 @@ CT_DEV void load_node_pair(const DevNode *nodes, uint32_t left, DevNode &l, DevN
 // the ray for k_overflow (both early-exit modes have an order-independent answer, see k_overflow).
 template <TraverseMode MODE, bool COUNT, bool BUDGET>
 CT_DEV int traverse(const Params &P, Ray &r, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
-    // stack entry = the pushed node's payload: (first, count) of a leaf or (left, 0) of an interior node,
-    // plus its slab tmin in kClosest mode
-    uint32_t stk_a[kStackMax], stk_n[kStackMax];
-    float stk_t[MODE == kClosest ? kStackMax : 1];
+    // stack entry = a pushed right child: (ref, cnt) and, in kClosest mode, the bracket of its tmin plus
+    // 2 * parent pair + 1 to find its fp64 bounds again
+    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax];
+    uint32_t stk_src[MODE == kClosest ? kStackMax : 1];
+    float stk_lo[MODE == kClosest ? kStackMax : 1], stk_hi[MODE == kClosest ? kStackMax : 1];
     int sp = 0;
     uint32_t spent = 0;
     tclosest = kFinf;          // raythread.cpp:204
     closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
-    uint32_t cur_a, cur_n;     // current (already accepted) node: cur_n > 0 leaf [cur_a, cur_a + cur_n), else children cur_a, cur_a + 1
-    {
-        DevNode root;
-        load_node(P.nodes, 0u, root);
-        if (COUNT) lc.box++;
-        if (!intersect_aabb(r, root.bmin, root.bmax)) return (MODE == kAnyHit || r.t == kRayTInit) ? kTravMiss : kTravHit;
-        cur_n = root.count; cur_a = cur_n ? root.first : root.left;
-        if (BUDGET) spent = 1u + cur_n;
-    }
+    if (COUNT) lc.box++;
+    if (!intersect_aabb(r, P.root_min, P.root_max)) return (MODE == kAnyHit || r.t == kRayTInit) ? kTravMiss : kTravHit;
+    uint32_t cur_ref = P.root_ref, cur_cnt = P.root_cnt;   // current (already accepted) node
+    if (BUDGET) spent = 1u + cur_cnt;
     while (true) {
-        if (cur_n > 0) {
-            for (uint32_t i = 0; i < cur_n; i++) {
-                uint32_t pos = cur_a + i;
-                V3 p1, e1, e2;
-                load_tri(P.tris, pos, p1, e1, e2);
+        if (cur_cnt > 0) {
+            for (uint32_t i = 0; i < cur_cnt; i++) {
+                uint32_t pos = cur_ref + i;
                 if (COUNT) lc.tri++;
-                float t;
-                if (intersect_triangle(r, p1, e1, e2, &t)) {
+                const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
+                const float t = th.t;
+                if (th.hit) {
                     if (MODE == kAnyHit) {
                         if (t > kEps && t < kRayTInit) return kTravHit;
                     } else if (MODE == kFirstLine) {
@@ -213,31 +263,36 @@ CT_DEV int traverse(const Params &P, Ray &r, float &tclosest, uint32_t &closest_
                 }
             }
         } else {
-            DevNode L, R;
-            load_node_pair(P.nodes, cur_a, L, R);
+            DevPair32 pr;
+            load_pair32(P.pairs32, cur_ref, pr);
             if (COUNT) lc.box += 2;
-            if (BUDGET) { spent += 2u + L.count + R.count; if (spent > P.budget) return kTravOverBudget; }
-            float ln, lx, rn, rx;
-            box_times(r, L.bmin, L.bmax, ln, lx);
-            box_times(r, R.bmin, R.bmax, rn, rx);
-            const bool hit_l = lx >= ln && ln < r.t && lx > 0.0f;              // bvh.cpp:178
-            const bool hit_r = rx >= rn && rn < r.t && rx > 0.0f;
-            const uint32_t ra = R.count ? R.first : R.left;
+            if (BUDGET) { spent += 2u + pr.l_cnt + pr.r_cnt; if (spent > P.budget) return kTravOverBudget; }
+            float l_lo, l_hi, r_lo, r_hi;
+            const bool hit_l = child_accept<COUNT>(P, r, cur_ref, 0u, pr.lmin, pr.lmax, l_lo, l_hi, lc);
+            const bool hit_r = child_accept<COUNT>(P, r, cur_ref, 1u, pr.rmin, pr.rmax, r_lo, r_hi, lc);
             if (hit_l) {
                 if (hit_r) {
-                    stk_a[sp] = ra; stk_n[sp] = R.count;
-                    if (MODE == kClosest) stk_t[sp] = rn;
+                    stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt;
+                    if (MODE == kClosest) { stk_lo[sp] = r_lo; stk_hi[sp] = r_hi; stk_src[sp] = 2u * cur_ref + 1u; }
                     sp++;
                 }
-                cur_n = L.count; cur_a = cur_n ? L.first : L.left;
+                cur_ref = pr.l_ref; cur_cnt = pr.l_cnt;
                 continue;
             }
-            if (hit_r) { cur_n = R.count; cur_a = ra; continue; }
+            if (hit_r) { cur_ref = pr.r_ref; cur_cnt = pr.r_cnt; continue; }
         }
         bool popped = false;
         while (sp > 0) {
             --sp;
-            if (MODE != kClosest || stk_t[sp] < r.t) { cur_a = stk_a[sp]; cur_n = stk_n[sp]; popped = true; break; }
+            if (MODE == kClosest) {                                   // the deferred `tmin < ray.t` of bvh.cpp:178
+                if (stk_lo[sp] >= r.t) continue;
+                if (!(stk_hi[sp] < r.t)) {
+                    BoxTimes e = exact_child(P.pairs64, stk_src[sp] >> 1, stk_src[sp] & 1u, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
+                    if (!(e.tmin < r.t)) continue;
+                }
+            }
+            cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; popped = true;
+            break;
         }
         if (!popped) break;
     }
@@ -321,7 +376,7 @@ CT_DEV bool park_ray(const Params &P, int ovf_idx, const Ray &r, uint32_t target
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads) k_primary(const __grid_constant__ Params P, int work_idx) {
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __grid_constant__ Params P, int work_idx) {
     LocalCount lc;
     uint32_t n_rays = 0;
     while (true) {
@@ -331,7 +386,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_primary(const __grid_constant
         int x, y, fbi;
         if (!slot_pixel(P, slot, x, y, fbi)) continue;
         Ray r = primary_ray(P, x, y);
-        ray_finish(r);
+        ray_finish(r, P.bound);
         float tc; uint32_t pos;
         bool found = traverse<kClosest, COUNT, false>(P, r, tc, pos, lc) == kTravHit;
         n_rays++;
@@ -345,14 +400,14 @@ __global__ void __launch_bounds__(kBlockThreads) k_primary(const __grid_constant
         }
     }
     warp_add(&P.tot->rays_primary, n_rays);
-    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
 
 // ComputeLighting's shadow rays (raythread.cpp:288-306) for the paths alive at `depth`.  Work item =
 // (shadow light j, path q), j-major, so the 32 lanes of a warp trace 32 neighbouring shading points towards
 // the same light.  Verdicts go to the per-path occlusion mask read by k_shade.
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads) k_shadow(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
     LocalCount lc;
     uint32_t n_shadow = 0, n_parked = 0;
     const uint32_t n = depth == 0 ? P.n_slots : P.sched->queue_count[depth];
@@ -370,7 +425,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_shadow(const __grid_constant_
         V3 position = vadd(r.o, vscale((double)tc, r.d));                                  // :360
         V3 lray = (L.type == CT_LIGHT_POINT) ? vsub(ld3(L.v), position) : ld3(L.v);        // :288 / :293
         Ray sr; sr.o = position; sr.d = lray; sr.t = kRayTInit;                            // :304 no offset, no t<=1 test
-        ray_finish(sr);
+        ray_finish(sr, P.bound);
         float stc; uint32_t spos;
         n_shadow++;
         uint32_t word = q * P.occ_words + (L.index >> 5), bit = L.index & 31u;
@@ -384,7 +439,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_shadow(const __grid_constant_
     }
     warp_add(&P.tot->rays_shadow, n_shadow);
     warp_add(&P.tot->rays_overflow, n_parked);
-    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
 
 // TraceRay body after the closest hit (raythread.cpp:359-373) for the paths alive at `depth`; the shadow
@@ -476,7 +531,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
 
 // Closest "hit" of the reflection rays {position, reflected, t = 0} (raythread.cpp:373).
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads) k_bounce(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
     LocalCount lc;
     uint32_t n_parked = 0;
     const uint32_t n = P.sched->queue_count[depth];
@@ -490,7 +545,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_bounce(const __grid_constant_
         double2 a = rb[0], b = rb[1], c = rb[2];
         Ray r;
         r.o = {a.x, a.y, b.x}; r.d = {b.y, c.x, c.y}; r.t = 0.0f;
-        ray_finish(r);
+        ray_finish(r, P.bound);
         float tc; uint32_t pos;
         clear_occ(P, q);
         int res = traverse<kFirstLine, COUNT, true>(P, r, tc, pos, lc);      // found is always true: 0 != 1e30f (:227)
@@ -503,7 +558,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_bounce(const __grid_constant_
         P.hitb_pos[q] = (pos == kNoPos) ? P.pos_of_tri0 : pos;
     }
     warp_add(&P.tot->rays_overflow, n_parked);
-    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
 
 // Parked rays (see the file header).  Both early-exit modes have an answer that does not depend on the visit
@@ -514,6 +569,20 @@ __global__ void __launch_bounds__(kBlockThreads) k_bounce(const __grid_constant_
 //               bvh.cpp:70-97, so leaf positions increase along the DFS).
 // The whole grid walks the tree breadth first, a batch of rays at a time: one frontier item = (ray, node), one
 // grid.sync per level, the frontier ping-pongs between two HBM buffers sized for the widest possible level.
+// Tests the triangles of an accepted leaf for a parked ray; records the verdict in `res`.
+template <TraverseMode MODE, bool COUNT>
+CT_DEV void overflow_leaf(const Params &P, const Ray &r, uint32_t first, uint32_t cnt, uint32_t *res, LocalCount &lc) {
+    for (uint32_t k = 0; k < cnt; k++) {
+        uint32_t pos = first + k;
+        if (COUNT) lc.tri++;
+        const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
+        const float t = th.t;
+        if (!th.hit) continue;
+        if (MODE == kAnyHit) { if (t > kEps && t < kRayTInit) { *(volatile uint32_t *)res = 1u; return; } }
+        else { atomicMin(res, pos); return; }                 // later positions of this leaf are larger
+    }
+}
+
 template <TraverseMode MODE, bool COUNT>
 __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant__ Params P, int ovf_idx) {
     const uint32_t n = min(P.sched->ovf_count[ovf_idx], P.ovf_cap);
@@ -522,16 +591,24 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
     LocalCount lc;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t per_ray = P.n_nodes / 2u + 2u;         // widest level of one ray
+    const uint32_t per_ray = P.n_pairs / 2u + 2u;         // widest level of interior nodes one ray can reach
     const uint32_t batch = max(1u, min(P.frontier_cap / per_ray, P.ovf_batch_max));
     volatile uint32_t *cnt = P.sched->bfs_count;
     for (uint32_t b0 = 0; b0 < n; b0 += batch) {
         const uint32_t bn = min(batch, n - b0);
+        if (tid == 0) { cnt[0] = 0u; cnt[1] = 0u; cnt[2] = 0u; }
+        for (uint32_t i = tid; i < bn; i += n_threads) P.ovf_result[i] = (MODE == kAnyHit) ? 0u : kNoPos;
+        grid.sync();
+        // level 0: the root (frontier items are accepted INTERIOR nodes = pair indices; leaves are tested on the spot)
         for (uint32_t i = tid; i < bn; i += n_threads) {
-            P.frontier[0][i] = make_uint2(i, 0u);
-            P.ovf_result[i] = (MODE == kAnyHit) ? 0u : kNoPos;
+            const OvfRay &o = P.ovf[b0 + i];
+            Ray r; r.o = ld3(o.o); r.d = ld3(o.d); r.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
+            ray_finish(r, P.bound);
+            if (COUNT) lc.box++;
+            if (!intersect_aabb(r, P.root_min, P.root_max)) continue;
+            if (P.root_cnt > 0) overflow_leaf<MODE, COUNT>(P, r, P.root_ref, P.root_cnt, P.ovf_result + i, lc);
+            else P.frontier[0][atomicAdd(const_cast<uint32_t *>(&cnt[0]), 1u)] = make_uint2(i, P.root_ref);
         }
-        if (tid == 0) { cnt[0] = bn; cnt[1] = 0u; cnt[2] = 0u; }
         grid.sync();
         for (uint32_t level = 0;; level++) {
             const uint32_t cin = cnt[level % 3u];
@@ -542,48 +619,41 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
             uint32_t *cout = const_cast<uint32_t *>(&cnt[(level + 1u) % 3u]);
             for (uint32_t base = tid - lane; base < cin; base += n_threads) {
                 const uint32_t i = base + lane;
-                bool expand = false;
+                uint32_t n_out = 0, out_a = 0, out_b = 0;
                 uint2 item = make_uint2(0u, 0u);
-                uint32_t left = 0;
                 if (i < cin) {
                     item = in[i];
-                    volatile uint32_t *res = P.ovf_result + item.x;
-                    if (!(MODE == kAnyHit && *res != 0u)) {
+                    uint32_t *res = P.ovf_result + item.x;
+                    if (!(MODE == kAnyHit && *(volatile uint32_t *)res != 0u)) {
                         const OvfRay &o = P.ovf[b0 + item.x];
                         Ray r; r.o = ld3(o.o); r.d = ld3(o.d); r.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
-                        ray_finish(r);
-                        DevNode nd;
-                        load_node(P.nodes, item.y, nd);
-                        if (COUNT) lc.box++;
-                        if (intersect_aabb(r, nd.bmin, nd.bmax)) {
-                            if (nd.count > 0) {
-                                for (uint32_t k = 0; k < nd.count; k++) {
-                                    uint32_t pos = nd.first + k;
-                                    V3 p1, e1, e2;
-                                    load_tri(P.tris, pos, p1, e1, e2);
-                                    if (COUNT) lc.tri++;
-                                    float t;
-                                    if (!intersect_triangle(r, p1, e1, e2, &t)) continue;
-                                    if (MODE == kAnyHit) { if (t > kEps && t < kRayTInit) { *res = 1u; break; } }
-                                    else { atomicMin(P.ovf_result + item.x, pos); break; }   // later positions of this leaf are larger
-                                }
-                            } else {
-                                expand = true; left = nd.left;
-                            }
+                        ray_finish(r, P.bound);
+                        DevPair32 pr;
+                        load_pair32(P.pairs32, item.y, pr);
+                        if (COUNT) lc.box += 2;
+                        float lo, hi;
+                        if (child_accept<COUNT>(P, r, item.y, 0u, pr.lmin, pr.lmax, lo, hi, lc)) {
+                            if (pr.l_cnt > 0) overflow_leaf<MODE, COUNT>(P, r, pr.l_ref, pr.l_cnt, res, lc);
+                            else { out_a = pr.l_ref; n_out = 1; }
+                        }
+                        if (child_accept<COUNT>(P, r, item.y, 1u, pr.rmin, pr.rmax, lo, hi, lc)) {
+                            if (pr.r_cnt > 0) overflow_leaf<MODE, COUNT>(P, r, pr.r_ref, pr.r_cnt, res, lc);
+                            else { if (n_out) out_b = pr.r_ref; else out_a = pr.r_ref; n_out++; }
                         }
                     }
                 }
-                uint32_t mask = __ballot_sync(0xffffffffu, expand);
-                if (mask) {
-                    uint32_t leader = __ffs(mask) - 1, obase = 0;
-                    if (lane == leader) obase = atomicAdd(cout, 2u * (uint32_t)__popc(mask));
-                    obase = __shfl_sync(0xffffffffu, obase, leader);
-                    if (expand) {
-                        uint32_t oi = obase + 2u * (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                        if (oi + 1u < P.frontier_cap) {           // cannot trigger: the batch is sized for the widest level
-                            out[oi] = make_uint2(item.x, left);
-                            out[oi + 1u] = make_uint2(item.x, left + 1u);
-                        }
+                // warp-aggregated append of the accepted interior children
+                uint32_t incl = n_out;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total) {
+                    uint32_t obase = 0;
+                    if (lane == 31u) obase = atomicAdd(cout, total);
+                    obase = __shfl_sync(0xffffffffu, obase, 31) + incl - n_out;
+                    if (obase + n_out <= P.frontier_cap) {        // cannot fail: the batch is sized for the widest level
+                        if (n_out > 0) out[obase] = make_uint2(item.x, out_a);
+                        if (n_out > 1) out[obase + 1u] = make_uint2(item.x, out_b);
                     }
                 }
             }
@@ -601,7 +671,7 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
         }
         grid.sync();                                      // results and frontier are reused by the next batch
     }
-    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); }
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
 
 // Unwind TraceRay's recursion (raythread.cpp:375-379) for pixels whose chain went past depth 0.
@@ -625,7 +695,7 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
     if (i >= n) return;
     Ray r;
     r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = t0[i];
-    ray_finish(r);
+    ray_finish(r, P.bound);
     LocalCount lc; float tc; uint32_t pos; bool f;
     if (r.t == 0.0f) f = traverse<kFirstLine, false, false>(P, r, tc, pos, lc) == kTravHit;
     else f = traverse<kClosest, false, false>(P, r, tc, pos, lc) == kTravHit;
@@ -635,15 +705,39 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
 }
 
 __global__ void k_debug_primitives(uint32_t n, const double *org, const double *dir, float *ray_t, const double *tri,
-                                   const double *bmin, const double *bmax, uint32_t *tri_hit, uint32_t *box_hit) {
+                                   const double *bmin, const double *bmax, uint32_t *tri_hit, uint32_t *box_hit,
+                                   uint32_t *filter_out, double bound_scale) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Ray r;
     r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = ray_t[i];
-    ray_finish(r);
     double mn[3] = {bmin[3ull * i], bmin[3ull * i + 1], bmin[3ull * i + 2]};
     double mx[3] = {bmax[3ull * i], bmax[3ull * i + 1], bmax[3ull * i + 2]};
-    box_hit[i] = intersect_aabb(r, mn, mx) ? 1u : 0u;
+    const bool exact = intersect_aabb(r, mn, mx);
+    box_hit[i] = exact ? 1u : 0u;
+    if (filter_out) {
+        // the certified filter on the same box: bit 0 exact verdict, bits 1-2 filter (0 undecided, 1 accept, 2 reject),
+        // bit 3 = the filter was usable for this ray.  A certain verdict that contradicts bit 0 is a soundness bug.
+        double bnd[3];
+        bool ordered = true;
+        for (int k = 0; k < 3; k++) {
+            bnd[k] = fmax(fabs(mn[k]), fabs(mx[k])) * bound_scale;
+            ordered = ordered && (mn[k] <= mx[k]) && isfinite(mn[k]) && isfinite(mx[k]);
+        }
+        if (!ordered) bnd[0] = bnd[1] = bnd[2] = INFINITY;
+        ray_finish(r, bnd);
+        uint32_t f = 0;
+        if (r.filt) {
+            const float fmn[3] = {(float)mn[0], (float)mn[1], (float)mn[2]}, fmx[3] = {(float)mx[0], (float)mx[1], (float)mx[2]};
+            BoxBracket b = box_filter(r, fmn, fmx);
+            if (bracket_geom_no(b) || bracket_t_no(b, r.t)) f = 2;
+            else if (bracket_geom_yes(b) && bracket_t_yes(b, r.t)) f = 1;
+            BoxTimes e = box_times(r, mn, mx);
+            bool inside = b.near_lo <= e.tmin && e.tmin <= b.near_hi && b.far_lo <= e.tmax && e.tmax <= b.far_hi;
+            if (!inside) f |= 8u;                                  // bracket does not contain the reference's floats: bug
+        }
+        filter_out[i] = (exact ? 1u : 0u) | ((f & 3u) << 1) | (r.filt ? 8u : 0u) | ((f & 8u) ? 16u : 0u);
+    }
     V3 p1 = ld3(tri + 9ull * i), p2 = ld3(tri + 9ull * i + 3), p3 = ld3(tri + 9ull * i + 6);
     float t;
     bool hit = intersect_triangle(r, p1, vsub(p2, p1), vsub(p3, p1), &t);
@@ -692,6 +786,7 @@ struct DeviceState {
     std::vector<void *> allocs;
     ct_ray_counters snapshot{};      // totals at the end of the previous counted tile
     unsigned long long rays_overflow = 0, rays_in_place = 0;   // DevTotals' overflow counters as of the last read_totals
+    unsigned long long box_exact = 0, tri_exact = 0;
     // rows rendered so far (framebuffer rows), for readback clipping
     int col_lo = 0, col_hi = 0;
 };
@@ -767,6 +862,7 @@ int read_totals(DeviceState &s, ct_ray_counters *out) {   // synchronises the st
     out->rays_primary = h.rays_primary; out->rays_shadow = h.rays_shadow; out->rays_reflection = h.rays_reflection;
     out->box_tests = h.box_tests; out->tri_tests = h.tri_tests;
     s.rays_overflow = h.rays_overflow; s.rays_in_place = h.rays_in_place;
+    s.box_exact = h.box_exact; s.tri_exact = h.tri_exact;
     return CT_OK;
 }
 
@@ -816,15 +912,48 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
 
     Params &p = s.p;
     p.n_tri = d->n_triangles; p.n_lights = d->n_lights;
-    // nodes: reference layout -> device layout (same 64 B, pad zeroed)
-    std::vector<DevNode> nodes(d->n_nodes);
+    // nodes: reference layout -> per-interior-node child pairs (fp32 for the filter, fp64 for the exact path)
+    std::vector<uint32_t> pid_of(d->n_nodes, kNoPos);
+    uint32_t n_pairs = 0;
+    for (uint32_t i = 0; i < d->n_nodes; i++)
+        if (d->nodes[i].triangle_count == 0) pid_of[i] = n_pairs++;
+    std::vector<DevPair32> pairs32(std::max<uint32_t>(n_pairs, 1));
+    std::vector<DevPair64> pairs64(std::max<uint32_t>(n_pairs, 1));
+    double bound[3] = {0, 0, 0};
+    bool boxes_ok = true;
+    auto child_ref = [&](uint32_t c, uint32_t &ref, uint32_t &cnt) {
+        const ct_bvh_node &n = d->nodes[c];
+        cnt = n.triangle_count;
+        ref = cnt ? n.first_triangle_index : pid_of[c];
+    };
     for (uint32_t i = 0; i < d->n_nodes; i++) {
         const ct_bvh_node &n = d->nodes[i];
-        for (int a = 0; a < 3; a++) { nodes[i].bmin[a] = n.aabb_min[a]; nodes[i].bmax[a] = n.aabb_max[a]; }
-        nodes[i].left = n.left_node; nodes[i].first = n.first_triangle_index; nodes[i].count = n.triangle_count; nodes[i].pad = 0;
+        for (int a = 0; a < 3; a++) {
+            // the filter needs finite, ordered boxes (box_filter picks near/far by the ray's sign)
+            if (!(n.aabb_min[a] <= n.aabb_max[a]) || !std::isfinite(n.aabb_min[a]) || !std::isfinite(n.aabb_max[a])) boxes_ok = false;
+            bound[a] = std::max(bound[a], std::max(std::fabs(n.aabb_min[a]), std::fabs(n.aabb_max[a])));
+        }
+        if (n.triangle_count != 0) continue;
+        const ct_bvh_node &L = d->nodes[n.left_node], &R = d->nodes[n.left_node + 1];
+        DevPair32 &p32 = pairs32[pid_of[i]];
+        DevPair64 &p64 = pairs64[pid_of[i]];
+        for (int a = 0; a < 3; a++) {
+            p64.lmin[a] = L.aabb_min[a]; p64.lmax[a] = L.aabb_max[a]; p64.rmin[a] = R.aabb_min[a]; p64.rmax[a] = R.aabb_max[a];
+            p32.lmin[a] = (float)L.aabb_min[a]; p32.lmax[a] = (float)L.aabb_max[a];
+            p32.rmin[a] = (float)R.aabb_min[a]; p32.rmax[a] = (float)R.aabb_max[a];
+        }
+        child_ref(n.left_node, p32.l_ref, p32.l_cnt);
+        child_ref(n.left_node + 1, p32.r_ref, p32.r_cnt);
     }
+    for (int a = 0; a < 3; a++) {
+        p.bound[a] = (boxes_ok && bound[a] < 1e30) ? bound[a] : INFINITY;
+        p.root_min[a] = d->nodes[0].aabb_min[a]; p.root_max[a] = d->nodes[0].aabb_max[a];
+    }
+    child_ref(0, p.root_ref, p.root_cnt);
+    p.n_pairs = n_pairs;
     // triangles in leaf order with precomputed edges
     std::vector<DevTri> tris(d->n_triangles);
+    std::vector<DevTri32> tris32(d->n_triangles);
     uint32_t pos0 = kNoPos;
     const unsigned char *tbase = static_cast<const unsigned char *>(d->triangles);
     for (uint32_t pos = 0; pos < d->n_triangles; pos++) {
@@ -839,6 +968,17 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
             tris[pos].e2[a] = v[6 + a] - v[a];
         }
         tris[pos].orig = k; tris[pos].pad = 0;
+        {   // fp32 copy + magnitudes for tri_filter_miss (rounded up; NaN k1 = "never certify")
+            DevTri32 &t32 = tris32[pos];
+            double k1 = 0, k2 = 0, k3 = 0;
+            for (int a = 0; a < 3; a++) {
+                t32.p1[a] = (float)tris[pos].p1[a]; t32.e1[a] = (float)tris[pos].e1[a]; t32.e2[a] = (float)tris[pos].e2[a];
+                k3 = std::max(k3, std::fabs(tris[pos].p1[a])); k1 = std::max(k1, std::fabs(tris[pos].e1[a])); k2 = std::max(k2, std::fabs(tris[pos].e2[a]));
+            }
+            auto up = [](double x) { float f = (float)x; return ((double)f < x) ? std::nextafterf(f, INFINITY) : f; };
+            const bool in_range = k1 >= 0x1p-30 && k1 <= 0x1p30 && k2 >= 0x1p-30 && k2 <= 0x1p30 && k3 <= 0x1p40;   // NaNs fail
+            t32.k1 = in_range ? up(k1) : NAN; t32.k2 = up(k2); t32.k3 = up(k3);
+        }
         if (d->materials[k].reflection > 0.0f) s.any_reflective = true;
     }
     if (pos0 == kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes is not a permutation (triangle 0 missing)"); }
@@ -860,17 +1000,22 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     p.n_slights = (uint32_t)slights.size();
     p.occ_words = std::max<uint32_t>((d->n_lights + 31u) / 32u, 1u);
     p.n_nodes = d->n_nodes;
-    DevNode *dn; DevTri *dt; ct_material *dm; DevLight *dl; DevShadowLight *dsl;
-    TRY(dev_alloc(s, &dn, nodes.size())); TRY(dev_alloc(s, &dt, tris.size()));
+    DevPair32 *dp32; DevPair64 *dp64; DevTri *dt; ct_material *dm; DevLight *dl; DevShadowLight *dsl;
+    TRY(dev_alloc(s, &dp32, pairs32.size())); TRY(dev_alloc(s, &dp64, pairs64.size())); TRY(dev_alloc(s, &dt, tris.size()));
+    DevTri32 *dt32;
+    TRY(dev_alloc(s, &dt32, tris32.size()));
+    CU(cudaMemcpy(dt32, tris32.data(), tris32.size() * sizeof(DevTri32), cudaMemcpyHostToDevice));
+    p.tris32 = dt32;
     TRY(dev_alloc(s, &dm, d->n_triangles)); TRY(dev_alloc(s, &dl, lights.size()));
     TRY(dev_alloc(s, &dsl, slights.size()));
     if (!slights.empty()) CU(cudaMemcpy(dsl, slights.data(), slights.size() * sizeof(DevShadowLight), cudaMemcpyHostToDevice));
     p.slights = dsl;
-    CU(cudaMemcpy(dn, nodes.data(), nodes.size() * sizeof(DevNode), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dp32, pairs32.data(), pairs32.size() * sizeof(DevPair32), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dp64, pairs64.data(), pairs64.size() * sizeof(DevPair64), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dt, tris.data(), tris.size() * sizeof(DevTri), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dm, d->materials, (size_t)d->n_triangles * sizeof(ct_material), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dl, lights.data(), lights.size() * sizeof(DevLight), cudaMemcpyHostToDevice));
-    p.nodes = dn; p.tris = dt; p.materials = dm; p.lights = dl;
+    p.pairs32 = dp32; p.pairs64 = dp64; p.tris = dt; p.materials = dm; p.lights = dl;
 
     memcpy(p.cam, d->camera_position, sizeof p.cam);
     memcpy(p.rot, d->camera_rotation, sizeof p.rot);
@@ -898,7 +1043,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     if (s.can_overflow) {
         p.ovf_cap = 1u << 16;
         p.ovf_batch_max = 1u << 16;
-        p.frontier_cap = std::max<uint32_t>(1u << 20, 2u * (d->n_nodes / 2u + 2u));
+        p.frontier_cap = std::max<uint32_t>(1u << 20, 2u * (n_pairs / 2u + 2u));
         TRY(dev_alloc(s, &p.ovf, p.ovf_cap));
         TRY(dev_alloc(s, &p.ovf_result, p.ovf_batch_max));
         for (int b = 0; b < 2; b++) TRY(dev_alloc(s, &p.frontier[b], p.frontier_cap));
@@ -1047,6 +1192,17 @@ int ct_gpu_overflow_stats(int device, uint64_t *parked, uint64_t *finished_in_pl
     TRY(read_totals(s, &tmp));
     if (parked) *parked = s.rays_overflow;
     if (finished_in_place) *finished_in_place = s.rays_in_place;
+    return CT_OK;
+}
+
+int ct_gpu_filter_stats(int device, uint64_t *box_exact, uint64_t *tri_exact) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    ct_ray_counters tmp;
+    TRY(read_totals(s, &tmp));
+    if (box_exact) *box_exact = s.box_exact;
+    if (tri_exact) *tri_exact = s.tri_exact;
     return CT_OK;
 }
 
@@ -1201,32 +1357,49 @@ int ct_gpu_debug_closest(int device, uint32_t n, const double *origins, const do
     return CT_OK;
 }
 
-int ct_gpu_debug_primitives(int device, uint32_t n, const double *origins, const double *directions, float *ray_t,
-                            const double *tri, const double *bmin, const double *bmax, uint32_t *tri_hit, uint32_t *box_hit) {
-    if (!origins || !directions || !ray_t || !tri || !bmin || !bmax || !tri_hit || !box_hit) return fail(CT_ERR_INVALID, "NULL array");
+static int debug_primitives_impl(int device, uint32_t n, const double *origins, const double *directions, float *ray_t,
+                                 const double *tri, const double *bmin, const double *bmax, uint32_t *tri_hit, uint32_t *box_hit,
+                                 uint32_t *filter_out, double bound_scale) {
     TRY(check_device(device));
     if (n == 0) return CT_OK;
-    double *d_o = nullptr, *d_d = nullptr, *d_tri = nullptr, *d_mn = nullptr, *d_mx = nullptr; float *d_t = nullptr; uint32_t *d_th = nullptr, *d_bh = nullptr;
+    double *d_o = nullptr, *d_d = nullptr, *d_tri = nullptr, *d_mn = nullptr, *d_mx = nullptr; float *d_t = nullptr;
+    uint32_t *d_th = nullptr, *d_bh = nullptr, *d_f = nullptr;
     int rc = CT_OK;
-    auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_tri); cudaFree(d_mn); cudaFree(d_mx); cudaFree(d_t); cudaFree(d_th); cudaFree(d_bh); };
+    auto cleanup = [&]() { cudaFree(d_o); cudaFree(d_d); cudaFree(d_tri); cudaFree(d_mn); cudaFree(d_mx); cudaFree(d_t); cudaFree(d_th); cudaFree(d_bh); cudaFree(d_f); };
     CUX(cudaMalloc(&d_o, 24ull * n)); CUX(cudaMalloc(&d_d, 24ull * n)); CUX(cudaMalloc(&d_tri, 72ull * n));
     CUX(cudaMalloc(&d_mn, 24ull * n)); CUX(cudaMalloc(&d_mx, 24ull * n)); CUX(cudaMalloc(&d_t, 4ull * n));
     CUX(cudaMalloc(&d_th, 4ull * n)); CUX(cudaMalloc(&d_bh, 4ull * n));
+    if (filter_out) CUX(cudaMalloc(&d_f, 4ull * n));
     CUX(cudaMemcpy(d_o, origins, 24ull * n, cudaMemcpyHostToDevice));
     CUX(cudaMemcpy(d_d, directions, 24ull * n, cudaMemcpyHostToDevice));
-    CUX(cudaMemcpy(d_tri, tri, 72ull * n, cudaMemcpyHostToDevice));
+    if (tri) CUX(cudaMemcpy(d_tri, tri, 72ull * n, cudaMemcpyHostToDevice));
+    else CUX(cudaMemset(d_tri, 0, 72ull * n));
     CUX(cudaMemcpy(d_mn, bmin, 24ull * n, cudaMemcpyHostToDevice));
     CUX(cudaMemcpy(d_mx, bmax, 24ull * n, cudaMemcpyHostToDevice));
     CUX(cudaMemcpy(d_t, ray_t, 4ull * n, cudaMemcpyHostToDevice));
-    k_debug_primitives<<<(n + 127) / 128, 128>>>(n, d_o, d_d, d_t, d_tri, d_mn, d_mx, d_th, d_bh);
+    k_debug_primitives<<<(n + 127) / 128, 128>>>(n, d_o, d_d, d_t, d_tri, d_mn, d_mx, d_th, d_bh, d_f, bound_scale);
     CUX(cudaGetLastError());
     CUX(cudaDeviceSynchronize());
-    CUX(cudaMemcpy(ray_t, d_t, 4ull * n, cudaMemcpyDeviceToHost));
-    CUX(cudaMemcpy(tri_hit, d_th, 4ull * n, cudaMemcpyDeviceToHost));
-    CUX(cudaMemcpy(box_hit, d_bh, 4ull * n, cudaMemcpyDeviceToHost));
+    if (tri) CUX(cudaMemcpy(ray_t, d_t, 4ull * n, cudaMemcpyDeviceToHost));
+    if (tri_hit) CUX(cudaMemcpy(tri_hit, d_th, 4ull * n, cudaMemcpyDeviceToHost));
+    if (box_hit) CUX(cudaMemcpy(box_hit, d_bh, 4ull * n, cudaMemcpyDeviceToHost));
+    if (filter_out) CUX(cudaMemcpy(filter_out, d_f, 4ull * n, cudaMemcpyDeviceToHost));
     cleanup();
 #undef CUX
     return CT_OK;
+}
+
+int ct_gpu_debug_primitives(int device, uint32_t n, const double *origins, const double *directions, float *ray_t,
+                            const double *tri, const double *bmin, const double *bmax, uint32_t *tri_hit, uint32_t *box_hit) {
+    if (!origins || !directions || !ray_t || !tri || !bmin || !bmax || !tri_hit || !box_hit) return fail(CT_ERR_INVALID, "NULL array");
+    return debug_primitives_impl(device, n, origins, directions, ray_t, tri, bmin, bmax, tri_hit, box_hit, nullptr, 1.0);
+}
+
+int ct_gpu_debug_filter(int device, uint32_t n, const double *origins, const double *directions, const float *ray_t,
+                        const double *bmin, const double *bmax, double bound_scale, uint32_t *verdict) {
+    if (!origins || !directions || !ray_t || !bmin || !bmax || !verdict) return fail(CT_ERR_INVALID, "NULL array");
+    if (!(bound_scale >= 1.0)) return fail(CT_ERR_INVALID, "bound_scale must be >= 1");
+    return debug_primitives_impl(device, n, origins, directions, const_cast<float *>(ray_t), nullptr, bmin, bmax, nullptr, nullptr, verdict, bound_scale);
 }
 
 int ct_gpu_shutdown(int device) {

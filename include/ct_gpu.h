@@ -169,6 +169,10 @@ int ct_gpu_set_option(const char *name, long long value);
  * of them found the parking buffer full and were finished by their own thread.  Synchronises. */
 int ct_gpu_overflow_stats(int device, uint64_t *parked, uint64_t *finished_in_place);
 
+/* With CT_FLAG_COUNT_TESTS: how many of the counted box / triangle tests the certified fp32 filters could not
+ * decide and handed to the reference's fp64 arithmetic (since upload / last counter reset).  Synchronises. */
+int ct_gpu_filter_stats(int device, uint64_t *box_exact, uint64_t *tri_exact);
+
 /* Blocks until at most `max_in_flight` of the submitted tiles are unfinished (0 == ct_gpu_sync).  Lets a
  * boss keep a GPU fed while tile stealing still follows real progress. */
 int ct_gpu_throttle(int device, int max_in_flight);
@@ -193,6 +197,14 @@ int ct_gpu_debug_closest(int device, uint32_t n, const double *origins, const do
 int ct_gpu_debug_primitives(int device, uint32_t n, const double *origins, const double *directions, float *ray_t,
                             const double *tri, const double *bmin, const double *bmax,
                             uint32_t *tri_hit, uint32_t *box_hit);
+
+/* Soundness test entry for the certified fp32 slab filter that fronts IntersectAABB on the device:
+ * n independent (ray, box) cases.  The filter's per-axis magnitude bound is max(|bmin|,|bmax|) * bound_scale
+ * (bound_scale >= 1 imitates a small box inside a large scene).  verdict[i]: bit 0 = the reference's verdict,
+ * bits 1-2 = the filter's (0 undecided, 1 accept, 2 reject), bit 3 = filter usable for this ray, bit 4 = the
+ * filter's bracket failed to contain the reference's float tmin/tmax (must never be set). */
+int ct_gpu_debug_filter(int device, uint32_t n, const double *origins, const double *directions, const float *ray_t,
+                        const double *bmin, const double *bmax, double bound_scale, uint32_t *verdict);
 
 /* Frees everything held for `device` (the reference never frees; this makes the library re-entrant). */
 int ct_gpu_shutdown(int device);

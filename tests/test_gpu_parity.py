@@ -68,6 +68,51 @@ def test_primitive_kats_against_reference(gpu):
     assert np.array_equal(t_out.view(np.uint32), z["t_out"].view(np.uint32))
 
 
+def _filter_cases(rng, n):
+    """(origins, directions, ray_t, bmin, bmax): generic boxes, then adversarial ones whose slab quotients tie."""
+    o = rng.normal(size=(n, 3)) * rng.choice([0.1, 5.0, 60.0, 4e9], (n, 1))
+    d = rng.normal(size=(n, 3)) * rng.choice([1e-3, 1.0, 300.0, 4e9], (n, 1))
+    d[rng.random((n, 3)) < 0.03] = 0.0                               # the x = 0 pixel column has dir.x == 0
+    c = o + d * rng.uniform(-1, 3, (n, 1)) + rng.normal(size=(n, 3)) * rng.choice([0.0, 1e-9, 0.05, 10.0], (n, 1))
+    half = np.abs(rng.normal(size=(n, 3))) * rng.choice([1e-6, 0.02, 1.0, 30.0], (n, 1))
+    half[rng.random((n, 3)) < 0.15] = 0.0                            # zero-thickness boxes of axis-aligned triangles
+    bmin, bmax = c - half, c + half
+    # ties: every axis enters at exactly t1 and leaves at exactly t2 (corner to corner), then nudged by a few ulps
+    k = n // 3
+    t1 = rng.uniform(-2, 5, (k, 1)); t2 = t1 + np.abs(rng.normal(size=(k, 1))) * rng.choice([0.0, 1e-7, 1.0], (k, 1))
+    pa, pb = o[:k] + t1 * d[:k], o[:k] + t2 * d[:k]
+    lo, hi = np.minimum(pa, pb), np.maximum(pa, pb)
+    for arr in (lo, hi):
+        steps = rng.integers(-3, 4, arr.shape)
+        for _ in range(3):
+            arr[:] = np.where(steps > 0, np.nextafter(arr, np.inf), np.where(steps < 0, np.nextafter(arr, -np.inf), arr))
+            steps = steps - np.sign(steps)
+    hi = np.maximum(lo, hi)
+    bmin[:k], bmax[:k] = lo, hi
+    rt = rng.choice(np.array([1e30, 1e30, 0.0, 1.0, 3.5], np.float32), n)
+    rt[:k:2] = (t1[::2, 0] * rng.choice([1.0, 1.0 + 1e-7, 1.0 - 1e-7], t1[::2, 0].shape)).astype(np.float32)   # ray.t next to tmin
+    return o, d, rt, bmin, bmax
+
+
+@pytest.mark.parametrize("bound_scale", [1.0, 64.0])
+def test_slab_filter_is_sound_and_mostly_decides(gpu, bound_scale):
+    """The certified fp32 filter in front of IntersectAABB may only ever answer what the reference's
+    arithmetic answers; undecided cases fall back to that arithmetic.  1M generic + adversarial (ray, box) cases."""
+    rng = np.random.default_rng(11)
+    o, d, rt, bmin, bmax = _filter_cases(rng, 1 << 20)
+    v = gpu.debug_filter(o, d, rt, bmin, bmax, bound_scale)
+    exact, filt, usable, escaped = v & 1, (v >> 1) & 3, (v >> 3) & 1, (v >> 4) & 1
+    assert not escaped.any(), f"{int(escaped.sum())} brackets do not contain the reference's tmin/tmax"
+    assert not ((filt == 1) & (exact == 0)).any() and not ((filt == 2) & (exact == 1)).any()
+    assert (filt[usable == 0] == 0).all()
+    zero_dir = (d == 0).any(1)
+    assert (usable[zero_dir] == 0).all()                              # +-inf / NaN quotients: reference arithmetic only
+    generic = (np.arange(len(v)) >= len(v) // 3) & ((bmax - bmin) > 0).all(1)     # ordinary boxes with some thickness
+    decided = (filt[generic & (usable == 1)] != 0).mean()
+    assert decided > 0.5, decided                                     # (real scenes: > 99.8 %, see tools/perf_stages.py)
+    assert ((filt == 1).sum() > 1000) and ((filt == 2).sum() > 1000)
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_golden_frames_from_reference(case, golden, scene_loader, gpu):
     fs, meta = case_scene(case, golden, scene_loader)

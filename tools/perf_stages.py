@@ -65,6 +65,12 @@ for name in names:
     per = {}
     for nm, d, ms in best[1]:
         per[nm] = per.get(nm, 0.0) + ms
+    # one counted frame for the filter statistics
+    r.shutdown()
+    r = api.GpuRenderer(0).upload(fs, W, H, max_depth=depth, flags=api.CT_FLAG_COUNT_TESTS)
+    cc = r.render_tile(counters=True)
+    bx, tx = r.filter_stats()
+    print(f"   tests: box={cc['box_tests']} (fp64 {bx / max(cc['box_tests'], 1) * 100:.2f}%)  tri={cc['tri_tests']} (fp64 {tx / max(cc['tri_tests'], 1) * 100:.2f}%)")
     print(f"{name}: {best[0]:.3f} ms/frame  {rays / best[0] / 1e3:.1f} Mrays/s  rays={rays}  " +
           " ".join(f"{k}={v:.3f}" for k, v in per.items()) + f"  overflow={r.overflow_stats()}", flush=True)
     r.shutdown()
