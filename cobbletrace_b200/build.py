@@ -53,7 +53,8 @@ def build_gpu(force: bool = False, verbose: bool = False) -> str:
     deps = srcs + _glob(CSRC, (".cuh",)) + [os.path.join(ROOT, "include", "ct_gpu.h")]
     if not force and _newer(GPU_LIB, deps):
         return GPU_LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", GPU_LIB] + srcs
+    extra = os.environ.get("CT_NVCC_EXTRA", "").split()         # experiments only, e.g. -DCT_MIN_BLOCKS=5
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", GPU_LIB] + srcs
     subprocess.check_call(cmd, cwd=ROOT)
     return GPU_LIB
 

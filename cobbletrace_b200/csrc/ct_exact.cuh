@@ -45,23 +45,29 @@ CT_DEV float macro_min(float a, float b) { return (a < b) ? a : b; }
 CT_DEV float macro_max(float a, float b) { return (a > b) ? a : b; }
 
 // ---- rays ------------------------------------------------------------------------------------------
-// ray_t (scenefile.h:104-108) plus the per-ray constants of the certified fp32 slab filter (box_filter).
-struct Ray {
+struct Ray {        // ray_t (scenefile.h:104-108)
     V3 o, d;
+    float t;
+};
+
+// What the traversal loop keeps in registers: ray.t and the per-ray constants of the two certified fp32 filters
+// (box_filter, tri_filter_miss).  The fp64 origin/direction the reference's own arithmetic needs stay in local
+// memory (r64[0..2] = origin, r64[3..5] = direction) and are only touched when a filter cannot decide.
+struct TRay {
     float t;
     float rdf[3];   // float(1/d)
     float cl[3];    // round-down float of  -o/d - E   } E = per-axis bound on |filter quotient - reference quotient|,
-    float cu[3];    // round-up   float of  -o/d + E   } see ray_finish
-    bool filt;      // false: some axis cannot be bounded (d == 0, non-finite, absurd magnitudes) -> exact tests only
-    // certified fp32 triangle filter (tri_filter_miss): float copies and magnitudes
-    float of[3], df[3];
+    float cu[3];    // round-up   float of  -o/d + E   } see tray_setup
+    float of[3], df[3];   // float(o), float(d)
     float cd;       // 2^-17 * max|d_i|, rounded up
     float om;       // max|o_i|, rounded up
-    bool tfilt;     // false: magnitudes outside the range the filter's error analysis covers
+    bool filt;      // false: some axis cannot be bounded (d == 0, non-finite, absurd magnitudes) -> exact slab tests only
+    bool tfilt;     // false: magnitudes outside the range the triangle filter's error analysis covers
+    const double *r64;
 };
 
-// Per-ray setup of the slab filter.  bound[k] >= |b| for every node bound b on axis k (computed at upload;
-// +inf when the tree holds non-finite or ill-ordered boxes, which disables the filter).
+// Per-ray setup of the filters.  bound[k] >= |b| for every node bound b on axis k (computed at upload;
+// +inf when the tree holds non-finite or ill-ordered boxes, which disables the slab filter).
 //
 // For a node bound b on axis k the reference computes  q_ref = float( fl64( fl64(b - o) / d ) )   (bvh.cpp:166-175).
 // With q* = (b - o)/d in real arithmetic, |q_ref - q*| <= (2^-24 + 2^-51) |q*|.
@@ -70,29 +76,33 @@ struct Ray {
 // so |y - q_ref| <= 3.01 * 2^-24 * (|b| + |o|) / |d|  <=  E := 2^-22 * (bound + |o|) * |1/d| .
 // cl / cu fold -E / +E into c, rounded DOWN / UP to float, and the filter's FMAs round down / up as well, so
 //     fma_rd(bf, rdf, cl) <= q_ref <= fma_ru(bf, rdf, cu)          for every finite node bound.
-CT_DEV void ray_finish(Ray &r, const double bound[3]) {
-    const double o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z};
+CT_DEV void tray_setup(TRay &r, const Ray &ray, const double bound[3], double *r64) {
+    const double o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         double rd = __ddiv_rn(1.0, d[k]);
         double c = __dmul_rn(-o[k], rd);
-        double m = __dmul_rn(__dadd_rn(bound[k], fabs(o[k])), fabs(rd));
+        double sum = __dadd_rn(bound[k], fabs(o[k]));
+        double m = __dmul_rn(sum, fabs(rd));
         double e = __dmul_rn(m, 0x1p-22);
-        // every quantity must be an ordinary number well inside the float range (rd != 0 rules out d = +-inf, a finite
-        // rd rules out d = 0, NaNs fail the comparisons); tiny E would let float underflow matter
-        ok = ok && (m < 0x1p100) && (fabs(rd) > 0x1p-100) && (e > 0x1p-100);
+        // every quantity must be an ordinary number well inside the float range (a finite non-zero rd rules out
+        // d = 0 and d = +-inf, NaNs fail the comparisons); magnitudes near the float subnormals are left alone
+        ok = ok && (m < 0x1p100) && (fabs(rd) > 0x1p-100) && (fabs(rd) < 0x1p100) && (e > 0x1p-100) && (sum > 0x1p-60);
         r.rdf[k] = __double2float_rn(rd);
         r.cl[k] = __double2float_rd(__dsub_rd(c, e));
         r.cu[k] = __double2float_ru(__dadd_ru(c, e));
+        r.of[k] = __double2float_rn(o[k]);
+        r.df[k] = __double2float_rn(d[k]);
+        r64[k] = o[k]; r64[3 + k] = d[k];
     }
     r.filt = ok;
     double dm = fmax(fmax(fabs(d[0]), fabs(d[1])), fabs(d[2])), om = fmax(fmax(fabs(o[0]), fabs(o[1])), fabs(o[2]));
     r.tfilt = (dm >= 0x1p-20) && (dm <= 0x1p40) && (om <= 0x1p40);          // NaNs fail
-#pragma unroll
-    for (int k = 0; k < 3; k++) { r.of[k] = __double2float_rn(o[k]); r.df[k] = __double2float_rn(d[k]); }
     r.cd = __double2float_ru(__dmul_ru(dm, 0x1p-17));
     r.om = __double2float_ru(om);
+    r.t = ray.t;
+    r.r64 = r64;
 }
 
 // ---- IntersectAABB (bvh.cpp:165-179) -------------------------------------------------------------------
@@ -129,7 +139,7 @@ CT_DEV bool intersect_aabb(const Ray &r, const double bmin[3], const double bmax
 // b -> q_ref(b) is monotone; max over axes of brackets brackets the max).  Only valid when r.filt.
 struct BoxBracket { float near_lo, near_hi, far_lo, far_hi; };
 
-CT_DEV BoxBracket box_filter(const Ray &r, const float bmin[3], const float bmax[3]) {
+CT_DEV BoxBracket box_filter(const TRay &r, const float bmin[3], const float bmax[3]) {
     float nl[3], nh[3], fl[3], fh[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -151,8 +161,8 @@ CT_DEV BoxBracket box_filter(const Ray &r, const float bmin[3], const float bmax
 // Verdicts that follow from the bracket alone (each is true only when certain; both false = undecided).
 //   geometry:  tmax >= tmin && tmax > 0      (independent of ray.t)
 //   distance:  tmin < ray.t
-CT_DEV bool bracket_geom_yes(const BoxBracket &b) { return b.far_lo >= b.near_hi && b.far_lo > 0.0f; }
-CT_DEV bool bracket_geom_no(const BoxBracket &b) { return b.far_hi < b.near_lo || b.far_hi <= 0.0f; }
+CT_DEV bool bracket_geom_yes(const BoxBracket &b) { return (b.far_lo >= b.near_hi) & (b.far_lo > 0.0f); }
+CT_DEV bool bracket_geom_no(const BoxBracket &b) { return (b.far_hi < b.near_lo) | (b.far_hi <= 0.0f); }
 CT_DEV bool bracket_t_yes(const BoxBracket &b, float ray_t) { return b.near_hi < ray_t; }
 CT_DEV bool bracket_t_no(const BoxBracket &b, float ray_t) { return b.near_lo >= ray_t; }
 
@@ -195,7 +205,7 @@ CT_DEV bool intersect_triangle(const Ray &r, V3 p1, V3 e1, V3 e2, float *t_out) 
 // normal float range; ES, EQ >= 2^-40 keeps the reference's f * S from underflowing to -0.
 // tri: 12 floats p1.xyz, K3, e1.xyz, K1, e2.xyz, K2.
 template <bool ANY_HIT>
-CT_DEV bool tri_filter_miss(const Ray &r, float4 t0, float4 t1, float4 t2) {
+CT_DEV bool tri_filter_miss(const TRay &r, float4 t0, float4 t1, float4 t2) {
     const float k3 = t0.w, k1 = t1.w, k2 = t2.w;
     // h = d x e2, q = s x e1
     const float hx = __fmaf_rn(r.df[1], t2.z, -__fmul_rn(r.df[2], t2.y));
@@ -209,25 +219,26 @@ CT_DEV bool tri_filter_miss(const Ray &r, float4 t0, float4 t1, float4 t2) {
     const float qz = __fmaf_rn(sx, t1.y, -__fmul_rn(sy, t1.x));
     const float Q = __fmaf_rn(r.df[0], qx, __fmaf_rn(r.df[1], qy, __fmul_rn(r.df[2], qz)));
     const float sig = __fadd_ru(r.om, k3);                       // O + K3
-    const float ea = __fmul_ru(__fmul_ru(k1, k2), r.cd);
+    const float k12 = __fmul_ru(k1, k2);
+    const float ea = __fmul_ru(k12, r.cd);
     const float es = fmaxf(__fmul_ru(__fmul_ru(r.cd, k2), sig), 0x1p-40f);
     const float eq = fmaxf(__fmul_ru(__fmul_ru(r.cd, k1), sig), 0x1p-40f);
     const float aa = fabsf(A);
-    if (__fadd_ru(aa, ea) < 9.9999e-05f) return true;             // |a| < 1e-4 for certain (bvh.cpp:152)
-    if (!(aa > __fmul_ru(2.0f, ea))) return false;                // sign of a not certain (also NaN K1)
-    const float Ss = A > 0.0f ? S : -S, Qs = A > 0.0f ? Q : -Q;   // S, Q oriented so that u = Ss/|A|, v = Qs/|A|
-    if (Ss < -__fmul_ru(2.0f, es)) return true;                   // u < 0
-    if (Qs < -__fmul_ru(2.0f, eq)) return true;                   // v < 0
-    if (__fsub_rd(Ss, aa) > __fmul_ru(2.0f, __fadd_ru(es, ea))) return true;                                   // u > 1
-    if (__fsub_rd(__fadd_rd(Ss, Qs), aa) > __fmul_ru(2.0f, __fadd_ru(__fadd_ru(es, eq), ea))) return true;      // u + v > 1
+    const bool tiny_a = __fadd_ru(aa, ea) < 9.9999e-05f;          // |a| < 1e-4 for certain (bvh.cpp:152)
+    const bool sign_ok = aa > __fmul_ru(2.0f, ea);                // sign of a certain (false for NaN K1)
+    const float Ss = A > 0.0f ? S : -S, Qs = A > 0.0f ? Q : -Q;   // oriented so that u = Ss/|A|, v = Qs/|A|
+    bool miss = (Ss < -__fmul_ru(2.0f, es))                                                                        // u < 0
+              | (Qs < -__fmul_ru(2.0f, eq))                                                                        // v < 0
+              | (__fsub_rd(Ss, aa) > __fmul_ru(2.0f, __fadd_ru(es, ea)))                                           // u > 1
+              | (__fsub_rd(__fadd_rd(Ss, Qs), aa) > __fmul_ru(2.0f, __fadd_ru(__fadd_ru(es, eq), ea)));            // u + v > 1
     if (ANY_HIT) {
         const float T = __fmaf_rn(t2.x, qx, __fmaf_rn(t2.y, qy, __fmul_rn(t2.z, qz)));
         const float Ts = A > 0.0f ? T : -T;
-        const float et = __fmul_ru(__fmul_ru(__fmul_ru(k1, k2), sig), 0x1p-16f);      // 2 * ET
+        const float et = __fmul_ru(__fmul_ru(k12, sig), 0x1p-16f);                    // 2 * ET
         // t <= 1e-4 for certain:  T <= 1e-4 (1 - 2^-20) |A|
-        if (__fadd_ru(Ts, et) <= __fmul_rd(9.9999e-05f, __fsub_rd(aa, ea))) return true;
+        miss |= __fadd_ru(Ts, et) <= __fmul_rd(9.9999e-05f, __fsub_rd(aa, ea));
     }
-    return false;
+    return tiny_a | (sign_ok & miss);
 }
 
 // ReflectRay raythread.cpp:270-273: 2.0*normal*Dot(normal,ray) - ray

@@ -44,7 +44,10 @@ using namespace ct;
 constexpr int kStackMax = 96;        // DFS stack entries per ray (tree depth limit, checked at upload)
 constexpr int kMaxDevices = 16;
 constexpr int kBlockThreads = 128;   // 4 warps per CTA
-constexpr int kMinBlocks = 6;        // traversal kernels: resident CTAs per SM the register allocation must allow
+#ifndef CT_MIN_BLOCKS
+#define CT_MIN_BLOCKS 6
+#endif
+constexpr int kMinBlocks = CT_MIN_BLOCKS;   // traversal kernels: resident CTAs per SM the register allocation must allow
 constexpr int kOvfThreads = 256;     // k_overflow CTA
 constexpr int kMaxLaunches = 80;     // launches of one tile (work cursors / stage events)
 constexpr uint32_t kNoPos = 0xffffffffu;
@@ -155,22 +158,25 @@ CT_DEV void load_pair32(const DevPair32 *pairs, uint32_t pid, DevPair32 &p) {
     p.l_ref = m.x; p.l_cnt = m.y; p.r_ref = m.z; p.r_cnt = m.w;
 }
 
-// The reference's own slab arithmetic for child `side` (0 left, 1 right) of pair `pid`.  Cold path.
-__device__ __noinline__ BoxTimes exact_child(const DevPair64 *pairs, uint32_t pid, uint32_t side, double ox, double oy, double oz,
-                                             double dx, double dy, double dz) {
+// ---- cold paths: the reference's own fp64 arithmetic, out of line so that its operands only occupy registers
+// while it runs.  `r64` = the ray's origin (0..2) and direction (3..5) in local memory.
+__device__ __noinline__ BoxTimes exact_child(const DevPair64 *pairs, uint32_t pid, uint32_t side, const double *r64) {
     const double2 *q = reinterpret_cast<const double2 *>(pairs + pid) + 3u * side;
     double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    return box_times_exact(ox, oy, oz, dx, dy, dz, a.x, a.y, b.x, b.y, c.x, c.y);
+    return box_times_exact(r64[0], r64[1], r64[2], r64[3], r64[4], r64[5], a.x, a.y, b.x, b.y, c.x, c.y);
 }
 
-// The reference's own triangle arithmetic for the triangle at leaf position `pos`.  Out of line so that the fp64
-// operands only occupy registers while it runs.
+CT_DEV bool exact_root(const Params &P, const double *r64, float ray_t) {
+    return box_accept(box_times_exact(r64[0], r64[1], r64[2], r64[3], r64[4], r64[5], P.root_min[0], P.root_min[1], P.root_min[2],
+                                      P.root_max[0], P.root_max[1], P.root_max[2]), ray_t);
+}
+
 struct TriHit { bool hit; float t; };
-__device__ __noinline__ TriHit tri_exact(const DevTri *tris, uint32_t pos, double ox, double oy, double oz, double dx, double dy, double dz) {
+__device__ __noinline__ TriHit tri_exact(const DevTri *tris, uint32_t pos, const double *r64) {
     V3 p1, e1, e2;
     load_tri(tris, pos, p1, e1, e2);
     Ray r;
-    r.o = {ox, oy, oz}; r.d = {dx, dy, dz};
+    r.o = {r64[0], r64[1], r64[2]}; r.d = {r64[3], r64[4], r64[5]}; r.t = 0.0f;
     TriHit h;
     h.t = 0.0f;
     h.hit = intersect_triangle(r, p1, e1, e2, &h.t);
@@ -180,35 +186,45 @@ __device__ __noinline__ TriHit tri_exact(const DevTri *tris, uint32_t pos, doubl
 // IntersectTriangle's verdict for the triangle at `pos`: the fp32 filter discards what certainly has no effect,
 // the fp64 arithmetic decides the rest.
 template <bool ANY_HIT, bool COUNT>
-CT_DEV TriHit leaf_triangle(const Params &P, const Ray &r, uint32_t pos, LocalCount &lc) {
-    if (r.tfilt) {
-        const float4 *q = reinterpret_cast<const float4 *>(P.tris32 + pos);
-        if (tri_filter_miss<ANY_HIT>(r, __ldg(q), __ldg(q + 1), __ldg(q + 2))) return {false, 0.0f};
-    }
+CT_DEV TriHit leaf_triangle(const Params &P, const TRay &r, uint32_t pos, LocalCount &lc) {
+    const float4 *q = reinterpret_cast<const float4 *>(P.tris32 + pos);
+    const bool miss = tri_filter_miss<ANY_HIT>(r, __ldg(q), __ldg(q + 1), __ldg(q + 2));
+    if (r.tfilt & miss) return {false, 0.0f};
     if (COUNT) lc.tri_exact++;
-    return tri_exact(P.tris, pos, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
+    return tri_exact(P.tris, pos, r.r64);
 }
 
-// IntersectAABB's verdict for one child, bit-exact: the fp32 bracket decides when it can, the fp64 arithmetic
-// otherwise.  On return [near_lo, near_hi] brackets the reference's tmin (collapsed to the exact value when the
-// fp64 path ran), which is what a deferred `tmin < ray.t` re-check needs.
+// IntersectAABB's verdicts for the two children of pair `pid`, bit-exact: the fp32 brackets decide when they
+// can (no branch on the way), the fp64 arithmetic otherwise.  On return [r_lo, r_hi] brackets the reference's
+// tmin of the RIGHT child (collapsed to the exact value when the fp64 path ran), which is what its deferred
+// `tmin < ray.t` re-check needs.
 template <bool COUNT>
-CT_DEV bool child_accept(const Params &P, const Ray &r, uint32_t pid, uint32_t side, const float bmin[3], const float bmax[3],
-                         float &near_lo, float &near_hi, LocalCount &lc) {
-    if (r.filt) {
-        BoxBracket b = box_filter(r, bmin, bmax);
-        near_lo = b.near_lo; near_hi = b.near_hi;
-        if (bracket_geom_no(b) || bracket_t_no(b, r.t)) return false;
-        if (bracket_geom_yes(b) && bracket_t_yes(b, r.t)) return true;
+CT_DEV void pair_accept(const Params &P, const TRay &r, uint32_t pid, const DevPair32 &pr, bool &hit_l, bool &hit_r,
+                        float &r_lo, float &r_hi, LocalCount &lc) {
+    const BoxBracket bl = box_filter(r, pr.lmin, pr.lmax), br = box_filter(r, pr.rmin, pr.rmax);
+    const bool no_l = bracket_geom_no(bl) | bracket_t_no(bl, r.t), yes_l = bracket_geom_yes(bl) & bracket_t_yes(bl, r.t);
+    const bool no_r = bracket_geom_no(br) | bracket_t_no(br, r.t), yes_r = bracket_geom_yes(br) & bracket_t_yes(br, r.t);
+    hit_l = yes_l; hit_r = yes_r;
+    r_lo = br.near_lo; r_hi = br.near_hi;
+    const bool open_l = !r.filt | !(no_l | yes_l), open_r = !r.filt | !(no_r | yes_r);
+    if (open_l | open_r) {
+        if (open_l) {
+            if (COUNT) lc.box_exact++;
+            hit_l = box_accept(exact_child(P.pairs64, pid, 0u, r.r64), r.t);
+        }
+        if (open_r) {
+            if (COUNT) lc.box_exact++;
+            BoxTimes e = exact_child(P.pairs64, pid, 1u, r.r64);
+            r_lo = r_hi = e.tmin;
+            hit_r = box_accept(e, r.t);
+        }
     }
-    if (COUNT) lc.box_exact++;
-    BoxTimes e = exact_child(P.pairs64, pid, side, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
-    near_lo = near_hi = e.tmin;
-    return box_accept(e, r.t);
 }
 
 enum TraverseMode { kClosest, kAnyHit, kFirstLine };
 enum { kTravMiss = 0, kTravHit = 1, kTravOverBudget = -1 };
+
+constexpr uint32_t kFullMask = 0xffffffffu;
 
 // IntersectBVHClosest (bvh.cpp:198-222) as an explicit-stack DFS in the reference's visit order (left subtree,
 // then right).  The reference tests a node's box when it VISITS the node; here both children of a passing
@@ -219,85 +235,165 @@ enum { kTravMiss = 0, kTravHit = 1, kTravOverBudget = -1 };
 //     and is dropped, and one that passes now is pushed WITH (a bracket of) its tmin and re-checked against the
 //     then-current ray.t when popped.  Same boxes accepted, same triangles tested in the same order, same counts.
 //   kClosest   general semantics (any initial ray.t).
-//   kAnyHit    shadow rays (ray.t = 1e30f): `found` is all that is used (raythread.cpp:306), so stop at
-//              the first triangle that lowers ray.t, i.e. bary pass and 1e-4 < t < 1e30.
 //   kFirstLine reflection rays (ray.t = 0, raythread.cpp:373): ray.t never changes, the first bary
 //              pass in DFS order becomes closestIndex with tclosest = 0, so stop there.
-// Returns kTravHit/kTravMiss: kAnyHit -> occluded; others -> ray.t != 1e30f ("found").
-// With BUDGET, gives up with kTravOverBudget after P.budget node visits + triangle tests; the caller parks
-// the ray for k_overflow (both early-exit modes have an order-independent answer, see k_overflow).
-template <TraverseMode MODE, bool COUNT, bool BUDGET>
-CT_DEV int traverse(const Params &P, Ray &r, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
-    // stack entry = a pushed right child: (ref, cnt) and, in kClosest mode, the bracket of its tmin plus
-    // 2 * parent pair + 1 to find its fp64 bounds again
+// (kAnyHit has its own loop, traverse_any_hit.)
+// WARP-SYNCHRONOUS: all 32 lanes call it (lanes without a ray pass active = false); every iteration = one node
+// visit per live lane, and the lanes re-converge at the vote that ends it (left to itself the compiler lets the
+// lanes of a warp drift apart for the whole walk: measured 8 of 32 lanes active).
+// Returns kTravHit/kTravMiss = ray.t != 1e30f ("found"); kFirstLine gives up with kTravOverBudget after `budget`
+// node visits + triangle tests and the caller parks the ray for k_overflow (order-independent answer, see there).
+template <TraverseMode MODE, bool COUNT>
+CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    static_assert(MODE != kAnyHit, "shadow rays use traverse_any_hit");
+    // stack entry = a pushed right child: (ref, cnt) and, in kClosest mode, the bracket of its tmin plus its
+    // parent pair to find its fp64 bounds again
     uint32_t stk_ref[kStackMax], stk_cnt[kStackMax];
     uint32_t stk_src[MODE == kClosest ? kStackMax : 1];
     float stk_lo[MODE == kClosest ? kStackMax : 1], stk_hi[MODE == kClosest ? kStackMax : 1];
     int sp = 0;
-    uint32_t spent = 0;
+    uint32_t spent = 1u;
+    int result = kTravMiss;
     tclosest = kFinf;          // raythread.cpp:204
     closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
-    if (COUNT) lc.box++;
-    if (!intersect_aabb(r, P.root_min, P.root_max)) return (MODE == kAnyHit || r.t == kRayTInit) ? kTravMiss : kTravHit;
     uint32_t cur_ref = P.root_ref, cur_cnt = P.root_cnt;   // current (already accepted) node
-    if (BUDGET) spent = 1u + cur_cnt;
-    while (true) {
-        if (cur_cnt > 0) {
-            for (uint32_t i = 0; i < cur_cnt; i++) {
-                uint32_t pos = cur_ref + i;
-                if (COUNT) lc.tri++;
-                const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
-                const float t = th.t;
-                if (th.hit) {
-                    if (MODE == kAnyHit) {
-                        if (t > kEps && t < kRayTInit) return kTravHit;
-                    } else if (MODE == kFirstLine) {
-                        closest_pos = pos; tclosest = 0.0f;
-                        return kTravHit;
-                    } else {
-                        if (t > kEps) r.t = macro_min(r.t, t);                     // bvh.cpp:161
-                        if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
-                            closest_pos = pos; tclosest = r.t;
+    bool live = false;
+    if (active) {
+        if (COUNT) lc.box++;
+        live = exact_root(P, r.r64, r.t);
+    }
+    while (__any_sync(kFullMask, live)) {
+        if (live) {
+            bool need_pop = true;
+            if (cur_cnt > 0) {
+                for (uint32_t i = 0; i < cur_cnt; i++) {
+                    uint32_t pos = cur_ref + i;
+                    if (COUNT) lc.tri++;
+                    const TriHit th = leaf_triangle<false, COUNT>(P, r, pos, lc);
+                    if (th.hit) {
+                        if (MODE == kFirstLine) {
+                            closest_pos = pos; tclosest = 0.0f;
+                            live = false; need_pop = false;
+                            break;
+                        } else {
+                            if (th.t > kEps) r.t = macro_min(r.t, th.t);               // bvh.cpp:161
+                            if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
+                                closest_pos = pos; tclosest = r.t;
+                            }
                         }
                     }
                 }
-            }
-        } else {
-            DevPair32 pr;
-            load_pair32(P.pairs32, cur_ref, pr);
-            if (COUNT) lc.box += 2;
-            if (BUDGET) { spent += 2u + pr.l_cnt + pr.r_cnt; if (spent > P.budget) return kTravOverBudget; }
-            float l_lo, l_hi, r_lo, r_hi;
-            const bool hit_l = child_accept<COUNT>(P, r, cur_ref, 0u, pr.lmin, pr.lmax, l_lo, l_hi, lc);
-            const bool hit_r = child_accept<COUNT>(P, r, cur_ref, 1u, pr.rmin, pr.rmax, r_lo, r_hi, lc);
-            if (hit_l) {
-                if (hit_r) {
-                    stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt;
-                    if (MODE == kClosest) { stk_lo[sp] = r_lo; stk_hi[sp] = r_hi; stk_src[sp] = 2u * cur_ref + 1u; }
-                    sp++;
-                }
-                cur_ref = pr.l_ref; cur_cnt = pr.l_cnt;
-                continue;
-            }
-            if (hit_r) { cur_ref = pr.r_ref; cur_cnt = pr.r_cnt; continue; }
-        }
-        bool popped = false;
-        while (sp > 0) {
-            --sp;
-            if (MODE == kClosest) {                                   // the deferred `tmin < ray.t` of bvh.cpp:178
-                if (stk_lo[sp] >= r.t) continue;
-                if (!(stk_hi[sp] < r.t)) {
-                    BoxTimes e = exact_child(P.pairs64, stk_src[sp] >> 1, stk_src[sp] & 1u, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
-                    if (!(e.tmin < r.t)) continue;
+            } else {
+                DevPair32 pr;
+                load_pair32(P.pairs32, cur_ref, pr);
+                if (COUNT) lc.box += 2;
+                spent += 2u + pr.l_cnt + pr.r_cnt;
+                if (MODE != kClosest && spent > budget) {
+                    result = kTravOverBudget; live = false; need_pop = false;
+                } else {
+                    bool hit_l, hit_r; float r_lo, r_hi;
+                    pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
+                    if (hit_l & hit_r) {
+                        stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt;
+                        if (MODE == kClosest) { stk_lo[sp] = r_lo; stk_hi[sp] = r_hi; stk_src[sp] = cur_ref; }
+                        sp++;
+                    }
+                    if (hit_l | hit_r) {
+                        cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
+                        need_pop = false;
+                    }
                 }
             }
-            cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; popped = true;
-            break;
+            if (need_pop) {
+                live = false;
+                while (sp > 0) {
+                    --sp;
+                    if (MODE == kClosest) {                                   // the deferred `tmin < ray.t` of bvh.cpp:178
+                        if (stk_lo[sp] >= r.t) continue;
+                        if (!(stk_hi[sp] < r.t)) {
+                            if (COUNT) lc.box_exact++;
+                            BoxTimes e = exact_child(P.pairs64, stk_src[sp], 1u, r.r64);
+                            if (!(e.tmin < r.t)) continue;
+                        }
+                    }
+                    cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; live = true;
+                    break;
+                }
+            }
         }
-        if (!popped) break;
     }
-    if (MODE == kAnyHit) return kTravMiss;
+    if (result == kTravOverBudget) return result;
+    if (!active) return kTravMiss;
     return r.t != kRayTInit ? kTravHit : kTravMiss;
+}
+
+// Shadow rays (ray.t = 1e30f): only `found` is used (raythread.cpp:306), i.e. whether SOME triangle reachable
+// through accepted boxes has a barycentric pass with 1e-4 < t < 1e30.  ray.t never changes before
+// that, so the set of accepted boxes is fixed and neither the visit order nor the moment a leaf is tested can
+// change the answer.  The loop therefore walks interior nodes only and DEFERS accepted leaves to a short list;
+// the warp alternates between a walk phase and a leaf phase so that its lanes test their triangles together
+// instead of one lane at a time in the middle of the walk (measured: 4 of 32 lanes active in an inline leaf
+// path).  WARP-SYNCHRONOUS like traverse().  Returns kTravHit (occluded) / kTravMiss / kTravOverBudget.
+constexpr int kLeafList = 12;
+template <bool COUNT>
+CT_DEV int traverse_any_hit(const Params &P, const TRay &r, bool active, const uint32_t budget, LocalCount &lc) {
+    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax];     // node stack grows up from 0, deferred leaves down from the top
+    int sp = 0, lp = kStackMax;
+    uint32_t spent = 1u;
+    uint32_t cur_ref = P.root_ref, cur_cnt = P.root_cnt;
+    bool occluded = false, over = false;
+    bool live = false;                                    // nodes left to walk (cur_* pending, or the stack non-empty)
+    if (active) {
+        if (COUNT) lc.box++;
+        live = exact_root(P, r.r64, r.t);
+    }
+    while (true) {
+        // ---- walk phase: one interior-node visit per live lane and iteration; leaves go to the list
+        bool room = true;                                 // false: list full (or the two stacks about to meet)
+        while (__any_sync(kFullMask, live & room)) {
+            if (live & room) {
+                bool need_pop = true;
+                if (cur_cnt > 0) {
+                    --lp; stk_ref[lp] = cur_ref; stk_cnt[lp] = cur_cnt;
+                    spent += cur_cnt;
+                    room = (kStackMax - lp < kLeafList) & (lp - sp >= 3);
+                } else {
+                    DevPair32 pr;
+                    load_pair32(P.pairs32, cur_ref, pr);
+                    if (COUNT) lc.box += 2;
+                    spent += 2u;
+                    if (spent > budget) {
+                        over = true; live = false; lp = kStackMax; need_pop = false;
+                    } else {
+                        bool hit_l, hit_r; float r_lo, r_hi;
+                        pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
+                        if (hit_l & hit_r) { stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt; sp++; }
+                        if (hit_l | hit_r) {
+                            cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
+                            need_pop = false;
+                        }
+                    }
+                }
+                if (need_pop) {
+                    if (sp == 0) live = false;
+                    else { --sp; cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; }
+                }
+            }
+        }
+        // ---- leaf phase: one triangle per lane and iteration
+        uint32_t tri = 0;                                 // next triangle inside the leaf at lp
+        while (__any_sync(kFullMask, lp < kStackMax)) {
+            if (lp < kStackMax) {
+                if (COUNT) lc.tri++;
+                const TriHit th = leaf_triangle<true, COUNT>(P, r, stk_ref[lp] + tri, lc);
+                if (th.hit & (th.t > kEps) & (th.t < kRayTInit)) { occluded = true; live = false; lp = kStackMax; }
+                else if (++tri == stk_cnt[lp]) { tri = 0; lp++; }
+            }
+        }
+        if (!__any_sync(kFullMask, live)) break;
+    }
+    if (over) return kTravOverBudget;
+    return occluded ? kTravHit : kTravMiss;
 }
 
 // Primary ray of canvas pixel (x,y): CanvasToViewport (raythread.cpp:186-194) * camera.rotation (mymath.h:68-75)
@@ -365,12 +461,12 @@ CT_DEV void clear_occ(const Params &P, uint32_t q) {
 }
 
 // Park a ray for k_overflow.  False when the buffer is full (the caller then finishes the ray in place).
-CT_DEV bool park_ray(const Params &P, int ovf_idx, const Ray &r, uint32_t target, uint32_t bit) {
+CT_DEV bool park_ray(const Params &P, int ovf_idx, const double *r64, uint32_t target, uint32_t bit) {
     uint32_t i = atomicAdd(&P.sched->ovf_count[ovf_idx], 1u);
     if (i >= P.ovf_cap) { atomicAdd(&P.tot->rays_in_place, 1ull); return false; }
     OvfRay &o = P.ovf[i];
-    o.o[0] = r.o.x; o.o[1] = r.o.y; o.o[2] = r.o.z;
-    o.d[0] = r.d.x; o.d[1] = r.d.y; o.d[2] = r.d.z;
+    o.o[0] = r64[0]; o.o[1] = r64[1]; o.o[2] = r64[2];
+    o.d[0] = r64[3]; o.d[1] = r64[4]; o.d[2] = r64[5];
     o.target = target; o.bit = bit;
     return true;
 }
@@ -384,11 +480,16 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
         if (base >= P.n_slots) break;
         uint32_t slot = (uint32_t)base + (threadIdx.x & 31u);
         int x, y, fbi;
-        if (!slot_pixel(P, slot, x, y, fbi)) continue;
-        Ray r = primary_ray(P, x, y);
-        ray_finish(r, P.bound);
+        const bool active = slot_pixel(P, slot, x, y, fbi);
+        double r64[6];
+        TRay r;
+        if (active) {
+            Ray ray = primary_ray(P, x, y);
+            tray_setup(r, ray, P.bound, r64);
+        }
         float tc; uint32_t pos;
-        bool found = traverse<kClosest, COUNT, false>(P, r, tc, pos, lc) == kTravHit;
+        bool found = traverse<kClosest, COUNT>(P, r, active, 0xffffffffu, tc, pos, lc) == kTravHit;   // warp-synchronous
+        if (!active) continue;
         n_rays++;
         P.hit0_t[slot] = tc;
         P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
@@ -418,24 +519,36 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
         if (base >= total) break;
         uint32_t j = (uint32_t)(base / n_pad);
         uint32_t q = (uint32_t)(base - (unsigned long long)j * n_pad) + (threadIdx.x & 31u);
-        if (q >= n) continue;
-        uint32_t slot, pos; int fbi; Ray r; float tc;
-        if (!load_path(P, depth, q, slot, fbi, r, tc, pos) || pos == kNoPos) continue;
-        const DevShadowLight &L = P.slights[j];
-        V3 position = vadd(r.o, vscale((double)tc, r.d));                                  // :360
-        V3 lray = (L.type == CT_LIGHT_POINT) ? vsub(ld3(L.v), position) : ld3(L.v);        // :288 / :293
-        Ray sr; sr.o = position; sr.d = lray; sr.t = kRayTInit;                            // :304 no offset, no t<=1 test
-        ray_finish(sr, P.bound);
-        float stc; uint32_t spos;
-        n_shadow++;
-        uint32_t word = q * P.occ_words + (L.index >> 5), bit = L.index & 31u;
-        int res = traverse<kAnyHit, COUNT, true>(P, sr, stc, spos, lc);
-        if (res == kTravOverBudget) {
-            n_parked++;
-            if (park_ray(P, ovf_idx, sr, word, bit)) continue;
-            res = traverse<kAnyHit, COUNT, false>(P, sr, stc, spos, lc);
+        uint32_t slot, pos = kNoPos; int fbi; Ray r; float tc = 0.0f;
+        bool active = q < n && load_path(P, depth, q, slot, fbi, r, tc, pos) && pos != kNoPos;
+        double r64[6];
+        TRay tr;
+        uint32_t word = 0, bit = 0;
+        if (active) {
+            const DevShadowLight &L = P.slights[j];
+            V3 position = vadd(r.o, vscale((double)tc, r.d));                                  // :360
+            V3 lray = (L.type == CT_LIGHT_POINT) ? vsub(ld3(L.v), position) : ld3(L.v);        // :288 / :293
+            Ray sr; sr.o = position; sr.d = lray; sr.t = kRayTInit;                            // :304 no offset, no t<=1 test
+            tray_setup(tr, sr, P.bound, r64);
+            n_shadow++;
+            word = q * P.occ_words + (L.index >> 5); bit = L.index & 31u;
         }
-        if (res == kTravHit) atomicOr(&P.occ[word], 1u << bit);
+        uint32_t budget = P.budget;
+        while (true) {                                                  // warp-uniform: traverse_any_hit is warp-synchronous
+            int res = traverse_any_hit<COUNT>(P, tr, active, budget, lc);
+            bool again = false;
+            if (active) {
+                if (res == kTravOverBudget) {
+                    n_parked++;
+                    again = !park_ray(P, ovf_idx, r64, word, bit);      // parking buffer full: finish in place, no budget
+                    budget = 0xffffffffu;
+                } else if (res == kTravHit) {
+                    atomicOr(&P.occ[word], 1u << bit);
+                }
+            }
+            active = again;
+            if (!__any_sync(0xffffffffu, again)) break;
+        }
     }
     warp_add(&P.tot->rays_shadow, n_shadow);
     warp_add(&P.tot->rays_overflow, n_parked);
@@ -540,22 +653,35 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
         unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
         if (base >= n) break;
         uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
-        if (q >= n) continue;
-        const double2 *rb = reinterpret_cast<const double2 *>(P.ray_buf[cur] + 6ull * q);
-        double2 a = rb[0], b = rb[1], c = rb[2];
-        Ray r;
-        r.o = {a.x, a.y, b.x}; r.d = {b.y, c.x, c.y}; r.t = 0.0f;
-        ray_finish(r, P.bound);
-        float tc; uint32_t pos;
-        clear_occ(P, q);
-        int res = traverse<kFirstLine, COUNT, true>(P, r, tc, pos, lc);      // found is always true: 0 != 1e30f (:227)
-        if (res == kTravOverBudget) {
-            n_parked++;
-            if (park_ray(P, ovf_idx, r, q, 0u)) continue;
-            traverse<kFirstLine, COUNT, false>(P, r, tc, pos, lc);
+        bool active = q < n;
+        double r64[6];
+        TRay r;
+        if (active) {
+            const double2 *rb = reinterpret_cast<const double2 *>(P.ray_buf[cur] + 6ull * q);
+            double2 a = rb[0], b = rb[1], c = rb[2];
+            Ray ray;
+            ray.o = {a.x, a.y, b.x}; ray.d = {b.y, c.x, c.y}; ray.t = 0.0f;
+            tray_setup(r, ray, P.bound, r64);
+            clear_occ(P, q);
         }
-        P.hitb_t[q] = tc;
-        P.hitb_pos[q] = (pos == kNoPos) ? P.pos_of_tri0 : pos;
+        uint32_t budget = P.budget;
+        while (true) {                                                  // warp-uniform: traverse is warp-synchronous
+            float tc; uint32_t pos;
+            int res = traverse<kFirstLine, COUNT>(P, r, active, budget, tc, pos, lc);
+            bool again = false;
+            if (active) {
+                if (res == kTravOverBudget) {
+                    n_parked++;
+                    again = !park_ray(P, ovf_idx, r64, q, 0u);          // parking buffer full: finish in place, no budget
+                    budget = 0xffffffffu;
+                } else {                                                // found is always true: 0 != 1e30f (:227)
+                    P.hitb_t[q] = tc;
+                    P.hitb_pos[q] = (pos == kNoPos) ? P.pos_of_tri0 : pos;
+                }
+            }
+            active = again;
+            if (!__any_sync(kFullMask, again)) break;
+        }
     }
     warp_add(&P.tot->rays_overflow, n_parked);
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
@@ -571,7 +697,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
 // grid.sync per level, the frontier ping-pongs between two HBM buffers sized for the widest possible level.
 // Tests the triangles of an accepted leaf for a parked ray; records the verdict in `res`.
 template <TraverseMode MODE, bool COUNT>
-CT_DEV void overflow_leaf(const Params &P, const Ray &r, uint32_t first, uint32_t cnt, uint32_t *res, LocalCount &lc) {
+CT_DEV void overflow_leaf(const Params &P, const TRay &r, uint32_t first, uint32_t cnt, uint32_t *res, LocalCount &lc) {
     for (uint32_t k = 0; k < cnt; k++) {
         uint32_t pos = first + k;
         if (COUNT) lc.tri++;
@@ -602,10 +728,12 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
         // level 0: the root (frontier items are accepted INTERIOR nodes = pair indices; leaves are tested on the spot)
         for (uint32_t i = tid; i < bn; i += n_threads) {
             const OvfRay &o = P.ovf[b0 + i];
-            Ray r; r.o = ld3(o.o); r.d = ld3(o.d); r.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
-            ray_finish(r, P.bound);
+            Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
+            double r64[6];
+            TRay r;
+            tray_setup(r, ray, P.bound, r64);
             if (COUNT) lc.box++;
-            if (!intersect_aabb(r, P.root_min, P.root_max)) continue;
+            if (!exact_root(P, r64, r.t)) continue;
             if (P.root_cnt > 0) overflow_leaf<MODE, COUNT>(P, r, P.root_ref, P.root_cnt, P.ovf_result + i, lc);
             else P.frontier[0][atomicAdd(const_cast<uint32_t *>(&cnt[0]), 1u)] = make_uint2(i, P.root_ref);
         }
@@ -626,17 +754,20 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
                     uint32_t *res = P.ovf_result + item.x;
                     if (!(MODE == kAnyHit && *(volatile uint32_t *)res != 0u)) {
                         const OvfRay &o = P.ovf[b0 + item.x];
-                        Ray r; r.o = ld3(o.o); r.d = ld3(o.d); r.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
-                        ray_finish(r, P.bound);
+                        Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
+                        double r64[6];
+                        TRay r;
+                        tray_setup(r, ray, P.bound, r64);
                         DevPair32 pr;
                         load_pair32(P.pairs32, item.y, pr);
                         if (COUNT) lc.box += 2;
-                        float lo, hi;
-                        if (child_accept<COUNT>(P, r, item.y, 0u, pr.lmin, pr.lmax, lo, hi, lc)) {
+                        bool hit_l, hit_r; float lo, hi;
+                        pair_accept<COUNT>(P, r, item.y, pr, hit_l, hit_r, lo, hi, lc);
+                        if (hit_l) {
                             if (pr.l_cnt > 0) overflow_leaf<MODE, COUNT>(P, r, pr.l_ref, pr.l_cnt, res, lc);
                             else { out_a = pr.l_ref; n_out = 1; }
                         }
-                        if (child_accept<COUNT>(P, r, item.y, 1u, pr.rmin, pr.rmax, lo, hi, lc)) {
+                        if (hit_r) {
                             if (pr.r_cnt > 0) overflow_leaf<MODE, COUNT>(P, r, pr.r_ref, pr.r_cnt, res, lc);
                             else { if (n_out) out_b = pr.r_ref; else out_a = pr.r_ref; n_out++; }
                         }
@@ -692,13 +823,21 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Params 
 __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, const double *org, const double *dir,
                                 const float *t0, uint32_t *found, uint32_t *index, float *tclosest) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const bool active = i < n;                           // the traversals are warp-synchronous: every lane calls both
     Ray r;
-    r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = t0[i];
-    ray_finish(r, P.bound);
-    LocalCount lc; float tc; uint32_t pos; bool f;
-    if (r.t == 0.0f) f = traverse<kFirstLine, false, false>(P, r, tc, pos, lc) == kTravHit;
-    else f = traverse<kClosest, false, false>(P, r, tc, pos, lc) == kTravHit;
+    r.t = 1.0f;
+    double r64[6];
+    TRay tr;
+    if (active) {
+        r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = t0[i];
+        tray_setup(tr, r, P.bound, r64);
+    }
+    LocalCount lc; float tc, tc2; uint32_t pos, pos2;
+    const bool first_line = r.t == 0.0f;
+    bool f = traverse<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc) == kTravHit;
+    bool f2 = traverse<kClosest, false>(P, tr, active && !first_line, 0xffffffffu, tc2, pos2, lc) == kTravHit;
+    if (!active) return;
+    if (!first_line) { f = f2; tc = tc2; pos = pos2; }
     if (found) found[i] = f ? 1u : 0u;
     if (index) index[i] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
     if (tclosest) tclosest[i] = tc;
@@ -725,18 +864,20 @@ __global__ void k_debug_primitives(uint32_t n, const double *org, const double *
             ordered = ordered && (mn[k] <= mx[k]) && isfinite(mn[k]) && isfinite(mx[k]);
         }
         if (!ordered) bnd[0] = bnd[1] = bnd[2] = INFINITY;
-        ray_finish(r, bnd);
+        double r64[6];
+        TRay tr;
+        tray_setup(tr, r, bnd, r64);
         uint32_t f = 0;
-        if (r.filt) {
+        if (tr.filt) {
             const float fmn[3] = {(float)mn[0], (float)mn[1], (float)mn[2]}, fmx[3] = {(float)mx[0], (float)mx[1], (float)mx[2]};
-            BoxBracket b = box_filter(r, fmn, fmx);
+            BoxBracket b = box_filter(tr, fmn, fmx);
             if (bracket_geom_no(b) || bracket_t_no(b, r.t)) f = 2;
             else if (bracket_geom_yes(b) && bracket_t_yes(b, r.t)) f = 1;
             BoxTimes e = box_times(r, mn, mx);
             bool inside = b.near_lo <= e.tmin && e.tmin <= b.near_hi && b.far_lo <= e.tmax && e.tmax <= b.far_hi;
             if (!inside) f |= 8u;                                  // bracket does not contain the reference's floats: bug
         }
-        filter_out[i] = (exact ? 1u : 0u) | ((f & 3u) << 1) | (r.filt ? 8u : 0u) | ((f & 8u) ? 16u : 0u);
+        filter_out[i] = (exact ? 1u : 0u) | ((f & 3u) << 1) | (tr.filt ? 8u : 0u) | ((f & 8u) ? 16u : 0u);
     }
     V3 p1 = ld3(tri + 9ull * i), p2 = ld3(tri + 9ull * i + 3), p3 = ld3(tri + 9ull * i + 6);
     float t;

