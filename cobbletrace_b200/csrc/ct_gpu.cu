@@ -51,7 +51,7 @@ constexpr int kMinBlocks = CT_MIN_BLOCKS;   // traversal kernels: resident CTAs 
 constexpr int kOvfThreads = 256;     // k_overflow CTA
 constexpr int kMaxLaunches = 80;     // launches of one tile (work cursors / stage events)
 constexpr uint32_t kNoPos = 0xffffffffu;
-constexpr uint32_t kDefaultBudget = 2048;   // node visits + triangle tests before a ray is parked for k_overflow
+constexpr uint32_t kDefaultBudget = 384;    // node visits + triangle tests before a ray is parked for k_overflow
 
 // ---- device-side scene layout (SoA arrays in HBM, uploaded once) -----------------------------------
 // The BVH is stored per INTERIOR node as the pair of its two children (bvh.cpp:89-97 allocates them adjacently
@@ -85,6 +85,8 @@ struct DevSched {                    // zeroed at the start of every tile render
     unsigned long long work[kMaxLaunches];   // dynamic-fetch cursors, one per launch of the tile
     uint32_t queue_count[16];        // paths alive at depth d (d >= 1)
     uint32_t ovf_count[40];          // rays parked for the k_overflow launch 2*depth + {0: bounce, 1: shadow}
+    uint32_t ovf_cursor[40];         // k_overflow's warp-cooperative pass: next parked ray to take
+    uint32_t huge_count[40];         // ... rays it handed on to the grid-wide breadth-first pass
     uint32_t bfs_count[3];           // frontier sizes of the breadth-first levels (rotating)
 };
 struct DevTotals {                   // running ray / test counters (never reset by a tile)
@@ -109,6 +111,7 @@ struct Params {
     uint32_t occ_words;              // words of occlusion bits per path = ceil(n_lights / 32)
     uint32_t pos_of_tri0;            // leaf position of original triangle 0 (closestIndex default, raythread.cpp:205)
     uint32_t budget;                 // see kDefaultBudget
+    uint32_t warp_budget;            // see kWarpBudget
     double cam[3], rot[9];
     float vp_w, vp_h, vp_d;
     int W, H, max_depth;
@@ -132,6 +135,7 @@ struct Params {
     OvfRay *ovf; uint32_t ovf_cap;
     uint2 *frontier[2]; uint32_t frontier_cap;   // items (parked-ray index inside the batch, node)
     uint32_t *ovf_result; uint32_t ovf_batch_max;
+    uint32_t *ovf_huge;                          // indices (into ovf) of the rays left to the breadth-first pass
     DevSched *sched;
     DevTotals *tot;
 };
@@ -695,20 +699,43 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
 //               bvh.cpp:70-97, so leaf positions increase along the DFS).
 // The whole grid walks the tree breadth first, a batch of rays at a time: one frontier item = (ray, node), one
 // grid.sync per level, the frontier ping-pongs between two HBM buffers sized for the widest possible level.
-// Tests the triangles of an accepted leaf for a parked ray; records the verdict in `res`.
+// Tests the triangles of an accepted leaf for a parked ray.  kAnyHit: 1 if one of them occludes, else 0;
+// kFirstLine: the first (lowest) leaf position with a barycentric pass, else kNoPos.
 template <TraverseMode MODE, bool COUNT>
-CT_DEV void overflow_leaf(const Params &P, const TRay &r, uint32_t first, uint32_t cnt, uint32_t *res, LocalCount &lc) {
+CT_DEV uint32_t overflow_leaf(const Params &P, const TRay &r, uint32_t first, uint32_t cnt, LocalCount &lc) {
     for (uint32_t k = 0; k < cnt; k++) {
         uint32_t pos = first + k;
         if (COUNT) lc.tri++;
         const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
-        const float t = th.t;
         if (!th.hit) continue;
-        if (MODE == kAnyHit) { if (t > kEps && t < kRayTInit) { *(volatile uint32_t *)res = 1u; return; } }
-        else { atomicMin(res, pos); return; }                 // later positions of this leaf are larger
+        if (MODE == kAnyHit) { if (th.t > kEps && th.t < kRayTInit) return 1u; }
+        else return pos;                                      // later positions of this leaf are larger
+    }
+    return MODE == kAnyHit ? 0u : kNoPos;
+}
+
+template <TraverseMode MODE>
+CT_DEV uint32_t overflow_merge(uint32_t a, uint32_t b) { return MODE == kAnyHit ? (a | b) : min(a, b); }
+
+template <TraverseMode MODE>
+CT_DEV void overflow_store(const Params &P, const OvfRay &o, uint32_t res) {
+    if (MODE == kAnyHit) {
+        if (res) atomicOr(&P.occ[o.target], 1u << o.bit);
+    } else {
+        P.hitb_t[o.target] = (res == kNoPos) ? kFinf : 0.0f;          // raythread.cpp:204 / first line pass
+        P.hitb_pos[o.target] = (res == kNoPos) ? P.pos_of_tri0 : res;
     }
 }
 
+constexpr int kWarpStack = 1024;         // pending interior nodes of one ray in the warp-cooperative pass
+constexpr uint32_t kWarpBudget = 4096;       // default node visits before a ray is handed to the grid-wide pass
+
+// Parked rays.  Pass 1: one WARP per ray -- the 32 lanes pop up to 32 pending interior nodes from a shared-memory
+// stack, test their child pairs, test accepted leaves on the spot and push accepted interior children back.
+// A ray whose stack outgrows kWarpStack or that needs more than kWarpBudget node visits (the every-box-passes
+// rays described in the header: up to ~1M visits) goes to pass 2: the whole grid walks the tree breadth first, a
+// batch of rays at a time, one frontier item = (ray, interior node), one grid.sync per level, the frontier
+// ping-pongs between two HBM buffers sized for the widest possible level.
 template <TraverseMode MODE, bool COUNT>
 __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant__ Params P, int ovf_idx) {
     const uint32_t n = min(P.sched->ovf_count[ovf_idx], P.ovf_cap);
@@ -717,24 +744,97 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
     LocalCount lc;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
+    // ---- pass 1: warp per ray
+    {
+        __shared__ uint32_t wstack[kOvfThreads / 32][kWarpStack];
+        uint32_t *stk = wstack[threadIdx.x >> 5];
+        while (true) {
+            uint32_t idx = 0;
+            if (lane == 0) idx = atomicAdd(&P.sched->ovf_cursor[ovf_idx], 1u);
+            idx = __shfl_sync(kFullMask, idx, 0);
+            if (idx >= n) break;
+            const OvfRay &o = P.ovf[idx];
+            Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
+            double r64[6];
+            TRay r;
+            tray_setup(r, ray, P.bound, r64);             // every lane holds the same ray
+            uint32_t res = MODE == kAnyHit ? 0u : kNoPos;
+            // An origin this far outside the scene (a shading point 2^32 ray lengths away) makes all slab
+            // quotients of an axis round to the same float: every box passes and no filter can help.  Straight to pass 2.
+            bool too_big = !r.filt || (double)r.om > 0x1p20 * fmax(fmax(P.bound[0], P.bound[1]), P.bound[2]);
+            if (COUNT && lane == 0 && !too_big) lc.box++;
+            if (!too_big && exact_root(P, r64, r.t)) {
+                if (P.root_cnt > 0) {
+                    if (lane == 0) res = overflow_leaf<MODE, COUNT>(P, r, P.root_ref, P.root_cnt, lc);
+                } else {
+                    if (lane == 0) stk[0] = P.root_ref;
+                    __syncwarp();
+                    uint32_t sp = 1, visits = 0;
+                    while (sp > 0) {
+                        const uint32_t take = min(sp, 32u);
+                        sp -= take;
+                        uint32_t n_out = 0, out_a = 0, out_b = 0;
+                        if (lane < take) {
+                            const uint32_t pid = stk[sp + lane];
+                            DevPair32 pr;
+                            load_pair32(P.pairs32, pid, pr);
+                            if (COUNT) lc.box += 2;
+                            bool hit_l, hit_r; float lo, hi;
+                            pair_accept<COUNT>(P, r, pid, pr, hit_l, hit_r, lo, hi, lc);
+                            if (hit_l) {
+                                if (pr.l_cnt > 0) res = overflow_merge<MODE>(res, overflow_leaf<MODE, COUNT>(P, r, pr.l_ref, pr.l_cnt, lc));
+                                else { out_a = pr.l_ref; n_out = 1; }
+                            }
+                            if (hit_r) {
+                                if (pr.r_cnt > 0) res = overflow_merge<MODE>(res, overflow_leaf<MODE, COUNT>(P, r, pr.r_ref, pr.r_cnt, lc));
+                                else { if (n_out) out_b = pr.r_ref; else out_a = pr.r_ref; n_out++; }
+                            }
+                        }
+                        __syncwarp();                     // every lane has read its entry before the pushes below
+                        if (MODE == kAnyHit && __any_sync(kFullMask, res != 0u)) break;
+                        uint32_t incl = n_out;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(kFullMask, incl, d); if ((int)lane >= d) incl += v; }
+                        const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+                        visits += take;
+                        if (sp + total > (uint32_t)kWarpStack || visits > P.warp_budget) { too_big = true; break; }
+                        const uint32_t at = sp + incl - n_out;
+                        if (n_out > 0) stk[at] = out_a;
+                        if (n_out > 1) stk[at + 1u] = out_b;
+                        sp += total;
+                        __syncwarp();
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) res = overflow_merge<MODE>(res, __shfl_xor_sync(kFullMask, res, d));
+            if (lane == 0) {
+                if (too_big) P.ovf_huge[atomicAdd(&P.sched->huge_count[ovf_idx], 1u)] = idx;
+                else overflow_store<MODE>(P, o, res);
+            }
+        }
+    }
+    grid.sync();
+    // ---- pass 2: grid-wide breadth-first walk of what is left
+    const uint32_t nh = *(volatile uint32_t *)&P.sched->huge_count[ovf_idx];
     const uint32_t per_ray = P.n_pairs / 2u + 2u;         // widest level of interior nodes one ray can reach
     const uint32_t batch = max(1u, min(P.frontier_cap / per_ray, P.ovf_batch_max));
     volatile uint32_t *cnt = P.sched->bfs_count;
-    for (uint32_t b0 = 0; b0 < n; b0 += batch) {
-        const uint32_t bn = min(batch, n - b0);
+    for (uint32_t b0 = 0; b0 < nh; b0 += batch) {
+        const uint32_t bn = min(batch, nh - b0);
         if (tid == 0) { cnt[0] = 0u; cnt[1] = 0u; cnt[2] = 0u; }
         for (uint32_t i = tid; i < bn; i += n_threads) P.ovf_result[i] = (MODE == kAnyHit) ? 0u : kNoPos;
         grid.sync();
         // level 0: the root (frontier items are accepted INTERIOR nodes = pair indices; leaves are tested on the spot)
         for (uint32_t i = tid; i < bn; i += n_threads) {
-            const OvfRay &o = P.ovf[b0 + i];
+            const OvfRay &o = P.ovf[P.ovf_huge[b0 + i]];
             Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
             double r64[6];
             TRay r;
             tray_setup(r, ray, P.bound, r64);
             if (COUNT) lc.box++;
             if (!exact_root(P, r64, r.t)) continue;
-            if (P.root_cnt > 0) overflow_leaf<MODE, COUNT>(P, r, P.root_ref, P.root_cnt, P.ovf_result + i, lc);
+            if (P.root_cnt > 0) P.ovf_result[i] = overflow_leaf<MODE, COUNT>(P, r, P.root_ref, P.root_cnt, lc);
             else P.frontier[0][atomicAdd(const_cast<uint32_t *>(&cnt[0]), 1u)] = make_uint2(i, P.root_ref);
         }
         grid.sync();
@@ -753,7 +853,7 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
                     item = in[i];
                     uint32_t *res = P.ovf_result + item.x;
                     if (!(MODE == kAnyHit && *(volatile uint32_t *)res != 0u)) {
-                        const OvfRay &o = P.ovf[b0 + item.x];
+                        const OvfRay &o = P.ovf[P.ovf_huge[b0 + item.x]];
                         Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
                         double r64[6];
                         TRay r;
@@ -763,25 +863,28 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
                         if (COUNT) lc.box += 2;
                         bool hit_l, hit_r; float lo, hi;
                         pair_accept<COUNT>(P, r, item.y, pr, hit_l, hit_r, lo, hi, lc);
+                        uint32_t found = MODE == kAnyHit ? 0u : kNoPos;
                         if (hit_l) {
-                            if (pr.l_cnt > 0) overflow_leaf<MODE, COUNT>(P, r, pr.l_ref, pr.l_cnt, res, lc);
+                            if (pr.l_cnt > 0) found = overflow_merge<MODE>(found, overflow_leaf<MODE, COUNT>(P, r, pr.l_ref, pr.l_cnt, lc));
                             else { out_a = pr.l_ref; n_out = 1; }
                         }
                         if (hit_r) {
-                            if (pr.r_cnt > 0) overflow_leaf<MODE, COUNT>(P, r, pr.r_ref, pr.r_cnt, res, lc);
+                            if (pr.r_cnt > 0) found = overflow_merge<MODE>(found, overflow_leaf<MODE, COUNT>(P, r, pr.r_ref, pr.r_cnt, lc));
                             else { if (n_out) out_b = pr.r_ref; else out_a = pr.r_ref; n_out++; }
                         }
+                        if (MODE == kAnyHit) { if (found) *(volatile uint32_t *)res = 1u; }
+                        else if (found != kNoPos) atomicMin(res, found);
                     }
                 }
                 // warp-aggregated append of the accepted interior children
                 uint32_t incl = n_out;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(kFullMask, incl, d); if ((int)lane >= d) incl += v; }
+                const uint32_t total = __shfl_sync(kFullMask, incl, 31);
                 if (total) {
                     uint32_t obase = 0;
                     if (lane == 31u) obase = atomicAdd(cout, total);
-                    obase = __shfl_sync(0xffffffffu, obase, 31) + incl - n_out;
+                    obase = __shfl_sync(kFullMask, obase, 31) + incl - n_out;
                     if (obase + n_out <= P.frontier_cap) {        // cannot fail: the batch is sized for the widest level
                         if (n_out > 0) out[obase] = make_uint2(item.x, out_a);
                         if (n_out > 1) out[obase + 1u] = make_uint2(item.x, out_b);
@@ -790,16 +893,7 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
             }
             grid.sync();
         }
-        for (uint32_t i = tid; i < bn; i += n_threads) {
-            const OvfRay &o = P.ovf[b0 + i];
-            uint32_t res = P.ovf_result[i];
-            if (MODE == kAnyHit) {
-                if (res) atomicOr(&P.occ[o.target], 1u << o.bit);
-            } else {
-                P.hitb_t[o.target] = (res == kNoPos) ? kFinf : 0.0f;          // raythread.cpp:204 / first line pass
-                P.hitb_pos[o.target] = (res == kNoPos) ? P.pos_of_tri0 : res;
-            }
-        }
+        for (uint32_t i = tid; i < bn; i += n_threads) overflow_store<MODE>(P, P.ovf[P.ovf_huge[b0 + i]], P.ovf_result[i]);
         grid.sync();                                      // results and frontier are reused by the next batch
     }
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
@@ -935,6 +1029,7 @@ struct DeviceState {
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mutex;
 long long g_budget_option = 0;       // ct_gpu_set_option("traversal_budget"); 0 = default
+long long g_warp_budget_option = 0;  // ct_gpu_set_option("overflow_warp_budget"); 0 = default
 
 int check_device(int device) {
     int n = 0;
@@ -1049,6 +1144,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     for (cudaEvent_t &e : s.tile_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (d->flags & CT_FLAG_STAGE_TIMING) for (cudaEvent_t &e : s.stage_ev) CU(cudaEventCreate(&e));
     s.p.budget = g_budget_option > 0 ? (uint32_t)std::min<long long>(g_budget_option, 1ll << 30) : kDefaultBudget;
+    s.p.warp_budget = g_warp_budget_option > 0 ? (uint32_t)std::min<long long>(g_warp_budget_option, 1ll << 30) : kWarpBudget;
     s.flags = d->flags;
 
     Params &p = s.p;
@@ -1184,9 +1280,10 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     if (s.can_overflow) {
         p.ovf_cap = 1u << 16;
         p.ovf_batch_max = 1u << 16;
-        p.frontier_cap = std::max<uint32_t>(1u << 20, 2u * (n_pairs / 2u + 2u));
+        p.frontier_cap = std::max<uint32_t>(1u << 24, 2u * (n_pairs / 2u + 2u));   // 2 x 128 MB: ~60 rays of a 1M-node tree per batch
         TRY(dev_alloc(s, &p.ovf, p.ovf_cap));
         TRY(dev_alloc(s, &p.ovf_result, p.ovf_batch_max));
+        TRY(dev_alloc(s, &p.ovf_huge, p.ovf_cap));
         for (int b = 0; b < 2; b++) TRY(dev_alloc(s, &p.frontier[b], p.frontier_cap));
         const void *fn[4] = {(const void *)k_overflow<kFirstLine, false>, (const void *)k_overflow<kFirstLine, true>,
                              (const void *)k_overflow<kAnyHit, false>, (const void *)k_overflow<kAnyHit, true>};
@@ -1320,6 +1417,11 @@ int ct_gpu_set_option(const char *name, long long value) {
     if (!strcmp(name, "traversal_budget")) {
         if (value < 0) return fail(CT_ERR_INVALID, "traversal_budget must be >= 0 (0 = default)");
         g_budget_option = value;
+        return CT_OK;
+    }
+    if (!strcmp(name, "overflow_warp_budget")) {
+        if (value < 0) return fail(CT_ERR_INVALID, "overflow_warp_budget must be >= 0 (0 = default)");
+        g_warp_budget_option = value;
         return CT_OK;
     }
     return fail(CT_ERR_INVALID, "unknown option '%s'", name);

@@ -160,8 +160,9 @@ int ct_gpu_sync(int device);
 
 /* Library-wide tuning knobs, applied by the next ct_gpu_upload_scene.  Names:
  *   "traversal_budget"  node visits + triangle tests a shadow / reflection ray may spend in its own thread
- *                       before it is parked and traversed breadth-first by the whole grid (0 = default 2048).
- *                       Results never depend on it; tests set it to 1 to push every ray through that path. */
+ *                       before it is parked for k_overflow (0 = default 512), which gives it a whole warp and,
+ *   "overflow_warp_budget"  after that many node visits (0 = default 32768), the whole grid (breadth-first).
+ *                       Results never depend on either; tests set them low to push rays through those paths. */
 int ct_gpu_set_option(const char *name, long long value);
 
 /* Rays parked so far on `device` since upload (shadow and reflection rays whose DFS ran past the budget, e.g. the

@@ -153,6 +153,29 @@ def test_frames_against_oracle(name, W, H, depth, refl, golden, scene_loader, gp
     assert 0 < ctr["box_tests"] <= 2 * octr["box_tests"] and 0 < ctr["tri_tests"] <= octr["tri_tests"]
 
 
+@pytest.mark.parametrize("budget,warp_budget", [(16, 0), (16, 4), (200, 64)])
+def test_parked_rays_give_the_same_frames(budget, warp_budget, golden, scene_loader):
+    """Shadow / reflection rays whose walk exceeds the budget are parked and finished by a warp (pass 1) or by the
+    whole grid (pass 2) in k_overflow; with tiny budgets nearly every ray takes those paths (and the parking
+    buffer overflows, so some are finished in place).  Frames must not change."""
+    ct.api.set_option("traversal_budget", budget)
+    ct.api.set_option("overflow_warp_budget", warp_budget)
+    try:
+        for case in ("bunny_refl_d2_160", "cube_160", "pc_big_96", "import_160"):
+            fs, meta = case_scene(case, golden, scene_loader)
+            r = ct.GpuRenderer(0).upload(fs, meta["width"], meta["height"], max_depth=meta["depth"])
+            r.render_tile()
+            frame = r.readback()
+            parked, in_place = r.overflow_stats()
+            r.shutdown()
+            assert np.array_equal(frame, load_frames(case)["frame"]), case
+            if budget == 16 and case != "cube_160":
+                assert parked > 1000, (case, parked)
+    finally:
+        ct.api.set_option("traversal_budget", 0)
+        ct.api.set_option("overflow_warp_budget", 0)
+
+
 def test_640_golden_hashes(golden, scene_loader, gpu):
     for name in ("scene_file_cube", "scene_import", "scene_import_bunny", "pc_big"):
         gpu.upload(scene_loader(name), 640, 640)
