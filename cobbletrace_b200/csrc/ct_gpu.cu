@@ -341,63 +341,56 @@ CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget
 constexpr int kLeafList = 12;
 template <bool COUNT>
 CT_DEV int traverse_any_hit(const Params &P, const TRay &r, bool active, const uint32_t budget, LocalCount &lc) {
-    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax];     // node stack grows up from 0, deferred leaves down from the top
-    int sp = 0, lp = kStackMax;
+    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax];     // pushed right children
+    uint32_t leaf_ref[kLeafList], leaf_cnt[kLeafList];   // deferred leaves
+    int sp = 0, nleaf = 0;
     uint32_t spent = 1u;
     uint32_t cur_ref = P.root_ref, cur_cnt = P.root_cnt;
-    bool occluded = false, over = false;
-    bool live = false;                                    // nodes left to walk (cur_* pending, or the stack non-empty)
+    int state = 0;                                        // 1: nodes left to walk (cur_* pending); 0: walk finished
+    int result = kTravMiss;
     if (active) {
         if (COUNT) lc.box++;
-        live = exact_root(P, r.r64, r.t);
+        state = exact_root(P, r.r64, r.t) ? 1 : 0;
     }
     while (true) {
-        // ---- walk phase: one interior-node visit per live lane and iteration; leaves go to the list
-        bool room = true;                                 // false: list full (or the two stacks about to meet)
-        while (__any_sync(kFullMask, live & room)) {
-            if (live & room) {
-                bool need_pop = true;
+        // ---- walk phase: one interior-node visit per walking lane and iteration; leaves go to the list
+        while (__any_sync(kFullMask, (state == 1) & (nleaf < kLeafList))) {
+            if ((state == 1) & (nleaf < kLeafList)) {
+                bool descend = false;
                 if (cur_cnt > 0) {
-                    --lp; stk_ref[lp] = cur_ref; stk_cnt[lp] = cur_cnt;
+                    leaf_ref[nleaf] = cur_ref; leaf_cnt[nleaf] = cur_cnt; nleaf++;
                     spent += cur_cnt;
-                    room = (kStackMax - lp < kLeafList) & (lp - sp >= 3);
                 } else {
                     DevPair32 pr;
                     load_pair32(P.pairs32, cur_ref, pr);
                     if (COUNT) lc.box += 2;
                     spent += 2u;
-                    if (spent > budget) {
-                        over = true; live = false; lp = kStackMax; need_pop = false;
-                    } else {
-                        bool hit_l, hit_r; float r_lo, r_hi;
-                        pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
-                        if (hit_l & hit_r) { stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt; sp++; }
-                        if (hit_l | hit_r) {
-                            cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
-                            need_pop = false;
-                        }
-                    }
+                    bool hit_l, hit_r; float r_lo, r_hi;
+                    pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
+                    if (hit_l & hit_r) { stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt; sp++; }
+                    descend = hit_l | hit_r;
+                    cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
                 }
-                if (need_pop) {
-                    if (sp == 0) live = false;
+                if (!descend) {
+                    if (sp == 0) state = 0;
                     else { --sp; cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; }
                 }
+                if (spent > budget) { result = kTravOverBudget; state = 0; nleaf = 0; }
             }
         }
         // ---- leaf phase: one triangle per lane and iteration
-        uint32_t tri = 0;                                 // next triangle inside the leaf at lp
-        while (__any_sync(kFullMask, lp < kStackMax)) {
-            if (lp < kStackMax) {
+        uint32_t tri = 0;                                 // next triangle inside the leaf on top of the list
+        while (__any_sync(kFullMask, nleaf > 0)) {
+            if (nleaf > 0) {
                 if (COUNT) lc.tri++;
-                const TriHit th = leaf_triangle<true, COUNT>(P, r, stk_ref[lp] + tri, lc);
-                if (th.hit & (th.t > kEps) & (th.t < kRayTInit)) { occluded = true; live = false; lp = kStackMax; }
-                else if (++tri == stk_cnt[lp]) { tri = 0; lp++; }
+                const TriHit th = leaf_triangle<true, COUNT>(P, r, leaf_ref[nleaf - 1] + tri, lc);
+                if (th.hit & (th.t > kEps) & (th.t < kRayTInit)) { result = kTravHit; state = 0; nleaf = 0; }
+                else if (++tri == leaf_cnt[nleaf - 1]) { tri = 0; nleaf--; }
             }
         }
-        if (!__any_sync(kFullMask, live)) break;
+        if (!__any_sync(kFullMask, state == 1)) break;
     }
-    if (over) return kTravOverBudget;
-    return occluded ? kTravHit : kTravMiss;
+    return result;
 }
 
 // Primary ray of canvas pixel (x,y): CanvasToViewport (raythread.cpp:186-194) * camera.rotation (mymath.h:68-75)
