@@ -10,8 +10,9 @@ step     one frame: every row tile of the frame through the hot path
 value    device-resident throughput (scene in HBM, CUDA events around the frame's kernels [+ gather at N>1])
 e2e      the same frame through the reference-facing plugin call with HOST buffers: camera in
          (ct_gpu_set_camera), bitmap out (ct_gpu_readback into pinned host memory), wall clock
-N > 1    one process per GPU (torchrun); ranks steal row tiles from a shared counter, rank 0 gathers the
-         finished rows over NCCL/NVLink; strong scaling of the same frame
+N > 1    one process per GPU (torchrun), scene replicated; all GPUs render the same frame, stealing 64-pixel chunks
+         from one cursor on GPU 0 (atomics over NVLink) and storing finished pixels straight into GPU 0's
+         framebuffer (peer stores); strong scaling of the same frame
 --impl reference   the reference's own boss/worker CPU renderer (oracle/_ref/ct_ref, compiled from the unmodified
          sources) on this box's host cores, same scene files, same metric.
 """
@@ -275,40 +276,52 @@ def main():
     hs.set_reflection(refl)
     t0 = time.time(); n_nodes = hs.build_bvh(); bvh_ms = (time.time() - t0) * 1e3
     t0 = time.time()
-    boss = host.Boss(hs, W, H, devices=(dev,), max_depth=depth, tile_rows=args.tile_rows,
-                     shared_counter=multi.shared_counter_name() if N > 1 else None, rank=rank, world_size=N)
-    upload_ms = (time.time() - t0) * 1e3
     stream = torch.cuda.Stream(device=dev)
-    boss.set_stream(stream.cuda_stream)
-    gpu = api.GpuRenderer(dev)
-    gpu.width, gpu.height = W, H
-    fb_ptr, _, _ = gpu.framebuffer_ptr()
-    fb = multi.framebuffer_tensor(fb_ptr, W, H, dev)
+    flat0 = hs.to_flat(with_bvh=False)
+    cam_pos, cam_rot = np.array(flat0.cam_pos), np.array(flat0.cam_rot)
+    boss = shared = None
+    if N == 1:
+        # the reference-facing host path: C++ boss (RayThread's boss half) driving one GPU
+        boss = host.Boss(hs, W, H, devices=(dev,), max_depth=depth, tile_rows=args.tile_rows)
+        boss.set_stream(stream.cuda_stream)
+        gpu = api.GpuRenderer(dev)
+        gpu.width, gpu.height = W, H
+    else:
+        # one process per GPU, one shared frame: chunks stolen from a cursor on GPU 0 over NVLink, pixels stored
+        # straight into GPU 0's framebuffer (multi.SharedFrame / ct_gpu_render_shared)
+        gpu = api.GpuRenderer(dev).upload(hs.to_flat(with_bvh=True), W, H, max_depth=depth)
+        gpu.set_stream(stream.cuda_stream)
+        shared = multi.SharedFrame(gpu, root=0)
+    upload_ms = (time.time() - t0) * 1e3
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")      # > 126 MB L2
     pinned = torch.zeros((H, W), dtype=torch.int32).pin_memory()
     bitmap = pinned.numpy().view(np.uint32)
-    cam_pos = np.array(hs.to_flat(with_bvh=False).cam_pos)
-    max_tiles = 4096
 
     def frame(to_host: bool):
-        """One step. Returns (stats, device_ms or None)."""
-        if N > 1:
-            if rank == 0:
-                boss.reset_shared_counter()
-            dist.barrier()
-        if to_host:
-            boss.set_camera(cam_pos, 0.0, 0.0, 0.0)          # the per-frame input of the reference's boss (HandleUpdates :564-572)
+        """One step. Returns (stats, device_ms)."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if N == 1:
+            if to_host:
+                boss.set_camera(cam_pos, 0.0, 0.0, 0.0)      # the per-frame input of the reference's boss (HandleUpdates :564-572)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                _, st = boss.render(bitmap if to_host else None, want_bitmap=False)
+                e1.record(stream)
+            stream.synchronize()
+            return st, e0.elapsed_time(e1)
+        shared.begin()                                       # root zeroes the cursor, barrier
+        if to_host:
+            gpu.set_camera(cam_pos, cam_rot)                 # the camera is the per-frame input of every rank
         with torch.cuda.stream(stream):
             e0.record(stream)
-            _, st = boss.render(bitmap if (to_host and N == 1) else None, want_bitmap=False)
-            if N > 1:
-                owners = multi.exchange_tiles(boss.tiles(), max_tiles, device=f"cuda:{dev}")
-                multi.gather_rows_to_root(fb, owners, root=0)
-                if to_host and rank == 0:
-                    gpu.readback(bitmap)
+            shared.render()
             e1.record(stream)
-        stream.synchronize()
+        shared.end()                                         # sync + barrier: the whole frame is in GPU 0's framebuffer
+        if to_host and rank == 0:
+            gpu.readback(bitmap)
+        st = gpu.counters(reset=True)
+        st["kernel_launches"] = gpu.kernel_launches(reset=True)
+        st["tiles_total"] = 1
         return st, e0.elapsed_time(e1)
 
     def flush_l2():
@@ -358,7 +371,7 @@ def main():
     ms_per_step = float(t_dev.mean())
     e2e_ms = float(t_e2e.mean())
     if rank != 0:
-        boss.close()
+        shared.close(); gpu.shutdown()
         if N > 1:
             dist.barrier(); dist.destroy_process_group()
         return 0
@@ -372,8 +385,11 @@ def main():
         "data": "synthetic (procedural 868352-triangle octa-sphere stand-in for the missing dragon.ply, generated in-run)",
         "config": {"workload": desc, "triangles": n_tri, "bvh_nodes": n_nodes, "lights": 3, "max_depth": depth, "forced_reflection": refl,
                    "l2": "flushed between timed steps (256 MiB device write, outside the timed events)",
-                   "timing": "CUDA events on the launching stream around each frame's kernels" + (" + NCCL gather to GPU 0; max over ranks per step" if N > 1 else ""),
-                   "tiles_per_frame": st["tiles_total"], "parallelism": f"row tiles stolen from a shared counter by {N} GPU(s); scene replicated"},
+                   "timing": "CUDA events on the launching stream around each frame's kernels" + ("; max over ranks per step (pixels land in GPU 0's framebuffer inside those kernels)" if N > 1 else ""),
+                   "tiles_per_frame": st["tiles_total"],
+                   "parallelism": (f"{N} GPUs, one process each, scene replicated: 64-pixel chunks stolen from one cursor on GPU 0 (atomics over NVLink), "
+                                   "finished pixels stored straight into GPU 0's framebuffer (peer stores, CUDA IPC); no collective" if N > 1
+                                   else "1 GPU; persistent warps steal 32-pixel chunks from a device-side cursor")},
         "ms_per_frame": ms_per_step,
         "rays_per_frame": {"primary": rays_primary, "shadow": rays_shadow, "reflection": rays_refl},
         "mrays_per_s_by_kind": {"primary": rays_primary / ms_per_step / 1e3, "shadow": rays_shadow / ms_per_step / 1e3,
@@ -381,7 +397,9 @@ def main():
         "ms_per_step_min": float(t_dev.min()), "ms_per_step_max": float(t_dev.max()),
         "e2e": {"value": rays_total / e2e_ms / 1e3, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
                 "h2d_bytes_per_step": 12 * 8, "d2h_bytes_per_step": int(traced_px) * 4,
-                "what": "ct_host_boss_set_camera (host doubles) + render + ct_gpu_readback into a pinned host bitmap, wall clock, max over ranks"},
+                "what": ("ct_host_boss_set_camera (host doubles) + render + ct_gpu_readback into a pinned host bitmap, wall clock" if N == 1 else
+                         "per frame: cursor reset + barrier, ct_gpu_set_camera on every rank, ct_gpu_render_shared, sync + barrier, ct_gpu_readback of the "
+                         "whole frame on rank 0 into a pinned host bitmap; wall clock, max over ranks")},
         "gpu_launches": total_launches,
         "clocks": clocks,
         "one_time_ms": {"scene_parse": load_ms, "bvh_build": bvh_ms, "upload_and_alloc": upload_ms},
@@ -443,7 +461,7 @@ def main():
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(workload, fs, counts)
     else:
-        boss.close()
+        shared.close(); gpu.shutdown()
     print(json.dumps(line), flush=True)
     if N > 1:
         dist.barrier(); dist.destroy_process_group()

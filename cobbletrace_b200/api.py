@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "ct_gpu_abi_version", "ct_gpu_device_count", "ct_gpu_last_error", "ct_gpu_upload_scene", "ct_gpu_set_camera",
     "ct_gpu_set_stream", "ct_gpu_render_tile", "ct_gpu_readback", "ct_gpu_readback_hits", "ct_gpu_get_counters",
     "ct_gpu_last_tile_ms", "ct_gpu_sync", "ct_gpu_throttle", "ct_gpu_kernel_launches", "ct_gpu_last_tile_stages", "ct_gpu_framebuffer", "ct_gpu_gather_rows", "ct_gpu_debug_closest",
-    "ct_gpu_debug_primitives", "ct_gpu_debug_filter", "ct_gpu_filter_stats", "ct_gpu_shutdown", "ct_gpu_set_option", "ct_gpu_overflow_stats",
+    "ct_gpu_debug_primitives", "ct_gpu_debug_filter", "ct_gpu_filter_stats", "ct_gpu_shutdown", "ct_gpu_share_export", "ct_gpu_share_attach", "ct_gpu_share_reset", "ct_gpu_render_shared", "ct_gpu_set_option", "ct_gpu_overflow_stats",
 ]
 
 
@@ -46,6 +46,11 @@ class Material(C.Structure):     # == ct_material == reference material_t (scene
 
 class Light(C.Structure):        # == ct_light == reference light_t (scenefile.h:61-66)
     _fields_ = [("type", C.c_int32), ("intensity", C.c_float), ("position", C.c_double * 3), ("direction", C.c_double * 3)]
+
+
+class Share(C.Structure):        # == ct_gpu_share
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("pid", C.c_int64), ("fb_ptr", C.c_uint64), ("cursor_ptr", C.c_uint64),
+                ("fb_ipc", C.c_ubyte * 64), ("cursor_ipc", C.c_ubyte * 64), ("width", C.c_int32), ("height", C.c_int32)]
 
 
 class SceneDesc(C.Structure):    # == ct_scene_desc
@@ -105,6 +110,10 @@ def load_library(path: Optional[str] = None):
     L.ct_gpu_debug_primitives.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ct_gpu_debug_filter.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, C.c_double, vp]
     L.ct_gpu_filter_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.ct_gpu_share_export.argtypes = [C.c_int, C.POINTER(Share)]
+    L.ct_gpu_share_attach.argtypes = [C.c_int, C.POINTER(Share)]
+    L.ct_gpu_share_reset.argtypes = [C.c_int]
+    L.ct_gpu_render_shared.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(RayCounters)]
     L.ct_gpu_shutdown.argtypes = [C.c_int]
     L.ct_gpu_set_option.argtypes = [C.c_char_p, C.c_longlong]
     L.ct_gpu_overflow_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -187,6 +196,31 @@ class GpuRenderer:
             y_start, y_end = self.full_range()
         c = RayCounters() if counters else None
         _check(self.L, self.L.ct_gpu_render_tile(self.device, y_start, y_end, C.byref(c) if counters else None))
+        return c.as_dict() if counters else None
+
+    # -- one frame on several GPUs (ct_gpu_share_*) ------------------------------------------------------------
+    def share_export(self) -> bytes:
+        """Root GPU: the handle (plain bytes) the other GPUs attach to."""
+        h = Share()
+        h.struct_size = C.sizeof(Share)
+        _check(self.L, self.L.ct_gpu_share_export(self.device, C.byref(h)))
+        return bytes(h)
+
+    def share_attach(self, handle: Optional[bytes]):
+        if handle is None:
+            _check(self.L, self.L.ct_gpu_share_attach(self.device, None))
+            return
+        h = Share.from_buffer_copy(handle)
+        _check(self.L, self.L.ct_gpu_share_attach(self.device, C.byref(h)))
+
+    def share_reset(self):
+        _check(self.L, self.L.ct_gpu_share_reset(self.device))
+
+    def render_shared(self, y_start: Optional[int] = None, y_end: Optional[int] = None, counters: bool = False):
+        if y_start is None:
+            y_start, y_end = self.full_range()
+        c = RayCounters() if counters else None
+        _check(self.L, self.L.ct_gpu_render_shared(self.device, y_start, y_end, C.byref(c) if counters else None))
         return c.as_dict() if counters else None
 
     def sync(self):

@@ -26,6 +26,7 @@
 
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -51,6 +52,9 @@ constexpr int kMinBlocks = CT_MIN_BLOCKS;   // traversal kernels: resident CTAs 
 constexpr int kOvfThreads = 256;     // k_overflow CTA
 constexpr int kMaxLaunches = 80;     // launches of one tile (work cursors / stage events)
 constexpr uint32_t kNoPos = 0xffffffffu;
+constexpr uint32_t kChunkLocalShift = 5;    // slots a warp takes from the tile's cursor at a time: 32 (one 8x4 pixel block) ...
+constexpr uint32_t kChunkSharedShift = 6;   // ... or 64 when the cursor is another GPU's memory (fewer NVLink round trips)
+constexpr uint32_t kChunkMax = 1u << kChunkSharedShift;
 constexpr uint32_t kDefaultBudget = 384;    // node visits + triangle tests before a ray is parked for k_overflow
 
 // ---- device-side scene layout (SoA arrays in HBM, uploaded once) -----------------------------------
@@ -84,6 +88,8 @@ struct __align__(16) OvfRay {        // a parked ray: 64 B
 struct DevSched {                    // zeroed at the start of every tile render
     unsigned long long work[kMaxLaunches];   // dynamic-fetch cursors, one per launch of the tile
     uint32_t queue_count[16];        // paths alive at depth d (d >= 1)
+    uint32_t own_count;              // chunks of the tile this device took from the (possibly shared) cursor
+    unsigned long long steal_local;  // the cursor of a tile rendered by this device alone
     uint32_t ovf_count[40];          // rays parked for the k_overflow launch 2*depth + {0: bounce, 1: shadow}
     uint32_t ovf_cursor[40];         // k_overflow's warp-cooperative pass: next parked ray to take
     uint32_t huge_count[40];         // ... rays it handed on to the grid-wide breadth-first pass
@@ -129,7 +135,11 @@ struct Params {
     uint32_t *occ;                               // [path][occ_words] shadow-ray verdicts of the current depth, bit i = light i occluded
     uint32_t *stack_color; float *stack_refl;    // [depth][slot]
     uint8_t *term_level;                         // [slot] level at which the chain ended
-    uint32_t *fb;                                // W*H
+    uint32_t *fb;                                // W*H, this device's framebuffer
+    uint32_t *fb_out;                            // where finished pixels are stored: fb, or the root GPU's fb (peer memory)
+    unsigned long long *steal;                   // the tile's chunk cursor: local, or on the root GPU (peer memory)
+    uint32_t chunk_shift;                        // log2(slots per chunk)
+    uint32_t *own_chunks;                        // chunk numbers this device took, in the order it took them
     uint32_t *dbg_found, *dbg_index; float *dbg_t;   // optional (CT_FLAG_KEEP_HITS), framebuffer layout
     // parked rays + breadth-first frontier
     OvfRay *ovf; uint32_t ovf_cap;
@@ -432,15 +442,21 @@ CT_DEV void warp_add(unsigned long long *dst, uint32_t v) {
     if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, (unsigned long long)v);
 }
 
+// Depth-0 paths are numbered in the order this device took their chunks from the cursor.
+CT_DEV uint32_t own_slot(const Params &P, uint32_t q) {
+    return (P.own_chunks[q >> P.chunk_shift] << P.chunk_shift) + (q & ((1u << P.chunk_shift) - 1u));
+}
+CT_DEV uint32_t depth0_count(const Params &P) { return P.sched->own_count << P.chunk_shift; }
+
 // The path with queue index q at `depth`: its ray (direction only for depth 0 is regenerated from the pixel),
 // its closest-hit record and its depth-0 slot.  False for padding lanes / untraced pixels.
 CT_DEV bool load_path(const Params &P, int depth, uint32_t q, uint32_t &slot, int &fbi, Ray &r, float &tc, uint32_t &pos) {
     if (depth == 0) {
         int x, y;
-        slot = q;
-        if (!slot_pixel(P, q, x, y, fbi)) return false;
+        slot = own_slot(P, q);
+        if (!slot_pixel(P, slot, x, y, fbi)) return false;
         r = primary_ray(P, x, y);
-        tc = P.hit0_t[q]; pos = P.hit0_pos[q];
+        tc = P.hit0_t[slot]; pos = P.hit0_pos[slot];
     } else {
         const int cur = depth & 1;
         slot = P.path_slot[cur][q];
@@ -468,33 +484,48 @@ CT_DEV bool park_ray(const Params &P, int ovf_idx, const double *r64, uint32_t t
     return true;
 }
 
+// Primary rays.  Persistent warps take chunks of 32 or 64 slots from the tile's cursor -- one counter for the whole
+// tile, which in a multi-GPU frame lives on the root GPU and is shared by all devices over NVLink (dynamic
+// stealing at chunk granularity) -- and remember which chunks they took: the later stages of this
+// device work on exactly those.
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __grid_constant__ Params P, int work_idx) {
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __grid_constant__ Params P) {
     LocalCount lc;
     uint32_t n_rays = 0;
+    const uint32_t lane = threadIdx.x & 31u, chunk = 1u << P.chunk_shift;
     while (true) {
-        unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
-        if (base >= P.n_slots) break;
-        uint32_t slot = (uint32_t)base + (threadIdx.x & 31u);
-        int x, y, fbi;
-        const bool active = slot_pixel(P, slot, x, y, fbi);
-        double r64[6];
-        TRay r;
-        if (active) {
-            Ray ray = primary_ray(P, x, y);
-            tray_setup(r, ray, P.bound, r64);
+        unsigned long long base = 0;
+        uint32_t mine = 0;
+        if (lane == 0) {
+            base = atomicAdd(P.steal, (unsigned long long)chunk);
+            if (base < P.n_slots) { mine = atomicAdd(&P.sched->own_count, 1u); P.own_chunks[mine] = (uint32_t)(base >> P.chunk_shift); }
         }
-        float tc; uint32_t pos;
-        bool found = traverse<kClosest, COUNT>(P, r, active, 0xffffffffu, tc, pos, lc) == kTravHit;   // warp-synchronous
-        if (!active) continue;
-        n_rays++;
-        P.hit0_t[slot] = tc;
-        P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
-        if (found) clear_occ(P, slot);
-        if (P.dbg_found) {
-            P.dbg_found[fbi] = found ? 1u : 0u;
-            P.dbg_index[fbi] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
-            P.dbg_t[fbi] = tc;
+        base = __shfl_sync(kFullMask, base, 0);
+        mine = __shfl_sync(kFullMask, mine, 0);
+        if (base >= P.n_slots) break;
+        for (uint32_t sub = 0; sub < chunk; sub += 32u) {
+            const uint32_t slot = (uint32_t)base + sub + lane;
+            const uint32_t q = (mine << P.chunk_shift) + sub + lane;   // this path's depth-0 number on this device
+            int x, y, fbi;
+            const bool active = slot < P.n_slots && slot_pixel(P, slot, x, y, fbi);
+            double r64[6];
+            TRay r;
+            if (active) {
+                Ray ray = primary_ray(P, x, y);
+                tray_setup(r, ray, P.bound, r64);
+            }
+            float tc; uint32_t pos;
+            bool found = traverse<kClosest, COUNT>(P, r, active, 0xffffffffu, tc, pos, lc) == kTravHit;   // warp-synchronous
+            if (!active) continue;
+            n_rays++;
+            P.hit0_t[slot] = tc;
+            P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
+            if (found) clear_occ(P, q);
+            if (P.dbg_found) {
+                P.dbg_found[fbi] = found ? 1u : 0u;
+                P.dbg_index[fbi] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
+                P.dbg_t[fbi] = tc;
+            }
         }
     }
     warp_add(&P.tot->rays_primary, n_rays);
@@ -508,7 +539,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
     LocalCount lc;
     uint32_t n_shadow = 0, n_parked = 0;
-    const uint32_t n = depth == 0 ? P.n_slots : P.sched->queue_count[depth];
+    const uint32_t n = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
     const unsigned long long n_pad = ((unsigned long long)n + 31ull) & ~31ull;
     const unsigned long long total = n_pad * P.n_slights;
     while (true) {
@@ -556,7 +587,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
 // verdicts were computed by k_shadow (+ k_overflow).
 __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__ Params P, int depth, int work_idx) {
     uint32_t n_refl = 0;
-    const uint32_t n = depth == 0 ? P.n_slots : P.sched->queue_count[depth];
+    const uint32_t n = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
     const int nxt = (depth & 1) ^ 1;
     while (true) {
         unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
@@ -570,7 +601,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
         if (active) {
             uint32_t *sc = P.stack_color + (size_t)depth * P.cap + slot;
             if (pos == kNoPos) {                                           // miss (depth 0 only): raythread.cpp:385
-                if (depth == 0) P.fb[fbi] = P.background;
+                if (depth == 0) P.fb_out[fbi] = P.background;
                 *sc = P.background;
                 P.term_level[slot] = (uint8_t)depth;
             } else {
@@ -611,7 +642,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
                 int remaining = P.max_depth - depth;                        // recursionDepth of this TraceRay call
                 if (remaining <= 0 || !(mat.reflection > 0.0f)) {           // :369  (reflection <= 0, NaN-safe)
                     P.term_level[slot] = (uint8_t)depth;
-                    if (depth == 0) P.fb[fbi] = local;
+                    if (depth == 0) P.fb_out[fbi] = local;
                 } else {
                     P.stack_refl[(size_t)depth * P.cap + slot] = mat.reflection;
                     rdir = reflect_ray(view, normal);                        // :372
@@ -894,7 +925,9 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
 
 // Unwind TraceRay's recursion (raythread.cpp:375-379) for pixels whose chain went past depth 0.
 __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Params P) {
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < P.n_slots; slot += gridDim.x * blockDim.x) {
+    const uint32_t n = depth0_count(P);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t slot = own_slot(P, q);
         int x, y, fbi;
         if (!slot_pixel(P, slot, x, y, fbi)) continue;
         int lvl = P.term_level[slot];
@@ -902,7 +935,7 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Params 
         uint32_t color = P.stack_color[(size_t)lvl * P.cap + slot];
         for (int d = lvl - 1; d >= 0; d--)
             color = blend_color(P.stack_color[(size_t)d * P.cap + slot], color, P.stack_refl[(size_t)d * P.cap + slot]);
-        P.fb[fbi] = color;
+        P.fb_out[fbi] = color;
     }
 }
 
@@ -1008,6 +1041,10 @@ struct DeviceState {
     const char *stage_name[kMaxLaunches] = {};
     int stage_depth[kMaxLaunches] = {};
     bool can_overflow = false;       // some traversal could exceed the visit budget: k_overflow launches are needed
+    // multi-GPU frame sharing (ct_gpu_share_*): the cursor and framebuffer a shared render uses (own or the root's)
+    unsigned long long *cursor_own = nullptr, *share_cursor = nullptr;
+    uint32_t *share_fb = nullptr;
+    void *ipc_opened[2] = {nullptr, nullptr};
     int ovf_grid[4] = {};            // co-resident grid of the k_overflow instantiations [mode][count]
     int n_stages = 0;
     bool timed = false;
@@ -1035,6 +1072,7 @@ int check_device(int device) {
 }
 
 void free_device(DeviceState &s) {
+    for (void *q : s.ipc_opened) if (q) cudaIpcCloseMemHandle(q);
     for (void *p : s.allocs) cudaFree(p);
     s.allocs.clear();
     if (s.ev0) cudaEventDestroy(s.ev0);
@@ -1261,7 +1299,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     s.col_lo = std::max(0, x_lo + d->width / 2);
     s.col_hi = std::min(d->width, x_lo + n_x + d->width / 2);
     int rows_max = 2 * half + 1;
-    p.cap = (uint32_t)p.blocks_x * (uint32_t)((rows_max + 3) / 4) * 32u;
+    p.cap = ((uint32_t)p.blocks_x * (uint32_t)((rows_max + 3) / 4) * 32u + kChunkMax - 1u) / kChunkMax * kChunkMax;
 
     const int levels = s.any_reflective ? d->max_depth + 1 : 1;
     TRY(dev_alloc(s, &p.hit0_t, p.cap)); TRY(dev_alloc(s, &p.hit0_pos, p.cap));
@@ -1293,6 +1331,9 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
         for (int b = 0; b < 2; b++) { TRY(dev_alloc(s, &p.ray_buf[b], (size_t)p.cap * 6)); TRY(dev_alloc(s, &p.path_slot[b], p.cap)); }
     }
     TRY(dev_alloc(s, &p.fb, (size_t)d->width * d->height, true));       // calloc'd like cobbletrace.cpp:57
+    TRY(dev_alloc(s, &p.own_chunks, (p.cap >> kChunkLocalShift) + 1u));
+    TRY(dev_alloc(s, &s.cursor_own, 1, true));                           // its own allocation: exported over CUDA IPC
+    s.share_cursor = s.cursor_own; s.share_fb = p.fb;
     if (d->flags & CT_FLAG_KEEP_HITS) {
         size_t npx = (size_t)d->width * d->height;
         TRY(dev_alloc(s, &p.dbg_found, npx)); TRY(dev_alloc(s, &p.dbg_index, npx, true)); TRY(dev_alloc(s, &p.dbg_t, npx, true));
@@ -1323,7 +1364,7 @@ int ct_gpu_set_stream(int device, void *cuda_stream) {
     return CT_OK;
 }
 
-int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *counters) {
+static int render_impl(int device, int y_start, int y_end, ct_ray_counters *counters, bool shared) {
     TRY(check_device(device));
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
@@ -1337,6 +1378,10 @@ int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *coun
     if (p.n_slots > p.cap) return fail(CT_ERR_INVALID, "tile [%d,%d) larger than the frame", y_start, y_end);
     const bool count = (s.flags & CT_FLAG_COUNT_TESTS) != 0;
     const int depth_max = s.any_reflective ? p.max_depth : 0;
+    // one device: its own cursor (zeroed with the rest of DevSched below) and framebuffer; shared frame: the root's
+    p.steal = shared ? s.share_cursor : &p.sched->steal_local;
+    p.chunk_shift = shared ? kChunkSharedShift : kChunkLocalShift;
+    p.fb_out = shared ? s.share_fb : p.fb;
     Params pk = p; pk.max_depth = depth_max;   // with no reflective material the recursion never goes past depth 0 (:369)
     cudaStream_t st = s.stream;
     CU(cudaMemsetAsync(p.sched, 0, sizeof(DevSched), st));
@@ -1362,8 +1407,8 @@ int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *coun
         CU(cudaLaunchCooperativeKernel(fn, dim3(s.ovf_grid[mode_anyhit * 2 + (count ? 1 : 0)]), dim3(kOvfThreads), args, 0, st));
         return mark(mode_anyhit ? "overflow_shadow" : "overflow_bounce", depth);
     };
-    if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(pk, work++);
-    else k_primary<false><<<grid, kBlockThreads, 0, st>>>(pk, work++);
+    if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(pk);
+    else k_primary<false><<<grid, kBlockThreads, 0, st>>>(pk);
     TRY(mark("primary", 0));
     for (int d = 0; d <= depth_max; d++) {
         if (d > 0) {
@@ -1402,6 +1447,76 @@ int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *coun
         counters->tri_tests = now.tri_tests - s.snapshot.tri_tests;
         s.snapshot = now;
     }
+    return CT_OK;
+}
+
+int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *counters) {
+    return render_impl(device, y_start, y_end, counters, false);
+}
+
+int ct_gpu_render_shared(int device, int y_start, int y_end, ct_ray_counters *counters) {
+    return render_impl(device, y_start, y_end, counters, true);
+}
+
+int ct_gpu_share_export(int device, ct_gpu_share *out) {
+    if (!out || out->struct_size != sizeof(ct_gpu_share)) return fail(CT_ERR_INVALID, "ct_gpu_share missing or struct_size != %zu", sizeof(ct_gpu_share));
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ct_gpu_share reserves 64 bytes per IPC handle");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s.p.fb));
+    memcpy(out->fb_ipc, &h, sizeof h);
+    CU(cudaIpcGetMemHandle(&h, s.cursor_own));
+    memcpy(out->cursor_ipc, &h, sizeof h);
+    out->device = device;
+    out->pid = (int64_t)getpid();
+    out->fb_ptr = (uint64_t)(uintptr_t)s.p.fb;
+    out->cursor_ptr = (uint64_t)(uintptr_t)s.cursor_own;
+    out->width = s.p.W; out->height = s.p.H;
+    return CT_OK;
+}
+
+int ct_gpu_share_attach(int device, const ct_gpu_share *root) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    for (void *&q : s.ipc_opened) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    if (!root) {                                             // detach: back to this device's own cursor and framebuffer
+        s.share_cursor = s.cursor_own; s.share_fb = s.p.fb;
+        return CT_OK;
+    }
+    if (root->struct_size != sizeof(ct_gpu_share)) return fail(CT_ERR_INVALID, "ct_gpu_share struct_size != %zu", sizeof(ct_gpu_share));
+    if (root->width != s.p.W || root->height != s.p.H) return fail(CT_ERR_INVALID, "shared frame is %dx%d, this device renders %dx%d", root->width, root->height, s.p.W, s.p.H);
+    if (root->pid == (int64_t)getpid()) {                    // same process: raw pointers (+ peer access between the two devices)
+        if (root->device != device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, device, root->device));
+            if (!can) return fail(CT_ERR_CUDA, "device %d cannot access device %d's memory", device, root->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(root->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(CT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        s.share_fb = (uint32_t *)(uintptr_t)root->fb_ptr;
+        s.share_cursor = (unsigned long long *)(uintptr_t)root->cursor_ptr;
+        return CT_OK;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, root->fb_ipc, sizeof h);
+    CU(cudaIpcOpenMemHandle(&s.ipc_opened[0], h, cudaIpcMemLazyEnablePeerAccess));
+    memcpy(&h, root->cursor_ipc, sizeof h);
+    CU(cudaIpcOpenMemHandle(&s.ipc_opened[1], h, cudaIpcMemLazyEnablePeerAccess));
+    s.share_fb = (uint32_t *)s.ipc_opened[0];
+    s.share_cursor = (unsigned long long *)s.ipc_opened[1];
+    return CT_OK;
+}
+
+int ct_gpu_share_reset(int device) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    CU(cudaMemsetAsync(s.cursor_own, 0, sizeof(unsigned long long), s.stream));
+    CU(cudaStreamSynchronize(s.stream));
     return CT_OK;
 }
 

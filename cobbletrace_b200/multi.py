@@ -1,9 +1,15 @@
-"""One-process-per-GPU plumbing (torch.distributed): the frame is cut into row tiles that the ranks steal
-from a shared counter (C++ boss, ct_host_boss_*), and the finished tiles are gathered to rank 0.
+"""One-process-per-GPU plumbing (torch.distributed).
 
-The path has exactly one exchange step -- the gather of 4-byte pixels to GPU 0 -- so that is
-the only collective: point-to-point sends of each rank's own rows into rank 0's framebuffer (NCCL over
-NVLink on GPUs; gloo on CPU for the tests).  Rendering itself needs no communication (scene replicated).
+The path shards by pixels and has exactly one exchange step -- collecting 4-byte pixels on GPU 0.
+Two ways to run a frame on N GPUs, scene replicated on each:
+
+  SharedFrame (the fast path, used by bench.py): every GPU renders the same tile with ct_gpu_render_shared; its
+      primary-ray warps steal 64-pixel chunks from ONE cursor in GPU 0's memory (atomics over NVLink) and its
+      shading kernels store finished pixels straight into GPU 0's framebuffer (peer stores through CUDA IPC).
+      No collective and no host in the loop; torch.distributed only ships the IPC handle and provides the
+      per-frame barriers.
+  row tiles (ct_host_boss_* / exchange_tiles / gather_rows_to_root): tiles stolen from a host-side counter and
+      gathered with point-to-point sends (NCCL on GPUs, gloo on CPU for the tests) -- the portable variant.
 """
 from __future__ import annotations
 
@@ -97,3 +103,40 @@ def gather_rows_to_root(fb: torch.Tensor, tiles_by_rank: Sequence[Sequence[Tuple
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return nbytes
+
+
+class SharedFrame:
+    """N ranks, one GPU each, one frame: see the module docstring.  `renderer` is this rank's GpuRenderer with the
+    scene already uploaded; rank `root`'s framebuffer receives the whole frame."""
+
+    def __init__(self, renderer, root: int = 0):
+        self.r, self.root = renderer, root
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        box = [renderer.share_export() if self.rank == root else None]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=root)
+            if self.rank != root:
+                renderer.share_attach(box[0])
+        self.handle = box[0]
+
+    def begin(self):
+        """Root zeroes the cursor; nobody may start stealing before that (barrier)."""
+        if self.rank == self.root:
+            self.r.share_reset()
+        if self.world > 1:
+            dist.barrier()
+
+    def render(self, counters: bool = False):
+        """This rank's share of the frame (asynchronous on the renderer's stream)."""
+        return self.r.render_shared(counters=counters)
+
+    def end(self):
+        """All ranks' pixels are in the root's framebuffer after this."""
+        self.r.sync()
+        if self.world > 1:
+            dist.barrier()
+
+    def close(self):
+        if self.rank != self.root and self.world > 1:
+            self.r.share_attach(None)

@@ -128,6 +128,34 @@ int ct_gpu_set_stream(int device, void *cuda_stream);
  * synchronises and returns this tile's ray counts. */
 int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *counters);
 
+/* ---- one frame on several GPUs -------------------------------------------------------------------
+ * The scene is uploaded to every GPU.  One of them is the ROOT: its framebuffer receives every pixel and it hosts
+ * the frame's chunk cursor.  Every GPU renders the SAME tile with ct_gpu_render_shared: its primary-ray warps take
+ * chunks of 64 pixels from the root's cursor with atomics over NVLink (dynamic stealing, no host in the loop) and
+ * its shading kernels store finished pixels straight into the root's framebuffer (peer stores) -- there is no
+ * separate gather step.  The GPUs may be driven by one process or by one process each (CUDA IPC).
+ *
+ *   root:    ct_gpu_share_export(dev, &h)  -> ship h to the others (it is plain bytes)
+ *   others:  ct_gpu_share_attach(dev, &h)
+ *   frame:   root: ct_gpu_share_reset(dev); [barrier]; all: ct_gpu_render_shared(dev, y0, y1, ..); ct_gpu_sync(dev);
+ *            [barrier]; root: ct_gpu_readback(dev, ...)
+ */
+typedef struct ct_gpu_share {
+    uint32_t struct_size;            /* = sizeof(ct_gpu_share) */
+    int32_t device;                  /* root device index inside the exporting process */
+    int64_t pid;                     /* exporting process */
+    uint64_t fb_ptr, cursor_ptr;     /* raw device pointers (used when the attaching device is driven by the same process) */
+    unsigned char fb_ipc[64], cursor_ipc[64];   /* cudaIpcMemHandle_t of the same two allocations (other processes) */
+    int32_t width, height;
+} ct_gpu_share;
+
+int ct_gpu_share_export(int device, ct_gpu_share *out);
+int ct_gpu_share_attach(int device, const ct_gpu_share *root);   /* root == NULL detaches */
+int ct_gpu_share_reset(int device);                              /* root only: zero the cursor; synchronises */
+/* ct_gpu_render_tile for a frame shared between GPUs.  Without an attach it behaves like a one-GPU frame whose
+ * cursor must be reset with ct_gpu_share_reset first. */
+int ct_gpu_render_shared(int device, int y_start, int y_end, ct_ray_counters *counters);
+
 /* Blocks until all submitted tiles are done, then copies framebuffer rows [row_start,row_end) into
  * dst (bitmap->memory, row stride in pixels).  Only pixels the tracer covers are written: the centred
  * square's columns (all columns with CT_FLAG_WIDE), and never a row the reference never writes

@@ -176,6 +176,26 @@ def test_parked_rays_give_the_same_frames(budget, warp_budget, golden, scene_loa
         ct.api.set_option("overflow_warp_budget", 0)
 
 
+def test_shared_frame_mode_on_one_gpu(golden, scene_loader, gpu):
+    """ct_gpu_render_shared (the multi-GPU path: cursor and output framebuffer reached through the share handle)
+    with this GPU as its own root: same frame as ct_gpu_render_tile; chunks are handed out exactly once per reset."""
+    fs, meta = case_scene("bunny_refl_d2_160", golden, scene_loader)
+    want = load_frames("bunny_refl_d2_160")["frame"]
+    gpu.upload(fs, meta["width"], meta["height"], max_depth=meta["depth"])
+    gpu.share_attach(gpu.share_export())                        # self-attach: same process, same device
+    gpu.share_reset()
+    c1 = gpu.render_shared(counters=True)
+    assert np.array_equal(gpu.readback(), want)
+    c2 = gpu.render_shared(counters=True)                       # cursor not reset: nothing left to steal
+    assert c2["rays_primary"] == 0 and c2["rays_shadow"] == 0 and np.array_equal(gpu.readback(), want)
+    gpu.share_reset()
+    c3 = gpu.render_shared(counters=True)
+    assert c3 == c1 and np.array_equal(gpu.readback(), want)
+    gpu.share_attach(None)
+    gpu.render_tile()
+    assert np.array_equal(gpu.readback(), want)
+
+
 def test_640_golden_hashes(golden, scene_loader, gpu):
     for name in ("scene_file_cube", "scene_import", "scene_import_bunny", "pc_big"):
         gpu.upload(scene_loader(name), 640, 640)

@@ -94,3 +94,90 @@ def test_tiles_to_rows_mapping():
     # H = 8: y in [-4,4) -> rows 8..1 ; tile [-4,-2) covers y=-4 (row 8, dropped) and y=-3 (row 7)
     assert multi.tiles_to_rows([(-4, -2), (2, 4)], 8) == [(7, 8), (1, 3)]
     assert multi.tiles_to_rows([(-2, 3)], 5) == [(0, 5)]            # odd H reaches row 0
+
+
+class _FakeRenderer:
+    """Stands in for GpuRenderer in the SharedFrame protocol test: the 'root framebuffer' and the chunk cursor live in
+    a file-backed numpy memmap that every rank opens -- the CPU analogue of the IPC-mapped GPU-0 memory."""
+
+    def __init__(self, rank, path, n_chunks):
+        self.rank, self.path, self.n_chunks = rank, path, n_chunks
+        self.calls = []
+        self.mem = None
+
+    def share_export(self):
+        np.lib.format.open_memmap(self.path, mode="w+", dtype=np.int64, shape=(1 + self.n_chunks,))[:] = -1
+        self.mem = np.load(self.path, mmap_mode="r+")
+        self.calls.append("export")
+        return self.path.encode()
+
+    def share_attach(self, handle):
+        self.calls.append("attach" if handle is not None else "detach")
+        if handle is not None:
+            self.mem = np.load(handle.decode(), mmap_mode="r+")
+
+    def share_reset(self):
+        self.calls.append("reset")
+        self.mem[0] = 0
+        self.mem.flush()
+
+    def render_shared(self, counters=False):
+        import fcntl, time
+        self.calls.append("render")
+        took = 0
+        with open(self.path + ".lock", "a+") as lock:
+            while True:
+                fcntl.flock(lock, fcntl.LOCK_EX)                    # "atomicAdd" on the shared cursor
+                mem = np.load(self.path, mmap_mode="r+")
+                c = int(mem[0]); mem[0] = c + 1; mem.flush()
+                fcntl.flock(lock, fcntl.LOCK_UN)
+                if c >= self.n_chunks:
+                    break
+                mem[1 + c] = self.rank; mem.flush()                 # "peer store" of the finished chunk into the root's frame
+                took += 1
+                time.sleep(0.002 if self.rank == 1 else 0.0005)
+        return {"rays_primary": took}
+
+    def sync(self):
+        self.calls.append("sync")
+
+
+def _shared_worker(rank, world, port, path, n_chunks, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from cobbletrace_b200 import multi
+    multi.init_distributed("gloo")
+    r = _FakeRenderer(rank, path, n_chunks)
+    sf = multi.SharedFrame(r, root=0)
+    shares = []
+    for frame in range(3):
+        sf.begin()
+        took = sf.render(counters=True)["rays_primary"]
+        sf.end()
+        t = torch.tensor([took])
+        dist.all_reduce(t)
+        assert int(t) == n_chunks, "every chunk exactly once"
+        if rank == 0:
+            owners = np.load(path, mmap_mode="r")[1:]
+            assert set(np.unique(owners).tolist()) <= {0, 1} and (owners >= 0).all(), "frame incomplete on the root"
+            shares.append([(owners == 0).sum(), (owners == 1).sum()])
+        dist.barrier()
+        if rank == 0:
+            np.load(path, mmap_mode="r+")[1:] = -1
+    sf.close()
+    want = ["export"] + ["reset", "render", "sync"] * 3 if rank == 0 else ["attach"] + ["render", "sync"] * 3 + ["detach"]
+    assert r.calls == want, r.calls
+    if rank == 0:
+        np.save(out_path, np.array(shares))
+    dist.destroy_process_group()
+
+
+def test_shared_frame_protocol_two_ranks(tmp_path):
+    """multi.SharedFrame on 2 gloo ranks: the root exports, the other attaches, every frame is reset -> barrier ->
+    render -> sync -> barrier, all chunks are taken exactly once and land in the root's frame."""
+    out = str(tmp_path / "shares.npy")
+    mp.spawn(_shared_worker, args=(2, _free_port(), str(tmp_path / "frame.npy"), 60, out), nprocs=2, join=True)
+    shares = np.load(out)
+    assert (shares.sum(1) == 60).all() and (shares > 0).all(), shares
+    assert shares[:, 0].sum() > shares[:, 1].sum(), shares          # the faster rank stole more
