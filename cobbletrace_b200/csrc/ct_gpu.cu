@@ -24,7 +24,6 @@
 #include "../../include/ct_gpu.h"
 #include "ct_exact.cuh"
 
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <unistd.h>
 
@@ -36,7 +35,6 @@
 #include <mutex>
 #include <vector>
 
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -92,8 +90,7 @@ struct DevSched {                    // zeroed at the start of every tile render
     unsigned long long steal_local;  // the cursor of a tile rendered by this device alone
     uint32_t ovf_count[40];          // rays parked for the k_overflow launch 2*depth + {0: bounce, 1: shadow}
     uint32_t ovf_cursor[40];         // k_overflow's warp-cooperative pass: next parked ray to take
-    uint32_t huge_count[40];         // ... rays it handed on to the grid-wide breadth-first pass
-    uint32_t bfs_count[3];           // frontier sizes of the breadth-first levels (rotating)
+    uint32_t huge_count[40];         // ... rays it handed on to k_overflow_huge
 };
 struct DevTotals {                   // running ray / test counters (never reset by a tile)
     unsigned long long rays_primary, rays_shadow, rays_reflection, box_tests, tri_tests;
@@ -141,11 +138,11 @@ struct Params {
     uint32_t chunk_shift;                        // log2(slots per chunk)
     uint32_t *own_chunks;                        // chunk numbers this device took, in the order it took them
     uint32_t *dbg_found, *dbg_index; float *dbg_t;   // optional (CT_FLAG_KEEP_HITS), framebuffer layout
-    // parked rays + breadth-first frontier
+    // parked rays
     OvfRay *ovf; uint32_t ovf_cap;
-    uint2 *frontier[2]; uint32_t frontier_cap;   // items (parked-ray index inside the batch, node)
-    uint32_t *ovf_result; uint32_t ovf_batch_max;
-    uint32_t *ovf_huge;                          // indices (into ovf) of the rays left to the breadth-first pass
+    uint32_t *ovf_huge;                          // indices (into ovf) of the rays k_overflow left to k_overflow_huge
+    const uint32_t *pair_parent;                 // pair -> 2 * parent pair + side of its own box (kNoPos for the root's children pair)
+    const uint32_t *tri_parent;                  // leaf position -> 2 * pair + side of the box of the leaf that holds it (kNoPos: root leaf)
     DevSched *sched;
     DevTotals *tot;
 };
@@ -465,6 +462,7 @@ CT_DEV bool load_path(const Params &P, int depth, uint32_t q, uint32_t &slot, in
         double2 a = rb[0], b = rb[1], c = rb[2];
         r.o = {a.x, a.y, b.x}; r.d = {b.y, c.x, c.y}; r.t = 0.0f;
         tc = P.hitb_t[q]; pos = P.hitb_pos[q];
+        if (pos == kNoPos) pos = P.pos_of_tri0;                 // "closestIndex = 0" (raythread.cpp:205): no barycentric pass at all
     }
     return true;
 }
@@ -721,8 +719,6 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
 //   kFirstLine  closestIndex = the bary-passing reachable triangle that the DFS meets first = the one with the
 //               smallest leaf position (BuildBVH hands the left child the lower part of the parent's index range,
 //               bvh.cpp:70-97, so leaf positions increase along the DFS).
-// The whole grid walks the tree breadth first, a batch of rays at a time: one frontier item = (ray, node), one
-// grid.sync per level, the frontier ping-pongs between two HBM buffers sized for the widest possible level.
 // Tests the triangles of an accepted leaf for a parked ray.  kAnyHit: 1 if one of them occludes, else 0;
 // kFirstLine: the first (lowest) leaf position with a barycentric pass, else kNoPos.
 template <TraverseMode MODE, bool COUNT>
@@ -754,171 +750,128 @@ CT_DEV void overflow_store(const Params &P, const OvfRay &o, uint32_t res) {
 constexpr int kWarpStack = 1024;         // pending interior nodes of one ray in the warp-cooperative pass
 constexpr uint32_t kWarpBudget = 4096;       // default node visits before a ray is handed to the grid-wide pass
 
-// Parked rays.  Pass 1: one WARP per ray -- the 32 lanes pop up to 32 pending interior nodes from a shared-memory
+// Parked rays, pass 1: one WARP per ray -- the 32 lanes pop up to 32 pending interior nodes from a shared-memory
 // stack, test their child pairs, test accepted leaves on the spot and push accepted interior children back.
-// A ray whose stack outgrows kWarpStack or that needs more than kWarpBudget node visits (the every-box-passes
-// rays described in the header: up to ~1M visits) goes to pass 2: the whole grid walks the tree breadth first, a
-// batch of rays at a time, one frontier item = (ray, interior node), one grid.sync per level, the frontier
-// ping-pongs between two HBM buffers sized for the widest possible level.
+// A ray whose stack outgrows kWarpStack, that needs more than P.warp_budget node visits or whose origin is so far
+// outside the scene that every box passes (the rays described in the header: ~1M visits) goes to k_overflow_huge.
 template <TraverseMode MODE, bool COUNT>
 __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant__ Params P, int ovf_idx) {
     const uint32_t n = min(P.sched->ovf_count[ovf_idx], P.ovf_cap);
-    if (n == 0) return;                                   // uniform over the grid: nobody reaches a grid.sync
-    cg::grid_group grid = cg::this_grid();
+    if (n == 0) return;
     LocalCount lc;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
-    // ---- pass 1: warp per ray
-    {
-        __shared__ uint32_t wstack[kOvfThreads / 32][kWarpStack];
-        uint32_t *stk = wstack[threadIdx.x >> 5];
-        while (true) {
-            uint32_t idx = 0;
-            if (lane == 0) idx = atomicAdd(&P.sched->ovf_cursor[ovf_idx], 1u);
-            idx = __shfl_sync(kFullMask, idx, 0);
-            if (idx >= n) break;
-            const OvfRay &o = P.ovf[idx];
-            Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
-            double r64[6];
-            TRay r;
-            tray_setup(r, ray, P.bound, r64);             // every lane holds the same ray
-            uint32_t res = MODE == kAnyHit ? 0u : kNoPos;
-            // An origin this far outside the scene (a shading point 2^32 ray lengths away) makes all slab
-            // quotients of an axis round to the same float: every box passes and no filter can help.  Straight to pass 2.
-            bool too_big = !r.filt || (double)r.om > 0x1p20 * fmax(fmax(P.bound[0], P.bound[1]), P.bound[2]);
-            if (COUNT && lane == 0 && !too_big) lc.box++;
-            if (!too_big && exact_root(P, r64, r.t)) {
-                if (P.root_cnt > 0) {
-                    if (lane == 0) res = overflow_leaf<MODE, COUNT>(P, r, P.root_ref, P.root_cnt, lc);
-                } else {
-                    if (lane == 0) stk[0] = P.root_ref;
-                    __syncwarp();
-                    uint32_t sp = 1, visits = 0;
-                    while (sp > 0) {
-                        const uint32_t take = min(sp, 32u);
-                        sp -= take;
-                        uint32_t n_out = 0, out_a = 0, out_b = 0;
-                        if (lane < take) {
-                            const uint32_t pid = stk[sp + lane];
-                            DevPair32 pr;
-                            load_pair32(P.pairs32, pid, pr);
-                            if (COUNT) lc.box += 2;
-                            bool hit_l, hit_r; float lo, hi;
-                            pair_accept<COUNT>(P, r, pid, pr, hit_l, hit_r, lo, hi, lc);
-                            if (hit_l) {
-                                if (pr.l_cnt > 0) res = overflow_merge<MODE>(res, overflow_leaf<MODE, COUNT>(P, r, pr.l_ref, pr.l_cnt, lc));
-                                else { out_a = pr.l_ref; n_out = 1; }
-                            }
-                            if (hit_r) {
-                                if (pr.r_cnt > 0) res = overflow_merge<MODE>(res, overflow_leaf<MODE, COUNT>(P, r, pr.r_ref, pr.r_cnt, lc));
-                                else { if (n_out) out_b = pr.r_ref; else out_a = pr.r_ref; n_out++; }
-                            }
-                        }
-                        __syncwarp();                     // every lane has read its entry before the pushes below
-                        if (MODE == kAnyHit && __any_sync(kFullMask, res != 0u)) break;
-                        uint32_t incl = n_out;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(kFullMask, incl, d); if ((int)lane >= d) incl += v; }
-                        const uint32_t total = __shfl_sync(kFullMask, incl, 31);
-                        visits += take;
-                        if (sp + total > (uint32_t)kWarpStack || visits > P.warp_budget) { too_big = true; break; }
-                        const uint32_t at = sp + incl - n_out;
-                        if (n_out > 0) stk[at] = out_a;
-                        if (n_out > 1) stk[at + 1u] = out_b;
-                        sp += total;
-                        __syncwarp();
-                    }
-                }
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) res = overflow_merge<MODE>(res, __shfl_xor_sync(kFullMask, res, d));
-            if (lane == 0) {
-                if (too_big) P.ovf_huge[atomicAdd(&P.sched->huge_count[ovf_idx], 1u)] = idx;
-                else overflow_store<MODE>(P, o, res);
-            }
-        }
-    }
-    grid.sync();
-    // ---- pass 2: grid-wide breadth-first walk of what is left
-    const uint32_t nh = *(volatile uint32_t *)&P.sched->huge_count[ovf_idx];
-    const uint32_t per_ray = P.n_pairs / 2u + 2u;         // widest level of interior nodes one ray can reach
-    const uint32_t batch = max(1u, min(P.frontier_cap / per_ray, P.ovf_batch_max));
-    volatile uint32_t *cnt = P.sched->bfs_count;
-    for (uint32_t b0 = 0; b0 < nh; b0 += batch) {
-        const uint32_t bn = min(batch, nh - b0);
-        if (tid == 0) { cnt[0] = 0u; cnt[1] = 0u; cnt[2] = 0u; }
-        for (uint32_t i = tid; i < bn; i += n_threads) P.ovf_result[i] = (MODE == kAnyHit) ? 0u : kNoPos;
-        grid.sync();
-        // level 0: the root (frontier items are accepted INTERIOR nodes = pair indices; leaves are tested on the spot)
-        for (uint32_t i = tid; i < bn; i += n_threads) {
-            const OvfRay &o = P.ovf[P.ovf_huge[b0 + i]];
-            Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
-            double r64[6];
-            TRay r;
-            tray_setup(r, ray, P.bound, r64);
-            if (COUNT) lc.box++;
-            if (!exact_root(P, r64, r.t)) continue;
-            if (P.root_cnt > 0) P.ovf_result[i] = overflow_leaf<MODE, COUNT>(P, r, P.root_ref, P.root_cnt, lc);
-            else P.frontier[0][atomicAdd(const_cast<uint32_t *>(&cnt[0]), 1u)] = make_uint2(i, P.root_ref);
-        }
-        grid.sync();
-        for (uint32_t level = 0;; level++) {
-            const uint32_t cin = cnt[level % 3u];
-            if (cin == 0) break;
-            if (tid == 0) cnt[(level + 2u) % 3u] = 0u;    // nobody touches this one during this level
-            const uint2 *in = P.frontier[level & 1u];
-            uint2 *out = P.frontier[(level + 1u) & 1u];
-            uint32_t *cout = const_cast<uint32_t *>(&cnt[(level + 1u) % 3u]);
-            for (uint32_t base = tid - lane; base < cin; base += n_threads) {
-                const uint32_t i = base + lane;
-                uint32_t n_out = 0, out_a = 0, out_b = 0;
-                uint2 item = make_uint2(0u, 0u);
-                if (i < cin) {
-                    item = in[i];
-                    uint32_t *res = P.ovf_result + item.x;
-                    if (!(MODE == kAnyHit && *(volatile uint32_t *)res != 0u)) {
-                        const OvfRay &o = P.ovf[P.ovf_huge[b0 + item.x]];
-                        Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
-                        double r64[6];
-                        TRay r;
-                        tray_setup(r, ray, P.bound, r64);
+    __shared__ uint32_t wstack[kOvfThreads / 32][kWarpStack];
+    uint32_t *stk = wstack[threadIdx.x >> 5];
+    while (true) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(&P.sched->ovf_cursor[ovf_idx], 1u);
+        idx = __shfl_sync(kFullMask, idx, 0);
+        if (idx >= n) break;
+        const OvfRay &o = P.ovf[idx];
+        Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
+        double r64[6];
+        TRay r;
+        tray_setup(r, ray, P.bound, r64);             // every lane holds the same ray
+        uint32_t res = MODE == kAnyHit ? 0u : kNoPos;
+        // An origin this far outside the scene (a shading point 2^32 ray lengths away) makes all slab
+        // quotients of an axis round to the same float: every box passes and no filter can help.
+        bool too_big = !r.filt || (double)r.om > 0x1p20 * fmax(fmax(P.bound[0], P.bound[1]), P.bound[2]);
+        if (COUNT && lane == 0 && !too_big) lc.box++;
+        if (!too_big && exact_root(P, r64, r.t)) {
+            if (P.root_cnt > 0) {
+                if (lane == 0) res = overflow_leaf<MODE, COUNT>(P, r, P.root_ref, P.root_cnt, lc);
+            } else {
+                if (lane == 0) stk[0] = P.root_ref;
+                __syncwarp();
+                uint32_t sp = 1, visits = 0;
+                while (sp > 0) {
+                    const uint32_t take = min(sp, 32u);
+                    sp -= take;
+                    uint32_t n_out = 0, out_a = 0, out_b = 0;
+                    if (lane < take) {
+                        const uint32_t pid = stk[sp + lane];
                         DevPair32 pr;
-                        load_pair32(P.pairs32, item.y, pr);
+                        load_pair32(P.pairs32, pid, pr);
                         if (COUNT) lc.box += 2;
                         bool hit_l, hit_r; float lo, hi;
-                        pair_accept<COUNT>(P, r, item.y, pr, hit_l, hit_r, lo, hi, lc);
-                        uint32_t found = MODE == kAnyHit ? 0u : kNoPos;
+                        pair_accept<COUNT>(P, r, pid, pr, hit_l, hit_r, lo, hi, lc);
                         if (hit_l) {
-                            if (pr.l_cnt > 0) found = overflow_merge<MODE>(found, overflow_leaf<MODE, COUNT>(P, r, pr.l_ref, pr.l_cnt, lc));
+                            if (pr.l_cnt > 0) res = overflow_merge<MODE>(res, overflow_leaf<MODE, COUNT>(P, r, pr.l_ref, pr.l_cnt, lc));
                             else { out_a = pr.l_ref; n_out = 1; }
                         }
                         if (hit_r) {
-                            if (pr.r_cnt > 0) found = overflow_merge<MODE>(found, overflow_leaf<MODE, COUNT>(P, r, pr.r_ref, pr.r_cnt, lc));
+                            if (pr.r_cnt > 0) res = overflow_merge<MODE>(res, overflow_leaf<MODE, COUNT>(P, r, pr.r_ref, pr.r_cnt, lc));
                             else { if (n_out) out_b = pr.r_ref; else out_a = pr.r_ref; n_out++; }
                         }
-                        if (MODE == kAnyHit) { if (found) *(volatile uint32_t *)res = 1u; }
-                        else if (found != kNoPos) atomicMin(res, found);
                     }
-                }
-                // warp-aggregated append of the accepted interior children
-                uint32_t incl = n_out;
+                    __syncwarp();                     // every lane has read its entry before the pushes below
+                    if (MODE == kAnyHit && __any_sync(kFullMask, res != 0u)) break;
+                    uint32_t incl = n_out;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(kFullMask, incl, d); if ((int)lane >= d) incl += v; }
-                const uint32_t total = __shfl_sync(kFullMask, incl, 31);
-                if (total) {
-                    uint32_t obase = 0;
-                    if (lane == 31u) obase = atomicAdd(cout, total);
-                    obase = __shfl_sync(kFullMask, obase, 31) + incl - n_out;
-                    if (obase + n_out <= P.frontier_cap) {        // cannot fail: the batch is sized for the widest level
-                        if (n_out > 0) out[obase] = make_uint2(item.x, out_a);
-                        if (n_out > 1) out[obase + 1u] = make_uint2(item.x, out_b);
-                    }
+                    for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(kFullMask, incl, d); if ((int)lane >= d) incl += v; }
+                    const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+                    visits += take;
+                    if (sp + total > (uint32_t)kWarpStack || visits > P.warp_budget) { too_big = true; break; }
+                    const uint32_t at = sp + incl - n_out;
+                    if (n_out > 0) stk[at] = out_a;
+                    if (n_out > 1) stk[at + 1u] = out_b;
+                    sp += total;
+                    __syncwarp();
                 }
             }
-            grid.sync();
         }
-        for (uint32_t i = tid; i < bn; i += n_threads) overflow_store<MODE>(P, P.ovf[P.ovf_huge[b0 + i]], P.ovf_result[i]);
-        grid.sync();                                      // results and frontier are reused by the next batch
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) res = overflow_merge<MODE>(res, __shfl_xor_sync(kFullMask, res, d));
+        if (lane == 0) {
+            if (too_big) {
+                P.ovf_huge[atomicAdd(&P.sched->huge_count[ovf_idx], 1u)] = idx;
+                if (MODE == kFirstLine) { P.hitb_t[o.target] = kFinf; P.hitb_pos[o.target] = kNoPos; }   // until k_overflow_huge finds a pass
+            } else {
+                overflow_store<MODE>(P, o, res);
+            }
+        }
+    }
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
+}
+
+// Is the leaf that holds a triangle REACHED by the reference's walk?  Every box on the way down must accept the ray:
+// the leaf's own box, its ancestors' boxes, the root's.  `code` = 2 * pair + side of the leaf's box.
+CT_DEV bool chain_accepts(const Params &P, const double *r64, float ray_t, uint32_t code) {
+    while (code != kNoPos) {
+        const uint32_t pid = code >> 1;
+        if (!box_accept(exact_child(P.pairs64, pid, code & 1u, r64), ray_t)) return false;
+        code = P.pair_parent[pid];
+    }
+    return exact_root(P, r64, ray_t);
+}
+
+// Parked rays, pass 2 (what pass 1 gave up on).  Walking a tree in which every box passes level by level costs a
+// grid-wide barrier per level; instead the whole grid tests ALL triangles against the ray at once and, for the few
+// that pass, checks whether the reference's walk would have reached them at all (chain_accepts).  No barrier, and
+// the answers are merged with idempotent atomics (OR into the occlusion mask / MIN of the leaf position).
+template <TraverseMode MODE, bool COUNT>
+__global__ void __launch_bounds__(256) k_overflow_huge(const __grid_constant__ Params P, int ovf_idx) {
+    const uint32_t nh = P.sched->huge_count[ovf_idx];
+    if (nh == 0) return;
+    LocalCount lc;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    for (uint32_t h = 0; h < nh; h++) {
+        const OvfRay &o = P.ovf[P.ovf_huge[h]];
+        Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
+        double r64[6];
+        TRay r;
+        tray_setup(r, ray, P.bound, r64);
+        for (uint32_t pos = tid; pos < P.n_tri; pos += n_threads) {
+            if (MODE == kAnyHit && (*(volatile uint32_t *)&P.occ[o.target] >> o.bit) & 1u) break;      // already occluded
+            if (MODE == kFirstLine && *(volatile uint32_t *)&P.hitb_pos[o.target] < pos) break;        // a lower position already passed
+            if (COUNT) lc.tri++;
+            const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
+            if (!th.hit) continue;
+            if (MODE == kAnyHit && !(th.t > kEps && th.t < kRayTInit)) continue;
+            if (!chain_accepts(P, r64, r.t, P.tri_parent[pos])) continue;
+            if (MODE == kAnyHit) atomicOr(&P.occ[o.target], 1u << o.bit);
+            else { atomicMin(&P.hitb_pos[o.target], pos); P.hitb_t[o.target] = 0.0f; }
+        }
     }
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
@@ -1045,7 +998,6 @@ struct DeviceState {
     unsigned long long *cursor_own = nullptr, *share_cursor = nullptr;
     uint32_t *share_fb = nullptr;
     void *ipc_opened[2] = {nullptr, nullptr};
-    int ovf_grid[4] = {};            // co-resident grid of the k_overflow instantiations [mode][count]
     int n_stages = 0;
     bool timed = false;
     std::vector<void *> allocs;
@@ -1310,20 +1262,26 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     s.can_overflow = (uint64_t)d->n_nodes + d->n_triangles > p.budget;
     if (s.can_overflow) {
         p.ovf_cap = 1u << 16;
-        p.ovf_batch_max = 1u << 16;
-        p.frontier_cap = std::max<uint32_t>(1u << 24, 2u * (n_pairs / 2u + 2u));   // 2 x 128 MB: ~60 rays of a 1M-node tree per batch
         TRY(dev_alloc(s, &p.ovf, p.ovf_cap));
-        TRY(dev_alloc(s, &p.ovf_result, p.ovf_batch_max));
         TRY(dev_alloc(s, &p.ovf_huge, p.ovf_cap));
-        for (int b = 0; b < 2; b++) TRY(dev_alloc(s, &p.frontier[b], p.frontier_cap));
-        const void *fn[4] = {(const void *)k_overflow<kFirstLine, false>, (const void *)k_overflow<kFirstLine, true>,
-                             (const void *)k_overflow<kAnyHit, false>, (const void *)k_overflow<kAnyHit, true>};
-        for (int i = 0; i < 4; i++) {
-            int per_sm = 0;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn[i], kOvfThreads, 0));
-            if (per_sm < 1) { free_device(s); return fail(CT_ERR_CUDA, "k_overflow does not fit on an SM"); }
-            s.ovf_grid[i] = s.n_sm * std::min(per_sm, 4);
+        // who holds whose box: lets k_overflow_huge check a triangle's ancestor chain without walking down
+        std::vector<uint32_t> pair_parent(std::max<uint32_t>(n_pairs, 1), kNoPos), tri_parent(d->n_triangles, kNoPos);
+        for (uint32_t i = 0; i < d->n_nodes; i++) {
+            const ct_bvh_node &n = d->nodes[i];
+            if (n.triangle_count != 0) continue;
+            for (uint32_t side = 0; side < 2; side++) {
+                const uint32_t c = n.left_node + side;
+                const ct_bvh_node &ch = d->nodes[c];
+                const uint32_t code = 2u * pid_of[i] + side;
+                if (ch.triangle_count == 0) pair_parent[pid_of[c]] = code;
+                else for (uint32_t k = 0; k < ch.triangle_count; k++) tri_parent[ch.first_triangle_index + k] = code;
+            }
         }
+        uint32_t *dpp, *dtp;
+        TRY(dev_alloc(s, &dpp, pair_parent.size())); TRY(dev_alloc(s, &dtp, tri_parent.size()));
+        CU(cudaMemcpy(dpp, pair_parent.data(), pair_parent.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(dtp, tri_parent.data(), tri_parent.size() * 4, cudaMemcpyHostToDevice));
+        p.pair_parent = dpp; p.tri_parent = dtp;
     }
     if (levels > 1) {
         TRY(dev_alloc(s, &p.hitb_t, p.cap)); TRY(dev_alloc(s, &p.hitb_pos, p.cap));
@@ -1401,10 +1359,15 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     };
     auto overflow = [&](int mode_anyhit, int ovf_idx, int depth) -> int {   // parked rays of the launch just made
         if (!s.can_overflow) return CT_OK;
-        void *args[] = {(void *)&pk, (void *)&ovf_idx};
-        const void *fn = mode_anyhit ? (count ? (const void *)k_overflow<kAnyHit, true> : (const void *)k_overflow<kAnyHit, false>)
-                                     : (count ? (const void *)k_overflow<kFirstLine, true> : (const void *)k_overflow<kFirstLine, false>);
-        CU(cudaLaunchCooperativeKernel(fn, dim3(s.ovf_grid[mode_anyhit * 2 + (count ? 1 : 0)]), dim3(kOvfThreads), args, 0, st));
+        const int g1 = s.n_sm * 2, g2 = s.n_sm * 4;
+        if (mode_anyhit) {
+            if (count) { k_overflow<kAnyHit, true><<<g1, kOvfThreads, 0, st>>>(pk, ovf_idx); k_overflow_huge<kAnyHit, true><<<g2, 256, 0, st>>>(pk, ovf_idx); }
+            else { k_overflow<kAnyHit, false><<<g1, kOvfThreads, 0, st>>>(pk, ovf_idx); k_overflow_huge<kAnyHit, false><<<g2, 256, 0, st>>>(pk, ovf_idx); }
+        } else {
+            if (count) { k_overflow<kFirstLine, true><<<g1, kOvfThreads, 0, st>>>(pk, ovf_idx); k_overflow_huge<kFirstLine, true><<<g2, 256, 0, st>>>(pk, ovf_idx); }
+            else { k_overflow<kFirstLine, false><<<g1, kOvfThreads, 0, st>>>(pk, ovf_idx); k_overflow_huge<kFirstLine, false><<<g2, 256, 0, st>>>(pk, ovf_idx); }
+        }
+        s.launches++;                                       // two kernels, one stage
         return mark(mode_anyhit ? "overflow_shadow" : "overflow_bounce", depth);
     };
     if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(pk);
