@@ -245,6 +245,9 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    # stdout carries exactly one line, the JSON (NCCL / torchrun banners go to stderr with everything else)
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -462,7 +465,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(workload, fs, counts)
     else:
         shared.close(); gpu.shutdown()
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
     if N > 1:
         dist.barrier(); dist.destroy_process_group()
     return 0

@@ -52,7 +52,9 @@ struct Ray {        // ray_t (scenefile.h:104-108)
 
 // What the traversal loop keeps in registers: ray.t and the per-ray constants of the two certified fp32 filters
 // (box_filter, tri_filter_miss).  The fp64 origin/direction the reference's own arithmetic needs stay in local
-// memory (r64[0..2] = origin, r64[3..5] = direction) and are only touched when a filter cannot decide.
+// memory (r64[0..2] = origin, r64[3..5] = direction, r64[6..8] = correctly rounded 1/direction, r64[9] != 0 when
+// some 1/d leaves the normal range) and are only touched when a filter cannot decide.
+constexpr int kRay64 = 10;
 struct TRay {
     float t;
     float rdf[3];   // float(1/d)
@@ -78,7 +80,7 @@ struct TRay {
 //     fma_rd(bf, rdf, cl) <= q_ref <= fma_ru(bf, rdf, cu)          for every finite node bound.
 CT_DEV void tray_setup(TRay &r, const Ray &ray, const double bound[3], double *r64) {
     const double o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
-    bool ok = true;
+    bool ok = true, odd = false;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         double rd = __ddiv_rn(1.0, d[k]);
@@ -94,8 +96,14 @@ CT_DEV void tray_setup(TRay &r, const Ray &ray, const double bound[3], double *r
         r.cu[k] = __double2float_ru(__dadd_ru(c, e));
         r.of[k] = __double2float_rn(o[k]);
         r.df[k] = __double2float_rn(d[k]);
-        r64[k] = o[k]; r64[3 + k] = d[k];
+        r64[k] = o[k]; r64[3 + k] = d[k]; r64[6 + k] = rd;
+        // zero/inf/NaN directions are fine for the reciprocal form (IEEE gives the same inf/NaN quotients both ways);
+        // only a finite non-zero d whose reciprocal leaves the normal range needs true divisions throughout
+        const uint32_t hi = (uint32_t)__double2hiint(d[k]), ex = (hi >> 20) & 0x7ffu;
+        const bool zero = ((hi & 0x7fffffffu) | (uint32_t)__double2loint(d[k])) == 0u;
+        odd = odd || (!zero && ex != 0x7ffu && (ex < 24u || ex > 2022u));
     }
+    r64[9] = odd ? 1.0 : 0.0;
     r.filt = ok;
     double dm = fmax(fmax(fabs(d[0]), fabs(d[1])), fabs(d[2])), om = fmax(fmax(fabs(o[0]), fabs(o[1])), fabs(o[2]));
     r.tfilt = (dm >= 0x1p-20) && (dm <= 0x1p40) && (om <= 0x1p40);          // NaNs fail
@@ -125,6 +133,45 @@ __device__ __noinline__ BoxTimes box_times_exact(double ox, double oy, double oz
     return {tmin, tmax};
 }
 
+// mymath.h:11-17 on doubles (same NaN behaviour as the float macros).
+CT_DEV double macro_min_d(double a, double b) { return (a < b) ? a : b; }
+CT_DEV double macro_max_d(double a, double b) { return (a > b) ? a : b; }
+
+// True when float(x) may differ from float(y) for some y within a few fp64 ulps of x: x sits within +-16 units of
+// a float rounding boundary (the 29 dropped mantissa bits ~ 0x10000000), or x is non-zero with |x| < 2^-125 (float
+// subnormal range, where the boundaries are elsewhere and the fp64 product may itself have lost bits).
+CT_DEV bool float_rounding_unsafe(double x) {
+    uint32_t lo = (uint32_t)__double2loint(x);
+    uint32_t hi = (uint32_t)__double2hiint(x) & 0x7fffffffu;
+    bool near_mid = ((lo & 0x1fffffffu) - 0x0ffffff0u) <= 0x20u;
+    bool tiny = (hi < 0x38200000u) && ((hi | lo) != 0u);
+    return near_mid | tiny;
+}
+
+// The two floats IntersectAABB compares, bit-exact (up to the sign of a zero, which no comparison sees), for ANY ray
+// (r64 as laid out by tray_setup), usually without a division:
+//   * rounding to float is monotonic and NaN-preserving, so taking the reference's macro min/max on the UNROUNDED
+//     fp64 quotients and rounding only the two survivors gives the same float values (whenever the double
+//     comparison picks a different operand than the float comparison would, both round to the same float);
+//   * the quotient (b - o)/d is replaced by (b - o) * fl(1/d): each survivor is then within a few fp64 ulps of the
+//     reference's double, so its float rounding can differ only if it lies that close to a float rounding boundary
+//     (~2^-24 of tests) -- those, and rays whose 1/d leaves the normal range, redo the six true divisions.
+CT_DEV BoxTimes box_times(const double *r64, const double bmin[3], const double bmax[3]) {
+    double x1 = __dmul_rn(__dsub_rn(bmin[0], r64[0]), r64[6]), x2 = __dmul_rn(__dsub_rn(bmax[0], r64[0]), r64[6]);
+    double y1 = __dmul_rn(__dsub_rn(bmin[1], r64[1]), r64[7]), y2 = __dmul_rn(__dsub_rn(bmax[1], r64[1]), r64[7]);
+    double z1 = __dmul_rn(__dsub_rn(bmin[2], r64[2]), r64[8]), z2 = __dmul_rn(__dsub_rn(bmax[2], r64[2]), r64[8]);
+    double tmin = macro_min_d(x1, x2);
+    double tmax = macro_max_d(x1, x2);
+    tmin = macro_max_d(tmin, macro_min_d(y1, y2));
+    tmax = macro_min_d(tmax, macro_max_d(y1, y2));
+    tmin = macro_max_d(tmin, macro_min_d(z1, z2));
+    tmax = macro_min_d(tmax, macro_max_d(z1, z2));
+    if (float_rounding_unsafe(tmin) | float_rounding_unsafe(tmax) | (r64[9] != 0.0))
+        return box_times_exact(r64[0], r64[1], r64[2], r64[3], r64[4], r64[5], bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]);
+    return {__double2float_rn(tmin), __double2float_rn(tmax)};
+}
+
+// The literal form, for callers that hold a plain Ray (KAT kernels).
 CT_DEV BoxTimes box_times(const Ray &r, const double bmin[3], const double bmax[3]) {
     return box_times_exact(r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2]);
 }

@@ -174,12 +174,12 @@ CT_DEV void load_pair32(const DevPair32 *pairs, uint32_t pid, DevPair32 &p) {
 __device__ __noinline__ BoxTimes exact_child(const DevPair64 *pairs, uint32_t pid, uint32_t side, const double *r64) {
     const double2 *q = reinterpret_cast<const double2 *>(pairs + pid) + 3u * side;
     double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    return box_times_exact(r64[0], r64[1], r64[2], r64[3], r64[4], r64[5], a.x, a.y, b.x, b.y, c.x, c.y);
+    const double bmin[3] = {a.x, a.y, b.x}, bmax[3] = {b.y, c.x, c.y};
+    return box_times(r64, bmin, bmax);
 }
 
 CT_DEV bool exact_root(const Params &P, const double *r64, float ray_t) {
-    return box_accept(box_times_exact(r64[0], r64[1], r64[2], r64[3], r64[4], r64[5], P.root_min[0], P.root_min[1], P.root_min[2],
-                                      P.root_max[0], P.root_max[1], P.root_max[2]), ray_t);
+    return box_accept(box_times(r64, P.root_min, P.root_max), ray_t);
 }
 
 struct TriHit { bool hit; float t; };
@@ -370,7 +370,7 @@ CT_DEV int traverse_any_hit(const Params &P, const TRay &r, bool active, const u
                 } else {
                     DevPair32 pr;
                     load_pair32(P.pairs32, cur_ref, pr);
-                    if (COUNT) lc.box += 2;
+                        if (COUNT) lc.box += 2;
                     spent += 2u;
                     bool hit_l, hit_r; float r_lo, r_hi;
                     pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
             const uint32_t q = (mine << P.chunk_shift) + sub + lane;   // this path's depth-0 number on this device
             int x, y, fbi;
             const bool active = slot < P.n_slots && slot_pixel(P, slot, x, y, fbi);
-            double r64[6];
+            double r64[kRay64];
             TRay r;
             if (active) {
                 Ray ray = primary_ray(P, x, y);
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
         uint32_t q = (uint32_t)(base - (unsigned long long)j * n_pad) + (threadIdx.x & 31u);
         uint32_t slot, pos = kNoPos; int fbi; Ray r; float tc = 0.0f;
         bool active = q < n && load_path(P, depth, q, slot, fbi, r, tc, pos) && pos != kNoPos;
-        double r64[6];
+        double r64[kRay64];
         TRay tr;
         uint32_t word = 0, bit = 0;
         if (active) {
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
         if (base >= n) break;
         uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
         bool active = q < n;
-        double r64[6];
+        double r64[kRay64];
         TRay r;
         if (active) {
             const double2 *rb = reinterpret_cast<const double2 *>(P.ray_buf[cur] + 6ull * q);
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
         if (idx >= n) break;
         const OvfRay &o = P.ovf[idx];
         Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
-        double r64[6];
+        double r64[kRay64];
         TRay r;
         tray_setup(r, ray, P.bound, r64);             // every lane holds the same ray
         uint32_t res = MODE == kAnyHit ? 0u : kNoPos;
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(256) k_overflow_huge(const __grid_constant__ P
     for (uint32_t h = 0; h < nh; h++) {
         const OvfRay &o = P.ovf[P.ovf_huge[h]];
         Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
-        double r64[6];
+        double r64[kRay64];
         TRay r;
         tray_setup(r, ray, P.bound, r64);
         for (uint32_t pos = tid; pos < P.n_tri; pos += n_threads) {
@@ -899,7 +899,7 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
     const bool active = i < n;                           // the traversals are warp-synchronous: every lane calls both
     Ray r;
     r.t = 1.0f;
-    double r64[6];
+    double r64[kRay64];
     TRay tr;
     if (active) {
         r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = t0[i];
@@ -937,7 +937,7 @@ __global__ void k_debug_primitives(uint32_t n, const double *org, const double *
             ordered = ordered && (mn[k] <= mx[k]) && isfinite(mn[k]) && isfinite(mx[k]);
         }
         if (!ordered) bnd[0] = bnd[1] = bnd[2] = INFINITY;
-        double r64[6];
+        double r64[kRay64];
         TRay tr;
         tray_setup(tr, r, bnd, r64);
         uint32_t f = 0;
@@ -950,7 +950,14 @@ __global__ void k_debug_primitives(uint32_t n, const double *org, const double *
             bool inside = b.near_lo <= e.tmin && e.tmin <= b.near_hi && b.far_lo <= e.tmax && e.tmax <= b.far_hi;
             if (!inside) f |= 8u;                                  // bracket does not contain the reference's floats: bug
         }
-        filter_out[i] = (exact ? 1u : 0u) | ((f & 3u) << 1) | (tr.filt ? 8u : 0u) | ((f & 8u) ? 16u : 0u);
+        // the division-free evaluation used for undecided tests must give the literal arithmetic's verdict and floats
+        {
+            const BoxTimes lit = box_times(r, mn, mx), rec = box_times(r64, mn, mx);
+            const bool same = (lit.tmin == rec.tmin || (lit.tmin != lit.tmin && rec.tmin != rec.tmin)) &&
+                              (lit.tmax == rec.tmax || (lit.tmax != lit.tmax && rec.tmax != rec.tmax));
+            if (!same || box_accept(rec, r.t) != exact) f |= 16u;
+        }
+        filter_out[i] = (exact ? 1u : 0u) | ((f & 3u) << 1) | (tr.filt ? 8u : 0u) | ((f & 8u) ? 16u : 0u) | ((f & 16u) ? 32u : 0u);
     }
     V3 p1 = ld3(tri + 9ull * i), p2 = ld3(tri + 9ull * i + 3), p3 = ld3(tri + 9ull * i + 6);
     float t;
@@ -1261,7 +1268,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     // parked rays: only needed when a DFS can run past the budget at all
     s.can_overflow = (uint64_t)d->n_nodes + d->n_triangles > p.budget;
     if (s.can_overflow) {
-        p.ovf_cap = 1u << 16;
+        p.ovf_cap = 1u << 20;          // 64 MB of parked rays; a full buffer means finishing rays in place, which must stay hypothetical
         TRY(dev_alloc(s, &p.ovf, p.ovf_cap));
         TRY(dev_alloc(s, &p.ovf_huge, p.ovf_cap));
         // who holds whose box: lets k_overflow_huge check a triangle's ancestor chain without walking down

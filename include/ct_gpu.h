@@ -231,7 +231,8 @@ int ct_gpu_debug_primitives(int device, uint32_t n, const double *origins, const
  * n independent (ray, box) cases.  The filter's per-axis magnitude bound is max(|bmin|,|bmax|) * bound_scale
  * (bound_scale >= 1 imitates a small box inside a large scene).  verdict[i]: bit 0 = the reference's verdict,
  * bits 1-2 = the filter's (0 undecided, 1 accept, 2 reject), bit 3 = filter usable for this ray, bit 4 = the
- * filter's bracket failed to contain the reference's float tmin/tmax (must never be set). */
+ * filter's bracket failed to contain the reference's float tmin/tmax, bit 5 = the division-free fp64 evaluation
+ * used for undecided tests differs from the literal arithmetic (neither may ever be set). */
 int ct_gpu_debug_filter(int device, uint32_t n, const double *origins, const double *directions, const float *ray_t,
                         const double *bmin, const double *bmax, double bound_scale, uint32_t *verdict);
 

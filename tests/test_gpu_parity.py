@@ -101,8 +101,9 @@ def test_slab_filter_is_sound_and_mostly_decides(gpu, bound_scale):
     rng = np.random.default_rng(11)
     o, d, rt, bmin, bmax = _filter_cases(rng, 1 << 20)
     v = gpu.debug_filter(o, d, rt, bmin, bmax, bound_scale)
-    exact, filt, usable, escaped = v & 1, (v >> 1) & 3, (v >> 3) & 1, (v >> 4) & 1
+    exact, filt, usable, escaped, recip_bad = v & 1, (v >> 1) & 3, (v >> 3) & 1, (v >> 4) & 1, (v >> 5) & 1
     assert not escaped.any(), f"{int(escaped.sum())} brackets do not contain the reference's tmin/tmax"
+    assert not recip_bad.any(), f"{int(recip_bad.sum())} division-free slab evaluations differ from the literal arithmetic"
     assert not ((filt == 1) & (exact == 0)).any() and not ((filt == 2) & (exact == 1)).any()
     assert (filt[usable == 0] == 0).all()
     zero_dir = (d == 0).any(1)
