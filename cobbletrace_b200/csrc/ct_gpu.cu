@@ -160,6 +160,18 @@ CT_DEV void load_tri(const DevTri *tris, uint32_t pos, V3 &p1, V3 &e1, V3 &e2) {
     e2 = {d.x, d.y, e};
 }
 
+// Optional (CT_PREFETCH=1): request the records of a pair's children as soon as the pair has arrived, so that their
+// latency overlaps this visit's slab tests.  Measured neutral-to-negative on full frames (the walks are issue
+// bound there), kept as a build-time experiment.
+CT_DEV void prefetch_children(const Params &P, const DevPair32 &pr) {
+#if defined(CT_PREFETCH) && CT_PREFETCH
+    const char *l = pr.l_cnt ? reinterpret_cast<const char *>(P.tris32 + pr.l_ref) : reinterpret_cast<const char *>(P.pairs32 + pr.l_ref);
+    const char *r = pr.r_cnt ? reinterpret_cast<const char *>(P.tris32 + pr.r_ref) : reinterpret_cast<const char *>(P.pairs32 + pr.r_ref);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(l)); asm volatile("prefetch.global.L2 [%0];" ::"l"(l + 32));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(r)); asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 32));
+#endif
+}
+
 CT_DEV void load_pair32(const DevPair32 *pairs, uint32_t pid, DevPair32 &p) {
     const float4 *q = reinterpret_cast<const float4 *>(pairs + pid);
     float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
@@ -297,6 +309,7 @@ CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget
             } else {
                 DevPair32 pr;
                 load_pair32(P.pairs32, cur_ref, pr);
+                prefetch_children(P, pr);
                 if (COUNT) lc.box += 2;
                 spent += 2u + pr.l_cnt + pr.r_cnt;
                 if (MODE != kClosest && spent > budget) {

@@ -10,6 +10,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 echo "launch list rc=$?"
 FRAME="python tools/prof_frame.py --frames 2"
 $FRAME > gpurun_out/${TAG}_frame_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'k_shadow|k_primary|k_bounce' -s 7 -c 7 -f -o gpurun_out/${TAG}_trav $FRAME > gpurun_out/${TAG}_ncu_trav.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_shadow|k_primary|k_bounce|k_overflow" -s 13 -c 12 -f -o gpurun_out/${TAG}_trav $FRAME > gpurun_out/${TAG}_ncu_trav.log 2>&1
 echo "full capture rc=$?"
 tail -3 gpurun_out/${TAG}_ncu_trav.log

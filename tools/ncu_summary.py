@@ -75,8 +75,15 @@ def source(rep, top=40):
             blocks.append(cur)
         elif cur is not None:
             cur["rows"].append(r)
+    seen = set()
     for b in blocks:
+        if len(b["rows"]) < 2:
+            continue
         hdr, data = b["rows"][0], b["rows"][1:]
+        key = (b["name"], len(data), tuple(r[0] for r in data[:3]))
+        if key in seen:                       # ncu lists each result twice when --page source is exported as csv
+            continue
+        seen.add(key)
         ix = {h: i for i, h in enumerate(hdr)}
         stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
         tot = sum(int(r[ix["# Samples"]]) for r in data) or 1
