@@ -594,9 +594,11 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
 
-// TraceRay body after the closest hit (raythread.cpp:359-373) for the paths alive at `depth`; the shadow
-// verdicts were computed by k_shadow (+ k_overflow).
-__global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__ Params P, int depth, int work_idx) {
+// TraceRay's recursion step (raythread.cpp:369-373) for the paths alive at `depth`: does the path end here, or does
+// it continue with the reflection ray {position, ReflectRay(-dir, normal), t = 0}?  Needs only the hit records --
+// not the shadow verdicts -- so it runs ahead of k_shadow / k_shade of the same depth (separate streams) and feeds
+// k_bounce of the next one.
+__global__ void __launch_bounds__(kBlockThreads) k_emit(const __grid_constant__ Params P, int depth, int work_idx) {
     uint32_t n_refl = 0;
     const uint32_t n = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
     const int nxt = (depth & 1) ^ 1;
@@ -610,55 +612,21 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
         bool emit = false;
         V3 position = {0, 0, 0}, rdir = {0, 0, 0};
         if (active) {
-            uint32_t *sc = P.stack_color + (size_t)depth * P.cap + slot;
-            if (pos == kNoPos) {                                           // miss (depth 0 only): raythread.cpp:385
-                if (depth == 0) P.fb_out[fbi] = P.background;
-                *sc = P.background;
+            float reflection = 0.0f;
+            if (pos != kNoPos) reflection = P.materials[P.tris[pos].orig].reflection;
+            const int remaining = P.max_depth - depth;                      // recursionDepth of this TraceRay call
+            if (pos == kNoPos || remaining <= 0 || !(reflection > 0.0f)) {  // miss :385 / :369 (reflection <= 0, NaN-safe)
                 P.term_level[slot] = (uint8_t)depth;
             } else {
                 V3 p1, e1, e2;
                 load_tri(P.tris, pos, p1, e1, e2);
-                const ct_material mat = P.materials[P.tris[pos].orig];
                 position = vadd(r.o, vscale((double)tc, r.d));              // :360
                 V3 nn = vcross(e1, e2);                                     // NormalOfSceneObject :337-339
                 float dd = vdot(nn, r.d);
                 V3 normal = (dd < 0.0f) ? nn : vneg(nn);                    // :341-345
-                V3 view = vneg(r.d);
-                // ---- ComputeLighting :275-327, lights in file order, fp32 accumulator
-                float intensity = 0.0f;
-                const uint32_t *occ = P.occ + (size_t)q * P.occ_words;
-                uint32_t occ_word = 0;
-                for (uint32_t i = 0; i < P.n_lights; i++) {
-                    const DevLight &L = P.lights[i];
-                    float li = L.intensity;
-                    if ((i & 31u) == 0) occ_word = occ[i >> 5];
-                    if (L.type == CT_LIGHT_AMBIENT) { intensity = __fadd_rn(intensity, li); continue; }
-                    if ((occ_word >> (i & 31u)) & 1u) continue;              // :306 shadowed
-                    V3 lray = (L.type == CT_LIGHT_POINT) ? vsub(ld3(L.pos), position) : ld3(L.dir);
-                    float ndl = vdot(normal, lray);                          // :310
-                    if (ndl > 0.0f)
-                        intensity = __fadd_rn(intensity, __fdiv_rn(__fmul_rn(li, ndl), __fmul_rn(vmag(normal), vmag(lray))));
-                    if (mat.specular != -1) {                                // :316
-                        V3 refl = reflect_ray(lray, normal);
-                        float rdv = vdot(refl, view);
-                        if (rdv > 0.0f) {                                    // :319-321 double pow, += rounds to float
-                            float qv = __fdiv_rn(rdv, __fmul_rn(vmag(refl), vmag(view)));
-                            double term = __dmul_rn((double)li, pow((double)qv, (double)mat.specular));
-                            intensity = __double2float_rn(__dadd_rn((double)intensity, term));
-                        }
-                    }
-                }
-                uint32_t local = shade_color(mat.color, intensity);
-                *sc = local;
-                int remaining = P.max_depth - depth;                        // recursionDepth of this TraceRay call
-                if (remaining <= 0 || !(mat.reflection > 0.0f)) {           // :369  (reflection <= 0, NaN-safe)
-                    P.term_level[slot] = (uint8_t)depth;
-                    if (depth == 0) P.fb_out[fbi] = local;
-                } else {
-                    P.stack_refl[(size_t)depth * P.cap + slot] = mat.reflection;
-                    rdir = reflect_ray(view, normal);                        // :372
-                    emit = true;
-                }
+                P.stack_refl[(size_t)depth * P.cap + slot] = reflection;
+                rdir = reflect_ray(vneg(r.d), normal);                      // :372
+                emit = true;
             }
         }
         // warp-aggregated append of the reflection rays to the next queue
@@ -679,6 +647,62 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
         }
     }
     warp_add(&P.tot->rays_reflection, n_refl);
+}
+
+// TraceRay's local colour (raythread.cpp:359-366) for the paths alive at `depth`; the shadow verdicts were computed
+// by k_shadow (+ k_overflow).
+__global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__ Params P, int depth, int work_idx) {
+    const uint32_t n = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
+    while (true) {
+        unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= n) break;
+        uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
+        uint32_t slot = q, pos = kNoPos; int fbi = 0;
+        Ray r; float tc = 0.0f;
+        if (!(q < n && load_path(P, depth, q, slot, fbi, r, tc, pos))) continue;
+        uint32_t *sc = P.stack_color + (size_t)depth * P.cap + slot;
+        if (pos == kNoPos) {                                           // miss (depth 0 only): raythread.cpp:385
+            if (depth == 0) P.fb_out[fbi] = P.background;
+            *sc = P.background;
+            continue;
+        }
+        V3 p1, e1, e2;
+        load_tri(P.tris, pos, p1, e1, e2);
+        const ct_material mat = P.materials[P.tris[pos].orig];
+        V3 position = vadd(r.o, vscale((double)tc, r.d));              // :360
+        V3 nn = vcross(e1, e2);                                         // NormalOfSceneObject :337-339
+        float dd = vdot(nn, r.d);
+        V3 normal = (dd < 0.0f) ? nn : vneg(nn);                        // :341-345
+        V3 view = vneg(r.d);
+        // ---- ComputeLighting :275-327, lights in file order, fp32 accumulator
+        float intensity = 0.0f;
+        const uint32_t *occ = P.occ + (size_t)q * P.occ_words;
+        uint32_t occ_word = 0;
+        for (uint32_t i = 0; i < P.n_lights; i++) {
+            const DevLight &L = P.lights[i];
+            float li = L.intensity;
+            if ((i & 31u) == 0) occ_word = occ[i >> 5];
+            if (L.type == CT_LIGHT_AMBIENT) { intensity = __fadd_rn(intensity, li); continue; }
+            if ((occ_word >> (i & 31u)) & 1u) continue;                  // :306 shadowed
+            V3 lray = (L.type == CT_LIGHT_POINT) ? vsub(ld3(L.pos), position) : ld3(L.dir);
+            float ndl = vdot(normal, lray);                              // :310
+            if (ndl > 0.0f)
+                intensity = __fadd_rn(intensity, __fdiv_rn(__fmul_rn(li, ndl), __fmul_rn(vmag(normal), vmag(lray))));
+            if (mat.specular != -1) {                                    // :316
+                V3 refl = reflect_ray(lray, normal);
+                float rdv = vdot(refl, view);
+                if (rdv > 0.0f) {                                        // :319-321 double pow, += rounds to float
+                    float qv = __fdiv_rn(rdv, __fmul_rn(vmag(refl), vmag(view)));
+                    double term = __dmul_rn((double)li, pow((double)qv, (double)mat.specular));
+                    intensity = __double2float_rn(__dadd_rn((double)intensity, term));
+                }
+            }
+        }
+        uint32_t local = shade_color(mat.color, intensity);
+        *sc = local;
+        // a depth-0 path that ends here (:369) is the pixel; longer chains are blended by k_resolve
+        if (depth == 0 && (P.max_depth <= 0 || !(mat.reflection > 0.0f))) P.fb_out[fbi] = local;
+    }
 }
 
 // Closest "hit" of the reflection rays {position, reflected, t = 0} (raythread.cpp:373).
@@ -1014,6 +1038,15 @@ struct DeviceState {
     const char *stage_name[kMaxLaunches] = {};
     int stage_depth[kMaxLaunches] = {};
     bool can_overflow = false;       // some traversal could exceed the visit budget: k_overflow launches are needed
+    // per-depth path state (render_impl hands each launch a Params view of its depth, so that the shadow / shade
+    // chain of one depth can run on its own stream next to the bounce chain of the next)
+    float *hitb_t_all = nullptr; uint32_t *hitb_pos_all = nullptr;      // [depth][cap]
+    double *rays_all = nullptr; uint32_t *path_slot_all = nullptr;      // [depth][cap * 6], [depth][cap]
+    uint32_t *occ_all = nullptr;                                        // [depth][cap * occ_words]
+    OvfRay *ovf_all = nullptr; uint32_t *ovf_huge_all = nullptr;        // [2 * depth + kind][ovf_cap]
+    int levels = 1;
+    cudaStream_t aux[4] = {};
+    cudaEvent_t ev_hit[16] = {}, ev_done[16] = {};
     // multi-GPU frame sharing (ct_gpu_share_*): the cursor and framebuffer a shared render uses (own or the root's)
     unsigned long long *cursor_own = nullptr, *share_cursor = nullptr;
     uint32_t *share_fb = nullptr;
@@ -1051,6 +1084,9 @@ void free_device(DeviceState &s) {
     if (s.ev1) cudaEventDestroy(s.ev1);
     for (cudaEvent_t e : s.tile_done) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s.stage_ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s.ev_hit) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s.ev_done) if (e) cudaEventDestroy(e);
+    for (cudaStream_t a : s.aux) if (a) cudaStreamDestroy(a);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
     s = DeviceState{};
 }
@@ -1145,6 +1181,9 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     CU(cudaEventCreate(&s.ev0));
     CU(cudaEventCreate(&s.ev1));
     for (cudaEvent_t &e : s.tile_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t &e : s.ev_hit) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t &e : s.ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaStream_t &a : s.aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
     if (d->flags & CT_FLAG_STAGE_TIMING) for (cudaEvent_t &e : s.stage_ev) CU(cudaEventCreate(&e));
     s.p.budget = g_budget_option > 0 ? (uint32_t)std::min<long long>(g_budget_option, 1ll << 30) : kDefaultBudget;
     s.p.warp_budget = g_warp_budget_option > 0 ? (uint32_t)std::min<long long>(g_warp_budget_option, 1ll << 30) : kWarpBudget;
@@ -1277,13 +1316,16 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     TRY(dev_alloc(s, &p.hit0_t, p.cap)); TRY(dev_alloc(s, &p.hit0_pos, p.cap));
     TRY(dev_alloc(s, &p.stack_color, (size_t)p.cap * levels));
     TRY(dev_alloc(s, &p.term_level, p.cap, true));
-    TRY(dev_alloc(s, &p.occ, (size_t)p.cap * p.occ_words, true));
+    s.levels = levels;
+    TRY(dev_alloc(s, &s.occ_all, (size_t)p.cap * p.occ_words * levels, true));
+    p.occ = s.occ_all;
     // parked rays: only needed when a DFS can run past the budget at all
     s.can_overflow = (uint64_t)d->n_nodes + d->n_triangles > p.budget;
     if (s.can_overflow) {
-        p.ovf_cap = 1u << 20;          // 64 MB of parked rays; a full buffer means finishing rays in place, which must stay hypothetical
-        TRY(dev_alloc(s, &p.ovf, p.ovf_cap));
-        TRY(dev_alloc(s, &p.ovf_huge, p.ovf_cap));
+        p.ovf_cap = 1u << 18;          // parked rays per launch (16 MB); a full buffer means finishing rays in place, which must stay hypothetical
+        TRY(dev_alloc(s, &s.ovf_all, (size_t)p.ovf_cap * 2 * levels));
+        TRY(dev_alloc(s, &s.ovf_huge_all, (size_t)p.ovf_cap * 2 * levels));
+        p.ovf = s.ovf_all; p.ovf_huge = s.ovf_huge_all;
         // who holds whose box: lets k_overflow_huge check a triangle's ancestor chain without walking down
         std::vector<uint32_t> pair_parent(std::max<uint32_t>(n_pairs, 1), kNoPos), tri_parent(d->n_triangles, kNoPos);
         for (uint32_t i = 0; i < d->n_nodes; i++) {
@@ -1304,9 +1346,9 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
         p.pair_parent = dpp; p.tri_parent = dtp;
     }
     if (levels > 1) {
-        TRY(dev_alloc(s, &p.hitb_t, p.cap)); TRY(dev_alloc(s, &p.hitb_pos, p.cap));
+        TRY(dev_alloc(s, &s.hitb_t_all, (size_t)p.cap * levels)); TRY(dev_alloc(s, &s.hitb_pos_all, (size_t)p.cap * levels));
         TRY(dev_alloc(s, &p.stack_refl, (size_t)p.cap * levels));
-        for (int b = 0; b < 2; b++) { TRY(dev_alloc(s, &p.ray_buf[b], (size_t)p.cap * 6)); TRY(dev_alloc(s, &p.path_slot[b], p.cap)); }
+        TRY(dev_alloc(s, &s.rays_all, (size_t)p.cap * 6 * (levels + 1))); TRY(dev_alloc(s, &s.path_slot_all, (size_t)p.cap * (levels + 1)));
     }
     TRY(dev_alloc(s, &p.fb, (size_t)d->width * d->height, true));       // calloc'd like cobbletrace.cpp:57
     TRY(dev_alloc(s, &p.own_chunks, (p.cap >> kChunkLocalShift) + 1u));
@@ -1377,38 +1419,76 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
         CU(cudaEventRecord(s.stage_ev[s.n_stages], st));
         return CT_OK;
     };
-    auto overflow = [&](int mode_anyhit, int ovf_idx, int depth) -> int {   // parked rays of the launch just made
+    // Params as the launches of depth d see them: their own hit records, occlusion masks, ray queue in / out
+    auto view = [&](int d) {
+        Params v = pk;
+        const size_t cap = pk.cap;
+        if (s.hitb_t_all) { v.hitb_t = s.hitb_t_all + cap * d; v.hitb_pos = s.hitb_pos_all + cap * d; }
+        if (s.rays_all) {
+            v.ray_buf[d & 1] = s.rays_all + cap * 6 * d;            v.path_slot[d & 1] = s.path_slot_all + cap * d;
+            v.ray_buf[(d & 1) ^ 1] = s.rays_all + cap * 6 * (d + 1); v.path_slot[(d & 1) ^ 1] = s.path_slot_all + cap * (d + 1);
+        }
+        v.occ = s.occ_all + cap * pk.occ_words * d;
+        return v;
+    };
+    auto overflow = [&](const Params &v0, cudaStream_t q, int mode_anyhit, int ovf_idx, int depth) -> int {   // parked rays of the launch just made
         if (!s.can_overflow) return CT_OK;
+        Params v = v0;
+        v.ovf = s.ovf_all + (size_t)pk.ovf_cap * ovf_idx; v.ovf_huge = s.ovf_huge_all + (size_t)pk.ovf_cap * ovf_idx;
         const int g1 = s.n_sm * 2, g2 = s.n_sm * 4;
         if (mode_anyhit) {
-            if (count) { k_overflow<kAnyHit, true><<<g1, kOvfThreads, 0, st>>>(pk, ovf_idx); k_overflow_huge<kAnyHit, true><<<g2, 256, 0, st>>>(pk, ovf_idx); }
-            else { k_overflow<kAnyHit, false><<<g1, kOvfThreads, 0, st>>>(pk, ovf_idx); k_overflow_huge<kAnyHit, false><<<g2, 256, 0, st>>>(pk, ovf_idx); }
+            if (count) { k_overflow<kAnyHit, true><<<g1, kOvfThreads, 0, q>>>(v, ovf_idx); k_overflow_huge<kAnyHit, true><<<g2, 256, 0, q>>>(v, ovf_idx); }
+            else { k_overflow<kAnyHit, false><<<g1, kOvfThreads, 0, q>>>(v, ovf_idx); k_overflow_huge<kAnyHit, false><<<g2, 256, 0, q>>>(v, ovf_idx); }
         } else {
-            if (count) { k_overflow<kFirstLine, true><<<g1, kOvfThreads, 0, st>>>(pk, ovf_idx); k_overflow_huge<kFirstLine, true><<<g2, 256, 0, st>>>(pk, ovf_idx); }
-            else { k_overflow<kFirstLine, false><<<g1, kOvfThreads, 0, st>>>(pk, ovf_idx); k_overflow_huge<kFirstLine, false><<<g2, 256, 0, st>>>(pk, ovf_idx); }
+            if (count) { k_overflow<kFirstLine, true><<<g1, kOvfThreads, 0, q>>>(v, ovf_idx); k_overflow_huge<kFirstLine, true><<<g2, 256, 0, q>>>(v, ovf_idx); }
+            else { k_overflow<kFirstLine, false><<<g1, kOvfThreads, 0, q>>>(v, ovf_idx); k_overflow_huge<kFirstLine, false><<<g2, 256, 0, q>>>(v, ovf_idx); }
         }
         s.launches++;                                       // two kernels, one stage
         return mark(mode_anyhit ? "overflow_shadow" : "overflow_bounce", depth);
     };
+    // Two dependency chains per frame:
+    //   hits      primary -> emit(0) -> bounce(1) -> emit(1) -> bounce(2) -> ...          (main stream)
+    //   lighting  shadow(d) -> shade(d), needs only the hits of depth d                   (one side stream per depth)
+    // so the lighting of depth d overlaps the hit chain of depth d+1 and the lighting of the other depths; the
+    // persistent CTAs of a later kernel move into an SM as those of an earlier one run out of work, which fills
+    // the kernels' tails.  With CT_FLAG_STAGE_TIMING everything is serialised on the main stream instead.
     if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(pk);
     else k_primary<false><<<grid, kBlockThreads, 0, st>>>(pk);
     TRY(mark("primary", 0));
     for (int d = 0; d <= depth_max; d++) {
+        const Params v = view(d);
+        const int ovf_b = 2 * d, ovf_s = 2 * d + 1;
         if (d > 0) {
-            if (count) k_bounce<true><<<grid, kBlockThreads, 0, st>>>(pk, d, work++, 2 * d);
-            else k_bounce<false><<<grid, kBlockThreads, 0, st>>>(pk, d, work++, 2 * d);
+            Params vb = v;
+            if (s.can_overflow) { vb.ovf = s.ovf_all + (size_t)pk.ovf_cap * ovf_b; vb.ovf_huge = s.ovf_huge_all + (size_t)pk.ovf_cap * ovf_b; }
+            if (count) k_bounce<true><<<grid, kBlockThreads, 0, st>>>(vb, d, work++, ovf_b);
+            else k_bounce<false><<<grid, kBlockThreads, 0, st>>>(vb, d, work++, ovf_b);
             TRY(mark("bounce", d));
-            TRY(overflow(0, 2 * d, d));
+            TRY(overflow(v, st, 0, ovf_b, d));
         }
+        cudaStream_t side = stages ? st : s.aux[d % 4];
+        if (!stages) { CU(cudaEventRecord(s.ev_hit[d], st)); CU(cudaStreamWaitEvent(side, s.ev_hit[d], 0)); }
+        if (depth_max > 0) { k_emit<<<grid, kBlockThreads, 0, st>>>(v, d, work++); TRY(mark("emit", d)); }
         if (pk.n_slights > 0) {
-            if (count) k_shadow<true><<<grid, kBlockThreads, 0, st>>>(pk, d, work++, 2 * d + 1);
-            else k_shadow<false><<<grid, kBlockThreads, 0, st>>>(pk, d, work++, 2 * d + 1);
-            TRY(mark("shadow", d));
-            TRY(overflow(1, 2 * d + 1, d));
+            Params vs = v;
+            if (s.can_overflow) { vs.ovf = s.ovf_all + (size_t)pk.ovf_cap * ovf_s; vs.ovf_huge = s.ovf_huge_all + (size_t)pk.ovf_cap * ovf_s; }
+            if (count) k_shadow<true><<<grid, kBlockThreads, 0, side>>>(vs, d, work++, ovf_s);
+            else k_shadow<false><<<grid, kBlockThreads, 0, side>>>(vs, d, work++, ovf_s);
+            if (stages) TRY(mark("shadow", d)); else s.launches++;
+            if (stages) { TRY(overflow(v, side, 1, ovf_s, d)); }
+            else if (s.can_overflow) {
+                Params vo = v;
+                vo.ovf = s.ovf_all + (size_t)pk.ovf_cap * ovf_s; vo.ovf_huge = s.ovf_huge_all + (size_t)pk.ovf_cap * ovf_s;
+                if (count) { k_overflow<kAnyHit, true><<<s.n_sm * 2, kOvfThreads, 0, side>>>(vo, ovf_s); k_overflow_huge<kAnyHit, true><<<s.n_sm * 4, 256, 0, side>>>(vo, ovf_s); }
+                else { k_overflow<kAnyHit, false><<<s.n_sm * 2, kOvfThreads, 0, side>>>(vo, ovf_s); k_overflow_huge<kAnyHit, false><<<s.n_sm * 4, 256, 0, side>>>(vo, ovf_s); }
+                s.launches += 2;
+            }
         }
-        k_shade<<<grid, kBlockThreads, 0, st>>>(pk, d, work++);
-        TRY(mark("shade", d));
+        k_shade<<<grid, kBlockThreads, 0, side>>>(v, d, work++);
+        if (stages) TRY(mark("shade", d)); else s.launches++;
+        if (!stages) CU(cudaEventRecord(s.ev_done[d], side));
     }
+    if (!stages) for (int d = 0; d <= depth_max; d++) CU(cudaStreamWaitEvent(st, s.ev_done[d], 0));
     if (depth_max > 0) { k_resolve<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("resolve", 0)); }
     CU(cudaEventRecord(s.ev1, st));
     CU(cudaEventRecord(s.tile_done[s.tiles_submitted % 8], st));

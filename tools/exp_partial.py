@@ -27,3 +27,20 @@ for (y0, y1, what) in ((H // 2 - 40, H // 2 - 8, "32 background rows"), (-16, 16
         r.render_tile(y0, y1); r.sync()
     print(f"{what}: {r.last_tile_ms():.3f} ms " + " ".join(f"{nm}[{d}]={ms:.3f}" for nm, d, ms in r.last_tile_stages()), flush=True)
 r.shutdown()
+print("-- concurrent mode (no stage timing): whole-tile device time", flush=True)
+r = api.GpuRenderer(0).upload(fs, W, H, max_depth=depth)
+for frac in (1, 2, 4, 8):
+    rows = H // frac
+    y0 = -rows // 2
+    best = 1e9
+    for i in range(6):
+        r.render_tile(y0, y0 + rows); r.sync()
+        if i >= 2: best = min(best, r.last_tile_ms())
+    print(f"concurrent 1/{frac} of the rows: {best:.3f} ms", flush=True)
+for (y0, y1, what) in ((H // 2 - 40, H // 2 - 8, "32 background rows"), (-16, 16, "32 rows through the centre"), (-64, 64, "128 centre rows")):
+    best = 1e9
+    for i in range(6):
+        r.render_tile(y0, y1); r.sync()
+        if i >= 2: best = min(best, r.last_tile_ms())
+    print(f"concurrent {what}: {best:.3f} ms", flush=True)
+r.shutdown()
