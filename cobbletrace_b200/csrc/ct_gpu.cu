@@ -6,20 +6,23 @@
 // becomes a wavefront of persistent-warp kernels over SoA path state in HBM:
 //
 //   k_primary   raygen (CanvasToViewport :186) + closest-hit DFS            -> hit records
-//   k_shadow    ComputeLighting's shadow rays (:288-306), one work item per (light, path) in
-//               light-major order (a warp = 32 neighbouring paths, same light); any-hit DFS
-//               with early exit                                              -> occlusion bit masks
-//   k_shade     NormalOfSceneObject :329 + ComputeLighting :275 accumulation (lights in file
-//               order, fp32) + HsvToColor; emits the reflection ray (:372-373) into the next queue
+//   k_emit      the recursion step (:369-373): end the path or append the reflection ray to the next queue
 //   k_bounce    the reference's degenerate t=0 reflection rays (:373): first barycentric
 //               pass in DFS order                               -> hit records
-//   k_overflow  rays whose DFS exceeds a visit budget (e.g. shadow rays cast from a shading point
+//   k_shadow    ComputeLighting's shadow rays (:288-306), one work item per (light, path) in
+//               light-major order (a warp = 32 neighbouring paths, same light); any-hit walk with deferred
+//               leaves                                                       -> occlusion bit masks
+//   k_shade     NormalOfSceneObject :329 + ComputeLighting :275 accumulation (lights in file
+//               order, fp32) + HsvToColor                                    -> per-depth colour stack / framebuffer
+//   k_overflow, k_overflow_huge
+//               rays whose walk exceeds a visit budget (e.g. shadow rays cast from a shading point
 //               4.3e9 units away after a reflection "miss": fp32 slab quotients all round to the
-//               same value and EVERY box passes) are parked by k_shadow / k_bounce and traversed
-//               here by the whole grid, breadth first (cooperative launch, one grid.sync per level)
+//               same value and EVERY box passes) are parked by k_shadow / k_bounce and finished by a warp
+//               each, or -- the every-box-passes ones -- by the whole grid testing all triangles at once
 //   k_resolve   unwinds the per-pixel blend chain (:375-379) and stores 0x00BBGGRR pixels
 //
-// Arithmetic is the reference's mixed fp64/fp32, reproduced exactly (ct_exact.cuh).
+// Arithmetic is the reference's mixed fp64/fp32, reproduced exactly: certified fp32 filters decide what they can,
+// the reference's own operations (explicit round-to-nearest intrinsics, ct_exact.cuh) decide the rest.
 // No tensor cores: the path has no dense contraction.  No CPU fallback.
 #include "../../include/ct_gpu.h"
 #include "ct_exact.cuh"
