@@ -108,7 +108,7 @@ def load_library(path: Optional[str] = None):
     L.ct_gpu_gather_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.ct_gpu_debug_closest.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp]
     L.ct_gpu_debug_primitives.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
-    L.ct_gpu_debug_filter.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, C.c_double, vp]
+    L.ct_gpu_debug_filter.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_double, vp]
     L.ct_gpu_filter_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.ct_gpu_share_export.argtypes = [C.c_int, C.POINTER(Share)]
     L.ct_gpu_share_attach.argtypes = [C.c_int, C.POINTER(Share)]
@@ -289,14 +289,15 @@ class GpuRenderer:
         _check(self.L, self.L.ct_gpu_debug_primitives(self.device, n, _ptr(o), _ptr(d), _ptr(rt), _ptr(tri), _ptr(mn), _ptr(mx), _ptr(th), _ptr(bh)))
         return th, bh, rt
 
-    def debug_filter(self, origins, directions, ray_t, bmin, bmax, bound_scale=1.0):
-        """ct_gpu_debug_filter: verdict codes of the certified fp32 slab filter next to the reference's verdict."""
+    def debug_filter(self, origins, directions, ray_t, bmin, bmax, bound_scale=1.0, tri=None):
+        """ct_gpu_debug_filter: verdict codes of the certified fp32 filters next to the reference's verdicts."""
         o = np.ascontiguousarray(origins, np.float64); d = np.ascontiguousarray(directions, np.float64)
         rt = np.ascontiguousarray(ray_t, np.float32)
         mn = np.ascontiguousarray(bmin, np.float64); mx = np.ascontiguousarray(bmax, np.float64)
+        tr = None if tri is None else np.ascontiguousarray(tri, np.float64)
         n = o.shape[0]
         out = np.zeros(n, np.uint32)
-        _check(self.L, self.L.ct_gpu_debug_filter(self.device, n, _ptr(o), _ptr(d), _ptr(rt), _ptr(mn), _ptr(mx), float(bound_scale), _ptr(out)))
+        _check(self.L, self.L.ct_gpu_debug_filter(self.device, n, _ptr(o), _ptr(d), _ptr(rt), _ptr(tr), _ptr(mn), _ptr(mx), float(bound_scale), _ptr(out)))
         return out
 
     def filter_stats(self):

@@ -958,7 +958,7 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
 
 __global__ void k_debug_primitives(uint32_t n, const double *org, const double *dir, float *ray_t, const double *tri,
                                    const double *bmin, const double *bmax, uint32_t *tri_hit, uint32_t *box_hit,
-                                   uint32_t *filter_out, double bound_scale) {
+                                   uint32_t *filter_out, double bound_scale, bool tri_filter) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Ray r;
@@ -997,7 +997,25 @@ __global__ void k_debug_primitives(uint32_t n, const double *org, const double *
                               (lit.tmax == rec.tmax || (lit.tmax != lit.tmax && rec.tmax != rec.tmax));
             if (!same || box_accept(rec, r.t) != exact) f |= 16u;
         }
-        filter_out[i] = (exact ? 1u : 0u) | ((f & 3u) << 1) | (tr.filt ? 8u : 0u) | ((f & 8u) ? 16u : 0u) | ((f & 16u) ? 32u : 0u);
+        uint32_t out = (exact ? 1u : 0u) | ((f & 3u) << 1) | (tr.filt ? 8u : 0u) | ((f & 8u) ? 16u : 0u) | ((f & 16u) ? 32u : 0u);
+        if (tri_filter) {
+            // the certified triangle filter on the same (ray, triangle), with the magnitudes the upload would store:
+            // bit 8 = reference returns true, bit 9 = ... and the hit would occlude a shadow ray (1e-4 < t < 1e30),
+            // bit 10 / 11 = tri_filter_miss<false> / <true> say "certainly no effect", bit 12 = filter usable
+            const V3 q1 = ld3(tri + 9ull * i), q2 = ld3(tri + 9ull * i + 3), q3 = ld3(tri + 9ull * i + 6);
+            const V3 e1 = vsub(q2, q1), e2 = vsub(q3, q1);
+            float tt = 0.0f;
+            const bool th = intersect_triangle(r, q1, e1, e2, &tt);
+            const double k1 = fmax(fmax(fabs(e1.x), fabs(e1.y)), fabs(e1.z)), k2 = fmax(fmax(fabs(e2.x), fabs(e2.y)), fabs(e2.z));
+            const double k3 = fmax(fmax(fabs(q1.x), fabs(q1.y)), fabs(q1.z));
+            const bool in_range = k1 >= 0x1p-30 && k1 <= 0x1p30 && k2 >= 0x1p-30 && k2 <= 0x1p30 && k3 <= 0x1p40;
+            const float4 t0 = make_float4((float)q1.x, (float)q1.y, (float)q1.z, __double2float_ru(k3));
+            const float4 t1 = make_float4((float)e1.x, (float)e1.y, (float)e1.z, in_range ? __double2float_ru(k1) : NAN);
+            const float4 t2 = make_float4((float)e2.x, (float)e2.y, (float)e2.z, __double2float_ru(k2));
+            const bool m0 = tr.tfilt && tri_filter_miss<false>(tr, t0, t1, t2), m1 = tr.tfilt && tri_filter_miss<true>(tr, t0, t1, t2);
+            out |= (th ? 1u << 8 : 0u) | ((th && tt > kEps && tt < kRayTInit) ? 1u << 9 : 0u) | (m0 ? 1u << 10 : 0u) | (m1 ? 1u << 11 : 0u) | (tr.tfilt ? 1u << 12 : 0u);
+        }
+        filter_out[i] = out;
     }
     V3 p1 = ld3(tri + 9ull * i), p2 = ld3(tri + 9ull * i + 3), p3 = ld3(tri + 9ull * i + 6);
     float t;
@@ -1776,7 +1794,7 @@ int ct_gpu_debug_closest(int device, uint32_t n, const double *origins, const do
 
 static int debug_primitives_impl(int device, uint32_t n, const double *origins, const double *directions, float *ray_t,
                                  const double *tri, const double *bmin, const double *bmax, uint32_t *tri_hit, uint32_t *box_hit,
-                                 uint32_t *filter_out, double bound_scale) {
+                                 uint32_t *filter_out, double bound_scale, bool keep_ray_t = false) {
     TRY(check_device(device));
     if (n == 0) return CT_OK;
     double *d_o = nullptr, *d_d = nullptr, *d_tri = nullptr, *d_mn = nullptr, *d_mx = nullptr; float *d_t = nullptr;
@@ -1794,10 +1812,10 @@ static int debug_primitives_impl(int device, uint32_t n, const double *origins, 
     CUX(cudaMemcpy(d_mn, bmin, 24ull * n, cudaMemcpyHostToDevice));
     CUX(cudaMemcpy(d_mx, bmax, 24ull * n, cudaMemcpyHostToDevice));
     CUX(cudaMemcpy(d_t, ray_t, 4ull * n, cudaMemcpyHostToDevice));
-    k_debug_primitives<<<(n + 127) / 128, 128>>>(n, d_o, d_d, d_t, d_tri, d_mn, d_mx, d_th, d_bh, d_f, bound_scale);
+    k_debug_primitives<<<(n + 127) / 128, 128>>>(n, d_o, d_d, d_t, d_tri, d_mn, d_mx, d_th, d_bh, d_f, bound_scale, filter_out != nullptr && tri != nullptr);
     CUX(cudaGetLastError());
     CUX(cudaDeviceSynchronize());
-    if (tri) CUX(cudaMemcpy(ray_t, d_t, 4ull * n, cudaMemcpyDeviceToHost));
+    if (tri && !keep_ray_t) CUX(cudaMemcpy(ray_t, d_t, 4ull * n, cudaMemcpyDeviceToHost));
     if (tri_hit) CUX(cudaMemcpy(tri_hit, d_th, 4ull * n, cudaMemcpyDeviceToHost));
     if (box_hit) CUX(cudaMemcpy(box_hit, d_bh, 4ull * n, cudaMemcpyDeviceToHost));
     if (filter_out) CUX(cudaMemcpy(filter_out, d_f, 4ull * n, cudaMemcpyDeviceToHost));
@@ -1813,10 +1831,10 @@ int ct_gpu_debug_primitives(int device, uint32_t n, const double *origins, const
 }
 
 int ct_gpu_debug_filter(int device, uint32_t n, const double *origins, const double *directions, const float *ray_t,
-                        const double *bmin, const double *bmax, double bound_scale, uint32_t *verdict) {
+                        const double *tri, const double *bmin, const double *bmax, double bound_scale, uint32_t *verdict) {
     if (!origins || !directions || !ray_t || !bmin || !bmax || !verdict) return fail(CT_ERR_INVALID, "NULL array");
     if (!(bound_scale >= 1.0)) return fail(CT_ERR_INVALID, "bound_scale must be >= 1");
-    return debug_primitives_impl(device, n, origins, directions, const_cast<float *>(ray_t), nullptr, bmin, bmax, nullptr, nullptr, verdict, bound_scale);
+    return debug_primitives_impl(device, n, origins, directions, const_cast<float *>(ray_t), tri, bmin, bmax, nullptr, nullptr, verdict, bound_scale, true);
 }
 
 int ct_gpu_shutdown(int device) {

@@ -227,14 +227,17 @@ int ct_gpu_debug_primitives(int device, uint32_t n, const double *origins, const
                             const double *tri, const double *bmin, const double *bmax,
                             uint32_t *tri_hit, uint32_t *box_hit);
 
-/* Soundness test entry for the certified fp32 slab filter that fronts IntersectAABB on the device:
- * n independent (ray, box) cases.  The filter's per-axis magnitude bound is max(|bmin|,|bmax|) * bound_scale
- * (bound_scale >= 1 imitates a small box inside a large scene).  verdict[i]: bit 0 = the reference's verdict,
- * bits 1-2 = the filter's (0 undecided, 1 accept, 2 reject), bit 3 = filter usable for this ray, bit 4 = the
- * filter's bracket failed to contain the reference's float tmin/tmax, bit 5 = the division-free fp64 evaluation
- * used for undecided tests differs from the literal arithmetic (neither may ever be set). */
+/* Soundness test entry for the certified fp32 filters that front IntersectAABB / IntersectTriangle on the device
+ * (DESIGN.md 2): n independent (ray, box[, triangle]) cases; tri (n x 9) may be NULL.  The slab filter's per-axis
+ * magnitude bound is max(|bmin|,|bmax|) * bound_scale (bound_scale >= 1 imitates a small box inside a large scene).
+ * verdict[i]: bit 0 = the reference's box verdict, bits 1-2 = the slab filter's (0 undecided, 1 accept, 2 reject),
+ * bit 3 = slab filter usable for this ray, bit 4 = its bracket failed to contain the reference's float tmin/tmax,
+ * bit 5 = the division-free fp64 evaluation used for undecided tests differs from the literal arithmetic (4 and 5
+ * must never be set); with tri: bit 8 = the reference's IntersectTriangle returns true, bit 9 = ... with
+ * 1e-4 < t < 1e30 (what occludes a shadow ray), bit 10 / 11 = the triangle filter says "certainly no effect" for
+ * closest-hit / shadow rays (must imply bit 8 / bit 9 clear), bit 12 = triangle filter usable for this ray. */
 int ct_gpu_debug_filter(int device, uint32_t n, const double *origins, const double *directions, const float *ray_t,
-                        const double *bmin, const double *bmax, double bound_scale, uint32_t *verdict);
+                        const double *tri, const double *bmin, const double *bmax, double bound_scale, uint32_t *verdict);
 
 /* Frees everything held for `device` (the reference never frees; this makes the library re-entrant). */
 int ct_gpu_shutdown(int device);

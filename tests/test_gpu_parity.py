@@ -114,6 +114,40 @@ def test_slab_filter_is_sound_and_mostly_decides(gpu, bound_scale):
     assert ((filt == 1).sum() > 1000) and ((filt == 2).sum() > 1000)
 
 
+def test_triangle_filter_is_sound_and_mostly_decides(gpu):
+    """The certified fp32 filter in front of IntersectTriangle may only discard a triangle whose reference test has no
+    effect: 1M (ray, triangle) cases -- rays aimed at / just past triangle edges and vertices, rays starting ON the
+    triangle (what a shadow or reflection ray does), slivers, tiny and huge triangles, far-away origins."""
+    rng = np.random.default_rng(5)
+    n = 1 << 20
+    scale = rng.choice([1e-3, 0.03, 1.0, 40.0], (n, 1))
+    p1 = rng.normal(size=(n, 3)) * rng.choice([0.0, 1.0, 30.0], (n, 1))
+    e1, e2 = rng.normal(size=(n, 3)) * scale, rng.normal(size=(n, 3)) * scale
+    sliver = rng.random(n) < 0.1
+    e2[sliver] = e1[sliver] * rng.uniform(0.5, 2, (int(sliver.sum()), 1)) + rng.normal(size=(int(sliver.sum()), 3)) * scale[sliver] * 1e-6
+    tri = np.concatenate([p1, p1 + e1, p1 + e2], 1)
+    # target point: barycentric (u, v) mostly near the boundary of the triangle
+    u = rng.choice([0.0, 1.0, 0.3, -1e-7, 1 + 1e-7, 0.5], n) + rng.normal(size=n) * rng.choice([0.0, 1e-9, 1e-4, 0.5], n)
+    v = rng.choice([0.0, 0.7, 0.3, -1e-7, 0.5], n) + rng.normal(size=n) * rng.choice([0.0, 1e-9, 1e-4, 0.5], n)
+    target = p1 + u[:, None] * e1 + v[:, None] * e2
+    d = rng.normal(size=(n, 3)) * rng.choice([1e-2, 1.0, 300.0], (n, 1))
+    tdist = rng.choice([0.0, 1e-5, 1e-4, 1.0, 50.0, -3.0], n) * rng.choice([1.0, 1 + 1e-7], n)
+    o = target - tdist[:, None] * d                               # tdist == 0: the ray starts on the triangle's plane
+    far = rng.random(n) < 0.02
+    o[far] *= 1e9
+    rt = np.full(n, 1e30, np.float32)
+    box = np.concatenate([np.minimum.reduce([p1, p1 + e1, p1 + e2]), np.maximum.reduce([p1, p1 + e1, p1 + e2])], 1)
+    vv = gpu.debug_filter(o, d, rt, box[:, :3], box[:, 3:], 1.0, tri=tri)
+    hit, occl, m_closest, m_shadow, usable = (vv >> 8) & 1, (vv >> 9) & 1, (vv >> 10) & 1, (vv >> 11) & 1, (vv >> 12) & 1
+    assert not (m_closest & hit).any(), f"{int((m_closest & hit).sum())} triangles discarded although the reference's test returns true"
+    assert not (m_shadow & occl).any(), f"{int((m_shadow & occl).sum())} occluders discarded"
+    assert (m_closest <= m_shadow).all()                          # the shadow variant only ever discards more
+    assert usable.mean() > 0.9 and hit.sum() > 10000 and occl.sum() > 1000
+    miss = (hit == 0) & (usable == 1)
+    assert m_closest[miss].mean() > 0.5, m_closest[miss].mean()   # (real scenes: ~90 %, tools/perf_stages.py)
+    assert (m_shadow & hit & (1 - occl)).sum() > 1000             # t <= 1e-4 hits (rays leaving the triangle) are discarded for shadow rays
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_golden_frames_from_reference(case, golden, scene_loader, gpu):
     fs, meta = case_scene(case, golden, scene_loader)
