@@ -123,7 +123,9 @@ struct Params {
     int W, H, max_depth;
     uint32_t background;
     // tile
-    int x_lo, n_x, y_lo, n_y;        // canvas x in [x_lo, x_lo+n_x), y in [y_lo, y_lo+n_y)
+    int x_lo, n_x, y_lo, n_y;        // canvas x in [x_lo, x_lo+n_x), n_y traced rows starting at y_lo
+    int subsample, n_rows;           // CT_FLAG_SUBSAMPLING: the tile spans n_rows canvas rows of which every other one is traced
+    uint32_t *final_color;           // ... and the traced pixels' colours by slot, for k_subsample
     int blocks_x;                    // ceil(n_x / 8): pixel blocks of 8x4 per warp
     uint32_t n_slots;                // blocks_x * ceil(n_y/4) * 32
     uint32_t cap;                    // capacity of every per-slot array
@@ -431,16 +433,30 @@ CT_DEV Ray primary_ray(const Params &P, int x, int y) {
 }
 
 // slot -> canvas pixel.  A warp owns an 8x4 pixel block (coherent rays); returns false for padding lanes
-// and for pixels PutPixel would drop (draw2d.h:11-14), which are not traced at all.
+// and for pixels PutPixel would drop (draw2d.h:11-14), which are not traced at all (with subsampling a dropped
+// row is still traced -- fb_index = -1 -- because its colour enters the average stored in the row above it).
+CT_DEV void store_pixel(const Params &P, uint32_t slot, int fb_index, uint32_t color) {
+    if (fb_index >= 0) P.fb_out[fb_index] = color;
+    if (P.final_color) P.final_color[slot] = color;
+}
+
 CT_DEV bool slot_pixel(const Params &P, uint32_t slot, int &x, int &y, int &fb_index) {
     uint32_t blk = slot >> 5, lane = slot & 31u;
     int bx = (int)(blk % (uint32_t)P.blocks_x), by = (int)(blk / (uint32_t)P.blocks_x);
     int ix = bx * 8 + (int)(lane & 7u), iy = by * 4 + (int)(lane >> 3);
     if (ix >= P.n_x || iy >= P.n_y) return false;
-    x = P.x_lo + ix; y = P.y_lo + iy;
+    x = P.x_lo + ix;
+    if (P.subsample)    // raythread.cpp:527-530: y += 2, except that the last row of the partition is always traced
+        y = P.y_lo + ((iy == P.n_y - 1 && (P.n_rows & 1) == 0) ? P.n_rows - 1 : 2 * iy);
+    else
+        y = P.y_lo + iy;
     int col = x + P.W / 2, row = P.H / 2 - y;               // CanvasPutPixel raythread.cpp:181-182
-    if (row < 0 || row >= P.H || col < 0 || col >= P.W) return false;
+    if (col < 0 || col >= P.W) return false;
     fb_index = row * P.W + col;
+    if (row < 0 || row >= P.H) {
+        if (!P.subsample) return false;
+        fb_index = -1;                                       // traced for the average of the row above it, never stored
+    }
     return true;
 }
 
@@ -535,7 +551,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
             P.hit0_t[slot] = tc;
             P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
             if (found) clear_occ(P, q);
-            if (P.dbg_found) {
+            if (P.dbg_found && fbi >= 0) {
                 P.dbg_found[fbi] = found ? 1u : 0u;
                 P.dbg_index[fbi] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
                 P.dbg_t[fbi] = tc;
@@ -665,7 +681,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
         if (!(q < n && load_path(P, depth, q, slot, fbi, r, tc, pos))) continue;
         uint32_t *sc = P.stack_color + (size_t)depth * P.cap + slot;
         if (pos == kNoPos) {                                           // miss (depth 0 only): raythread.cpp:385
-            if (depth == 0) P.fb_out[fbi] = P.background;
+            if (depth == 0) store_pixel(P, slot, fbi, P.background);
             *sc = P.background;
             continue;
         }
@@ -704,7 +720,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
         uint32_t local = shade_color(mat.color, intensity);
         *sc = local;
         // a depth-0 path that ends here (:369) is the pixel; longer chains are blended by k_resolve
-        if (depth == 0 && (P.max_depth <= 0 || !(mat.reflection > 0.0f))) P.fb_out[fbi] = local;
+        if (depth == 0 && (P.max_depth <= 0 || !(mat.reflection > 0.0f))) store_pixel(P, slot, fbi, local);
     }
 }
 
@@ -928,7 +944,32 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Params 
         uint32_t color = P.stack_color[(size_t)lvl * P.cap + slot];
         for (int d = lvl - 1; d >= 0; d--)
             color = blend_color(P.stack_color[(size_t)d * P.cap + slot], color, P.stack_refl[(size_t)d * P.cap + slot]);
-        P.fb_out[fbi] = color;
+        store_pixel(P, slot, fbi, color);
+    }
+}
+
+// settings.subsampling (raythread.cpp:512-531): after a traced pixel (x, y) the reference stores the average of its
+// colour and the previously traced colour of the column (its own for the first row of the partition) one row
+// below, at (x, y - 1).  Runs after every traced pixel of the tile has its final colour; a later store wins where
+// the reference's sequential loop would overwrite (the always-traced last row of an even partition).
+__global__ void __launch_bounds__(256) k_subsample(const __grid_constant__ Params P) {
+    const uint32_t n = depth0_count(P);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t slot = own_slot(P, q);
+        int x, y, fbi;
+        if (!slot_pixel(P, slot, x, y, fbi)) continue;
+        const uint32_t blk = slot >> 5, lane = slot & 31u;
+        const uint32_t iy = (blk / (uint32_t)P.blocks_x) * 4u + (lane >> 3);
+        const uint32_t color = P.final_color[slot];
+        uint32_t last = color;                                                 // :513-514
+        if (iy > 0) {
+            const uint32_t py = iy - 1u, ix = (blk % (uint32_t)P.blocks_x) * 8u + (lane & 7u);
+            last = P.final_color[(((py >> 2) * (uint32_t)P.blocks_x + (ix >> 3)) << 5) + ((py & 3u) << 3) + (ix & 7u)];
+        }
+        uint32_t avg = 0;                                                      // :517-523: float (a + b) / 2, min 0xff, truncated
+        for (int sh = 0; sh <= 16; sh += 8) avg |= ((((last >> sh) & 0xffu) + ((color >> sh) & 0xffu)) >> 1) << sh;
+        const int col = x + P.W / 2, row = P.H / 2 - (y - 1);                  // CanvasPutPixel(bitmap, {x, y-1}, avgColor) :524
+        if (row >= 0 && row < P.H && col >= 0 && col < P.W) P.fb_out[row * P.W + col] = avg;
     }
 }
 
@@ -1372,6 +1413,8 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
         TRY(dev_alloc(s, &s.rays_all, (size_t)p.cap * 6 * (levels + 1))); TRY(dev_alloc(s, &s.path_slot_all, (size_t)p.cap * (levels + 1)));
     }
     TRY(dev_alloc(s, &p.fb, (size_t)d->width * d->height, true));       // calloc'd like cobbletrace.cpp:57
+    p.subsample = (d->flags & CT_FLAG_SUBSAMPLING) ? 1 : 0;
+    if (p.subsample) TRY(dev_alloc(s, &p.final_color, p.cap, true));
     TRY(dev_alloc(s, &p.own_chunks, (p.cap >> kChunkLocalShift) + 1u));
     TRY(dev_alloc(s, &s.cursor_own, 1, true));                           // its own allocation: exported over CUDA IPC
     s.share_cursor = s.cursor_own; s.share_fb = p.fb;
@@ -1412,9 +1455,16 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     int half = s.p.H / 2;
     // rows outside [-half+?, half] can never be stored (draw2d.h:11): clip so no ray is wasted on them
     int y0 = std::max(y_start, half - (s.p.H - 1)), y1 = std::min(y_end, half + 1);
+    if (s.p.subsample) {
+        // the partition's own bounds define which rows are traced and averaged (raythread.cpp:457,513,527): no clipping
+        if (shared) return fail(CT_ERR_INVALID, "CT_FLAG_SUBSAMPLING needs the whole partition on one device (neighbouring rows are averaged)");
+        y0 = y_start; y1 = y_end;
+        if (y0 < -(1 << 20) || y1 > (1 << 20)) return fail(CT_ERR_INVALID, "tile [%d,%d) out of range", y_start, y_end);
+    }
     if (y1 <= y0) { if (counters) memset(counters, 0, sizeof *counters); return CT_OK; }
     Params p = s.p;
-    p.y_lo = y0; p.n_y = y1 - y0;
+    p.y_lo = y0; p.n_rows = y1 - y0;
+    p.n_y = s.p.subsample ? (p.n_rows + 1) / 2 + ((p.n_rows & 1) == 0 ? 1 : 0) : p.n_rows;
     p.n_slots = (uint32_t)p.blocks_x * (uint32_t)((p.n_y + 3) / 4) * 32u;
     if (p.n_slots > p.cap) return fail(CT_ERR_INVALID, "tile [%d,%d) larger than the frame", y_start, y_end);
     const bool count = (s.flags & CT_FLAG_COUNT_TESTS) != 0;
@@ -1511,13 +1561,15 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     }
     if (!stages) for (int d = 0; d <= depth_max; d++) CU(cudaStreamWaitEvent(st, s.ev_done[d], 0));
     if (depth_max > 0) { k_resolve<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("resolve", 0)); }
+    if (pk.subsample) { k_subsample<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("subsample", 0)); }
     CU(cudaEventRecord(s.ev1, st));
     CU(cudaEventRecord(s.tile_done[s.tiles_submitted % 8], st));
     s.tiles_submitted++;
     CU(cudaGetLastError());
     s.timed = true;
     {   // framebuffer rows this tile writes: row = H/2 - y
-        int lo = half - (y1 - 1), hi = half - y0 + 1;
+        int lo = half - (y1 - 1), hi = half - y0 + 1 + (s.p.subsample ? 1 : 0);   // subsampling also stores row y0 - 1
+        lo = std::max(lo, 0); hi = std::min(hi, s.p.H);
         if (s.row_hi <= s.row_lo) { s.row_lo = lo; s.row_hi = hi; }
         else { s.row_lo = std::min(s.row_lo, lo); s.row_hi = std::max(s.row_hi, hi); }
     }

@@ -70,7 +70,11 @@ enum {
                                  (raythread.cpp:454-455 "Keep it square"); SURVEY f2 */
     CT_FLAG_KEEP_HITS = 2u,   /* keep the primary-ray hit records for ct_gpu_readback_hits */
     CT_FLAG_COUNT_TESTS = 4u, /* count box / triangle tests (slower; for roofline accounting) */
-    CT_FLAG_STAGE_TIMING = 8u /* bracket every kernel launch of a tile with CUDA events (profiling passes only) */
+    CT_FLAG_STAGE_TIMING = 8u, /* bracket every kernel launch of a tile with CUDA events (profiling passes only) */
+    CT_FLAG_SUBSAMPLING = 16u /* settings.subsampling (raythread.cpp:512-531): of the rows of a tile (= one worker's
+                                 partition) every other one and the last are traced, the rows between get the average
+                                 of their neighbours.  Tiles must be rendered in the order the caller wants their
+                                 seams resolved (the reference's threads race there); not with ct_gpu_render_shared */
 };
 
 /* What RayThread hands its workers (display_partition_t raythread.cpp:69-78 + bvh_state_t bvh.h:19-25). */

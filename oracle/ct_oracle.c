@@ -288,8 +288,10 @@ static void *render_rows(void *arg) {
     float sx = 1.0f / (float)H, sy = 1.0f / (float)H;   /* :189-192 viewport {1,1,1} :554, float quotient */
     vec3 cam = v_load(s->cam_pos);
     const double *m = s->cam_rot;
+    const int subsample = (j->flags & CT_ORACLE_SUBSAMPLE) != 0;
     for (int x = x_lo; x < x_hi; x++) {
-        for (int y = j->y0; y < j->y1; y++) {
+        uint32_t last_color = 0;                       /* :456 */
+        for (int y = j->y0; y < j->y1;) {              /* :457 -- the increment depends on settings.subsampling */
             double vx = (double)(float)x * (double)sx, vy = (double)(float)y * (double)sy, vz = 1.0;
             vec3 dir;                                  /* v3_t * m3x3_t, mymath.h:68-75 */
             dir.x = vx * m[0] + vy * m[3] + vz * m[6];
@@ -307,6 +309,24 @@ static void *render_rows(void *arg) {
             j->cx.kind = 0;
             uint32_t color = trace_ray(&j->cx, r, j->max_depth);
             if (stored) j->frame[(size_t)row * W + col] = color;
+            if (subsample) {                           /* :512-531 */
+                if (y == j->y0) last_color = color;
+                /* rgb_t holds floats (color.h:11-13): (a + b)/2 in float, min with 0xff, truncated by the uint8_t
+                 * parameters of RgbToColor (color.h:77-85) */
+                uint32_t avg = 0;
+                for (int sh = 0; sh <= 16; sh += 8) {
+                    float a = (float)((last_color >> sh) & 0xffu), b = (float)((color >> sh) & 0xffu);
+                    float m = (a + b) / 2;
+                    m = MACRO_MIN(m, (float)0xff);
+                    avg |= (uint32_t)(unsigned char)m << sh;
+                }
+                int row2 = H / 2 - (y - 1);            /* CanvasPutPixel(bitmap, {x, y-1}, avgColor) */
+                if (!(row2 < 0 || row2 >= H || col < 0 || col >= W)) j->frame[(size_t)row2 * W + col] = avg;
+                if (y + 2 >= j->y1) y++; else y += 2;
+            } else {
+                y++;
+            }
+            last_color = color;
         }
     }
     return NULL;

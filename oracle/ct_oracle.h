@@ -53,7 +53,9 @@ typedef struct ct_oracle_counters {
 typedef struct ct_oracle_hit { uint32_t found, index; float t; } ct_oracle_hit;
 
 enum {
-    CT_ORACLE_WIDE = 1  /* trace x in [-W/2, W/2) instead of the reference's centred square */
+    CT_ORACLE_WIDE = 1,     /* trace x in [-W/2, W/2) instead of the reference's centred square */
+    CT_ORACLE_SUBSAMPLE = 2 /* settings.subsampling (raythread.cpp:512-531): every other row of [y_start,y_end) is traced, the
+                               rows between are averages; each thread's row range is one partition (use n_threads = 1) */
 };
 
 /* BVH build, bvh.cpp:16-120.  Arrays sized: node_* for 2*n_tri-1 nodes, tri_index n_tri. Returns nodesUsed. */

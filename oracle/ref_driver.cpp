@@ -25,6 +25,7 @@
 //   --dump-scene F write the flattened scene + BVH (format: see tests/ctscene.py)
 //   --time K       time K frames through the boss/worker, print JSON
 //   --counters     print ray / box-test / triangle-test counters (needs -DCT_COUNT build)
+//   --subsampling  leave settings.subsampling on (every other row traced, the rows between averaged, :512-531)
 //   --keys STR     feed STR as key presses to the reference's HandleKeyboard (raythread.cpp:388) before
 //                  the first frame: y/p/r rotate by pi/16, wasd/io move the camera by 0.1
 
@@ -156,7 +157,7 @@ int main(int argc, char **argv) {
     const char *sceneFile = NULL, *dir = NULL, *frameOut = NULL, *hitsOut = NULL, *sceneOut = NULL, *keys = NULL;
     int W = 640, H = 640, threads = 8, timeFrames = 0, warmFrames = 0;
     float forceReflection = -1;
-    bool counters = false;
+    bool counters = false, subsampling = false;
     if (argc == 4 && strcmp(argv[1], "--kat") == 0) return RunKat(argv[2], argv[3]);
     for (int i = 1; i < argc; i++) {
         #define ARG(name) (strcmp(argv[i], name) == 0 && i + 1 < argc)
@@ -174,6 +175,7 @@ int main(int argc, char **argv) {
         else if (ARG("--warmup")) warmFrames = atoi(argv[++i]);   // untimed frames before the --time frames
         else if (ARG("--keys")) keys = argv[++i];       // key presses fed to HandleKeyboard before the first frame
         else if (strcmp(argv[i], "--counters") == 0) counters = true;
+        else if (strcmp(argv[i], "--subsampling") == 0) subsampling = true;   // settings.subsampling (raythread.cpp:512-531); use --threads 1
         else if (strcmp(argv[i], "--verbose") == 0) ct_sdl_stub_quiet = 0;
         else { fprintf(stderr, "unknown arg %s\n", argv[i]); return 2; }
     }
@@ -199,7 +201,7 @@ int main(int argc, char **argv) {
 
     // Parity settings: sampling modes off (supersampling draws from shared rand()).
     scene.settings.supersampling = false;
-    scene.settings.subsampling = false;
+    scene.settings.subsampling = subsampling;   // deterministic with one thread (several threads race on the rows between partitions)
     scene.settings.numberOfThreads = threads;
     if (forceReflection >= 0) {
         for (int i = 0; i < scene.objectStack.index; i++) scene.objectStack.objects[i].material.reflection = forceReflection;

@@ -231,6 +231,37 @@ def test_shared_frame_mode_on_one_gpu(golden, scene_loader, gpu):
     assert np.array_equal(gpu.readback(), want)
 
 
+def test_subsampling_against_reference_and_oracle(golden, scene_loader, gpu):
+    """CT_FLAG_SUBSAMPLING = settings.subsampling (raythread.cpp:512-531): one tile per frame against frames of the
+    compiled reference (one worker thread), then two tiles in sequence against the oracle run the same way."""
+    for case, m in golden["frames_subsampling"].items():
+        fs = scene_loader(m["scene"])
+        if m["force_reflection"] is not None:
+            fs = fs.with_reflection(m["force_reflection"])
+        gpu.upload(fs, m["width"], m["height"], max_depth=m["depth"], flags=ct.CT_FLAG_SUBSAMPLING)
+        gpu.render_tile()
+        want = np.load(os.path.join(GOLD, f"frames_sub_{case}.npz"))["frame"]
+        got = np.zeros_like(want)
+        gpu.readback(got)
+        assert np.array_equal(got, want), f"{case}: {int((got != want).sum())} pixels differ"
+    fs = scene_loader("scene_import_bunny").with_reflection(0.4)
+    W, H = 211, 158
+    y0, y1 = -(H // 2), -(H // 2) + H
+    for cut in (y0 + 37, y0 + 80):                      # odd and even first partition
+        osc = O.OracleScene(fs)
+        want = np.zeros((H, W), np.uint32)
+        for a, b in ((y0, cut), (cut, y1)):             # the second partition overwrites the seam row, as in submission order
+            f, _, _ = osc.render(W, H, y_start=a, y_end=b, max_depth=2, flags=O.SUBSAMPLE, want_hits=False, n_threads=1)
+            want = np.where(f != 0, f, want)
+        gpu.upload(fs, W, H, max_depth=2, flags=ct.CT_FLAG_SUBSAMPLING)
+        gpu.render_tile(y0, cut); gpu.render_tile(cut, y1)
+        got = np.zeros_like(want)
+        gpu.readback(got)
+        assert np.array_equal(got, want), f"cut {cut}: {int((got != want).sum())} pixels differ"
+    with pytest.raises(ct.CtError):
+        gpu.render_shared()                             # neighbouring rows may not live on different GPUs
+
+
 def test_640_golden_hashes(golden, scene_loader, gpu):
     for name in ("scene_file_cube", "scene_import", "scene_import_bunny", "pc_big"):
         gpu.upload(scene_loader(name), 640, 640)

@@ -91,3 +91,19 @@ def test_color_helpers_edge_cases():
     assert L.ct_oracle_shade_color(0x000000, 0.7) == 0xB2B2B2          # black material: s == 0 -> grey of value v
     assert L.ct_oracle_blend(0x00FF00, 0x0000FF, 1.0) == 0x0000FF
     assert L.ct_oracle_blend(0x102030, 0x405060, 0.0) == 0x102030
+
+
+def test_subsampling_frames_match_reference(golden, scene_loader):
+    """settings.subsampling (raythread.cpp:512-531): the restatement against frames of the compiled
+    reference run with one worker thread (tests/golden/make_golden_subsampling.py)."""
+    import os
+    from oracle import ct_oracle_py as O
+    from conftest import GOLD
+    assert len(golden["frames_subsampling"]) >= 4
+    for case, m in golden["frames_subsampling"].items():
+        fs = scene_loader(m["scene"])
+        if m["force_reflection"] is not None:
+            fs = fs.with_reflection(m["force_reflection"])
+        frame, _, _ = O.OracleScene(fs).render(m["width"], m["height"], max_depth=m["depth"], flags=O.SUBSAMPLE, want_hits=False, n_threads=1)
+        want = np.load(os.path.join(GOLD, f"frames_sub_{case}.npz"))["frame"]
+        assert np.array_equal(frame, want), case
