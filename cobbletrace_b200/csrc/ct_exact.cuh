@@ -89,8 +89,9 @@ CT_DEV void tray_setup(TRay &r, const Ray &ray, const double bound[3], double *r
         double m = __dmul_rn(sum, fabs(rd));
         double e = __dmul_rn(m, 0x1p-22);
         // every quantity must be an ordinary number well inside the float range (a finite non-zero rd rules out
-        // d = 0 and d = +-inf, NaNs fail the comparisons); magnitudes near the float subnormals are left alone
-        ok = ok && (m < 0x1p100) && (fabs(rd) > 0x1p-100) && (fabs(rd) < 0x1p100) && (e > 0x1p-100) && (sum > 0x1p-60);
+        // d = 0 and d = +-inf, NaNs fail the comparisons); magnitudes near the float subnormals are left alone.
+        // m < 2^99 also puts every quotient of a filtered ray below 1e30f (pair_accept's T_FAR relies on it)
+        ok = ok && (m < 0x1p99) && (fabs(rd) > 0x1p-100) && (fabs(rd) < 0x1p100) && (e > 0x1p-100) && (sum > 0x1p-60);
         r.rdf[k] = __double2float_rn(rd);
         r.cl[k] = __double2float_rd(__dsub_rd(c, e));
         r.cu[k] = __double2float_ru(__dadd_ru(c, e));

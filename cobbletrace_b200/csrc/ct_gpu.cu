@@ -226,12 +226,16 @@ CT_DEV TriHit leaf_triangle(const Params &P, const TRay &r, uint32_t pos, LocalC
 // can (no branch on the way), the fp64 arithmetic otherwise.  On return [r_lo, r_hi] brackets the reference's
 // tmin of the RIGHT child (collapsed to the exact value when the fp64 path ran), which is what its deferred
 // `tmin < ray.t` re-check needs.
-template <bool COUNT>
+// T_FAR: the caller's ray.t is 1e30f for good (shadow rays); a filtered ray has |quotients| < 2^99 < 1e30 (tray_setup),
+// so `tmin < ray.t` needs no test.
+template <bool COUNT, bool T_FAR = false>
 CT_DEV void pair_accept(const Params &P, const TRay &r, uint32_t pid, const DevPair32 &pr, bool &hit_l, bool &hit_r,
                         float &r_lo, float &r_hi, LocalCount &lc) {
     const BoxBracket bl = box_filter(r, pr.lmin, pr.lmax), br = box_filter(r, pr.rmin, pr.rmax);
-    const bool no_l = bracket_geom_no(bl) | bracket_t_no(bl, r.t), yes_l = bracket_geom_yes(bl) & bracket_t_yes(bl, r.t);
-    const bool no_r = bracket_geom_no(br) | bracket_t_no(br, r.t), yes_r = bracket_geom_yes(br) & bracket_t_yes(br, r.t);
+    const bool no_l = T_FAR ? bracket_geom_no(bl) : (bracket_geom_no(bl) | bracket_t_no(bl, r.t));
+    const bool yes_l = T_FAR ? bracket_geom_yes(bl) : (bracket_geom_yes(bl) & bracket_t_yes(bl, r.t));
+    const bool no_r = T_FAR ? bracket_geom_no(br) : (bracket_geom_no(br) | bracket_t_no(br, r.t));
+    const bool yes_r = T_FAR ? bracket_geom_yes(br) : (bracket_geom_yes(br) & bracket_t_yes(br, r.t));
     hit_l = yes_l; hit_r = yes_r;
     r_lo = br.near_lo; r_hi = br.near_hi;
     const bool open_l = !r.filt | !(no_l | yes_l), open_r = !r.filt | !(no_r | yes_r);
@@ -265,7 +269,7 @@ constexpr uint32_t kFullMask = 0xffffffffu;
 //   kClosest   general semantics (any initial ray.t).
 //   kFirstLine reflection rays (ray.t = 0, raythread.cpp:373): ray.t never changes, the first bary
 //              pass in DFS order becomes closestIndex with tclosest = 0, so stop there.
-// (kAnyHit has its own loop, traverse_any_hit.)
+// (The early-exit walks have their own loop, traverse_early; kFirstLine is kept here only as its plain DFS form.)
 // WARP-SYNCHRONOUS: all 32 lanes call it (lanes without a ray pass active = false); every iteration = one node
 // visit per live lane, and the lanes re-converge at the vote that ends it (left to itself the compiler lets the
 // lanes of a warp drift apart for the whole walk: measured 8 of 32 lanes active).
@@ -273,7 +277,7 @@ constexpr uint32_t kFullMask = 0xffffffffu;
 // node visits + triangle tests and the caller parks the ray for k_overflow (order-independent answer, see there).
 template <TraverseMode MODE, bool COUNT>
 CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
-    static_assert(MODE != kAnyHit, "shadow rays use traverse_any_hit");
+    static_assert(MODE != kAnyHit, "shadow rays use traverse_early");
     // stack entry = a pushed right child: (ref, cnt) and, in kClosest mode, the bracket of its tmin plus its
     // parent pair to find its fp64 bounds again
     uint32_t stk_ref[kStackMax], stk_cnt[kStackMax];
@@ -356,26 +360,38 @@ CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget
     return r.t != kRayTInit ? kTravHit : kTravMiss;
 }
 
-// Shadow rays (ray.t = 1e30f): only `found` is used (raythread.cpp:306), i.e. whether SOME triangle reachable
-// through accepted boxes has a barycentric pass with 1e-4 < t < 1e30.  ray.t never changes before
-// that, so the set of accepted boxes is fixed and neither the visit order nor the moment a leaf is tested can
-// change the answer.  The loop therefore walks interior nodes only and DEFERS accepted leaves to a short list;
-// the warp alternates between a walk phase and a leaf phase so that its lanes test their triangles together
-// instead of one lane at a time in the middle of the walk (measured: 4 of 32 lanes active in an inline leaf
-// path).  WARP-SYNCHRONOUS like traverse().  Returns kTravHit (occluded) / kTravMiss / kTravOverBudget.
+// The two early-exit walks.
+//   kAnyHit    shadow rays (ray.t = 1e30f): only `found` is used (raythread.cpp:306), i.e. whether SOME triangle
+//              reachable through accepted boxes has a barycentric pass with 1e-4 < t < 1e30;
+//   kFirstLine reflection rays (ray.t = 0, raythread.cpp:373): the first barycentric pass in DFS order becomes
+//              closestIndex with tclosest = 0 = the passing reachable triangle with the LOWEST leaf
+//              position (leaf positions increase along the DFS).
+// ray.t never changes before the exit, so the set of accepted boxes is fixed and the moment a leaf is tested
+// cannot change the answer.  The loop therefore walks interior nodes only and DEFERS accepted leaves to a short
+// list, in DFS order; the warp alternates between a walk phase and a leaf phase in which its lanes test their
+// triangles together, oldest leaf first, instead of one lane at a time in the middle of the walk (measured: 4 of
+// 32 lanes active in an inline leaf path, 16 in the leaf phase).  A leaf phase runs when some lane's list is full
+// and after the walk; kFirstLine stops at the first pass of a phase (every leaf before it has been tested).
+// WARP-SYNCHRONOUS like traverse().  Returns kTravHit (kAnyHit: occluded; kFirstLine: always -- `found` is
+// 0 != 1e30f, raythread.cpp:227 -- with closest_pos = kNoPos when nothing passed), kTravMiss or kTravOverBudget.
 constexpr int kLeafList = 12;
-template <bool COUNT>
-CT_DEV int traverse_any_hit(const Params &P, const TRay &r, bool active, const uint32_t budget, LocalCount &lc) {
+template <TraverseMode MODE, bool COUNT>
+CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    static_assert(MODE != kClosest, "closest-hit rays use traverse");
     uint32_t stk_ref[kStackMax], stk_cnt[kStackMax];     // pushed right children
-    uint32_t leaf_ref[kLeafList], leaf_cnt[kLeafList];   // deferred leaves
+    uint32_t leaf_ref[kLeafList], leaf_cnt[kLeafList];   // deferred leaves, DFS order
     int sp = 0, nleaf = 0;
     uint32_t spent = 1u;
     uint32_t cur_ref = P.root_ref, cur_cnt = P.root_cnt;
     int state = 0;                                        // 1: nodes left to walk (cur_* pending); 0: walk finished
-    int result = kTravMiss;
+    int result = MODE == kFirstLine ? kTravHit : kTravMiss;
+    tclosest = kFinf;          // raythread.cpp:204
+    closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
     if (active) {
         if (COUNT) lc.box++;
         state = exact_root(P, r.r64, r.t) ? 1 : 0;
+    } else {
+        result = kTravMiss;
     }
     while (true) {
         // ---- walk phase: one interior-node visit per walking lane and iteration; leaves go to the list
@@ -388,10 +404,10 @@ CT_DEV int traverse_any_hit(const Params &P, const TRay &r, bool active, const u
                 } else {
                     DevPair32 pr;
                     load_pair32(P.pairs32, cur_ref, pr);
-                        if (COUNT) lc.box += 2;
+                    if (COUNT) lc.box += 2;
                     spent += 2u;
                     bool hit_l, hit_r; float r_lo, r_hi;
-                    pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
+                    pair_accept<COUNT, MODE == kAnyHit>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
                     if (hit_l & hit_r) { stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt; sp++; }
                     descend = hit_l | hit_r;
                     cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
@@ -403,16 +419,23 @@ CT_DEV int traverse_any_hit(const Params &P, const TRay &r, bool active, const u
                 if (spent > budget) { result = kTravOverBudget; state = 0; nleaf = 0; }
             }
         }
-        // ---- leaf phase: one triangle per lane and iteration
-        uint32_t tri = 0;                                 // next triangle inside the leaf on top of the list
-        while (__any_sync(kFullMask, nleaf > 0)) {
-            if (nleaf > 0) {
+        // ---- leaf phase: one triangle per lane and iteration, oldest leaf first
+        int li = 0;
+        uint32_t tri = 0;                                 // next triangle inside leaf li
+        while (__any_sync(kFullMask, li < nleaf)) {
+            if (li < nleaf) {
+                const uint32_t pos = leaf_ref[li] + tri;
                 if (COUNT) lc.tri++;
-                const TriHit th = leaf_triangle<true, COUNT>(P, r, leaf_ref[nleaf - 1] + tri, lc);
-                if (th.hit & (th.t > kEps) & (th.t < kRayTInit)) { result = kTravHit; state = 0; nleaf = 0; }
-                else if (++tri == leaf_cnt[nleaf - 1]) { tri = 0; nleaf--; }
+                const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
+                const bool done = MODE == kAnyHit ? (th.hit & (th.t > kEps) & (th.t < kRayTInit)) : th.hit;
+                if (done) {
+                    if (MODE == kAnyHit) result = kTravHit;
+                    else { closest_pos = pos; tclosest = 0.0f; }
+                    state = 0; nleaf = 0;
+                } else if (++tri == leaf_cnt[li]) { tri = 0; li++; }
             }
         }
+        nleaf = 0;
         if (!__any_sync(kFullMask, state == 1)) break;
     }
     return result;
@@ -592,8 +615,9 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
             word = q * P.occ_words + (L.index >> 5); bit = L.index & 31u;
         }
         uint32_t budget = P.budget;
-        while (true) {                                                  // warp-uniform: traverse_any_hit is warp-synchronous
-            int res = traverse_any_hit<COUNT>(P, tr, active, budget, lc);
+        while (true) {                                                  // warp-uniform: traverse_early is warp-synchronous
+            float stc; uint32_t spos;
+            int res = traverse_early<kAnyHit, COUNT>(P, tr, active, budget, stc, spos, lc);
             bool again = false;
             if (active) {
                 if (res == kTravOverBudget) {
@@ -749,7 +773,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
         uint32_t budget = P.budget;
         while (true) {                                                  // warp-uniform: traverse is warp-synchronous
             float tc; uint32_t pos;
-            int res = traverse<kFirstLine, COUNT>(P, r, active, budget, tc, pos, lc);
+            int res = traverse_early<kFirstLine, COUNT>(P, r, active, budget, tc, pos, lc);
             bool again = false;
             if (active) {
                 if (res == kTravOverBudget) {
@@ -988,7 +1012,7 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
     }
     LocalCount lc; float tc, tc2; uint32_t pos, pos2;
     const bool first_line = r.t == 0.0f;
-    bool f = traverse<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc) == kTravHit;
+    bool f = traverse_early<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc) == kTravHit;
     bool f2 = traverse<kClosest, false>(P, tr, active && !first_line, 0xffffffffu, tc2, pos2, lc) == kTravHit;
     if (!active) return;
     if (!first_line) { f = f2; tc = tc2; pos = pos2; }
