@@ -459,7 +459,11 @@ def main():
                             "frac": frame_alg / (ms_per_step * 1e-3) / 1e9 / peak,
                             "bytes_per_ray": frame_alg / (counts["rays_primary"] + counts["rays_shadow"] + counts["rays_reflection"])},
             "reference_dfs_counts": {k: counts[k] for k in counts if k.startswith(("box_tests", "tri_tests"))},
-            "note": "the whole scene is L2-resident-sized (~140 MB vs 126 MB L2): DRAM traffic is far below the algorithmic figure; see profiles/",
+            "note": ("achieved = algorithmic bytes of the REFERENCE's walk (32 B per box test + 48 B per triangle test of its closest-hit DFS, "
+                     "SURVEY 8d) / kernel time: a throughput normalisation, not traffic.  The hot set (fp32 child pairs + fp32 triangles, 76 MB) is "
+                     "L2-resident and a shadow ray needs fewer tests than the reference's full closest-hit walk, so the figure can exceed the HBM peak; "
+                     "`traffic` is the measured DRAM bytes per launch (ncu, profiles/traffic.json).  The kernels are issue/latency bound: "
+                     "profiles/r01_ncu_traversal_*_final.txt"),
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(workload, fs, counts)
