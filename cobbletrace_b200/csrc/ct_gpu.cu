@@ -141,6 +141,7 @@ struct Params {
     uint32_t *fb_out;                            // where finished pixels are stored: fb, or the root GPU's fb (peer memory)
     unsigned long long *steal;                   // the tile's chunk cursor: local, or on the root GPU (peer memory)
     uint32_t chunk_shift;                        // log2(slots per chunk)
+    uint32_t steal_stride;                       // 1; R > 1 (option "emulate_ranks") takes every R-th chunk only: the share of one of R GPUs
     uint32_t *own_chunks;                        // chunk numbers this device took, in the order it took them
     uint32_t *dbg_found, *dbg_index; float *dbg_t;   // optional (CT_FLAG_KEEP_HITS), framebuffer layout
     // parked rays
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
         unsigned long long base = 0;
         uint32_t mine = 0;
         if (lane == 0) {
-            base = atomicAdd(P.steal, (unsigned long long)chunk);
+            base = atomicAdd(P.steal, (unsigned long long)chunk * P.steal_stride);
             if (base < P.n_slots) { mine = atomicAdd(&P.sched->own_count, 1u); P.own_chunks[mine] = (uint32_t)(base >> P.chunk_shift); }
         }
         base = __shfl_sync(kFullMask, base, 0);
@@ -1151,6 +1152,7 @@ DeviceState g_dev[kMaxDevices];
 std::mutex g_mutex;
 long long g_budget_option = 0;       // ct_gpu_set_option("traversal_budget"); 0 = default
 long long g_warp_budget_option = 0;  // ct_gpu_set_option("overflow_warp_budget"); 0 = default
+long long g_emulate_ranks = 0;       // ct_gpu_set_option("emulate_ranks"): profiling aid, see ct_gpu.h
 
 int check_device(int device) {
     int n = 0;
@@ -1496,6 +1498,8 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     // one device: its own cursor (zeroed with the rest of DevSched below) and framebuffer; shared frame: the root's
     p.steal = shared ? s.share_cursor : &p.sched->steal_local;
     p.chunk_shift = shared ? kChunkSharedShift : kChunkLocalShift;
+    p.steal_stride = g_emulate_ranks > 1 ? (uint32_t)g_emulate_ranks : 1u;
+    if (p.steal_stride > 1) p.chunk_shift = kChunkSharedShift;
     p.fb_out = shared ? s.share_fb : p.fb;
     Params pk = p; pk.max_depth = depth_max;   // with no reflective material the recursion never goes past depth 0 (:369)
     cudaStream_t st = s.stream;
@@ -1685,6 +1689,11 @@ int ct_gpu_set_option(const char *name, long long value) {
     if (!strcmp(name, "traversal_budget")) {
         if (value < 0) return fail(CT_ERR_INVALID, "traversal_budget must be >= 0 (0 = default)");
         g_budget_option = value;
+        return CT_OK;
+    }
+    if (!strcmp(name, "emulate_ranks")) {
+        if (value < 0 || value > 64) return fail(CT_ERR_INVALID, "emulate_ranks must be 0..64");
+        g_emulate_ranks = value;
         return CT_OK;
     }
     if (!strcmp(name, "overflow_warp_budget")) {

@@ -194,7 +194,10 @@ int ct_gpu_sync(int device);
  *   "traversal_budget"  node visits + triangle tests a shadow / reflection ray may spend in its own thread
  *                       before it is parked for k_overflow (0 = default 512), which gives it a whole warp and,
  *   "overflow_warp_budget"  after that many node visits (0 = default 32768), the whole grid (breadth-first).
- *                       Results never depend on either; tests set them low to push rays through those paths. */
+ *                       Results never depend on either; tests set them low to push rays through those paths.
+ *   "emulate_ranks"     R > 1: a profiling aid -- every render takes only every R-th chunk of the tile, i.e. the share
+ *                       one of R GPUs gets in a shared frame (the other pixels are simply not rendered); applies to
+ *                       the next render, 0 / 1 = off. */
 int ct_gpu_set_option(const char *name, long long value);
 
 /* Rays parked so far on `device` since upload (shadow and reflection rays whose DFS ran past the budget, e.g. the

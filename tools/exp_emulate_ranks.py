@@ -1,0 +1,24 @@
+"""Per-kernel times of ONE rank's share of a shared frame, emulated on one GPU (option "emulate_ranks")."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.argv = [sys.argv[0], "cube640"]
+import importlib.util
+from cobbletrace_b200 import api
+spec = importlib.util.spec_from_file_location("ps", os.path.join(os.path.dirname(os.path.abspath(__file__)), "perf_stages.py"))
+ps = importlib.util.module_from_spec(spec); spec.loader.exec_module(ps)
+mk, W, H, depth = ps.CASES["dragon4k"]
+fs = mk()
+for R in (1, 2, 4, 8):
+    api.set_option("emulate_ranks", R)
+    for flags, what in ((api.CT_FLAG_STAGE_TIMING, "serialised"), (0, "concurrent")):
+        r = api.GpuRenderer(0).upload(fs, W, H, max_depth=depth, flags=flags)
+        best = 1e9
+        for i in range(6):
+            r.render_tile(); r.sync()
+            if i >= 2: best = min(best, r.last_tile_ms())
+        line = f"ranks={R} {what}: {best:.3f} ms"
+        if flags:
+            line += "  " + " ".join(f"{nm}[{d}]={ms:.3f}" for nm, d, ms in r.last_tile_stages())
+        print(line, flush=True)
+        r.shutdown()
+api.set_option("emulate_ranks", 0)
