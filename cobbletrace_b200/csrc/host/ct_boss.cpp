@@ -7,8 +7,10 @@
 //     drives (one host thread per GPU), or a POSIX shared-memory counter when one process per GPU is
 //     used (torchrun): load balance follows the image content, no row is ever dropped;
 //   * completion is a stream synchronisation, not polling of `status` flags (:657-661);
-//   * finished tiles of GPUs other than devices[0] are copied to devices[0] over NVLink
-//     (ct_gpu_gather_rows -> cudaMemcpyPeerAsync) before the single readback.
+//   * with several GPUs in one process and no tile size given, the frame is ONE shared tile: the devices' own
+//     warps steal 64-pixel chunks from a cursor on devices[0] over NVLink and store finished pixels straight into
+//     its framebuffer (ct_gpu_render_shared); with a tile size, finished row tiles of the other GPUs are copied
+//     to devices[0] (ct_gpu_gather_rows -> cudaMemcpyPeerAsync) before the single readback.
 // libct_gpu.so is loaded with dlopen so this library also loads on machines without CUDA; rendering
 // then fails loudly (there is no CPU path).
 #include <dlfcn.h>
@@ -45,6 +47,10 @@ struct GpuApi {
     int (*get_counters)(int, ct_ray_counters *, int) = nullptr;
     int (*sync)(int) = nullptr;
     int (*gather_rows)(int, int, int, int) = nullptr;
+    int (*share_export)(int, ct_gpu_share *) = nullptr;
+    int (*share_attach)(int, const ct_gpu_share *) = nullptr;
+    int (*share_reset)(int) = nullptr;
+    int (*render_shared)(int, int, int, ct_ray_counters *) = nullptr;
     int (*shutdown)(int) = nullptr;
 
     void load(const std::string &path) {
@@ -67,6 +73,10 @@ struct GpuApi {
         get_counters = (int (*)(int, ct_ray_counters *, int))sym("ct_gpu_get_counters");
         sync = (int (*)(int))sym("ct_gpu_sync");
         gather_rows = (int (*)(int, int, int, int))sym("ct_gpu_gather_rows");
+        share_export = (int (*)(int, ct_gpu_share *))sym("ct_gpu_share_export");
+        share_attach = (int (*)(int, const ct_gpu_share *))sym("ct_gpu_share_attach");
+        share_reset = (int (*)(int))sym("ct_gpu_share_reset");
+        render_shared = (int (*)(int, int, int, ct_ray_counters *))sym("ct_gpu_render_shared");
         shutdown = (int (*)(int))sym("ct_gpu_shutdown");
         if (abi_version() != CT_GPU_ABI_VERSION) throw std::runtime_error("libct_gpu.so ABI version mismatch");
     }
@@ -81,6 +91,7 @@ struct Boss {
     GpuApi gpu;
     TileCounter counter;
     int tile_rows = 0, n_tiles = 0, y_lo = 0, y_hi = 0;
+    bool shared_frame = false;      // several GPUs of this process render ONE tile, stealing chunks on the device (ct_gpu_render_shared)
     std::vector<std::vector<std::pair<int, int>>> tiles_by_dev;   // last frame
     std::string error;
 };
@@ -121,6 +132,17 @@ Boss *boss_create(Scene *scene, const ct_host_boss_config *cfg) {
             if (total_devices == 1) rows = b->y_hi - b->y_lo;                        // one tile: whole frame in flight
             else rows = std::max(8, ((b->y_hi - b->y_lo) / (total_devices * 8) + 3) / 4 * 4);
         }
+        // Several GPUs in this process and no tile size asked for: one shared frame -- the devices' own warps steal
+        // 64-pixel chunks from a cursor on devices[0] over NVLink and store their pixels into its framebuffer.
+        b->shared_frame = !shared && cfg->n_devices > 1 && cfg->tile_rows <= 0 && !(cfg->flags & CT_FLAG_SUBSAMPLING);
+        if (b->shared_frame) {
+            rows = b->y_hi - b->y_lo;
+            ct_gpu_share h;
+            memset(&h, 0, sizeof h);
+            h.struct_size = sizeof h;
+            b->gpu.check(b->gpu.share_export(cfg->devices[0], &h), "ct_gpu_share_export");
+            for (int i = 1; i < cfg->n_devices; i++) b->gpu.check(b->gpu.share_attach(cfg->devices[i], &h), "ct_gpu_share_attach");
+        }
         b->tile_rows = rows;
         b->n_tiles = (b->y_hi - b->y_lo + rows - 1) / rows;
         b->tiles_by_dev.resize(cfg->n_devices);
@@ -153,9 +175,16 @@ void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *sta
     if (!shared) b->counter.reset();
     for (auto &v : b->tiles_by_dev) v.clear();
     std::vector<std::string> errs(nd);
+    if (b->shared_frame) b->gpu.check(b->gpu.share_reset(b->cfg.devices[0]), "ct_gpu_share_reset");
     auto worker = [&](int k) {
         try {
             const int dev = b->cfg.devices[k];
+            if (b->shared_frame) {                       // every device renders the same tile; the split happens on the devices
+                b->gpu.check(b->gpu.render_shared(dev, b->y_lo, b->y_hi, nullptr), "ct_gpu_render_shared");
+                b->tiles_by_dev[k].push_back({b->y_lo, b->y_hi});
+                b->gpu.check(b->gpu.sync(dev), "ct_gpu_sync");
+                return;
+            }
             while (true) {
                 int t = b->counter.next();
                 if (t >= b->n_tiles) break;

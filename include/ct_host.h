@@ -7,8 +7,8 @@
  *   ct_host_build_bvh       GetSceneTriangles + InitializeBVHState + BuildBVH  raythread.cpp:621, bvh.cpp:16,108
  *   ct_host_camera_rotation the camera matrix of HandleUpdates               raythread.cpp:564-572
  *   ct_host_boss_*          RayThread's boss half: dispatch row tiles, wait, hand back the bitmap
- *                           (raythread.cpp:641-666, 546-594) -- workers are ct_gpu_render_tile calls on
- *                           one or more GPUs, with dynamic tile stealing instead of the static yStep split.
+ *                           (raythread.cpp:641-666, 546-594) -- workers are ct_gpu_render_tile / ct_gpu_render_shared
+ *                           calls on one or more GPUs, with dynamic stealing instead of the static yStep split.
  *
  * All functions are thread-compatible (one thread per object).  Errors: NULL / negative return and a
  * message via ct_host_last_error(); nothing asserts or exits (the reference's parser asserts).
@@ -83,7 +83,8 @@ typedef struct ct_host_boss_config {
     uint32_t flags;               /* CT_FLAG_* */
     int32_t n_devices;            /* GPUs driven by THIS process (one host thread each) */
     int32_t devices[16];
-    int32_t tile_rows;            /* rows per stolen tile; <= 0 picks a default */
+    int32_t tile_rows;            /* rows per stolen tile; <= 0: one GPU renders the frame as one tile, several GPUs of this
+                                     process share ONE tile (device-side chunk stealing, ct_gpu_render_shared) */
     /* Optional cross-process tile stealing (one process per GPU): name of a POSIX shared-memory
      * counter shared by all ranks of the job, or NULL/"" for a process-local counter. */
     const char *shared_counter_name;

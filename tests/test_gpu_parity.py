@@ -392,6 +392,23 @@ def test_boss_matches_direct_calls(scene_loader):
         b.close()
 
 
+def test_boss_two_gpus_in_one_process(scene_loader):
+    """ct_host_boss over two devices of this process: one shared frame (device-side chunk stealing, peer stores into
+    devices[0]) and the row-tile variant (host-side counter, peer copies).  Needs a box with >= 2 GPUs."""
+    if ct.api.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    fs = scene_loader("scene_import_bunny").with_reflection(0.5)
+    W, H = 640, 480
+    oframe, _, _ = O.OracleScene(fs).render(W, H, max_depth=2, want_hits=False)
+    hs = host.HostScene.from_flat(fs.without_bvh())
+    for tile_rows in (0, 32):
+        b = host.Boss(hs, W, H, devices=(0, 1), max_depth=2, tile_rows=tile_rows)
+        for _ in range(2):
+            bitmap, stats = b.render(np.zeros((H, W), np.uint32))
+            assert np.array_equal(bitmap, oframe), tile_rows
+        b.close()
+
+
 @pytest.mark.parametrize("W,H", [(3840, 2160)])
 def test_dragon_class_full_size(tmp_path_factory, W, H, gpu):
     """BASELINE config 3 at full size: procedural 868k-triangle stand-in, forced reflection, depth 2."""
