@@ -259,6 +259,13 @@ enum { kTravMiss = 0, kTravHit = 1, kTravOverBudget = -1 };
 
 constexpr uint32_t kFullMask = 0xffffffffu;
 
+// Build-time bounds checks (-DCT_DEBUG_BOUNDS=1; compute-sanitizer is not available on every pool): trap with a message.
+#if defined(CT_DEBUG_BOUNDS) && CT_DEBUG_BOUNDS
+#define CT_CHECK(cond) do { if (!(cond)) { printf("CT_CHECK failed: %s (line %d)\n", #cond, __LINE__); __trap(); } } while (0)
+#else
+#define CT_CHECK(cond) do { } while (0)
+#endif
+
 // IntersectBVHClosest (bvh.cpp:198-222) as an explicit-stack DFS in the reference's visit order (left subtree,
 // then right).  The reference tests a node's box when it VISITS the node; here both children of a passing
 // interior node are fetched and tested together (one 64-byte fetch, two independent slab tests in flight):
@@ -328,6 +335,7 @@ CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget
                     bool hit_l, hit_r; float r_lo, r_hi;
                     pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
                     if (hit_l & hit_r) {
+                        CT_CHECK(sp < kStackMax);
                         stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt;
                         if (MODE == kClosest) { stk_lo[sp] = r_lo; stk_hi[sp] = r_hi; stk_src[sp] = cur_ref; }
                         sp++;
@@ -400,16 +408,18 @@ CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uin
             if ((state == 1) & (nleaf < kLeafList)) {
                 bool descend = false;
                 if (cur_cnt > 0) {
+                    CT_CHECK(nleaf < kLeafList && cur_ref + cur_cnt <= P.n_tri);
                     leaf_ref[nleaf] = cur_ref; leaf_cnt[nleaf] = cur_cnt; nleaf++;
                     spent += cur_cnt;
                 } else {
+                    CT_CHECK(cur_ref < P.n_pairs);
                     DevPair32 pr;
                     load_pair32(P.pairs32, cur_ref, pr);
                     if (COUNT) lc.box += 2;
                     spent += 2u;
                     bool hit_l, hit_r; float r_lo, r_hi;
                     pair_accept<COUNT, MODE == kAnyHit>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
-                    if (hit_l & hit_r) { stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt; sp++; }
+                    if (hit_l & hit_r) { CT_CHECK(sp < kStackMax); stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt; sp++; }
                     descend = hit_l | hit_r;
                     cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
                 }
@@ -552,7 +562,11 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
         uint32_t mine = 0;
         if (lane == 0) {
             base = atomicAdd(P.steal, (unsigned long long)chunk * P.steal_stride);
-            if (base < P.n_slots) { mine = atomicAdd(&P.sched->own_count, 1u); P.own_chunks[mine] = (uint32_t)(base >> P.chunk_shift); }
+            if (base < P.n_slots) {
+                mine = atomicAdd(&P.sched->own_count, 1u);
+                CT_CHECK(mine <= (P.cap >> kChunkLocalShift));
+                P.own_chunks[mine] = (uint32_t)(base >> P.chunk_shift);
+            }
         }
         base = __shfl_sync(kFullMask, base, 0);
         mine = __shfl_sync(kFullMask, mine, 0);
@@ -572,6 +586,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
             bool found = traverse<kClosest, COUNT>(P, r, active, 0xffffffffu, tc, pos, lc) == kTravHit;   // warp-synchronous
             if (!active) continue;
             n_rays++;
+            CT_CHECK(slot < P.cap && q < P.cap);
             P.hit0_t[slot] = tc;
             P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
             if (found) clear_occ(P, q);
@@ -681,6 +696,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_emit(const __grid_constant__ 
             qbase = __shfl_sync(0xffffffffu, qbase, leader);
             if (emit) {
                 uint32_t nq = qbase + __popc(mask & ((1u << lane) - 1u));
+                CT_CHECK(nq < P.cap && slot < P.cap);
                 double2 *rb = reinterpret_cast<double2 *>(P.ray_buf[nxt] + 6ull * nq);
                 rb[0] = make_double2(position.x, position.y);
                 rb[1] = make_double2(position.z, rdir.x);
