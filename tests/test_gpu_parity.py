@@ -392,6 +392,43 @@ def test_boss_matches_direct_calls(scene_loader):
         b.close()
 
 
+def _soup_scene(rng, n_tri, spread, size, reflection, same_centroid=False):
+    """Random triangle soup in front of a camera at the origin looking down +z (cobbletrace.cpp's default frame)."""
+    from cobbletrace_b200.sceneio import FlatScene, LT_AMBIENT, LT_POINT, LT_DIRECTIONAL
+    c = rng.normal(size=(n_tri, 3)) * spread + np.array([0.0, 0.0, 6.0])
+    if same_centroid:
+        c[:] = c[0]                                              # BuildBVH cannot split: one big leaf at the root
+    a, b = rng.normal(size=(n_tri, 3)) * size, rng.normal(size=(n_tri, 3)) * size
+    tri = np.concatenate([c - (a + b) / 3, c - (a + b) / 3 + a, c - (a + b) / 3 + b], 1)
+    return FlatScene(tri=tri, mat_color=rng.integers(0x202020, 0xffffff, n_tri).astype(np.uint32),
+                     mat_specular=rng.choice(np.array([-1, 0, 10, 500], np.int32), n_tri),
+                     mat_reflection=np.where(rng.random(n_tri) < 0.5, reflection, 0.0).astype(np.float32),
+                     light_type=np.array([LT_AMBIENT, LT_POINT, LT_DIRECTIONAL], np.int32), light_intensity=np.array([0.2, 0.6, 0.3], np.float32),
+                     light_pos=np.array([[0, 0, 0], [3.0, 5.0, -2.0], [0, 0, 0]]), light_dir=np.array([[0, 0, 0], [0, 0, 0], [1.0, 4.0, -4.0]]),
+                     cam_pos=np.zeros(3), cam_rot=np.eye(3).reshape(9))
+
+
+@pytest.mark.parametrize("n_tri,same_centroid", [(1, False), (2, False), (3, False), (40, True), (700, False)])
+def test_small_and_degenerate_trees_against_oracle(n_tri, same_centroid, gpu):
+    """Trees the bundled scenes never produce: a root that is a leaf (1-2 triangles, or 40 triangles with one common
+    centroid that BuildBVH cannot split), a 3-triangle tree, and a soup with heavy overlap -- each with mirrors."""
+    rng = np.random.default_rng(100 + n_tri)
+    fs = _soup_scene(rng, n_tri, spread=1.2, size=1.5, reflection=0.6, same_centroid=same_centroid)
+    fs = host.HostScene.from_flat(fs).to_flat(with_bvh=True)
+    if n_tri <= 2 or same_centroid:
+        assert fs.n_nodes == 1 and int(fs.node_count[0]) == n_tri
+    W, H = 96, 80
+    oframe, ohits, _ = O.OracleScene(fs).render(W, H, max_depth=4)
+    for budget in (0, 8):                                        # 8: nearly every early-exit ray goes through k_overflow
+        ct.api.set_option("traversal_budget", budget)
+        try:
+            gpu.upload(fs, W, H, max_depth=4, flags=DBG)
+            gpu.render_tile()
+            assert_same(gpu, oframe, ohits, f"soup n={n_tri} budget={budget}")
+        finally:
+            ct.api.set_option("traversal_budget", 0)
+
+
 def test_boss_two_gpus_in_one_process(scene_loader):
     """ct_host_boss over two devices of this process: one shared frame (device-side chunk stealing, peer stores into
     devices[0]) and the row-tile variant (host-side counter, peer copies).  Needs a box with >= 2 GPUs."""
