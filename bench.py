@@ -32,6 +32,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Mrays/s (primary+shadow+reflection) dragon-class 4K, shadows + 2 reflection bounces"
+
+
+def metric_name(workload_key: str) -> str:
+    return METRIC if workload_key.startswith("dragon") else f"Mrays/s (primary+shadow+reflection), workload {workload_key}"
+
+
+def data_note(kind: str) -> str:
+    if kind == "dragon":
+        return "synthetic (procedural 868352-triangle octa-sphere stand-in for the missing dragon.ply, generated in-run)"
+    return "bundled reference scene (tests/golden flattened copy of the reference's own scene file and meshes)"
 REFLECTION = 0.5
 
 WORKLOADS = {
@@ -40,7 +50,14 @@ WORKLOADS = {
                  "3840x2160 (traced square 2160^2), shadows + 2 reflection bounces", "dragon", 3840, 2160, 2, REFLECTION),
     "dragon8k": ("configs[4]: same scene at 7680x4320 (traced square 4320^2)", "dragon", 7680, 4320, 2, REFLECTION),
     "dragon1080": ("reduced sample of configs[2]: same scene at 1920x1080", "dragon", 1920, 1080, 2, REFLECTION),
+    # the other BASELINE configs (parity-test cases; here for measurement on request, never the default)
+    "cube640": ("configs[0]: scene_file_cube.json (37 triangles, 3 lights, one mirror) 640x640, depth 10", "golden:scene_file_cube", 640, 640, 10, None),
+    "import640": ("configs[0]: scene_import.json (roundedCube.obj x4, 1712 triangles) 640x640, depth 10", "golden:scene_import", 640, 640, 10, None),
+    "bunny1080": ("configs[1]: scene_import_bunny.json (69451 triangles) 1920x1080 (traced square 1080^2), shadow rays", "golden:scene_import_bunny", 1920, 1080, 10, None),
+    "pcbig1080": ("configs[3]: utils/pc_big.json (6468 triangles, 66 lights from sphereOfLights) 1920x1080, any-hit bound", "golden:pc_big", 1920, 1080, 10, None),
 }
+GOLDEN_JSON = {"scene_file_cube": "scene_file_cube.json", "scene_import": "scene_import.json", "scene_import_bunny": "scene_import_bunny.json",
+               "pc_big": "pc_big.json"}
 
 
 def log(*a):
@@ -54,9 +71,42 @@ def scene_cache_dir() -> str:
 
 
 def ensure_scene(kind: str):
+    """(scene file the reference's parser can read, triangle count).  dragon: generated; golden:<name>: the reference's own
+    scene file as copied next to the compiled reference (oracle/_ref/scenes), triangle count from tests/golden."""
     from cobbletrace_b200 import procedural
-    assert kind == "dragon"
-    return procedural.write_dragon_standin(scene_cache_dir())
+    if kind == "dragon":
+        return procedural.write_dragon_standin(scene_cache_dir())
+    from oracle import ct_oracle_py as O
+    name = kind.split(":", 1)[1]
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["scenes"][name]
+    return os.path.join(O.REF_DIR, "scenes", GOLDEN_JSON[name]), int(meta["n_tri"])
+
+
+def scene_dir(kind: str) -> str:
+    """Directory the reference must run in so that the scene's relative model paths resolve."""
+    if kind == "dragon":
+        return scene_cache_dir()
+    from oracle import ct_oracle_py as O
+    return os.path.join(O.REF_DIR, "scenes")
+
+
+def load_host_scene(kind: str, refl):
+    """The product's host scene for a workload: parsed by the product's own parser (dragon) or rebuilt from the
+    flattened golden scene (the bundled scenes; tests prove both routes give the reference's triangles and BVH)."""
+    import cobbletrace_b200 as ct
+    from cobbletrace_b200 import host
+    t0 = time.time()
+    if kind == "dragon":
+        path, _ = ensure_scene(kind)
+        hs = host.HostScene.load(path, base_dir=scene_cache_dir())
+    else:
+        name = kind.split(":", 1)[1]
+        meta = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["scenes"][name]
+        hs = host.HostScene.from_flat(ct.load_ctscene(os.path.join(ROOT, "tests", "golden", meta["file"])).without_bvh())
+    load_ms = (time.time() - t0) * 1e3
+    if refl is not None:
+        hs.set_reflection(refl)
+    return hs, load_ms
 
 
 def host_cores() -> int:
@@ -133,7 +183,9 @@ def run_ref_cpu(scene_json, chdir, W, H, depth, refl, threads, frames, warmup, t
     from oracle import ct_oracle_py as O
     exe = os.path.join(O.REF_DIR, "ct_ref")
     cmd = [exe, "--scene", scene_json, "--chdir", chdir, "--width", str(W), "--height", str(H), "--depth", str(depth), "--threads", str(threads),
-           "--force-reflection", repr(float(refl)), "--time", str(frames), "--warmup", str(warmup)]
+           "--time", str(frames), "--warmup", str(warmup)]
+    if refl is not None:
+        cmd += ["--force-reflection", repr(float(refl))]
     out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=timeout).stdout
     return json.loads(out.strip().splitlines()[-1])
 
@@ -149,14 +201,14 @@ def cpu_baseline(workload, fs, counts_full, budget_s=25.0):
         # calibrate on a 1/16-area frame, then choose the largest sample that fits the budget (frame cost ~ pixels)
         w, h = W // 4, H // 4
         thr = ref_threads(h, cores)
-        cal = run_ref_cpu(os.path.basename(scene_path), scene_cache_dir(), w, h, depth, refl, thr, 1, 0)
+        cal = run_ref_cpu(os.path.basename(scene_path), scene_dir(kind), w, h, depth, refl, thr, 1, 0)
         est_full = cal["best_ms"] * 16 / 1e3
         scale = 1
         while est_full / (scale * scale) > budget_s and scale < 8:
             scale *= 2
         w, h = W // scale, H // scale
         thr = ref_threads(h, cores)
-        r = run_ref_cpu(os.path.basename(scene_path), scene_cache_dir(), w, h, depth, refl, thr, 2, 0)
+        r = run_ref_cpu(os.path.basename(scene_path), scene_dir(kind), w, h, depth, refl, thr, 2, 0)
         rays = rays_full / (scale * scale)          # ray counts scale with the pixel count (same view, same scene)
         if scale > 1:
             c = oracle_counts(fs, w, h, depth)
@@ -187,20 +239,19 @@ def reference_arm(args):
     desc, kind, W, H, depth, refl = workload
     scene_path, n_tri = ensure_scene(kind)
     cores = host_cores()
-    hs = host.HostScene.load(scene_path, base_dir=scene_cache_dir())
-    hs.set_reflection(refl)
+    hs, _ = load_host_scene(kind, refl)
     fs = hs.to_flat(with_bvh=True)
     steps, warm = args.steps, args.warmup
     if O.ref_available():
         w, h = W // 4, H // 4
-        cal = run_ref_cpu(os.path.basename(scene_path), scene_cache_dir(), w, h, depth, refl, ref_threads(h, cores), 1, 0)
+        cal = run_ref_cpu(os.path.basename(scene_path), scene_dir(kind), w, h, depth, refl, ref_threads(h, cores), 1, 0)
         est = cal["best_ms"] * 16 / 1e3 * (steps + warm + 1)
         scale = 1
         while est / (scale * scale) > 200 and scale < 8:
             scale *= 2
         w, h = W // scale, H // scale
         thr = ref_threads(h, cores)
-        r = run_ref_cpu(os.path.basename(scene_path), scene_cache_dir(), w, h, depth, refl, thr, steps, warm)
+        r = run_ref_cpu(os.path.basename(scene_path), scene_dir(kind), w, h, depth, refl, thr, steps, warm)
         ms = r["mean_ms"]
         kind_s, used = "reference", thr
         sample = (f"each step = one {w}x{h} frame ({'the full workload' if scale == 1 else f'1/{scale * scale} of the pixels'}) through the reference's "
@@ -220,9 +271,9 @@ def reference_arm(args):
     rays = c["rays_primary"] + c["rays_shadow"] + c["rays_reflection"]
     value = rays / ms / 1e3
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64/f32 mixed (reference arithmetic)",
-        "data": "synthetic (procedural dragon stand-in, generated in-run)",
+        "data": data_note(kind),
         "config": {"workload": desc, "sample": sample, "triangles": n_tri},
         "rays_per_step": {k: c[k] for k in ("rays_primary", "rays_shadow", "rays_reflection")},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": used, "kind": kind_s, "sample": sample},
@@ -273,10 +324,7 @@ def main():
     if N > 1:
         dist.barrier()
     scene_path, n_tri = ensure_scene(kind)
-    t0 = time.time()
-    hs = host.HostScene.load(scene_path, base_dir=scene_cache_dir())
-    load_ms = (time.time() - t0) * 1e3
-    hs.set_reflection(refl)
+    hs, load_ms = load_host_scene(kind, refl)
     t0 = time.time(); n_nodes = hs.build_bvh(); bvh_ms = (time.time() - t0) * 1e3
     t0 = time.time()
     stream = torch.cuda.Stream(device=dev)
@@ -382,11 +430,11 @@ def main():
     value = rays_total / ms_per_step / 1e3
     traced_px = rays_primary
     line = {
-        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": N, "steps": steps, "warmup": warm,
+        "metric": metric_name(args.workload), "value": value, "unit": "Mrays/s", "n_gpus": N, "steps": steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64/f32 mixed (the reference's arithmetic, reproduced bit-exactly)",
-        "data": "synthetic (procedural 868352-triangle octa-sphere stand-in for the missing dragon.ply, generated in-run)",
-        "config": {"workload": desc, "triangles": n_tri, "bvh_nodes": n_nodes, "lights": 3, "max_depth": depth, "forced_reflection": refl,
+        "data": data_note(kind),
+        "config": {"workload": desc, "triangles": n_tri, "bvh_nodes": n_nodes, "lights": int(hs.to_flat(with_bvh=False).n_lights), "max_depth": depth, "forced_reflection": refl,
                    "l2": "flushed between timed steps (256 MiB device write, outside the timed events)",
                    "timing": "CUDA events on the launching stream around each frame's kernels" + ("; max over ranks per step (pixels land in GPU 0's framebuffer inside those kernels)" if N > 1 else ""),
                    "tiles_per_frame": st["tiles_total"],
