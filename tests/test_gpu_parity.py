@@ -164,6 +164,7 @@ def test_golden_frames_from_reference(case, golden, scene_loader, gpu):
     ("scene_import", 640, 640, 10, None),             # config 1b: leaves of up to 54 triangles
     ("scene_import_bunny", 1920, 1080, 10, None),     # config 2
     ("pc_big", 640, 640, 10, None),                   # config 4 scene (66 lights, any-hit bound)
+    ("pc_big", 1920, 1080, 10, None),                 # config 4 at BASELINE's size
     ("scene_import_bunny", 1000, 700, 2, 0.5),        # config-3-like: forced reflection, depth 2
     ("scene_file_cube", 333, 517, 10, 0.9),           # W < H, odd sizes, everything reflective to full depth
     ("scene_file_cube", 401, 301, 10, 0.9),           # odd H, W > H: no pixel is dropped, all counters comparable
@@ -446,9 +447,10 @@ def test_boss_two_gpus_in_one_process(scene_loader):
         b.close()
 
 
-@pytest.mark.parametrize("W,H", [(3840, 2160)])
+@pytest.mark.parametrize("W,H", [(3840, 2160), (7680, 4320)])
 def test_dragon_class_full_size(tmp_path_factory, W, H, gpu):
-    """BASELINE config 3 at full size: procedural 868k-triangle stand-in, forced reflection, depth 2."""
+    """BASELINE configs 3 (4K) and 5 (8K, here on one GPU, cut into row tiles) at full size: procedural 868k-triangle
+    stand-in, forced reflection, depth 2."""
     d = os.environ.get("CT_SCENE_CACHE") or str(tmp_path_factory.mktemp("dragon"))
     scene, n = procedural.write_dragon_standin(d)
     hs = host.HostScene.load(scene, base_dir=d)
@@ -459,8 +461,8 @@ def test_dragon_class_full_size(tmp_path_factory, W, H, gpu):
     ctr = gpu.render_tile(counters=True)
     full = gpu.readback()
     # property 1: oracle agreement at full size (bit-exact)
-    oframe, ohits, octr = O.OracleScene(fs).render(W, H, max_depth=2)
-    assert_same(gpu, oframe, ohits, "dragon stand-in 4K")
+    oframe, ohits, octr = O.OracleScene(fs).render(W, H, max_depth=2, n_threads=os.cpu_count() or 8)
+    assert_same(gpu, oframe, ohits, f"dragon stand-in {W}x{H}")
     # property 2: tile-split invariance (what multi-GPU row tiles rely on)
     gpu.upload(fs, W, H, max_depth=2)
     y0, y1 = gpu.full_range()
