@@ -383,7 +383,10 @@ CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget
 // and after the walk; kFirstLine stops at the first pass of a phase (every leaf before it has been tested).
 // WARP-SYNCHRONOUS like traverse().  Returns kTravHit (kAnyHit: occluded; kFirstLine: always -- `found` is
 // 0 != 1e30f, raythread.cpp:227 -- with closest_pos = kNoPos when nothing passed), kTravMiss or kTravOverBudget.
-constexpr int kLeafList = 12;
+#ifndef CT_LEAF_LIST
+#define CT_LEAF_LIST 8
+#endif
+constexpr int kLeafList = CT_LEAF_LIST;       // deferred leaves per lane before a leaf phase is forced
 template <TraverseMode MODE, bool COUNT>
 CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
     static_assert(MODE != kClosest, "closest-hit rays use traverse");
