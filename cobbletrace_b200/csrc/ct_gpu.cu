@@ -35,7 +35,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
+#include <cstdlib>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 
@@ -1212,6 +1215,18 @@ int dev_alloc(DeviceState &s, T **out, size_t count, bool zero = false) {
 
 #define TRY(expr) do { int rc_ = (expr); if (rc_ != CT_OK) return rc_; } while (0)
 
+// fn(begin, end, worker) over [0, n) on up to `max_threads` host threads (upload-time array conversion)
+template <typename F>
+void parallel_for(uint32_t n, int max_threads, F fn) {
+    int nt = (int)std::min<uint64_t>((uint64_t)std::max(max_threads, 1), (n + 65535u) / 65536u);
+    if (nt <= 1) { fn(0u, n, 0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([=] { fn((uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt), t); });
+    for (auto &t : th) t.join();
+}
+constexpr int kHostThreads = 16;
+
 // depth of the reference's DFS (stack entries needed) -- iterative to survive degenerate trees
 int bvh_depth(const ct_bvh_node *nodes, uint32_t n_nodes, uint32_t n_tri, bool *ok) {
     std::vector<std::pair<uint32_t, int>> st;
@@ -1296,6 +1311,11 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     s.p.warp_budget = g_warp_budget_option > 0 ? (uint32_t)std::min<long long>(g_warp_budget_option, 1ll << 30) : kWarpBudget;
     s.flags = d->flags;
 
+    const bool timing = getenv("CT_GPU_TIMING") != nullptr;
+    auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now_ms();
+    double t_mark = t_begin;
+    auto lap = [&](const char *what) { if (timing) { double t = now_ms(); fprintf(stderr, "ct_gpu_upload_scene: %-28s %7.1f ms\n", what, t - t_mark); t_mark = t; } };
     Params &p = s.p;
     p.n_tri = d->n_triangles; p.n_lights = d->n_lights;
     // nodes: reference layout -> per-interior-node child pairs (fp32 for the filter, fp64 for the exact path)
@@ -1312,24 +1332,35 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
         cnt = n.triangle_count;
         ref = cnt ? n.first_triangle_index : pid_of[c];
     };
-    for (uint32_t i = 0; i < d->n_nodes; i++) {
-        const ct_bvh_node &n = d->nodes[i];
-        for (int a = 0; a < 3; a++) {
-            // the filter needs finite, ordered boxes (box_filter picks near/far by the ray's sign)
-            if (!(n.aabb_min[a] <= n.aabb_max[a]) || !std::isfinite(n.aabb_min[a]) || !std::isfinite(n.aabb_max[a])) boxes_ok = false;
-            bound[a] = std::max(bound[a], std::max(std::fabs(n.aabb_min[a]), std::fabs(n.aabb_max[a])));
+    {
+        double part_bound[kHostThreads][3] = {};
+        bool part_ok[kHostThreads];
+        for (bool &b : part_ok) b = true;
+        parallel_for(d->n_nodes, kHostThreads, [&](uint32_t i0, uint32_t i1, int w) {
+            for (uint32_t i = i0; i < i1; i++) {
+                const ct_bvh_node &n = d->nodes[i];
+                for (int a = 0; a < 3; a++) {
+                    // the filter needs finite, ordered boxes (box_filter picks near/far by the ray's sign)
+                    if (!(n.aabb_min[a] <= n.aabb_max[a]) || !std::isfinite(n.aabb_min[a]) || !std::isfinite(n.aabb_max[a])) part_ok[w] = false;
+                    part_bound[w][a] = std::max(part_bound[w][a], std::max(std::fabs(n.aabb_min[a]), std::fabs(n.aabb_max[a])));
+                }
+                if (n.triangle_count != 0) continue;
+                const ct_bvh_node &L = d->nodes[n.left_node], &R = d->nodes[n.left_node + 1];
+                DevPair32 &p32 = pairs32[pid_of[i]];
+                DevPair64 &p64 = pairs64[pid_of[i]];
+                for (int a = 0; a < 3; a++) {
+                    p64.lmin[a] = L.aabb_min[a]; p64.lmax[a] = L.aabb_max[a]; p64.rmin[a] = R.aabb_min[a]; p64.rmax[a] = R.aabb_max[a];
+                    p32.lmin[a] = (float)L.aabb_min[a]; p32.lmax[a] = (float)L.aabb_max[a];
+                    p32.rmin[a] = (float)R.aabb_min[a]; p32.rmax[a] = (float)R.aabb_max[a];
+                }
+                child_ref(n.left_node, p32.l_ref, p32.l_cnt);
+                child_ref(n.left_node + 1, p32.r_ref, p32.r_cnt);
+            }
+        });
+        for (int w = 0; w < kHostThreads; w++) {
+            boxes_ok = boxes_ok && part_ok[w];
+            for (int a = 0; a < 3; a++) bound[a] = std::max(bound[a], part_bound[w][a]);
         }
-        if (n.triangle_count != 0) continue;
-        const ct_bvh_node &L = d->nodes[n.left_node], &R = d->nodes[n.left_node + 1];
-        DevPair32 &p32 = pairs32[pid_of[i]];
-        DevPair64 &p64 = pairs64[pid_of[i]];
-        for (int a = 0; a < 3; a++) {
-            p64.lmin[a] = L.aabb_min[a]; p64.lmax[a] = L.aabb_max[a]; p64.rmin[a] = R.aabb_min[a]; p64.rmax[a] = R.aabb_max[a];
-            p32.lmin[a] = (float)L.aabb_min[a]; p32.lmax[a] = (float)L.aabb_max[a];
-            p32.rmin[a] = (float)R.aabb_min[a]; p32.rmax[a] = (float)R.aabb_max[a];
-        }
-        child_ref(n.left_node, p32.l_ref, p32.l_cnt);
-        child_ref(n.left_node + 1, p32.r_ref, p32.r_cnt);
     }
     for (int a = 0; a < 3; a++) {
         p.bound[a] = (boxes_ok && bound[a] < 1e30) ? bound[a] : INFINITY;
@@ -1337,38 +1368,51 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     }
     child_ref(0, p.root_ref, p.root_cnt);
     p.n_pairs = n_pairs;
+    lap("pairs (host)");
     // triangles in leaf order with precomputed edges
     std::vector<DevTri> tris(d->n_triangles);
     std::vector<DevTri32> tris32(d->n_triangles);
     uint32_t pos0 = kNoPos;
     const unsigned char *tbase = static_cast<const unsigned char *>(d->triangles);
-    for (uint32_t pos = 0; pos < d->n_triangles; pos++) {
-        uint32_t k = d->tri_indexes[pos];
-        if (k >= d->n_triangles) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes[%u] = %u out of range", pos, k); }
-        if (k == 0) pos0 = pos;
-        double v[9];
-        memcpy(v, tbase + (size_t)k * d->triangle_stride, sizeof v);
-        for (int a = 0; a < 3; a++) {
-            tris[pos].p1[a] = v[a];
-            tris[pos].e1[a] = v[3 + a] - v[a];
-            tris[pos].e2[a] = v[6 + a] - v[a];
-        }
-        tris[pos].orig = k; tris[pos].pad = 0;
-        {   // fp32 copy + magnitudes for tri_filter_miss (rounded up; NaN k1 = "never certify")
-            DevTri32 &t32 = tris32[pos];
-            double k1 = 0, k2 = 0, k3 = 0;
-            for (int a = 0; a < 3; a++) {
-                t32.p1[a] = (float)tris[pos].p1[a]; t32.e1[a] = (float)tris[pos].e1[a]; t32.e2[a] = (float)tris[pos].e2[a];
-                k3 = std::max(k3, std::fabs(tris[pos].p1[a])); k1 = std::max(k1, std::fabs(tris[pos].e1[a])); k2 = std::max(k2, std::fabs(tris[pos].e2[a]));
+    {
+        uint32_t part_pos0[kHostThreads], part_bad[kHostThreads];
+        bool part_refl[kHostThreads];
+        for (int w = 0; w < kHostThreads; w++) { part_pos0[w] = kNoPos; part_bad[w] = kNoPos; part_refl[w] = false; }
+        parallel_for(d->n_triangles, kHostThreads, [&](uint32_t q0, uint32_t q1, int w) {
+            for (uint32_t pos = q0; pos < q1; pos++) {
+                uint32_t k = d->tri_indexes[pos];
+                if (k >= d->n_triangles) { part_bad[w] = pos; return; }
+                if (k == 0) part_pos0[w] = pos;
+                double v[9];
+                memcpy(v, tbase + (size_t)k * d->triangle_stride, sizeof v);
+                for (int a = 0; a < 3; a++) {
+                    tris[pos].p1[a] = v[a];
+                    tris[pos].e1[a] = v[3 + a] - v[a];
+                    tris[pos].e2[a] = v[6 + a] - v[a];
+                }
+                tris[pos].orig = k; tris[pos].pad = 0;
+                // fp32 copy + magnitudes for tri_filter_miss (rounded up; NaN k1 = "never certify")
+                DevTri32 &t32 = tris32[pos];
+                double k1 = 0, k2 = 0, k3 = 0;
+                for (int a = 0; a < 3; a++) {
+                    t32.p1[a] = (float)tris[pos].p1[a]; t32.e1[a] = (float)tris[pos].e1[a]; t32.e2[a] = (float)tris[pos].e2[a];
+                    k3 = std::max(k3, std::fabs(tris[pos].p1[a])); k1 = std::max(k1, std::fabs(tris[pos].e1[a])); k2 = std::max(k2, std::fabs(tris[pos].e2[a]));
+                }
+                auto up = [](double x) { float f = (float)x; return ((double)f < x) ? std::nextafterf(f, INFINITY) : f; };
+                const bool in_range = k1 >= 0x1p-30 && k1 <= 0x1p30 && k2 >= 0x1p-30 && k2 <= 0x1p30 && k3 <= 0x1p40;   // NaNs fail
+                t32.k1 = in_range ? up(k1) : NAN; t32.k2 = up(k2); t32.k3 = up(k3);
+                if (d->materials[k].reflection > 0.0f) part_refl[w] = true;
             }
-            auto up = [](double x) { float f = (float)x; return ((double)f < x) ? std::nextafterf(f, INFINITY) : f; };
-            const bool in_range = k1 >= 0x1p-30 && k1 <= 0x1p30 && k2 >= 0x1p-30 && k2 <= 0x1p30 && k3 <= 0x1p40;   // NaNs fail
-            t32.k1 = in_range ? up(k1) : NAN; t32.k2 = up(k2); t32.k3 = up(k3);
+        });
+        for (int w = 0; w < kHostThreads; w++) {
+            if (part_bad[w] != kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes[%u] = %u out of range", part_bad[w], d->tri_indexes[part_bad[w]]); }
+            if (part_pos0[w] != kNoPos) pos0 = part_pos0[w];
+            if (part_refl[w]) s.any_reflective = true;
         }
-        if (d->materials[k].reflection > 0.0f) s.any_reflective = true;
     }
     if (pos0 == kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes is not a permutation (triangle 0 missing)"); }
     p.pos_of_tri0 = pos0;
+    lap("triangles (host)");
     std::vector<DevLight> lights(std::max<uint32_t>(d->n_lights, 1));
     for (uint32_t i = 0; i < d->n_lights; i++) {
         lights[i].type = d->lights[i].type; lights[i].intensity = d->lights[i].intensity;
@@ -1401,7 +1445,8 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     CU(cudaMemcpy(dt, tris.data(), tris.size() * sizeof(DevTri), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dm, d->materials, (size_t)d->n_triangles * sizeof(ct_material), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dl, lights.data(), lights.size() * sizeof(DevLight), cudaMemcpyHostToDevice));
-    p.pairs32 = dp32; p.pairs64 = dp64; p.tris = dt; p.materials = dm; p.lights = dl;
+    p.pairs32 = dp32; p.pairs64 = dp64; p.tris = dt;
+    lap("scene arrays to the device"); p.materials = dm; p.lights = dl;
 
     memcpy(p.cam, d->camera_position, sizeof p.cam);
     memcpy(p.rot, d->camera_rotation, sizeof p.rot);
@@ -1470,6 +1515,8 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     }
     TRY(dev_alloc(s, &p.sched, 1, true));
     TRY(dev_alloc(s, &p.tot, 1, true));
+    lap("path state allocation");
+    if (timing) fprintf(stderr, "ct_gpu_upload_scene: total %.1f ms\n", now_ms() - t_begin);
     s.loaded = true;
     return CT_OK;
 }
