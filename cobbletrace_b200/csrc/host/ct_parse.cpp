@@ -12,7 +12,10 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <sstream>
+#include <thread>
+#include <atomic>
 #include <stdexcept>
 
 #include "ct_scene.hpp"
@@ -21,11 +24,13 @@ namespace cth {
 namespace {
 
 struct Cursor {
-    std::string buf;
+    std::shared_ptr<const std::string> hold;    // the file; copies of a Cursor are cheap views of the same bytes
+    const char *buf = nullptr;
+    size_t size = 0;
     size_t pos = 0;
     std::string name;
 
-    bool eof() const { return pos >= buf.size(); }
+    bool eof() const { return pos >= size; }
     char peek() const { return eof() ? '\0' : buf[pos]; }
     static bool is_space(char c) { return c == '\n' || c == '\r' || c == ' ' || c == '\t'; }   // fileBuffer.cpp:36-43
     void skip_space() { while (!eof() && is_space(buf[pos])) pos++; }
@@ -44,7 +49,7 @@ struct Cursor {
 
     [[noreturn]] void fail(const std::string &what) const {
         size_t line = 1;
-        for (size_t i = 0; i < pos && i < buf.size(); i++) line += buf[i] == '\n';
+        for (size_t i = 0; i < pos && i < size; i++) line += buf[i] == '\n';
         std::ostringstream m;
         m << name << ":" << line << ": " << what;
         throw std::runtime_error(m.str());
@@ -128,12 +133,17 @@ struct Cursor {
 };
 
 Cursor open_cursor(const std::string &path) {
-    std::ifstream f(path, std::ios::binary);
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
     if (!f) throw std::runtime_error("cannot open " + path);
-    std::ostringstream ss;
-    ss << f.rdbuf();
+    const std::streamoff len = f.tellg();
+    std::string bytes((size_t)std::max<std::streamoff>(len, 0), '\0');
+    f.seekg(0);
+    if (len > 0) f.read(&bytes[0], len);
     Cursor c;
-    c.buf = ss.str();
+    auto data = std::make_shared<const std::string>(std::move(bytes));
+    c.hold = data;
+    c.buf = data->data();
+    c.size = data->size();
     c.name = path;
     return c;
 }
@@ -192,6 +202,67 @@ void push_triangle(Scene &s, const Triangle &t, const ct_material &m) {
     s.mats.push_back(m);
 }
 
+// Multi-threaded body of import_ply for well-formed files: one record per line.  The sequential
+// cursor walk of the reference (parse the leading numbers of a line, skip to the next line) visits exactly the
+// line starts, so the lines can be parsed independently -- with the same number() -- as long as no record runs over
+// its line end.  Anything unusual (a short line, a non-triangle, an index out of range, too few lines) returns false
+// and the sequential path takes over from the untouched cursor, errors included.
+bool import_ply_parallel(const Cursor &c0, uint32_t n_vert, uint32_t n_face, std::vector<Vec3> &verts, const Placement &place,
+                         const ct_material &mat, Scene &s) {
+    const size_t n_rec = (size_t)n_vert + n_face;
+    unsigned hw = std::thread::hardware_concurrency();
+    int threads = (int)std::min(std::max(hw, 1u), 32u);
+    if (const char *e = std::getenv("CT_HOST_THREADS")) { int v = std::atoi(e); if (v >= 1) threads = std::min(v, 64); }
+    if (threads <= 1 || n_rec < 50000) return false;
+    if (s.tris.size() + n_face > 1000000u) return false;            // the sequential path raises the MAX_OBJECTS error
+    std::vector<size_t> start(n_rec), eol(n_rec);
+    {
+        Cursor c = c0;
+        for (size_t i = 0; i < n_rec; i++) {
+            if (c.eof()) return false;
+            start[i] = c.pos;
+            while (!c.eof() && c.buf[c.pos] != '\n' && c.buf[c.pos] != '\r') c.pos++;
+            eol[i] = c.pos;
+            c.skip_space();
+        }
+    }
+    std::atomic<bool> ok{true};
+    auto run = [&](size_t n, auto body) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++)
+            th.emplace_back([&, t] {
+                Cursor c = c0;
+                for (size_t i = n * t / threads, e = n * (t + 1) / threads; i < e && ok.load(std::memory_order_relaxed); i++)
+                    if (!body(c, i)) { ok = false; return; }
+            });
+        for (auto &t : th) t.join();
+    };
+    run(n_vert, [&](Cursor &c, size_t i) {
+        c.pos = start[i];
+        verts[i] = c.vec3_raw();
+        return c.pos <= eol[i];
+    });
+    if (!ok) return false;
+    const size_t base = s.tris.size();
+    std::vector<Triangle> tris(n_face);
+    run(n_face, [&](Cursor &c, size_t i) {
+        c.pos = start[n_vert + i];
+        int n = (int)c.number();
+        if (n != 3) return false;
+        Vec3 f = c.vec3_raw();
+        if (c.pos > eol[n_vert + i]) return false;
+        int a = (int)f.x, b = (int)f.y, d = (int)f.z;
+        if (a < 0 || b < 0 || d < 0 || (uint32_t)a >= n_vert || (uint32_t)b >= n_vert || (uint32_t)d >= n_vert) return false;
+        tris[i] = place.place(Triangle{verts[a], verts[b], verts[d]});
+        return true;
+    });
+    if (!ok) return false;
+    s.tris.resize(base + n_face);
+    s.mats.resize(base + n_face, mat);
+    std::copy(tris.begin(), tris.end(), s.tris.begin() + (ptrdiff_t)base);
+    return true;
+}
+
 // ImportPlyObject objectLoader.cpp:142-202 (ASCII PLY: x y z first on each vertex line, "3 i j k" faces)
 void import_ply(const ImportSpec &spec, const ct_material &mat, const std::string &base_dir, Scene &s) {
     Cursor c = open_cursor(resolve(base_dir, spec.filename));
@@ -209,8 +280,10 @@ void import_ply(const ImportSpec &spec, const ct_material &mat, const std::strin
         }
     }
     std::vector<Vec3> verts(n_vert);
-    for (uint32_t i = 0; i < n_vert && !c.eof(); i++) { verts[i] = c.vec3_raw(); c.skip_line(); }
     Placement place(spec.position, spec.rotation, spec.scale);
+    if (import_ply_parallel(c, n_vert, n_face, verts, place, mat, s)) return;
+    // the reference's sequential walk over the file (also the path that reports malformed input)
+    for (uint32_t i = 0; i < n_vert && !c.eof(); i++) { verts[i] = c.vec3_raw(); c.skip_line(); }
     for (uint32_t i = 0; i < n_face && !c.eof(); i++) {
         int n = (int)c.number();
         if (n != 3) c.fail("only triangular faces are supported");
