@@ -128,6 +128,24 @@ def test_procedural_standin_parses_identically_in_reference(tmp_path):
     assert ref.geometry_digest() == fs.geometry_digest() and ref.bvh_digest() == fs.bvh_digest()
 
 
+@pytest.mark.parametrize("threads", ["1", "3", "8"])
+def test_threaded_ingest_and_build_match_the_sequential_reference_algorithms(threads, tmp_path, monkeypatch):
+    """PLY import and BVH build on several host threads give, value for value and node for node,
+    what one thread gives -- which the tests above tie to the reference's parser and BuildBVH.  A mesh big enough
+    to take the threaded paths (> 50k PLY lines, > 16k triangles), checked against the oracle's BuildBVH restatement."""
+    parts = procedural.small_standin_parts(6)             # 8 * 4^6 = 32768 triangles in the largest part
+    scene, n = procedural.write_dragon_standin(str(tmp_path), parts=parts, name="mid")
+    assert n > 40000
+    monkeypatch.setenv("CT_HOST_THREADS", threads)
+    fs = host.HostScene.load(scene, base_dir=str(tmp_path)).to_flat(with_bvh=True)
+    monkeypatch.setenv("CT_HOST_THREADS", "1")
+    one = host.HostScene.load(scene, base_dir=str(tmp_path)).to_flat(with_bvh=True)
+    assert fs.geometry_digest() == one.geometry_digest() and fs.bvh_digest() == one.bvh_digest()
+    if threads == "8":
+        b = O.build_bvh(fs.tri)
+        assert all(np.array_equal(v, getattr(fs, k)) for k, v in b.items())
+
+
 def test_boss_fails_loudly_without_gpu(scene_loader):
     import torch
     if torch.cuda.is_available():
