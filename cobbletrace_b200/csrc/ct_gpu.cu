@@ -109,6 +109,7 @@ struct Params {
     const DevPair32 *pairs32;
     const DevPair64 *pairs64;
     double root_min[3], root_max[3];     // node 0
+    float root_min32[3], root_max32[3];  // ... as floats, for the slab filter
     uint32_t root_ref, root_cnt;
     double bound[3];                     // >= |b| for every node bound b per axis (+inf disables the filter), see ray_finish
     const DevTri *tris;
@@ -201,6 +202,16 @@ __device__ __noinline__ BoxTimes exact_child(const DevPair64 *pairs, uint32_t pi
 
 CT_DEV bool exact_root(const Params &P, const double *r64, float ray_t) {
     return box_accept(box_times(r64, P.root_min, P.root_max), ray_t);
+}
+
+// IntersectAABB's verdict for the root box: the fp32 bracket when it is certain, the fp64 arithmetic otherwise.
+CT_DEV bool root_accept(const Params &P, const TRay &r) {
+    if (r.filt) {
+        const BoxBracket b = box_filter(r, P.root_min32, P.root_max32);
+        if (bracket_geom_no(b) | bracket_t_no(b, r.t)) return false;
+        if (bracket_geom_yes(b) & bracket_t_yes(b, r.t)) return true;
+    }
+    return exact_root(P, r.r64, r.t);
 }
 
 struct TriHit { bool hit; float t; };
@@ -303,7 +314,7 @@ CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget
     bool live = false;
     if (active) {
         if (COUNT) lc.box++;
-        live = exact_root(P, r.r64, r.t);
+        live = root_accept(P, r);
     }
     while (__any_sync(kFullMask, live)) {
         if (live) {
@@ -404,7 +415,7 @@ CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uin
     closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
     if (active) {
         if (COUNT) lc.box++;
-        state = exact_root(P, r.r64, r.t) ? 1 : 0;
+        state = root_accept(P, r) ? 1 : 0;
     } else {
         result = kTravMiss;
     }
@@ -1365,6 +1376,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     for (int a = 0; a < 3; a++) {
         p.bound[a] = (boxes_ok && bound[a] < 1e30) ? bound[a] : INFINITY;
         p.root_min[a] = d->nodes[0].aabb_min[a]; p.root_max[a] = d->nodes[0].aabb_max[a];
+        p.root_min32[a] = (float)p.root_min[a]; p.root_max32[a] = (float)p.root_max[a];
     }
     child_ref(0, p.root_ref, p.root_cnt);
     p.n_pairs = n_pairs;
