@@ -52,8 +52,8 @@ struct Ray {        // ray_t (scenefile.h:104-108)
 
 // What the traversal loop keeps in registers: ray.t and the per-ray constants of the two certified fp32 filters
 // (box_filter, tri_filter_miss).  The fp64 origin/direction the reference's own arithmetic needs stay in local
-// memory (r64[0..2] = origin, r64[3..5] = direction, r64[6..8] = correctly rounded 1/direction, r64[9] != 0 when
-// some 1/d leaves the normal range) and are only touched when a filter cannot decide.
+// memory (r64[0..2] = origin, r64[3..5] = direction, r64[6..8] = correctly rounded 1/direction once needed, r64[9] its
+// state: < 0 not computed, 1 when some 1/d leaves the normal range) and are only touched when a filter cannot decide.
 constexpr int kRay64 = 10;
 struct TRay {
     float t;
@@ -65,7 +65,7 @@ struct TRay {
     float om;       // max|o_i|, rounded up
     bool filt;      // false: some axis cannot be bounded (d == 0, non-finite, absurd magnitudes) -> exact slab tests only
     bool tfilt;     // false: magnitudes outside the range the triangle filter's error analysis covers
-    const double *r64;
+    double *r64;
 };
 
 // Per-ray setup of the filters.  bound[k] >= |b| for every node bound b on axis k (computed at upload;
@@ -73,38 +73,39 @@ struct TRay {
 //
 // For a node bound b on axis k the reference computes  q_ref = float( fl64( fl64(b - o) / d ) )   (bvh.cpp:166-175).
 // With q* = (b - o)/d in real arithmetic, |q_ref - q*| <= (2^-24 + 2^-51) |q*|.
-// The filter evaluates  y = bf * rdf + c  with  bf = float(b), rdf = float(fl64(1/d)), c ~ fl64(-o * fl64(1/d)):
-//     |bf*rdf - b/d| <= (2 * 2^-24 + 2^-47) |b/d| ,   |c - (-o/d)| <= 2^-51 |o/d|
-// so |y - q_ref| <= 3.01 * 2^-24 * (|b| + |o|) / |d|  <=  E := 2^-22 * (bound + |o|) * |1/d| .
+// The filter evaluates  y = bf * rdf + c  with  bf = float(b), rdf = float-reciprocal of float(d), c = fl64(-o * rdf):
+//     rdf = (1/d)(1 + e),  |e| <= 2 * 2^-24 + 2^-47        (one rounding for float(d), one for the reciprocal)
+//     |bf*rdf - b/d| <= 3.01 * 2^-24 |b/d| ,   |c - (-o/d)| <= 2.01 * 2^-24 |o/d|
+// so |y - q_ref| <= 4.1 * 2^-24 * (|b| + |o|) / |d|  <=  E := 2^-21 * (bound + |o|) * |rdf| .
 // cl / cu fold -E / +E into c, rounded DOWN / UP to float, and the filter's FMAs round down / up as well, so
 //     fma_rd(bf, rdf, cl) <= q_ref <= fma_ru(bf, rdf, cu)          for every finite node bound.
+// No fp64 division here: the correctly rounded 1/d that the division-free fp64 evaluation (box_times) wants is
+// only computed when a ray first needs that path (ray64_reciprocals); r64[9] < 0 marks "not yet".
 CT_DEV void tray_setup(TRay &r, const Ray &ray, const double bound[3], double *r64) {
     const double o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
-    bool ok = true, odd = false;
+    bool ok = true;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        double rd = __ddiv_rn(1.0, d[k]);
+        const float df = __double2float_rn(d[k]);
+        const float rdf = __frcp_rn(df);
+        const double rd = (double)rdf;
         double c = __dmul_rn(-o[k], rd);
         double sum = __dadd_rn(bound[k], fabs(o[k]));
         double m = __dmul_rn(sum, fabs(rd));
-        double e = __dmul_rn(m, 0x1p-22);
-        // every quantity must be an ordinary number well inside the float range (a finite non-zero rd rules out
-        // d = 0 and d = +-inf, NaNs fail the comparisons); magnitudes near the float subnormals are left alone.
-        // m < 2^99 also puts every quotient of a filtered ray below 1e30f (pair_accept's T_FAR relies on it)
+        double e = __dmul_rn(m, 0x1p-21);
+        // every quantity must be an ordinary number well inside the float range (a finite non-zero rdf rules out
+        // d = 0, d = +-inf and directions outside the float range, NaNs fail the comparisons); magnitudes near the
+        // float subnormals are left alone.  m < 2^99 also puts every quotient of a filtered ray below 1e30f
+        // (pair_accept's T_FAR relies on it)
         ok = ok && (m < 0x1p99) && (fabs(rd) > 0x1p-100) && (fabs(rd) < 0x1p100) && (e > 0x1p-100) && (sum > 0x1p-60);
-        r.rdf[k] = __double2float_rn(rd);
+        r.rdf[k] = rdf;
         r.cl[k] = __double2float_rd(__dsub_rd(c, e));
         r.cu[k] = __double2float_ru(__dadd_ru(c, e));
         r.of[k] = __double2float_rn(o[k]);
-        r.df[k] = __double2float_rn(d[k]);
-        r64[k] = o[k]; r64[3 + k] = d[k]; r64[6 + k] = rd;
-        // zero/inf/NaN directions are fine for the reciprocal form (IEEE gives the same inf/NaN quotients both ways);
-        // only a finite non-zero d whose reciprocal leaves the normal range needs true divisions throughout
-        const uint32_t hi = (uint32_t)__double2hiint(d[k]), ex = (hi >> 20) & 0x7ffu;
-        const bool zero = ((hi & 0x7fffffffu) | (uint32_t)__double2loint(d[k])) == 0u;
-        odd = odd || (!zero && ex != 0x7ffu && (ex < 24u || ex > 2022u));
+        r.df[k] = df;
+        r64[k] = o[k]; r64[3 + k] = d[k];
     }
-    r64[9] = odd ? 1.0 : 0.0;
+    r64[9] = -1.0;
     r.filt = ok;
     double dm = fmax(fmax(fabs(d[0]), fabs(d[1])), fabs(d[2])), om = fmax(fmax(fabs(o[0]), fabs(o[1])), fabs(o[2]));
     r.tfilt = (dm >= 0x1p-20) && (dm <= 0x1p40) && (om <= 0x1p40);          // NaNs fail
@@ -112,6 +113,22 @@ CT_DEV void tray_setup(TRay &r, const Ray &ray, const double bound[3], double *r
     r.om = __double2float_ru(om);
     r.t = ray.t;
     r.r64 = r64;
+}
+
+// r64[6..8] = correctly rounded 1/d, r64[9] = 1 when some 1/d leaves the normal range (then box_times divides).
+CT_DEV void ray64_reciprocals(double *r64) {
+    bool odd = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double d = r64[3 + k];
+        r64[6 + k] = __ddiv_rn(1.0, d);
+        // zero/inf/NaN directions are fine for the reciprocal form (IEEE gives the same inf/NaN quotients both ways);
+        // only a finite non-zero d whose reciprocal leaves the normal range needs true divisions throughout
+        const uint32_t hi = (uint32_t)__double2hiint(d), ex = (hi >> 20) & 0x7ffu;
+        const bool zero = ((hi & 0x7fffffffu) | (uint32_t)__double2loint(d)) == 0u;
+        odd = odd || (!zero && ex != 0x7ffu && (ex < 24u || ex > 2022u));
+    }
+    r64[9] = odd ? 1.0 : 0.0;
 }
 
 // ---- IntersectAABB (bvh.cpp:165-179) -------------------------------------------------------------------
@@ -157,7 +174,8 @@ CT_DEV bool float_rounding_unsafe(double x) {
 //   * the quotient (b - o)/d is replaced by (b - o) * fl(1/d): each survivor is then within a few fp64 ulps of the
 //     reference's double, so its float rounding can differ only if it lies that close to a float rounding boundary
 //     (~2^-24 of tests) -- those, and rays whose 1/d leaves the normal range, redo the six true divisions.
-CT_DEV BoxTimes box_times(const double *r64, const double bmin[3], const double bmax[3]) {
+CT_DEV BoxTimes box_times(double *r64, const double bmin[3], const double bmax[3]) {
+    if (r64[9] < 0.0) ray64_reciprocals(r64);
     double x1 = __dmul_rn(__dsub_rn(bmin[0], r64[0]), r64[6]), x2 = __dmul_rn(__dsub_rn(bmax[0], r64[0]), r64[6]);
     double y1 = __dmul_rn(__dsub_rn(bmin[1], r64[1]), r64[7]), y2 = __dmul_rn(__dsub_rn(bmax[1], r64[1]), r64[7]);
     double z1 = __dmul_rn(__dsub_rn(bmin[2], r64[2]), r64[8]), z2 = __dmul_rn(__dsub_rn(bmax[2], r64[2]), r64[8]);

@@ -193,14 +193,14 @@ CT_DEV void load_pair32(const DevPair32 *pairs, uint32_t pid, DevPair32 &p) {
 
 // ---- cold paths: the reference's own fp64 arithmetic, out of line so that its operands only occupy registers
 // while it runs.  `r64` = the ray's origin (0..2) and direction (3..5) in local memory.
-__device__ __noinline__ BoxTimes exact_child(const DevPair64 *pairs, uint32_t pid, uint32_t side, const double *r64) {
+__device__ __noinline__ BoxTimes exact_child(const DevPair64 *pairs, uint32_t pid, uint32_t side, double *r64) {
     const double2 *q = reinterpret_cast<const double2 *>(pairs + pid) + 3u * side;
     double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
     const double bmin[3] = {a.x, a.y, b.x}, bmax[3] = {b.y, c.x, c.y};
     return box_times(r64, bmin, bmax);
 }
 
-CT_DEV bool exact_root(const Params &P, const double *r64, float ray_t) {
+CT_DEV bool exact_root(const Params &P, double *r64, float ray_t) {
     return box_accept(box_times(r64, P.root_min, P.root_max), ray_t);
 }
 
@@ -950,7 +950,7 @@ __global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant_
 
 // Is the leaf that holds a triangle REACHED by the reference's walk?  Every box on the way down must accept the ray:
 // the leaf's own box, its ancestors' boxes, the root's.  `code` = 2 * pair + side of the leaf's box.
-CT_DEV bool chain_accepts(const Params &P, const double *r64, float ray_t, uint32_t code) {
+CT_DEV bool chain_accepts(const Params &P, double *r64, float ray_t, uint32_t code) {
     while (code != kNoPos) {
         const uint32_t pid = code >> 1;
         if (!box_accept(exact_child(P.pairs64, pid, code & 1u, r64), ray_t)) return false;
