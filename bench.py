@@ -50,6 +50,8 @@ WORKLOADS = {
                  "3840x2160 (traced square 2160^2), shadows + 2 reflection bounces", "dragon", 3840, 2160, 2, REFLECTION),
     "dragon8k": ("configs[4]: same scene at 7680x4320 (traced square 4320^2)", "dragon", 7680, 4320, 2, REFLECTION),
     "dragon1080": ("reduced sample of configs[2]: same scene at 1920x1080", "dragon", 1920, 1080, 2, REFLECTION),
+    "dragon1080ss": ("stress: the configs[2] scene at 1920x1080 with settings.supersampling (16 jittered samples per pixel, counter-based jitter)",
+                     "dragon", 1920, 1080, 2, REFLECTION, 32),
     # the other BASELINE configs (parity-test cases; here for measurement on request, never the default)
     "cube640": ("configs[0]: scene_file_cube.json (37 triangles, 3 lights, one mirror) 640x640, depth 10", "golden:scene_file_cube", 640, 640, 10, None),
     "import640": ("configs[0]: scene_import.json (roundedCube.obj x4, 1712 triangles) 640x640, depth 10", "golden:scene_import", 640, 640, 10, None),
@@ -193,7 +195,7 @@ def run_ref_cpu(scene_json, chdir, W, H, depth, refl, threads, frames, warmup, t
 def cpu_baseline(workload, fs, counts_full, budget_s=25.0):
     """The reference's CPU renderer on this box's cores, on a bounded sample of the workload (rank 0, N = 1)."""
     from oracle import ct_oracle_py as O
-    desc, kind, W, H, depth, refl = workload
+    desc, kind, W, H, depth, refl = workload[:6]
     cores = host_cores()
     scene_path, _ = ensure_scene(kind)
     rays_full = counts_full["rays_primary"] + counts_full["rays_shadow"] + counts_full["rays_reflection"]
@@ -236,7 +238,7 @@ def reference_arm(args):
     from cobbletrace_b200 import host
     from oracle import ct_oracle_py as O
     workload = WORKLOADS[args.workload]
-    desc, kind, W, H, depth, refl = workload
+    desc, kind, W, H, depth, refl = workload[:6]
     scene_path, n_tri = ensure_scene(kind)
     cores = host_cores()
     hs, _ = load_host_scene(kind, refl)
@@ -315,7 +317,8 @@ def main():
     dev = local_rank
     torch.cuda.set_device(dev)
     workload = WORKLOADS[args.workload]
-    desc, kind, W, H, depth, refl = workload
+    desc, kind, W, H, depth, refl = workload[:6]
+    wflags = workload[6] if len(workload) > 6 else 0
     steps, warm = args.steps, max(args.warmup, 3)
 
     # ---- scene: generated once per box, parsed + BVH built by every rank (scene is replicated)
@@ -333,14 +336,14 @@ def main():
     boss = shared = None
     if N == 1:
         # the reference-facing host path: C++ boss (RayThread's boss half) driving one GPU
-        boss = host.Boss(hs, W, H, devices=(dev,), max_depth=depth, tile_rows=args.tile_rows)
+        boss = host.Boss(hs, W, H, devices=(dev,), max_depth=depth, tile_rows=args.tile_rows, flags=wflags)
         boss.set_stream(stream.cuda_stream)
         gpu = api.GpuRenderer(dev)
         gpu.width, gpu.height = W, H
     else:
         # one process per GPU, one shared frame: chunks stolen from a cursor on GPU 0 over NVLink, pixels stored
         # straight into GPU 0's framebuffer (multi.SharedFrame / ct_gpu_render_shared)
-        gpu = api.GpuRenderer(dev).upload(hs.to_flat(with_bvh=True), W, H, max_depth=depth)
+        gpu = api.GpuRenderer(dev).upload(hs.to_flat(with_bvh=True), W, H, max_depth=depth, flags=wflags)
         gpu.set_stream(stream.cuda_stream)
         shared = multi.SharedFrame(gpu, root=0)
     upload_ms = (time.time() - t0) * 1e3
@@ -457,7 +460,10 @@ def main():
     }
 
     # ---- roofline of the dominant kernel + CPU baseline (rank 0; only meaningful at N = 1)
-    if N == 1:
+    if N == 1 and wflags:
+        boss.close()
+        line["config"]["note"] = "sampling-mode stress workload: no roofline / CPU baseline (the reference's own supersampling is not reproducible)"
+    elif N == 1:
         boss.close()
         fs = hs.to_flat(with_bvh=True)
         counts = oracle_counts(fs, W, H, depth)

@@ -16,7 +16,7 @@ from .sceneio import FlatScene
 PKG = os.path.dirname(os.path.abspath(__file__))
 GPU_LIB = os.path.join(PKG, "libct_gpu.so")
 
-CT_FLAG_WIDE, CT_FLAG_KEEP_HITS, CT_FLAG_COUNT_TESTS, CT_FLAG_STAGE_TIMING, CT_FLAG_SUBSAMPLING = 1, 2, 4, 8, 16
+CT_FLAG_WIDE, CT_FLAG_KEEP_HITS, CT_FLAG_COUNT_TESTS, CT_FLAG_STAGE_TIMING, CT_FLAG_SUBSAMPLING, CT_FLAG_SUPERSAMPLING = 1, 2, 4, 8, 16, 32
 BACKGROUND = 0x333333      # raythread.cpp:59
 REFERENCE_MAX_DEPTH = 10   # raythread.cpp:508
 

@@ -129,7 +129,8 @@ struct Params {
     // tile
     int x_lo, n_x, y_lo, n_y;        // canvas x in [x_lo, x_lo+n_x), n_y traced rows starting at y_lo
     int subsample, n_rows;           // CT_FLAG_SUBSAMPLING: the tile spans n_rows canvas rows of which every other one is traced
-    uint32_t *final_color;           // ... and the traced pixels' colours by slot, for k_subsample
+    int supersample;                 // CT_FLAG_SUPERSAMPLING: 16 consecutive slots = the 4x4 jittered samples of one pixel
+    uint32_t *final_color;           // the traced pixels' / samples' colours by slot, for k_subsample / k_supersample
     int blocks_x;                    // ceil(n_x / 8): pixel blocks of 8x4 per warp
     uint32_t n_slots;                // blocks_x * ceil(n_y/4) * 32
     uint32_t cap;                    // capacity of every per-slot array
@@ -469,11 +470,43 @@ CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uin
     return result;
 }
 
-// Primary ray of canvas pixel (x,y): CanvasToViewport (raythread.cpp:186-194) * camera.rotation (mymath.h:68-75)
-CT_DEV Ray primary_ray(const Params &P, int x, int y) {
+// The counter-based stand-in for rand() in the supersampling jitter (oracle/ref_driver.cpp CT_RAND, oracle/ct_oracle.c).
+CT_DEV uint32_t hash3(uint32_t x, uint32_t y, uint32_t k) {
+    uint32_t h = x * 0x9E3779B1u ^ (y * 0x85EBCA77u) ^ (k * 0xC2B2AE3Du);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+
+// Canvas point of sample k (= 4 xs + ys) of pixel (x, y): the reference's float bookkeeping (raythread.cpp:461-505)
+// replayed up to that sample -- sampleX/sampleY are jittered, used, un-jittered and stepped in float, so each
+// sample's point depends on the rounding of the ones before it.
+CT_DEV void sample_point(int x, int y, int k, float &px, float &py) {
+    const float stepsize = 0.25f, jitter = 0.03125f;          // 1/(float)samples, stepsize/8
+    float sample_x = (float)x, sample_y = (float)y;
+    uint32_t call = 0;
+    for (int xs = 0; xs < 4; xs++) {
+        sample_y = (float)y;
+        for (int ys = 0; ys < 4; ys++) {
+            float rx = __fdiv_rn(__int2float_rn((int)(hash3((uint32_t)x, (uint32_t)y, call++) & 0x7fffffffu)), 2147483648.0f);   // (float)RAND_MAX
+            float ry = __fdiv_rn(__int2float_rn((int)(hash3((uint32_t)x, (uint32_t)y, call++) & 0x7fffffffu)), 2147483648.0f);
+            rx = __fsub_rn(__fmul_rn(rx, 0.0625f), jitter);
+            ry = __fsub_rn(__fmul_rn(ry, 0.0625f), jitter);
+            sample_x = __fadd_rn(sample_x, rx);
+            sample_y = __fadd_rn(sample_y, ry);
+            if (xs * 4 + ys == k) { px = sample_x; py = sample_y; return; }
+            sample_y = __fadd_rn(__fsub_rn(sample_y, ry), stepsize);
+            sample_x = __fsub_rn(sample_x, rx);
+        }
+        sample_x = __fadd_rn(sample_x, stepsize);
+    }
+    px = sample_x; py = sample_y;
+}
+
+// Primary ray through canvas point (px, py): CanvasToViewport (raythread.cpp:186-194) * camera.rotation (mymath.h:68-75)
+CT_DEV Ray primary_ray_at(const Params &P, float px, float py) {
     float hh = (float)P.H;                                  // "Keep it square": both scales use bitmap->height
     double sx = (double)__fdiv_rn(P.vp_w, hh), sy = (double)__fdiv_rn(P.vp_h, hh);
-    double vx = __dmul_rn((double)(float)x, sx), vy = __dmul_rn((double)(float)y, sy), vz = (double)P.vp_d;
+    double vx = __dmul_rn((double)px, sx), vy = __dmul_rn((double)py, sy), vz = (double)P.vp_d;
     Ray r;
     r.o = {P.cam[0], P.cam[1], P.cam[2]};
     r.d.x = __dadd_rn(__dadd_rn(__dmul_rn(vx, P.rot[0]), __dmul_rn(vy, P.rot[3])), __dmul_rn(vz, P.rot[6]));
@@ -481,6 +514,14 @@ CT_DEV Ray primary_ray(const Params &P, int x, int y) {
     r.d.z = __dadd_rn(__dadd_rn(__dmul_rn(vx, P.rot[2]), __dmul_rn(vy, P.rot[5])), __dmul_rn(vz, P.rot[8]));
     r.t = kRayTInit;
     return r;
+}
+
+// Primary ray of depth-0 slot `slot`, whose pixel is (x, y): the pixel centre, or one of its 16 jittered samples.
+CT_DEV Ray primary_ray(const Params &P, uint32_t slot, int x, int y) {
+    if (!P.supersample) return primary_ray_at(P, (float)x, (float)y);
+    float px, py;
+    sample_point(x, y, (int)(slot & 15u), px, py);
+    return primary_ray_at(P, px, py);
 }
 
 // slot -> canvas pixel.  A warp owns an 8x4 pixel block (coherent rays); returns false for padding lanes
@@ -492,6 +533,7 @@ CT_DEV void store_pixel(const Params &P, uint32_t slot, int fb_index, uint32_t c
 }
 
 CT_DEV bool slot_pixel(const Params &P, uint32_t slot, int &x, int &y, int &fb_index) {
+    if (P.supersample) slot >>= 4;                            // 16 samples per pixel
     uint32_t blk = slot >> 5, lane = slot & 31u;
     int bx = (int)(blk % (uint32_t)P.blocks_x), by = (int)(blk / (uint32_t)P.blocks_x);
     int ix = bx * 8 + (int)(lane & 7u), iy = by * 4 + (int)(lane >> 3);
@@ -508,6 +550,7 @@ CT_DEV bool slot_pixel(const Params &P, uint32_t slot, int &x, int &y, int &fb_i
         if (!P.subsample) return false;
         fb_index = -1;                                       // traced for the average of the row above it, never stored
     }
+    if (P.supersample) fb_index = -1;                        // a sample: k_supersample blends the 16 of a pixel and stores it
     return true;
 }
 
@@ -535,7 +578,7 @@ CT_DEV bool load_path(const Params &P, int depth, uint32_t q, uint32_t &slot, in
         int x, y;
         slot = own_slot(P, q);
         if (!slot_pixel(P, slot, x, y, fbi)) return false;
-        r = primary_ray(P, x, y);
+        r = primary_ray(P, slot, x, y);
         tc = P.hit0_t[slot]; pos = P.hit0_pos[slot];
     } else {
         const int cur = depth & 1;
@@ -596,7 +639,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
             double r64[kRay64];
             TRay r;
             if (active) {
-                Ray ray = primary_ray(P, x, y);
+                Ray ray = primary_ray(P, slot, x, y);
                 tray_setup(r, ray, P.bound, r64);
             }
             float tc; uint32_t pos;
@@ -1031,6 +1074,31 @@ __global__ void __launch_bounds__(256) k_subsample(const __grid_constant__ Param
     }
 }
 
+// settings.supersampling (raythread.cpp:460-505): the 16 samples of a pixel are folded into its colour one after the
+// other -- colour -= colour/8; colour += sample/8 per channel in float, truncated to uint8 after every sample (:486-497).
+__global__ void __launch_bounds__(256) k_supersample(const __grid_constant__ Params P) {
+    const uint32_t n = depth0_count(P) >> 4;                                  // chunks hold whole pixels (32 or 64 slots)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = own_slot(P, i << 4);
+        int x, y, fbi;
+        if (!slot_pixel(P, slot, x, y, fbi)) continue;
+        uint32_t color = P.final_color[slot];
+        for (uint32_t k = 1; k < 16u; k++) {
+            const uint32_t temp = P.final_color[slot + k];
+            uint32_t out = 0;
+            for (int sh = 0; sh <= 16; sh += 8) {
+                float c = (float)((color >> sh) & 0xffu), t = (float)((temp >> sh) & 0xffu);
+                c = __fsub_rn(c, __fdiv_rn(c, 8.0f));
+                c = __fadd_rn(c, __fdiv_rn(t, 8.0f));
+                out |= to_u8(c) << sh;
+            }
+            color = out;
+        }
+        const int col = x + P.W / 2, row = P.H / 2 - y;
+        P.fb_out[row * P.W + col] = color;
+    }
+}
+
 // ---- KAT kernels -----------------------------------------------------------------------------------------
 __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, const double *org, const double *dir,
                                 const float *t0, uint32_t *found, uint32_t *index, float *tclosest) {
@@ -1298,6 +1366,8 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     if (d->n_lights && !d->lights) return fail(CT_ERR_INVALID, "n_lights > 0 but lights == NULL");
     if (d->width <= 0 || d->height <= 0 || (int64_t)d->width * d->height > (1ll << 30)) return fail(CT_ERR_INVALID, "bad frame size %dx%d", d->width, d->height);
     if (d->max_depth < 0 || d->max_depth > 15) return fail(CT_ERR_LIMIT, "max_depth %d outside 0..15", d->max_depth);
+    if ((d->flags & CT_FLAG_SUPERSAMPLING) && (d->flags & (CT_FLAG_SUBSAMPLING | CT_FLAG_KEEP_HITS)))
+        return fail(CT_ERR_INVALID, "CT_FLAG_SUPERSAMPLING cannot be combined with CT_FLAG_SUBSAMPLING or CT_FLAG_KEEP_HITS");
     bool ok = true;
     int depth = bvh_depth(d->nodes, d->n_nodes, d->n_triangles, &ok);
     if (!ok) return fail(CT_ERR_INVALID, "BVH is malformed (child or triangle range out of bounds, or a cycle)");
@@ -1474,7 +1544,12 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     s.col_lo = std::max(0, x_lo + d->width / 2);
     s.col_hi = std::min(d->width, x_lo + n_x + d->width / 2);
     int rows_max = 2 * half + 1;
-    p.cap = ((uint32_t)p.blocks_x * (uint32_t)((rows_max + 3) / 4) * 32u + kChunkMax - 1u) / kChunkMax * kChunkMax;
+    {
+        const uint64_t pixel_slots = (uint64_t)p.blocks_x * (uint64_t)((rows_max + 3) / 4) * 32u;
+        const uint64_t slots = pixel_slots * ((d->flags & CT_FLAG_SUPERSAMPLING) ? 16u : 1u);
+        if (slots > (1ull << 31)) { free_device(s); return fail(CT_ERR_LIMIT, "frame needs %llu path slots (limit 2^31)", (unsigned long long)slots); }
+        p.cap = (uint32_t)((slots + kChunkMax - 1u) / kChunkMax * kChunkMax);
+    }
 
     const int levels = s.any_reflective ? d->max_depth + 1 : 1;
     TRY(dev_alloc(s, &p.hit0_t, p.cap)); TRY(dev_alloc(s, &p.hit0_pos, p.cap));
@@ -1516,7 +1591,8 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     }
     TRY(dev_alloc(s, &p.fb, (size_t)d->width * d->height, true));       // calloc'd like cobbletrace.cpp:57
     p.subsample = (d->flags & CT_FLAG_SUBSAMPLING) ? 1 : 0;
-    if (p.subsample) TRY(dev_alloc(s, &p.final_color, p.cap, true));
+    p.supersample = (d->flags & CT_FLAG_SUPERSAMPLING) ? 1 : 0;
+    if (p.subsample || p.supersample) TRY(dev_alloc(s, &p.final_color, p.cap, true));
     TRY(dev_alloc(s, &p.own_chunks, (p.cap >> kChunkLocalShift) + 1u));
     TRY(dev_alloc(s, &s.cursor_own, 1, true));                           // its own allocation: exported over CUDA IPC
     s.share_cursor = s.cursor_own; s.share_fb = p.fb;
@@ -1569,7 +1645,7 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     Params p = s.p;
     p.y_lo = y0; p.n_rows = y1 - y0;
     p.n_y = s.p.subsample ? (p.n_rows + 1) / 2 + ((p.n_rows & 1) == 0 ? 1 : 0) : p.n_rows;
-    p.n_slots = (uint32_t)p.blocks_x * (uint32_t)((p.n_y + 3) / 4) * 32u;
+    p.n_slots = (uint32_t)p.blocks_x * (uint32_t)((p.n_y + 3) / 4) * 32u * (s.p.supersample ? 16u : 1u);
     if (p.n_slots > p.cap) return fail(CT_ERR_INVALID, "tile [%d,%d) larger than the frame", y_start, y_end);
     const bool count = (s.flags & CT_FLAG_COUNT_TESTS) != 0;
     const int depth_max = s.any_reflective ? p.max_depth : 0;
@@ -1668,6 +1744,7 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     if (!stages) for (int d = 0; d <= depth_max; d++) CU(cudaStreamWaitEvent(st, s.ev_done[d], 0));
     if (depth_max > 0) { k_resolve<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("resolve", 0)); }
     if (pk.subsample) { k_subsample<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("subsample", 0)); }
+    if (pk.supersample) { k_supersample<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("supersample", 0)); }
     CU(cudaEventRecord(s.ev1, st));
     CU(cudaEventRecord(s.tile_done[s.tiles_submitted % 8], st));
     s.tiles_submitted++;

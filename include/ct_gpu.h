@@ -71,6 +71,11 @@ enum {
     CT_FLAG_KEEP_HITS = 2u,   /* keep the primary-ray hit records for ct_gpu_readback_hits */
     CT_FLAG_COUNT_TESTS = 4u, /* count box / triangle tests (slower; for roofline accounting) */
     CT_FLAG_STAGE_TIMING = 8u, /* bracket every kernel launch of a tile with CUDA events (profiling passes only) */
+    CT_FLAG_SUPERSAMPLING = 32u, /* settings.supersampling (raythread.cpp:460-505): 4x4 jittered samples per pixel folded into
+                                 the pixel by the reference's running blend.  The reference draws the jitter from libc rand()
+                                 on all worker threads at once and is not reproducible; this flag uses a counter-based
+                                 generator keyed on (x, y, call number) instead -- the function oracle/ref_driver.cpp
+                                 substitutes for rand() with --supersampling-hash.  16x the rays of a plain frame. */
     CT_FLAG_SUBSAMPLING = 16u /* settings.subsampling (raythread.cpp:512-531): of the rows of a tile (= one worker's
                                  partition) every other one and the last are traced, the rows between get the average
                                  of their neighbours.  Tiles must be rendered in the order the caller wants their

@@ -278,36 +278,89 @@ typedef struct {
     ct_oracle_hit *hits;
 } job;
 
+/* The counter-based stand-in for rand() in the supersampling jitter (see oracle/ref_driver.cpp CT_RAND): keyed on the
+ * pixel and the number of the call inside it. */
+static uint32_t hash3(uint32_t x, uint32_t y, uint32_t k) {
+    uint32_t h = x * 0x9E3779B1u ^ (y * 0x85EBCA77u) ^ (k * 0xC2B2AE3Du);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+
+/* One primary ray through canvas point (px, py) (floats, as the reference passes them): CanvasToViewport :186-194
+ * times the camera matrix (mymath.h:68-75), then TraceRay. */
+static uint32_t trace_canvas_point(job *j, float px, float py, int want_hit, int stored, int row, int col) {
+    const ct_oracle_scene *s = j->cx.s;
+    float sx = 1.0f / (float)j->H, sy = 1.0f / (float)j->H;   /* :189-192 viewport {1,1,1} :554, float quotient */
+    const double *m = s->cam_rot;
+    double vx = (double)px * (double)sx, vy = (double)py * (double)sy, vz = 1.0;
+    vec3 dir;                                  /* v3_t * m3x3_t, mymath.h:68-75 */
+    dir.x = vx * m[0] + vy * m[3] + vz * m[6];
+    dir.y = vx * m[1] + vy * m[4] + vz * m[7];
+    dir.z = vx * m[2] + vy * m[5] + vz * m[8];
+    ray r = {v_load(s->cam_pos), dir, RAY_T_INIT};
+    j->cx.c.rays_primary++;
+    if (want_hit && j->hits && stored) {
+        ctx tmp; memset(&tmp, 0, sizeof tmp); tmp.s = s;
+        ct_oracle_hit *h = &j->hits[(size_t)row * j->W + col];
+        h->found = (uint32_t)closest_intersection(&tmp, r, &h->t, &h->index);
+    }
+    j->cx.kind = 0;
+    return trace_ray(&j->cx, r, j->max_depth);
+}
+
 static void *render_rows(void *arg) {
     job *j = (job *)arg;
-    const ct_oracle_scene *s = j->cx.s;
     int W = j->W, H = j->H;
     float half = (float)(H / 2);                 /* :454 float width = bitmap->height/2 (int division) */
     int x_lo = (int)-half, x_hi = (int)half;
     if (j->flags & CT_ORACLE_WIDE) { x_lo = -(W / 2); x_hi = W - W / 2; }
-    float sx = 1.0f / (float)H, sy = 1.0f / (float)H;   /* :189-192 viewport {1,1,1} :554, float quotient */
-    vec3 cam = v_load(s->cam_pos);
-    const double *m = s->cam_rot;
-    const int subsample = (j->flags & CT_ORACLE_SUBSAMPLE) != 0;
+    const int subsample = (j->flags & CT_ORACLE_SUBSAMPLE) != 0, supersample = (j->flags & CT_ORACLE_SUPERSAMPLE) != 0;
     for (int x = x_lo; x < x_hi; x++) {
         uint32_t last_color = 0;                       /* :456 */
         for (int y = j->y0; y < j->y1;) {              /* :457 -- the increment depends on settings.subsampling */
-            double vx = (double)(float)x * (double)sx, vy = (double)(float)y * (double)sy, vz = 1.0;
-            vec3 dir;                                  /* v3_t * m3x3_t, mymath.h:68-75 */
-            dir.x = vx * m[0] + vy * m[3] + vz * m[6];
-            dir.y = vx * m[1] + vy * m[4] + vz * m[7];
-            dir.z = vx * m[2] + vy * m[5] + vz * m[8];
             int col = x + W / 2, row = H / 2 - y;      /* :181-182 */
             int stored = !(row < 0 || row >= H || col < 0 || col >= W);   /* draw2d.h:11-14 */
-            ray r = {cam, dir, RAY_T_INIT};
-            j->cx.c.rays_primary++;
-            if (j->hits && stored) {
-                ctx tmp; memset(&tmp, 0, sizeof tmp); tmp.s = s;
-                ct_oracle_hit *h = &j->hits[(size_t)row * W + col];
-                h->found = (uint32_t)closest_intersection(&tmp, r, &h->t, &h->index);
+            uint32_t color = 0;
+            if (supersample) {                         /* :460-505, rand() -> hash3(x, y, call number) */
+                const int samples = 4;
+                float denom = samples * 2;
+                float stepsize = 1 / (float)samples;
+                float jitter = stepsize / 8;
+                float sampleX = (float)x;
+                int first = 1;
+                uint32_t call = 0;
+                for (int xs = 0; xs < samples; xs++) {
+                    float sampleY = (float)y;
+                    for (int ys = 0; ys < samples; ys++) {
+                        float rx = (float)(int)(hash3((uint32_t)x, (uint32_t)y, call++) & 0x7FFFFFFFu) / (float)2147483647;
+                        float ry = (float)(int)(hash3((uint32_t)x, (uint32_t)y, call++) & 0x7FFFFFFFu) / (float)2147483647;
+                        rx = (rx * (2 * jitter)) - jitter;
+                        ry = (ry * (2 * jitter)) - jitter;
+                        sampleX += rx;
+                        sampleY += ry;
+                        uint32_t temp = trace_canvas_point(j, sampleX, sampleY, 0, stored, row, col);
+                        if (first) {
+                            first = 0;
+                            color = temp;
+                        } else {                       /* :486-497: running blend in float rgb, truncated to uint8 each time */
+                            uint32_t out = 0;
+                            for (int sh = 0; sh <= 16; sh += 8) {
+                                float c = (float)((color >> sh) & 0xffu), t = (float)((temp >> sh) & 0xffu);
+                                c -= (c / denom);
+                                c += (t / denom);
+                                out |= (uint32_t)(unsigned char)c << sh;
+                            }
+                            color = out;
+                        }
+                        sampleY -= ry;
+                        sampleY += stepsize;
+                        sampleX -= rx;
+                    }
+                    sampleX += stepsize;
+                }
+            } else {
+                color = trace_canvas_point(j, (float)x, (float)y, 1, stored, row, col);
             }
-            j->cx.kind = 0;
-            uint32_t color = trace_ray(&j->cx, r, j->max_depth);
             if (stored) j->frame[(size_t)row * W + col] = color;
             if (subsample) {                           /* :512-531 */
                 if (y == j->y0) last_color = color;

@@ -54,6 +54,8 @@ typedef struct ct_oracle_hit { uint32_t found, index; float t; } ct_oracle_hit;
 
 enum {
     CT_ORACLE_WIDE = 1,     /* trace x in [-W/2, W/2) instead of the reference's centred square */
+    CT_ORACLE_SUPERSAMPLE = 4, /* settings.supersampling (raythread.cpp:460-505): 4x4 jittered samples per pixel, running blend; the
+                               jitter comes from a counter-based generator instead of rand() (oracle/ref_driver.cpp CT_RAND) */
     CT_ORACLE_SUBSAMPLE = 2 /* settings.subsampling (raythread.cpp:512-531): every other row of [y_start,y_end) is traced, the
                                rows between are averages; each thread's row range is one partition (use n_threads = 1) */
 };

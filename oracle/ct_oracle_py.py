@@ -40,7 +40,7 @@ class Counters(C.Structure):
         return d
 
 
-WIDE, SUBSAMPLE = 1, 2     # ct_oracle_render flags (ct_oracle.h)
+WIDE, SUBSAMPLE, SUPERSAMPLE = 1, 2, 4     # ct_oracle_render flags (ct_oracle.h)
 HIT_DT = np.dtype([("found", "<u4"), ("index", "<u4"), ("t", "<f4")])
 
 _lib = None

@@ -25,6 +25,8 @@
 //   --dump-scene F write the flattened scene + BVH (format: see tests/ctscene.py)
 //   --time K       time K frames through the boss/worker, print JSON
 //   --counters     print ray / box-test / triangle-test counters (needs -DCT_COUNT build)
+//   --supersampling-hash  settings.supersampling (:460-505: 4x4 jittered samples per pixel, running blend) with the jitter taken
+//                  from a counter-based generator instead of rand() (see CT_RAND below)
 //   --subsampling  leave settings.subsampling on (every other row traced, the rows between averaged, :512-531)
 //   --keys STR     feed STR as key presses to the reference's HandleKeyboard (raythread.cpp:388) before
 //                  the first frame: y/p/r rotate by pi/16, wasd/io move the camera by 0.1
@@ -48,6 +50,20 @@ extern unsigned long long g_ctBoxTests, g_ctTriTests;
 #define CT_HOOK_TRACERAY
 #define CT_HOOK_CLOSEST
 #endif
+
+// Supersampling (raythread.cpp:460-505) draws its jitter from libc rand() on every worker thread at once, so the
+// reference's own output is not reproducible.  The generated copy routes those two calls through
+// CT_RAND(): rand() itself by default; with --supersampling-hash a counter-based generator keyed on (x, y, call
+// number within the pixel) -- the only change, and the same function the oracle restatement and the GPU use.
+int g_ctHashRand = 0;
+static thread_local uint32_t t_ctPx, t_ctPy, t_ctPk;
+static inline uint32_t CtHash3(uint32_t x, uint32_t y, uint32_t k) {
+    uint32_t h = x * 0x9E3779B1u ^ (y * 0x85EBCA77u) ^ (k * 0xC2B2AE3Du);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+#define CT_HOOK_PIXEL(x, y) t_ctPx = (uint32_t)(x); t_ctPy = (uint32_t)(y); t_ctPk = 0;
+#define CT_RAND() (g_ctHashRand ? (int)(CtHash3(t_ctPx, t_ctPy, t_ctPk++) & 0x7FFFFFFFu) : rand())
 
 #include "raythread_gen.cpp"   // generated from /root/reference/raythread.cpp
 
@@ -157,7 +173,7 @@ int main(int argc, char **argv) {
     const char *sceneFile = NULL, *dir = NULL, *frameOut = NULL, *hitsOut = NULL, *sceneOut = NULL, *keys = NULL;
     int W = 640, H = 640, threads = 8, timeFrames = 0, warmFrames = 0;
     float forceReflection = -1;
-    bool counters = false, subsampling = false;
+    bool counters = false, subsampling = false, supersampling = false;
     if (argc == 4 && strcmp(argv[1], "--kat") == 0) return RunKat(argv[2], argv[3]);
     for (int i = 1; i < argc; i++) {
         #define ARG(name) (strcmp(argv[i], name) == 0 && i + 1 < argc)
@@ -176,6 +192,7 @@ int main(int argc, char **argv) {
         else if (ARG("--keys")) keys = argv[++i];       // key presses fed to HandleKeyboard before the first frame
         else if (strcmp(argv[i], "--counters") == 0) counters = true;
         else if (strcmp(argv[i], "--subsampling") == 0) subsampling = true;   // settings.subsampling (raythread.cpp:512-531); use --threads 1
+        else if (strcmp(argv[i], "--supersampling-hash") == 0) { supersampling = true; g_ctHashRand = 1; }   // :460-505 with the counter-based CT_RAND
         else if (strcmp(argv[i], "--verbose") == 0) ct_sdl_stub_quiet = 0;
         else { fprintf(stderr, "unknown arg %s\n", argv[i]); return 2; }
     }
@@ -200,7 +217,7 @@ int main(int argc, char **argv) {
     double tLoad1 = NowMs();
 
     // Parity settings: sampling modes off (supersampling draws from shared rand()).
-    scene.settings.supersampling = false;
+    scene.settings.supersampling = supersampling;   // only with --supersampling-hash (deterministic jitter)
     scene.settings.subsampling = subsampling;   // deterministic with one thread (several threads race on the rows between partitions)
     scene.settings.numberOfThreads = threads;
     if (forceReflection >= 0) {

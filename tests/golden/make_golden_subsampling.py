@@ -1,6 +1,10 @@
 #!/usr/bin/env python
-"""Adds the settings.subsampling goldens to tests/golden/ from the UNMODIFIED reference compiled
-under oracle/_ref:   make -C oracle ref && python tests/golden/make_golden_subsampling.py
+"""Adds the sampling-mode goldens to tests/golden/ from the reference compiled under oracle/_ref:
+    make -C oracle ref && python tests/golden/make_golden_subsampling.py
+
+settings.subsampling: the UNMODIFIED reference.  settings.supersampling: the reference with its two rand() calls
+routed through a counter-based generator (ct_ref --supersampling-hash, see oracle/ref_driver.cpp CT_RAND) -- with
+libc rand() on several threads the reference's own output is not reproducible.
 
 One worker thread per frame: with several, the reference's partitions race on the rows between them
 (raythread.cpp:526 writes row y-1 of the first row of a partition, which belongs to the partition below).
@@ -30,6 +34,13 @@ CASES = [
 ]
 
 
+SS_CASES = [
+    ("cube_96", "scene_file_cube", "scene_file_cube.json", 96, 96, 10, None, 3),
+    ("bunny_refl_d2_80x60", "scene_import_bunny", "scene_import_bunny.json", 80, 60, 2, 0.5, 2),
+    ("import_wide_100x61", "scene_import", "scene_import.json", 100, 61, 10, None, 1),
+]
+
+
 def main():
     if not O.ref_available():
         sys.exit("oracle/_ref/ct_ref missing: run `make -C oracle ref` first (needs /root/reference)")
@@ -49,6 +60,19 @@ def main():
         gold["frames_subsampling"][case] = {"scene": scene, "width": W, "height": H, "depth": depth, "force_reflection": refl,
                                             "fnv1a": frame_fnv1a(frame)}
         print(case, gold["frames_subsampling"][case]["fnv1a"], flush=True)
+    gold["frames_supersampling"] = {}
+    for case, scene, jf, W, H, depth, refl, threads in SS_CASES:
+        fr = os.path.join(tmp, case + ".ssframe")
+        args = ["--scene", jf, "--chdir", SCENES, "--width", str(W), "--height", str(H), "--depth", str(depth), "--threads", str(threads),
+                "--supersampling-hash", "--frame", fr]
+        if refl is not None:
+            args += ["--force-reflection", repr(refl)]
+        subprocess.run([os.path.join(O.REF_DIR, "ct_ref")] + args, check=True, capture_output=True)
+        frame = np.fromfile(fr, np.uint32).reshape(H, W)
+        np.savez_compressed(os.path.join(GOLD, f"frames_ss_{case}.npz"), frame=frame)
+        gold["frames_supersampling"][case] = {"scene": scene, "width": W, "height": H, "depth": depth, "force_reflection": refl,
+                                              "fnv1a": frame_fnv1a(frame)}
+        print("supersampling", case, gold["frames_supersampling"][case]["fnv1a"], flush=True)
     with open(gpath, "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
 

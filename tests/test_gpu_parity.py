@@ -263,6 +263,38 @@ def test_subsampling_against_reference_and_oracle(golden, scene_loader, gpu):
         gpu.render_shared()                             # neighbouring rows may not live on different GPUs
 
 
+def test_supersampling_against_patched_reference_and_oracle(golden, scene_loader, gpu):
+    """CT_FLAG_SUPERSAMPLING = settings.supersampling (raythread.cpp:460-505) with the counter-based jitter: frames of
+    the compiled reference (--supersampling-hash), then a larger frame, cut into ragged tiles, against the oracle."""
+    for case, m in golden["frames_supersampling"].items():
+        fs = scene_loader(m["scene"])
+        if m["force_reflection"] is not None:
+            fs = fs.with_reflection(m["force_reflection"])
+        gpu.upload(fs, m["width"], m["height"], max_depth=m["depth"], flags=ct.CT_FLAG_SUPERSAMPLING)
+        c = gpu.render_tile(counters=True)
+        want = np.load(os.path.join(GOLD, f"frames_ss_{case}.npz"))["frame"]
+        got = np.zeros_like(want)
+        gpu.readback(got)
+        assert np.array_equal(got, want), f"{case}: {int((got != want).sum())} pixels differ"
+        assert c["rays_primary"] == 16 * int((want != 0).sum())
+    fs = scene_loader("scene_import_bunny").with_reflection(0.3)
+    W, H = 333, 250
+    want, _, octr = O.OracleScene(fs).render(W, H, max_depth=3, flags=O.SUPERSAMPLE, want_hits=False)
+    gpu.upload(fs, W, H, max_depth=3, flags=ct.CT_FLAG_SUPERSAMPLING)
+    y0, y1 = gpu.full_range()
+    cuts = [y0, y0 + 3, y0 + 70, 1, y1]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        gpu.render_tile(a, b)
+    got = np.zeros_like(want)
+    gpu.readback(got)
+    assert np.array_equal(got, want), f"{int((got != want).sum())} pixels differ"
+    gpu.share_attach(gpu.share_export()); gpu.share_reset()      # whole pixels per chunk: the shared-frame path works too
+    gpu.render_shared()
+    got2 = np.zeros_like(want)
+    gpu.readback(got2)
+    assert np.array_equal(got2, want)
+
+
 def test_640_golden_hashes(golden, scene_loader, gpu):
     for name in ("scene_file_cube", "scene_import", "scene_import_bunny", "pc_big"):
         gpu.upload(scene_loader(name), 640, 640)

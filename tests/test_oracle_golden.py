@@ -107,3 +107,19 @@ def test_subsampling_frames_match_reference(golden, scene_loader):
         frame, _, _ = O.OracleScene(fs).render(m["width"], m["height"], max_depth=m["depth"], flags=O.SUBSAMPLE, want_hits=False, n_threads=1)
         want = np.load(os.path.join(GOLD, f"frames_sub_{case}.npz"))["frame"]
         assert np.array_equal(frame, want), case
+
+
+def test_supersampling_frames_match_patched_reference(golden, scene_loader):
+    """settings.supersampling (raythread.cpp:460-505) with the jitter from the counter-based generator: the restatement
+    against frames of the compiled reference run with --supersampling-hash on 1-3 worker threads."""
+    import os
+    from oracle import ct_oracle_py as O
+    from conftest import GOLD
+    assert len(golden["frames_supersampling"]) >= 3
+    for case, m in golden["frames_supersampling"].items():
+        fs = scene_loader(m["scene"])
+        if m["force_reflection"] is not None:
+            fs = fs.with_reflection(m["force_reflection"])
+        frame, _, _ = O.OracleScene(fs).render(m["width"], m["height"], max_depth=m["depth"], flags=O.SUPERSAMPLE, want_hits=False)
+        want = np.load(os.path.join(GOLD, f"frames_ss_{case}.npz"))["frame"]
+        assert np.array_equal(frame, want), case
