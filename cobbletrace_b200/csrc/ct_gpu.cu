@@ -282,33 +282,27 @@ constexpr uint32_t kFullMask = 0xffffffffu;
 #endif
 
 // IntersectBVHClosest (bvh.cpp:198-222) as an explicit-stack DFS in the reference's visit order (left subtree,
-// then right).  The reference tests a node's box when it VISITS the node; here both children of a passing
-// interior node are fetched and tested together (one 64-byte fetch, two independent slab tests in flight):
+// then right) -- the closest-hit walk of primary rays and of ct_gpu_debug_closest (any initial ray.t).
+// The reference tests a node's box when it VISITS the node; here both children of a passing interior node are
+// fetched and tested together (one 64-byte fetch, two independent slab tests in flight):
 //   * the left child is visited next, so "now" is its visit time;
 //   * the right child's tmin/tmax do not depend on ray.t; of the three accept conditions (bvh.cpp:178) only
 //     `tmin < ray.t` does, and ray.t only ever decreases -- so a right child failing now fails at visit time too
 //     and is dropped, and one that passes now is pushed WITH (a bracket of) its tmin and re-checked against the
 //     then-current ray.t when popped.  Same boxes accepted, same triangles tested in the same order, same counts.
-//   kClosest   general semantics (any initial ray.t).
-//   kFirstLine reflection rays (ray.t = 0, raythread.cpp:373): ray.t never changes, the first bary
-//              pass in DFS order becomes closestIndex with tclosest = 0, so stop there.
-// (The early-exit walks have their own loop, traverse_early; kFirstLine is kept here only as its plain DFS form.)
+// Leaves are tested on the spot: ray.t must be up to date for the next box (an early-exit walk may defer them,
+// traverse_early; this one may not, and for the same reason it cannot be parked and finished out of order).
 // WARP-SYNCHRONOUS: all 32 lanes call it (lanes without a ray pass active = false); every iteration = one node
 // visit per live lane, and the lanes re-converge at the vote that ends it (left to itself the compiler lets the
 // lanes of a warp drift apart for the whole walk: measured 8 of 32 lanes active).
-// Returns kTravHit/kTravMiss = ray.t != 1e30f ("found"); kFirstLine gives up with kTravOverBudget after `budget`
-// node visits + triangle tests and the caller parks the ray for k_overflow (order-independent answer, see there).
-template <TraverseMode MODE, bool COUNT>
-CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
-    static_assert(MODE != kAnyHit, "shadow rays use traverse_early");
-    // stack entry = a pushed right child: (ref, cnt) and, in kClosest mode, the bracket of its tmin plus its
-    // parent pair to find its fp64 bounds again
-    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax];
-    uint32_t stk_src[MODE == kClosest ? kStackMax : 1];
-    float stk_lo[MODE == kClosest ? kStackMax : 1], stk_hi[MODE == kClosest ? kStackMax : 1];
+// Returns kTravHit/kTravMiss = ray.t != 1e30f ("found").
+template <bool COUNT>
+CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    // stack entry = a pushed right child: (ref, cnt), the bracket of its tmin and its parent pair (to find its fp64
+    // bounds again when the bracket cannot decide)
+    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax], stk_src[kStackMax];
+    float stk_lo[kStackMax], stk_hi[kStackMax];
     int sp = 0;
-    uint32_t spent = 1u;
-    int result = kTravMiss;
     tclosest = kFinf;          // raythread.cpp:204
     closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
     uint32_t cur_ref = P.root_ref, cur_cnt = P.root_cnt;   // current (already accepted) node
@@ -326,52 +320,40 @@ CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget
                     if (COUNT) lc.tri++;
                     const TriHit th = leaf_triangle<false, COUNT>(P, r, pos, lc);
                     if (th.hit) {
-                        if (MODE == kFirstLine) {
-                            closest_pos = pos; tclosest = 0.0f;
-                            live = false; need_pop = false;
-                            break;
-                        } else {
-                            if (th.t > kEps) r.t = macro_min(r.t, th.t);               // bvh.cpp:161
-                            if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
-                                closest_pos = pos; tclosest = r.t;
-                            }
+                        if (th.t > kEps) r.t = macro_min(r.t, th.t);               // bvh.cpp:161
+                        if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
+                            closest_pos = pos; tclosest = r.t;
                         }
                     }
                 }
             } else {
+                CT_CHECK(cur_ref < P.n_pairs);
                 DevPair32 pr;
                 load_pair32(P.pairs32, cur_ref, pr);
                 prefetch_children(P, pr);
                 if (COUNT) lc.box += 2;
-                spent += 2u + pr.l_cnt + pr.r_cnt;
-                if (MODE != kClosest && spent > budget) {
-                    result = kTravOverBudget; live = false; need_pop = false;
-                } else {
-                    bool hit_l, hit_r; float r_lo, r_hi;
-                    pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
-                    if (hit_l & hit_r) {
-                        CT_CHECK(sp < kStackMax);
-                        stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt;
-                        if (MODE == kClosest) { stk_lo[sp] = r_lo; stk_hi[sp] = r_hi; stk_src[sp] = cur_ref; }
-                        sp++;
-                    }
-                    if (hit_l | hit_r) {
-                        cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
-                        need_pop = false;
-                    }
+                bool hit_l, hit_r; float r_lo, r_hi;
+                pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
+                if (hit_l & hit_r) {
+                    CT_CHECK(sp < kStackMax);
+                    stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt;
+                    stk_lo[sp] = r_lo; stk_hi[sp] = r_hi; stk_src[sp] = cur_ref;
+                    sp++;
+                }
+                if (hit_l | hit_r) {
+                    cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
+                    need_pop = false;
                 }
             }
             if (need_pop) {
                 live = false;
                 while (sp > 0) {
                     --sp;
-                    if (MODE == kClosest) {                                   // the deferred `tmin < ray.t` of bvh.cpp:178
-                        if (stk_lo[sp] >= r.t) continue;
-                        if (!(stk_hi[sp] < r.t)) {
-                            if (COUNT) lc.box_exact++;
-                            BoxTimes e = exact_child(P.pairs64, stk_src[sp], 1u, r.r64);
-                            if (!(e.tmin < r.t)) continue;
-                        }
+                    if (stk_lo[sp] >= r.t) continue;                          // the deferred `tmin < ray.t` of bvh.cpp:178
+                    if (!(stk_hi[sp] < r.t)) {
+                        if (COUNT) lc.box_exact++;
+                        BoxTimes e = exact_child(P.pairs64, stk_src[sp], 1u, r.r64);
+                        if (!(e.tmin < r.t)) continue;
                     }
                     cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; live = true;
                     break;
@@ -379,7 +361,6 @@ CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget
             }
         }
     }
-    if (result == kTravOverBudget) return result;
     if (!active) return kTravMiss;
     return r.t != kRayTInit ? kTravHit : kTravMiss;
 }
@@ -396,7 +377,7 @@ CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget
 // triangles together, oldest leaf first, instead of one lane at a time in the middle of the walk (measured: 4 of
 // 32 lanes active in an inline leaf path, 16 in the leaf phase).  A leaf phase runs when some lane's list is full
 // and after the walk; kFirstLine stops at the first pass of a phase (every leaf before it has been tested).
-// WARP-SYNCHRONOUS like traverse().  Returns kTravHit (kAnyHit: occluded; kFirstLine: always -- `found` is
+// WARP-SYNCHRONOUS like traverse_closest().  Returns kTravHit (kAnyHit: occluded; kFirstLine: always -- `found` is
 // 0 != 1e30f, raythread.cpp:227 -- with closest_pos = kNoPos when nothing passed), kTravMiss or kTravOverBudget.
 #ifndef CT_LEAF_LIST
 #define CT_LEAF_LIST 8
@@ -404,7 +385,7 @@ CT_DEV int traverse(const Params &P, TRay &r, bool active, const uint32_t budget
 constexpr int kLeafList = CT_LEAF_LIST;       // deferred leaves per lane before a leaf phase is forced
 template <TraverseMode MODE, bool COUNT>
 CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
-    static_assert(MODE != kClosest, "closest-hit rays use traverse");
+    static_assert(MODE != kClosest, "closest-hit rays use traverse_closest");
     uint32_t stk_ref[kStackMax], stk_cnt[kStackMax];     // pushed right children
     uint32_t leaf_ref[kLeafList], leaf_cnt[kLeafList];   // deferred leaves, DFS order
     int sp = 0, nleaf = 0;
@@ -470,7 +451,8 @@ CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uin
     return result;
 }
 
-// The counter-based stand-in for rand() in the supersampling jitter (oracle/ref_driver.cpp CT_RAND, oracle/ct_oracle.c).
+// The counter-based stand-in for rand() in the supersampling jitter (the parity harness patches the same
+// function into the compiled reference in place of rand(); DESIGN.md, sampling modes).
 CT_DEV uint32_t hash3(uint32_t x, uint32_t y, uint32_t k) {
     uint32_t h = x * 0x9E3779B1u ^ (y * 0x85EBCA77u) ^ (k * 0xC2B2AE3Du);
     h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
@@ -643,7 +625,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
                 tray_setup(r, ray, P.bound, r64);
             }
             float tc; uint32_t pos;
-            bool found = traverse<kClosest, COUNT>(P, r, active, 0xffffffffu, tc, pos, lc) == kTravHit;   // warp-synchronous
+            bool found = traverse_closest<COUNT>(P, r, active, tc, pos, lc) == kTravHit;   // warp-synchronous
             if (!active) continue;
             n_rays++;
             CT_CHECK(slot < P.cap && q < P.cap);
@@ -1115,7 +1097,7 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
     LocalCount lc; float tc, tc2; uint32_t pos, pos2;
     const bool first_line = r.t == 0.0f;
     bool f = traverse_early<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc) == kTravHit;
-    bool f2 = traverse<kClosest, false>(P, tr, active && !first_line, 0xffffffffu, tc2, pos2, lc) == kTravHit;
+    bool f2 = traverse_closest<false>(P, tr, active && !first_line, tc2, pos2, lc) == kTravHit;
     if (!active) return;
     if (!first_line) { f = f2; tc = tc2; pos = pos2; }
     if (found) found[i] = f ? 1u : 0u;
@@ -1512,9 +1494,9 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     p.n_slights = (uint32_t)slights.size();
     p.occ_words = std::max<uint32_t>((d->n_lights + 31u) / 32u, 1u);
     p.n_nodes = d->n_nodes;
-    DevPair32 *dp32; DevPair64 *dp64; DevTri *dt; ct_material *dm; DevLight *dl; DevShadowLight *dsl;
+    DevPair32 *dp32 = nullptr; DevPair64 *dp64 = nullptr; DevTri *dt = nullptr; ct_material *dm = nullptr; DevLight *dl = nullptr; DevShadowLight *dsl = nullptr;
     TRY(dev_alloc(s, &dp32, pairs32.size())); TRY(dev_alloc(s, &dp64, pairs64.size())); TRY(dev_alloc(s, &dt, tris.size()));
-    DevTri32 *dt32;
+    DevTri32 *dt32 = nullptr;
     TRY(dev_alloc(s, &dt32, tris32.size()));
     CU(cudaMemcpy(dt32, tris32.data(), tris32.size() * sizeof(DevTri32), cudaMemcpyHostToDevice));
     p.tris32 = dt32;

@@ -74,8 +74,8 @@ enum {
     CT_FLAG_SUPERSAMPLING = 32u, /* settings.supersampling (raythread.cpp:460-505): 4x4 jittered samples per pixel folded into
                                  the pixel by the reference's running blend.  The reference draws the jitter from libc rand()
                                  on all worker threads at once and is not reproducible; this flag uses a counter-based
-                                 generator keyed on (x, y, call number) instead -- the function oracle/ref_driver.cpp
-                                 substitutes for rand() with --supersampling-hash.  16x the rays of a plain frame. */
+                                 generator keyed on (x, y, call number) instead -- the same function the parity
+                                 harness substitutes for rand() in the compiled reference (sampling modes).  16x the rays of a plain frame. */
     CT_FLAG_SUBSAMPLING = 16u /* settings.subsampling (raythread.cpp:512-531): of the rows of a tile (= one worker's
                                  partition) every other one and the last are traced, the rows between get the average
                                  of their neighbours.  Tiles must be rendered in the order the caller wants their
