@@ -16,6 +16,15 @@ void boss_set_stream(Boss *b, int slot, void *stream);
 void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *stats);
 int boss_tiles(const Boss *b, int32_t *out, int max_tiles);
 void boss_destroy(Boss *b);
+struct Controls;
+Controls *controls_create(const Scene *scene, uint32_t capacity);
+bool controls_add_event(Controls *c, uint32_t type, uint32_t value);
+bool controls_update(Controls *c);
+void controls_camera(const Controls *c, double pos[3], float ypr[3], double rot[9]);
+uint32_t controls_pending(const Controls *c);
+uint64_t controls_frames(const Controls *c);
+void controls_destroy(Controls *c);
+bool viewer_tick(Boss *b, Controls *c, uint32_t *bitmap, int stride, ct_host_present_fn present, void *user, ct_host_frame_stats *stats);
 }  // namespace cth
 
 namespace {
@@ -179,5 +188,46 @@ void ct_host_tile_counter_close(ct_host_tile_counter *c, int unlink_shared) {
 }
 
 void ct_host_boss_destroy(ct_host_boss *b) { cth::boss_destroy(reinterpret_cast<cth::Boss *>(b)); }
+
+#define CTL(c) reinterpret_cast<cth::Controls *>(c)
+#define CCTL(c) reinterpret_cast<const cth::Controls *>(c)
+
+ct_host_controls *ct_host_controls_create(const ct_host_scene *s, uint32_t event_capacity) {
+    if (!s) { g_err = "NULL scene"; return nullptr; }
+    return reinterpret_cast<ct_host_controls *>(cth::controls_create(S(s), event_capacity));
+}
+
+int ct_host_controls_add_event(ct_host_controls *c, uint32_t type, uint32_t value) {
+    if (!c) { g_err = "NULL controls"; return CT_ERR_INVALID; }
+    if (!cth::controls_add_event(CTL(c), type, value)) { g_err = "event queue full"; return CT_ERR_INVALID; }
+    return CT_OK;
+}
+
+int ct_host_controls_update(ct_host_controls *c) {
+    if (!c) { g_err = "NULL controls"; return CT_ERR_INVALID; }
+    return cth::controls_update(CTL(c)) ? 1 : 0;
+}
+
+uint32_t ct_host_controls_pending(const ct_host_controls *c) { return c ? cth::controls_pending(CCTL(c)) : 0; }
+uint64_t ct_host_controls_frames(const ct_host_controls *c) { return c ? cth::controls_frames(CCTL(c)) : 0; }
+
+void ct_host_controls_camera(const ct_host_controls *c, double pos[3], float ypr[3], double rot[9]) {
+    if (c) cth::controls_camera(CCTL(c), pos, ypr, rot);
+}
+
+void ct_host_controls_destroy(ct_host_controls *c) { cth::controls_destroy(CTL(c)); }
+
+int ct_host_viewer_tick(ct_host_boss *b, ct_host_controls *c, uint32_t *bitmap, int stride_pixels, ct_host_present_fn present,
+                        void *user, int *rendered, ct_host_frame_stats *stats) {
+    if (!b || !c || !bitmap) { g_err = "ct_host_viewer_tick: NULL boss, controls or bitmap"; return CT_ERR_INVALID; }
+    try {
+        const bool r = cth::viewer_tick(reinterpret_cast<cth::Boss *>(b), CTL(c), bitmap, stride_pixels, present, user, stats);
+        if (rendered) *rendered = r ? 1 : 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return CT_ERR_CUDA;
+    }
+    return CT_OK;
+}
 
 }  // extern "C"

@@ -44,6 +44,9 @@ class FrameStats(C.Structure):
                 ("tiles_total", C.c_int32), ("tiles_mine", C.c_int32), ("kernel_launches", C.c_uint64)]
 
 
+PRESENT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int)   # ct_host_present_fn
+EVENT_KEY_UP, EVENT_KEY_DOWN = 2, 3                                         # eventType_t, eventQueue.h:7-12
+
 _lib = None
 
 
@@ -79,6 +82,14 @@ def load_library():
         L.ct_host_boss_reset_shared_counter.argtypes = [vp]
         L.ct_host_boss_tiles.argtypes = [vp, vp, C.c_int]
         L.ct_host_boss_destroy.argtypes = [vp]
+        L.ct_host_controls_create.restype = vp; L.ct_host_controls_create.argtypes = [vp, C.c_uint32]
+        L.ct_host_controls_add_event.argtypes = [vp, C.c_uint32, C.c_uint32]
+        L.ct_host_controls_update.argtypes = [vp]
+        L.ct_host_controls_pending.restype = C.c_uint32; L.ct_host_controls_pending.argtypes = [vp]
+        L.ct_host_controls_frames.restype = C.c_uint64; L.ct_host_controls_frames.argtypes = [vp]
+        L.ct_host_controls_camera.argtypes = [vp, vp, vp, vp]
+        L.ct_host_controls_destroy.argtypes = [vp]
+        L.ct_host_viewer_tick.argtypes = [vp, vp, vp, C.c_int, PRESENT_FN, vp, C.POINTER(C.c_int), C.POINTER(FrameStats)]
         L.ct_host_tile_counter_open.restype = vp; L.ct_host_tile_counter_open.argtypes = [C.c_char_p]
         L.ct_host_tile_counter_next.restype = C.c_int32; L.ct_host_tile_counter_next.argtypes = [vp]
         L.ct_host_tile_counter_reset.argtypes = [vp]
@@ -263,6 +274,94 @@ class Boss:
             self.close()
         except Exception:
             pass
+
+
+class Controls:
+    """The event queue + HandleKeyboard + HandleUpdates' camera state (ct_host_controls_*); host state only."""
+
+    def __init__(self, scene: HostScene, event_capacity: int = 0):
+        self.L = load_library()
+        self.scene = scene
+        self.h = self.L.ct_host_controls_create(scene.h, event_capacity)
+        if not self.h:
+            raise RuntimeError("ct_host_controls_create: " + _err(self.L))
+
+    def key(self, ch: str, event_type: int = EVENT_KEY_DOWN):
+        """One SDL_KEYDOWN (cobbletrace.cpp:103-105)."""
+        if self.L.ct_host_controls_add_event(self.h, event_type, ord(ch)) < 0:
+            raise RuntimeError("ct_host_controls_add_event: " + _err(self.L))
+
+    def keys(self, s: str):
+        for ch in s:
+            self.key(ch)
+
+    def update(self) -> bool:
+        rc = self.L.ct_host_controls_update(self.h)
+        if rc < 0:
+            raise RuntimeError("ct_host_controls_update: " + _err(self.L))
+        return bool(rc)
+
+    @property
+    def pending(self) -> int:
+        return int(self.L.ct_host_controls_pending(self.h))
+
+    @property
+    def frames(self) -> int:
+        return int(self.L.ct_host_controls_frames(self.h))
+
+    def camera(self):
+        """(position[3] float64, (yaw, pitch, roll) float32, rotation[9] float64)."""
+        pos, ypr, rot = np.zeros(3), np.zeros(3, np.float32), np.zeros(9)
+        vp = C.c_void_p
+        self.L.ct_host_controls_camera(self.h, pos.ctypes.data_as(vp), ypr.ctypes.data_as(vp), rot.ctypes.data_as(vp))
+        return pos, ypr, rot
+
+    def close(self):
+        if self.h:
+            self.L.ct_host_controls_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Viewer:
+    """cobbletrace.cpp's main loop without the window: feed key presses, call tick() once per iteration.
+    `present(bitmap, frame_is_new)` stands where Blit (draw2d.h:22) is."""
+
+    def __init__(self, boss: "Boss", controls: Optional[Controls] = None, present=None):
+        self.boss = boss
+        self.controls = controls or Controls(boss.scene)
+        self.bitmap = np.zeros((boss.height, boss.width), np.uint32)      # env->bitmap, calloc'ed (cobbletrace.cpp:56)
+        self._present_py = present
+        bm = self.bitmap
+
+        def _thunk(_user, _ptr, _stride, is_new):
+            if self._present_py is not None:
+                self._present_py(bm, bool(is_new))
+        self._thunk = PRESENT_FN(_thunk)
+        self.last_stats = None
+
+    def key(self, ch: str):
+        self.controls.key(ch)
+
+    def keys(self, s: str):
+        self.controls.keys(s)
+
+    def tick(self) -> bool:
+        """One main-loop iteration; True when a new frame was rendered into self.bitmap."""
+        L = self.boss.L
+        rendered, st = C.c_int(0), FrameStats()
+        rc = L.ct_host_viewer_tick(self.boss.h, self.controls.h, self.bitmap.ctypes.data_as(C.c_void_p), self.bitmap.shape[1],
+                                   self._thunk, None, C.byref(rendered), C.byref(st))
+        if rc < 0:
+            raise RuntimeError("ct_host_viewer_tick: " + _err(L))
+        if rendered.value:
+            self.last_stats = dict(st.rays.as_dict(), wall_ms=float(st.wall_ms), kernel_launches=int(st.kernel_launches))
+        return bool(rendered.value)
 
 
 class TileCounter:

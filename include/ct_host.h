@@ -9,6 +9,8 @@
  *   ct_host_boss_*          RayThread's boss half: dispatch row tiles, wait, hand back the bitmap
  *                           (raythread.cpp:641-666, 546-594) -- workers are ct_gpu_render_tile / ct_gpu_render_shared
  *                           calls on one or more GPUs, with dynamic stealing instead of the static yStep split.
+ *   ct_host_controls_*      the event queue + HandleKeyboard + HandleUpdates' camera state  eventQueue.cpp, raythread.cpp:388-434,546-572
+ *   ct_host_viewer_tick     one main-loop iteration (RayThread + Blit seam)     cobbletrace.cpp:88-118
  *
  * All functions are thread-compatible (one thread per object).  Errors: NULL / negative return and a
  * message via ct_host_last_error(); nothing asserts or exits (the reference's parser asserts).
@@ -117,6 +119,38 @@ int ct_host_boss_reset_shared_counter(ct_host_boss *b);
 /* Tiles rendered by this process in the last frame: writes up to max (y_start,y_end) pairs, returns count. */
 int ct_host_boss_tiles(const ct_host_boss *b, int32_t *y_ranges, int max_tiles);
 void ct_host_boss_destroy(ct_host_boss *b);
+
+/* ---- controls + viewer tick (the interactive shell, minus the window) ----------------------- */
+/* eventType_t (eventQueue.h:7-12) */
+enum { CT_EVENT_MOUSE_MOVE = 0, CT_EVENT_MOUSE_CLICK = 1, CT_EVENT_KEY_UP = 2, CT_EVENT_KEY_DOWN = 3 };
+/* eventManager_t (eventQueue.h:32-38) + the statics of HandleUpdates (raythread.cpp:548-552: changesMade, yaw,
+ * pitch, roll) + scene->camera.position.  Host state only; needs no GPU. */
+typedef struct ct_host_controls ct_host_controls;
+/* Camera position from the scene file, yaw = pitch = roll = 0, "a frame is due".  event_capacity 0 = 1000. */
+ct_host_controls *ct_host_controls_create(const ct_host_scene *s, uint32_t event_capacity);
+/* AddEvent (eventQueue.cpp:5, called from the SDL loop cobbletrace.cpp:104): value = the key's character.
+ * CT_ERR_INVALID when `capacity` events are pending (the reference overwrites unread slots instead). */
+int ct_host_controls_add_event(ct_host_controls *c, uint32_t type, uint32_t value);
+/* The decision half of HandleUpdates (raythread.cpp:557-562): `changesMade || HandleKeyboard(...)` -- the queue is
+ * drained through HandleKeyboard (:388-434; w/s, d/a, i/o move by 0.1, y/p/r turn by pi/16, c = origin, m = log)
+ * unless a frame is already due (so keys queued before the first frame are read on the second call).
+ * Returns 1 when a frame has to be rendered now (and clears "due"), 0 when nothing changed, <0 on error. */
+int ct_host_controls_update(ct_host_controls *c);
+uint32_t ct_host_controls_pending(const ct_host_controls *c);     /* unread events */
+uint64_t ct_host_controls_frames(const ct_host_controls *c);      /* how often update() returned 1 */
+/* Current camera: position, (yaw, pitch, roll), rotation matrix (raythread.cpp:564-572).  Any pointer may be NULL. */
+void ct_host_controls_camera(const ct_host_controls *c, double pos[3], float ypr[3], double rot[9]);
+void ct_host_controls_destroy(ct_host_controls *c);
+
+/* Blit's seam (draw2d.h:22-64): called once per tick with the bitmap, whether or not it changed. */
+typedef void (*ct_host_present_fn)(void *user, const uint32_t *bitmap, int stride_pixels, int frame_is_new);
+/* One iteration of the main loop (cobbletrace.cpp:88-118) minus SDL: RayThread -> HandleUpdates; when a frame is due
+ * the camera goes to every device of the boss, the frame is rendered and read back into `bitmap` (blocking -- the
+ * reference re-dispatches its workers and lets the bitmap fill in over the next ticks; here the tick ends with the
+ * finished frame, i.e. what the reference's bitmap converges to); then `present` (may be NULL) gets the bitmap.
+ * *rendered (may be NULL) = 1 when a new frame was rendered. */
+int ct_host_viewer_tick(ct_host_boss *b, ct_host_controls *c, uint32_t *bitmap, int stride_pixels, ct_host_present_fn present,
+                        void *user, int *rendered, ct_host_frame_stats *stats);
 
 /* The tile dispenser on its own (what the boss steals from): a process-local atomic (shared_name NULL/"")
  * or a POSIX shared-memory counter common to all processes that open the same name. */

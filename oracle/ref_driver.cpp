@@ -30,6 +30,10 @@
 //   --subsampling  leave settings.subsampling on (every other row traced, the rows between averaged, :512-531)
 //   --keys STR     feed STR as key presses to the reference's HandleKeyboard (raythread.cpp:388) before
 //                  the first frame: y/p/r rotate by pi/16, wasd/io move the camera by 0.1
+//   --session STR  an interactive session: STR = batches of key presses separated by '|'; every batch is queued and one
+//                  frame rendered (one main-loop tick of cobbletrace.cpp:88-118 with the workers run to completion);
+//                  the camera and the frame's FNV-1a hash after every tick are printed as "session": [...]
+//                  (tick 0 = the first frame, rendered before any key is read, raythread.cpp:548,557)
 
 #include <stdint.h>
 #include <stdio.h>
@@ -37,6 +41,7 @@
 #include <string.h>
 #include <unistd.h>
 #include <time.h>
+#include <string>
 
 int ct_sdl_stub_quiet = 1;
 int g_ctMaxDepth = 10;
@@ -170,7 +175,7 @@ static int RunKat(const char *in, const char *out) {
 }
 
 int main(int argc, char **argv) {
-    const char *sceneFile = NULL, *dir = NULL, *frameOut = NULL, *hitsOut = NULL, *sceneOut = NULL, *keys = NULL;
+    const char *sceneFile = NULL, *dir = NULL, *frameOut = NULL, *hitsOut = NULL, *sceneOut = NULL, *keys = NULL, *session = NULL;
     int W = 640, H = 640, threads = 8, timeFrames = 0, warmFrames = 0;
     float forceReflection = -1;
     bool counters = false, subsampling = false, supersampling = false;
@@ -189,6 +194,7 @@ int main(int argc, char **argv) {
         else if (ARG("--dump-scene")) sceneOut = argv[++i];
         else if (ARG("--time")) timeFrames = atoi(argv[++i]);
         else if (ARG("--warmup")) warmFrames = atoi(argv[++i]);   // untimed frames before the --time frames
+        else if (ARG("--session")) session = argv[++i];
         else if (ARG("--keys")) keys = argv[++i];       // key presses fed to HandleKeyboard before the first frame
         else if (strcmp(argv[i], "--counters") == 0) counters = true;
         else if (strcmp(argv[i], "--subsampling") == 0) subsampling = true;   // settings.subsampling (raythread.cpp:512-531); use --threads 1
@@ -249,6 +255,28 @@ int main(int argc, char **argv) {
         // raythread.cpp:548,557), so key presses only take effect from the second frame on.
         for (const char *k = keys; *k; k++) AddEvent(&env.events, {ET_KEY_DOWN, EM_NONE, {0, 0}, (uint32_t)*k});
         ms = RenderFrame(&env, &scene, &bvh, false);
+    }
+
+    std::string sessionLog;
+    if (session) {
+        const char *k = session;
+        for (int tick = 0;; tick++) {
+            if (tick > 0) {
+                for (; *k && *k != '|'; k++) AddEvent(&env.events, {ET_KEY_DOWN, EM_NONE, {0, 0}, (uint32_t)*k});
+                ms = RenderFrame(&env, &scene, &bvh, false);
+            }
+            uint64_t h = 1469598103934665603ull;
+            const uint32_t *px = (const uint32_t *)bitmap.memory;
+            for (size_t i = 0; i < (size_t)W * H; i++) h = (h ^ px[i]) * 1099511628211ull;
+            char buf[1024];
+            const double *r = &scene.camera.rotation.data[0][0];
+            snprintf(buf, sizeof buf, "%s{\"pos\": [%.17g, %.17g, %.17g], \"rot\": [%.17g, %.17g, %.17g, %.17g, %.17g, %.17g, %.17g, %.17g, %.17g], \"fnv\": \"%016llx\"}",
+                     tick ? ", " : "", scene.camera.position.x, scene.camera.position.y, scene.camera.position.z,
+                     r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], (unsigned long long)h);
+            sessionLog += buf;
+            if (tick > 0) { if (*k == '|') k++; else break; }
+            else if (!*k) break;
+        }
     }
 
     if (frameP) WriteFile(frameP, bitmap.memory, (size_t)W * H * 4);
@@ -315,6 +343,7 @@ int main(int argc, char **argv) {
 #else
     (void)counters;
 #endif
+    if (session) printf(", \"session\": [%s]", sessionLog.c_str());
     printf("}\n");
     fflush(stdout);
     _exit(0); // worker threads never return (raythread.cpp:438)

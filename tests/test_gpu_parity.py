@@ -505,3 +505,29 @@ def test_dragon_class_full_size(tmp_path_factory, W, H, gpu):
     # property 3: every reflection ray "hits" (SURVEY 0.4): per primary hit 3 shading points -> 6 shadow rays
     hits = int((ohits["found"] == 1).sum())
     assert ctr["rays_reflection"] == 2 * hits and ctr["rays_shadow"] == 6 * hits
+
+
+@pytest.mark.gpu
+def test_viewer_sessions_match_reference(golden, scene_loader):
+    """cobbletrace.cpp's main loop without the window.  Key presses go through ct_host_controls
+    (AddEvent / HandleKeyboard / HandleUpdates), frames through the boss; every tick's bitmap must hash to what the
+    compiled reference showed after the same keys (tests/golden/make_golden_sessions.py), and no frame is rendered
+    when nothing changed."""
+    from cobbletrace_b200.sceneio import frame_fnv1a
+    for case, m in golden["sessions"].items():
+        hs = host.HostScene.from_flat(scene_loader(m["scene"]).without_bvh())
+        boss = host.Boss(hs, m["width"], m["height"], devices=(0,), max_depth=m["depth"])
+        shown = []
+        v = host.Viewer(boss, present=lambda bitmap, is_new: shown.append((frame_fnv1a(bitmap), is_new)))
+        assert v.tick()                                           # the first frame
+        assert frame_fnv1a(v.bitmap) == m["ticks"][0]["fnv1a"], (case, 0)
+        assert not v.tick() and shown[-1] == (m["ticks"][0]["fnv1a"], False)      # idle tick: Blit only
+        for k, batch in enumerate(m["session"].split("|"), 1):
+            v.keys(batch + "m")                                   # the reference harness appends 'm' to every batch
+            assert v.tick()
+            assert frame_fnv1a(v.bitmap) == m["ticks"][k]["fnv1a"], (case, k)
+            pos, _, rot = v.controls.camera()
+            assert np.array_equal(pos, np.array(m["ticks"][k]["pos"])) and np.array_equal(rot, np.array(m["ticks"][k]["rot"]))
+            assert v.last_stats["kernel_launches"] > 0
+        assert len(shown) == len(m["ticks"]) + 1 and not v.tick()
+        boss.close()

@@ -154,3 +154,59 @@ def test_boss_fails_loudly_without_gpu(scene_loader):
     with pytest.raises(RuntimeError) as e:
         host.Boss(hs, 64, 64)
     assert "no CPU fallback" in str(e.value) or "no CUDA device" in str(e.value)
+
+
+# ---- controls: the event queue + HandleKeyboard + HandleUpdates' camera state ----------------
+
+def _replay(ctl, session):
+    """Feed a golden session the way oracle/ref_driver.cpp --session does; yields the camera after every tick."""
+    assert ctl.update()                              # tick 0: the first frame, before any key is read
+    yield ctl.camera()
+    for batch in session.split("|"):
+        ctl.keys(batch + "m")                        # the harness appends 'm' so the reference always re-dispatches
+        assert ctl.update() and ctl.pending == 0
+        yield ctl.camera()
+
+
+def test_controls_follow_reference_keyboard_sessions(golden, scene_loader):
+    assert len(golden["sessions"]) >= 4
+    for case, m in golden["sessions"].items():
+        ctl = host.Controls(host.HostScene.from_flat(scene_loader(m["scene"])))
+        cams = list(_replay(ctl, m["session"]))
+        assert len(cams) == len(m["ticks"]) and ctl.frames == len(cams)
+        for k, ((pos, _, rot), t) in enumerate(zip(cams, m["ticks"])):
+            assert np.array_equal(pos, np.array(t["pos"])), (case, k)      # doubles stepped by 0.1: bit-exact
+            assert np.array_equal(rot, np.array(t["rot"])), (case, k)      # float yaw/pitch/roll, float cos/sin
+
+
+def test_controls_queue_and_redraw_rules(scene_loader):
+    hs = host.HostScene.from_flat(scene_loader("scene_file_cube"))
+    ctl = host.Controls(hs, event_capacity=4)
+    pos0 = ctl.camera()[0].copy()
+    ctl.keys("wd")                                   # queued before the first frame ...
+    assert ctl.update() and ctl.pending == 2         # ... and not read by it (raythread.cpp:548,557: `changesMade || ...`)
+    assert np.array_equal(ctl.camera()[0], pos0)
+    assert ctl.update() and ctl.pending == 0         # second tick reads them
+    assert np.array_equal(ctl.camera()[0], pos0 + np.array([0.1, 0.1, 0.0]))
+    assert not ctl.update() and ctl.frames == 2      # nothing pending -> no new frame
+    ctl.keys("xz ")                                  # unbound keys are consumed without a redraw
+    assert not ctl.update() and ctl.pending == 0
+    ctl.key("w", host.EVENT_KEY_UP)                  # only ET_KEY_DOWN counts (:392)
+    assert not ctl.update()
+    ctl.key("m")                                     # logs, changes nothing, still a redraw (:424-429)
+    assert ctl.update() and np.array_equal(ctl.camera()[0], pos0 + np.array([0.1, 0.1, 0.0]))
+    ctl.keys("yyyy")
+    with pytest.raises(RuntimeError, match="queue full"):
+        ctl.key("y")
+    assert ctl.update()
+    yaw = np.float32(0)
+    for _ in range(4):
+        yaw = np.float32(np.float64(yaw) + math.pi / 4 / 4)          # float += double, :417
+    assert ctl.camera()[1][0] == yaw
+    ctl.keys("c")
+    assert ctl.update()
+    pos, ypr, rot = ctl.camera()
+    assert not pos.any() and not ypr.any() and np.array_equal(rot, np.array([1, 0, 0, 0, 1, 0, 0, 0, 1.0]))
+    for _ in range(3):                               # the ring wraps
+        ctl.keys("adad"); assert ctl.update()
+    assert ctl.pending == 0

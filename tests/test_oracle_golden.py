@@ -123,3 +123,17 @@ def test_supersampling_frames_match_patched_reference(golden, scene_loader):
         frame, _, _ = O.OracleScene(fs).render(m["width"], m["height"], max_depth=m["depth"], flags=O.SUPERSAMPLE, want_hits=False)
         want = np.load(os.path.join(GOLD, f"frames_ss_{case}.npz"))["frame"]
         assert np.array_equal(frame, want), case
+
+
+def test_session_frames_match_reference(golden, scene_loader):
+    """the frames of the reference's interactive sessions (ct_ref --session: key presses through its
+    own AddEvent / HandleKeyboard / HandleUpdates) are what the restatement renders from the recorded cameras."""
+    import dataclasses
+    from oracle import ct_oracle_py as O
+    from cobbletrace_b200.sceneio import frame_fnv1a
+    for case, m in golden["sessions"].items():
+        fs = scene_loader(m["scene"])
+        for k, t in enumerate(m["ticks"]):
+            cam = dataclasses.replace(fs, cam_pos=np.array(t["pos"]), cam_rot=np.array(t["rot"]))
+            frame, _, _ = O.OracleScene(cam).render(m["width"], m["height"], max_depth=m["depth"], want_hits=False)
+            assert frame_fnv1a(frame) == t["fnv1a"], (case, k)
