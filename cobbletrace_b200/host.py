@@ -26,6 +26,8 @@ ABI_SYMBOLS = [
     "ct_host_boss_create", "ct_host_boss_set_stream", "ct_host_boss_set_camera", "ct_host_boss_render", "ct_host_boss_reset_shared_counter",
     "ct_host_boss_tiles", "ct_host_boss_destroy",
     "ct_host_tile_counter_open", "ct_host_tile_counter_next", "ct_host_tile_counter_reset", "ct_host_tile_counter_close",
+    "ct_host_controls_create", "ct_host_controls_add_event", "ct_host_controls_update", "ct_host_controls_pending",
+    "ct_host_controls_frames", "ct_host_controls_camera", "ct_host_controls_destroy", "ct_host_viewer_tick",
 ]
 
 
