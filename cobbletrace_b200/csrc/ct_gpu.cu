@@ -56,9 +56,14 @@ constexpr int kMinBlocks = CT_MIN_BLOCKS;   // traversal kernels: resident CTAs 
 constexpr int kOvfThreads = 256;     // k_overflow CTA
 constexpr int kMaxLaunches = 80;     // launches of one tile (work cursors / stage events)
 constexpr uint32_t kNoPos = 0xffffffffu;
-constexpr uint32_t kChunkLocalShift = 5;    // slots a warp takes from the tile's cursor at a time: 32 (one 8x4 pixel block) ...
-constexpr uint32_t kChunkSharedShift = 6;   // ... or 64 when the cursor is another GPU's memory (fewer NVLink round trips)
-constexpr uint32_t kChunkMax = 1u << kChunkSharedShift;
+// Slots a warp takes from the tile's cursor at a time: 32 = one 8x4 pixel block, one ray per lane.  When the cursor is
+// another GPU's memory, 64 would halve the NVLink round trips, but a kernel ends with its slowest warp and a warp's
+// chunk is walked one ray per lane at a time: measured on dragon 4K, 2 / 4 GPUs: 4.10 / 2.49 ms with 64 against
+// 4.01 / 2.36 ms with 32 (option "shared_chunk_shift" for experiments).
+constexpr uint32_t kChunkLocalShift = 5;
+constexpr uint32_t kChunkSharedShift = 5;
+constexpr uint32_t kChunkMaxShift = 6;
+constexpr uint32_t kChunkMax = 1u << kChunkMaxShift;
 constexpr uint32_t kDefaultBudget = 384;    // node visits + triangle tests before a ray is parked for k_overflow
 
 // ---- device-side scene layout (SoA arrays in HBM, uploaded once) -----------------------------------
@@ -1235,6 +1240,7 @@ DeviceState g_dev[kMaxDevices];
 std::mutex g_mutex;
 long long g_budget_option = 0;       // ct_gpu_set_option("traversal_budget"); 0 = default
 long long g_warp_budget_option = 0;  // ct_gpu_set_option("overflow_warp_budget"); 0 = default
+long long g_shared_chunk_shift = 0;  // ct_gpu_set_option("shared_chunk_shift"): 0 = kChunkSharedShift
 long long g_emulate_ranks = 0;       // ct_gpu_set_option("emulate_ranks"): profiling aid, see ct_gpu.h
 
 int check_device(int device) {
@@ -1633,9 +1639,10 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     const int depth_max = s.any_reflective ? p.max_depth : 0;
     // one device: its own cursor (zeroed with the rest of DevSched below) and framebuffer; shared frame: the root's
     p.steal = shared ? s.share_cursor : &p.sched->steal_local;
-    p.chunk_shift = shared ? kChunkSharedShift : kChunkLocalShift;
+    const uint32_t shared_shift = g_shared_chunk_shift ? (uint32_t)g_shared_chunk_shift : kChunkSharedShift;
+    p.chunk_shift = shared ? shared_shift : kChunkLocalShift;
     p.steal_stride = g_emulate_ranks > 1 ? (uint32_t)g_emulate_ranks : 1u;
-    if (p.steal_stride > 1) p.chunk_shift = kChunkSharedShift;
+    if (p.steal_stride > 1) p.chunk_shift = shared_shift;
     p.fb_out = shared ? s.share_fb : p.fb;
     Params pk = p; pk.max_depth = depth_max;   // with no reflective material the recursion never goes past depth 0 (:369)
     cudaStream_t st = s.stream;
@@ -1831,6 +1838,11 @@ int ct_gpu_set_option(const char *name, long long value) {
     if (!strcmp(name, "emulate_ranks")) {
         if (value < 0 || value > 64) return fail(CT_ERR_INVALID, "emulate_ranks must be 0..64");
         g_emulate_ranks = value;
+        return CT_OK;
+    }
+    if (!strcmp(name, "shared_chunk_shift")) {
+        if (value != 0 && (value < kChunkLocalShift || value > kChunkMaxShift)) return fail(CT_ERR_INVALID, "shared_chunk_shift must be 0 (default), 5 or 6");
+        g_shared_chunk_shift = value;
         return CT_OK;
     }
     if (!strcmp(name, "overflow_warp_budget")) {

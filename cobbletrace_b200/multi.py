@@ -4,7 +4,7 @@ The path shards by pixels and has exactly one exchange step -- collecting 4-byte
 Two ways to run a frame on N GPUs, scene replicated on each:
 
   SharedFrame (the fast path, used by bench.py): every GPU renders the same tile with ct_gpu_render_shared; its
-      primary-ray warps steal 64-pixel chunks from ONE cursor in GPU 0's memory (atomics over NVLink) and its
+      primary-ray warps steal 32-pixel chunks from ONE cursor in GPU 0's memory (atomics over NVLink) and its
       shading kernels store finished pixels straight into GPU 0's framebuffer (peer stores through CUDA IPC).
       No collective and no host in the loop; torch.distributed only ships the IPC handle and provides the
       per-frame barriers.

@@ -140,7 +140,7 @@ int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *coun
 /* ---- one frame on several GPUs -------------------------------------------------------------------
  * The scene is uploaded to every GPU.  One of them is the ROOT: its framebuffer receives every pixel and it hosts
  * the frame's chunk cursor.  Every GPU renders the SAME tile with ct_gpu_render_shared: its primary-ray warps take
- * chunks of 64 pixels from the root's cursor with atomics over NVLink (dynamic stealing, no host in the loop) and
+ * chunks of 32 pixels from the root's cursor with atomics over NVLink (dynamic stealing, no host in the loop) and
  * its shading kernels store finished pixels straight into the root's framebuffer (peer stores) -- there is no
  * separate gather step.  The GPUs may be driven by one process or by one process each (CUDA IPC).
  *
@@ -197,12 +197,14 @@ int ct_gpu_sync(int device);
 
 /* Library-wide tuning knobs, applied by the next ct_gpu_upload_scene.  Names:
  *   "traversal_budget"  node visits + triangle tests a shadow / reflection ray may spend in its own thread
- *                       before it is parked for k_overflow (0 = default 512), which gives it a whole warp and,
- *   "overflow_warp_budget"  after that many node visits (0 = default 32768), the whole grid (breadth-first).
+ *                       before it is parked for k_overflow (0 = default 384), which gives it a whole warp and,
+ *   "overflow_warp_budget"  after that many node visits (0 = default 4096), hands it to a kernel that tests every triangle
+ *                       with the whole grid and checks the ancestor boxes of the ones that pass.
  *                       Results never depend on either; tests set them low to push rays through those paths.
  *   "emulate_ranks"     R > 1: a profiling aid -- every render takes only every R-th chunk of the tile, i.e. the share
  *                       one of R GPUs gets in a shared frame (the other pixels are simply not rendered); applies to
- *                       the next render, 0 / 1 = off. */
+ *                       the next render, 0 / 1 = off.
+ *   "shared_chunk_shift"  log2 of the pixels a warp steals at a time in a shared frame: 5 (default, also 0) or 6. */
 int ct_gpu_set_option(const char *name, long long value);
 
 /* Rays parked so far on `device` since upload (shadow and reflection rays whose DFS ran past the budget, e.g. the
