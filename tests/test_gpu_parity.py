@@ -531,3 +531,33 @@ def test_viewer_sessions_match_reference(golden, scene_loader):
             assert v.last_stats["kernel_launches"] > 0
         assert len(shown) == len(m["ticks"]) + 1 and not v.tick()
         boss.close()
+
+
+@pytest.mark.gpu
+def test_tiny_and_narrow_frames_match_reference(golden, scene_loader, gpu):
+    """Degenerate bitmap sizes against frames of the compiled reference (tests/golden/make_golden_tiny.py): H = 1 (nothing
+    is traced), odd H (row 0 is reached after all), W < H (columns outside the bitmap wrap into neighbouring rows)."""
+    for m in golden["tiny_frames"]:
+        W, H = m["width"], m["height"]
+        gpu.upload(scene_loader(m["scene"]), W, H, max_depth=m["depth"])
+        gpu.render_tile()
+        assert np.array_equal(gpu.readback(), np.array(m["frame"], np.uint32)), (m["scene"], W, H, m["depth"])
+
+
+@pytest.mark.gpu
+def test_light_sets_and_depth_limits_against_oracle(scene_loader, gpu):
+    """Scenes without lights, with the ambient light only, one light of each kind; recursion depth 0 and 1 on the
+    mirror scene (raythread.cpp:366: `recursionDepth <= 0 || reflection <= 0`)."""
+    from cobbletrace_b200.sceneio import LT_AMBIENT
+    fs = scene_loader("scene_file_cube")
+    W, H = 72, 64
+    variants = [("depth0", fs, 0), ("depth1", fs, 1)]
+    for keep in ([], [int(np.flatnonzero(fs.light_type == LT_AMBIENT)[0])], [1], [2], [0, 1, 2, 1, 2]):
+        sel = np.array(keep, np.int64)
+        variants.append((f"lights{keep}", dataclasses.replace(fs, light_type=fs.light_type[sel], light_intensity=fs.light_intensity[sel],
+                                                             light_pos=fs.light_pos[sel], light_dir=fs.light_dir[sel]), 3))
+    for what, scene, depth in variants:
+        oframe, ohits, _ = O.OracleScene(scene).render(W, H, max_depth=depth)
+        gpu.upload(scene, W, H, max_depth=depth, flags=DBG)
+        gpu.render_tile()
+        assert_same(gpu, oframe, ohits, what)

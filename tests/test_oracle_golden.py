@@ -137,3 +137,13 @@ def test_session_frames_match_reference(golden, scene_loader):
             cam = dataclasses.replace(fs, cam_pos=np.array(t["pos"]), cam_rot=np.array(t["rot"]))
             frame, _, _ = O.OracleScene(cam).render(m["width"], m["height"], max_depth=m["depth"], want_hits=False)
             assert frame_fnv1a(frame) == t["fnv1a"], (case, k)
+
+
+def test_tiny_and_narrow_frames_match_reference(golden, scene_loader):
+    """Bitmap sizes the reference treats oddly (H = 1 traces nothing, odd H reaches row 0, W < H wraps columns into the
+    neighbouring rows through PutPixel, draw2d.h:8-20): the restatement against frames of the compiled reference."""
+    from oracle import ct_oracle_py as O
+    assert len(golden["tiny_frames"]) >= 30
+    for m in golden["tiny_frames"]:
+        frame, _, _ = O.OracleScene(scene_loader(m["scene"])).render(m["width"], m["height"], max_depth=m["depth"], want_hits=False)
+        assert np.array_equal(frame, np.array(m["frame"], np.uint32)), (m["scene"], m["width"], m["height"], m["depth"])
