@@ -1282,19 +1282,96 @@ int dev_alloc(DeviceState &s, T **out, size_t count, bool zero = false) {
 
 #define TRY(expr) do { int rc_ = (expr); if (rc_ != CT_OK) return rc_; } while (0)
 
-// fn(begin, end, worker) over [0, n) on up to `max_threads` host threads (upload-time array conversion)
-template <typename F>
-void parallel_for(uint32_t n, int max_threads, F fn) {
-    int nt = (int)std::min<uint64_t>((uint64_t)std::max(max_threads, 1), (n + 65535u) / 65536u);
-    if (nt <= 1) { fn(0u, n, 0); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++)
-        th.emplace_back([=] { fn((uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt), t); });
-    for (auto &t : th) t.join();
-}
-constexpr int kHostThreads = 16;
 
 // depth of the reference's DFS (stack entries needed) -- iterative to survive degenerate trees
+// ---- scene build on the device (ct_gpu_upload_scene) -------------------------------------------------------------
+// The reference's arrays go to the device as they are (nodes, triangles at their stride, the leaf permutation) and
+// two kernels turn them into the layout above -- a gather through the permutation plus conversions is bandwidth work
+// the host does an order of magnitude slower (868k triangles: 130 ms on 16 host threads, < 1 ms here).  Every value is
+// produced by the same IEEE operations as before (fp64 subtractions, round-to-nearest / round-up conversions).
+struct BuildReport {
+    unsigned long long bound_bits[3];    // max |bound| over all nodes, per axis (bit pattern of a non-negative double)
+    uint32_t boxes_bad;                  // some box is unordered or not finite
+    uint32_t bad_pos;                    // a tri_indexes entry out of range (kNoPos: none)
+    uint32_t pos0;                       // leaf position of triangle 0
+    uint32_t any_reflective;
+};
+
+__global__ void __launch_bounds__(256) k_build_pairs(const ct_bvh_node *__restrict__ nodes, const uint32_t *__restrict__ pid_of, uint32_t n_nodes,
+                                                     DevPair32 *__restrict__ pairs32, DevPair64 *__restrict__ pairs64,
+                                                     uint32_t *__restrict__ pair_parent, uint32_t *__restrict__ tri_parent, uint32_t n_tri, BuildReport *rep) {
+    double bound[3] = {0.0, 0.0, 0.0};
+    bool bad = false;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
+        const ct_bvh_node n = nodes[i];
+        for (int a = 0; a < 3; a++) {
+            // the filter needs finite, ordered boxes (box_filter picks near/far by the ray's sign)
+            if (!(n.aabb_min[a] <= n.aabb_max[a]) || isinf(n.aabb_min[a]) || isinf(n.aabb_max[a])) bad = true;
+            else bound[a] = fmax(bound[a], fmax(fabs(n.aabb_min[a]), fabs(n.aabb_max[a])));
+        }
+        if (n.triangle_count != 0 || n.left_node == 0u || (uint64_t)n.left_node + 1u >= n_nodes) continue;      // leaf, or an unreachable slot (the reference never uses node 1) holding zeros or garbage
+        const uint32_t pid = pid_of[i];
+        const ct_bvh_node L = nodes[n.left_node], R = nodes[n.left_node + 1u];
+        DevPair32 p32;
+        DevPair64 p64;
+        for (int a = 0; a < 3; a++) {
+            p64.lmin[a] = L.aabb_min[a]; p64.lmax[a] = L.aabb_max[a]; p64.rmin[a] = R.aabb_min[a]; p64.rmax[a] = R.aabb_max[a];
+            p32.lmin[a] = __double2float_rn(L.aabb_min[a]); p32.lmax[a] = __double2float_rn(L.aabb_max[a]);
+            p32.rmin[a] = __double2float_rn(R.aabb_min[a]); p32.rmax[a] = __double2float_rn(R.aabb_max[a]);
+        }
+        p32.l_cnt = L.triangle_count; p32.l_ref = L.triangle_count ? L.first_triangle_index : pid_of[n.left_node];
+        p32.r_cnt = R.triangle_count; p32.r_ref = R.triangle_count ? R.first_triangle_index : pid_of[n.left_node + 1u];
+        pairs32[pid] = p32;
+        pairs64[pid] = p64;
+        if (pair_parent) {
+            // who holds whose box: lets k_overflow_huge check a triangle's ancestor chain without walking down
+            for (uint32_t side = 0; side < 2u; side++) {
+                const ct_bvh_node &ch = side ? R : L;
+                const uint32_t code = 2u * pid + side;
+                if (ch.triangle_count == 0) pair_parent[pid_of[n.left_node + side]] = code;
+                else for (uint32_t k = 0; k < ch.triangle_count && (uint64_t)ch.first_triangle_index + k < n_tri; k++) tri_parent[ch.first_triangle_index + k] = code;
+            }
+        }
+    }
+    for (int a = 0; a < 3; a++) {
+        for (int off = 16; off > 0; off >>= 1) bound[a] = fmax(bound[a], __shfl_xor_sync(0xffffffffu, bound[a], off));
+        if ((threadIdx.x & 31u) == 0 && bound[a] > 0.0) atomicMax(&rep->bound_bits[a], (unsigned long long)__double_as_longlong(bound[a]));
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31u) == 0) atomicOr(&rep->boxes_bad, 1u);
+}
+
+__global__ void __launch_bounds__(256) k_build_tris(const unsigned char *__restrict__ raw, uint32_t stride, const uint32_t *__restrict__ tri_indexes,
+                                                    const ct_material *__restrict__ materials, uint32_t n_tri,
+                                                    DevTri *__restrict__ tris, DevTri32 *__restrict__ tris32, BuildReport *rep) {
+    bool refl = false;
+    auto dmax = [](double a, double b) { return (a < b) ? b : a; };      // std::max: a NaN component is skipped
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n_tri; pos += gridDim.x * blockDim.x) {
+        const uint32_t k = tri_indexes[pos];
+        if (k >= n_tri) { atomicMin(&rep->bad_pos, pos); continue; }
+        if (k == 0) rep->pos0 = pos;                     // a permutation holds it once (checked by the host afterwards)
+        const double *v = reinterpret_cast<const double *>(raw + (size_t)k * stride);
+        DevTri t;
+        DevTri32 t32;
+        double k1 = 0.0, k2 = 0.0, k3 = 0.0;
+        for (int a = 0; a < 3; a++) {
+            t.p1[a] = v[a];
+            t.e1[a] = __dsub_rn(v[3 + a], v[a]);
+            t.e2[a] = __dsub_rn(v[6 + a], v[a]);
+            // fp32 copy + magnitudes for tri_filter_miss (rounded up; NaN k1 = "never certify")
+            t32.p1[a] = __double2float_rn(t.p1[a]); t32.e1[a] = __double2float_rn(t.e1[a]); t32.e2[a] = __double2float_rn(t.e2[a]);
+            k3 = dmax(k3, fabs(t.p1[a])); k1 = dmax(k1, fabs(t.e1[a])); k2 = dmax(k2, fabs(t.e2[a]));
+        }
+        t.orig = k; t.pad = 0;
+        const bool in_range = k1 >= 0x1p-30 && k1 <= 0x1p30 && k2 >= 0x1p-30 && k2 <= 0x1p30 && k3 <= 0x1p40;   // NaNs fail
+        t32.k1 = in_range ? __double2float_ru(k1) : __int_as_float(0x7fc00000);
+        t32.k2 = __double2float_ru(k2); t32.k3 = __double2float_ru(k3);
+        tris[pos] = t;
+        tris32[pos] = t32;
+        if (materials[k].reflection > 0.0f) refl = true;
+    }
+    if (__any_sync(0xffffffffu, refl) && (threadIdx.x & 31u) == 0) atomicOr(&rep->any_reflective, 1u);
+}
+
 int bvh_depth(const ct_bvh_node *nodes, uint32_t n_nodes, uint32_t n_tri, bool *ok) {
     std::vector<std::pair<uint32_t, int>> st;
     st.push_back({0u, 1});
@@ -1387,102 +1464,73 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     auto lap = [&](const char *what) { if (timing) { double t = now_ms(); fprintf(stderr, "ct_gpu_upload_scene: %-28s %7.1f ms\n", what, t - t_mark); t_mark = t; } };
     Params &p = s.p;
     p.n_tri = d->n_triangles; p.n_lights = d->n_lights;
-    // nodes: reference layout -> per-interior-node child pairs (fp32 for the filter, fp64 for the exact path)
+    // nodes: reference layout -> per-interior-node child pairs (fp32 for the filter, fp64 for the exact path), built on
+    // the device from the raw arrays (k_build_pairs / k_build_tris); the host only numbers the interior nodes
     std::vector<uint32_t> pid_of(d->n_nodes, kNoPos);
     uint32_t n_pairs = 0;
     for (uint32_t i = 0; i < d->n_nodes; i++)
         if (d->nodes[i].triangle_count == 0) pid_of[i] = n_pairs++;
-    std::vector<DevPair32> pairs32(std::max<uint32_t>(n_pairs, 1));
-    std::vector<DevPair64> pairs64(std::max<uint32_t>(n_pairs, 1));
-    double bound[3] = {0, 0, 0};
-    bool boxes_ok = true;
     auto child_ref = [&](uint32_t c, uint32_t &ref, uint32_t &cnt) {
         const ct_bvh_node &n = d->nodes[c];
         cnt = n.triangle_count;
         ref = cnt ? n.first_triangle_index : pid_of[c];
     };
+    child_ref(0, p.root_ref, p.root_cnt);
+    p.n_pairs = n_pairs;
+    p.n_nodes = d->n_nodes;
+    s.can_overflow = (uint64_t)d->n_nodes + d->n_triangles > p.budget;      // parked rays: only when a DFS can run past the budget at all
+    lap("interior-node numbering (host)");
+
+    DevPair32 *dp32 = nullptr; DevPair64 *dp64 = nullptr; DevTri *dt = nullptr; DevTri32 *dt32 = nullptr; ct_material *dm = nullptr;
+    uint32_t *dpp = nullptr, *dtp = nullptr;
+    TRY(dev_alloc(s, &dp32, std::max<uint32_t>(n_pairs, 1))); TRY(dev_alloc(s, &dp64, std::max<uint32_t>(n_pairs, 1)));
+    TRY(dev_alloc(s, &dt, d->n_triangles)); TRY(dev_alloc(s, &dt32, d->n_triangles)); TRY(dev_alloc(s, &dm, d->n_triangles));
+    if (s.can_overflow) { TRY(dev_alloc(s, &dpp, std::max<uint32_t>(n_pairs, 1))); TRY(dev_alloc(s, &dtp, d->n_triangles)); }
+    BuildReport rep{};
     {
-        double part_bound[kHostThreads][3] = {};
-        bool part_ok[kHostThreads];
-        for (bool &b : part_ok) b = true;
-        parallel_for(d->n_nodes, kHostThreads, [&](uint32_t i0, uint32_t i1, int w) {
-            for (uint32_t i = i0; i < i1; i++) {
-                const ct_bvh_node &n = d->nodes[i];
-                for (int a = 0; a < 3; a++) {
-                    // the filter needs finite, ordered boxes (box_filter picks near/far by the ray's sign)
-                    if (!(n.aabb_min[a] <= n.aabb_max[a]) || !std::isfinite(n.aabb_min[a]) || !std::isfinite(n.aabb_max[a])) part_ok[w] = false;
-                    part_bound[w][a] = std::max(part_bound[w][a], std::max(std::fabs(n.aabb_min[a]), std::fabs(n.aabb_max[a])));
-                }
-                if (n.triangle_count != 0) continue;
-                const ct_bvh_node &L = d->nodes[n.left_node], &R = d->nodes[n.left_node + 1];
-                DevPair32 &p32 = pairs32[pid_of[i]];
-                DevPair64 &p64 = pairs64[pid_of[i]];
-                for (int a = 0; a < 3; a++) {
-                    p64.lmin[a] = L.aabb_min[a]; p64.lmax[a] = L.aabb_max[a]; p64.rmin[a] = R.aabb_min[a]; p64.rmax[a] = R.aabb_max[a];
-                    p32.lmin[a] = (float)L.aabb_min[a]; p32.lmax[a] = (float)L.aabb_max[a];
-                    p32.rmin[a] = (float)R.aabb_min[a]; p32.rmax[a] = (float)R.aabb_max[a];
-                }
-                child_ref(n.left_node, p32.l_ref, p32.l_cnt);
-                child_ref(n.left_node + 1, p32.r_ref, p32.r_cnt);
-            }
-        });
-        for (int w = 0; w < kHostThreads; w++) {
-            boxes_ok = boxes_ok && part_ok[w];
-            for (int a = 0; a < 3; a++) bound[a] = std::max(bound[a], part_bound[w][a]);
+        // staging copies of the caller's arrays, freed again below
+        ct_bvh_node *raw_nodes = nullptr; uint32_t *raw_pid = nullptr, *raw_idx = nullptr; unsigned char *raw_tris = nullptr; BuildReport *drep = nullptr;
+        const size_t tri_bytes = (size_t)(d->n_triangles - 1) * d->triangle_stride + 72;      // the last triangle may end at its third vertex
+        auto release = [&] { cudaFree(raw_nodes); cudaFree(raw_pid); cudaFree(raw_idx); cudaFree(raw_tris); cudaFree(drep); };
+        auto staged = [&](cudaError_t e) { if (e != cudaSuccess) { release(); free_device(s); } return e; };
+        CU(staged(cudaMalloc(&raw_nodes, (size_t)d->n_nodes * sizeof(ct_bvh_node))));
+        CU(staged(cudaMalloc(&raw_pid, (size_t)d->n_nodes * 4)));
+        CU(staged(cudaMalloc(&raw_idx, (size_t)d->n_triangles * 4)));
+        CU(staged(cudaMalloc(&raw_tris, tri_bytes)));
+        CU(staged(cudaMalloc(&drep, sizeof rep)));
+        rep.bad_pos = kNoPos; rep.pos0 = kNoPos;
+        CU(staged(cudaMemcpyAsync(drep, &rep, sizeof rep, cudaMemcpyHostToDevice, s.stream)));
+        CU(staged(cudaMemcpyAsync(raw_nodes, d->nodes, (size_t)d->n_nodes * sizeof(ct_bvh_node), cudaMemcpyHostToDevice, s.stream)));
+        CU(staged(cudaMemcpyAsync(raw_pid, pid_of.data(), (size_t)d->n_nodes * 4, cudaMemcpyHostToDevice, s.stream)));
+        if (dpp) {
+            CU(staged(cudaMemsetAsync(dpp, 0xff, (size_t)std::max<uint32_t>(n_pairs, 1) * 4, s.stream)));
+            CU(staged(cudaMemsetAsync(dtp, 0xff, (size_t)d->n_triangles * 4, s.stream)));
         }
+        const int build_blocks = s.n_sm * 8;
+        k_build_pairs<<<build_blocks, 256, 0, s.stream>>>(raw_nodes, raw_pid, d->n_nodes, dp32, dp64, dpp, dtp, d->n_triangles, drep);
+        CU(staged(cudaMemcpyAsync(raw_idx, d->tri_indexes, (size_t)d->n_triangles * 4, cudaMemcpyHostToDevice, s.stream)));
+        CU(staged(cudaMemcpyAsync(raw_tris, d->triangles, tri_bytes, cudaMemcpyHostToDevice, s.stream)));
+        CU(staged(cudaMemcpyAsync(dm, d->materials, (size_t)d->n_triangles * sizeof(ct_material), cudaMemcpyHostToDevice, s.stream)));
+        k_build_tris<<<build_blocks, 256, 0, s.stream>>>(raw_tris, (uint32_t)d->triangle_stride, raw_idx, dm, d->n_triangles, dt, dt32, drep);
+        CU(staged(cudaGetLastError()));
+        CU(staged(cudaMemcpyAsync(&rep, drep, sizeof rep, cudaMemcpyDeviceToHost, s.stream)));
+        CU(staged(cudaStreamSynchronize(s.stream)));
+        release();
     }
+    if (rep.bad_pos != kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes[%u] = %u out of range", rep.bad_pos, d->tri_indexes[rep.bad_pos]); }
+    if (rep.pos0 == kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes is not a permutation (triangle 0 missing)"); }
+    p.pos_of_tri0 = rep.pos0;
+    s.any_reflective = rep.any_reflective != 0;
     for (int a = 0; a < 3; a++) {
-        p.bound[a] = (boxes_ok && bound[a] < 1e30) ? bound[a] : INFINITY;
+        double bound;
+        memcpy(&bound, &rep.bound_bits[a], sizeof bound);
+        p.bound[a] = (!rep.boxes_bad && bound < 1e30) ? bound : INFINITY;
         p.root_min[a] = d->nodes[0].aabb_min[a]; p.root_max[a] = d->nodes[0].aabb_max[a];
         p.root_min32[a] = (float)p.root_min[a]; p.root_max32[a] = (float)p.root_max[a];
     }
-    child_ref(0, p.root_ref, p.root_cnt);
-    p.n_pairs = n_pairs;
-    lap("pairs (host)");
-    // triangles in leaf order with precomputed edges
-    std::vector<DevTri> tris(d->n_triangles);
-    std::vector<DevTri32> tris32(d->n_triangles);
-    uint32_t pos0 = kNoPos;
-    const unsigned char *tbase = static_cast<const unsigned char *>(d->triangles);
-    {
-        uint32_t part_pos0[kHostThreads], part_bad[kHostThreads];
-        bool part_refl[kHostThreads];
-        for (int w = 0; w < kHostThreads; w++) { part_pos0[w] = kNoPos; part_bad[w] = kNoPos; part_refl[w] = false; }
-        parallel_for(d->n_triangles, kHostThreads, [&](uint32_t q0, uint32_t q1, int w) {
-            for (uint32_t pos = q0; pos < q1; pos++) {
-                uint32_t k = d->tri_indexes[pos];
-                if (k >= d->n_triangles) { part_bad[w] = pos; return; }
-                if (k == 0) part_pos0[w] = pos;
-                double v[9];
-                memcpy(v, tbase + (size_t)k * d->triangle_stride, sizeof v);
-                for (int a = 0; a < 3; a++) {
-                    tris[pos].p1[a] = v[a];
-                    tris[pos].e1[a] = v[3 + a] - v[a];
-                    tris[pos].e2[a] = v[6 + a] - v[a];
-                }
-                tris[pos].orig = k; tris[pos].pad = 0;
-                // fp32 copy + magnitudes for tri_filter_miss (rounded up; NaN k1 = "never certify")
-                DevTri32 &t32 = tris32[pos];
-                double k1 = 0, k2 = 0, k3 = 0;
-                for (int a = 0; a < 3; a++) {
-                    t32.p1[a] = (float)tris[pos].p1[a]; t32.e1[a] = (float)tris[pos].e1[a]; t32.e2[a] = (float)tris[pos].e2[a];
-                    k3 = std::max(k3, std::fabs(tris[pos].p1[a])); k1 = std::max(k1, std::fabs(tris[pos].e1[a])); k2 = std::max(k2, std::fabs(tris[pos].e2[a]));
-                }
-                auto up = [](double x) { float f = (float)x; return ((double)f < x) ? std::nextafterf(f, INFINITY) : f; };
-                const bool in_range = k1 >= 0x1p-30 && k1 <= 0x1p30 && k2 >= 0x1p-30 && k2 <= 0x1p30 && k3 <= 0x1p40;   // NaNs fail
-                t32.k1 = in_range ? up(k1) : NAN; t32.k2 = up(k2); t32.k3 = up(k3);
-                if (d->materials[k].reflection > 0.0f) part_refl[w] = true;
-            }
-        });
-        for (int w = 0; w < kHostThreads; w++) {
-            if (part_bad[w] != kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes[%u] = %u out of range", part_bad[w], d->tri_indexes[part_bad[w]]); }
-            if (part_pos0[w] != kNoPos) pos0 = part_pos0[w];
-            if (part_refl[w]) s.any_reflective = true;
-        }
-    }
-    if (pos0 == kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes is not a permutation (triangle 0 missing)"); }
-    p.pos_of_tri0 = pos0;
-    lap("triangles (host)");
+    p.pairs32 = dp32; p.pairs64 = dp64; p.tris = dt; p.tris32 = dt32; p.materials = dm;
+    p.pair_parent = dpp; p.tri_parent = dtp;
+    lap("scene arrays built on the device");
     std::vector<DevLight> lights(std::max<uint32_t>(d->n_lights, 1));
     for (uint32_t i = 0; i < d->n_lights; i++) {
         lights[i].type = d->lights[i].type; lights[i].intensity = d->lights[i].intensity;
@@ -1499,24 +1547,12 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     }
     p.n_slights = (uint32_t)slights.size();
     p.occ_words = std::max<uint32_t>((d->n_lights + 31u) / 32u, 1u);
-    p.n_nodes = d->n_nodes;
-    DevPair32 *dp32 = nullptr; DevPair64 *dp64 = nullptr; DevTri *dt = nullptr; ct_material *dm = nullptr; DevLight *dl = nullptr; DevShadowLight *dsl = nullptr;
-    TRY(dev_alloc(s, &dp32, pairs32.size())); TRY(dev_alloc(s, &dp64, pairs64.size())); TRY(dev_alloc(s, &dt, tris.size()));
-    DevTri32 *dt32 = nullptr;
-    TRY(dev_alloc(s, &dt32, tris32.size()));
-    CU(cudaMemcpy(dt32, tris32.data(), tris32.size() * sizeof(DevTri32), cudaMemcpyHostToDevice));
-    p.tris32 = dt32;
-    TRY(dev_alloc(s, &dm, d->n_triangles)); TRY(dev_alloc(s, &dl, lights.size()));
+    DevLight *dl = nullptr; DevShadowLight *dsl = nullptr;
+    TRY(dev_alloc(s, &dl, lights.size()));
     TRY(dev_alloc(s, &dsl, slights.size()));
     if (!slights.empty()) CU(cudaMemcpy(dsl, slights.data(), slights.size() * sizeof(DevShadowLight), cudaMemcpyHostToDevice));
-    p.slights = dsl;
-    CU(cudaMemcpy(dp32, pairs32.data(), pairs32.size() * sizeof(DevPair32), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dp64, pairs64.data(), pairs64.size() * sizeof(DevPair64), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dt, tris.data(), tris.size() * sizeof(DevTri), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dm, d->materials, (size_t)d->n_triangles * sizeof(ct_material), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dl, lights.data(), lights.size() * sizeof(DevLight), cudaMemcpyHostToDevice));
-    p.pairs32 = dp32; p.pairs64 = dp64; p.tris = dt;
-    lap("scene arrays to the device"); p.materials = dm; p.lights = dl;
+    p.slights = dsl; p.lights = dl;
 
     memcpy(p.cam, d->camera_position, sizeof p.cam);
     memcpy(p.rot, d->camera_rotation, sizeof p.rot);
@@ -1546,31 +1582,11 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     s.levels = levels;
     TRY(dev_alloc(s, &s.occ_all, (size_t)p.cap * p.occ_words * levels, true));
     p.occ = s.occ_all;
-    // parked rays: only needed when a DFS can run past the budget at all
-    s.can_overflow = (uint64_t)d->n_nodes + d->n_triangles > p.budget;
     if (s.can_overflow) {
         p.ovf_cap = 1u << 18;          // parked rays per launch (16 MB); a full buffer means finishing rays in place, which must stay hypothetical
         TRY(dev_alloc(s, &s.ovf_all, (size_t)p.ovf_cap * 2 * levels));
         TRY(dev_alloc(s, &s.ovf_huge_all, (size_t)p.ovf_cap * 2 * levels));
         p.ovf = s.ovf_all; p.ovf_huge = s.ovf_huge_all;
-        // who holds whose box: lets k_overflow_huge check a triangle's ancestor chain without walking down
-        std::vector<uint32_t> pair_parent(std::max<uint32_t>(n_pairs, 1), kNoPos), tri_parent(d->n_triangles, kNoPos);
-        for (uint32_t i = 0; i < d->n_nodes; i++) {
-            const ct_bvh_node &n = d->nodes[i];
-            if (n.triangle_count != 0) continue;
-            for (uint32_t side = 0; side < 2; side++) {
-                const uint32_t c = n.left_node + side;
-                const ct_bvh_node &ch = d->nodes[c];
-                const uint32_t code = 2u * pid_of[i] + side;
-                if (ch.triangle_count == 0) pair_parent[pid_of[c]] = code;
-                else for (uint32_t k = 0; k < ch.triangle_count; k++) tri_parent[ch.first_triangle_index + k] = code;
-            }
-        }
-        uint32_t *dpp, *dtp;
-        TRY(dev_alloc(s, &dpp, pair_parent.size())); TRY(dev_alloc(s, &dtp, tri_parent.size()));
-        CU(cudaMemcpy(dpp, pair_parent.data(), pair_parent.size() * 4, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(dtp, tri_parent.data(), tri_parent.size() * 4, cudaMemcpyHostToDevice));
-        p.pair_parent = dpp; p.tri_parent = dtp;
     }
     if (levels > 1) {
         TRY(dev_alloc(s, &s.hitb_t_all, (size_t)p.cap * levels)); TRY(dev_alloc(s, &s.hitb_pos_all, (size_t)p.cap * levels));
