@@ -345,7 +345,7 @@ def main():
         # straight into GPU 0's framebuffer (multi.SharedFrame / ct_gpu_render_shared)
         gpu = api.GpuRenderer(dev).upload(hs.to_flat(with_bvh=True), W, H, max_depth=depth, flags=wflags)
         gpu.set_stream(stream.cuda_stream)
-        shared = multi.SharedFrame(gpu, root=0)
+        shared = multi.SharedFrame(gpu, root=0, stream=stream)
     upload_ms = (time.time() - t0) * 1e3
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")      # > 126 MB L2
     pinned = torch.zeros((H, W), dtype=torch.int32).pin_memory()
@@ -363,7 +363,7 @@ def main():
                 e1.record(stream)
             stream.synchronize()
             return st, e0.elapsed_time(e1)
-        shared.begin()                                       # root zeroes the cursor, barrier
+        shared.begin()                                       # root zeroes the cursor; rendezvous on the render stream
         if to_host:
             gpu.set_camera(cam_pos, cam_rot)                 # the camera is the per-frame input of every rank
         with torch.cuda.stream(stream):

@@ -49,6 +49,7 @@ struct GpuApi {
     int (*gather_rows)(int, int, int, int) = nullptr;
     int (*share_export)(int, ct_gpu_share *) = nullptr;
     int (*share_attach)(int, const ct_gpu_share *) = nullptr;
+    int (*share_partition)(int, int, int) = nullptr;
     int (*share_reset)(int) = nullptr;
     int (*render_shared)(int, int, int, ct_ray_counters *) = nullptr;
     int (*shutdown)(int) = nullptr;
@@ -75,6 +76,7 @@ struct GpuApi {
         gather_rows = (int (*)(int, int, int, int))sym("ct_gpu_gather_rows");
         share_export = (int (*)(int, ct_gpu_share *))sym("ct_gpu_share_export");
         share_attach = (int (*)(int, const ct_gpu_share *))sym("ct_gpu_share_attach");
+        share_partition = (int (*)(int, int, int))sym("ct_gpu_share_partition");
         share_reset = (int (*)(int))sym("ct_gpu_share_reset");
         render_shared = (int (*)(int, int, int, ct_ray_counters *))sym("ct_gpu_render_shared");
         shutdown = (int (*)(int))sym("ct_gpu_shutdown");
@@ -142,6 +144,8 @@ Boss *boss_create(Scene *scene, const ct_host_boss_config *cfg) {
             h.struct_size = sizeof h;
             b->gpu.check(b->gpu.share_export(cfg->devices[0], &h), "ct_gpu_share_export");
             for (int i = 1; i < cfg->n_devices; i++) b->gpu.check(b->gpu.share_attach(cfg->devices[i], &h), "ct_gpu_share_attach");
+            // every device renders every frame: deal most chunks round-robin, steal the rest (ct_gpu_share_partition)
+            for (int i = 0; i < cfg->n_devices; i++) b->gpu.check(b->gpu.share_partition(cfg->devices[i], i, cfg->n_devices), "ct_gpu_share_partition");
         }
         b->tile_rows = rows;
         b->n_tiles = (b->y_hi - b->y_lo + rows - 1) / rows;

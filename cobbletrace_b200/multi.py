@@ -109,23 +109,36 @@ class SharedFrame:
     """N ranks, one GPU each, one frame: see the module docstring.  `renderer` is this rank's GpuRenderer with the
     scene already uploaded; rank `root`'s framebuffer receives the whole frame."""
 
-    def __init__(self, renderer, root: int = 0):
+    def __init__(self, renderer, root: int = 0, stream=None, partition: bool = True):
+        """`stream`: the torch.cuda.Stream the renderer launches on (ct_gpu_set_stream).  With it, the per-frame
+        rendezvous is an all-reduce of one word ON THAT STREAM: the ranks' kernels start within microseconds of each
+        other instead of a host-side barrier's exit skew (which the rank that starts first pays for in full: it
+        keeps stealing until the last rank is done).  Without it (CPU tests, gloo): dist.barrier()."""
         self.r, self.root = renderer, root
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self._stream = stream
+        self._token = torch.zeros(1, dtype=torch.int32, device=stream.device) if (stream is not None and self.world > 1) else None
         box = [renderer.share_export() if self.rank == root else None]
         if self.world > 1:
             dist.broadcast_object_list(box, src=root)
             if self.rank != root:
                 renderer.share_attach(box[0])
         self.handle = box[0]
+        if partition and self.world > 1:
+            # every rank renders every frame: most chunks are dealt round-robin, the rest stolen (ct_gpu_share_partition)
+            renderer.share_partition(self.rank, self.world)
 
     def begin(self):
         """Root zeroes the cursor; nobody may start stealing before that (barrier)."""
         if self.rank == self.root:
             self.r.share_reset()
         if self.world > 1:
-            dist.barrier()
+            if self._token is not None:
+                with torch.cuda.stream(self._stream):
+                    dist.all_reduce(self._token)      # stream-ordered: after the root's reset, before anybody's kernels
+            else:
+                dist.barrier()
 
     def render(self, counters: bool = False):
         """This rank's share of the frame (asynchronous on the renderer's stream)."""
@@ -138,5 +151,7 @@ class SharedFrame:
             dist.barrier()
 
     def close(self):
+        if self.world > 1:
+            self.r.share_partition(0, 0)
         if self.rank != self.root and self.world > 1:
             self.r.share_attach(None)

@@ -146,6 +146,7 @@ int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *coun
  *
  *   root:    ct_gpu_share_export(dev, &h)  -> ship h to the others (it is plain bytes)
  *   others:  ct_gpu_share_attach(dev, &h)
+ *   all:     ct_gpu_share_partition(dev, k, n)   (optional, recommended: see below)
  *   frame:   root: ct_gpu_share_reset(dev); [barrier]; all: ct_gpu_render_shared(dev, y0, y1, ..); ct_gpu_sync(dev);
  *            [barrier]; root: ct_gpu_readback(dev, ...)
  */
@@ -161,6 +162,14 @@ typedef struct ct_gpu_share {
 int ct_gpu_share_export(int device, ct_gpu_share *out);
 int ct_gpu_share_attach(int device, const ct_gpu_share *root);   /* root == NULL detaches */
 int ct_gpu_share_reset(int device);                              /* root only: zero the cursor; synchronises */
+/* Declare that `count` GPUs render every shared frame and that this one is number `index` (0..count-1, all different).
+ * Then only part of the chunks is stolen: of every 8*count consecutive chunks, 7*count are dealt round-robin
+ * (GPU k owns chunks k, k+count, ... -- no remote atomics, and an equal share of the lighting work that follows,
+ * which stealing alone does not balance: the GPU next to the cursor steals cheaper and ends up with more paths to
+ * light), the last `count` are stolen from the root's cursor as before (absorbs a slower or busier GPU).  Every declared
+ * participant must then call ct_gpu_render_shared for every frame.  count <= 1 takes the declaration back: pure stealing,
+ * any subset of the GPUs renders the whole frame.  The dealt fraction is option "shared_static_eighths" (0..8, default 7). */
+int ct_gpu_share_partition(int device, int index, int count);
 /* ct_gpu_render_tile for a frame shared between GPUs.  Without an attach it behaves like a one-GPU frame whose
  * cursor must be reset with ct_gpu_share_reset first. */
 int ct_gpu_render_shared(int device, int y_start, int y_end, ct_ray_counters *counters);
@@ -204,6 +213,7 @@ int ct_gpu_sync(int device);
  *   "emulate_ranks"     R > 1: a profiling aid -- every render takes only every R-th chunk of the tile, i.e. the share
  *                       one of R GPUs gets in a shared frame (the other pixels are simply not rendered); applies to
  *                       the next render, 0 / 1 = off.
+ *   "shared_static_eighths"  see ct_gpu_share_partition.
  *   "shared_chunk_shift"  log2 of the pixels a warp steals at a time in a shared frame: 5 (default, also 0) or 6. */
 int ct_gpu_set_option(const char *name, long long value);
 

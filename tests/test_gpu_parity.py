@@ -232,6 +232,38 @@ def test_shared_frame_mode_on_one_gpu(golden, scene_loader, gpu):
     assert np.array_equal(gpu.readback(), want)
 
 
+@pytest.mark.parametrize("count,eighths", [(2, 7), (3, 7), (8, 7), (4, 8), (4, 0), (5, 3)])
+def test_shared_frame_partition_covers_the_frame_once(count, eighths, golden, scene_loader, gpu):
+    """ct_gpu_share_partition: of every 8*count chunks `eighths`*count are dealt round-robin, the rest stolen from the
+    cursor.  One GPU plays all `count` participants in turn (the first one to run steals every stolen chunk): together
+    they must trace every pixel exactly once -- the ray counts add up to the one-GPU frame's and the frame is identical."""
+    fs, meta = case_scene("bunny_refl_d2_160", golden, scene_loader)
+    want = load_frames("bunny_refl_d2_160")["frame"]
+    gpu.upload(fs, meta["width"], meta["height"], max_depth=meta["depth"])
+    gpu.render_tile()
+    whole = gpu.counters(reset=True)
+    gpu.upload(fs, meta["width"], meta["height"], max_depth=meta["depth"])      # fresh framebuffer
+    gpu.share_attach(gpu.share_export())
+    ct.api.set_option("shared_static_eighths", eighths)
+    try:
+        gpu.share_reset()
+        parts = []
+        for k in range(count):
+            gpu.share_partition(k, count)
+            parts.append(gpu.render_shared(counters=True))
+            if k == 0 and count > 1 and eighths > 0:
+                assert not np.array_equal(gpu.readback(), want)      # one participant alone does not finish the frame
+        assert np.array_equal(gpu.readback(), want)
+        for key in ("rays_primary", "rays_shadow", "rays_reflection"):
+            assert sum(p[key] for p in parts) == whole[key], key
+        if eighths == 8:
+            assert max(p["rays_primary"] for p in parts) <= min(p["rays_primary"] for p in parts) + 64 * 2
+    finally:
+        ct.api.set_option("shared_static_eighths", 7)
+        gpu.share_partition(0, 0)
+        gpu.share_attach(None)
+
+
 def test_subsampling_against_reference_and_oracle(golden, scene_loader, gpu):
     """CT_FLAG_SUBSAMPLING = settings.subsampling (raythread.cpp:512-531): one tile per frame against frames of the
     compiled reference (one worker thread), then two tiles in sequence against the oracle run the same way."""

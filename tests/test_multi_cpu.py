@@ -104,6 +104,7 @@ class _FakeRenderer:
         self.rank, self.path, self.n_chunks = rank, path, n_chunks
         self.calls = []
         self.mem = None
+        self.part = None
 
     def share_export(self):
         np.lib.format.open_memmap(self.path, mode="w+", dtype=np.int64, shape=(1 + self.n_chunks,))[:] = -1
@@ -116,6 +117,10 @@ class _FakeRenderer:
         if handle is not None:
             self.mem = np.load(handle.decode(), mmap_mode="r+")
 
+    def share_partition(self, index, count):
+        self.calls.append("partition" if count > 1 else "unpartition")
+        self.part = (index, count) if count > 1 else None
+
     def share_reset(self):
         self.calls.append("reset")
         self.mem[0] = 0
@@ -125,17 +130,36 @@ class _FakeRenderer:
         import fcntl, time
         self.calls.append("render")
         took = 0
+        mem = np.load(self.path, mmap_mode="r+")
+
+        def trace(idx):
+            assert mem[1 + idx] == -1, "chunk rendered twice"
+            mem[1 + idx] = self.rank; mem.flush()                   # "peer store" of the finished chunk into the root's frame
+            time.sleep(0.002 if self.rank == 1 else 0.0005)
+            return 1
+        # the numbering of next_chunk (ct_gpu.cu): groups of 8R chunks, 7R dealt round-robin, R stolen from the cursor
+        R, E = (self.part[1], 7) if self.part else (1, 0)
+        G = 8 * R
+        n_groups = (self.n_chunks + G - 1) // G
+        if self.part:
+            for g in range(n_groups):
+                for j in range(E):
+                    idx = g * G + j * R + self.part[0]
+                    if idx < self.n_chunks:
+                        took += trace(idx)
+        per = (8 - E) * R
         with open(self.path + ".lock", "a+") as lock:
             while True:
                 fcntl.flock(lock, fcntl.LOCK_EX)                    # "atomicAdd" on the shared cursor
-                mem = np.load(self.path, mmap_mode="r+")
-                c = int(mem[0]); mem[0] = c + 1; mem.flush()
+                cur = np.load(self.path, mmap_mode="r+")
+                c = int(cur[0]); cur[0] = c + 1; cur.flush()
                 fcntl.flock(lock, fcntl.LOCK_UN)
-                if c >= self.n_chunks:
+                g = c // per
+                if g >= n_groups:
                     break
-                mem[1 + c] = self.rank; mem.flush()                 # "peer store" of the finished chunk into the root's frame
-                took += 1
-                time.sleep(0.002 if self.rank == 1 else 0.0005)
+                idx = g * G + E * R + (c - g * per)
+                if idx < self.n_chunks:
+                    took += trace(idx)
         return {"rays_primary": took}
 
     def sync(self):
@@ -166,7 +190,8 @@ def _shared_worker(rank, world, port, path, n_chunks, out_path):
         if rank == 0:
             np.load(path, mmap_mode="r+")[1:] = -1
     sf.close()
-    want = ["export"] + ["reset", "render", "sync"] * 3 if rank == 0 else ["attach"] + ["render", "sync"] * 3 + ["detach"]
+    want = (["export", "partition"] + ["reset", "render", "sync"] * 3 + ["unpartition"] if rank == 0
+            else ["attach", "partition"] + ["render", "sync"] * 3 + ["unpartition", "detach"])
     assert r.calls == want, r.calls
     if rank == 0:
         np.save(out_path, np.array(shares))
@@ -175,7 +200,8 @@ def _shared_worker(rank, world, port, path, n_chunks, out_path):
 
 def test_shared_frame_protocol_two_ranks(tmp_path):
     """multi.SharedFrame on 2 gloo ranks: the root exports, the other attaches, every frame is reset -> barrier ->
-    render -> sync -> barrier, all chunks are taken exactly once and land in the root's frame."""
+    render -> sync -> barrier, all chunks are taken exactly once (most dealt round-robin, the rest stolen from the shared
+    cursor: ct_gpu_share_partition) and land in the root's frame."""
     out = str(tmp_path / "shares.npy")
     mp.spawn(_shared_worker, args=(2, _free_port(), str(tmp_path / "frame.npy"), 60, out), nprocs=2, join=True)
     shares = np.load(out)
