@@ -10,9 +10,9 @@ step     one frame: every row tile of the frame through the hot path
 value    device-resident throughput (scene in HBM, CUDA events around the frame's kernels [+ gather at N>1])
 e2e      the same frame through the reference-facing plugin call with HOST buffers: camera in
          (ct_gpu_set_camera), bitmap out (ct_gpu_readback into pinned host memory), wall clock
-N > 1    one process per GPU (torchrun), scene replicated; all GPUs render the same frame, stealing 32-pixel chunks
-         from one cursor on GPU 0 (atomics over NVLink) and storing finished pixels straight into GPU 0's
-         framebuffer (peer stores); strong scaling of the same frame
+N > 1    one process per GPU (torchrun), scene replicated; all GPUs render the same frame in 32-pixel chunks (7/8 dealt
+         round-robin, 1/8 stolen from one cursor on GPU 0 with atomics over NVLink) and store finished pixels straight
+         into GPU 0's framebuffer (peer stores); strong scaling of the same frame
 --impl reference   the reference's own boss/worker CPU renderer (oracle/_ref/ct_ref, compiled from the unmodified
          sources) on this box's host cores, same scene files, same metric.
 """
@@ -441,7 +441,7 @@ def main():
                    "l2": "flushed between timed steps (256 MiB device write, outside the timed events)",
                    "timing": "CUDA events on the launching stream around each frame's kernels" + ("; max over ranks per step (pixels land in GPU 0's framebuffer inside those kernels)" if N > 1 else ""),
                    "tiles_per_frame": st["tiles_total"],
-                   "parallelism": (f"{N} GPUs, one process each, scene replicated: 32-pixel chunks stolen from one cursor on GPU 0 (atomics over NVLink), "
+                   "parallelism": (f"{N} GPUs, one process each, scene replicated: 32-pixel chunks, 7/8 dealt round-robin and 1/8 stolen from one cursor on GPU 0 (atomics over NVLink), "
                                    "finished pixels stored straight into GPU 0's framebuffer (peer stores, CUDA IPC); no collective" if N > 1
                                    else "1 GPU; persistent warps steal 32-pixel chunks from a device-side cursor")},
         "ms_per_frame": ms_per_step,

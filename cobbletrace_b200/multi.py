@@ -4,10 +4,11 @@ The path shards by pixels and has exactly one exchange step -- collecting 4-byte
 Two ways to run a frame on N GPUs, scene replicated on each:
 
   SharedFrame (the fast path, used by bench.py): every GPU renders the same tile with ct_gpu_render_shared; its
-      primary-ray warps steal 32-pixel chunks from ONE cursor in GPU 0's memory (atomics over NVLink) and its
-      shading kernels store finished pixels straight into GPU 0's framebuffer (peer stores through CUDA IPC).
-      No collective and no host in the loop; torch.distributed only ships the IPC handle and provides the
-      per-frame barriers.
+      primary-ray warps trace 32-pixel chunks -- 7/8 dealt round-robin, 1/8 stolen from ONE cursor in GPU 0's memory
+      (atomics over NVLink; ct_gpu_share_partition) -- and its shading kernels store finished pixels straight into
+      GPU 0's framebuffer (peer stores through CUDA IPC).  No data-path collective and no host in the loop;
+      torch.distributed ships the IPC handle, and per frame a one-word all-reduce on the render stream is the
+      rendezvous and a barrier marks the end.
   row tiles (ct_host_boss_* / exchange_tiles / gather_rows_to_root): tiles stolen from a host-side counter and
       gathered with point-to-point sends (NCCL on GPUs, gloo on CPU for the tests) -- the portable variant.
 """
