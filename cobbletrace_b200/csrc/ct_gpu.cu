@@ -1351,7 +1351,7 @@ __global__ void __launch_bounds__(256) k_build_pairs(const ct_bvh_node *__restri
             if (!(n.aabb_min[a] <= n.aabb_max[a]) || isinf(n.aabb_min[a]) || isinf(n.aabb_max[a])) bad = true;
             else bound[a] = fmax(bound[a], fmax(fabs(n.aabb_min[a]), fabs(n.aabb_max[a])));
         }
-        if (n.triangle_count != 0 || n.left_node == 0u || (uint64_t)n.left_node + 1u >= n_nodes) continue;      // leaf, or an unreachable slot (the reference never uses node 1) holding zeros or garbage
+        if (n.triangle_count != 0 || n.left_node == 0u || (uint64_t)n.left_node + 1u >= n_nodes) continue;      // leaf, or an unreachable slot holding zeros or garbage (the root is nobody's child)
         const uint32_t pid = pid_of[i];
         const ct_bvh_node L = nodes[n.left_node], R = nodes[n.left_node + 1u];
         DevPair32 p32;

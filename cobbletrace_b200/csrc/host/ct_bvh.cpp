@@ -9,10 +9,11 @@
 //   * multi-threaded (once the tracer takes milliseconds, the 0.5 s single-threaded build is what
 //     a user waits for).  The reference numbers nodes in the order its recursion allocates them (nodesUsed++ at each
 //     split, left subtree before right), so a subtree occupies one contiguous block of indices and its internal
-//     numbering does not depend on anything outside it.  The top of the tree is split sequentially (its bounds
-//     computed by all threads), the subtrees below a frontier are built concurrently with block-local numbering,
-//     and one pre-order pass over the top assigns every block its place.  The in-place partition of the index
-//     array (bvh.cpp:70-81) is order-dependent and stays sequential per node; disjoint ranges run concurrently.
+//     numbering does not depend on anything outside it.  Nodes are tasks in one pool: a big node is split (the
+//     in-place partition of the index array, bvh.cpp:70-81, is order-dependent and stays sequential per node;
+//     disjoint ranges run concurrently) and its children are queued; a node at or below the grain is built with its
+//     whole subtree as a block with block-local numbering; one pre-order pass over the top then assigns every block
+//     its place and the blocks are copied there concurrently.
 //
 // Rounding points that decide the partition (all reproduced):
 //   centroid = (p1+p2+p3) * 0.3333f   -> fp64 product with the float constant widened   (bvh.cpp:112)
@@ -22,6 +23,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,9 +45,10 @@ inline double hi(double a, double b) { return (a > b) ? a : b; }   // mymath.h:1
 // the partition swaps them together with the indices, so that the bounds of a range are a streaming read instead
 // of a gather through tri_index (4x faster single-threaded on the 868k-triangle scene).  Same comparisons, same
 // swaps, same result.
+struct Tri9 { double v[9]; };        // a Triangle without constructors (the copies are written by worker threads)
 struct Work {
-    std::vector<Triangle> tri;      // [n]
-    std::vector<double> centroid;   // [3 n]
+    std::vector<Tri9, NoInitAlloc<Tri9>> tri;          // [n]
+    std::vector<double, NoInitAlloc<double>> centroid; // [3 n]
     std::vector<uint32_t> *index;   // -> Scene::tri_index
 };
 
@@ -51,7 +56,7 @@ struct Work {
 void fit_range(const Work &s, uint32_t first, uint32_t count, double mn[3], double mx[3]) {
     for (int a = 0; a < 3; a++) { mn[a] = (double)1e30f; mx[a] = (double)-1e30f; }
     for (uint32_t i = 0; i < count; i++) {
-        const double *v = &s.tri[first + i].p1.x;                 // 9 packed doubles
+        const double *v = s.tri[first + i].v;                     // 9 packed doubles
         for (int p = 0; p < 3; p++)
             for (int a = 0; a < 3; a++) {
                 mn[a] = lo(mn[a], v[3 * p + a]);
@@ -135,6 +140,17 @@ void build_block(Work &s, std::vector<ct_bvh_node> &nodes) {
     }
 }
 
+// fn(begin, end) over [0, n) on up to `threads` workers (big, independent slices only)
+template <typename F>
+void run_slices(uint32_t n, int threads, F fn) {
+    const int nt = (int)std::min<uint64_t>((uint64_t)std::max(threads, 1), (n + 65535u) / 65536u);
+    if (nt <= 1) { fn(0u, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([=] { fn((uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt)); });
+    for (auto &t : th) t.join();
+}
+
 int build_threads() {
     if (const char *e = std::getenv("CT_HOST_THREADS")) { int v = std::atoi(e); if (v >= 1) return std::min(v, 64); }
     unsigned hw = std::thread::hardware_concurrency();
@@ -152,84 +168,106 @@ void build_bvh(Scene &s) {
     const double t_start = now();
     s.tri_index.resize(n);
     Work w;
-    w.tri = s.tris;
+    w.tri.resize(n);
     w.centroid.resize((size_t)3 * n);
     w.index = &s.tri_index;
     const double third = (double)0.3333f;
-    for (uint32_t k = 0; k < n; k++) {
-        s.tri_index[k] = k;
-        const Triangle &t = s.tris[k];
-        w.centroid[3 * (size_t)k + 0] = third * ((t.p1.x + t.p2.x) + t.p3.x);
-        w.centroid[3 * (size_t)k + 1] = third * ((t.p1.y + t.p2.y) + t.p3.y);
-        w.centroid[3 * (size_t)k + 2] = third * ((t.p1.z + t.p2.z) + t.p3.z);
-    }
+    run_slices(n, threads, [&](uint32_t k0, uint32_t k1) {
+        for (uint32_t k = k0; k < k1; k++) {
+            s.tri_index[k] = k;
+            const Triangle &t = s.tris[k];
+            memcpy(w.tri[k].v, &t.p1.x, sizeof(Tri9));
+            w.centroid[3 * (size_t)k + 0] = third * ((t.p1.x + t.p2.x) + t.p3.x);
+            w.centroid[3 * (size_t)k + 1] = third * ((t.p1.y + t.p2.y) + t.p3.y);
+            w.centroid[3 * (size_t)k + 2] = third * ((t.p1.z + t.p2.z) + t.p3.z);
+        }
+    });
+    const double t_prologue = now();
 
-    // ---- top of the tree, sequential splits with temporary numbering; nodes at or below `grain` triangles are left
-    // for the blocks.  top[i].left_node indexes `top`; is_block marks frontier nodes.
+    // ---- top of the tree and the blocks below it, as one pool of tasks.  A task = one node: at or below `grain`
+    // triangles it becomes a block (its whole subtree is built on the spot, block-local numbering); above, it is split
+    // (the order-dependent partition runs on this thread, disjoint ranges run concurrently) and its children become
+    // tasks.  The critical path is the root's partition plus half of it, a quarter, ...: about twice the root instead
+    // of once per level.  top[i].left_node indexes `top` (temporary numbering); is_block marks frontier nodes.
     const uint32_t grain = (threads <= 1 || n < 16384) ? n : std::max<uint32_t>(4096, n / (uint32_t)(threads * 3));
-    std::vector<ct_bvh_node> top(1);
-    std::vector<char> is_block(1, 0);
+    std::deque<ct_bvh_node> top(1);                                // deques: references stay valid while other tasks append
+    std::deque<char> is_block(1, 0);
+    std::deque<uint32_t> block_of(1, 0xffffffffu);
+    std::deque<std::vector<ct_bvh_node>> blocks;
     top[0].first_triangle_index = 0; top[0].triangle_count = n;
     fit_range_parallel(w, 0, n, top[0].aabb_min, top[0].aabb_max, threads);
     {
-        std::vector<uint32_t> work(1, 0u);
-        while (!work.empty()) {
-            const uint32_t idx = work.back();
-            work.pop_back();
-            if (top[idx].triangle_count <= grain) { is_block[idx] = 1; continue; }
-            const uint32_t left_count = split_node(w, top[idx]);
-            if (left_count == 0) continue;                          // a big leaf (unsplittable): stays in the top part
-            const uint32_t l = (uint32_t)top.size();
-            top.push_back(ct_bvh_node{}); top.push_back(ct_bvh_node{});
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<uint32_t> ready(1, 0u);
+        int running = 0;
+        auto process = [&](uint32_t idx) {
+            ct_bvh_node node;
+            { std::lock_guard<std::mutex> g(mu); node = top[idx]; }
+            if (node.triangle_count <= grain) {
+                std::vector<ct_bvh_node> *blk;
+                {
+                    std::lock_guard<std::mutex> g(mu);
+                    is_block[idx] = 1; block_of[idx] = (uint32_t)blocks.size();
+                    blocks.emplace_back(1, node);
+                    blk = &blocks.back();
+                }
+                blk->reserve((size_t)2 * node.triangle_count);
+                build_block(w, *blk);
+                return;
+            }
+            const uint32_t left_count = split_node(w, node);
+            if (left_count == 0) return;                            // a big leaf (unsplittable): stays in the top part
+            ct_bvh_node l{}, r{};
+            l.first_triangle_index = node.first_triangle_index; l.triangle_count = left_count;
+            r.first_triangle_index = node.first_triangle_index + left_count; r.triangle_count = node.triangle_count - left_count;
+            // big children: all hands on the bounds while there are not yet enough tasks to go round
+            const int fit_threads = node.triangle_count >= n / 4 ? threads : 1;
+            fit_range_parallel(w, l.first_triangle_index, l.triangle_count, l.aabb_min, l.aabb_max, fit_threads);
+            fit_range_parallel(w, r.first_triangle_index, r.triangle_count, r.aabb_min, r.aabb_max, fit_threads);
+            std::lock_guard<std::mutex> g(mu);
+            const uint32_t li = (uint32_t)top.size();
+            top.push_back(l); top.push_back(r);
             is_block.push_back(0); is_block.push_back(0);
-            ct_bvh_node &node = top[idx];
-            node.left_node = l;
-            top[l].first_triangle_index = node.first_triangle_index;
-            top[l].triangle_count = left_count;
-            top[l + 1].first_triangle_index = node.first_triangle_index + left_count;
-            top[l + 1].triangle_count = node.triangle_count - left_count;
-            node.triangle_count = 0;
-            fit_range_parallel(w, top[l].first_triangle_index, top[l].triangle_count, top[l].aabb_min, top[l].aabb_max, threads);
-            fit_range_parallel(w, top[l + 1].first_triangle_index, top[l + 1].triangle_count, top[l + 1].aabb_min, top[l + 1].aabb_max, threads);
-            work.push_back(l + 1);
-            work.push_back(l);
-        }
-    }
-
-    const double t_top = now();
-    // ---- blocks, concurrently (disjoint index ranges)
-    std::vector<uint32_t> block_of(top.size(), 0xffffffffu);
-    std::vector<std::vector<ct_bvh_node>> blocks;
-    for (uint32_t i = 0; i < top.size(); i++)
-        if (is_block[i]) { block_of[i] = (uint32_t)blocks.size(); blocks.emplace_back(1, top[i]); }
-    {
-        std::vector<uint32_t> order(blocks.size());
-        for (uint32_t b = 0; b < blocks.size(); b++) order[b] = b;
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return blocks[a][0].triangle_count > blocks[b][0].triangle_count; });
-        std::atomic<uint32_t> next{0};
+            block_of.push_back(0xffffffffu); block_of.push_back(0xffffffffu);
+            top[idx].left_node = li;
+            top[idx].triangle_count = 0;
+            ready.push_back(li + 1);
+            ready.push_back(li);
+            cv.notify_all();
+        };
         auto worker = [&] {
-            for (uint32_t k; (k = next.fetch_add(1)) < order.size();) {
-                auto &blk = blocks[order[k]];
-                blk.reserve((size_t)2 * blk[0].triangle_count);
-                build_block(w, blk);
+            std::unique_lock<std::mutex> lk(mu);
+            for (;;) {
+                cv.wait(lk, [&] { return !ready.empty() || running == 0; });
+                if (ready.empty()) { cv.notify_all(); return; }    // nothing queued and nobody left to queue more
+                const uint32_t idx = ready.back();
+                ready.pop_back();
+                running++;
+                lk.unlock();
+                process(idx);
+                lk.lock();
+                running--;
+                if (ready.empty() && running == 0) cv.notify_all();
             }
         };
-        const int nt = (int)std::min<size_t>((size_t)threads, blocks.size());
-        if (nt <= 1) worker();
+        if (threads <= 1) worker();
         else {
             std::vector<std::thread> th;
-            for (int t = 0; t < nt; t++) th.emplace_back(worker);
+            for (int t = 0; t < threads; t++) th.emplace_back(worker);
             for (auto &t : th) t.join();
         }
     }
+    const double t_top = now();
 
-    const double t_blocks = now();
     // ---- final numbering: the reference's allocation order (pre-order over splits, left before right)
     size_t total = top.size();
     for (uint32_t i = 0; i < top.size(); i++) if (is_block[i]) total += blocks[block_of[i]].size() - 1;
-    s.nodes.assign(total, ct_bvh_node{});
+    s.nodes.resize(total);                                         // not filled: every entry is written below
     uint32_t used = 1;
     struct Item { uint32_t top_idx, final_idx; };
+    struct Placed { uint32_t block, root_idx, base; };
+    std::vector<Placed> placed;                                    // where every block goes; copied concurrently below
     std::vector<Item> work(1, Item{0u, 0u});
     while (!work.empty()) {
         const Item it = work.back();
@@ -237,15 +275,9 @@ void build_bvh(Scene &s) {
         if (is_block[it.top_idx]) {
             // the block's root sits at final_idx (allocated by its parent); its other nodes take the next indices in
             // block order, which IS the reference's order because the recursion finishes a subtree before leaving it
-            const auto &blk = blocks[block_of[it.top_idx]];
-            const uint32_t base = used - 1;                         // block-local index k >= 1 -> final index base + k
-            s.nodes[it.final_idx] = blk[0];
-            if (blk[0].triangle_count == 0) s.nodes[it.final_idx].left_node = base + blk[0].left_node;
-            for (uint32_t k = 1; k < blk.size(); k++) {
-                s.nodes[base + k] = blk[k];
-                if (blk[k].triangle_count == 0) s.nodes[base + k].left_node = base + blk[k].left_node;
-            }
-            used += (uint32_t)blk.size() - 1;
+            const uint32_t b = block_of[it.top_idx];
+            placed.push_back(Placed{b, it.final_idx, used - 1});   // block-local index k >= 1 -> final index base + k
+            used += (uint32_t)blocks[b].size() - 1;
             continue;
         }
         s.nodes[it.final_idx] = top[it.top_idx];
@@ -256,9 +288,31 @@ void build_bvh(Scene &s) {
         work.push_back(Item{top[it.top_idx].left_node, l});
     }
     if (used != total) throw std::runtime_error("BVH numbering is inconsistent (internal error)");
+    {
+        std::atomic<uint32_t> next{0};
+        auto copier = [&] {
+            for (uint32_t i; (i = next.fetch_add(1)) < placed.size();) {
+                const auto &blk = blocks[placed[i].block];
+                const uint32_t base = placed[i].base;
+                s.nodes[placed[i].root_idx] = blk[0];
+                if (blk[0].triangle_count == 0) s.nodes[placed[i].root_idx].left_node = base + blk[0].left_node;
+                for (uint32_t k = 1; k < blk.size(); k++) {
+                    s.nodes[base + k] = blk[k];
+                    if (blk[k].triangle_count == 0) s.nodes[base + k].left_node = base + blk[k].left_node;
+                }
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)threads, placed.size());
+        if (nt <= 1) copier();
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; t++) th.emplace_back(copier);
+            for (auto &t : th) t.join();
+        }
+    }
     if (timing)
-        fprintf(stderr, "build_bvh: %d threads, %zu top nodes, %zu blocks: top %.1f ms, blocks %.1f ms, numbering %.1f ms\n", threads, top.size(),
-                blocks.size(), t_top - t_start, t_blocks - t_top, now() - t_blocks);
+        fprintf(stderr, "build_bvh: %d threads, %zu top nodes, %zu blocks: working copies %.1f ms, tree %.1f ms, numbering %.1f ms\n", threads,
+                top.size(), blocks.size(), t_prologue - t_start, t_top - t_prologue, now() - t_top);
 }
 
 }  // namespace cth

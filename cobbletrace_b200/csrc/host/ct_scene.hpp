@@ -5,7 +5,10 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
+#include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ct_gpu.h"
@@ -18,6 +21,18 @@ struct Vec3 { double x = 0, y = 0, z = 0; };
 struct Triangle { Vec3 p1, p2, p3; };   // 72 bytes, == 9 packed doubles
 static_assert(sizeof(Triangle) == 72, "Triangle must be 9 packed doubles");
 
+// std::allocator whose value-less construct() default-initialises: resize() of a vector of PODs allocates without
+// filling, so that big arrays are first touched by the threads that write them.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    template <class U, class... A>
+    void construct(U *p, A &&...a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void *)p) U;
+        else ::new ((void *)p) U(std::forward<A>(a)...);
+    }
+};
+
 struct Scene {
     std::vector<Triangle> tris;
     std::vector<ct_material> mats;       // per triangle
@@ -27,7 +42,7 @@ struct Scene {
     ct_host_settings settings{8, 1, 0, 0};                // scenefile.cpp:23-26
     uint32_t n_spheres = 0;
     // BVH (reference layout)
-    std::vector<ct_bvh_node> nodes;
+    std::vector<ct_bvh_node, NoInitAlloc<ct_bvh_node>> nodes;
     std::vector<uint32_t> tri_index;
 };
 
