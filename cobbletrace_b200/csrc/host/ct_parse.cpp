@@ -9,6 +9,7 @@
 //     Scale, Translate (objectLoader.cpp:27-139), each evaluated ((x*m0 + y*m1) + z*m2) + 1*m3 in fp64.
 // Unlike the reference (assert / exit), malformed input raises an error.
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -215,16 +216,50 @@ bool import_ply_parallel(const Cursor &c0, uint32_t n_vert, uint32_t n_face, std
     if (const char *e = std::getenv("CT_HOST_THREADS")) { int v = std::atoi(e); if (v >= 1) threads = std::min(v, 64); }
     if (threads <= 1 || n_rec < 50000) return false;
     if (s.tris.size() + n_face > 1000000u) return false;            // the sequential path raises the MAX_OBJECTS error
-    std::vector<size_t> start(n_rec), eol(n_rec);
+    // where the records are: the sequential walk (take a line, skip the white space after it) visits the first non-space
+    // character after every run of white space that holds a line end.  Each thread finds those in its slice of the file.
+    std::vector<size_t> start, eol;
     {
-        Cursor c = c0;
-        for (size_t i = 0; i < n_rec; i++) {
-            if (c.eof()) return false;
-            start[i] = c.pos;
-            while (!c.eof() && c.buf[c.pos] != '\n' && c.buf[c.pos] != '\r') c.pos++;
-            eol[i] = c.pos;
-            c.skip_space();
-        }
+        const char *buf = c0.buf;
+        const size_t lo = c0.pos, size = c0.size;
+        auto is_eol = [](char ch) { return ch == '\n' || ch == '\r'; };
+        std::vector<std::vector<size_t>> found(threads);           // (start, eol) pairs of the records that START in the slice
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++)
+            th.emplace_back([&, t] {
+                const size_t a = lo + (size - lo) * (size_t)t / (size_t)threads, b = lo + (size - lo) * (size_t)(t + 1) / (size_t)threads;
+                size_t p = a;
+                bool between = (t == 0);                            // the header's skip_line left the cursor on the first record
+                if (t > 0) {
+                    size_t k = a;
+                    while (k > lo && (buf[k - 1] == ' ' || buf[k - 1] == '\t')) k--;
+                    between = (k > lo) && is_eol(buf[k - 1]);
+                    if (k == lo) between = false;                   // still inside the first record's line
+                }
+                auto &out = found[t];
+                out.reserve((size_t)((b - a) / 16 + 16));
+                for (;;) {
+                    if (!between) {
+                        while (p < size && !is_eol(buf[p])) p++;
+                        if (p >= b) return;                         // the next line end belongs to a later slice (or there is none)
+                        between = true;
+                    }
+                    while (p < size && Cursor::is_space(buf[p])) p++;
+                    if (p >= b || p >= size) return;                // the next record starts in a later slice
+                    const size_t q = p;
+                    while (p < size && !is_eol(buf[p])) p++;
+                    out.push_back(q); out.push_back(p);
+                    between = false;
+                }
+            });
+        for (auto &t : th) t.join();
+        size_t total = 0;
+        for (auto &f : found) total += f.size() / 2;
+        if (total < n_rec) return false;                            // too few lines: the sequential path reports it
+        start.resize(n_rec); eol.resize(n_rec);
+        size_t i = 0;
+        for (auto &f : found)
+            for (size_t k = 0; k + 1 < f.size() && i < n_rec; k += 2, i++) { start[i] = f[k]; eol[i] = f[k + 1]; }
     }
     std::atomic<bool> ok{true};
     auto run = [&](size_t n, auto body) {
@@ -244,7 +279,7 @@ bool import_ply_parallel(const Cursor &c0, uint32_t n_vert, uint32_t n_face, std
     });
     if (!ok) return false;
     const size_t base = s.tris.size();
-    std::vector<Triangle> tris(n_face);
+    s.tris.resize(base + n_face);
     run(n_face, [&](Cursor &c, size_t i) {
         c.pos = start[n_vert + i];
         int n = (int)c.number();
@@ -253,13 +288,11 @@ bool import_ply_parallel(const Cursor &c0, uint32_t n_vert, uint32_t n_face, std
         if (c.pos > eol[n_vert + i]) return false;
         int a = (int)f.x, b = (int)f.y, d = (int)f.z;
         if (a < 0 || b < 0 || d < 0 || (uint32_t)a >= n_vert || (uint32_t)b >= n_vert || (uint32_t)d >= n_vert) return false;
-        tris[i] = place.place(Triangle{verts[a], verts[b], verts[d]});
+        s.tris[base + i] = place.place(Triangle{verts[a], verts[b], verts[d]});
         return true;
     });
-    if (!ok) return false;
-    s.tris.resize(base + n_face);
+    if (!ok) { s.tris.resize(base); return false; }
     s.mats.resize(base + n_face, mat);
-    std::copy(tris.begin(), tris.end(), s.tris.begin() + (ptrdiff_t)base);
     return true;
 }
 
@@ -281,7 +314,13 @@ void import_ply(const ImportSpec &spec, const ct_material &mat, const std::strin
     }
     std::vector<Vec3> verts(n_vert);
     Placement place(spec.position, spec.rotation, spec.scale);
-    if (import_ply_parallel(c, n_vert, n_face, verts, place, mat, s)) return;
+    const bool timing = std::getenv("CT_HOST_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    const bool threaded = import_ply_parallel(c, n_vert, n_face, verts, place, mat, s);
+    if (timing)
+        fprintf(stderr, "import_ply: %u vertices, %u faces, %s: %.1f ms\n", n_vert, n_face, threaded ? "threaded" : "threaded path declined, sequential walk",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    if (threaded) return;
     // the reference's sequential walk over the file (also the path that reports malformed input)
     for (uint32_t i = 0; i < n_vert && !c.eof(); i++) { verts[i] = c.vec3_raw(); c.skip_line(); }
     for (uint32_t i = 0; i < n_face && !c.eof(); i++) {

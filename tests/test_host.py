@@ -146,6 +146,55 @@ def test_threaded_ingest_and_build_match_the_sequential_reference_algorithms(thr
         assert all(np.array_equal(v, getattr(fs, k)) for k, v in b.items())
 
 
+@pytest.mark.parametrize("style", ["crlf", "blank_lines", "indented", "no_final_newline", "short_line"])
+def test_threaded_ply_import_on_untidy_files(style, tmp_path, monkeypatch, capfd):
+    """The threaded PLY import finds its records by the rule of the reference's walk (take the leading numbers of a line,
+    skip to the first non-space character after the line end) in slices of the file: CRLF line ends, blank lines,
+    indented and padded lines and a missing final newline must give what the one-thread walk gives; a vertex line that
+    is too short makes the record run into the next line -- then the sequential walk takes over, same (odd) result."""
+    rng = np.random.default_rng(7)
+    nv, nf = 30000, 30000                               # 60000 records: above the threaded path's threshold
+    verts = rng.normal(size=(nv, 3)).round(4)
+    faces = rng.integers(0, nv, size=(nf, 3))
+    eol = "\r\n" if style == "crlf" else "\n"
+    lines = ["ply", "format ascii 1.0", f"element vertex {nv}", "property float x", "property float y", "property float z",
+             f"element face {nf}", "property list uchar int vertex_indices", "end_header"]
+    for i, v in enumerate(verts):
+        text = f"{v[0]} {v[1]} {v[2]}"
+        if style == "indented":
+            text = " " * (i % 3) + text + " " * (i % 4) + ("\t" if i % 5 == 0 else "")
+        if style == "short_line" and i == 12345:
+            text = f"{v[0]} {v[1]}"
+        lines.append(text)
+        if style == "blank_lines" and i % 7 == 0:
+            lines.extend(["", "   "][: 1 + i % 2])
+    for f in faces:
+        lines.append(f"3 {f[0]} {f[1]} {f[2]}")
+    body = eol.join(lines) + ("" if style == "no_final_newline" else eol)
+    os.makedirs(tmp_path / "models")
+    (tmp_path / "models" / "m.ply").write_text(body, newline="")
+    (tmp_path / "s.json").write_text('{"settings": {"numberOfThreads": 2}, "camera": {"position": [0, 0, -8]}, "lights": [{"type": "ambient", "intensity": 0.5}],'
+                                     ' "objects": [{"type": "import", "format": "ply", "filename": "models/m.ply", "position": [0, 0, 0], "rotation": [0, 0, 0],'
+                                     ' "scale": [1, 1, 1], "color": [255, 255, 255], "specular": 10, "reflection": 0}]}')
+    digests = []
+    monkeypatch.setenv("CT_HOST_TIMING", "1")
+    for threads in ("1", "5", "8"):
+        monkeypatch.setenv("CT_HOST_THREADS", threads)
+        try:
+            fs = host.HostScene.load(str(tmp_path / "s.json"), base_dir=str(tmp_path)).to_flat(with_bvh=False)
+            digests.append((fs.n_tri, fs.geometry_digest()))
+        except RuntimeError as e:
+            digests.append(("error", str(e)))
+    assert digests[0] == digests[1] == digests[2], digests
+    log = [ln for ln in capfd.readouterr().err.splitlines() if ln.startswith("import_ply:")]
+    assert len(log) == 3 and "declined" in log[0]                  # one thread: always the sequential walk
+    if style != "short_line":
+        assert digests[0][0] == nf
+        assert all(", threaded:" in ln for ln in log[1:]), log       # the threaded path really ran
+    else:
+        assert all("declined" in ln for ln in log[1:]), log
+
+
 def test_boss_fails_loudly_without_gpu(scene_loader):
     import torch
     if torch.cuda.is_available():
