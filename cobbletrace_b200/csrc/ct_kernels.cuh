@@ -1,0 +1,770 @@
+// ct_kernels.cuh -- ray generation, work distribution, and the wavefront kernels of one tile
+// (k_primary, k_shadow, k_emit, k_shade, k_bounce, k_overflow, k_overflow_huge, k_resolve, k_subsample, k_supersample) plus the KAT kernels.
+// Part of the single translation unit ct_gpu.cu (everything lives in its anonymous namespace).
+#pragma once
+
+#include "ct_traverse.cuh"
+
+namespace {
+
+// The counter-based stand-in for rand() in the supersampling jitter (the parity harness patches the same
+// function into the compiled reference in place of rand(); DESIGN.md, sampling modes).
+CT_DEV uint32_t hash3(uint32_t x, uint32_t y, uint32_t k) {
+    uint32_t h = x * 0x9E3779B1u ^ (y * 0x85EBCA77u) ^ (k * 0xC2B2AE3Du);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+
+// Canvas point of sample k (= 4 xs + ys) of pixel (x, y): the reference's float bookkeeping (raythread.cpp:461-505)
+// replayed up to that sample -- sampleX/sampleY are jittered, used, un-jittered and stepped in float, so each
+// sample's point depends on the rounding of the ones before it.
+CT_DEV void sample_point(int x, int y, int k, float &px, float &py) {
+    const float stepsize = 0.25f, jitter = 0.03125f;          // 1/(float)samples, stepsize/8
+    float sample_x = (float)x, sample_y = (float)y;
+    uint32_t call = 0;
+    for (int xs = 0; xs < 4; xs++) {
+        sample_y = (float)y;
+        for (int ys = 0; ys < 4; ys++) {
+            float rx = __fdiv_rn(__int2float_rn((int)(hash3((uint32_t)x, (uint32_t)y, call++) & 0x7fffffffu)), 2147483648.0f);   // (float)RAND_MAX
+            float ry = __fdiv_rn(__int2float_rn((int)(hash3((uint32_t)x, (uint32_t)y, call++) & 0x7fffffffu)), 2147483648.0f);
+            rx = __fsub_rn(__fmul_rn(rx, 0.0625f), jitter);
+            ry = __fsub_rn(__fmul_rn(ry, 0.0625f), jitter);
+            sample_x = __fadd_rn(sample_x, rx);
+            sample_y = __fadd_rn(sample_y, ry);
+            if (xs * 4 + ys == k) { px = sample_x; py = sample_y; return; }
+            sample_y = __fadd_rn(__fsub_rn(sample_y, ry), stepsize);
+            sample_x = __fsub_rn(sample_x, rx);
+        }
+        sample_x = __fadd_rn(sample_x, stepsize);
+    }
+    px = sample_x; py = sample_y;
+}
+
+// Primary ray through canvas point (px, py): CanvasToViewport (raythread.cpp:186-194) * camera.rotation (mymath.h:68-75)
+CT_DEV Ray primary_ray_at(const Params &P, float px, float py) {
+    float hh = (float)P.H;                                  // "Keep it square": both scales use bitmap->height
+    double sx = (double)__fdiv_rn(P.vp_w, hh), sy = (double)__fdiv_rn(P.vp_h, hh);
+    double vx = __dmul_rn((double)px, sx), vy = __dmul_rn((double)py, sy), vz = (double)P.vp_d;
+    Ray r;
+    r.o = {P.cam[0], P.cam[1], P.cam[2]};
+    r.d.x = __dadd_rn(__dadd_rn(__dmul_rn(vx, P.rot[0]), __dmul_rn(vy, P.rot[3])), __dmul_rn(vz, P.rot[6]));
+    r.d.y = __dadd_rn(__dadd_rn(__dmul_rn(vx, P.rot[1]), __dmul_rn(vy, P.rot[4])), __dmul_rn(vz, P.rot[7]));
+    r.d.z = __dadd_rn(__dadd_rn(__dmul_rn(vx, P.rot[2]), __dmul_rn(vy, P.rot[5])), __dmul_rn(vz, P.rot[8]));
+    r.t = kRayTInit;
+    return r;
+}
+
+// Primary ray of depth-0 slot `slot`, whose pixel is (x, y): the pixel centre, or one of its 16 jittered samples.
+CT_DEV Ray primary_ray(const Params &P, uint32_t slot, int x, int y) {
+    if (!P.supersample) return primary_ray_at(P, (float)x, (float)y);
+    float px, py;
+    sample_point(x, y, (int)(slot & 15u), px, py);
+    return primary_ray_at(P, px, py);
+}
+
+// slot -> canvas pixel.  A warp owns an 8x4 pixel block (coherent rays); returns false for padding lanes
+// and for pixels PutPixel would drop (draw2d.h:11-14), which are not traced at all (with subsampling a dropped
+// row is still traced -- fb_index = -1 -- because its colour enters the average stored in the row above it).
+CT_DEV void store_pixel(const Params &P, uint32_t slot, int fb_index, uint32_t color) {
+    if (fb_index >= 0) P.fb_out[fb_index] = color;
+    if (P.final_color) P.final_color[slot] = color;
+}
+
+CT_DEV bool slot_pixel(const Params &P, uint32_t slot, int &x, int &y, int &fb_index) {
+    if (P.supersample) slot >>= 4;                            // 16 samples per pixel
+    uint32_t blk = slot >> 5, lane = slot & 31u;
+    int bx = (int)(blk % (uint32_t)P.blocks_x), by = (int)(blk / (uint32_t)P.blocks_x);
+    int ix = bx * 8 + (int)(lane & 7u), iy = by * 4 + (int)(lane >> 3);
+    if (ix >= P.n_x || iy >= P.n_y) return false;
+    x = P.x_lo + ix;
+    if (P.subsample)    // raythread.cpp:527-530: y += 2, except that the last row of the partition is always traced
+        y = P.y_lo + ((iy == P.n_y - 1 && (P.n_rows & 1) == 0) ? P.n_rows - 1 : 2 * iy);
+    else
+        y = P.y_lo + iy;
+    int col = x + P.W / 2, row = P.H / 2 - y;               // CanvasPutPixel raythread.cpp:181-182
+    if (col < 0 || col >= P.W) return false;
+    fb_index = row * P.W + col;
+    if (row < 0 || row >= P.H) {
+        if (!P.subsample) return false;
+        fb_index = -1;                                       // traced for the average of the row above it, never stored
+    }
+    if (P.supersample) fb_index = -1;                        // a sample: k_supersample blends the 16 of a pixel and stores it
+    return true;
+}
+
+CT_DEV unsigned long long warp_fetch(unsigned long long *cursor) {   // persistent warps pull 32 work items at a time
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31u) == 0) base = atomicAdd(cursor, 32ull);
+    return __shfl_sync(0xffffffffu, base, 0);
+}
+
+CT_DEV void warp_add(unsigned long long *dst, uint32_t v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+}
+
+// Depth-0 paths are numbered in the order this device took their chunks from the cursor.
+CT_DEV uint32_t own_slot(const Params &P, uint32_t q) {
+    return (P.own_chunks[q >> P.chunk_shift] << P.chunk_shift) + (q & ((1u << P.chunk_shift) - 1u));
+}
+CT_DEV uint32_t depth0_count(const Params &P) { return P.sched->own_count << P.chunk_shift; }
+
+// The path with queue index q at `depth`: its ray (direction only for depth 0 is regenerated from the pixel),
+// its closest-hit record and its depth-0 slot.  False for padding lanes / untraced pixels.
+CT_DEV bool load_path(const Params &P, int depth, uint32_t q, uint32_t &slot, int &fbi, Ray &r, float &tc, uint32_t &pos) {
+    if (depth == 0) {
+        int x, y;
+        slot = own_slot(P, q);
+        if (!slot_pixel(P, slot, x, y, fbi)) return false;
+        r = primary_ray(P, slot, x, y);
+        tc = P.hit0_t[slot]; pos = P.hit0_pos[slot];
+    } else {
+        const int cur = depth & 1;
+        slot = P.path_slot[cur][q];
+        fbi = 0;
+        const double2 *rb = reinterpret_cast<const double2 *>(P.ray_buf[cur] + 6ull * q);
+        double2 a = rb[0], b = rb[1], c = rb[2];
+        r.o = {a.x, a.y, b.x}; r.d = {b.y, c.x, c.y}; r.t = 0.0f;
+        tc = P.hitb_t[q]; pos = P.hitb_pos[q];
+        if (pos == kNoPos) pos = P.pos_of_tri0;                 // "closestIndex = 0" (raythread.cpp:205): no barycentric pass at all
+    }
+    return true;
+}
+
+CT_DEV void clear_occ(const Params &P, uint32_t q) {
+    for (uint32_t w = 0; w < P.occ_words; w++) P.occ[(size_t)q * P.occ_words + w] = 0u;
+}
+
+// Park a ray for k_overflow.  False when the buffer is full (the caller then finishes the ray in place).
+CT_DEV bool park_ray(const Params &P, int ovf_idx, const double *r64, uint32_t target, uint32_t bit) {
+    uint32_t i = atomicAdd(&P.sched->ovf_count[ovf_idx], 1u);
+    if (i >= P.ovf_cap) { atomicAdd(&P.tot->rays_in_place, 1ull); return false; }
+    OvfRay &o = P.ovf[i];
+    o.o[0] = r64[0]; o.o[1] = r64[1]; o.o[2] = r64[2];
+    o.d[0] = r64[3]; o.d[1] = r64[4]; o.d[2] = r64[5];
+    o.target = target; o.bit = bit;
+    return true;
+}
+
+// Primary rays.  Persistent warps take chunks of 32 or 64 slots from the tile's cursor -- one counter for the whole
+// tile, which in a multi-GPU frame lives on the root GPU and is shared by all devices over NVLink (dynamic
+// stealing at chunk granularity) -- and remember which chunks they took: the later stages of this
+// device work on exactly those.
+// Which chunk of the tile does this warp trace next?  (called by lane 0)
+//   one device, or a shared frame without a declared partition: the next one from the cursor (P.steal: this device's own
+//     or, shared, the root GPU's over NVLink) -- pure dynamic stealing;
+//   shared frame of R declared participants: the chunks are numbered in groups of 8R; of every group the first E*R are
+//     DEALT (participant r owns r, r + R, ...: no atomics on another GPU, and -- being interleaved at 32-pixel grain --
+//     an equal share of every later stage's work too), the other (8 - E)*R are STOLEN from the root's cursor (absorbs a
+//     slower or busier GPU).  Stealing everything balances only this kernel: the GPU that holds the cursor steals
+//     cheaper and ends up with more paths to light (measured at 8 GPUs: 1.75 ms on the root against 1.41 ms elsewhere).
+CT_DEV bool next_chunk(const Params &P, uint32_t n_chunks, bool &dealt_left, uint32_t &idx) {
+    const uint32_t R = P.part_count, E = P.static_eighths;
+    if (R <= 1u) {
+        const unsigned long long d = atomicAdd(P.steal, (unsigned long long)P.steal_stride);
+        idx = (uint32_t)d;
+        return d < n_chunks;
+    }
+    const uint32_t G = 8u * R, n_groups = (n_chunks + G - 1u) / G;
+    while (dealt_left) {
+        const uint32_t c = atomicAdd(&P.sched->static_next, 1u);
+        const uint32_t g = c / E;
+        if (g >= n_groups) { dealt_left = false; break; }
+        idx = g * G + (c - g * E) * R + P.part_index;
+        if (idx < n_chunks) return true;
+    }
+    const uint32_t per = (8u - E) * R;
+    while (per) {
+        const unsigned long long d = atomicAdd(P.steal, 1ull);
+        const unsigned long long g = d / per;
+        if (g >= n_groups) break;
+        idx = (uint32_t)(g * G + E * R + (d - g * per));
+        if (idx < n_chunks) return true;
+    }
+    return false;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __grid_constant__ Params P) {
+    LocalCount lc;
+    uint32_t n_rays = 0;
+    const uint32_t lane = threadIdx.x & 31u, chunk = 1u << P.chunk_shift;
+    const uint32_t n_chunks = (P.n_slots + chunk - 1u) >> P.chunk_shift;
+    bool dealt_left = P.part_count > 1u && P.static_eighths > 0u;     // lane 0's view of this device's dealt share
+    while (true) {
+        unsigned long long base = ~0ull;
+        uint32_t mine = 0;
+        if (lane == 0) {
+            uint32_t idx;
+            if (next_chunk(P, n_chunks, dealt_left, idx)) {
+                base = (unsigned long long)idx << P.chunk_shift;
+                mine = atomicAdd(&P.sched->own_count, 1u);
+                CT_CHECK(mine <= (P.cap >> kChunkLocalShift));
+                P.own_chunks[mine] = idx;
+            }
+        }
+        base = __shfl_sync(kFullMask, base, 0);
+        mine = __shfl_sync(kFullMask, mine, 0);
+        if (base == ~0ull) break;
+        for (uint32_t sub = 0; sub < chunk; sub += 32u) {
+            const uint32_t slot = (uint32_t)base + sub + lane;
+            const uint32_t q = (mine << P.chunk_shift) + sub + lane;   // this path's depth-0 number on this device
+            int x, y, fbi;
+            const bool active = slot < P.n_slots && slot_pixel(P, slot, x, y, fbi);
+            double r64[kRay64];
+            TRay r;
+            if (active) {
+                Ray ray = primary_ray(P, slot, x, y);
+                tray_setup(r, ray, P.bound, r64);
+            }
+            float tc; uint32_t pos;
+            bool found = traverse_closest<COUNT>(P, r, active, tc, pos, lc) == kTravHit;   // warp-synchronous
+            if (!active) continue;
+            n_rays++;
+            CT_CHECK(slot < P.cap && q < P.cap);
+            P.hit0_t[slot] = tc;
+            P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
+            if (found) clear_occ(P, q);
+            if (P.dbg_found && fbi >= 0) {
+                P.dbg_found[fbi] = found ? 1u : 0u;
+                P.dbg_index[fbi] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
+                P.dbg_t[fbi] = tc;
+            }
+        }
+    }
+    warp_add(&P.tot->rays_primary, n_rays);
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
+}
+
+// ComputeLighting's shadow rays (raythread.cpp:288-306) for the paths alive at `depth`.  Work item =
+// (shadow light j, path q), j-major, so the 32 lanes of a warp trace 32 neighbouring shading points towards
+// the same light.  Verdicts go to the per-path occlusion mask read by k_shade.
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
+    LocalCount lc;
+    uint32_t n_shadow = 0, n_parked = 0;
+    const uint32_t n = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
+    const unsigned long long n_pad = ((unsigned long long)n + 31ull) & ~31ull;
+    const unsigned long long total = n_pad * P.n_slights;
+    while (true) {
+        unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= total) break;
+        uint32_t j = (uint32_t)(base / n_pad);
+        uint32_t q = (uint32_t)(base - (unsigned long long)j * n_pad) + (threadIdx.x & 31u);
+        uint32_t slot, pos = kNoPos; int fbi; Ray r; float tc = 0.0f;
+        bool active = q < n && load_path(P, depth, q, slot, fbi, r, tc, pos) && pos != kNoPos;
+        double r64[kRay64];
+        TRay tr;
+        uint32_t word = 0, bit = 0;
+        if (active) {
+            const DevShadowLight &L = P.slights[j];
+            V3 position = vadd(r.o, vscale((double)tc, r.d));                                  // :360
+            V3 lray = (L.type == CT_LIGHT_POINT) ? vsub(ld3(L.v), position) : ld3(L.v);        // :288 / :293
+            Ray sr; sr.o = position; sr.d = lray; sr.t = kRayTInit;                            // :304 no offset, no t<=1 test
+            tray_setup(tr, sr, P.bound, r64);
+            n_shadow++;
+            word = q * P.occ_words + (L.index >> 5); bit = L.index & 31u;
+        }
+        uint32_t budget = P.budget;
+        while (true) {                                                  // warp-uniform: traverse_early is warp-synchronous
+            float stc; uint32_t spos;
+            int res = traverse_early<kAnyHit, COUNT>(P, tr, active, budget, stc, spos, lc);
+            bool again = false;
+            if (active) {
+                if (res == kTravOverBudget) {
+                    n_parked++;
+                    again = !park_ray(P, ovf_idx, r64, word, bit);      // parking buffer full: finish in place, no budget
+                    budget = 0xffffffffu;
+                } else if (res == kTravHit) {
+                    atomicOr(&P.occ[word], 1u << bit);
+                }
+            }
+            active = again;
+            if (!__any_sync(0xffffffffu, again)) break;
+        }
+    }
+    warp_add(&P.tot->rays_shadow, n_shadow);
+    warp_add(&P.tot->rays_overflow, n_parked);
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
+}
+
+// TraceRay's recursion step (raythread.cpp:369-373) for the paths alive at `depth`: does the path end here, or does
+// it continue with the reflection ray {position, ReflectRay(-dir, normal), t = 0}?  Needs only the hit records --
+// not the shadow verdicts -- so it runs ahead of k_shadow / k_shade of the same depth (separate streams) and feeds
+// k_bounce of the next one.
+__global__ void __launch_bounds__(kBlockThreads) k_emit(const __grid_constant__ Params P, int depth, int work_idx) {
+    uint32_t n_refl = 0;
+    const uint32_t n = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
+    const int nxt = (depth & 1) ^ 1;
+    while (true) {
+        unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= n) break;
+        uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
+        uint32_t slot = q, pos = kNoPos; int fbi = 0;
+        Ray r; float tc = 0.0f;
+        bool active = q < n && load_path(P, depth, q, slot, fbi, r, tc, pos);
+        bool emit = false;
+        V3 position = {0, 0, 0}, rdir = {0, 0, 0};
+        if (active) {
+            float reflection = 0.0f;
+            if (pos != kNoPos) reflection = P.materials[P.tris[pos].orig].reflection;
+            const int remaining = P.max_depth - depth;                      // recursionDepth of this TraceRay call
+            if (pos == kNoPos || remaining <= 0 || !(reflection > 0.0f)) {  // miss :385 / :369 (reflection <= 0, NaN-safe)
+                P.term_level[slot] = (uint8_t)depth;
+            } else {
+                V3 p1, e1, e2;
+                load_tri(P.tris, pos, p1, e1, e2);
+                position = vadd(r.o, vscale((double)tc, r.d));              // :360
+                V3 nn = vcross(e1, e2);                                     // NormalOfSceneObject :337-339
+                float dd = vdot(nn, r.d);
+                V3 normal = (dd < 0.0f) ? nn : vneg(nn);                    // :341-345
+                P.stack_refl[(size_t)depth * P.cap + slot] = reflection;
+                rdir = reflect_ray(vneg(r.d), normal);                      // :372
+                emit = true;
+            }
+        }
+        // warp-aggregated append of the reflection rays to the next queue
+        uint32_t mask = __ballot_sync(0xffffffffu, emit);
+        if (mask) {
+            uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1, qbase = 0;
+            if (lane == leader) qbase = atomicAdd(&P.sched->queue_count[depth + 1], (uint32_t)__popc(mask));
+            qbase = __shfl_sync(0xffffffffu, qbase, leader);
+            if (emit) {
+                uint32_t nq = qbase + __popc(mask & ((1u << lane) - 1u));
+                CT_CHECK(nq < P.cap && slot < P.cap);
+                double2 *rb = reinterpret_cast<double2 *>(P.ray_buf[nxt] + 6ull * nq);
+                rb[0] = make_double2(position.x, position.y);
+                rb[1] = make_double2(position.z, rdir.x);
+                rb[2] = make_double2(rdir.y, rdir.z);
+                P.path_slot[nxt][nq] = slot;
+                n_refl++;
+            }
+        }
+    }
+    warp_add(&P.tot->rays_reflection, n_refl);
+}
+
+// TraceRay's local colour (raythread.cpp:359-366) for the paths alive at `depth`; the shadow verdicts were computed
+// by k_shadow (+ k_overflow).
+__global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__ Params P, int depth, int work_idx) {
+    const uint32_t n = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
+    while (true) {
+        unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= n) break;
+        uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
+        uint32_t slot = q, pos = kNoPos; int fbi = 0;
+        Ray r; float tc = 0.0f;
+        if (!(q < n && load_path(P, depth, q, slot, fbi, r, tc, pos))) continue;
+        uint32_t *sc = P.stack_color + (size_t)depth * P.cap + slot;
+        if (pos == kNoPos) {                                           // miss (depth 0 only): raythread.cpp:385
+            if (depth == 0) store_pixel(P, slot, fbi, P.background);
+            *sc = P.background;
+            continue;
+        }
+        V3 p1, e1, e2;
+        load_tri(P.tris, pos, p1, e1, e2);
+        const ct_material mat = P.materials[P.tris[pos].orig];
+        V3 position = vadd(r.o, vscale((double)tc, r.d));              // :360
+        V3 nn = vcross(e1, e2);                                         // NormalOfSceneObject :337-339
+        float dd = vdot(nn, r.d);
+        V3 normal = (dd < 0.0f) ? nn : vneg(nn);                        // :341-345
+        V3 view = vneg(r.d);
+        // ---- ComputeLighting :275-327, lights in file order, fp32 accumulator
+        float intensity = 0.0f;
+        const uint32_t *occ = P.occ + (size_t)q * P.occ_words;
+        uint32_t occ_word = 0;
+        for (uint32_t i = 0; i < P.n_lights; i++) {
+            const DevLight &L = P.lights[i];
+            float li = L.intensity;
+            if ((i & 31u) == 0) occ_word = occ[i >> 5];
+            if (L.type == CT_LIGHT_AMBIENT) { intensity = __fadd_rn(intensity, li); continue; }
+            if ((occ_word >> (i & 31u)) & 1u) continue;                  // :306 shadowed
+            V3 lray = (L.type == CT_LIGHT_POINT) ? vsub(ld3(L.pos), position) : ld3(L.dir);
+            float ndl = vdot(normal, lray);                              // :310
+            if (ndl > 0.0f)
+                intensity = __fadd_rn(intensity, __fdiv_rn(__fmul_rn(li, ndl), __fmul_rn(vmag(normal), vmag(lray))));
+            if (mat.specular != -1) {                                    // :316
+                V3 refl = reflect_ray(lray, normal);
+                float rdv = vdot(refl, view);
+                if (rdv > 0.0f) {                                        // :319-321 double pow, += rounds to float
+                    float qv = __fdiv_rn(rdv, __fmul_rn(vmag(refl), vmag(view)));
+                    double term = __dmul_rn((double)li, pow((double)qv, (double)mat.specular));
+                    intensity = __double2float_rn(__dadd_rn((double)intensity, term));
+                }
+            }
+        }
+        uint32_t local = shade_color(mat.color, intensity);
+        *sc = local;
+        // a depth-0 path that ends here (:369) is the pixel; longer chains are blended by k_resolve
+        if (depth == 0 && (P.max_depth <= 0 || !(mat.reflection > 0.0f))) store_pixel(P, slot, fbi, local);
+    }
+}
+
+// Closest "hit" of the reflection rays {position, reflected, t = 0} (raythread.cpp:373).
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
+    LocalCount lc;
+    uint32_t n_parked = 0;
+    const uint32_t n = P.sched->queue_count[depth];
+    const int cur = depth & 1;
+    while (true) {
+        unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= n) break;
+        uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
+        bool active = q < n;
+        double r64[kRay64];
+        TRay r;
+        if (active) {
+            const double2 *rb = reinterpret_cast<const double2 *>(P.ray_buf[cur] + 6ull * q);
+            double2 a = rb[0], b = rb[1], c = rb[2];
+            Ray ray;
+            ray.o = {a.x, a.y, b.x}; ray.d = {b.y, c.x, c.y}; ray.t = 0.0f;
+            tray_setup(r, ray, P.bound, r64);
+            clear_occ(P, q);
+        }
+        uint32_t budget = P.budget;
+        while (true) {                                                  // warp-uniform: traverse is warp-synchronous
+            float tc; uint32_t pos;
+            int res = traverse_early<kFirstLine, COUNT>(P, r, active, budget, tc, pos, lc);
+            bool again = false;
+            if (active) {
+                if (res == kTravOverBudget) {
+                    n_parked++;
+                    again = !park_ray(P, ovf_idx, r64, q, 0u);          // parking buffer full: finish in place, no budget
+                    budget = 0xffffffffu;
+                } else {                                                // found is always true: 0 != 1e30f (:227)
+                    P.hitb_t[q] = tc;
+                    P.hitb_pos[q] = (pos == kNoPos) ? P.pos_of_tri0 : pos;
+                }
+            }
+            active = again;
+            if (!__any_sync(kFullMask, again)) break;
+        }
+    }
+    warp_add(&P.tot->rays_overflow, n_parked);
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
+}
+
+// Parked rays (see the file header).  Both early-exit modes have an answer that does not depend on the visit
+// order, because ray.t never changes before the exit, so the set of boxes that pass is fixed:
+//   kAnyHit     occluded  <=>  SOME triangle reachable through passing boxes has a bary pass with 1e-4 < t < 1e30;
+//   kFirstLine  closestIndex = the bary-passing reachable triangle that the DFS meets first = the one with the
+//               smallest leaf position (BuildBVH hands the left child the lower part of the parent's index range,
+//               bvh.cpp:70-97, so leaf positions increase along the DFS).
+// Tests the triangles of an accepted leaf for a parked ray.  kAnyHit: 1 if one of them occludes, else 0;
+// kFirstLine: the first (lowest) leaf position with a barycentric pass, else kNoPos.
+template <TraverseMode MODE, bool COUNT>
+CT_DEV uint32_t overflow_leaf(const Params &P, const TRay &r, uint32_t first, uint32_t cnt, LocalCount &lc) {
+    for (uint32_t k = 0; k < cnt; k++) {
+        uint32_t pos = first + k;
+        if (COUNT) lc.tri++;
+        const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
+        if (!th.hit) continue;
+        if (MODE == kAnyHit) { if (th.t > kEps && th.t < kRayTInit) return 1u; }
+        else return pos;                                      // later positions of this leaf are larger
+    }
+    return MODE == kAnyHit ? 0u : kNoPos;
+}
+
+template <TraverseMode MODE>
+CT_DEV uint32_t overflow_merge(uint32_t a, uint32_t b) { return MODE == kAnyHit ? (a | b) : min(a, b); }
+
+template <TraverseMode MODE>
+CT_DEV void overflow_store(const Params &P, const OvfRay &o, uint32_t res) {
+    if (MODE == kAnyHit) {
+        if (res) atomicOr(&P.occ[o.target], 1u << o.bit);
+    } else {
+        P.hitb_t[o.target] = (res == kNoPos) ? kFinf : 0.0f;          // raythread.cpp:204 / first line pass
+        P.hitb_pos[o.target] = (res == kNoPos) ? P.pos_of_tri0 : res;
+    }
+}
+
+constexpr int kWarpStack = 1024;         // pending interior nodes of one ray in the warp-cooperative pass
+constexpr uint32_t kWarpBudget = 4096;       // default node visits before a ray is handed to the grid-wide pass
+
+// Parked rays, pass 1: one WARP per ray -- the 32 lanes pop up to 32 pending interior nodes from a shared-memory
+// stack, test their child pairs, test accepted leaves on the spot and push accepted interior children back.
+// A ray whose stack outgrows kWarpStack, that needs more than P.warp_budget node visits or whose origin is so far
+// outside the scene that every box passes (the rays described in the header: ~1M visits) goes to k_overflow_huge.
+template <TraverseMode MODE, bool COUNT>
+__global__ void __launch_bounds__(kOvfThreads) k_overflow(const __grid_constant__ Params P, int ovf_idx) {
+    const uint32_t n = min(P.sched->ovf_count[ovf_idx], P.ovf_cap);
+    if (n == 0) return;
+    LocalCount lc;
+    const uint32_t lane = threadIdx.x & 31u;
+    __shared__ uint32_t wstack[kOvfThreads / 32][kWarpStack];
+    uint32_t *stk = wstack[threadIdx.x >> 5];
+    while (true) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(&P.sched->ovf_cursor[ovf_idx], 1u);
+        idx = __shfl_sync(kFullMask, idx, 0);
+        if (idx >= n) break;
+        const OvfRay &o = P.ovf[idx];
+        Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
+        double r64[kRay64];
+        TRay r;
+        tray_setup(r, ray, P.bound, r64);             // every lane holds the same ray
+        uint32_t res = MODE == kAnyHit ? 0u : kNoPos;
+        // An origin this far outside the scene (a shading point 2^32 ray lengths away) makes all slab
+        // quotients of an axis round to the same float: every box passes and no filter can help.
+        bool too_big = !r.filt || (double)r.om > 0x1p20 * fmax(fmax(P.bound[0], P.bound[1]), P.bound[2]);
+        if (COUNT && lane == 0 && !too_big) lc.box++;
+        if (!too_big && exact_root(P, r64, r.t)) {
+            if (P.root_cnt > 0) {
+                if (lane == 0) res = overflow_leaf<MODE, COUNT>(P, r, P.root_ref, P.root_cnt, lc);
+            } else {
+                if (lane == 0) stk[0] = P.root_ref;
+                __syncwarp();
+                uint32_t sp = 1, visits = 0;
+                while (sp > 0) {
+                    const uint32_t take = min(sp, 32u);
+                    sp -= take;
+                    uint32_t n_out = 0, out_a = 0, out_b = 0;
+                    if (lane < take) {
+                        const uint32_t pid = stk[sp + lane];
+                        DevPair32 pr;
+                        load_pair32(P.pairs32, pid, pr);
+                        if (COUNT) lc.box += 2;
+                        bool hit_l, hit_r; float lo, hi;
+                        pair_accept<COUNT>(P, r, pid, pr, hit_l, hit_r, lo, hi, lc);
+                        if (hit_l) {
+                            if (pr.l_cnt > 0) res = overflow_merge<MODE>(res, overflow_leaf<MODE, COUNT>(P, r, pr.l_ref, pr.l_cnt, lc));
+                            else { out_a = pr.l_ref; n_out = 1; }
+                        }
+                        if (hit_r) {
+                            if (pr.r_cnt > 0) res = overflow_merge<MODE>(res, overflow_leaf<MODE, COUNT>(P, r, pr.r_ref, pr.r_cnt, lc));
+                            else { if (n_out) out_b = pr.r_ref; else out_a = pr.r_ref; n_out++; }
+                        }
+                    }
+                    __syncwarp();                     // every lane has read its entry before the pushes below
+                    if (MODE == kAnyHit && __any_sync(kFullMask, res != 0u)) break;
+                    uint32_t incl = n_out;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(kFullMask, incl, d); if ((int)lane >= d) incl += v; }
+                    const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+                    visits += take;
+                    if (sp + total > (uint32_t)kWarpStack || visits > P.warp_budget) { too_big = true; break; }
+                    const uint32_t at = sp + incl - n_out;
+                    if (n_out > 0) stk[at] = out_a;
+                    if (n_out > 1) stk[at + 1u] = out_b;
+                    sp += total;
+                    __syncwarp();
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) res = overflow_merge<MODE>(res, __shfl_xor_sync(kFullMask, res, d));
+        if (lane == 0) {
+            if (too_big) {
+                P.ovf_huge[atomicAdd(&P.sched->huge_count[ovf_idx], 1u)] = idx;
+                if (MODE == kFirstLine) { P.hitb_t[o.target] = kFinf; P.hitb_pos[o.target] = kNoPos; }   // until k_overflow_huge finds a pass
+            } else {
+                overflow_store<MODE>(P, o, res);
+            }
+        }
+    }
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
+}
+
+// Is the leaf that holds a triangle REACHED by the reference's walk?  Every box on the way down must accept the ray:
+// the leaf's own box, its ancestors' boxes, the root's.  `code` = 2 * pair + side of the leaf's box.
+CT_DEV bool chain_accepts(const Params &P, double *r64, float ray_t, uint32_t code) {
+    while (code != kNoPos) {
+        const uint32_t pid = code >> 1;
+        if (!box_accept(exact_child(P.pairs64, pid, code & 1u, r64), ray_t)) return false;
+        code = P.pair_parent[pid];
+    }
+    return exact_root(P, r64, ray_t);
+}
+
+// Parked rays, pass 2 (what pass 1 gave up on).  Walking a tree in which every box passes level by level costs a
+// grid-wide barrier per level; instead the whole grid tests ALL triangles against the ray at once and, for the few
+// that pass, checks whether the reference's walk would have reached them at all (chain_accepts).  No barrier, and
+// the answers are merged with idempotent atomics (OR into the occlusion mask / MIN of the leaf position).
+template <TraverseMode MODE, bool COUNT>
+__global__ void __launch_bounds__(256) k_overflow_huge(const __grid_constant__ Params P, int ovf_idx) {
+    const uint32_t nh = P.sched->huge_count[ovf_idx];
+    if (nh == 0) return;
+    LocalCount lc;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    for (uint32_t h = 0; h < nh; h++) {
+        const OvfRay &o = P.ovf[P.ovf_huge[h]];
+        Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = (MODE == kAnyHit) ? kRayTInit : 0.0f;
+        double r64[kRay64];
+        TRay r;
+        tray_setup(r, ray, P.bound, r64);
+        for (uint32_t pos = tid; pos < P.n_tri; pos += n_threads) {
+            if (MODE == kAnyHit && (*(volatile uint32_t *)&P.occ[o.target] >> o.bit) & 1u) break;      // already occluded
+            if (MODE == kFirstLine && *(volatile uint32_t *)&P.hitb_pos[o.target] < pos) break;        // a lower position already passed
+            if (COUNT) lc.tri++;
+            const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
+            if (!th.hit) continue;
+            if (MODE == kAnyHit && !(th.t > kEps && th.t < kRayTInit)) continue;
+            if (!chain_accepts(P, r64, r.t, P.tri_parent[pos])) continue;
+            if (MODE == kAnyHit) atomicOr(&P.occ[o.target], 1u << o.bit);
+            else { atomicMin(&P.hitb_pos[o.target], pos); P.hitb_t[o.target] = 0.0f; }
+        }
+    }
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
+}
+
+// Unwind TraceRay's recursion (raythread.cpp:375-379) for pixels whose chain went past depth 0.
+__global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Params P) {
+    const uint32_t n = depth0_count(P);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t slot = own_slot(P, q);
+        int x, y, fbi;
+        if (!slot_pixel(P, slot, x, y, fbi)) continue;
+        int lvl = P.term_level[slot];
+        if (lvl == 0) continue;                              // already stored by k_shade
+        uint32_t color = P.stack_color[(size_t)lvl * P.cap + slot];
+        for (int d = lvl - 1; d >= 0; d--)
+            color = blend_color(P.stack_color[(size_t)d * P.cap + slot], color, P.stack_refl[(size_t)d * P.cap + slot]);
+        store_pixel(P, slot, fbi, color);
+    }
+}
+
+// settings.subsampling (raythread.cpp:512-531): after a traced pixel (x, y) the reference stores the average of its
+// colour and the previously traced colour of the column (its own for the first row of the partition) one row
+// below, at (x, y - 1).  Runs after every traced pixel of the tile has its final colour; a later store wins where
+// the reference's sequential loop would overwrite (the always-traced last row of an even partition).
+__global__ void __launch_bounds__(256) k_subsample(const __grid_constant__ Params P) {
+    const uint32_t n = depth0_count(P);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t slot = own_slot(P, q);
+        int x, y, fbi;
+        if (!slot_pixel(P, slot, x, y, fbi)) continue;
+        const uint32_t blk = slot >> 5, lane = slot & 31u;
+        const uint32_t iy = (blk / (uint32_t)P.blocks_x) * 4u + (lane >> 3);
+        const uint32_t color = P.final_color[slot];
+        uint32_t last = color;                                                 // :513-514
+        if (iy > 0) {
+            const uint32_t py = iy - 1u, ix = (blk % (uint32_t)P.blocks_x) * 8u + (lane & 7u);
+            last = P.final_color[(((py >> 2) * (uint32_t)P.blocks_x + (ix >> 3)) << 5) + ((py & 3u) << 3) + (ix & 7u)];
+        }
+        uint32_t avg = 0;                                                      // :517-523: float (a + b) / 2, min 0xff, truncated
+        for (int sh = 0; sh <= 16; sh += 8) avg |= ((((last >> sh) & 0xffu) + ((color >> sh) & 0xffu)) >> 1) << sh;
+        const int col = x + P.W / 2, row = P.H / 2 - (y - 1);                  // CanvasPutPixel(bitmap, {x, y-1}, avgColor) :524
+        if (row >= 0 && row < P.H && col >= 0 && col < P.W) P.fb_out[row * P.W + col] = avg;
+    }
+}
+
+// settings.supersampling (raythread.cpp:460-505): the 16 samples of a pixel are folded into its colour one after the
+// other -- colour -= colour/8; colour += sample/8 per channel in float, truncated to uint8 after every sample (:486-497).
+__global__ void __launch_bounds__(256) k_supersample(const __grid_constant__ Params P) {
+    const uint32_t n = depth0_count(P) >> 4;                                  // chunks hold whole pixels (32 or 64 slots)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = own_slot(P, i << 4);
+        int x, y, fbi;
+        if (!slot_pixel(P, slot, x, y, fbi)) continue;
+        uint32_t color = P.final_color[slot];
+        for (uint32_t k = 1; k < 16u; k++) {
+            const uint32_t temp = P.final_color[slot + k];
+            uint32_t out = 0;
+            for (int sh = 0; sh <= 16; sh += 8) {
+                float c = (float)((color >> sh) & 0xffu), t = (float)((temp >> sh) & 0xffu);
+                c = __fsub_rn(c, __fdiv_rn(c, 8.0f));
+                c = __fadd_rn(c, __fdiv_rn(t, 8.0f));
+                out |= to_u8(c) << sh;
+            }
+            color = out;
+        }
+        const int col = x + P.W / 2, row = P.H / 2 - y;
+        P.fb_out[row * P.W + col] = color;
+    }
+}
+
+// ---- KAT kernels -----------------------------------------------------------------------------------------
+__global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, const double *org, const double *dir,
+                                const float *t0, uint32_t *found, uint32_t *index, float *tclosest) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;                           // the traversals are warp-synchronous: every lane calls both
+    Ray r;
+    r.t = 1.0f;
+    double r64[kRay64];
+    TRay tr;
+    if (active) {
+        r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = t0[i];
+        tray_setup(tr, r, P.bound, r64);
+    }
+    LocalCount lc; float tc, tc2; uint32_t pos, pos2;
+    const bool first_line = r.t == 0.0f;
+    bool f = traverse_early<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc) == kTravHit;
+    bool f2 = traverse_closest<false>(P, tr, active && !first_line, tc2, pos2, lc) == kTravHit;
+    if (!active) return;
+    if (!first_line) { f = f2; tc = tc2; pos = pos2; }
+    if (found) found[i] = f ? 1u : 0u;
+    if (index) index[i] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
+    if (tclosest) tclosest[i] = tc;
+}
+
+__global__ void k_debug_primitives(uint32_t n, const double *org, const double *dir, float *ray_t, const double *tri,
+                                   const double *bmin, const double *bmax, uint32_t *tri_hit, uint32_t *box_hit,
+                                   uint32_t *filter_out, double bound_scale, bool tri_filter) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r;
+    r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = ray_t[i];
+    double mn[3] = {bmin[3ull * i], bmin[3ull * i + 1], bmin[3ull * i + 2]};
+    double mx[3] = {bmax[3ull * i], bmax[3ull * i + 1], bmax[3ull * i + 2]};
+    const bool exact = intersect_aabb(r, mn, mx);
+    box_hit[i] = exact ? 1u : 0u;
+    if (filter_out) {
+        // the certified filter on the same box: bit 0 exact verdict, bits 1-2 filter (0 undecided, 1 accept, 2 reject),
+        // bit 3 = the filter was usable for this ray.  A certain verdict that contradicts bit 0 is a soundness bug.
+        double bnd[3];
+        bool ordered = true;
+        for (int k = 0; k < 3; k++) {
+            bnd[k] = fmax(fabs(mn[k]), fabs(mx[k])) * bound_scale;
+            ordered = ordered && (mn[k] <= mx[k]) && isfinite(mn[k]) && isfinite(mx[k]);
+        }
+        if (!ordered) bnd[0] = bnd[1] = bnd[2] = INFINITY;
+        double r64[kRay64];
+        TRay tr;
+        tray_setup(tr, r, bnd, r64);
+        uint32_t f = 0;
+        if (tr.filt) {
+            const float fmn[3] = {(float)mn[0], (float)mn[1], (float)mn[2]}, fmx[3] = {(float)mx[0], (float)mx[1], (float)mx[2]};
+            BoxBracket b = box_filter(tr, fmn, fmx);
+            if (bracket_geom_no(b) || bracket_t_no(b, r.t)) f = 2;
+            else if (bracket_geom_yes(b) && bracket_t_yes(b, r.t)) f = 1;
+            BoxTimes e = box_times(r, mn, mx);
+            bool inside = b.near_lo <= e.tmin && e.tmin <= b.near_hi && b.far_lo <= e.tmax && e.tmax <= b.far_hi;
+            if (!inside) f |= 8u;                                  // bracket does not contain the reference's floats: bug
+        }
+        // the division-free evaluation used for undecided tests must give the literal arithmetic's verdict and floats
+        {
+            const BoxTimes lit = box_times(r, mn, mx), rec = box_times(r64, mn, mx);
+            const bool same = (lit.tmin == rec.tmin || (lit.tmin != lit.tmin && rec.tmin != rec.tmin)) &&
+                              (lit.tmax == rec.tmax || (lit.tmax != lit.tmax && rec.tmax != rec.tmax));
+            if (!same || box_accept(rec, r.t) != exact) f |= 16u;
+        }
+        uint32_t out = (exact ? 1u : 0u) | ((f & 3u) << 1) | (tr.filt ? 8u : 0u) | ((f & 8u) ? 16u : 0u) | ((f & 16u) ? 32u : 0u);
+        if (tri_filter) {
+            // the certified triangle filter on the same (ray, triangle), with the magnitudes the upload would store:
+            // bit 8 = reference returns true, bit 9 = ... and the hit would occlude a shadow ray (1e-4 < t < 1e30),
+            // bit 10 / 11 = tri_filter_miss<false> / <true> say "certainly no effect", bit 12 = filter usable
+            const V3 q1 = ld3(tri + 9ull * i), q2 = ld3(tri + 9ull * i + 3), q3 = ld3(tri + 9ull * i + 6);
+            const V3 e1 = vsub(q2, q1), e2 = vsub(q3, q1);
+            float tt = 0.0f;
+            const bool th = intersect_triangle(r, q1, e1, e2, &tt);
+            const double k1 = fmax(fmax(fabs(e1.x), fabs(e1.y)), fabs(e1.z)), k2 = fmax(fmax(fabs(e2.x), fabs(e2.y)), fabs(e2.z));
+            const double k3 = fmax(fmax(fabs(q1.x), fabs(q1.y)), fabs(q1.z));
+            const bool in_range = k1 >= 0x1p-30 && k1 <= 0x1p30 && k2 >= 0x1p-30 && k2 <= 0x1p30 && k3 <= 0x1p40;
+            const float4 t0 = make_float4((float)q1.x, (float)q1.y, (float)q1.z, __double2float_ru(k3));
+            const float4 t1 = make_float4((float)e1.x, (float)e1.y, (float)e1.z, in_range ? __double2float_ru(k1) : NAN);
+            const float4 t2 = make_float4((float)e2.x, (float)e2.y, (float)e2.z, __double2float_ru(k2));
+            const bool m0 = tr.tfilt && tri_filter_miss<false>(tr, t0, t1, t2), m1 = tr.tfilt && tri_filter_miss<true>(tr, t0, t1, t2);
+            out |= (th ? 1u << 8 : 0u) | ((th && tt > kEps && tt < kRayTInit) ? 1u << 9 : 0u) | (m0 ? 1u << 10 : 0u) | (m1 ? 1u << 11 : 0u) | (tr.tfilt ? 1u << 12 : 0u);
+        }
+        filter_out[i] = out;
+    }
+    V3 p1 = ld3(tri + 9ull * i), p2 = ld3(tri + 9ull * i + 3), p3 = ld3(tri + 9ull * i + 6);
+    float t;
+    bool hit = intersect_triangle(r, p1, vsub(p2, p1), vsub(p3, p1), &t);
+    if (hit && t > kEps) r.t = macro_min(r.t, t);
+    tri_hit[i] = hit ? 1u : 0u;
+    ray_t[i] = r.t;
+}
+
+}  // namespace

@@ -1,0 +1,301 @@
+// ct_traverse.cuh -- record loads, the exact (fp64) fallbacks behind the certified filters, and the three BVH walks
+// (traverse_closest: IntersectBVHClosest in the reference's visit order; traverse_early: any-hit and first-line walks with deferred leaves).
+// Part of the single translation unit ct_gpu.cu (everything lives in its anonymous namespace).
+#pragma once
+
+#include "ct_layout.cuh"
+
+namespace {
+
+CT_DEV V3 ld3(const double *p) { return {p[0], p[1], p[2]}; }
+
+CT_DEV void load_tri(const DevTri *tris, uint32_t pos, V3 &p1, V3 &e1, V3 &e2) {
+    const double2 *p = reinterpret_cast<const double2 *>(tris + pos);
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    double e = __ldg(reinterpret_cast<const double *>(p + 4));
+    p1 = {a.x, a.y, b.x};
+    e1 = {b.y, c.x, c.y};
+    e2 = {d.x, d.y, e};
+}
+
+// Optional (CT_PREFETCH=1): request the records of a pair's children as soon as the pair has arrived, so that their
+// latency overlaps this visit's slab tests.  Measured neutral-to-negative on full frames (the walks are issue
+// bound there), kept as a build-time experiment.
+CT_DEV void prefetch_children(const Params &P, const DevPair32 &pr) {
+#if defined(CT_PREFETCH) && CT_PREFETCH
+    const char *l = pr.l_cnt ? reinterpret_cast<const char *>(P.tris32 + pr.l_ref) : reinterpret_cast<const char *>(P.pairs32 + pr.l_ref);
+    const char *r = pr.r_cnt ? reinterpret_cast<const char *>(P.tris32 + pr.r_ref) : reinterpret_cast<const char *>(P.pairs32 + pr.r_ref);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(l)); asm volatile("prefetch.global.L2 [%0];" ::"l"(l + 32));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(r)); asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 32));
+#endif
+}
+
+CT_DEV void load_pair32(const DevPair32 *pairs, uint32_t pid, DevPair32 &p) {
+    const float4 *q = reinterpret_cast<const float4 *>(pairs + pid);
+    float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    uint4 m = __ldg(reinterpret_cast<const uint4 *>(q + 3));
+    p.lmin[0] = a.x; p.lmin[1] = a.y; p.lmin[2] = a.z; p.lmax[0] = a.w; p.lmax[1] = b.x; p.lmax[2] = b.y;
+    p.rmin[0] = b.z; p.rmin[1] = b.w; p.rmin[2] = c.x; p.rmax[0] = c.y; p.rmax[1] = c.z; p.rmax[2] = c.w;
+    p.l_ref = m.x; p.l_cnt = m.y; p.r_ref = m.z; p.r_cnt = m.w;
+}
+
+// ---- cold paths: the reference's own fp64 arithmetic, out of line so that its operands only occupy registers
+// while it runs.  `r64` = the ray's origin (0..2) and direction (3..5) in local memory.
+__device__ __noinline__ BoxTimes exact_child(const DevPair64 *pairs, uint32_t pid, uint32_t side, double *r64) {
+    const double2 *q = reinterpret_cast<const double2 *>(pairs + pid) + 3u * side;
+    double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    const double bmin[3] = {a.x, a.y, b.x}, bmax[3] = {b.y, c.x, c.y};
+    return box_times(r64, bmin, bmax);
+}
+
+CT_DEV bool exact_root(const Params &P, double *r64, float ray_t) {
+    return box_accept(box_times(r64, P.root_min, P.root_max), ray_t);
+}
+
+// IntersectAABB's verdict for the root box: the fp32 bracket when it is certain, the fp64 arithmetic otherwise.
+CT_DEV bool root_accept(const Params &P, const TRay &r) {
+    if (r.filt) {
+        const BoxBracket b = box_filter(r, P.root_min32, P.root_max32);
+        if (bracket_geom_no(b) | bracket_t_no(b, r.t)) return false;
+        if (bracket_geom_yes(b) & bracket_t_yes(b, r.t)) return true;
+    }
+    return exact_root(P, r.r64, r.t);
+}
+
+struct TriHit { bool hit; float t; };
+__device__ __noinline__ TriHit tri_exact(const DevTri *tris, uint32_t pos, const double *r64) {
+    V3 p1, e1, e2;
+    load_tri(tris, pos, p1, e1, e2);
+    Ray r;
+    r.o = {r64[0], r64[1], r64[2]}; r.d = {r64[3], r64[4], r64[5]}; r.t = 0.0f;
+    TriHit h;
+    h.t = 0.0f;
+    h.hit = intersect_triangle(r, p1, e1, e2, &h.t);
+    return h;
+}
+
+// IntersectTriangle's verdict for the triangle at `pos`: the fp32 filter discards what certainly has no effect,
+// the fp64 arithmetic decides the rest.
+template <bool ANY_HIT, bool COUNT>
+CT_DEV TriHit leaf_triangle(const Params &P, const TRay &r, uint32_t pos, LocalCount &lc) {
+    const float4 *q = reinterpret_cast<const float4 *>(P.tris32 + pos);
+    const bool miss = tri_filter_miss<ANY_HIT>(r, __ldg(q), __ldg(q + 1), __ldg(q + 2));
+    if (r.tfilt & miss) return {false, 0.0f};
+    if (COUNT) lc.tri_exact++;
+    return tri_exact(P.tris, pos, r.r64);
+}
+
+// IntersectAABB's verdicts for the two children of pair `pid`, bit-exact: the fp32 brackets decide when they
+// can (no branch on the way), the fp64 arithmetic otherwise.  On return [r_lo, r_hi] brackets the reference's
+// tmin of the RIGHT child (collapsed to the exact value when the fp64 path ran), which is what its deferred
+// `tmin < ray.t` re-check needs.
+// T_FAR: the caller's ray.t is 1e30f for good (shadow rays); a filtered ray has |quotients| < 2^99 < 1e30 (tray_setup),
+// so `tmin < ray.t` needs no test.
+template <bool COUNT, bool T_FAR = false>
+CT_DEV void pair_accept(const Params &P, const TRay &r, uint32_t pid, const DevPair32 &pr, bool &hit_l, bool &hit_r,
+                        float &r_lo, float &r_hi, LocalCount &lc) {
+    const BoxBracket bl = box_filter(r, pr.lmin, pr.lmax), br = box_filter(r, pr.rmin, pr.rmax);
+    const bool no_l = T_FAR ? bracket_geom_no(bl) : (bracket_geom_no(bl) | bracket_t_no(bl, r.t));
+    const bool yes_l = T_FAR ? bracket_geom_yes(bl) : (bracket_geom_yes(bl) & bracket_t_yes(bl, r.t));
+    const bool no_r = T_FAR ? bracket_geom_no(br) : (bracket_geom_no(br) | bracket_t_no(br, r.t));
+    const bool yes_r = T_FAR ? bracket_geom_yes(br) : (bracket_geom_yes(br) & bracket_t_yes(br, r.t));
+    hit_l = yes_l; hit_r = yes_r;
+    r_lo = br.near_lo; r_hi = br.near_hi;
+    const bool open_l = !r.filt | !(no_l | yes_l), open_r = !r.filt | !(no_r | yes_r);
+    if (open_l | open_r) {
+        if (open_l) {
+            if (COUNT) lc.box_exact++;
+            hit_l = box_accept(exact_child(P.pairs64, pid, 0u, r.r64), r.t);
+        }
+        if (open_r) {
+            if (COUNT) lc.box_exact++;
+            BoxTimes e = exact_child(P.pairs64, pid, 1u, r.r64);
+            r_lo = r_hi = e.tmin;
+            hit_r = box_accept(e, r.t);
+        }
+    }
+}
+
+enum TraverseMode { kClosest, kAnyHit, kFirstLine };
+enum { kTravMiss = 0, kTravHit = 1, kTravOverBudget = -1 };
+
+constexpr uint32_t kFullMask = 0xffffffffu;
+
+// Build-time bounds checks (-DCT_DEBUG_BOUNDS=1; compute-sanitizer is not available on every pool): trap with a message.
+#if defined(CT_DEBUG_BOUNDS) && CT_DEBUG_BOUNDS
+#define CT_CHECK(cond) do { if (!(cond)) { printf("CT_CHECK failed: %s (line %d)\n", #cond, __LINE__); __trap(); } } while (0)
+#else
+#define CT_CHECK(cond) do { } while (0)
+#endif
+
+// IntersectBVHClosest (bvh.cpp:198-222) as an explicit-stack DFS in the reference's visit order (left subtree,
+// then right) -- the closest-hit walk of primary rays and of ct_gpu_debug_closest (any initial ray.t).
+// The reference tests a node's box when it VISITS the node; here both children of a passing interior node are
+// fetched and tested together (one 64-byte fetch, two independent slab tests in flight):
+//   * the left child is visited next, so "now" is its visit time;
+//   * the right child's tmin/tmax do not depend on ray.t; of the three accept conditions (bvh.cpp:178) only
+//     `tmin < ray.t` does, and ray.t only ever decreases -- so a right child failing now fails at visit time too
+//     and is dropped, and one that passes now is pushed WITH (a bracket of) its tmin and re-checked against the
+//     then-current ray.t when popped.  Same boxes accepted, same triangles tested in the same order, same counts.
+// Leaves are tested on the spot: ray.t must be up to date for the next box (an early-exit walk may defer them,
+// traverse_early; this one may not, and for the same reason it cannot be parked and finished out of order).
+// WARP-SYNCHRONOUS: all 32 lanes call it (lanes without a ray pass active = false); every iteration = one node
+// visit per live lane, and the lanes re-converge at the vote that ends it (left to itself the compiler lets the
+// lanes of a warp drift apart for the whole walk: measured 8 of 32 lanes active).
+// Returns kTravHit/kTravMiss = ray.t != 1e30f ("found").
+template <bool COUNT>
+CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    // stack entry = a pushed right child: (ref, cnt), the bracket of its tmin and its parent pair (to find its fp64
+    // bounds again when the bracket cannot decide)
+    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax], stk_src[kStackMax];
+    float stk_lo[kStackMax], stk_hi[kStackMax];
+    int sp = 0;
+    tclosest = kFinf;          // raythread.cpp:204
+    closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
+    uint32_t cur_ref = P.root_ref, cur_cnt = P.root_cnt;   // current (already accepted) node
+    bool live = false;
+    if (active) {
+        if (COUNT) lc.box++;
+        live = root_accept(P, r);
+    }
+    while (__any_sync(kFullMask, live)) {
+        if (live) {
+            bool need_pop = true;
+            if (cur_cnt > 0) {
+                for (uint32_t i = 0; i < cur_cnt; i++) {
+                    uint32_t pos = cur_ref + i;
+                    if (COUNT) lc.tri++;
+                    const TriHit th = leaf_triangle<false, COUNT>(P, r, pos, lc);
+                    if (th.hit) {
+                        if (th.t > kEps) r.t = macro_min(r.t, th.t);               // bvh.cpp:161
+                        if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
+                            closest_pos = pos; tclosest = r.t;
+                        }
+                    }
+                }
+            } else {
+                CT_CHECK(cur_ref < P.n_pairs);
+                DevPair32 pr;
+                load_pair32(P.pairs32, cur_ref, pr);
+                prefetch_children(P, pr);
+                if (COUNT) lc.box += 2;
+                bool hit_l, hit_r; float r_lo, r_hi;
+                pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
+                if (hit_l & hit_r) {
+                    CT_CHECK(sp < kStackMax);
+                    stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt;
+                    stk_lo[sp] = r_lo; stk_hi[sp] = r_hi; stk_src[sp] = cur_ref;
+                    sp++;
+                }
+                if (hit_l | hit_r) {
+                    cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
+                    need_pop = false;
+                }
+            }
+            if (need_pop) {
+                live = false;
+                while (sp > 0) {
+                    --sp;
+                    if (stk_lo[sp] >= r.t) continue;                          // the deferred `tmin < ray.t` of bvh.cpp:178
+                    if (!(stk_hi[sp] < r.t)) {
+                        if (COUNT) lc.box_exact++;
+                        BoxTimes e = exact_child(P.pairs64, stk_src[sp], 1u, r.r64);
+                        if (!(e.tmin < r.t)) continue;
+                    }
+                    cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; live = true;
+                    break;
+                }
+            }
+        }
+    }
+    if (!active) return kTravMiss;
+    return r.t != kRayTInit ? kTravHit : kTravMiss;
+}
+
+// The two early-exit walks.
+//   kAnyHit    shadow rays (ray.t = 1e30f): only `found` is used (raythread.cpp:306), i.e. whether SOME triangle
+//              reachable through accepted boxes has a barycentric pass with 1e-4 < t < 1e30;
+//   kFirstLine reflection rays (ray.t = 0, raythread.cpp:373): the first barycentric pass in DFS order becomes
+//              closestIndex with tclosest = 0 = the passing reachable triangle with the LOWEST leaf
+//              position (leaf positions increase along the DFS).
+// ray.t never changes before the exit, so the set of accepted boxes is fixed and the moment a leaf is tested
+// cannot change the answer.  The loop therefore walks interior nodes only and DEFERS accepted leaves to a short
+// list, in DFS order; the warp alternates between a walk phase and a leaf phase in which its lanes test their
+// triangles together, oldest leaf first, instead of one lane at a time in the middle of the walk (measured: 4 of
+// 32 lanes active in an inline leaf path, 16 in the leaf phase).  A leaf phase runs when some lane's list is full
+// and after the walk; kFirstLine stops at the first pass of a phase (every leaf before it has been tested).
+// WARP-SYNCHRONOUS like traverse_closest().  Returns kTravHit (kAnyHit: occluded; kFirstLine: always -- `found` is
+// 0 != 1e30f, raythread.cpp:227 -- with closest_pos = kNoPos when nothing passed), kTravMiss or kTravOverBudget.
+#ifndef CT_LEAF_LIST
+#define CT_LEAF_LIST 8
+#endif
+constexpr int kLeafList = CT_LEAF_LIST;       // deferred leaves per lane before a leaf phase is forced
+template <TraverseMode MODE, bool COUNT>
+CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    static_assert(MODE != kClosest, "closest-hit rays use traverse_closest");
+    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax];     // pushed right children
+    uint32_t leaf_ref[kLeafList], leaf_cnt[kLeafList];   // deferred leaves, DFS order
+    int sp = 0, nleaf = 0;
+    uint32_t spent = 1u;
+    uint32_t cur_ref = P.root_ref, cur_cnt = P.root_cnt;
+    int state = 0;                                        // 1: nodes left to walk (cur_* pending); 0: walk finished
+    int result = MODE == kFirstLine ? kTravHit : kTravMiss;
+    tclosest = kFinf;          // raythread.cpp:204
+    closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
+    if (active) {
+        if (COUNT) lc.box++;
+        state = root_accept(P, r) ? 1 : 0;
+    } else {
+        result = kTravMiss;
+    }
+    while (true) {
+        // ---- walk phase: one interior-node visit per walking lane and iteration; leaves go to the list
+        while (__any_sync(kFullMask, (state == 1) & (nleaf < kLeafList))) {
+            if ((state == 1) & (nleaf < kLeafList)) {
+                bool descend = false;
+                if (cur_cnt > 0) {
+                    CT_CHECK(nleaf < kLeafList && cur_ref + cur_cnt <= P.n_tri);
+                    leaf_ref[nleaf] = cur_ref; leaf_cnt[nleaf] = cur_cnt; nleaf++;
+                    spent += cur_cnt;
+                } else {
+                    CT_CHECK(cur_ref < P.n_pairs);
+                    DevPair32 pr;
+                    load_pair32(P.pairs32, cur_ref, pr);
+                    if (COUNT) lc.box += 2;
+                    spent += 2u;
+                    bool hit_l, hit_r; float r_lo, r_hi;
+                    pair_accept<COUNT, MODE == kAnyHit>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
+                    if (hit_l & hit_r) { CT_CHECK(sp < kStackMax); stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt; sp++; }
+                    descend = hit_l | hit_r;
+                    cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
+                }
+                if (!descend) {
+                    if (sp == 0) state = 0;
+                    else { --sp; cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; }
+                }
+                if (spent > budget) { result = kTravOverBudget; state = 0; nleaf = 0; }
+            }
+        }
+        // ---- leaf phase: one triangle per lane and iteration, oldest leaf first
+        int li = 0;
+        uint32_t tri = 0;                                 // next triangle inside leaf li
+        while (__any_sync(kFullMask, li < nleaf)) {
+            if (li < nleaf) {
+                const uint32_t pos = leaf_ref[li] + tri;
+                if (COUNT) lc.tri++;
+                const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
+                const bool done = MODE == kAnyHit ? (th.hit & (th.t > kEps) & (th.t < kRayTInit)) : th.hit;
+                if (done) {
+                    if (MODE == kAnyHit) result = kTravHit;
+                    else { closest_pos = pos; tclosest = 0.0f; }
+                    state = 0; nleaf = 0;
+                } else if (++tri == leaf_cnt[li]) { tri = 0; li++; }
+            }
+        }
+        nleaf = 0;
+        if (!__any_sync(kFullMask, state == 1)) break;
+    }
+    return result;
+}
+
+}  // namespace

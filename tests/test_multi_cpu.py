@@ -137,7 +137,7 @@ class _FakeRenderer:
             mem[1 + idx] = self.rank; mem.flush()                   # "peer store" of the finished chunk into the root's frame
             time.sleep(0.002 if self.rank == 1 else 0.0005)
             return 1
-        # the numbering of next_chunk (ct_gpu.cu): groups of 8R chunks, 7R dealt round-robin, R stolen from the cursor
+        # the numbering of next_chunk (ct_kernels.cuh): groups of 8R chunks, 7R dealt round-robin, R stolen from the cursor
         R, E = (self.part[1], 7) if self.part else (1, 0)
         G = 8 * R
         n_groups = (self.n_chunks + G - 1) // G
