@@ -71,3 +71,14 @@ def case_scene(case, golden, loader):
     if meta["force_reflection"] is not None:
         fs = fs.with_reflection(meta["force_reflection"])
     return fs, meta
+
+
+def load_fuzz_case(k):
+    """tests/golden/fuzz_<k>.npz (make_golden_fuzz.py) -> (FlatScene as the reference flattened + built it, dict of the rest)."""
+    from cobbletrace_b200.sceneio import FlatScene
+    z = np.load(os.path.join(GOLD, f"fuzz_{k}.npz"))
+    fs = FlatScene(**{f: z[f] for f in ("tri", "mat_color", "mat_specular", "mat_reflection", "light_type", "light_intensity", "light_pos",
+                                        "light_dir", "cam_pos", "cam_rot", "node_min", "node_max", "node_left", "node_first", "node_count", "tri_index")})
+    rest = {"json": bytes(z["json"]).decode(), "keys": bytes(z["keys"]).decode(), "depth": int(z["depth"]), "frame": z["frame"],
+            "found": z["found"], "index": z["index"], "t": z["t"]}
+    return fs, rest

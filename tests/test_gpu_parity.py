@@ -593,3 +593,24 @@ def test_light_sets_and_depth_limits_against_oracle(scene_loader, gpu):
         gpu.upload(scene, W, H, max_depth=depth, flags=DBG)
         gpu.render_tile()
         assert_same(gpu, oframe, ohits, what)
+
+
+@pytest.mark.gpu
+def test_random_scene_files_match_reference(golden, gpu):
+    """The 20 generated scene files of tests/golden/make_golden_fuzz.py: frames and primary hit records of the compiled
+    reference, bit for bit, with the default walk budget and with one that parks nearly every early-exit ray."""
+    from conftest import load_fuzz_case
+    for k, m in golden["fuzz"].items():
+        fs, g = load_fuzz_case(k)
+        for budget in (0, 6):
+            ct.api.set_option("traversal_budget", budget)
+            try:
+                gpu.upload(fs, m["width"], m["height"], max_depth=m["depth"], flags=DBG)
+                gpu.render_tile()
+                assert np.array_equal(gpu.readback(), g["frame"]), (k, budget)
+                found, index, t = gpu.readback_hits()
+                traced = g["found"] != 0xFFFFFFFF
+                assert np.array_equal(found, g["found"]) and np.array_equal(index[traced], g["index"][traced]), (k, budget)
+                assert np.array_equal(t[traced].view(np.uint32), g["t"][traced].view(np.uint32)), (k, budget)
+            finally:
+                ct.api.set_option("traversal_budget", 0)
