@@ -20,7 +20,10 @@ if rank == 0:
 dist.barrier()
 fs = mk()
 stream = torch.cuda.Stream(device=local)
-for flags, what in ((api.CT_FLAG_STAGE_TIMING, "serialised"), (0, "concurrent")):
+eighths = [int(v) for v in os.environ.get("CT_EIGHTHS", "7").split(",")]      # dealt share of the chunks, in eighths
+modes = ((api.CT_FLAG_STAGE_TIMING, "serialised"), (0, "concurrent")) if len(eighths) == 1 else ((0, "concurrent"),)
+for e8, (flags, what) in [(e, m) for e in eighths for m in modes]:
+    api.set_option("shared_static_eighths", e8)
     r = api.GpuRenderer(local).upload(fs, W, H, max_depth=depth, flags=flags)
     r.set_stream(stream.cuda_stream)
     sf = multi.SharedFrame(r, stream=stream)
@@ -33,7 +36,7 @@ for flags, what in ((api.CT_FLAG_STAGE_TIMING, "serialised"), (0, "concurrent"))
     agg = {}
     for nm, d, ms in (stages or []):
         agg[nm] = agg.get(nm, 0.0) + ms
-    line = f"rank {rank}/{world} {what}: {best:.3f} ms  " + " ".join(f"{k}={v:.3f}" for k, v in agg.items())
+    line = f"rank {rank}/{world} dealt {e8}/8 {what}: {best:.3f} ms  " + " ".join(f"{k}={v:.3f}" for k, v in agg.items())
     out = [None] * world
     dist.all_gather_object(out, line)
     if rank == 0:
