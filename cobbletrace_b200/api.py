@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "ct_gpu_abi_version", "ct_gpu_device_count", "ct_gpu_last_error", "ct_gpu_upload_scene", "ct_gpu_set_camera",
     "ct_gpu_set_stream", "ct_gpu_render_tile", "ct_gpu_readback", "ct_gpu_readback_hits", "ct_gpu_get_counters",
     "ct_gpu_last_tile_ms", "ct_gpu_sync", "ct_gpu_throttle", "ct_gpu_kernel_launches", "ct_gpu_last_tile_stages", "ct_gpu_framebuffer", "ct_gpu_gather_rows", "ct_gpu_debug_closest",
-    "ct_gpu_debug_primitives", "ct_gpu_debug_filter", "ct_gpu_filter_stats", "ct_gpu_shutdown", "ct_gpu_share_export", "ct_gpu_share_attach", "ct_gpu_share_reset", "ct_gpu_share_partition", "ct_gpu_render_shared", "ct_gpu_set_option", "ct_gpu_overflow_stats",
+    "ct_gpu_debug_primitives", "ct_gpu_debug_filter", "ct_gpu_filter_stats", "ct_gpu_shutdown", "ct_gpu_share_export", "ct_gpu_share_attach", "ct_gpu_share_reset", "ct_gpu_share_partition", "ct_gpu_mark_rows", "ct_gpu_render_shared", "ct_gpu_set_option", "ct_gpu_overflow_stats",
 ]
 
 
@@ -114,6 +114,7 @@ def load_library(path: Optional[str] = None):
     L.ct_gpu_share_attach.argtypes = [C.c_int, C.POINTER(Share)]
     L.ct_gpu_share_reset.argtypes = [C.c_int]
     L.ct_gpu_share_partition.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.ct_gpu_mark_rows.argtypes = [C.c_int, C.c_int, C.c_int]
     L.ct_gpu_render_shared.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(RayCounters)]
     L.ct_gpu_shutdown.argtypes = [C.c_int]
     L.ct_gpu_set_option.argtypes = [C.c_char_p, C.c_longlong]
@@ -213,6 +214,10 @@ class GpuRenderer:
             return
         h = Share.from_buffer_copy(handle)
         _check(self.L, self.L.ct_gpu_share_attach(self.device, C.byref(h)))
+
+    def mark_rows(self, row_start: int, row_end: int):
+        """Framebuffer rows filled from outside the library (e.g. multi.gather_rows_to_root): readback must cover them."""
+        _check(self.L, self.L.ct_gpu_mark_rows(self.device, row_start, row_end))
 
     def share_partition(self, index: int, count: int):
         """This GPU is participant `index` of `count` in every shared frame (ct_gpu_share_partition)."""

@@ -140,6 +140,15 @@ void free_device(DeviceState &s) {
     s = DeviceState{};
 }
 
+// The hull of rows holding rendered pixels grows from two sides: tiles this device renders (its own host thread) and rows
+// gathered into it from other devices (their host threads, ct_gpu_gather_rows).
+std::mutex g_rows_mutex;
+void extend_rows(DeviceState &s, int lo, int hi) {
+    std::lock_guard<std::mutex> lock(g_rows_mutex);
+    if (s.row_hi <= s.row_lo) { s.row_lo = lo; s.row_hi = hi; }
+    else { s.row_lo = std::min(s.row_lo, lo); s.row_hi = std::max(s.row_hi, hi); }
+}
+
 template <typename T>
 int dev_alloc(DeviceState &s, T **out, size_t count, bool zero = false) {
     void *p = nullptr;
@@ -546,8 +555,7 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     {   // framebuffer rows this tile writes: row = H/2 - y
         int lo = half - (y1 - 1), hi = half - y0 + 1 + (s.p.subsample ? 1 : 0);   // subsampling also stores row y0 - 1
         lo = std::max(lo, 0); hi = std::min(hi, s.p.H);
-        if (s.row_hi <= s.row_lo) { s.row_lo = lo; s.row_hi = hi; }
-        else { s.row_lo = std::min(s.row_lo, lo); s.row_hi = std::max(s.row_hi, hi); }
+        extend_rows(s, lo, hi);
     }
     if (counters) {
         ct_ray_counters now;
@@ -767,7 +775,9 @@ int ct_gpu_readback(int device, uint32_t *dst, int dst_stride_pixels, int row_st
     const Params &p = s.p;
     // Only rows some tile has rendered are copied: e.g. row 0 (y = H/2) is never reached by the reference's
     // loops (y < yEnd <= H/2) and so stays untouched in dst here as well.
-    int r0 = std::max(row_start, s.row_lo), r1 = std::min(row_end, s.row_hi);
+    int row_lo, row_hi;
+    { std::lock_guard<std::mutex> lock(g_rows_mutex); row_lo = s.row_lo; row_hi = s.row_hi; }
+    int r0 = std::max(row_start, row_lo), r1 = std::min(row_end, row_hi);
     int cols = s.col_hi - s.col_lo;
     if (dst_stride_pixels < p.W) return fail(CT_ERR_INVALID, "dst stride %d < width %d", dst_stride_pixels, p.W);
     CU(cudaStreamSynchronize(s.stream));
@@ -815,6 +825,16 @@ int ct_gpu_gather_rows(int src_device, int dst_device, int row_start, int row_en
     if (r1 <= r0 || src_device == dst_device) return CT_OK;
     size_t off = (size_t)r0 * a.p.W, bytes = (size_t)(r1 - r0) * a.p.W * 4;
     CU(cudaMemcpyPeerAsync(b.p.fb + off, dst_device, a.p.fb + off, src_device, bytes, a.stream));
+    extend_rows(b, r0, r1);                 // the destination's readback must cover rows it did not render itself
+    return CT_OK;
+}
+
+int ct_gpu_mark_rows(int device, int row_start, int row_end) {
+    TRY(check_device(device));
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    int r0 = std::max(row_start, 0), r1 = std::min(row_end, s.p.H);
+    if (r1 > r0) extend_rows(s, r0, r1);
     return CT_OK;
 }
 

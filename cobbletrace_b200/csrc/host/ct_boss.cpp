@@ -256,7 +256,10 @@ int boss_tiles(const Boss *b, int32_t *out, int max_tiles) {
 
 void boss_destroy(Boss *b) {
     if (!b) return;
-    if (b->gpu.shutdown) for (int i = 0; i < b->cfg.n_devices; i++) b->gpu.shutdown(b->cfg.devices[i]);
+    // nothing may still be writing into devices[0] (peer stores, gathered rows) when its memory goes: drain every
+    // device first, then let go of the attached ones before the root
+    if (b->gpu.sync) for (int i = 0; i < b->cfg.n_devices; i++) b->gpu.sync(b->cfg.devices[i]);
+    if (b->gpu.shutdown) for (int i = b->cfg.n_devices - 1; i >= 0; i--) b->gpu.shutdown(b->cfg.devices[i]);
     delete b;
 }
 

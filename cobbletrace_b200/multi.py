@@ -82,9 +82,10 @@ def exchange_tiles(my_tiles: Sequence[Tuple[int, int]], max_tiles: int, device=N
     return res
 
 
-def gather_rows_to_root(fb: torch.Tensor, tiles_by_rank: Sequence[Sequence[Tuple[int, int]]], root: int = 0) -> int:
+def gather_rows_to_root(fb: torch.Tensor, tiles_by_rank: Sequence[Sequence[Tuple[int, int]]], root: int = 0, renderer=None) -> int:
     """Every rank sends the framebuffer rows of the tiles it rendered to `root`, which receives them in place.
-    Returns the number of bytes that crossed into root."""
+    `renderer` (the root's GpuRenderer, when `fb` aliases its framebuffer) is told which rows arrived, so that its
+    readback covers them (ct_gpu_mark_rows).  Returns the number of bytes that crossed into root."""
     rank = dist.get_rank()
     H = fb.shape[0]
     ops, nbytes = [], 0
@@ -100,6 +101,8 @@ def gather_rows_to_root(fb: torch.Tensor, tiles_by_rank: Sequence[Sequence[Tuple
             elif rank == root:
                 ops.append(dist.P2POp(dist.irecv, view, r))
                 nbytes += view.numel() * view.element_size()
+                if renderer is not None:
+                    renderer.mark_rows(r0, r1)
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()

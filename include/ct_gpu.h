@@ -238,6 +238,10 @@ int ct_gpu_framebuffer(int device, void **device_ptr, int *width, int *height);
  * [row_start,row_end) of src_device into dst_device's framebuffer over NVLink.  Both devices must hold
  * an uploaded scene of the same frame size.  Asynchronous on src_device's stream. */
 int ct_gpu_gather_rows(int src_device, int dst_device, int row_start, int row_end);
+/* Rows [row_start, row_end) of `device`'s framebuffer now hold pixels that arrived from outside this library (a
+ * collective or peer copy into ct_gpu_framebuffer's pointer): ct_gpu_readback copies only rows known to hold pixels
+ * -- those this device rendered, those gathered with ct_gpu_gather_rows, and those marked here. */
+int ct_gpu_mark_rows(int device, int row_start, int row_end);
 
 /* Known-answer-test entry: ClosestIntersection (raythread.cpp:197-227) for n arbitrary rays through the
  * uploaded scene.  origins/directions: n x 3 doubles; t0: initial ray_t.t per ray (1e30f primary/shadow,

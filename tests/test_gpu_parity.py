@@ -503,12 +503,16 @@ def test_boss_two_gpus_in_one_process(scene_loader):
     W, H = 640, 480
     oframe, _, _ = O.OracleScene(fs).render(W, H, max_depth=2, want_hits=False)
     hs = host.HostScene.from_flat(fs.without_bvh())
-    for tile_rows in (0, 32):
+    for tile_rows in (0, 32, 7, 0):
         b = host.Boss(hs, W, H, devices=(0, 1), max_depth=2, tile_rows=tile_rows)
-        for _ in range(2):
-            bitmap, stats = b.render(np.zeros((H, W), np.uint32))
-            assert np.array_equal(bitmap, oframe), tile_rows
-        b.close()
+        try:
+            for _ in range(3):
+                # a fresh bitmap every frame: rows that one device rendered and the other has to hand over (gathered
+                # rows must count as "hold pixels" for the root's readback, whichever device took the outermost tiles)
+                bitmap, stats = b.render(np.zeros((H, W), np.uint32))
+                assert np.array_equal(bitmap, oframe), tile_rows
+        finally:
+            b.close()
 
 
 @pytest.mark.parametrize("W,H", [(3840, 2160), (7680, 4320)])

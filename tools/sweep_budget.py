@@ -9,7 +9,7 @@ ps = importlib.util.module_from_spec(spec); spec.loader.exec_module(ps)
 for case in ("dragon4k", "pcbig1080", "bunny1080"):
     mk, W, H, depth = ps.CASES[case]
     fs = mk()
-    for budget in (96, 128, 192, 256, 384, 512):
+    for budget in (256, 320, 384, 448, 512, 768):
         api.set_option("traversal_budget", budget)
         r = api.GpuRenderer(0).upload(fs, W, H, max_depth=depth, flags=api.CT_FLAG_STAGE_TIMING)
         best = None
