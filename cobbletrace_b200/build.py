@@ -7,6 +7,8 @@
 """
 from __future__ import annotations
 
+import contextlib
+import fcntl
 import os
 import shutil
 import subprocess
@@ -41,6 +43,28 @@ def _glob(d, exts):
     return sorted(out)
 
 
+@contextlib.contextmanager
+def _build_lock():
+    """One builder at a time per checkout: the ranks of a torchrun job all call build_all() on start-up."""
+    with open(os.path.join(PKG, ".build.lock"), "a+") as f:
+        fcntl.flock(f, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(f, fcntl.LOCK_UN)
+
+
+def _compile(cmd, target: str):
+    """Compile to a temporary name and rename: a library another process has loaded (or is loading) is never rewritten."""
+    tmp = f"{target}.tmp{os.getpid()}"
+    try:
+        subprocess.check_call([tmp if c == target else c for c in cmd], cwd=ROOT)
+        os.replace(tmp, target)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+
+
 def find_nvcc() -> str:
     for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if c and os.path.exists(c):
@@ -53,9 +77,12 @@ def build_gpu(force: bool = False, verbose: bool = False) -> str:
     deps = srcs + _glob(CSRC, (".cuh",)) + [os.path.join(ROOT, "include", "ct_gpu.h")]
     if not force and _newer(GPU_LIB, deps):
         return GPU_LIB
-    extra = os.environ.get("CT_NVCC_EXTRA", "").split()         # experiments only, e.g. -DCT_MIN_BLOCKS=5
-    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", GPU_LIB] + srcs
-    subprocess.check_call(cmd, cwd=ROOT)
+    with _build_lock():
+        if not force and _newer(GPU_LIB, deps):                 # another rank built it while we waited
+            return GPU_LIB
+        extra = os.environ.get("CT_NVCC_EXTRA", "").split()     # experiments only, e.g. -DCT_MIN_BLOCKS=5
+        cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", GPU_LIB] + srcs
+        _compile(cmd, GPU_LIB)
     return GPU_LIB
 
 
@@ -68,8 +95,11 @@ def build_host(force: bool = False) -> str:
     # Deliberately the PATH g++ and not $CXX: this image exports CXX=/opt/gcc/bin/g++, whose libstdc++.so link
     # dangles, so it silently links libstdc++.a into the .so -- a second C++ runtime next to the one torch
     # loads, and exceptions thrown inside the library then crash the process.
-    cmd = [shutil.which("g++") or "g++"] + GXX_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", HOST_LIB] + srcs + ["-ldl"]
-    subprocess.check_call(cmd, cwd=ROOT)
+    with _build_lock():
+        if not force and _newer(HOST_LIB, deps):
+            return HOST_LIB
+        cmd = [shutil.which("g++") or "g++"] + GXX_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", HOST_LIB] + srcs + ["-ldl"]
+        _compile(cmd, HOST_LIB)
     return HOST_LIB
 
 
