@@ -1,6 +1,7 @@
 // ct_host_api.cpp -- extern "C" surface of include/ct_host.h.
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
@@ -166,6 +167,27 @@ int ct_host_boss_render(ct_host_boss *b, uint32_t *bitmap, int stride_pixels, ct
 
 int ct_host_boss_tiles(const ct_host_boss *b, int32_t *y_ranges, int max_tiles) {
     return cth::boss_tiles(reinterpret_cast<const cth::Boss *>(b), y_ranges, max_tiles);
+}
+
+int ct_host_write_ppm(const char *path, const uint32_t *bitmap, int width, int height, int stride_pixels) {
+    if (!path || !bitmap || width <= 0 || height <= 0 || stride_pixels < width) { g_err = "ct_host_write_ppm: bad arguments"; return CT_ERR_INVALID; }
+    FILE *f = fopen(path, "wb");
+    if (!f) { g_err = std::string("cannot open ") + path; return CT_ERR_INVALID; }
+    fprintf(f, "P6\n%d %d\n255\n", width, height);
+    std::vector<unsigned char> row((size_t)width * 3);
+    bool ok = true;
+    for (int y = 0; y < height && ok; y++) {
+        const uint32_t *src = bitmap + (size_t)y * stride_pixels;
+        for (int x = 0; x < width; x++) {
+            row[3 * (size_t)x + 0] = (unsigned char)(src[x] & 0xFF);             // red is the low byte
+            row[3 * (size_t)x + 1] = (unsigned char)((src[x] >> 8) & 0xFF);
+            row[3 * (size_t)x + 2] = (unsigned char)((src[x] >> 16) & 0xFF);
+        }
+        ok = fwrite(row.data(), 1, row.size(), f) == row.size();
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { g_err = std::string("short write to ") + path; return CT_ERR_INVALID; }
+    return CT_OK;
 }
 
 ct_host_tile_counter *ct_host_tile_counter_open(const char *shared_name) {

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "ct_host_boss_tiles", "ct_host_boss_destroy",
     "ct_host_tile_counter_open", "ct_host_tile_counter_next", "ct_host_tile_counter_reset", "ct_host_tile_counter_close",
     "ct_host_controls_create", "ct_host_controls_add_event", "ct_host_controls_update", "ct_host_controls_pending",
-    "ct_host_controls_frames", "ct_host_controls_camera", "ct_host_controls_destroy", "ct_host_viewer_tick",
+    "ct_host_controls_frames", "ct_host_controls_camera", "ct_host_controls_destroy", "ct_host_viewer_tick", "ct_host_write_ppm",
 ]
 
 
@@ -92,6 +92,7 @@ def load_library():
         L.ct_host_controls_camera.argtypes = [vp, vp, vp, vp]
         L.ct_host_controls_destroy.argtypes = [vp]
         L.ct_host_viewer_tick.argtypes = [vp, vp, vp, C.c_int, PRESENT_FN, vp, C.POINTER(C.c_int), C.POINTER(FrameStats)]
+        L.ct_host_write_ppm.argtypes = [C.c_char_p, vp, C.c_int, C.c_int, C.c_int]
         L.ct_host_tile_counter_open.restype = vp; L.ct_host_tile_counter_open.argtypes = [C.c_char_p]
         L.ct_host_tile_counter_next.restype = C.c_int32; L.ct_host_tile_counter_next.argtypes = [vp]
         L.ct_host_tile_counter_reset.argtypes = [vp]
@@ -276,6 +277,14 @@ class Boss:
             self.close()
         except Exception:
             pass
+
+
+def write_ppm(path: str, bitmap: np.ndarray):
+    """ct_host_write_ppm: the bitmap (uint32 0x00BBGGRR, [H, W]) as a binary PPM."""
+    L = load_library()
+    b = np.ascontiguousarray(bitmap, np.uint32)
+    if L.ct_host_write_ppm(os.fsencode(path), b.ctypes.data_as(C.c_void_p), b.shape[1], b.shape[0], b.shape[1]) < 0:
+        raise RuntimeError("ct_host_write_ppm: " + _err(L))
 
 
 class Controls:

@@ -152,6 +152,10 @@ typedef void (*ct_host_present_fn)(void *user, const uint32_t *bitmap, int strid
 int ct_host_viewer_tick(ct_host_boss *b, ct_host_controls *c, uint32_t *bitmap, int stride_pixels, ct_host_present_fn present,
                         void *user, int *rendered, ct_host_frame_stats *stats);
 
+/* A ready-made frame sink for hosts without a window: writes the bitmap (0x00BBGGRR pixels, PutPixel draw2d.h:8-20) as a
+ * binary PPM (P6).  Returns CT_OK or CT_ERR_INVALID with the reason in ct_host_last_error(). */
+int ct_host_write_ppm(const char *path, const uint32_t *bitmap, int width, int height, int stride_pixels);
+
 /* The tile dispenser on its own (what the boss steals from): a process-local atomic (shared_name NULL/"")
  * or a POSIX shared-memory counter common to all processes that open the same name. */
 ct_host_tile_counter *ct_host_tile_counter_open(const char *shared_name);

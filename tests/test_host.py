@@ -283,3 +283,17 @@ def test_random_scene_files_parse_and_build_like_the_reference(golden, tmp_path)
         assert ctl.update()
         pos, _, rot = ctl.camera()
         assert np.array_equal(pos, ref.cam_pos) and np.array_equal(rot, ref.cam_rot), k
+
+
+def test_write_ppm_channel_order(tmp_path):
+    """0x00BBGGRR (PutPixel, draw2d.h:8-20) -> P6 bytes R, G, B."""
+    bm = np.array([[0x00112233, 0x000000FF], [0x0000FF00, 0x00FF0000], [0, 0xFFFFFFFF]], np.uint32)
+    p = str(tmp_path / "f.ppm")
+    host.write_ppm(p, bm)
+    data = open(p, "rb").read()
+    assert data.startswith(b"P6\n2 3\n255\n")
+    px = np.frombuffer(data[len(b"P6\n2 3\n255\n"):], np.uint8).reshape(3, 2, 3)
+    assert px[0, 0].tolist() == [0x33, 0x22, 0x11] and px[0, 1].tolist() == [255, 0, 0]
+    assert px[1, 0].tolist() == [0, 255, 0] and px[1, 1].tolist() == [0, 0, 255] and px[2, 1].tolist() == [255, 255, 255]
+    with pytest.raises(RuntimeError):
+        host.write_ppm(str(tmp_path / "no" / "such" / "dir.ppm"), bm)

@@ -17,14 +17,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cobbletrace_b200 import host  # noqa: E402
 
 
-def write_ppm(path, bitmap):
-    """bitmap: uint32 0x00BBGGRR (PutPixel, draw2d.h:8-20)."""
-    rgb = np.stack([bitmap & 0xFF, (bitmap >> 8) & 0xFF, (bitmap >> 16) & 0xFF], -1).astype(np.uint8)
-    with open(path, "wb") as f:
-        f.write(b"P6\n%d %d\n255\n" % (bitmap.shape[1], bitmap.shape[0]))
-        f.write(rgb.tobytes())
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scene", required=True)
@@ -44,7 +36,7 @@ def main():
 
     def present(bitmap, is_new):
         if is_new and a.out:
-            write_ppm(os.path.join(a.out, f"frame_{n[0]:03d}.ppm"), bitmap)
+            host.write_ppm(os.path.join(a.out, f"frame_{n[0]:03d}.ppm"), bitmap)
         n[0] += int(is_new)
 
     v = host.Viewer(boss, present=present)
