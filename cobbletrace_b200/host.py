@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "ct_host_boss_tiles", "ct_host_boss_destroy",
     "ct_host_tile_counter_open", "ct_host_tile_counter_next", "ct_host_tile_counter_reset", "ct_host_tile_counter_close",
     "ct_host_controls_create", "ct_host_controls_add_event", "ct_host_controls_update", "ct_host_controls_pending",
-    "ct_host_controls_frames", "ct_host_controls_camera", "ct_host_controls_destroy", "ct_host_viewer_tick", "ct_host_write_ppm",
+    "ct_host_controls_frames", "ct_host_controls_camera", "ct_host_controls_destroy", "ct_host_viewer_tick", "ct_host_write_ppm", "ct_host_scene_render_flags",
 ]
 
 
@@ -92,6 +92,7 @@ def load_library():
         L.ct_host_controls_camera.argtypes = [vp, vp, vp, vp]
         L.ct_host_controls_destroy.argtypes = [vp]
         L.ct_host_viewer_tick.argtypes = [vp, vp, vp, C.c_int, PRESENT_FN, vp, C.POINTER(C.c_int), C.POINTER(FrameStats)]
+        L.ct_host_scene_render_flags.argtypes = [vp, C.POINTER(C.c_uint32)]
         L.ct_host_write_ppm.argtypes = [C.c_char_p, vp, C.c_int, C.c_int, C.c_int]
         L.ct_host_tile_counter_open.restype = vp; L.ct_host_tile_counter_open.argtypes = [C.c_char_p]
         L.ct_host_tile_counter_next.restype = C.c_int32; L.ct_host_tile_counter_next.argtypes = [vp]
@@ -174,6 +175,13 @@ class HostScene:
         s = HostSettings(); self.L.ct_host_scene_settings(self.h, C.byref(s))
         return dict(numberOfThreads=s.number_of_threads, subsampling=bool(s.subsampling), wireframe=bool(s.wireframe),
                     supersampling=bool(s.supersampling))
+
+    def render_flags(self) -> int:
+        """CT_FLAG_* implied by the scene file's settings (ct_host_scene_render_flags)."""
+        f = C.c_uint32(0)
+        if self.L.ct_host_scene_render_flags(self.h, C.byref(f)) < 0:
+            raise RuntimeError("ct_host_scene_render_flags: " + _err(self.L))
+        return int(f.value)
 
     def set_reflection(self, reflection: float):
         self.L.ct_host_scene_set_reflection(self.h, reflection)

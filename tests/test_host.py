@@ -76,6 +76,14 @@ def test_parser_number_and_colour_semantics(tmp_path):
     assert fs.mat_specular[0] == -1 and fs.mat_reflection[0] == f32(0.3333)
     assert list(fs.light_type) == [ct.sceneio.LT_AMBIENT, ct.sceneio.LT_POINT, ct.sceneio.LT_DIRECTIONAL]
     assert hs.settings() == dict(numberOfThreads=4, subsampling=False, wireframe=False, supersampling=True)
+    assert hs.render_flags() == ct.api.CT_FLAG_SUPERSAMPLING
+    both = tmp_path / "both.json"
+    both.write_text(SMALL_SCENE.replace('"subsampling": false', '"subsampling": true'))
+    with pytest.raises(RuntimeError, match="at once"):
+        host.HostScene.load(str(both)).render_flags()
+    plain = tmp_path / "plain.json"
+    plain.write_text(SMALL_SCENE.replace('"supersampling": true', '"supersampling": false'))
+    assert host.HostScene.load(str(plain)).render_flags() == 0
     assert np.array_equal(fs.cam_pos, [0, 0.5, -3])
 
 
