@@ -224,8 +224,8 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     if (d->n_lights && !d->lights) return fail(CT_ERR_INVALID, "n_lights > 0 but lights == NULL");
     if (d->width <= 0 || d->height <= 0 || (int64_t)d->width * d->height > (1ll << 30)) return fail(CT_ERR_INVALID, "bad frame size %dx%d", d->width, d->height);
     if (d->max_depth < 0 || d->max_depth > 15) return fail(CT_ERR_LIMIT, "max_depth %d outside 0..15", d->max_depth);
-    if ((d->flags & CT_FLAG_SUPERSAMPLING) && (d->flags & (CT_FLAG_SUBSAMPLING | CT_FLAG_KEEP_HITS)))
-        return fail(CT_ERR_INVALID, "CT_FLAG_SUPERSAMPLING cannot be combined with CT_FLAG_SUBSAMPLING or CT_FLAG_KEEP_HITS");
+    if ((d->flags & CT_FLAG_SUPERSAMPLING) && (d->flags & CT_FLAG_KEEP_HITS))
+        return fail(CT_ERR_INVALID, "CT_FLAG_SUPERSAMPLING cannot be combined with CT_FLAG_KEEP_HITS (a pixel has 16 primary rays)");
     bool ok = true;
     int depth = bvh_depth(d->nodes, d->n_nodes, d->n_triangles, &ok);
     if (!ok) return fail(CT_ERR_INVALID, "BVH is malformed (child or triangle range out of bounds, or a cycle)");
@@ -545,8 +545,8 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     }
     if (!stages) for (int d = 0; d <= depth_max; d++) CU(cudaStreamWaitEvent(st, s.ev_done[d], 0));
     if (depth_max > 0) { k_resolve<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("resolve", 0)); }
-    if (pk.subsample) { k_subsample<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("subsample", 0)); }
     if (pk.supersample) { k_supersample<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("supersample", 0)); }
+    if (pk.subsample) { k_subsample<<<s.n_sm * 4, 256, 0, st>>>(pk); TRY(mark("subsample", 0)); }
     CU(cudaEventRecord(s.ev1, st));
     CU(cudaEventRecord(s.tile_done[s.tiles_submitted % 8], st));
     s.tiles_submitted++;

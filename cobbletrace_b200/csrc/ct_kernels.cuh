@@ -629,18 +629,19 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Params 
 // below, at (x, y - 1).  Runs after every traced pixel of the tile has its final colour; a later store wins where
 // the reference's sequential loop would overwrite (the always-traced last row of an even partition).
 __global__ void __launch_bounds__(256) k_subsample(const __grid_constant__ Params P) {
-    const uint32_t n = depth0_count(P);
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        const uint32_t slot = own_slot(P, q);
+    const uint32_t ss = P.supersample ? 4u : 0u;              // with supersampling a pixel owns 16 slots; its blended colour sits in the first
+    const uint32_t n = depth0_count(P) >> ss;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = own_slot(P, i << ss);
         int x, y, fbi;
         if (!slot_pixel(P, slot, x, y, fbi)) continue;
-        const uint32_t blk = slot >> 5, lane = slot & 31u;
+        const uint32_t pix = slot >> ss, blk = pix >> 5, lane = pix & 31u;
         const uint32_t iy = (blk / (uint32_t)P.blocks_x) * 4u + (lane >> 3);
         const uint32_t color = P.final_color[slot];
         uint32_t last = color;                                                 // :513-514
         if (iy > 0) {
             const uint32_t py = iy - 1u, ix = (blk % (uint32_t)P.blocks_x) * 8u + (lane & 7u);
-            last = P.final_color[(((py >> 2) * (uint32_t)P.blocks_x + (ix >> 3)) << 5) + ((py & 3u) << 3) + (ix & 7u)];
+            last = P.final_color[((((py >> 2) * (uint32_t)P.blocks_x + (ix >> 3)) << 5) + ((py & 3u) << 3) + (ix & 7u)) << ss];
         }
         uint32_t avg = 0;                                                      // :517-523: float (a + b) / 2, min 0xff, truncated
         for (int sh = 0; sh <= 16; sh += 8) avg |= ((((last >> sh) & 0xffu) + ((color >> sh) & 0xffu)) >> 1) << sh;
@@ -670,7 +671,8 @@ __global__ void __launch_bounds__(256) k_supersample(const __grid_constant__ Par
             color = out;
         }
         const int col = x + P.W / 2, row = P.H / 2 - y;
-        P.fb_out[row * P.W + col] = color;
+        if (row >= 0 && row < P.H) P.fb_out[row * P.W + col] = color;          // with subsampling a row PutPixel drops is still traced
+        if (P.subsample) P.final_color[slot] = color;                          // the pixel's colour, for k_subsample (runs after this kernel)
     }
 }
 

@@ -94,7 +94,6 @@ int ct_host_scene_render_flags(const ct_host_scene *s, uint32_t *flags) {
     if (!s || !flags) { g_err = "NULL scene or flags"; return CT_ERR_INVALID; }
     const ct_host_settings &st = S(s)->settings;
     *flags = (st.subsampling ? (uint32_t)CT_FLAG_SUBSAMPLING : 0u) | (st.supersampling ? (uint32_t)CT_FLAG_SUPERSAMPLING : 0u);
-    if (st.subsampling && st.supersampling) { g_err = "settings ask for subsampling and supersampling at once: not supported by ct_gpu"; return CT_ERR_INVALID; }
     return CT_OK;
 }
 

@@ -75,7 +75,8 @@ enum {
                                  the pixel by the reference's running blend.  The reference draws the jitter from libc rand()
                                  on all worker threads at once and is not reproducible; this flag uses a counter-based
                                  generator keyed on (x, y, call number) instead -- the same function the parity
-                                 harness substitutes for rand() in the compiled reference (sampling modes).  16x the rays of a plain frame. */
+                                 harness substitutes for rand() in the compiled reference (sampling modes).  16x the rays of a plain frame.
+                                 Combines with CT_FLAG_SUBSAMPLING as in the reference (not with CT_FLAG_KEEP_HITS). */
     CT_FLAG_SUBSAMPLING = 16u /* settings.subsampling (raythread.cpp:512-531): of the rows of a tile (= one worker's
                                  partition) every other one and the last are traced, the rows between get the average
                                  of their neighbours.  Tiles must be rendered in the order the caller wants their

@@ -61,9 +61,8 @@ void ct_host_scene_camera(const ct_host_scene *s, double pos[3], double rot[9]);
 void ct_host_scene_set_camera(ct_host_scene *s, const double pos[3], const double rot[9]);
 void ct_host_scene_settings(const ct_host_scene *s, ct_host_settings *out);
 /* The CT_FLAG_* a renderer needs to honour the scene file's own settings (raythread.cpp:460,512): subsampling ->
- * CT_FLAG_SUBSAMPLING, supersampling -> CT_FLAG_SUPERSAMPLING (deterministic jitter, see ct_gpu.h).  Both at once is the one
- * combination ct_gpu does not render: then *flags gets both bits and the call returns CT_ERR_INVALID.  Benchmarks and
- * parity tests pass 0 instead (sampling off). */
+ * CT_FLAG_SUBSAMPLING, supersampling -> CT_FLAG_SUPERSAMPLING (deterministic jitter, see ct_gpu.h); they combine as in the
+ * reference.  Benchmarks and parity tests pass 0 instead (sampling off). */
 int ct_host_scene_render_flags(const ct_host_scene *s, uint32_t *flags);
 /* Harness-level material override (BASELINE config 3: "reflection > 0 forced"). */
 void ct_host_scene_set_reflection(ct_host_scene *s, float reflection);

@@ -41,6 +41,14 @@ SS_CASES = [
 ]
 
 
+# both settings at once (the reference blends the 16 samples of every traced pixel, then averages the rows between)
+BOTH_CASES = [
+    ("cube_64x61", "scene_file_cube", "scene_file_cube.json", 64, 61, 4, None),
+    ("bunny_refl_d2_72x48", "scene_import_bunny", "scene_import_bunny.json", 72, 48, 2, 0.5),
+    ("import_tall_40x66", "scene_import", "scene_import.json", 40, 66, 10, None),
+]
+
+
 def main():
     if not O.ref_available():
         sys.exit("oracle/_ref/ct_ref missing: run `make -C oracle ref` first (needs /root/reference)")
@@ -73,6 +81,19 @@ def main():
         gold["frames_supersampling"][case] = {"scene": scene, "width": W, "height": H, "depth": depth, "force_reflection": refl,
                                               "fnv1a": frame_fnv1a(frame)}
         print("supersampling", case, gold["frames_supersampling"][case]["fnv1a"], flush=True)
+    gold["frames_both_sampling"] = {}
+    for case, scene, jf, W, H, depth, refl in BOTH_CASES:
+        fr = os.path.join(tmp, case + ".bothframe")
+        args = ["--scene", jf, "--chdir", SCENES, "--width", str(W), "--height", str(H), "--depth", str(depth), "--threads", "1",
+                "--subsampling", "--supersampling-hash", "--frame", fr]
+        if refl is not None:
+            args += ["--force-reflection", repr(refl)]
+        subprocess.run([os.path.join(O.REF_DIR, "ct_ref")] + args, check=True, capture_output=True)
+        frame = np.fromfile(fr, np.uint32).reshape(H, W)
+        np.savez_compressed(os.path.join(GOLD, f"frames_both_{case}.npz"), frame=frame)
+        gold["frames_both_sampling"][case] = {"scene": scene, "width": W, "height": H, "depth": depth, "force_reflection": refl,
+                                              "fnv1a": frame_fnv1a(frame)}
+        print("both", case, gold["frames_both_sampling"][case]["fnv1a"], flush=True)
     with open(gpath, "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
 

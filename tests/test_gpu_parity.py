@@ -618,3 +618,31 @@ def test_random_scene_files_match_reference(golden, gpu):
                 assert np.array_equal(t[traced].view(np.uint32), g["t"][traced].view(np.uint32)), (k, budget)
             finally:
                 ct.api.set_option("traversal_budget", 0)
+
+
+@pytest.mark.gpu
+def test_both_sampling_modes_at_once(golden, scene_loader, gpu):
+    """CT_FLAG_SUBSAMPLING | CT_FLAG_SUPERSAMPLING: frames of the compiled reference with both settings on, then a frame cut
+    into partitions rendered in sequence against the oracle doing the same."""
+    both = ct.CT_FLAG_SUBSAMPLING | ct.CT_FLAG_SUPERSAMPLING
+    for case, m in golden["frames_both_sampling"].items():
+        fs = scene_loader(m["scene"])
+        if m["force_reflection"] is not None:
+            fs = fs.with_reflection(m["force_reflection"])
+        gpu.upload(fs, m["width"], m["height"], max_depth=m["depth"], flags=both)
+        gpu.render_tile()
+        assert np.array_equal(gpu.readback(), np.load(os.path.join(GOLD, f"frames_both_{case}.npz"))["frame"]), case
+    fs = scene_loader("scene_import_bunny").with_reflection(0.4)
+    W, H = 150, 101
+    half = H // 2
+    cuts = [-half, -31, -30, 2, 17, -half + H]
+    want = np.zeros((H, W), np.uint32)
+    osc = O.OracleScene(fs)
+    for a, b in zip(cuts[:-1], cuts[1:]):                     # the oracle's partitions write into one frame, in order
+        part, _, _ = osc.render(W, H, y_start=a, y_end=b, max_depth=2, flags=O.SUBSAMPLE | O.SUPERSAMPLE, want_hits=False, n_threads=1)
+        want = np.where(part != 0, part, want)
+    gpu.upload(fs, W, H, max_depth=2, flags=both)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        gpu.render_tile(a, b)
+    got = gpu.readback()
+    assert np.array_equal(got, want)

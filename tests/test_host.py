@@ -79,8 +79,7 @@ def test_parser_number_and_colour_semantics(tmp_path):
     assert hs.render_flags() == ct.api.CT_FLAG_SUPERSAMPLING
     both = tmp_path / "both.json"
     both.write_text(SMALL_SCENE.replace('"subsampling": false', '"subsampling": true'))
-    with pytest.raises(RuntimeError, match="at once"):
-        host.HostScene.load(str(both)).render_flags()
+    assert host.HostScene.load(str(both)).render_flags() == ct.api.CT_FLAG_SUPERSAMPLING | ct.api.CT_FLAG_SUBSAMPLING
     plain = tmp_path / "plain.json"
     plain.write_text(SMALL_SCENE.replace('"supersampling": true', '"supersampling": false'))
     assert host.HostScene.load(str(plain)).render_flags() == 0

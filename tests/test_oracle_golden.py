@@ -163,3 +163,18 @@ def test_random_scene_files_match_reference(golden):
         traced = g["found"] != 0xFFFFFFFF
         assert np.array_equal(hits["found"], g["found"]) and np.array_equal(hits["index"][traced], g["index"][traced]), k
         assert np.array_equal(hits["t"][traced].view(np.uint32), g["t"][traced].view(np.uint32)), k
+
+
+def test_both_sampling_modes_at_once_match_patched_reference(golden, scene_loader):
+    """settings.subsampling and settings.supersampling together (raythread.cpp:460-531): frames of the compiled reference
+    (one thread, --subsampling --supersampling-hash) against the restatement."""
+    import os
+    from oracle import ct_oracle_py as O
+    from conftest import GOLD
+    assert len(golden["frames_both_sampling"]) >= 3
+    for case, m in golden["frames_both_sampling"].items():
+        fs = scene_loader(m["scene"])
+        if m["force_reflection"] is not None:
+            fs = fs.with_reflection(m["force_reflection"])
+        frame, _, _ = O.OracleScene(fs).render(m["width"], m["height"], max_depth=m["depth"], flags=O.SUBSAMPLE | O.SUPERSAMPLE, want_hits=False, n_threads=1)
+        assert np.array_equal(frame, np.load(os.path.join(GOLD, f"frames_both_{case}.npz"))["frame"]), case
