@@ -66,3 +66,26 @@ def test_product_never_imports_oracle():
                     if re.search(r"ct_oracle|from oracle|import oracle|oracle/", txt):
                         bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_headers_are_plain_c_and_the_example_host_builds(tmp_path):
+    """include/*.h must be usable from C (the reference is C-style C++; other hosts bind the same header): the example
+    host compiles as C99 with -Werror, links against libct_host.so only, and -- without a CUDA device -- fails loudly
+    instead of rendering anything on the CPU."""
+    import shutil, subprocess
+    import torch
+    host.load_library()                                        # make sure libct_host.so is built
+    exe = str(tmp_path / "viewer")
+    pkg = os.path.join(ROOT, "cobbletrace_b200")
+    subprocess.run([shutil.which("gcc") or "gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", "headless_viewer.c"),
+                    "-I", os.path.join(ROOT, "include"), "-L", pkg, "-lct_host", f"-Wl,-rpath,{pkg}", "-o", exe], check=True)
+    scene = tmp_path / "s.json"
+    scene.write_text('{"objects":[{"type": "triangle", "p1": [-1, -1, 4], "p2": [1, -1, 4], "p3": [0, 1, 4], "color": [255, 0, 0], "specular": 10, "reflection": 0}],'
+                     ' "lights":[{"type": "ambient", "intensity": 0.5}], "camera":{"position": [0, 0, -3]},'
+                     ' "settings":{"numberOfThreads": 2, "subsampling": false, "wireframe": false, "supersampling": false}}')
+    r = subprocess.run([exe, str(scene), "w|", str(tmp_path / "f")], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "tick 1: new frame" in r.stdout and "tick 2: nothing changed" in r.stdout, r.stdout + r.stderr
+        assert os.path.exists(str(tmp_path / "f_001.ppm"))
+    else:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr, r.stdout + r.stderr
