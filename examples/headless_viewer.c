@@ -46,13 +46,13 @@ int main(int argc, char **argv) {
     if (!boss) { fprintf(stderr, "%s\n", ct_host_last_error()); return 1; }
     ctl = ct_host_controls_create(scene, 0);
     bitmap = (uint32_t *)calloc((size_t)WIDTH * HEIGHT, sizeof *bitmap);
-    for (;;) {                                                /* one iteration = one tick of the reference's loop */
+    for (int more = 1; more;) {                               /* one iteration = one tick of the reference's loop */
         int fresh = 0;
         if (ct_host_viewer_tick(boss, ctl, bitmap, WIDTH, present, &out, &fresh, NULL) != CT_OK) { fprintf(stderr, "%s\n", ct_host_last_error()); return 1; }
         printf("tick %d: %s\n", tick++, fresh ? "new frame" : "nothing changed");
-        if (!*keys) break;
+        more = tick == 1 ? *keys != 0 : *keys == '|';          /* "a|b" = two batches; "a|" = a batch and an idle tick */
+        if (tick > 1 && more) keys++;
         for (; *keys && *keys != '|'; keys++) ct_host_controls_add_event(ctl, CT_EVENT_KEY_DOWN, (uint32_t)*keys);
-        if (*keys == '|') keys++;
     }
     free(bitmap);
     ct_host_controls_destroy(ctl);
