@@ -151,6 +151,12 @@ def test_threaded_ingest_and_build_match_the_sequential_reference_algorithms(thr
     if threads == "8":
         b = O.build_bvh(fs.tri)
         assert all(np.array_equal(v, getattr(fs, k)) for k, v in b.items())
+    # the order-exact scatter form of the reference's partition (split_node_parallel, tools/partition_closed_form.py),
+    # forced onto every node above the task grain
+    monkeypatch.setenv("CT_HOST_THREADS", "4" if threads == "1" else threads)
+    monkeypatch.setenv("CT_HOST_PAR_PARTITION_MIN", "3")
+    par = host.HostScene.load(scene, base_dir=str(tmp_path)).to_flat(with_bvh=True)
+    assert par.bvh_digest() == one.bvh_digest()
 
 
 @pytest.mark.parametrize("style", ["crlf", "blank_lines", "indented", "no_final_newline", "short_line"])
