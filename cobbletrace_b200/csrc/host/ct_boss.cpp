@@ -8,8 +8,8 @@
 //     used (torchrun): load balance follows the image content, no row is ever dropped;
 //   * completion is a stream synchronisation, not polling of `status` flags (:657-661);
 //   * with several GPUs in one process and no tile size given, the frame is ONE shared tile: the devices' own
-//     warps steal 64-pixel chunks from a cursor on devices[0] over NVLink and store finished pixels straight into
-//     its framebuffer (ct_gpu_render_shared); with a tile size, finished row tiles of the other GPUs are copied
+//     warps trace 32-pixel chunks (most dealt round-robin, the rest stolen from a cursor on devices[0] over NVLink:
+//     ct_gpu_share_partition) and store finished pixels straight into its framebuffer (ct_gpu_render_shared); with a tile size, finished row tiles of the other GPUs are copied
 //     to devices[0] (ct_gpu_gather_rows -> cudaMemcpyPeerAsync) before the single readback.
 // libct_gpu.so is loaded with dlopen so this library also loads on machines without CUDA; rendering
 // then fails loudly (there is no CPU path).
@@ -134,8 +134,8 @@ Boss *boss_create(Scene *scene, const ct_host_boss_config *cfg) {
             if (total_devices == 1) rows = b->y_hi - b->y_lo;                        // one tile: whole frame in flight
             else rows = std::max(8, ((b->y_hi - b->y_lo) / (total_devices * 8) + 3) / 4 * 4);
         }
-        // Several GPUs in this process and no tile size asked for: one shared frame -- the devices' own warps steal
-        // 64-pixel chunks from a cursor on devices[0] over NVLink and store their pixels into its framebuffer.
+        // Several GPUs in this process and no tile size asked for: one shared frame -- the devices' own warps take
+        // 32-pixel chunks (dealt, and stolen from a cursor on devices[0] over NVLink) and store their pixels into its framebuffer.
         b->shared_frame = !shared && cfg->n_devices > 1 && cfg->tile_rows <= 0 && !(cfg->flags & CT_FLAG_SUBSAMPLING);
         if (b->shared_frame) {
             rows = b->y_hi - b->y_lo;
