@@ -539,3 +539,82 @@ uint32_t ct_oracle_build_bvh(uint32_t n_tri, const double *tri, double *node_min
     free(b.centroid);
     return b.used;
 }
+
+/* ---- prototype ("what comes next" 1): the pre-hit phase of a closest-hit walk is order-free ----------
+ * Until the first triangle test that changes ray.t (barycentric pass with 1e-4 < t < 1e30) the set of accepted boxes
+ * is fixed, so WHICH triangle that is -- the one with the lowest leaf position among all such triangles reachable
+ * through boxes accepted with ray.t = 1e30 -- can be found in any order.  From there the reference's walk is
+ * reproduced by rebuilding its stack: the accepted right siblings along the root path of that leaf, deepest on top.
+ * ct_oracle_closest_prehit does exactly that (phase 1 deliberately right-child-first) and must return what
+ * ct_oracle_closest returns; tests/test_prehit_prototype.py checks it on every primary ray of the golden scenes. */
+static void prehit_search(const ct_oracle_scene *s, const ray *r0, uint32_t node, uint32_t *best_pos) {
+    if (!intersect_aabb(r0, s->node_min + 3 * (size_t)node, s->node_max + 3 * (size_t)node)) return;
+    uint32_t count = s->node_count[node];
+    if (count > 0) {
+        uint32_t first = s->node_first[node];
+        for (uint32_t i = 0; i < count && first + i < *best_pos; i++) {
+            ray tmp = *r0;
+            if (intersect_triangle(&tmp, s->tri + 9 * (size_t)s->tri_index[first + i]) && tmp.t != RAY_T_INIT) *best_pos = first + i;
+        }
+    } else {
+        prehit_search(s, r0, s->node_left[node] + 1, best_pos);      /* any order will do: right child first */
+        prehit_search(s, r0, s->node_left[node], best_pos);
+    }
+}
+
+void ct_oracle_prehit_tables(const ct_oracle_scene *s, uint32_t *node_parent, uint32_t *leaf_of_pos) {
+    node_parent[0] = 0xffffffffu;
+    for (uint32_t n = 0; n < s->n_nodes; n++) {
+        if (s->node_count[n] == 0) {
+            if (s->node_left[n] + 1 < s->n_nodes) { node_parent[s->node_left[n]] = n; node_parent[s->node_left[n] + 1] = n; }
+        } else {
+            for (uint32_t i = 0; i < s->node_count[n]; i++) leaf_of_pos[s->node_first[n] + i] = n;
+        }
+    }
+}
+
+int ct_oracle_closest_prehit(const ct_oracle_scene *s, const uint32_t *node_parent, const uint32_t *leaf_of_pos,
+                             const double org[3], const double dir[3], uint32_t *index, float *tclosest) {
+    ctx cx; memset(&cx, 0, sizeof cx); cx.s = s;
+    ray r = {v_load(org), v_load(dir), RAY_T_INIT};
+    *tclosest = FINF;
+    *index = 0;
+    uint32_t best = 0xffffffffu;
+    prehit_search(s, &r, 0, &best);
+    if (best == 0xffffffffu) return 0;                              /* ray.t never changes: "not found" */
+    /* the leaf of the first effective hit, tested as the reference tests it (the triangles before the hit change nothing) */
+    uint32_t leaf = leaf_of_pos[best];
+    for (uint32_t i = 0; i < s->node_count[leaf]; i++) {
+        uint32_t k = s->tri_index[s->node_first[leaf] + i];
+        int hit = intersect_triangle(&r, s->tri + 9 * (size_t)k);
+        if (hit && r.t != RAY_T_INIT && r.t < *tclosest) { *index = k; *tclosest = r.t; }
+    }
+    /* the reference's pending work at that moment: right siblings of the left turns on the root path, accepted when
+     * they were pushed (ray.t was still 1e30); the deepest is visited first, each re-tested against the current ray.t */
+    ray r0 = {r.org, r.dir, RAY_T_INIT};
+    for (uint32_t child = leaf, parent = node_parent[leaf]; parent != 0xffffffffu; child = parent, parent = node_parent[parent]) {
+        if (child != s->node_left[parent]) continue;                 /* came from the right child: nothing pending here */
+        uint32_t sib = child + 1;
+        if (!intersect_aabb(&r0, s->node_min + 3 * (size_t)sib, s->node_max + 3 * (size_t)sib)) continue;
+        bvh_closest(&cx, &r, sib, tclosest, index);
+    }
+    return r.t != RAY_T_INIT;
+}
+
+/* Both walks over n rays (ray.t = 1e30); returns the number of rays on which found / index / tclosest differ. */
+uint64_t ct_oracle_prehit_check(const ct_oracle_scene *s, uint64_t n, const double *org, const double *dir, uint64_t *n_found) {
+    uint32_t *node_parent = (uint32_t *)malloc((size_t)s->n_nodes * sizeof(uint32_t));
+    uint32_t *leaf_of_pos = (uint32_t *)malloc((size_t)s->n_tri * sizeof(uint32_t));
+    ct_oracle_prehit_tables(s, node_parent, leaf_of_pos);
+    uint64_t bad = 0, found = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t ia, ib; float ta, tb;
+        int fa = ct_oracle_closest(s, org + 3 * i, dir + 3 * i, RAY_T_INIT, &ia, &ta);
+        int fb = ct_oracle_closest_prehit(s, node_parent, leaf_of_pos, org + 3 * i, dir + 3 * i, &ib, &tb);
+        found += (uint64_t)fa;
+        if (fa != fb || ia != ib || memcmp(&ta, &tb, sizeof ta) != 0) bad++;
+    }
+    free(node_parent); free(leaf_of_pos);
+    if (n_found) *n_found = found;
+    return bad;
+}

@@ -83,6 +83,14 @@ int ct_oracle_closest(const ct_oracle_scene *s, const double org[3], const doubl
 uint32_t ct_oracle_shade_color(uint32_t material_color, float intensity); /* ColorToHsv + HsvToColor, color.h:114-126 */
 uint32_t ct_oracle_blend(uint32_t local_color, uint32_t reflected_color, float reflection); /* raythread.cpp:375-379 */
 
+/* Prototype of the order-free pre-hit phase of a closest-hit walk (see the comment in ct_oracle.c): must agree with
+ * ct_oracle_closest for ray_t0 = 1e30.  Tables: node_parent[n_nodes], leaf_of_pos[n_tri]. */
+void ct_oracle_prehit_tables(const ct_oracle_scene *s, uint32_t *node_parent, uint32_t *leaf_of_pos);
+int ct_oracle_closest_prehit(const ct_oracle_scene *s, const uint32_t *node_parent, const uint32_t *leaf_of_pos,
+                             const double org[3], const double dir[3], uint32_t *index, float *tclosest);
+/* Both walks over n rays; returns how many differ in found / index / tclosest (bitwise). */
+uint64_t ct_oracle_prehit_check(const ct_oracle_scene *s, uint64_t n, const double *org, const double *dir, uint64_t *n_found);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,8 @@ def lib():
         L.ct_oracle_intersect_triangle.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
         L.ct_oracle_intersect_aabb.restype = C.c_int
         L.ct_oracle_intersect_aabb.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        L.ct_oracle_prehit_check.restype = C.c_uint64
+        L.ct_oracle_prehit_check.argtypes = [C.POINTER(_Scene), C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.ct_oracle_closest.restype = C.c_int
         L.ct_oracle_closest.argtypes = [C.POINTER(_Scene), C.c_void_p, C.c_void_p, C.c_float, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         L.ct_oracle_shade_color.restype = C.c_uint32
@@ -140,6 +142,15 @@ class OracleScene:
         idx = C.c_uint32(); t = C.c_float()
         found = lib().ct_oracle_closest(C.byref(self.c), _ptr(org), _ptr(direction), np.float32(t0), C.byref(idx), C.byref(t))
         return bool(found), int(idx.value), float(t.value)
+
+
+def prehit_check(scene: "OracleScene", org, direction):
+    """Prototype check (ct_oracle.c): reference-order closest-hit walk vs "order-free pre-hit phase + rebuilt stack"
+    over the given rays.  Returns (rays that differ, rays that found something)."""
+    org = np.ascontiguousarray(org, np.float64); direction = np.ascontiguousarray(direction, np.float64)
+    found = C.c_uint64()
+    bad = lib().ct_oracle_prehit_check(C.byref(scene.c), org.shape[0], _ptr(org), _ptr(direction), C.byref(found))
+    return int(bad), int(found.value)
 
 
 def camera_rotation(yaw=0.0, pitch=0.0, roll=0.0):
