@@ -152,10 +152,16 @@ class GpuRenderer:
 
     # -- ct_gpu_upload_scene ------------------------------------------------------------------------
     def upload(self, fs: FlatScene, width: int, height: int, max_depth: int = REFERENCE_MAX_DEPTH, flags: int = 0,
-               background: int = BACKGROUND, viewport=(1.0, 1.0, 1.0)):
+               background: int = BACKGROUND, viewport=(1.0, 1.0, 1.0), triangle_stride: int = 72):
+        """`triangle_stride` = 96 lays the vertices out like the reference's triangle_t (scenefile.h:36-41: p1, p2, p3 and
+        a centroid the tracer never reads -- filled with NaNs here so that a wrong stride cannot go unnoticed)."""
         if not fs.has_bvh():
             raise ValueError("FlatScene has no BVH: build it on the host first (cobbletrace_b200.host.build_bvh)")
         tri = np.ascontiguousarray(fs.tri, np.float64)
+        if triangle_stride != 72:
+            wide = np.full((fs.n_tri, triangle_stride // 8), np.nan)
+            wide[:, :9] = tri.reshape(fs.n_tri, 9)
+            tri = wide
         mats = np.zeros(fs.n_tri, MAT_DT)
         mats["color"], mats["specular"], mats["reflection"] = fs.mat_color, fs.mat_specular, fs.mat_reflection
         lights = np.zeros(max(fs.n_lights, 1), LIGHT_DT)
@@ -167,7 +173,7 @@ class GpuRenderer:
         d = SceneDesc()
         d.struct_size = C.sizeof(SceneDesc)
         d.flags = flags
-        d.n_triangles, d.triangle_stride = fs.n_tri, 72
+        d.n_triangles, d.triangle_stride = fs.n_tri, triangle_stride
         d.triangles, d.materials = _ptr(tri), _ptr(mats)
         d.n_nodes, d.n_lights = fs.n_nodes, fs.n_lights
         d.nodes, d.tri_indexes, d.lights = _ptr(nodes), _ptr(idx), _ptr(lights)

@@ -215,7 +215,9 @@ int ct_gpu_sync(int device);
  *                       one of R GPUs gets in a shared frame (the other pixels are simply not rendered); applies to
  *                       the next render, 0 / 1 = off.
  *   "shared_static_eighths"  see ct_gpu_share_partition.
- *   "shared_chunk_shift"  log2 of the pixels a warp steals at a time in a shared frame: 5 (default, also 0) or 6. */
+ *   "shared_chunk_shift"  log2 of the pixels a warp steals at a time in a shared frame: 5 (default, also 0) or 6.
+ *   "l2_persist"        1 (default): set aside L2 for persisting lines and open an access-policy window over the walk's
+ *                       fp32 records on the render streams; 0: leave the L2 to the default policy (for A/B measurements). */
 int ct_gpu_set_option(const char *name, long long value);
 
 /* Rays parked so far on `device` since upload (shadow and reflection rays whose DFS ran past the budget, e.g. the

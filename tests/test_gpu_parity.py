@@ -327,6 +327,17 @@ def test_supersampling_against_patched_reference_and_oracle(golden, scene_loader
     assert np.array_equal(got2, want)
 
 
+@pytest.mark.parametrize("stride", [96, 120])
+def test_reference_triangle_stride(stride, golden, scene_loader, gpu):
+    """The reference's triangle_t is 96 bytes (p1, p2, p3, centroid: scenefile.h:36-41) and sits inside a 120-byte
+    scene_object_t; both strides give the frame of the packed 72-byte layout (the bytes between triangles are NaNs here)."""
+    fs, meta = case_scene("bunny_refl_d2_160", golden, scene_loader)
+    g = load_frames("bunny_refl_d2_160")
+    gpu.upload(fs, meta["width"], meta["height"], max_depth=meta["depth"], triangle_stride=stride)
+    gpu.render_tile()
+    assert np.array_equal(gpu.readback(), g["frame"])
+
+
 def test_640_golden_hashes(golden, scene_loader, gpu):
     for name in ("scene_file_cube", "scene_import", "scene_import_bunny", "pc_big"):
         gpu.upload(scene_loader(name), 640, 640)
