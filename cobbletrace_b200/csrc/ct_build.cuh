@@ -17,13 +17,14 @@ struct BuildReport {
     uint32_t bad_pos;                    // a tri_indexes entry out of range (kNoPos: none)
     uint32_t pos0;                       // leaf position of triangle 0
     uint32_t any_reflective;
+    uint32_t not_nested;                 // some child's box is not inside its parent's box
 };
 
 __global__ void __launch_bounds__(256) k_build_pairs(const ct_bvh_node *__restrict__ nodes, const uint32_t *__restrict__ pid_of, uint32_t n_nodes,
                                                      DevPair32 *__restrict__ pairs32, DevPair64 *__restrict__ pairs64,
                                                      uint32_t *__restrict__ pair_parent, uint32_t *__restrict__ tri_parent, uint32_t n_tri, BuildReport *rep) {
     double bound[3] = {0.0, 0.0, 0.0};
-    bool bad = false;
+    bool bad = false, nest_bad = false;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
         const ct_bvh_node n = nodes[i];
         for (int a = 0; a < 3; a++) {
@@ -34,6 +35,8 @@ __global__ void __launch_bounds__(256) k_build_pairs(const ct_bvh_node *__restri
         if (n.triangle_count != 0 || n.left_node == 0u || (uint64_t)n.left_node + 1u >= n_nodes) continue;      // leaf, or an unreachable slot holding zeros or garbage (the root is nobody's child)
         const uint32_t pid = pid_of[i];
         const ct_bvh_node L = nodes[n.left_node], R = nodes[n.left_node + 1u];
+        for (int a = 0; a < 3; a++)          // nesting, bit for bit (NaNs fail): what box_maybe's walks rely on
+            if (!(L.aabb_min[a] >= n.aabb_min[a] && L.aabb_max[a] <= n.aabb_max[a] && R.aabb_min[a] >= n.aabb_min[a] && R.aabb_max[a] <= n.aabb_max[a])) nest_bad = true;
         DevPair32 p32;
         DevPair64 p64;
         for (int a = 0; a < 3; a++) {
@@ -45,12 +48,13 @@ __global__ void __launch_bounds__(256) k_build_pairs(const ct_bvh_node *__restri
         p32.r_cnt = R.triangle_count; p32.r_ref = R.triangle_count ? R.first_triangle_index : pid_of[n.left_node + 1u];
         pairs32[pid] = p32;
         pairs64[pid] = p64;
-        if (pair_parent) {
-            // who holds whose box: lets k_overflow_huge check a triangle's ancestor chain without walking down
+        {
+            // who holds whose box: lets candidate_reached find a triangle's leaf box and k_overflow_huge check its ancestor
+            // chain without walking down
             for (uint32_t side = 0; side < 2u; side++) {
                 const ct_bvh_node &ch = side ? R : L;
                 const uint32_t code = 2u * pid + side;
-                if (ch.triangle_count == 0) pair_parent[pid_of[n.left_node + side]] = code;
+                if (ch.triangle_count == 0) { if (pair_parent) pair_parent[pid_of[n.left_node + side]] = code; }
                 else for (uint32_t k = 0; k < ch.triangle_count && (uint64_t)ch.first_triangle_index + k < n_tri; k++) tri_parent[ch.first_triangle_index + k] = code;
             }
         }
@@ -60,6 +64,7 @@ __global__ void __launch_bounds__(256) k_build_pairs(const ct_bvh_node *__restri
         if ((threadIdx.x & 31u) == 0 && bound[a] > 0.0) atomicMax(&rep->bound_bits[a], (unsigned long long)__double_as_longlong(bound[a]));
     }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31u) == 0) atomicOr(&rep->boxes_bad, 1u);
+    if (__any_sync(0xffffffffu, nest_bad) && (threadIdx.x & 31u) == 0) atomicOr(&rep->not_nested, 1u);
 }
 
 __global__ void __launch_bounds__(256) k_build_tris(const unsigned char *__restrict__ raw, uint32_t stride, const uint32_t *__restrict__ tri_indexes,

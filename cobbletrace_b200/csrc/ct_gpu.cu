@@ -328,7 +328,8 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     }
     TRY(dev_alloc(s, &dp64, std::max<uint32_t>(n_pairs, 1)));
     TRY(dev_alloc(s, &dt, d->n_triangles)); TRY(dev_alloc(s, &dm, d->n_triangles));
-    if (s.can_overflow) { TRY(dev_alloc(s, &dpp, std::max<uint32_t>(n_pairs, 1))); TRY(dev_alloc(s, &dtp, d->n_triangles)); }
+    TRY(dev_alloc(s, &dtp, d->n_triangles));
+    if (s.can_overflow) TRY(dev_alloc(s, &dpp, std::max<uint32_t>(n_pairs, 1)));
     BuildReport rep{};
     {
         // staging copies of the caller's arrays, freed again below
@@ -345,10 +346,8 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
         CU(staged(cudaMemcpyAsync(drep, &rep, sizeof rep, cudaMemcpyHostToDevice, s.stream)));
         CU(staged(cudaMemcpyAsync(raw_nodes, d->nodes, (size_t)d->n_nodes * sizeof(ct_bvh_node), cudaMemcpyHostToDevice, s.stream)));
         CU(staged(cudaMemcpyAsync(raw_pid, pid_of.data(), (size_t)d->n_nodes * 4, cudaMemcpyHostToDevice, s.stream)));
-        if (dpp) {
-            CU(staged(cudaMemsetAsync(dpp, 0xff, (size_t)std::max<uint32_t>(n_pairs, 1) * 4, s.stream)));
-            CU(staged(cudaMemsetAsync(dtp, 0xff, (size_t)d->n_triangles * 4, s.stream)));
-        }
+        if (dpp) CU(staged(cudaMemsetAsync(dpp, 0xff, (size_t)std::max<uint32_t>(n_pairs, 1) * 4, s.stream)));
+        CU(staged(cudaMemsetAsync(dtp, 0xff, (size_t)d->n_triangles * 4, s.stream)));
         const int build_blocks = s.n_sm * 8;
         k_build_pairs<<<build_blocks, 256, 0, s.stream>>>(raw_nodes, raw_pid, d->n_nodes, dp32, dp64, dpp, dtp, d->n_triangles, drep);
         CU(staged(cudaMemcpyAsync(raw_idx, d->tri_indexes, (size_t)d->n_triangles * 4, cudaMemcpyHostToDevice, s.stream)));
@@ -363,6 +362,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     if (rep.bad_pos != kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes[%u] = %u out of range", rep.bad_pos, d->tri_indexes[rep.bad_pos]); }
     if (rep.pos0 == kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes is not a permutation (triangle 0 missing)"); }
     p.pos_of_tri0 = rep.pos0;
+    p.nested = (!rep.not_nested && !rep.boxes_bad) ? 1u : 0u;
     s.any_reflective = rep.any_reflective != 0;
     for (int a = 0; a < 3; a++) {
         double bound;

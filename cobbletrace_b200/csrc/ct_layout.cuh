@@ -82,6 +82,7 @@ struct Params {
     double root_min[3], root_max[3];     // node 0
     float root_min32[3], root_max32[3];  // ... as floats, for the slab filter
     uint32_t root_ref, root_cnt;
+    uint32_t nested;                     // every child's box lies inside its parent's (checked at upload): box_maybe may be used
     double bound[3];                     // >= |b| for every node bound b per axis (+inf disables the filter), see ray_finish
     const DevTri *tris;
     const DevTri32 *tris32;

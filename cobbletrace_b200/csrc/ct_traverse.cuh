@@ -116,6 +116,41 @@ CT_DEV void pair_accept(const Params &P, const TRay &r, uint32_t pid, const DevP
     }
 }
 
+// The early-exit walks on a NESTED tree (every child's box inside its parent's box, bit for bit -- what UpdateNodeBounds,
+// bvh.cpp:30-49, produces: a node's box is the min / max over its own triangles' vertices, and a child's triangles are a
+// subset of its parent's; checked at upload) only need a CONSERVATIVE box test.  With ray.t fixed (1e30f or 0 until the
+// walk ends) and no NaN among the slab quotients (r.filt: no zero direction component), the reference's floats are
+// monotone in the box:  q(b) = float(fl64(fl64(b - o) / d))  is a monotone function of the bound b, so per axis the
+// parent's near quotient <= the child's and its far quotient >= the child's, hence
+//     tmin(parent) <= tmin(child)   and   tmax(parent) >= tmax(child)
+// and IntersectAABB's verdict (tmax >= tmin && tmin < ray.t && tmax > 0, bvh.cpp:178) for a child implies the same verdict
+// for its parent, grand-parent, ... up to the root.  "The reference's walk reaches this leaf" is therefore equivalent to
+// "the leaf's OWN box passes IntersectAABB", whatever happened on the way down.  So the walk may accept any superset of
+// the boxes the reference accepts -- it only has to find the candidate leaves; a triangle that passes the exact test
+// counts if its leaf's box passes the exact slab test (candidate_reached, one fp64 box test per candidate instead of
+// exact verdicts for every box of the walk).  pair_maybe is that superset test: the lower end of the near bracket and
+// the upper end of the far bracket of box_filter, i.e. half its FMAs, no undecided case, no fp64 fallback, no branch.
+template <bool T_FAR>
+CT_DEV bool box_maybe(const TRay &r, const float bmin[3], const float bmax[3]) {
+    float nl[3], fh[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const bool pos = r.rdf[k] > 0.0f;
+        nl[k] = __fmaf_rd(pos ? bmin[k] : bmax[k], r.rdf[k], r.cl[k]);       // <= the reference's near quotient on this axis
+        fh[k] = __fmaf_ru(pos ? bmax[k] : bmin[k], r.rdf[k], r.cu[k]);       // >= its far quotient
+    }
+    const float near_lo = fmaxf(fmaxf(nl[0], nl[1]), nl[2]), far_hi = fminf(fminf(fh[0], fh[1]), fh[2]);
+    const bool no = T_FAR ? ((far_hi < near_lo) | (far_hi <= 0.0f)) : ((far_hi < near_lo) | (far_hi <= 0.0f) | (near_lo >= r.t));
+    return !no;                                                              // false only when the reference certainly rejects
+}
+
+// Does the reference's walk reach the leaf that holds the triangle at `pos`?  (nested tree, r.filt: see above)
+CT_DEV bool candidate_reached(const Params &P, const TRay &r, uint32_t pos) {
+    const uint32_t code = __ldg(P.tri_parent + pos);                         // 2 * pair + side of the leaf's box
+    if (code == kNoPos) return exact_root(P, r.r64, r.t);                    // the root itself is the leaf
+    return box_accept(exact_child(P.pairs64, code >> 1, code & 1u, r.r64), r.t);
+}
+
 enum TraverseMode { kClosest, kAnyHit, kFirstLine };
 enum { kTravMiss = 0, kTravHit = 1, kTravOverBudget = -1 };
 
@@ -242,6 +277,7 @@ CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uin
     int result = MODE == kFirstLine ? kTravHit : kTravMiss;
     tclosest = kFinf;          // raythread.cpp:204
     closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
+    const bool cons = r.filt & (P.nested != 0u);      // conservative box tests + verified candidates (see box_maybe)
     if (active) {
         if (COUNT) lc.box++;
         state = root_accept(P, r) ? 1 : 0;
@@ -263,8 +299,14 @@ CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uin
                     load_pair32(P.pairs32, cur_ref, pr);
                     if (COUNT) lc.box += 2;
                     spent += 2u;
-                    bool hit_l, hit_r; float r_lo, r_hi;
-                    pair_accept<COUNT, MODE == kAnyHit>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
+                    bool hit_l, hit_r;
+                    if (cons) {
+                        hit_l = box_maybe<MODE == kAnyHit>(r, pr.lmin, pr.lmax);
+                        hit_r = box_maybe<MODE == kAnyHit>(r, pr.rmin, pr.rmax);
+                    } else {
+                        float r_lo, r_hi;
+                        pair_accept<COUNT, MODE == kAnyHit>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
+                    }
                     if (hit_l & hit_r) { CT_CHECK(sp < kStackMax); stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt; sp++; }
                     descend = hit_l | hit_r;
                     cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
@@ -284,7 +326,8 @@ CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uin
                 const uint32_t pos = leaf_ref[li] + tri;
                 if (COUNT) lc.tri++;
                 const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
-                const bool done = MODE == kAnyHit ? (th.hit & (th.t > kEps) & (th.t < kRayTInit)) : th.hit;
+                bool done = MODE == kAnyHit ? (th.hit & (th.t > kEps) & (th.t < kRayTInit)) : th.hit;
+                if (done & cons) done = candidate_reached(P, r, pos);     // the walk's box tests were only conservative
                 if (done) {
                     if (MODE == kAnyHit) result = kTravHit;
                     else { closest_pos = pos; tclosest = 0.0f; }
