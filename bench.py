@@ -66,6 +66,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def workload_config(key: str, n_gpus: int, n_tri: int, n_nodes: int, n_lights: int) -> dict:
+    """`config` of the JSON line: what was rendered.  The same function serves both arms, so that the two lines name the
+    workload identically (how each arm ran it is in `method` / `cpu_baseline.sample`, not here)."""
+    desc, kind, W, H, depth, refl = WORKLOADS[key][:6]
+    return {"workload": desc, "scene": kind, "width": W, "height": H, "triangles": int(n_tri), "bvh_nodes": int(n_nodes), "lights": int(n_lights),
+            "max_depth": depth, "forced_reflection": refl, "n_gpus": int(n_gpus),
+            "l2": "b200 arm: flushed between timed steps (256 MiB device write, outside the timed events); reference arm: host CPU, not applicable"}
+
+
+def expected_frame(key: str):
+    """(fnv1a, source) of the workload's frame as the compiled, unmodified reference rendered it (tests/golden/bench_frames.json,
+    made by tests/golden/make_golden_bench.py), or (None, None)."""
+    try:
+        e = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_frames.json")))[key]
+        return e["fnv1a"], e["source"]
+    except Exception:
+        return None, None
+
+
 def scene_cache_dir() -> str:
     d = os.environ.get("CT_SCENE_CACHE") or os.path.join("/tmp", f"ct_bench_scene_{os.getuid()}")
     os.makedirs(d, exist_ok=True)
@@ -176,8 +195,10 @@ def oracle_counts(fs, W, H, depth):
     """Reference-DFS ray and test counts for the frame (restatement; counters proven equal to oracle/_ref's in tests)."""
     from oracle import ct_oracle_py as O
     t0 = time.time()
-    _, _, ctr = O.OracleScene(fs).render(W, H, max_depth=depth, want_hits=False, by_kind=True)
+    frame, _, ctr = O.OracleScene(fs).render(W, H, max_depth=depth, want_hits=False, by_kind=True)
     ctr["oracle_seconds"] = time.time() - t0
+    from cobbletrace_b200.sceneio import frame_fnv1a
+    ctr["frame_fnv1a"] = frame_fnv1a(frame)
     return ctr
 
 
@@ -230,19 +251,29 @@ def cpu_baseline(workload, fs, counts_full, budget_s=25.0):
             "sample": f"{W // 2}x{H // 2} frame (1/4 of the pixels), oracle/ct_oracle.c with {cores} pthreads"}
 
 
+def ref_counters(scene_json, chdir, W, H, depth, refl, threads, timeout=3000):
+    """Ray / test counters of one frame from the compiled reference itself (oracle/_ref/ct_ref_count --counters)."""
+    from oracle import ct_oracle_py as O
+    cmd = [os.path.join(O.REF_DIR, "ct_ref_count"), "--scene", scene_json, "--chdir", chdir, "--width", str(W), "--height", str(H), "--depth", str(depth),
+           "--threads", str(threads), "--counters"]
+    if refl is not None:
+        cmd += ["--force-reflection", repr(float(refl))]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=timeout).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
 def reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores.  Nothing of the
+    product is loaded here: the scene file comes from the (pure Python) generator / the reference's own scene files, the
+    frame times from oracle/_ref/ct_ref and the ray counts from oracle/_ref/ct_ref_count."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return 0
-    from cobbletrace_b200 import host
     from oracle import ct_oracle_py as O
     workload = WORKLOADS[args.workload]
     desc, kind, W, H, depth, refl = workload[:6]
     scene_path, n_tri = ensure_scene(kind)
     cores = host_cores()
-    hs, _ = load_host_scene(kind, refl)
-    fs = hs.to_flat(with_bvh=True)
     steps, warm = args.steps, args.warmup
     if O.ref_available():
         w, h = W // 4, H // 4
@@ -255,10 +286,16 @@ def reference_arm(args):
         thr = ref_threads(h, cores)
         r = run_ref_cpu(os.path.basename(scene_path), scene_dir(kind), w, h, depth, refl, thr, steps, warm)
         ms = r["mean_ms"]
+        c = ref_counters(os.path.basename(scene_path), scene_dir(kind), w, h, depth, refl, thr)
+        n_nodes, n_lights = r["nodes"], r["lights"]
         kind_s, used = "reference", thr
         sample = (f"each step = one {w}x{h} frame ({'the full workload' if scale == 1 else f'1/{scale * scale} of the pixels'}) through the reference's "
-                  f"boss/worker (AllocatePartitions/HandleUpdates/RayTracePartition), numberOfThreads={thr} of {cores} cores")
+                  f"boss/worker (AllocatePartitions/HandleUpdates/RayTracePartition), numberOfThreads={thr} of {cores} cores; "
+                  "ray counts from the reference's own counters (ct_ref_count --counters)")
     else:
+        # no compiled reference on this box: the plain-C restatement (needs the product's parser for the scene arrays)
+        hs, _ = load_host_scene(kind, refl)
+        fs = hs.to_flat(with_bvh=True)
         scale, w, h = 2, W // 2, H // 2
         osc = O.OracleScene(fs)
         for _ in range(warm):
@@ -267,16 +304,18 @@ def reference_arm(args):
         for _ in range(steps):
             osc.render(w, h, max_depth=depth, want_hits=False, n_threads=cores)
         ms = (time.time() - t0) / steps * 1e3
+        c = oracle_counts(fs, w, h, depth)
+        n_nodes, n_lights = fs.n_nodes, fs.n_lights
         kind_s, used = "port", cores
         sample = f"each step = one {w}x{h} frame (1/4 of the pixels) through oracle/ct_oracle.c with {cores} pthreads"
-    c = oracle_counts(fs, w, h, depth)
     rays = c["rays_primary"] + c["rays_shadow"] + c["rays_reflection"]
     value = rays / ms / 1e3
     line = {
         "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64/f32 mixed (reference arithmetic)",
         "data": data_note(kind),
-        "config": {"workload": desc, "sample": sample, "triangles": n_tri},
+        "config": workload_config(args.workload, args.gpus, n_tri, n_nodes, n_lights),
+        "sample": sample,
         "rays_per_step": {k: c[k] for k in ("rays_primary", "rays_shadow", "rays_reflection")},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": used, "kind": kind_s, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -437,9 +476,8 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64/f32 mixed (the reference's arithmetic, reproduced bit-exactly)",
         "data": data_note(kind),
-        "config": {"workload": desc, "triangles": n_tri, "bvh_nodes": n_nodes, "lights": int(hs.to_flat(with_bvh=False).n_lights), "max_depth": depth, "forced_reflection": refl,
-                   "l2": "flushed between timed steps (256 MiB device write, outside the timed events)",
-                   "timing": "CUDA events on the launching stream around each frame's kernels" + ("; max over ranks per step (pixels land in GPU 0's framebuffer inside those kernels)" if N > 1 else ""),
+        "config": workload_config(args.workload, N, n_tri, n_nodes, int(flat0.n_lights)),
+        "method": {"timing": "CUDA events on the launching stream around each frame's kernels" + ("; max over ranks per step (pixels land in GPU 0's framebuffer inside those kernels)" if N > 1 else ""),
                    "tiles_per_frame": st["tiles_total"],
                    "parallelism": (f"{N} GPUs, one process each, scene replicated: 32-pixel chunks, 7/8 dealt round-robin and 1/8 stolen from one cursor on GPU 0 (atomics over NVLink), "
                                    "finished pixels stored straight into GPU 0's framebuffer (peer stores, CUDA IPC); no collective" if N > 1
@@ -459,6 +497,15 @@ def main():
         "one_time_ms": {"scene_parse": load_ms, "bvh_build": bvh_ms, "upload_and_alloc": upload_ms},
     }
 
+    # ---- the pixels: the bitmap of the last end-to-end frame (read back from GPU 0, every rank's share in it) against the
+    # frame the compiled, unmodified reference rendered for this workload (committed hash) -- at every N
+    from cobbletrace_b200.sceneio import frame_fnv1a
+    got_hash = frame_fnv1a(bitmap)
+    want_hash, want_src = expected_frame(args.workload)
+    line["frame_fnv1a"] = got_hash
+    line["frame_check"] = {"reference_fnv1a": want_hash, "reference_source": want_src, "matches_reference": (got_hash == want_hash) if want_hash else None}
+    frame_ok = (got_hash == want_hash) if want_hash else True
+
     # ---- roofline of the dominant kernel + CPU baseline (rank 0; only meaningful at N = 1)
     if N == 1 and wflags:
         boss.close()
@@ -467,6 +514,9 @@ def main():
         boss.close()
         fs = hs.to_flat(with_bvh=True)
         counts = oracle_counts(fs, W, H, depth)
+        line["frame_check"]["oracle_fnv1a"] = counts["frame_fnv1a"]       # the live oracle render of the same inputs
+        line["frame_check"]["matches_oracle"] = got_hash == counts["frame_fnv1a"]
+        frame_ok = frame_ok and got_hash == counts["frame_fnv1a"]
         prof = api.GpuRenderer(dev).upload(fs, W, H, max_depth=depth, flags=api.CT_FLAG_STAGE_TIMING)
         per = {}
         for i in range(3 + 5):
@@ -523,9 +573,13 @@ def main():
             line["cpu_baseline"] = cpu_baseline(workload, fs, counts)
     else:
         shared.close(); gpu.shutdown()
+    line["frame_matches_oracle"] = bool(frame_ok) if (want_hash or "matches_oracle" in line["frame_check"]) else None
     print(json.dumps(line), file=real_stdout, flush=True)
     if N > 1:
         dist.barrier(); dist.destroy_process_group()
+    if not frame_ok:
+        log(f"FRAME MISMATCH: read back {got_hash}, expected {line['frame_check']}")
+        return 3
     return 0
 
 

@@ -542,6 +542,11 @@ def test_dragon_class_full_size(tmp_path_factory, W, H, gpu):
     # property 1: oracle agreement at full size (bit-exact)
     oframe, ohits, octr = O.OracleScene(fs).render(W, H, max_depth=2, n_threads=os.cpu_count() or 8)
     assert_same(gpu, oframe, ohits, f"dragon stand-in {W}x{H}")
+    # ... and the frame the compiled, unmodified reference rendered from the same scene file (tests/golden/make_golden_bench.py)
+    import json
+    pins = json.load(open(os.path.join(GOLD, "bench_frames.json")))
+    pin = pins["dragon4k" if W == 3840 else "dragon8k"]
+    assert (pin["width"], pin["height"], pin["triangles"]) == (W, H, n) and ct.frame_fnv1a(full) == pin["fnv1a"]
     # property 2: tile-split invariance (what multi-GPU row tiles rely on)
     gpu.upload(fs, W, H, max_depth=2)
     y0, y1 = gpu.full_range()
