@@ -313,6 +313,49 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     p.n_nodes = d->n_nodes;
     s.can_overflow = (uint64_t)d->n_nodes + d->n_triangles > p.budget;      // parked rays: only when a DFS can run past the budget at all
     lap("interior-node numbering (host)");
+    // the early-exit walks' wide tree: kWideLevels levels of the reference's tree per node, children in DFS order
+    std::vector<DevWide> wide;
+    if (d->nodes[0].triangle_count == 0) {
+        std::vector<uint32_t> root_of;                  // wide node -> the interior node whose descendants it holds
+        std::vector<uint32_t> wid_of(d->n_nodes, kNoPos);
+        root_of.reserve(n_pairs / 2 + 1);
+        root_of.push_back(0u); wid_of[0] = 0u;
+        wide.reserve(n_pairs / 2 + 1);
+        for (size_t w = 0; w < root_of.size(); w++) {
+            uint32_t cur[kWide], nxt[kWide];
+            int n_cur = 2;
+            cur[0] = d->nodes[root_of[w]].left_node; cur[1] = cur[0] + 1u;
+            for (int lvl = 1; lvl < kWideLevels; lvl++) {
+                int n_nxt = 0;
+                for (int i = 0; i < n_cur; i++) {
+                    const ct_bvh_node &c = d->nodes[cur[i]];
+                    if (c.triangle_count != 0) nxt[n_nxt++] = cur[i];
+                    else { nxt[n_nxt++] = c.left_node; nxt[n_nxt++] = c.left_node + 1u; }
+                }
+                n_cur = n_nxt;
+                memcpy(cur, nxt, sizeof cur);
+            }
+            DevWide rec;
+            for (int i = 0; i < kWide; i++) {
+                DevWideChild &e = rec.c[i];
+                if (i >= n_cur) {
+                    for (int a = 0; a < 3; a++) { e.bmin[a] = 1e30f; e.bmax[a] = -1e30f; }
+                    e.ref = kNoPos; e.cnt = 0u;
+                    continue;
+                }
+                const ct_bvh_node &c = d->nodes[cur[i]];
+                for (int a = 0; a < 3; a++) { e.bmin[a] = (float)c.aabb_min[a]; e.bmax[a] = (float)c.aabb_max[a]; }
+                e.cnt = c.triangle_count;
+                if (c.triangle_count != 0) e.ref = c.first_triangle_index;
+                else {
+                    if (wid_of[cur[i]] == kNoPos) { wid_of[cur[i]] = (uint32_t)root_of.size(); root_of.push_back(cur[i]); }
+                    e.ref = wid_of[cur[i]];
+                }
+            }
+            wide.push_back(rec);
+        }
+    }
+    lap("wide tree (host)");
 
     DevPair32 *dp32 = nullptr; DevPair64 *dp64 = nullptr; DevTri *dt = nullptr; DevTri32 *dt32 = nullptr; ct_material *dm = nullptr;
     uint32_t *dpp = nullptr, *dtp = nullptr;
@@ -320,11 +363,17 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
         // the records every walk step reads -- fp32 child pairs and fp32 triangles -- share ONE allocation, so that a single
         // L2 access-policy window can cover them (apply_l2_policy)
         const size_t pair_bytes = ((size_t)std::max<uint32_t>(n_pairs, 1) * sizeof(DevPair32) + 255u) & ~(size_t)255u;
+        const size_t wide_bytes = (wide.size() * sizeof(DevWide) + 255u) & ~(size_t)255u;
         unsigned char *hot = nullptr;
-        s.hot_bytes = pair_bytes + (size_t)d->n_triangles * sizeof(DevTri32);
+        s.hot_bytes = wide_bytes + pair_bytes + (size_t)d->n_triangles * sizeof(DevTri32);
         TRY(dev_alloc(s, &hot, s.hot_bytes));
         s.hot_base = hot;
-        dp32 = reinterpret_cast<DevPair32 *>(hot); dt32 = reinterpret_cast<DevTri32 *>(hot + pair_bytes);
+        if (!wide.empty()) {
+            CU(cudaMemcpyAsync(hot, wide.data(), wide.size() * sizeof(DevWide), cudaMemcpyHostToDevice, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+            p.wide = reinterpret_cast<const DevWide *>(hot);
+        }
+        dp32 = reinterpret_cast<DevPair32 *>(hot + wide_bytes); dt32 = reinterpret_cast<DevTri32 *>(hot + wide_bytes + pair_bytes);
     }
     TRY(dev_alloc(s, &dp64, std::max<uint32_t>(n_pairs, 1)));
     TRY(dev_alloc(s, &dt, d->n_triangles)); TRY(dev_alloc(s, &dm, d->n_triangles));

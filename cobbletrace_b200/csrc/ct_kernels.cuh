@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
         uint32_t budget = P.budget;
         while (true) {                                                  // warp-uniform: traverse_early is warp-synchronous
             float stc; uint32_t spos;
-            int res = traverse_early<kAnyHit, COUNT>(P, tr, active, budget, stc, spos, lc);
+            int res = traverse_early_any<kAnyHit, COUNT>(P, tr, active, budget, stc, spos, lc);
             bool again = false;
             if (active) {
                 if (res == kTravOverBudget) {
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
         uint32_t budget = P.budget;
         while (true) {                                                  // warp-uniform: traverse is warp-synchronous
             float tc; uint32_t pos;
-            int res = traverse_early<kFirstLine, COUNT>(P, r, active, budget, tc, pos, lc);
+            int res = traverse_early_any<kFirstLine, COUNT>(P, r, active, budget, tc, pos, lc);
             bool again = false;
             if (active) {
                 if (res == kTravOverBudget) {
@@ -691,7 +691,7 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
     }
     LocalCount lc; float tc, tc2; uint32_t pos, pos2;
     const bool first_line = r.t == 0.0f;
-    bool f = traverse_early<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc) == kTravHit;
+    bool f = traverse_early_any<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc) == kTravHit;
     bool f2 = traverse_closest<false>(P, tr, active && !first_line, tc2, pos2, lc) == kTravHit;
     if (!active) return;
     if (!first_line) { f = f2; tc = tc2; pos = pos2; }

@@ -51,6 +51,19 @@ struct __align__(16) DevTri32 {      // 48 B, same order: what the certified fp3
     float e1[3], k1;                 // k1 = max|e1_i| rounded up (NaN: magnitudes outside the filter's range)
     float e2[3], k2;
 };
+// The early-exit walks' own tree: the reference's binary tree with kWideLevels levels collapsed into one node of up to
+// kWide children (box_maybe / candidate_reached in ct_traverse.cuh explain why these walks may skip the boxes in between).
+// A child is 32 bytes, two 16-byte loads: its box as floats (round to nearest, the same values pairs32 holds) and
+// (ref, cnt): cnt > 0 -> leaf holding triangles [ref, ref + cnt); cnt == 0 -> ref = its own wide node.  Children keep the
+// reference's DFS order; unused children hold an inverted box (never accepted) and ref = kNoPos.
+#ifndef CT_WIDE_LEVELS
+#define CT_WIDE_LEVELS 2
+#endif
+constexpr int kWideLevels = CT_WIDE_LEVELS;
+constexpr int kWide = 1 << kWideLevels;
+struct __align__(16) DevWideChild { float bmin[3], bmax[3]; uint32_t ref, cnt; };
+struct __align__(16) DevWide { DevWideChild c[kWide]; };
+
 struct DevLight { int32_t type; float intensity; double pos[3]; double dir[3]; };
 struct DevShadowLight { int32_t type; uint32_t index; double v[3]; };   // non-ambient lights, file order; index = light number
 struct __align__(16) OvfRay {        // a parked ray: 64 B
@@ -79,6 +92,7 @@ struct DevTotals {                   // running ray / test counters (never reset
 struct Params {
     const DevPair32 *pairs32;
     const DevPair64 *pairs64;
+    const DevWide *wide;                 // node 0 = the root's children (nullptr: the root is a leaf)
     double root_min[3], root_max[3];     // node 0
     float root_min32[3], root_max32[3];  // ... as floats, for the slab filter
     uint32_t root_ref, root_cnt;

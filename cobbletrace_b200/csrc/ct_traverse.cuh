@@ -341,4 +341,111 @@ CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uin
     return result;
 }
 
+// The early-exit walks over the WIDE tree (DevWide, ct_layout.cuh), for rays whose box tests may be conservative
+// (`cons` above: nested tree, no NaN among the slab quotients): every visit tests the kWide descendants kWideLevels
+// levels down with box_maybe and skips the boxes in between -- a child's verdict implies its ancestors' -- so a ray
+// descends the tree in 1 / kWideLevels of the dependent fetches and pays the loop's bookkeeping once per kWide boxes.
+// Accepted children are pushed in reverse order and popped: the visit order is the reference's DFS order, deferred
+// leaves reach the list in DFS order, and kFirstLine's "first pass of a leaf phase" is the lowest leaf position as in
+// traverse_early (kAnyHit appends accepted leaves to the list at once; its answer does not depend on the order).
+// A triangle that passes the exact test counts only if the reference's walk reaches its leaf (candidate_reached).
+// WARP-SYNCHRONOUS, same contract as traverse_early; a stack that would overflow ends the walk as kTravOverBudget (the
+// ray is parked and finished on the binary tree).
+constexpr int kWideStack = 64;                 // pending children per lane: (kWide - 1) per level of the wide tree
+constexpr int kWideLeaves = 2 * kWide + 8;     // deferred leaves per lane; a visit may add kWide
+template <TraverseMode MODE, bool COUNT>
+CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    static_assert(MODE != kClosest, "closest-hit rays use traverse_closest");
+    uint2 stk[kWideStack];                                // pushed children (ref, cnt)
+    uint2 leaf[kWideLeaves];                              // deferred leaves (ref, cnt), DFS order
+    int sp = 0, nleaf = 0;
+    uint32_t spent = 1u;
+    uint32_t cur_ref = 0u, cur_cnt = P.root_cnt;          // wide node 0 = the root's descendants; a leaf root has no wide tree
+    if (P.root_cnt > 0u) cur_ref = P.root_ref;
+    int state = 0;                                        // 1: nodes left to walk (cur_* pending); 0: walk finished
+    int result = MODE == kFirstLine ? kTravHit : kTravMiss;
+    tclosest = kFinf;          // raythread.cpp:204
+    closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
+    if (active) {
+        if (COUNT) lc.box++;
+        state = root_accept(P, r) ? 1 : 0;
+    } else {
+        result = kTravMiss;
+    }
+    while (true) {
+        // ---- walk phase: one wide-node visit per walking lane and iteration; leaves go to the list
+        while (__any_sync(kFullMask, (state == 1) & (nleaf <= kWideLeaves - kWide))) {
+            if ((state == 1) & (nleaf <= kWideLeaves - kWide)) {
+                if (cur_cnt > 0u) {                       // a leaf that came off the stack (or a leaf root)
+                    leaf[nleaf] = make_uint2(cur_ref, cur_cnt); nleaf++;
+                    spent += cur_cnt;
+                } else {
+                    const float4 *q = reinterpret_cast<const float4 *>(P.wide + cur_ref);
+                    if (COUNT) lc.box += kWide;
+                    spent += (uint32_t)kWide;
+                    if (sp > kWideStack - kWide) { result = kTravOverBudget; state = 0; nleaf = 0; sp = 0; }
+                    else {
+#pragma unroll
+                        for (int e = kWide - 1; e >= 0; e--) {             // reverse: the first accepted child is popped first
+                            const float4 a = __ldg(q + 2 * e);
+                            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(q + 2 * e + 1));
+                            const float bmin[3] = {a.x, a.y, a.z}, bmax[3] = {a.w, __uint_as_float(b.x), __uint_as_float(b.y)};
+                            const bool hit = box_maybe<MODE == kAnyHit>(r, bmin, bmax);
+                            if (MODE == kAnyHit) {
+                                const bool is_leaf = b.w > 0u;
+                                if (hit & is_leaf) { leaf[nleaf] = make_uint2(b.z, b.w); nleaf++; spent += b.w; }
+                                if (hit & !is_leaf) { stk[sp] = make_uint2(b.z, 0u); sp++; }
+                            } else {
+                                if (hit) { stk[sp] = make_uint2(b.z, b.w); sp++; }
+                            }
+                        }
+                    }
+                }
+                if (state == 1) {
+                    if (sp == 0) state = 0;
+                    else { --sp; const uint2 t = stk[sp]; cur_ref = t.x; cur_cnt = t.y; }
+                }
+                if (spent > budget) { result = kTravOverBudget; state = 0; nleaf = 0; }
+            }
+        }
+        // ---- leaf phase: one triangle per lane and iteration, oldest leaf first
+        int li = 0;
+        uint32_t tri = 0;                                 // next triangle inside leaf li
+        while (__any_sync(kFullMask, li < nleaf)) {
+            if (li < nleaf) {
+                const uint2 lf = leaf[li];
+                const uint32_t pos = lf.x + tri;
+                if (COUNT) lc.tri++;
+                const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
+                bool done = MODE == kAnyHit ? (th.hit & (th.t > kEps) & (th.t < kRayTInit)) : th.hit;
+                if (done) done = candidate_reached(P, r, pos);        // the walk's box tests were only conservative
+                if (done) {
+                    if (MODE == kAnyHit) result = kTravHit;
+                    else { closest_pos = pos; tclosest = 0.0f; }
+                    state = 0; nleaf = 0;
+                } else if (++tri == lf.y) { tri = 0; li++; }
+            }
+        }
+        nleaf = 0;
+        if (!__any_sync(kFullMask, state == 1)) break;
+    }
+    return result;
+}
+
+// An early-exit walk for every lane's ray: over the wide tree where the ray allows conservative box tests, with the
+// reference's exact verdicts at every box of the binary tree otherwise (zero direction components, non-nested trees).
+template <TraverseMode MODE, bool COUNT>
+CT_DEV int traverse_early_any(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    const bool cons = r.filt & (P.nested != 0u) & (P.wide != nullptr);
+    int res = traverse_wide<MODE, COUNT>(P, r, active & cons, budget, tclosest, closest_pos, lc);
+    // the binary walk for the other rays, and for rays that may not be parked (no budget) whose wide stack overflowed
+    const bool binary = active & (!cons | ((res == kTravOverBudget) & (budget == 0xffffffffu)));
+    if (__any_sync(kFullMask, binary)) {
+        float tc2; uint32_t pos2;
+        const int res2 = traverse_early<MODE, COUNT>(P, r, binary, budget, tc2, pos2, lc);
+        if (binary) { res = res2; tclosest = tc2; closest_pos = pos2; }
+    }
+    return res;
+}
+
 }  // namespace
