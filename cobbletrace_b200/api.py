@@ -50,7 +50,7 @@ class Light(C.Structure):        # == ct_light == reference light_t (scenefile.h
 
 class Share(C.Structure):        # == ct_gpu_share
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("pid", C.c_int64), ("fb_ptr", C.c_uint64), ("cursor_ptr", C.c_uint64),
-                ("fb_ipc", C.c_ubyte * 64), ("cursor_ipc", C.c_ubyte * 64), ("width", C.c_int32), ("height", C.c_int32)]
+                ("fb_ipc", C.c_ubyte * 64), ("cursor_ipc", C.c_ubyte * 64), ("width", C.c_int32), ("height", C.c_int32), ("frames", C.c_uint64)]
 
 
 class SceneDesc(C.Structure):    # == ct_scene_desc

@@ -11,6 +11,7 @@ namespace {
 // two kernels turn them into the layout above -- a gather through the permutation plus conversions is bandwidth work
 // the host does an order of magnitude slower (868k triangles: 130 ms on 16 host threads, < 1 ms here).  Every value is
 // produced by the same IEEE operations as before (fp64 subtractions, round-to-nearest / round-up conversions).
+constexpr uint32_t kLeafMark = 0xfffffffeu;       // pid_of[] of a reachable leaf
 struct BuildReport {
     unsigned long long bound_bits[3];    // max |bound| over all nodes, per axis (bit pattern of a non-negative double)
     uint32_t boxes_bad;                  // some box is unordered or not finite
@@ -18,6 +19,7 @@ struct BuildReport {
     uint32_t pos0;                       // leaf position of triangle 0
     uint32_t any_reflective;
     uint32_t not_nested;                 // some child's box is not inside its parent's box
+    uint32_t duplicate;                  // a tri_indexes value occurs twice (with every value in range: not a permutation)
 };
 
 __global__ void __launch_bounds__(256) k_build_pairs(const ct_bvh_node *__restrict__ nodes, const uint32_t *__restrict__ pid_of, uint32_t n_nodes,
@@ -27,13 +29,14 @@ __global__ void __launch_bounds__(256) k_build_pairs(const ct_bvh_node *__restri
     bool bad = false, nest_bad = false;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
         const ct_bvh_node n = nodes[i];
+        const uint32_t pid = pid_of[i];      // interior: its pair; kLeafMark: a leaf; kNoPos: a slot the tree does not reach (may hold anything)
+        if (pid == kNoPos) continue;
         for (int a = 0; a < 3; a++) {
             // the filter needs finite, ordered boxes (box_filter picks near/far by the ray's sign)
             if (!(n.aabb_min[a] <= n.aabb_max[a]) || isinf(n.aabb_min[a]) || isinf(n.aabb_max[a])) bad = true;
             else bound[a] = fmax(bound[a], fmax(fabs(n.aabb_min[a]), fabs(n.aabb_max[a])));
         }
-        if (n.triangle_count != 0 || n.left_node == 0u || (uint64_t)n.left_node + 1u >= n_nodes) continue;      // leaf, or an unreachable slot holding zeros or garbage (the root is nobody's child)
-        const uint32_t pid = pid_of[i];
+        if (n.triangle_count != 0) continue;
         const ct_bvh_node L = nodes[n.left_node], R = nodes[n.left_node + 1u];
         for (int a = 0; a < 3; a++)          // nesting, bit for bit (NaNs fail): what box_maybe's walks rely on
             if (!(L.aabb_min[a] >= n.aabb_min[a] && L.aabb_max[a] <= n.aabb_max[a] && R.aabb_min[a] >= n.aabb_min[a] && R.aabb_max[a] <= n.aabb_max[a])) nest_bad = true;
@@ -69,13 +72,14 @@ __global__ void __launch_bounds__(256) k_build_pairs(const ct_bvh_node *__restri
 
 __global__ void __launch_bounds__(256) k_build_tris(const unsigned char *__restrict__ raw, uint32_t stride, const uint32_t *__restrict__ tri_indexes,
                                                     const ct_material *__restrict__ materials, uint32_t n_tri,
-                                                    DevTri *__restrict__ tris, DevTri32 *__restrict__ tris32, BuildReport *rep) {
+                                                    DevTri *__restrict__ tris, DevTri32 *__restrict__ tris32, uint32_t *__restrict__ seen, BuildReport *rep) {
     bool refl = false;
     auto dmax = [](double a, double b) { return (a < b) ? b : a; };      // std::max: a NaN component is skipped
     for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n_tri; pos += gridDim.x * blockDim.x) {
         const uint32_t k = tri_indexes[pos];
         if (k >= n_tri) { atomicMin(&rep->bad_pos, pos); continue; }
-        if (k == 0) rep->pos0 = pos;                     // a permutation holds it once (checked by the host afterwards)
+        if (atomicOr(&seen[k >> 5], 1u << (k & 31u)) & (1u << (k & 31u))) { rep->duplicate = 1u; continue; }   // n values in range, none twice: a permutation
+        if (k == 0) rep->pos0 = pos;
         const double *v = reinterpret_cast<const double *>(raw + (size_t)k * stride);
         DevTri t;
         DevTri32 t32;

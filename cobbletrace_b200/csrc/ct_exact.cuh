@@ -313,6 +313,32 @@ CT_DEV V3 reflect_ray(V3 rv, V3 n) {
     return vsub(vscale(d, vscale(2.0, n)), rv);
 }
 
+// pow(x, n) for ComputeLighting's specular term (raythread.cpp:321: pow(float, int) resolves to the double pow of glibc,
+// whose result is the correctly rounded x^n except within ~2^-15 ulp of a rounding boundary -- its error bound is
+// 0.52 ulp).  CUDA's pow() is documented at up to 2 ulp, so it is not used: for the integer exponents scene files hold
+// (material_t.specular is an int) x^n is computed by square-and-multiply in double-double arithmetic (error < 2^-95
+// relative for n <= 2^20) and rounded once, i.e. the correctly rounded value, which is what glibc returns in all but
+// astronomically rare cases; the double then enters a float accumulator, which discards its last 29 bits anyway.
+// Arguments outside the analysed range (x <= 0, huge or negative n, results near the subnormal range) use pow().
+struct DD { double hi, lo; };
+CT_DEV DD dd_mul(DD a, DD b) {
+    const double p = __dmul_rn(a.hi, b.hi);
+    const double e = __fma_rn(a.hi, b.hi, -p);                                   // exact error of the product
+    const double c = __dadd_rn(e, __dadd_rn(__dmul_rn(a.hi, b.lo), __dmul_rn(a.lo, b.hi)));
+    const double hi = __dadd_rn(p, c);
+    return {hi, __dadd_rn(__dsub_rn(p, hi), c)};                                 // fast two-sum: |p| >= |c|
+}
+CT_DEV double pow_int(double x, int n) {
+    if (!(x > 0x1p-1000) || !(x < 0x1p1000) || n < 0 || n > (1 << 20)) return pow(x, (double)n);
+    DD r = {1.0, 0.0}, b = {x, 0.0};
+    for (uint32_t k = (uint32_t)n; k; k >>= 1) {
+        if (k & 1u) r = dd_mul(r, b);
+        if (k > 1u) b = dd_mul(b, b);
+        if (!(fabs(b.hi) > 0x1p-900) || !(fabs(b.hi) < 0x1p900) || !(fabs(r.hi) > 0x1p-900)) return pow(x, (double)n);   // leaves the range in which the error terms are normal numbers
+    }
+    return __dadd_rn(r.hi, r.lo);
+}
+
 // ---- color.h ------------------------------------------------------------------------------------
 CT_DEV uint32_t to_u8(float x) { return (uint32_t)__float2int_rz(x) & 0xffu; }   // float -> uint8_t argument conversion
 

@@ -94,7 +94,9 @@ struct DeviceState {
     cudaEvent_t ev_hit[16] = {}, ev_done[16] = {};
     // multi-GPU frame sharing (ct_gpu_share_*): the cursor and framebuffer a shared render uses (own or the root's)
     unsigned long long *cursor_own = nullptr, *share_cursor = nullptr;
+    unsigned long long shared_frames = 0;    // shared renders so far: frame f uses cursor f & 1 (the root zeroes the other one meanwhile)
     int part_index = 0, part_count = 0;      // ct_gpu_share_partition
+    bool remote_cursor_ok = true;            // atomics on the attached root's cursor are native (same device, or P2P native atomics)
     uint32_t *share_fb = nullptr;
     void *ipc_opened[2] = {nullptr, nullptr};
     int n_stages = 0;
@@ -116,6 +118,7 @@ long long g_warp_budget_option = 0;  // ct_gpu_set_option("overflow_warp_budget"
 long long g_static_eighths = 7;      // ct_gpu_set_option("shared_static_eighths"), see next_chunk
 long long g_shared_chunk_shift = 0;  // ct_gpu_set_option("shared_chunk_shift"): 0 = kChunkSharedShift
 long long g_emulate_ranks = 0;       // ct_gpu_set_option("emulate_ranks"): profiling aid, see ct_gpu.h
+long long g_hold_frame = 0;          // ct_gpu_set_option("shared_hold_frame"): test aid, see ct_gpu.h
 long long g_l2_persist = 1;          // ct_gpu_set_option("l2_persist"): pin the walk's fp32 records in L2 (apply_l2_policy)
 
 int check_device(int device) {
@@ -174,9 +177,12 @@ int dev_alloc(DeviceState &s, T **out, size_t count, bool zero = false) {
 #define TRY(expr) do { int rc_ = (expr); if (rc_ != CT_OK) return rc_; } while (0)
 
 
-// depth of the reference's DFS (stack entries needed) -- iterative to survive degenerate trees
-int bvh_depth(const ct_bvh_node *nodes, uint32_t n_nodes, uint32_t n_tri, bool *ok) {
+// depth of the reference's DFS (stack entries needed) -- iterative to survive degenerate trees.  Also marks the nodes the
+// DFS reaches (array slots nobody points at may hold anything) and rejects leaves whose triangle ranges overlap.
+int bvh_depth(const ct_bvh_node *nodes, uint32_t n_nodes, uint32_t n_tri, bool *ok, std::vector<uint8_t> &reachable) {
     std::vector<std::pair<uint32_t, int>> st;
+    std::vector<uint8_t> covered(n_tri, 0);
+    reachable.assign(n_nodes, 0);
     st.push_back({0u, 1});
     int best = 0;
     size_t visited = 0;
@@ -184,14 +190,21 @@ int bvh_depth(const ct_bvh_node *nodes, uint32_t n_nodes, uint32_t n_tri, bool *
     while (!st.empty()) {
         auto [i, d] = st.back();
         st.pop_back();
-        if (i >= n_nodes || ++visited > (size_t)n_nodes) { *ok = false; return 0; }
+        if (i >= n_nodes || ++visited > (size_t)n_nodes || reachable[i]) { *ok = false; return 0; }      // out of range, a cycle, or a node with two parents
+        reachable[i] = 1;
         best = std::max(best, d);
         const ct_bvh_node &nd = nodes[i];
         if (nd.triangle_count == 0) {
+            if ((uint64_t)nd.left_node + 1u >= n_nodes || nd.left_node == 0u) { *ok = false; return 0; }
             st.push_back({nd.left_node, d + 1});
             st.push_back({nd.left_node + 1, d + 1});
-        } else if ((uint64_t)nd.first_triangle_index + nd.triangle_count > n_tri) {
-            *ok = false; return 0;
+        } else {
+            if ((uint64_t)nd.first_triangle_index + nd.triangle_count > n_tri) { *ok = false; return 0; }
+            for (uint32_t k = 0; k < nd.triangle_count; k++) {
+                uint8_t &c = covered[nd.first_triangle_index + k];
+                if (c) { *ok = false; return 0; }                                  // two leaves hold the same position
+                c = 1;
+            }
         }
     }
     return best;
@@ -267,8 +280,9 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     if ((d->flags & CT_FLAG_SUPERSAMPLING) && (d->flags & CT_FLAG_KEEP_HITS))
         return fail(CT_ERR_INVALID, "CT_FLAG_SUPERSAMPLING cannot be combined with CT_FLAG_KEEP_HITS (a pixel has 16 primary rays)");
     bool ok = true;
-    int depth = bvh_depth(d->nodes, d->n_nodes, d->n_triangles, &ok);
-    if (!ok) return fail(CT_ERR_INVALID, "BVH is malformed (child or triangle range out of bounds, or a cycle)");
+    std::vector<uint8_t> reachable;
+    int depth = bvh_depth(d->nodes, d->n_nodes, d->n_triangles, &ok, reachable);
+    if (!ok) return fail(CT_ERR_INVALID, "BVH is malformed (child or triangle range out of bounds, overlapping leaves, a cycle or a shared child)");
     if (depth > kStackMax) return fail(CT_ERR_LIMIT, "BVH depth %d exceeds the device traversal stack (%d)", depth, kStackMax);
     TRY(check_device(device));
     std::lock_guard<std::mutex> lock(g_mutex);
@@ -302,7 +316,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     std::vector<uint32_t> pid_of(d->n_nodes, kNoPos);
     uint32_t n_pairs = 0;
     for (uint32_t i = 0; i < d->n_nodes; i++)
-        if (d->nodes[i].triangle_count == 0) pid_of[i] = n_pairs++;
+        if (reachable[i]) pid_of[i] = d->nodes[i].triangle_count == 0 ? n_pairs++ : kLeafMark;      // unreachable slots get no record and write nothing
     auto child_ref = [&](uint32_t c, uint32_t &ref, uint32_t &cnt) {
         const ct_bvh_node &n = d->nodes[c];
         cnt = n.triangle_count;
@@ -372,6 +386,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
             CU(cudaMemcpyAsync(hot, wide.data(), wide.size() * sizeof(DevWide), cudaMemcpyHostToDevice, s.stream));
             CU(cudaStreamSynchronize(s.stream));
             p.wide = reinterpret_cast<const DevWide *>(hot);
+            p.n_wide = (uint32_t)wide.size();
         }
         dp32 = reinterpret_cast<DevPair32 *>(hot + wide_bytes); dt32 = reinterpret_cast<DevTri32 *>(hot + wide_bytes + pair_bytes);
     }
@@ -382,15 +397,18 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     BuildReport rep{};
     {
         // staging copies of the caller's arrays, freed again below
-        ct_bvh_node *raw_nodes = nullptr; uint32_t *raw_pid = nullptr, *raw_idx = nullptr; unsigned char *raw_tris = nullptr; BuildReport *drep = nullptr;
+        ct_bvh_node *raw_nodes = nullptr; uint32_t *raw_pid = nullptr, *raw_idx = nullptr, *seen = nullptr; unsigned char *raw_tris = nullptr; BuildReport *drep = nullptr;
         const size_t tri_bytes = (size_t)(d->n_triangles - 1) * d->triangle_stride + 72;      // the last triangle may end at its third vertex
-        auto release = [&] { cudaFree(raw_nodes); cudaFree(raw_pid); cudaFree(raw_idx); cudaFree(raw_tris); cudaFree(drep); };
+        auto release = [&] { cudaFree(raw_nodes); cudaFree(raw_pid); cudaFree(raw_idx); cudaFree(raw_tris); cudaFree(drep); cudaFree(seen); };
         auto staged = [&](cudaError_t e) { if (e != cudaSuccess) { release(); free_device(s); } return e; };
         CU(staged(cudaMalloc(&raw_nodes, (size_t)d->n_nodes * sizeof(ct_bvh_node))));
         CU(staged(cudaMalloc(&raw_pid, (size_t)d->n_nodes * 4)));
         CU(staged(cudaMalloc(&raw_idx, (size_t)d->n_triangles * 4)));
         CU(staged(cudaMalloc(&raw_tris, tri_bytes)));
         CU(staged(cudaMalloc(&drep, sizeof rep)));
+        const size_t seen_words = ((size_t)d->n_triangles + 31u) / 32u;
+        CU(staged(cudaMalloc(&seen, seen_words * 4)));
+        CU(staged(cudaMemsetAsync(seen, 0, seen_words * 4, s.stream)));
         rep.bad_pos = kNoPos; rep.pos0 = kNoPos;
         CU(staged(cudaMemcpyAsync(drep, &rep, sizeof rep, cudaMemcpyHostToDevice, s.stream)));
         CU(staged(cudaMemcpyAsync(raw_nodes, d->nodes, (size_t)d->n_nodes * sizeof(ct_bvh_node), cudaMemcpyHostToDevice, s.stream)));
@@ -402,14 +420,14 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
         CU(staged(cudaMemcpyAsync(raw_idx, d->tri_indexes, (size_t)d->n_triangles * 4, cudaMemcpyHostToDevice, s.stream)));
         CU(staged(cudaMemcpyAsync(raw_tris, d->triangles, tri_bytes, cudaMemcpyHostToDevice, s.stream)));
         CU(staged(cudaMemcpyAsync(dm, d->materials, (size_t)d->n_triangles * sizeof(ct_material), cudaMemcpyHostToDevice, s.stream)));
-        k_build_tris<<<build_blocks, 256, 0, s.stream>>>(raw_tris, (uint32_t)d->triangle_stride, raw_idx, dm, d->n_triangles, dt, dt32, drep);
+        k_build_tris<<<build_blocks, 256, 0, s.stream>>>(raw_tris, (uint32_t)d->triangle_stride, raw_idx, dm, d->n_triangles, dt, dt32, seen, drep);
         CU(staged(cudaGetLastError()));
         CU(staged(cudaMemcpyAsync(&rep, drep, sizeof rep, cudaMemcpyDeviceToHost, s.stream)));
         CU(staged(cudaStreamSynchronize(s.stream)));
         release();
     }
     if (rep.bad_pos != kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes[%u] = %u out of range", rep.bad_pos, d->tri_indexes[rep.bad_pos]); }
-    if (rep.pos0 == kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes is not a permutation (triangle 0 missing)"); }
+    if (rep.duplicate || rep.pos0 == kNoPos) { free_device(s); return fail(CT_ERR_INVALID, "tri_indexes is not a permutation of 0..n_triangles-1 (an index occurs twice)"); }
     p.pos_of_tri0 = rep.pos0;
     p.nested = (!rep.not_nested && !rep.boxes_bad) ? 1u : 0u;
     s.any_reflective = rep.any_reflective != 0;
@@ -490,7 +508,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     p.supersample = (d->flags & CT_FLAG_SUPERSAMPLING) ? 1 : 0;
     if (p.subsample || p.supersample) TRY(dev_alloc(s, &p.final_color, p.cap, true));
     TRY(dev_alloc(s, &p.own_chunks, (p.cap >> kChunkLocalShift) + 1u));
-    TRY(dev_alloc(s, &s.cursor_own, 1, true));                           // its own allocation: exported over CUDA IPC
+    TRY(dev_alloc(s, &s.cursor_own, 2 * kCursorStride, true));           // its own allocation: exported over CUDA IPC; two cursors, 128 bytes apart
     s.share_cursor = s.cursor_own; s.share_fb = p.fb;
     if (d->flags & CT_FLAG_KEEP_HITS) {
         size_t npx = (size_t)d->width * d->height;
@@ -554,7 +572,12 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     const bool count = (s.flags & CT_FLAG_COUNT_TESTS) != 0;
     const int depth_max = s.any_reflective ? p.max_depth : 0;
     // one device: its own cursor (zeroed with the rest of DevSched below) and framebuffer; shared frame: the root's
-    p.steal = shared ? s.share_cursor : &p.sched->steal_local;
+    // shared frames alternate between two cursors: while frame f steals from cursor f & 1, the root zeroes the other one on
+    // its stream for frame f + 1 -- nobody touches that one before the frame-end rendezvous, so no reset call and no
+    // host synchronisation stands between two frames
+    const bool same_frame = shared && g_hold_frame && s.shared_frames > 0;      // (tests: one device plays several participants of ONE frame)
+    const unsigned long long frame_no = same_frame ? s.shared_frames - 1ull : s.shared_frames;
+    p.steal = shared ? s.share_cursor + kCursorStride * (frame_no & 1ull) : &p.sched->steal_local;
     const uint32_t shared_shift = g_shared_chunk_shift ? (uint32_t)g_shared_chunk_shift : kChunkSharedShift;
     p.chunk_shift = shared ? shared_shift : kChunkLocalShift;
     p.steal_stride = g_emulate_ranks > 1 ? (uint32_t)g_emulate_ranks : 1u;
@@ -563,9 +586,18 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     p.part_index = dealt ? (uint32_t)s.part_index : 0u;
     p.part_count = dealt ? (uint32_t)s.part_count : 0u;
     p.static_eighths = (uint32_t)g_static_eighths;
+    if (shared && !s.remote_cursor_ok) {
+        // no native atomics to the root's cursor: stealing from it would hand chunks out twice or not at all
+        if (!dealt) return fail(CT_ERR_CUDA, "device %d has no native atomics to the shared frame's cursor: declare the participants (ct_gpu_share_partition), then every chunk is dealt", device);
+        p.static_eighths = 8u;
+    }
     p.fb_out = shared ? s.share_fb : p.fb;
     Params pk = p; pk.max_depth = depth_max;   // with no reflective material the recursion never goes past depth 0 (:369)
     cudaStream_t st = s.stream;
+    if (shared && !same_frame) {
+        if (s.share_cursor == s.cursor_own) CU(cudaMemsetAsync(s.cursor_own + kCursorStride * ((s.shared_frames + 1ull) & 1ull), 0, sizeof(unsigned long long), st));
+        s.shared_frames++;
+    }
     CU(cudaMemsetAsync(p.sched, 0, sizeof(DevSched), st));
     CU(cudaEventRecord(s.ev0, st));
     const int grid = launch_grid(s, 8);
@@ -701,6 +733,7 @@ int ct_gpu_share_export(int device, ct_gpu_share *out) {
     out->fb_ptr = (uint64_t)(uintptr_t)s.p.fb;
     out->cursor_ptr = (uint64_t)(uintptr_t)s.cursor_own;
     out->width = s.p.W; out->height = s.p.H;
+    out->frames = s.shared_frames;
     return CT_OK;
 }
 
@@ -709,12 +742,21 @@ int ct_gpu_share_attach(int device, const ct_gpu_share *root) {
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     for (void *&q : s.ipc_opened) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    s.remote_cursor_ok = true;
+    if (root) s.shared_frames = root->frames;                // which of the two cursors the next shared frame uses
     if (!root) {                                             // detach: back to this device's own cursor and framebuffer
         s.share_cursor = s.cursor_own; s.share_fb = s.p.fb;
         return CT_OK;
     }
     if (root->struct_size != sizeof(ct_gpu_share)) return fail(CT_ERR_INVALID, "ct_gpu_share struct_size != %zu", sizeof(ct_gpu_share));
     if (root->width != s.p.W || root->height != s.p.H) return fail(CT_ERR_INVALID, "shared frame is %dx%d, this device renders %dx%d", root->width, root->height, s.p.W, s.p.H);
+    if (root->device != device) {
+        // next_chunk steals with atomicAdd on the root's cursor: across devices that is only atomic where the link has
+        // native atomics (NVLink; not PCIe peer access).  Without them this device takes dealt chunks only (render_impl).
+        int native = 0;
+        if (cudaDeviceGetP2PAttribute(&native, cudaDevP2PAttrNativeAtomicSupported, device, root->device) != cudaSuccess) { cudaGetLastError(); native = 0; }
+        s.remote_cursor_ok = native != 0;
+    }
     if (root->pid == (int64_t)getpid()) {                    // same process: raw pointers (+ peer access between the two devices)
         if (root->device != device) {
             int can = 0;
@@ -752,7 +794,7 @@ int ct_gpu_share_reset(int device) {
     TRY(check_device(device));
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
-    CU(cudaMemsetAsync(s.cursor_own, 0, sizeof(unsigned long long), s.stream));
+    CU(cudaMemsetAsync(s.cursor_own, 0, 2 * kCursorStride * sizeof(unsigned long long), s.stream));
     CU(cudaStreamSynchronize(s.stream));
     return CT_OK;
 }
@@ -777,6 +819,11 @@ int ct_gpu_set_option(const char *name, long long value) {
     if (!strcmp(name, "shared_chunk_shift")) {
         if (value != 0 && (value < kChunkLocalShift || value > kChunkMaxShift)) return fail(CT_ERR_INVALID, "shared_chunk_shift must be 0 (default), 5 or 6");
         g_shared_chunk_shift = value;
+        return CT_OK;
+    }
+    if (!strcmp(name, "shared_hold_frame")) {
+        if (value != 0 && value != 1) return fail(CT_ERR_INVALID, "shared_hold_frame must be 0 or 1");
+        g_hold_frame = value;
         return CT_OK;
     }
     if (!strcmp(name, "l2_persist")) {

@@ -243,6 +243,9 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
     LocalCount lc;
     uint32_t n_shadow = 0, n_parked = 0;
+    __shared__ __align__(128) DevWide top_nodes[kTopSmem > 0u ? kTopSmem : 1u];
+    __shared__ unsigned long long top_bar;
+    const uint32_t n_top = (kTopSmem > 0u && P.wide) ? stage_top_nodes(P, top_nodes, &top_bar, P.n_wide) : 0u;
     const uint32_t n = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
     const unsigned long long n_pad = ((unsigned long long)n + 31ull) & ~31ull;
     const unsigned long long total = n_pad * P.n_slights;
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
         uint32_t budget = P.budget;
         while (true) {                                                  // warp-uniform: traverse_early is warp-synchronous
             float stc; uint32_t spos;
-            int res = traverse_early_any<kAnyHit, COUNT>(P, tr, active, budget, stc, spos, lc);
+            int res = traverse_early_any<kAnyHit, COUNT>(P, tr, active, budget, stc, spos, lc, top_nodes, n_top);
             bool again = false;
             if (active) {
                 if (res == kTravOverBudget) {
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
                 float rdv = vdot(refl, view);
                 if (rdv > 0.0f) {                                        // :319-321 double pow, += rounds to float
                     float qv = __fdiv_rn(rdv, __fmul_rn(vmag(refl), vmag(view)));
-                    double term = __dmul_rn((double)li, pow((double)qv, (double)mat.specular));
+                    double term = __dmul_rn((double)li, pow_int((double)qv, mat.specular));
                     intensity = __double2float_rn(__dadd_rn((double)intensity, term));
                 }
             }
@@ -405,6 +408,9 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
     LocalCount lc;
     uint32_t n_parked = 0;
+    __shared__ __align__(128) DevWide top_nodes[kTopSmem > 0u ? kTopSmem : 1u];
+    __shared__ unsigned long long top_bar;
+    const uint32_t n_top = (kTopSmem > 0u && P.wide) ? stage_top_nodes(P, top_nodes, &top_bar, P.n_wide) : 0u;
     const uint32_t n = P.sched->queue_count[depth];
     const int cur = depth & 1;
     while (true) {
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
         uint32_t budget = P.budget;
         while (true) {                                                  // warp-uniform: traverse is warp-synchronous
             float tc; uint32_t pos;
-            int res = traverse_early_any<kFirstLine, COUNT>(P, r, active, budget, tc, pos, lc);
+            int res = traverse_early_any<kFirstLine, COUNT>(P, r, active, budget, tc, pos, lc, top_nodes, n_top);
             bool again = false;
             if (active) {
                 if (res == kTravOverBudget) {

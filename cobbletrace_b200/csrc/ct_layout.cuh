@@ -21,6 +21,7 @@ constexpr int kMinBlocks = CT_MIN_BLOCKS;   // traversal kernels: resident CTAs 
 constexpr int kOvfThreads = 256;     // k_overflow CTA
 constexpr int kMaxLaunches = 80;     // launches of one tile (work cursors / stage events)
 constexpr uint32_t kNoPos = 0xffffffffu;
+constexpr int kCursorStride = 16;    // unsigned long longs between the two chunk cursors of a shared frame (128 bytes)
 // Slots a warp takes from the tile's cursor at a time: 32 = one 8x4 pixel block, one ray per lane.  When the cursor is
 // another GPU's memory, 64 would halve the NVLink round trips, but a kernel ends with its slowest warp and a warp's
 // chunk is walked one ray per lane at a time: measured on dragon 4K, 2 / 4 GPUs: 4.10 / 2.49 ms with 64 against
@@ -93,6 +94,7 @@ struct Params {
     const DevPair32 *pairs32;
     const DevPair64 *pairs64;
     const DevWide *wide;                 // node 0 = the root's children (nullptr: the root is a leaf)
+    uint32_t n_wide;
     double root_min[3], root_max[3];     // node 0
     float root_min32[3], root_max32[3];  // ... as floats, for the slab filter
     uint32_t root_ref, root_cnt;

@@ -351,10 +351,41 @@ CT_DEV int traverse_early(const Params &P, const TRay &r, bool active, const uin
 // A triangle that passes the exact test counts only if the reference's walk reaches its leaf (candidate_reached).
 // WARP-SYNCHRONOUS, same contract as traverse_early; a stack that would overflow ends the walk as kTravOverBudget (the
 // ray is parked and finished on the binary tree).
+// Optional experiment (-DCT_TOP_SMEM=M, north_star: "BVH nodes staged through shared memory or TMA for the top levels"):
+// the first M nodes of the wide tree -- they are numbered breadth first, so these are its top levels -- are copied into
+// shared memory by one bulk-copy (TMA) instruction per CTA and the walk reads them from there.  Off by default: see the
+// staging table in DESIGN.md 5.
+#ifndef CT_TOP_SMEM
+#define CT_TOP_SMEM 0
+#endif
+constexpr uint32_t kTopSmem = CT_TOP_SMEM;
+
+// Stage the top of the wide tree: thread 0 arms an mbarrier with the byte count and issues one cp.async.bulk
+// (global -> shared, completion on the mbarrier); everybody waits on the barrier's phase.  Returns the staged node count.
+CT_DEV uint32_t stage_top_nodes(const Params &P, DevWide *top, unsigned long long *bar, uint32_t n_wide) {
+    const uint32_t n_top = min(kTopSmem, n_wide);
+    if (n_top == 0u) return 0u;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar), dst_a = (uint32_t)__cvta_generic_to_shared(top);
+    const uint32_t bytes = n_top * (uint32_t)sizeof(DevWide);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst_a), "l"(P.wide), "r"(bytes), "r"(bar_a) : "memory");
+    }
+    asm volatile("{\n .reg .pred p;\n WAIT_TOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra DONE_TOP;\n bra WAIT_TOP;\n DONE_TOP:\n}" ::"r"(bar_a) : "memory");
+    return n_top;
+}
+
 constexpr int kWideStack = 64;                 // pending children per lane: (kWide - 1) per level of the wide tree
 constexpr int kWideLeaves = 2 * kWide + 8;     // deferred leaves per lane; a visit may add kWide
 template <TraverseMode MODE, bool COUNT>
-CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc,
+                         const DevWide *top = nullptr, uint32_t n_top = 0u) {
     static_assert(MODE != kClosest, "closest-hit rays use traverse_closest");
     uint2 stk[kWideStack];                                // pushed children (ref, cnt)
     uint2 leaf[kWideLeaves];                              // deferred leaves (ref, cnt), DFS order
@@ -381,14 +412,16 @@ CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint
                     spent += cur_cnt;
                 } else {
                     const float4 *q = reinterpret_cast<const float4 *>(P.wide + cur_ref);
+                    const bool staged = kTopSmem > 0u && cur_ref < n_top;             // (generic loads below when the experiment is on)
+                    if (staged) q = reinterpret_cast<const float4 *>(top + cur_ref);
                     if (COUNT) lc.box += kWide;
                     spent += (uint32_t)kWide;
                     if (sp > kWideStack - kWide) { result = kTravOverBudget; state = 0; nleaf = 0; sp = 0; }
                     else {
 #pragma unroll
                         for (int e = kWide - 1; e >= 0; e--) {             // reverse: the first accepted child is popped first
-                            const float4 a = __ldg(q + 2 * e);
-                            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(q + 2 * e + 1));
+                            const float4 a = kTopSmem > 0u ? q[2 * e] : __ldg(q + 2 * e);
+                            const uint4 b = kTopSmem > 0u ? *reinterpret_cast<const uint4 *>(q + 2 * e + 1) : __ldg(reinterpret_cast<const uint4 *>(q + 2 * e + 1));
                             const float bmin[3] = {a.x, a.y, a.z}, bmax[3] = {a.w, __uint_as_float(b.x), __uint_as_float(b.y)};
                             const bool hit = box_maybe<MODE == kAnyHit>(r, bmin, bmax);
                             if (MODE == kAnyHit) {
@@ -435,9 +468,10 @@ CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint
 // An early-exit walk for every lane's ray: over the wide tree where the ray allows conservative box tests, with the
 // reference's exact verdicts at every box of the binary tree otherwise (zero direction components, non-nested trees).
 template <TraverseMode MODE, bool COUNT>
-CT_DEV int traverse_early_any(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+CT_DEV int traverse_early_any(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc,
+                              const DevWide *top = nullptr, uint32_t n_top = 0u) {
     const bool cons = r.filt & (P.nested != 0u) & (P.wide != nullptr);
-    int res = traverse_wide<MODE, COUNT>(P, r, active & cons, budget, tclosest, closest_pos, lc);
+    int res = traverse_wide<MODE, COUNT>(P, r, active & cons, budget, tclosest, closest_pos, lc, top, n_top);
     // the binary walk for the other rays, and for rays that may not be parked (no budget) whose wide stack overflowed
     const bool binary = active & (!cons | ((res == kTravOverBudget) & (budget == 0xffffffffu)));
     if (__any_sync(kFullMask, binary)) {

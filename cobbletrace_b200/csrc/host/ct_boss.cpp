@@ -46,6 +46,7 @@ struct GpuApi {
     int (*readback)(int, uint32_t *, int, int, int) = nullptr;
     int (*get_counters)(int, ct_ray_counters *, int) = nullptr;
     int (*sync)(int) = nullptr;
+    int (*last_tile_ms)(int, float *) = nullptr;
     int (*gather_rows)(int, int, int, int) = nullptr;
     int (*share_export)(int, ct_gpu_share *) = nullptr;
     int (*share_attach)(int, const ct_gpu_share *) = nullptr;
@@ -73,6 +74,7 @@ struct GpuApi {
         readback = (int (*)(int, uint32_t *, int, int, int))sym("ct_gpu_readback");
         get_counters = (int (*)(int, ct_ray_counters *, int))sym("ct_gpu_get_counters");
         sync = (int (*)(int))sym("ct_gpu_sync");
+        last_tile_ms = (int (*)(int, float *))sym("ct_gpu_last_tile_ms");
         gather_rows = (int (*)(int, int, int, int))sym("ct_gpu_gather_rows");
         share_export = (int (*)(int, ct_gpu_share *))sym("ct_gpu_share_export");
         share_attach = (int (*)(int, const ct_gpu_share *))sym("ct_gpu_share_attach");
@@ -95,6 +97,7 @@ struct Boss {
     int tile_rows = 0, n_tiles = 0, y_lo = 0, y_hi = 0;
     bool shared_frame = false;      // several GPUs of this process render ONE tile, stealing chunks on the device (ct_gpu_render_shared)
     std::vector<std::vector<std::pair<int, int>>> tiles_by_dev;   // last frame
+    std::vector<double> device_ms;  // last frame: kernel time of the tiles each device rendered
     std::string error;
 };
 
@@ -116,6 +119,13 @@ Boss *boss_create(Scene *scene, const ct_host_boss_config *cfg) {
     try {
         b->scene = scene;
         b->cfg = *cfg;
+        // settings.subsampling stores, for every traced row, an averaged pixel into the row BELOW it (raythread.cpp:512-531): a
+        // tile writes one row of its neighbour.  Tiles of one device are rendered in order and resolve that seam like the
+        // reference's sequential loop; tiles on different devices would race on it (and the gather copies only a tile's own
+        // rows), so the frame must stay on one device.
+        if ((cfg->flags & CT_FLAG_SUBSAMPLING) &&
+            (cfg->n_devices > 1 || (cfg->shared_counter_name && cfg->shared_counter_name[0] && cfg->world_size > 1)))
+            throw std::runtime_error("CT_FLAG_SUBSAMPLING needs the whole frame on one device (a tile writes into the row below it); use one device");
         b->gpu.load(cfg->gpu_library && cfg->gpu_library[0] ? cfg->gpu_library : default_gpu_library());
         if (scene->nodes.empty()) build_bvh(*scene);                               // raythread.cpp:650-651
         ct_scene_desc d;
@@ -150,6 +160,7 @@ Boss *boss_create(Scene *scene, const ct_host_boss_config *cfg) {
         b->tile_rows = rows;
         b->n_tiles = (b->y_hi - b->y_lo + rows - 1) / rows;
         b->tiles_by_dev.resize(cfg->n_devices);
+        b->device_ms.assign(cfg->n_devices, 0.0);
     } catch (...) {
         delete b;
         throw;
@@ -178,8 +189,8 @@ void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *sta
     const bool shared = b->counter.shared != nullptr;
     if (!shared) b->counter.reset();
     for (auto &v : b->tiles_by_dev) v.clear();
+    std::fill(b->device_ms.begin(), b->device_ms.end(), 0.0);
     std::vector<std::string> errs(nd);
-    if (b->shared_frame) b->gpu.check(b->gpu.share_reset(b->cfg.devices[0]), "ct_gpu_share_reset");
     auto worker = [&](int k) {
         try {
             const int dev = b->cfg.devices[k];
@@ -187,6 +198,8 @@ void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *sta
                 b->gpu.check(b->gpu.render_shared(dev, b->y_lo, b->y_hi, nullptr), "ct_gpu_render_shared");
                 b->tiles_by_dev[k].push_back({b->y_lo, b->y_hi});
                 b->gpu.check(b->gpu.sync(dev), "ct_gpu_sync");
+                float ms = 0.0f;
+                if (b->gpu.last_tile_ms(dev, &ms) >= 0) b->device_ms[k] += ms;
                 return;
             }
             while (true) {
@@ -197,6 +210,10 @@ void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *sta
                 b->tiles_by_dev[k].push_back({y0, y1});
                 // keep at most two tiles in flight per GPU so that stealing follows real progress
                 b->gpu.check(b->gpu.throttle(dev, 1), "ct_gpu_throttle");
+                if (stats && b->n_tiles > 1) {           // per-tile kernel times are only read when somebody asks (it waits for the tile)
+                    float ms = 0.0f;
+                    if (b->gpu.last_tile_ms(dev, &ms) >= 0) b->device_ms[k] += ms;
+                }
             }
             // finished tiles -> devices[0] over NVLink
             if (k != 0) {
@@ -205,6 +222,10 @@ void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *sta
                     b->gpu.check(b->gpu.gather_rows(dev, b->cfg.devices[0], half - (y1 - 1), half - y0 + 1), "ct_gpu_gather_rows");
             }
             b->gpu.check(b->gpu.sync(dev), "ct_gpu_sync");
+            if (b->n_tiles == 1 && !b->tiles_by_dev[k].empty()) {
+                float ms = 0.0f;
+                if (b->gpu.last_tile_ms(dev, &ms) >= 0) b->device_ms[k] += ms;
+            }
         } catch (const std::exception &e) {
             errs[k] = e.what();
         }
@@ -240,6 +261,7 @@ void boss_render(Boss *b, uint32_t *bitmap, int stride, ct_host_frame_stats *sta
             stats->kernel_launches += nl;
         }
         stats->tiles_total = b->n_tiles;
+        stats->device_ms_max = (float)*std::max_element(b->device_ms.begin(), b->device_ms.end());
         stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
 }

@@ -267,7 +267,7 @@ class Boss:
         if rc < 0:
             raise RuntimeError("ct_host_boss_render: " + _err(self.L))
         stats = dict(st.rays.as_dict(), wall_ms=float(st.wall_ms), tiles_total=int(st.tiles_total), tiles_mine=int(st.tiles_mine),
-                     kernel_launches=int(st.kernel_launches))
+                     kernel_launches=int(st.kernel_launches), device_ms_max=float(st.device_ms_max))
         return bitmap, stats
 
     def tiles(self):

@@ -134,9 +134,9 @@ class SharedFrame:
             renderer.share_partition(self.rank, self.world)
 
     def begin(self):
-        """Root zeroes the cursor; nobody may start stealing before that (barrier)."""
-        if self.rank == self.root:
-            self.r.share_reset()
+        """Rendezvous before the frame: the ranks' kernels should start together (a rank that starts early steals more than
+        its share).  The cursor needs no reset: shared frames alternate between two cursors and the root zeroes the idle one
+        on its stream (ct_gpu_render_shared)."""
         if self.world > 1:
             if self._token is not None:
                 with torch.cuda.stream(self._stream):

@@ -148,8 +148,11 @@ int ct_gpu_render_tile(int device, int y_start, int y_end, ct_ray_counters *coun
  *   root:    ct_gpu_share_export(dev, &h)  -> ship h to the others (it is plain bytes)
  *   others:  ct_gpu_share_attach(dev, &h)
  *   all:     ct_gpu_share_partition(dev, k, n)   (optional, recommended: see below)
- *   frame:   root: ct_gpu_share_reset(dev); [barrier]; all: ct_gpu_render_shared(dev, y0, y1, ..); ct_gpu_sync(dev);
- *            [barrier]; root: ct_gpu_readback(dev, ...)
+ *   frame:   all: ct_gpu_render_shared(dev, y0, y1, ..); ct_gpu_sync(dev); [barrier]; root: ct_gpu_readback(dev, ...)
+ * Every participant calls ct_gpu_render_shared once per frame, and nobody starts frame f + 1 before everybody has
+ * finished frame f (the barrier).  The root keeps TWO cursors: frame f steals from cursor f & 1 while the root zeroes the
+ * other one on its stream, so no reset call and no host synchronisation is needed between frames (ct_gpu_share_reset
+ * remains for callers that abandon a frame half way: it zeroes both).
  */
 typedef struct ct_gpu_share {
     uint32_t struct_size;            /* = sizeof(ct_gpu_share) */
@@ -158,11 +161,12 @@ typedef struct ct_gpu_share {
     uint64_t fb_ptr, cursor_ptr;     /* raw device pointers (used when the attaching device is driven by the same process) */
     unsigned char fb_ipc[64], cursor_ipc[64];   /* cudaIpcMemHandle_t of the same two allocations (other processes) */
     int32_t width, height;
+    uint64_t frames;                 /* shared frames the root has rendered so far (which of its two cursors comes next) */
 } ct_gpu_share;
 
 int ct_gpu_share_export(int device, ct_gpu_share *out);
 int ct_gpu_share_attach(int device, const ct_gpu_share *root);   /* root == NULL detaches */
-int ct_gpu_share_reset(int device);                              /* root only: zero the cursor; synchronises */
+int ct_gpu_share_reset(int device);                              /* root only: zero both cursors; synchronises (not needed in the protocol above) */
 /* Declare that `count` GPUs render every shared frame and that this one is number `index` (0..count-1, all different).
  * Then only part of the chunks is stolen: of every 8*count consecutive chunks, 7*count are dealt round-robin
  * (GPU k owns chunks k, k+count, ... -- no remote atomics, and an equal share of the lighting work that follows,
@@ -171,8 +175,7 @@ int ct_gpu_share_reset(int device);                              /* root only: z
  * participant must then call ct_gpu_render_shared for every frame.  count <= 1 takes the declaration back: pure stealing,
  * any subset of the GPUs renders the whole frame.  The dealt fraction is option "shared_static_eighths" (0..8, default 7). */
 int ct_gpu_share_partition(int device, int index, int count);
-/* ct_gpu_render_tile for a frame shared between GPUs.  Without an attach it behaves like a one-GPU frame whose
- * cursor must be reset with ct_gpu_share_reset first. */
+/* ct_gpu_render_tile for a frame shared between GPUs.  Without an attach it behaves like a one-GPU frame. */
 int ct_gpu_render_shared(int device, int y_start, int y_end, ct_ray_counters *counters);
 
 /* Blocks until all submitted tiles are done, then copies framebuffer rows [row_start,row_end) into
@@ -216,6 +219,8 @@ int ct_gpu_sync(int device);
  *                       the next render, 0 / 1 = off.
  *   "shared_static_eighths"  see ct_gpu_share_partition.
  *   "shared_chunk_shift"  log2 of the pixels a warp steals at a time in a shared frame: 5 (default, also 0) or 6.
+ *   "shared_hold_frame" 1: the next ct_gpu_render_shared calls belong to the SAME shared frame as the previous one (same
+ *                       cursor, not advanced) -- for tests in which one device plays several participants in turn; 0 = off.
  *   "l2_persist"        1 (default): set aside L2 for persisting lines and open an access-policy window over the walk's
  *                       fp32 records on the render streams; 0: leave the L2 to the default policy (for A/B measurements). */
 int ct_gpu_set_option(const char *name, long long value);

@@ -100,7 +100,7 @@ typedef struct ct_host_boss_config {
 
 typedef struct ct_host_frame_stats {
     ct_ray_counters rays;         /* this process's devices only */
-    float device_ms_max;          /* max over this process's devices of summed tile kernel time */
+    float device_ms_max;          /* max over this process's devices of the summed kernel time of the tiles it rendered (CUDA events) */
     double wall_ms;               /* dispatch -> bitmap complete */
     int32_t tiles_total, tiles_mine;
     uint64_t kernel_launches;     /* CUDA kernels launched for this frame by this process */

@@ -20,7 +20,16 @@ def pytest_configure(config):
 def _built():
     """Native libraries are built in-tree once per session (no JIT cache)."""
     from cobbletrace_b200 import build
-    build.build_all()
+    build.build_host()
+    try:
+        build.find_nvcc()
+    except Exception:
+        # a machine without the CUDA toolkit: the CPU-side tests (oracle, host parser / BVH builder, controls) still run;
+        # whatever needs libct_gpu.so reports that it is missing
+        if not os.path.exists(build.GPU_LIB):
+            print("conftest: nvcc not found and libct_gpu.so not built -- tests that load it will fail", file=sys.stderr)
+    else:
+        build.build_gpu()
     from oracle import ct_oracle_py
     ct_oracle_py.build()
 

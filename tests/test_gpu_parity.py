@@ -219,14 +219,20 @@ def test_shared_frame_mode_on_one_gpu(golden, scene_loader, gpu):
     want = load_frames("bunny_refl_d2_160")["frame"]
     gpu.upload(fs, meta["width"], meta["height"], max_depth=meta["depth"])
     gpu.share_attach(gpu.share_export())                        # self-attach: same process, same device
-    gpu.share_reset()
     c1 = gpu.render_shared(counters=True)
     assert np.array_equal(gpu.readback(), want)
-    c2 = gpu.render_shared(counters=True)                       # cursor not reset: nothing left to steal
+    ct.api.set_option("shared_hold_frame", 1)
+    try:
+        c2 = gpu.render_shared(counters=True)                   # the same frame again: nothing left to steal
+    finally:
+        ct.api.set_option("shared_hold_frame", 0)
     assert c2["rays_primary"] == 0 and c2["rays_shadow"] == 0 and np.array_equal(gpu.readback(), want)
-    gpu.share_reset()
-    c3 = gpu.render_shared(counters=True)
-    assert c3 == c1 and np.array_equal(gpu.readback(), want)
+    for _ in range(3):                                          # new frames alternate between the two cursors; no reset call
+        c3 = gpu.render_shared(counters=True)
+        assert c3 == c1 and np.array_equal(gpu.readback(), want)
+    gpu.share_reset()                                           # still allowed: zeroes both cursors
+    c4 = gpu.render_shared(counters=True)
+    assert c4 == c1 and np.array_equal(gpu.readback(), want)
     gpu.share_attach(None)
     gpu.render_tile()
     assert np.array_equal(gpu.readback(), want)
@@ -246,10 +252,10 @@ def test_shared_frame_partition_covers_the_frame_once(count, eighths, golden, sc
     gpu.share_attach(gpu.share_export())
     ct.api.set_option("shared_static_eighths", eighths)
     try:
-        gpu.share_reset()
         parts = []
         for k in range(count):
             gpu.share_partition(k, count)
+            ct.api.set_option("shared_hold_frame", 1 if k > 0 else 0)      # participants 1.. render the SAME frame as participant 0
             parts.append(gpu.render_shared(counters=True))
             if k == 0 and count > 1 and eighths > 0:
                 assert not np.array_equal(gpu.readback(), want)      # one participant alone does not finish the frame
@@ -260,6 +266,7 @@ def test_shared_frame_partition_covers_the_frame_once(count, eighths, golden, sc
             assert max(p["rays_primary"] for p in parts) <= min(p["rays_primary"] for p in parts) + 64 * 2
     finally:
         ct.api.set_option("shared_static_eighths", 7)
+        ct.api.set_option("shared_hold_frame", 0)
         gpu.share_partition(0, 0)
         gpu.share_attach(None)
 
@@ -320,7 +327,7 @@ def test_supersampling_against_patched_reference_and_oracle(golden, scene_loader
     got = np.zeros_like(want)
     gpu.readback(got)
     assert np.array_equal(got, want), f"{int((got != want).sum())} pixels differ"
-    gpu.share_attach(gpu.share_export()); gpu.share_reset()      # whole pixels per chunk: the shared-frame path works too
+    gpu.share_attach(gpu.share_export())      # whole pixels per chunk: the shared-frame path works too
     gpu.render_shared()
     got2 = np.zeros_like(want)
     gpu.readback(got2)
@@ -662,3 +669,64 @@ def test_both_sampling_modes_at_once(golden, scene_loader, gpu):
         gpu.render_tile(a, b)
     got = gpu.readback()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_upload_validates_the_tree_and_ignores_unreachable_slots(golden, scene_loader, gpu):
+    """What ct_gpu_upload_scene guarantees about a caller's BVH: tri_indexes must be a permutation (a duplicate is rejected, not
+    silently rendered), leaves may not overlap, a node has one parent -- and array slots the tree never reaches may hold
+    anything (NaN boxes, wild child indices) without changing a pixel or switching the filters off."""
+    fs, meta = case_scene("bunny_refl_d2_160", golden, scene_loader)
+    want = load_frames("bunny_refl_d2_160")["frame"]
+    W, H, depth = meta["width"], meta["height"], meta["depth"]
+    # garbage in unreachable slots
+    k = 5
+    junk = dataclasses.replace(
+        fs, node_min=np.concatenate([fs.node_min, np.full((k, 3), np.nan)]), node_max=np.concatenate([fs.node_max, np.full((k, 3), -np.inf)]),
+        node_left=np.concatenate([fs.node_left, np.array([3, 0xFFFFFFF0, 1, 7, 2], np.uint32)]),
+        node_first=np.concatenate([fs.node_first, np.array([0, 9, 0xFFFFFF00, 1, 2], np.uint32)]),
+        node_count=np.concatenate([fs.node_count, np.array([0, 0, 2, 0, 1], np.uint32)]))
+    gpu.upload(junk, W, H, max_depth=depth, flags=ct.CT_FLAG_COUNT_TESTS)
+    gpu.render_tile()
+    assert np.array_equal(gpu.readback(), want)
+    bx, tx = gpu.filter_stats()
+    c = gpu.counters()
+    assert bx < 0.02 * c["box_tests"]                       # the certified slab filter still decides nearly everything
+    # a duplicated triangle index
+    dup = fs.tri_index.copy(); dup[7] = dup[8]
+    with pytest.raises(ct.CtError, match="not a permutation"):
+        gpu.upload(dataclasses.replace(fs, tri_index=dup), W, H, max_depth=depth)
+    # two leaves that share a position
+    leaves = np.flatnonzero(fs.node_count > 0)
+    a = leaves[np.argmax(fs.node_first[leaves] > 0)]
+    first = fs.node_first.copy(); first[a] -= 1
+    with pytest.raises(ct.CtError, match="malformed"):
+        gpu.upload(dataclasses.replace(fs, node_first=first), W, H, max_depth=depth)
+    # a node with two parents
+    interior = np.flatnonzero(fs.node_count == 0)
+    left = fs.node_left.copy(); left[interior[3]] = left[interior[2]]
+    with pytest.raises(ct.CtError, match="malformed"):
+        gpu.upload(dataclasses.replace(fs, node_left=left), W, H, max_depth=depth)
+
+
+@pytest.mark.gpu
+def test_tree_that_is_not_nested_takes_the_exact_walks(golden, scene_loader, gpu):
+    """The early-exit walks' conservative box tests rest on every child's box lying inside its parent's (box_maybe in
+    ct_traverse.cuh).  A caller's tree without that property -- here: boxes of some inner nodes SHRUNK, so that rays the
+    parent rejects would have hit the children -- must be walked with the reference's verdict at every box: the frame then
+    equals the oracle's on the same (odd) tree, and differs from the frame of the proper tree."""
+    fs, meta = case_scene("bunny_refl_d2_160", golden, scene_loader)
+    W, H, depth = meta["width"], meta["height"], meta["depth"]
+    nmin, nmax = fs.node_min.copy(), fs.node_max.copy()
+    interior = np.flatnonzero(fs.node_count == 0)
+    rng = np.random.default_rng(3)
+    pick = interior[rng.choice(len(interior), len(interior) // 6, replace=False)]
+    pick = pick[pick != 0]
+    mid = 0.5 * (nmin[pick] + nmax[pick])
+    nmin[pick] = mid + 0.6 * (nmin[pick] - mid); nmax[pick] = mid + 0.6 * (nmax[pick] - mid)
+    odd = dataclasses.replace(fs, node_min=nmin, node_max=nmax)
+    oframe, ohits, _ = O.OracleScene(odd).render(W, H, max_depth=depth)
+    gpu.upload(odd, W, H, max_depth=depth, flags=DBG)
+    gpu.render_tile()
+    assert_same(gpu, oframe, ohits, "shrunk inner boxes")
+    assert not np.array_equal(oframe, load_frames("bunny_refl_d2_160")["frame"])

@@ -310,3 +310,15 @@ def test_write_ppm_channel_order(tmp_path):
     assert px[1, 0].tolist() == [0, 255, 0] and px[1, 1].tolist() == [0, 0, 255] and px[2, 1].tolist() == [255, 255, 255]
     with pytest.raises(RuntimeError):
         host.write_ppm(str(tmp_path / "no" / "such" / "dir.ppm"), bm)
+
+
+def test_boss_refuses_subsampling_on_several_devices(golden):
+    """settings.subsampling writes into the row below a partition (raythread.cpp:512-531): the boss keeps such a frame on
+    one device instead of racing on the seam between devices (and says so before touching any GPU)."""
+    from cobbletrace_b200 import api, host
+    from conftest import load_golden_scene
+    hs = host.HostScene.from_flat(load_golden_scene("scene_file_cube", golden).without_bvh())
+    with pytest.raises(RuntimeError, match="whole frame on one device"):
+        host.Boss(hs, 64, 64, devices=(0, 1), flags=api.CT_FLAG_SUBSAMPLING)
+    with pytest.raises(RuntimeError, match="whole frame on one device"):
+        host.Boss(hs, 64, 64, devices=(0,), flags=api.CT_FLAG_SUBSAMPLING, shared_counter="ct_test_subsample", rank=0, world_size=2)

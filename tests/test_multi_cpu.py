@@ -105,9 +105,11 @@ class _FakeRenderer:
         self.calls = []
         self.mem = None
         self.part = None
+        self.frames = 0              # shared renders so far: frame f uses cursor f & 1, the root zeroes the other one meanwhile
 
     def share_export(self):
-        np.lib.format.open_memmap(self.path, mode="w+", dtype=np.int64, shape=(1 + self.n_chunks,))[:] = -1
+        m = np.lib.format.open_memmap(self.path, mode="w+", dtype=np.int64, shape=(2 + self.n_chunks,))
+        m[:2] = 0; m[2:] = -1
         self.mem = np.load(self.path, mmap_mode="r+")
         self.calls.append("export")
         return self.path.encode()
@@ -123,7 +125,7 @@ class _FakeRenderer:
 
     def share_reset(self):
         self.calls.append("reset")
-        self.mem[0] = 0
+        self.mem[:2] = 0
         self.mem.flush()
 
     def render_shared(self, counters=False):
@@ -131,10 +133,14 @@ class _FakeRenderer:
         self.calls.append("render")
         took = 0
         mem = np.load(self.path, mmap_mode="r+")
+        slot = self.frames & 1
+        if self.rank == 0:                                          # the root prepares the cursor of the NEXT frame (ct_gpu_render_shared)
+            mem[slot ^ 1] = 0; mem.flush()
+        self.frames += 1
 
         def trace(idx):
-            assert mem[1 + idx] == -1, "chunk rendered twice"
-            mem[1 + idx] = self.rank; mem.flush()                   # "peer store" of the finished chunk into the root's frame
+            assert mem[2 + idx] == -1, "chunk rendered twice"
+            mem[2 + idx] = self.rank; mem.flush()                   # "peer store" of the finished chunk into the root's frame
             time.sleep(0.002 if self.rank == 1 else 0.0005)
             return 1
         # the numbering of next_chunk (ct_kernels.cuh): groups of 8R chunks, 7R dealt round-robin, R stolen from the cursor
@@ -152,7 +158,7 @@ class _FakeRenderer:
             while True:
                 fcntl.flock(lock, fcntl.LOCK_EX)                    # "atomicAdd" on the shared cursor
                 cur = np.load(self.path, mmap_mode="r+")
-                c = int(cur[0]); cur[0] = c + 1; cur.flush()
+                c = int(cur[slot]); cur[slot] = c + 1; cur.flush()
                 fcntl.flock(lock, fcntl.LOCK_UN)
                 g = c // per
                 if g >= n_groups:
@@ -183,14 +189,14 @@ def _shared_worker(rank, world, port, path, n_chunks, out_path):
         dist.all_reduce(t)
         assert int(t) == n_chunks, "every chunk exactly once"
         if rank == 0:
-            owners = np.load(path, mmap_mode="r")[1:]
+            owners = np.load(path, mmap_mode="r")[2:]
             assert set(np.unique(owners).tolist()) <= {0, 1} and (owners >= 0).all(), "frame incomplete on the root"
             shares.append([(owners == 0).sum(), (owners == 1).sum()])
         dist.barrier()
         if rank == 0:
-            np.load(path, mmap_mode="r+")[1:] = -1
+            np.load(path, mmap_mode="r+")[2:] = -1
     sf.close()
-    want = (["export", "partition"] + ["reset", "render", "sync"] * 3 + ["unpartition"] if rank == 0
+    want = (["export", "partition"] + ["render", "sync"] * 3 + ["unpartition"] if rank == 0
             else ["attach", "partition"] + ["render", "sync"] * 3 + ["unpartition", "detach"])
     assert r.calls == want, r.calls
     if rank == 0:
@@ -199,8 +205,8 @@ def _shared_worker(rank, world, port, path, n_chunks, out_path):
 
 
 def test_shared_frame_protocol_two_ranks(tmp_path):
-    """multi.SharedFrame on 2 gloo ranks: the root exports, the other attaches, every frame is reset -> barrier ->
-    render -> sync -> barrier, all chunks are taken exactly once (most dealt round-robin, the rest stolen from the shared
+    """multi.SharedFrame on 2 gloo ranks: the root exports, the other attaches, every frame is barrier -> render -> sync
+    -> barrier (no cursor reset: frames alternate between two cursors), all chunks are taken exactly once (most dealt round-robin, the rest stolen from the shared
     cursor: ct_gpu_share_partition) and land in the root's frame."""
     out = str(tmp_path / "shares.npy")
     mp.spawn(_shared_worker, args=(2, _free_port(), str(tmp_path / "frame.npy"), 60, out), nprocs=2, join=True)
