@@ -390,19 +390,26 @@ def main():
     pinned = torch.zeros((H, W), dtype=torch.int32).pin_memory()
     bitmap = pinned.numpy().view(np.uint32)
 
-    def frame(to_host: bool):
-        """One step. Returns (stats, device_ms)."""
+    pinned2 = torch.zeros((H, W), dtype=torch.int32).pin_memory()
+    bitmaps = [bitmap, pinned2.numpy().view(np.uint32)]
+
+    def frame(to_host: bool, want_stats: bool = False, async_copy: int = -1):
+        """One step.  Returns (stats or None, device_ms).  async_copy >= 0: the bitmap goes to the host through
+        ct_gpu_readback_async into bitmaps[async_copy] (the copy overlaps the next frame) instead of ct_gpu_readback."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if N == 1:
             if to_host:
                 boss.set_camera(cam_pos, 0.0, 0.0, 0.0)      # the per-frame input of the reference's boss (HandleUpdates :564-572)
             with torch.cuda.stream(stream):
                 e0.record(stream)
-                _, st = boss.render(bitmap if to_host else None, want_bitmap=False)
+                _, st = boss.render(bitmap if (to_host and async_copy < 0) else None, want_bitmap=False)
                 e1.record(stream)
+            if to_host and async_copy >= 0:
+                gpu.readback_wait()                          # frame k - 1 has arrived ...
+                gpu.readback_async(bitmaps[async_copy])      # ... frame k sets off, and travels while frame k + 1 renders
             stream.synchronize()
             return st, e0.elapsed_time(e1)
-        shared.begin()                                       # root zeroes the cursor; rendezvous on the render stream
+        shared.begin()                                       # rendezvous on the render stream (no cursor reset: two cursors alternate)
         if to_host:
             gpu.set_camera(cam_pos, cam_rot)                 # the camera is the per-frame input of every rank
         with torch.cuda.stream(stream):
@@ -411,10 +418,17 @@ def main():
             e1.record(stream)
         shared.end()                                         # sync + barrier: the whole frame is in GPU 0's framebuffer
         if to_host and rank == 0:
-            gpu.readback(bitmap)
-        st = gpu.counters(reset=True)
-        st["kernel_launches"] = gpu.kernel_launches(reset=True)
-        st["tiles_total"] = 1
+            if async_copy >= 0:
+                # snapshot in stream order BEFORE the next frame's rendezvous on the same stream: no rank can store into
+                # the framebuffer until the snapshot is taken
+                gpu.readback_wait()
+                gpu.readback_async(bitmaps[async_copy])
+            else:
+                gpu.readback(bitmap)
+        st = None
+        if want_stats:
+            st = gpu.counters(reset=True)
+            st["tiles_total"] = 1
         return st, e0.elapsed_time(e1)
 
     def flush_l2():
@@ -422,34 +436,55 @@ def main():
             flush.fill_(1)
         stream.synchronize()
 
-    def timed(to_host: bool, k: int):
+    def launches_so_far(reset=False):
+        return gpu.kernel_launches(reset=reset) if N > 1 else 0
+
+    def timed(to_host: bool, k: int, pipelined: bool = False):
         dev_ms, wall_ms, launches = [], [], 0
-        rays = None
-        for _ in range(k):
-            flush_l2()
+        launches_so_far(reset=True)
+        for i in range(k):
+            if not pipelined:
+                flush_l2()
             t0 = time.perf_counter()
-            st, ms = frame(to_host)
+            st, ms = frame(to_host, async_copy=(i & 1) if pipelined else -1)
             wall_ms.append((time.perf_counter() - t0) * 1e3)
             dev_ms.append(ms)
-            launches += st["kernel_launches"]
-            rays = st
-        return np.array(dev_ms), np.array(wall_ms), launches, rays
+            if N == 1:
+                launches += st["kernel_launches"]
+        if pipelined and (N == 1 or rank == 0):
+            gpu.readback_wait()
+        launches += launches_so_far(reset=True)
+        return np.array(dev_ms), np.array(wall_ms), launches
 
     for _ in range(warm):
         frame(False)
     if N > 1:
+        gpu.counters(reset=True)
+    st, _ = frame(False, want_stats=True)                    # the frame's ray counts (identical every frame)
+    if N > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(physical_gpu_index(local_rank)); sampler.start()
-    dev_ms, wall_ms, launches, st = timed(False, steps)
+    dev_ms, wall_ms, launches = timed(False, steps)
     torch.cuda.synchronize()
     if N > 1:
         dist.barrier()
     clocks = sampler.result()
-    # end-to-end: host camera in, host bitmap out, wall clock
+    # end-to-end: host camera in, host bitmap out, wall clock -- one frame at a time (latency) ...
     for _ in range(2):
         frame(True)
-    e2e_dev, e2e_wall, _, _ = timed(True, max(5, steps // 3))
+    e2e_dev, e2e_wall, _ = timed(True, max(5, steps // 3))
+    # ... and back to back with the copy of frame k overlapping the rendering of frame k + 1 (throughput of an interactive loop)
+    n_pipe = max(8, steps // 2)
+    frame(True, async_copy=0)
+    if N > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    timed(True, n_pipe, pipelined=True)
+    if N > 1:
+        dist.barrier()
+    pipe_ms = (time.perf_counter() - t0) * 1e3 / n_pipe
+    frame(True)                                              # leaves the last frame in `bitmap` for the pixel check below
 
     # ---- reduce over ranks: per-step max of the device time; sum of rays
     rays_vec = torch.tensor([st["rays_primary"], st["rays_shadow"], st["rays_reflection"], launches], dtype=torch.float64, device=f"cuda:{dev}")
@@ -488,10 +523,12 @@ def main():
                                 "reflection": rays_refl / ms_per_step / 1e3},
         "ms_per_step_min": float(t_dev.min()), "ms_per_step_max": float(t_dev.max()),
         "e2e": {"value": rays_total / e2e_ms / 1e3, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
+                "pipelined": {"value": rays_total / pipe_ms / 1e3, "unit": "Mrays/s", "ms_per_frame": pipe_ms, "frames": n_pipe,
+                              "what": "the same loop back to back with ct_gpu_readback_async: frame k travels to the (pinned) host bitmap while frame k + 1 renders; wall clock over all frames, no L2 flush in between"},
                 "h2d_bytes_per_step": 12 * 8, "d2h_bytes_per_step": int(traced_px) * 4,
                 "what": ("ct_host_boss_set_camera (host doubles) + render + ct_gpu_readback into a pinned host bitmap, wall clock" if N == 1 else
-                         "per frame: cursor reset + barrier, ct_gpu_set_camera on every rank, ct_gpu_render_shared, sync + barrier, ct_gpu_readback of the "
-                         "whole frame on rank 0 into a pinned host bitmap; wall clock, max over ranks")},
+                         "per frame: rendezvous (one-word all-reduce on the render stream), ct_gpu_set_camera on every rank, ct_gpu_render_shared, sync + barrier, "
+                         "ct_gpu_readback of the whole frame on rank 0 into a pinned host bitmap; wall clock, max over ranks")},
         "gpu_launches": total_launches,
         "clocks": clocks,
         "one_time_ms": {"scene_parse": load_ms, "bvh_build": bvh_ms, "upload_and_alloc": upload_ms},

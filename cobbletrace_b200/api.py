@@ -23,7 +23,7 @@ REFERENCE_MAX_DEPTH = 10   # raythread.cpp:508
 # every symbol include/ct_gpu.h declares
 ABI_SYMBOLS = [
     "ct_gpu_abi_version", "ct_gpu_device_count", "ct_gpu_last_error", "ct_gpu_upload_scene", "ct_gpu_set_camera",
-    "ct_gpu_set_stream", "ct_gpu_render_tile", "ct_gpu_readback", "ct_gpu_readback_hits", "ct_gpu_get_counters",
+    "ct_gpu_set_stream", "ct_gpu_render_tile", "ct_gpu_readback", "ct_gpu_readback_async", "ct_gpu_readback_wait", "ct_gpu_readback_hits", "ct_gpu_get_counters",
     "ct_gpu_last_tile_ms", "ct_gpu_sync", "ct_gpu_throttle", "ct_gpu_kernel_launches", "ct_gpu_last_tile_stages", "ct_gpu_framebuffer", "ct_gpu_gather_rows", "ct_gpu_debug_closest",
     "ct_gpu_debug_primitives", "ct_gpu_debug_filter", "ct_gpu_filter_stats", "ct_gpu_shutdown", "ct_gpu_share_export", "ct_gpu_share_attach", "ct_gpu_share_reset", "ct_gpu_share_partition", "ct_gpu_mark_rows", "ct_gpu_render_shared", "ct_gpu_set_option", "ct_gpu_overflow_stats",
 ]
@@ -97,6 +97,8 @@ def load_library(path: Optional[str] = None):
     L.ct_gpu_set_stream.argtypes = [C.c_int, vp]
     L.ct_gpu_render_tile.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(RayCounters)]
     L.ct_gpu_readback.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int]
+    L.ct_gpu_readback_async.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int]
+    L.ct_gpu_readback_wait.argtypes = [C.c_int]
     L.ct_gpu_readback_hits.argtypes = [C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int]
     L.ct_gpu_get_counters.argtypes = [C.c_int, C.POINTER(RayCounters), C.c_int]
     L.ct_gpu_last_tile_ms.argtypes = [C.c_int, C.POINTER(C.c_float)]
@@ -271,6 +273,15 @@ class GpuRenderer:
         row_end = self.height if row_end is None else row_end
         _check(self.L, self.L.ct_gpu_readback(self.device, _ptr(out), out.shape[1], row_start, row_end))
         return out
+
+    def readback_async(self, out: np.ndarray, row_start: int = 0, row_end: Optional[int] = None) -> None:
+        """ct_gpu_readback_async: `out` (page-locked for a truly asynchronous copy) is filled by readback_wait()."""
+        assert out.dtype == np.uint32 and out.flags.c_contiguous and out.shape[0] >= self.height
+        row_end = self.height if row_end is None else row_end
+        _check(self.L, self.L.ct_gpu_readback_async(self.device, _ptr(out), out.shape[1], row_start, row_end))
+
+    def readback_wait(self) -> None:
+        _check(self.L, self.L.ct_gpu_readback_wait(self.device))
 
     def readback_hits(self):
         H, W = self.height, self.width

@@ -184,6 +184,14 @@ int ct_gpu_render_shared(int device, int y_start, int y_end, ct_ray_counters *co
  * (row 0) -- everything else in dst is left untouched, as the reference leaves it. */
 int ct_gpu_readback(int device, uint32_t *dst, int dst_stride_pixels, int row_start, int row_end);
 
+/* The same copy without stalling the renderer, for loops that render frame k + 1 while frame k travels to the host
+ * (cobbletrace.cpp:114-118 does RayThread, then Blit, every tick).  ct_gpu_readback_async returns at once: in stream order
+ * behind the tiles submitted so far the rows are snapshotted on the device, and a copy stream moves the snapshot into dst
+ * -- which should be page-locked (cudaHostAlloc / cudaHostRegister) and must stay valid until ct_gpu_readback_wait(device)
+ * has returned.  One copy may be in flight per device; a second request queues behind the first. */
+int ct_gpu_readback_async(int device, uint32_t *dst, int dst_stride_pixels, int row_start, int row_end);
+int ct_gpu_readback_wait(int device);
+
 /* Debug/parity export (needs CT_FLAG_KEEP_HITS): primary-ray hit records in framebuffer layout.
  * found: 1/0, or 0xFFFFFFFF where no ray was traced.  Any pointer may be NULL. */
 int ct_gpu_readback_hits(int device, uint32_t *found, uint32_t *index, float *t, int stride_pixels,
