@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
                 tray_setup(r, ray, P.bound, r64);
             }
             float tc; uint32_t pos;
-            bool found = traverse_closest<COUNT>(P, r, active, tc, pos, lc) == kTravHit;   // warp-synchronous
+            bool found = traverse_closest_any<COUNT>(P, r, active, tc, pos, lc) == kTravHit;   // warp-synchronous
             if (!active) continue;
             n_rays++;
             CT_CHECK(slot < P.cap && q < P.cap);
@@ -698,7 +698,7 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
     LocalCount lc; float tc, tc2; uint32_t pos, pos2;
     const bool first_line = r.t == 0.0f;
     bool f = traverse_early_any<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc) == kTravHit;
-    bool f2 = traverse_closest<false>(P, tr, active && !first_line, tc2, pos2, lc) == kTravHit;
+    bool f2 = traverse_closest_any<false>(P, tr, active && !first_line, tc2, pos2, lc) == kTravHit;
     if (!active) return;
     if (!first_line) { f = f2; tc = tc2; pos = pos2; }
     if (found) found[i] = f ? 1u : 0u;

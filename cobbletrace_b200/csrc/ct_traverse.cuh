@@ -465,6 +465,143 @@ CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint
     return result;
 }
 
+// IntersectBVHClosest over the wide tree.  On a nested tree the closest-hit walk is, like the early-exit walks, a matter of
+// its LEAVES only: with ray.t only ever decreasing,  tmin(ancestor) <= tmin(leaf) < ray.t(at the leaf's visit) <= ray.t(at
+// the ancestor's visit),  so the reference visits a leaf exactly when the leaf's own box passes IntersectAABB against the
+// ray.t of that moment -- i.e. the reference's result is that of scanning the leaves in DFS order, testing each leaf's own
+// box against the current ray.t and, where it passes, its triangles in order (bvh.cpp:198-222).  So:
+//   * the walk enumerates candidate leaves in DFS order with the conservative box_maybe against whatever ray.t it holds
+//     at the time -- never smaller than the reference's at that node, because the leaves processed so far all precede the
+//     node in DFS order -- hence a superset of the leaves the reference visits, in the reference's order;
+//   * leaves are deferred to the list and processed in the leaf phase, oldest first: the exact slab test of the leaf's
+//     own box (certified bracket, fp64 when undecided) against the CURRENT ray.t, then its triangles in order with the
+//     reference's update rules.
+// Same hits, same order, same ray.t / tclosest / closestIndex as traverse_closest; rays that do not allow conservative
+// tests (and walks whose stack would overflow) take traverse_closest.  WARP-SYNCHRONOUS.
+// How long the walk runs ahead of the leaf tests decides how stale the ray.t it prunes with is (a closest-hit walk lives on
+// pruning): a lane defers at most kClosestLeaves leaves, and a leaf phase starts as soon as kClosestLanes lanes hold one.
+#ifndef CT_CLOSEST_LEAVES
+#define CT_CLOSEST_LEAVES 1
+#endif
+#ifndef CT_CLOSEST_LANES
+#define CT_CLOSEST_LANES 24
+#endif
+constexpr int kClosestLeaves = CT_CLOSEST_LEAVES, kClosestLanes = CT_CLOSEST_LANES;
+template <bool COUNT>
+CT_DEV int traverse_wide_closest(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    uint2 stk[kWideStack];
+    uint2 leaf[kClosestLeaves];
+    int sp = 0, nleaf = 0;
+    uint32_t cur_ref = 0u, cur_cnt = P.root_cnt;
+    if (P.root_cnt > 0u) cur_ref = P.root_ref;
+    int state = 0;
+    bool overflow = false;
+    tclosest = kFinf;          // raythread.cpp:204
+    closest_pos = kNoPos;
+    if (active) {
+        if (COUNT) lc.box++;
+        state = root_accept(P, r) ? 1 : 0;
+    }
+    while (true) {
+        // ---- walk phase: candidate leaves in DFS order
+        while (__any_sync(kFullMask, (state == 1) & (nleaf < kClosestLeaves)) && __popc(__ballot_sync(kFullMask, nleaf > 0)) < kClosestLanes) {
+            if ((state == 1) & (nleaf < kClosestLeaves)) {
+                if (cur_cnt > 0u) {
+                    leaf[nleaf] = make_uint2(cur_ref, cur_cnt); nleaf++;
+                } else if (sp > kWideStack - kWide) {
+                    overflow = true; state = 0; nleaf = 0; sp = 0;
+                } else {
+                    const float4 *q = reinterpret_cast<const float4 *>(P.wide + cur_ref);
+                    if (COUNT) lc.box += kWide;
+#pragma unroll
+                    for (int e = kWide - 1; e >= 0; e--) {                 // reverse: the first accepted child is popped first
+                        const float4 a = __ldg(q + 2 * e);
+                        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(q + 2 * e + 1));
+                        const float bmin[3] = {a.x, a.y, a.z}, bmax[3] = {a.w, __uint_as_float(b.x), __uint_as_float(b.y)};
+                        if (box_maybe<false>(r, bmin, bmax)) { stk[sp] = make_uint2(b.z, b.w); sp++; }
+                    }
+                }
+                if (state == 1) {
+                    if (sp == 0) state = 0;
+                    else { --sp; const uint2 t = stk[sp]; cur_ref = t.x; cur_cnt = t.y; }
+                }
+            }
+        }
+        // ---- leaf phase: the deferred leaves in order; per iteration a lane either opens its next leaf (the exact test of
+        // the leaf's own box against the current ray.t) or tests one triangle of the open leaf
+        int li = 0;
+        uint32_t tri = 0;
+        bool open = false;
+        while (__any_sync(kFullMask, li < nleaf)) {
+            if (li < nleaf) {
+                const uint2 lf = leaf[li];
+                if (!open) {
+                    const uint32_t code = __ldg(P.tri_parent + lf.x);
+                    bool acc;
+                    if (code == kNoPos) acc = true;                    // the root itself: accepted before the walk (nothing has changed ray.t since)
+                    else {
+                        const uint32_t pid = code >> 1, side = code & 1u;
+                        const float4 *q = reinterpret_cast<const float4 *>(P.pairs32 + pid);
+                        const float4 x = __ldg(q + side), y = __ldg(q + 1 + side);      // left: floats 0..5, right: floats 6..11
+                        float bmin[3], bmax[3];
+                        if (side == 0u) { bmin[0] = x.x; bmin[1] = x.y; bmin[2] = x.z; bmax[0] = x.w; bmax[1] = y.x; bmax[2] = y.y; }
+                        else { bmin[0] = x.z; bmin[1] = x.w; bmin[2] = y.x; bmax[0] = y.y; bmax[1] = y.z; bmax[2] = y.w; }
+                        const BoxBracket bb = box_filter(r, bmin, bmax);
+                        const bool no = bracket_geom_no(bb) | bracket_t_no(bb, r.t), yes = bracket_geom_yes(bb) & bracket_t_yes(bb, r.t);
+                        acc = yes;
+                        if (!(no | yes)) {
+                            if (COUNT) lc.box_exact++;
+                            acc = box_accept(exact_child(P.pairs64, pid, side, r.r64), r.t);
+                        }
+                    }
+                    if (COUNT) lc.box++;
+                    if (acc) { open = true; tri = 0; } else li++;
+                } else {
+                    const uint32_t pos = lf.x + tri;
+                    if (COUNT) lc.tri++;
+                    const TriHit th = leaf_triangle<false, COUNT>(P, r, pos, lc);
+                    if (th.hit) {
+                        if (th.t > kEps) r.t = macro_min(r.t, th.t);               // bvh.cpp:161
+                        if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
+                            closest_pos = pos; tclosest = r.t;
+                        }
+                    }
+                    if (++tri == lf.y) { open = false; li++; }
+                }
+            }
+        }
+        nleaf = 0;
+        if (!__any_sync(kFullMask, state == 1)) break;
+    }
+    if (!active) return kTravMiss;
+    if (overflow) return kTravOverBudget;
+    return r.t != kRayTInit ? kTravHit : kTravMiss;
+}
+
+// The closest-hit walk for every lane's ray: over the wide tree where the ray allows conservative box tests, the binary
+// walk with the reference's verdict at every box otherwise.
+// Measured: the wide closest-hit walk is 7 % faster than the binary one on the dragon-class frame, 8 % slower
+// on the bunny and 30 % slower on scene_import.json (leaves of up to 54 triangles) -- a closest-hit walk wants its leaves
+// tested at once, which is what the binary walk does.  It is therefore an experiment: -DCT_WIDE_CLOSEST=1 switches it on.
+#ifndef CT_WIDE_CLOSEST
+#define CT_WIDE_CLOSEST 0
+#endif
+template <bool COUNT>
+CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    if (!CT_WIDE_CLOSEST) return traverse_closest<COUNT>(P, r, active, tclosest, closest_pos, lc);
+    const bool cons = r.filt & (P.nested != 0u) & (P.wide != nullptr);
+    const float t0 = r.t;
+    int res = traverse_wide_closest<COUNT>(P, r, active & cons, tclosest, closest_pos, lc);
+    const bool binary = active & (!cons | (res == kTravOverBudget));
+    if (__any_sync(kFullMask, binary)) {
+        float tc2; uint32_t pos2;
+        if (binary) r.t = t0;                                          // (a walk given up half way starts over)
+        const int res2 = traverse_closest<COUNT>(P, r, binary, tc2, pos2, lc);
+        if (binary) { res = res2; tclosest = tc2; closest_pos = pos2; }
+    }
+    return res;
+}
+
 // An early-exit walk for every lane's ray: over the wide tree where the ray allows conservative box tests, with the
 // reference's exact verdicts at every box of the binary tree otherwise (zero direction components, non-nested trees).
 template <TraverseMode MODE, bool COUNT>
