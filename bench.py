@@ -360,30 +360,38 @@ def main():
     wflags = workload[6] if len(workload) > 6 else 0
     steps, warm = args.steps, max(args.warmup, 3)
 
-    # ---- scene: generated once per box, parsed + BVH built by every rank (scene is replicated)
+    # ---- scene: generated, parsed and its BVH built ONCE per box (rank 0); the other ranks take a copy out of POSIX shared
+    # memory (ct_host_scene_share / _attach).  The scene itself is replicated on every GPU.
+    shm_name = f"ct_bench_scene_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
+    load_ms = bvh_ms = attach_ms = 0.0
+    hs = None
     if rank == 0:
-        t0 = time.time(); scene_path, n_tri = ensure_scene(kind); gen_s = time.time() - t0
+        scene_path, n_tri = ensure_scene(kind)
+        hs, load_ms = load_host_scene(kind, refl)
+        t0 = time.time(); n_nodes = hs.build_bvh(); bvh_ms = (time.time() - t0) * 1e3
+        if N > 1:
+            t0 = time.time(); hs.share(shm_name); attach_ms = (time.time() - t0) * 1e3
     if N > 1:
         dist.barrier()
-    scene_path, n_tri = ensure_scene(kind)
-    hs, load_ms = load_host_scene(kind, refl)
-    t0 = time.time(); n_nodes = hs.build_bvh(); bvh_ms = (time.time() - t0) * 1e3
+        if rank != 0:
+            t0 = time.time(); hs = host.HostScene.attach(shm_name); attach_ms = (time.time() - t0) * 1e3
+            n_tri, n_nodes = hs.n_tri, hs.build_bvh()                      # (the BVH came with the copy: nothing is built)
+        dist.barrier()
+        if rank == 0:
+            host.HostScene.unshare(shm_name)
     t0 = time.time()
     stream = torch.cuda.Stream(device=dev)
-    flat0 = hs.to_flat(with_bvh=False)
-    cam_pos, cam_rot = np.array(flat0.cam_pos), np.array(flat0.cam_rot)
-    boss = shared = None
-    if N == 1:
-        # the reference-facing host path: C++ boss (RayThread's boss half) driving one GPU
-        boss = host.Boss(hs, W, H, devices=(dev,), max_depth=depth, tile_rows=args.tile_rows, flags=wflags)
-        boss.set_stream(stream.cuda_stream)
-        gpu = api.GpuRenderer(dev)
-        gpu.width, gpu.height = W, H
-    else:
-        # one process per GPU, one shared frame: chunks stolen from a cursor on GPU 0 over NVLink, pixels stored
+    cam_pos, cam_rot = hs.camera()
+    n_lights = hs.n_lights
+    # the reference-facing host path: the C++ boss (RayThread's boss half) uploads the scene arrays as they are
+    boss = host.Boss(hs, W, H, devices=(dev,), max_depth=depth, tile_rows=args.tile_rows, flags=wflags)
+    boss.set_stream(stream.cuda_stream)
+    gpu = api.GpuRenderer(dev)                                              # the same device state, for the calls the boss does not wrap
+    gpu.width, gpu.height = W, H
+    shared = None
+    if N > 1:
+        # one process per GPU, one shared frame: chunks dealt / stolen from a cursor on GPU 0 over NVLink, pixels stored
         # straight into GPU 0's framebuffer (multi.SharedFrame / ct_gpu_render_shared)
-        gpu = api.GpuRenderer(dev).upload(hs.to_flat(with_bvh=True), W, H, max_depth=depth, flags=wflags)
-        gpu.set_stream(stream.cuda_stream)
         shared = multi.SharedFrame(gpu, root=0, stream=stream)
     upload_ms = (time.time() - t0) * 1e3
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")      # > 126 MB L2
@@ -490,7 +498,9 @@ def main():
     rays_vec = torch.tensor([st["rays_primary"], st["rays_shadow"], st["rays_reflection"], launches], dtype=torch.float64, device=f"cuda:{dev}")
     t_dev = torch.tensor(dev_ms, dtype=torch.float64, device=f"cuda:{dev}")
     t_e2e = torch.tensor(e2e_wall, dtype=torch.float64, device=f"cuda:{dev}")
+    t_once = torch.tensor([attach_ms + upload_ms if rank != 0 else 0.0], dtype=torch.float64, device=f"cuda:{dev}")
     if N > 1:
+        dist.all_reduce(t_once, op=dist.ReduceOp.MAX)
         dist.all_reduce(rays_vec, op=dist.ReduceOp.SUM)
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -499,7 +509,7 @@ def main():
     ms_per_step = float(t_dev.mean())
     e2e_ms = float(t_e2e.mean())
     if rank != 0:
-        shared.close(); gpu.shutdown()
+        shared.close(); boss.close()
         if N > 1:
             dist.barrier(); dist.destroy_process_group()
         return 0
@@ -511,7 +521,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64/f32 mixed (the reference's arithmetic, reproduced bit-exactly)",
         "data": data_note(kind),
-        "config": workload_config(args.workload, N, n_tri, n_nodes, int(flat0.n_lights)),
+        "config": workload_config(args.workload, N, n_tri, n_nodes, int(n_lights)),
         "method": {"timing": "CUDA events on the launching stream around each frame's kernels" + ("; max over ranks per step (pixels land in GPU 0's framebuffer inside those kernels)" if N > 1 else ""),
                    "tiles_per_frame": st["tiles_total"],
                    "parallelism": (f"{N} GPUs, one process each, scene replicated: 32-pixel chunks, 7/8 dealt round-robin and 1/8 stolen from one cursor on GPU 0 (atomics over NVLink), "
@@ -531,7 +541,9 @@ def main():
                          "ct_gpu_readback of the whole frame on rank 0 into a pinned host bitmap; wall clock, max over ranks")},
         "gpu_launches": total_launches,
         "clocks": clocks,
-        "one_time_ms": {"scene_parse": load_ms, "bvh_build": bvh_ms, "upload_and_alloc": upload_ms},
+        "one_time_ms": {"scene_parse": load_ms, "bvh_build": bvh_ms, "share_or_attach": attach_ms, "upload_and_alloc": upload_ms,
+                        "other_ranks_max_total": float(t_once[0]),
+                        "note": "rank 0's figures; at N > 1 only rank 0 parses and builds, the other ranks copy the scene out of shared memory (max over ranks below)"},
     }
 
     # ---- the pixels: the bitmap of the last end-to-end frame (read back from GPU 0, every rank's share in it) against the
@@ -609,7 +621,7 @@ def main():
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(workload, fs, counts)
     else:
-        shared.close(); gpu.shutdown()
+        shared.close(); boss.close()
     line["frame_matches_oracle"] = bool(frame_ok) if (want_hash or "matches_oracle" in line["frame_check"]) else None
     print(json.dumps(line), file=real_stdout, flush=True)
     if N > 1:

@@ -5,6 +5,13 @@
 #include <stdexcept>
 #include <string>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <cerrno>
+#include <thread>
+
 #include "ct_scene.hpp"
 #include "ct_tiles.hpp"
 
@@ -63,6 +70,95 @@ ct_host_scene *ct_host_scene_from_arrays(uint32_t n_tri, const double *tri, cons
     if (cam_pos) s->cam_pos = {cam_pos[0], cam_pos[1], cam_pos[2]};
     if (cam_rot) memcpy(s->cam_rot, cam_rot, sizeof s->cam_rot);
     return reinterpret_cast<ct_host_scene *>(s);
+}
+
+// ---- one parse + one BVH build per box: the scene in POSIX shared memory for the other processes of a multi-GPU job ----
+namespace {
+struct ShmHeader {
+    uint64_t magic, total_bytes;
+    uint32_t n_tri, n_lights, n_nodes, n_spheres;
+    double cam_pos[3], cam_rot[9];
+    ct_host_settings settings;
+    uint64_t off_tris, off_mats, off_lights, off_nodes, off_index;
+};
+constexpr uint64_t kShmMagic = 0x43545343454e4531ull;      // "CTSCENE1"
+size_t align64(size_t v) { return (v + 63u) & ~(size_t)63u; }
+std::string shm_path(const char *name) { return std::string("/") + name; }
+// big copies by a few threads (a single memcpy of 150 MB is bound by one core's page faults)
+void copy_parallel(void *dst, const void *src, size_t bytes) {
+    const int nt = bytes > (8u << 20) ? 4 : 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([=] {
+            const size_t a = bytes * t / nt, b = bytes * (t + 1) / nt;
+            memcpy(static_cast<char *>(dst) + a, static_cast<const char *>(src) + a, b - a);
+        });
+    for (auto &t : th) t.join();
+}
+}  // namespace
+
+int ct_host_scene_share(const ct_host_scene *scene, const char *name) {
+    if (!scene || !name || !name[0]) { g_err = "ct_host_scene_share: NULL scene or name"; return -1; }
+    const cth::Scene &s = *S(scene);
+    ShmHeader h{};
+    h.magic = kShmMagic;
+    h.n_tri = (uint32_t)s.tris.size(); h.n_lights = (uint32_t)s.lights.size(); h.n_nodes = (uint32_t)s.nodes.size(); h.n_spheres = s.n_spheres;
+    h.cam_pos[0] = s.cam_pos.x; h.cam_pos[1] = s.cam_pos.y; h.cam_pos[2] = s.cam_pos.z;
+    memcpy(h.cam_rot, s.cam_rot, sizeof h.cam_rot);
+    h.settings = s.settings;
+    size_t off = align64(sizeof h);
+    h.off_tris = off; off = align64(off + s.tris.size() * sizeof(cth::Triangle));
+    h.off_mats = off; off = align64(off + s.mats.size() * sizeof(ct_material));
+    h.off_lights = off; off = align64(off + s.lights.size() * sizeof(ct_light));
+    h.off_nodes = off; off = align64(off + s.nodes.size() * sizeof(ct_bvh_node));
+    h.off_index = off; off = align64(off + s.tri_index.size() * sizeof(uint32_t));
+    h.total_bytes = off;
+    shm_unlink(shm_path(name).c_str());
+    const int fd = shm_open(shm_path(name).c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) { g_err = std::string("shm_open(") + name + "): " + strerror(errno); return -1; }
+    if (ftruncate(fd, (off_t)off) != 0) { g_err = std::string("ftruncate: ") + strerror(errno); close(fd); shm_unlink(shm_path(name).c_str()); return -1; }
+    char *m = static_cast<char *>(mmap(nullptr, off, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0));
+    close(fd);
+    if (m == MAP_FAILED) { g_err = std::string("mmap: ") + strerror(errno); shm_unlink(shm_path(name).c_str()); return -1; }
+    copy_parallel(m + h.off_tris, s.tris.data(), s.tris.size() * sizeof(cth::Triangle));
+    memcpy(m + h.off_mats, s.mats.data(), s.mats.size() * sizeof(ct_material));
+    memcpy(m + h.off_lights, s.lights.data(), s.lights.size() * sizeof(ct_light));
+    copy_parallel(m + h.off_nodes, s.nodes.data(), s.nodes.size() * sizeof(ct_bvh_node));
+    memcpy(m + h.off_index, s.tri_index.data(), s.tri_index.size() * sizeof(uint32_t));
+    memcpy(m, &h, sizeof h);                             // the header last: an importer that sees the magic sees everything
+    munmap(m, off);
+    return 0;
+}
+
+ct_host_scene *ct_host_scene_attach(const char *name) {
+    if (!name || !name[0]) { g_err = "ct_host_scene_attach: NULL name"; return nullptr; }
+    const int fd = shm_open(shm_path(name).c_str(), O_RDONLY, 0);
+    if (fd < 0) { g_err = std::string("shm_open(") + name + "): " + strerror(errno); return nullptr; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(ShmHeader)) { g_err = "shared scene is truncated"; close(fd); return nullptr; }
+    const char *m = static_cast<const char *>(mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_SHARED, fd, 0));
+    close(fd);
+    if (m == MAP_FAILED) { g_err = std::string("mmap: ") + strerror(errno); return nullptr; }
+    ShmHeader h;
+    memcpy(&h, m, sizeof h);
+    if (h.magic != kShmMagic || h.total_bytes > (uint64_t)st.st_size) { g_err = "shared scene has a bad header"; munmap(const_cast<char *>(m), (size_t)st.st_size); return nullptr; }
+    auto *s = new cth::Scene();
+    s->tris.resize(h.n_tri); s->mats.resize(h.n_tri); s->lights.resize(h.n_lights); s->nodes.resize(h.n_nodes); s->tri_index.resize(h.n_nodes ? h.n_tri : 0);
+    copy_parallel(static_cast<void *>(s->tris.data()), m + h.off_tris, (size_t)h.n_tri * sizeof(cth::Triangle));
+    memcpy(s->mats.data(), m + h.off_mats, (size_t)h.n_tri * sizeof(ct_material));
+    memcpy(s->lights.data(), m + h.off_lights, (size_t)h.n_lights * sizeof(ct_light));
+    copy_parallel(static_cast<void *>(s->nodes.data()), m + h.off_nodes, (size_t)h.n_nodes * sizeof(ct_bvh_node));
+    memcpy(s->tri_index.data(), m + h.off_index, s->tri_index.size() * sizeof(uint32_t));
+    s->cam_pos = {h.cam_pos[0], h.cam_pos[1], h.cam_pos[2]};
+    memcpy(s->cam_rot, h.cam_rot, sizeof h.cam_rot);
+    s->settings = h.settings; s->n_spheres = h.n_spheres;
+    munmap(const_cast<char *>(m), (size_t)st.st_size);
+    return reinterpret_cast<ct_host_scene *>(s);
+}
+
+int ct_host_scene_unshare(const char *name) {
+    if (!name || !name[0]) return -1;
+    return shm_unlink(shm_path(name).c_str()) == 0 ? 0 : -1;
 }
 
 void ct_host_scene_free(ct_host_scene *s) { delete S(s); }

@@ -19,6 +19,7 @@ HOST_LIB = os.path.join(PKG, "libct_host.so")
 
 ABI_SYMBOLS = [
     "ct_host_last_error", "ct_host_scene_load", "ct_host_scene_from_arrays", "ct_host_scene_free",
+    "ct_host_scene_share", "ct_host_scene_attach", "ct_host_scene_unshare",
     "ct_host_scene_triangle_count", "ct_host_scene_sphere_count", "ct_host_scene_triangles", "ct_host_scene_materials",
     "ct_host_scene_light_count", "ct_host_scene_lights", "ct_host_scene_camera", "ct_host_scene_set_camera",
     "ct_host_scene_settings", "ct_host_scene_set_reflection", "ct_host_build_bvh", "ct_host_scene_nodes",
@@ -64,6 +65,9 @@ def load_library():
         L.ct_host_scene_from_arrays.restype = vp
         L.ct_host_scene_from_arrays.argtypes = [C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp]
         L.ct_host_scene_free.argtypes = [vp]
+        L.ct_host_scene_share.argtypes = [vp, C.c_char_p]
+        L.ct_host_scene_attach.restype = vp; L.ct_host_scene_attach.argtypes = [C.c_char_p]
+        L.ct_host_scene_unshare.argtypes = [C.c_char_p]
         for f in ("ct_host_scene_triangle_count", "ct_host_scene_sphere_count", "ct_host_scene_light_count"):
             getattr(L, f).restype = C.c_uint32; getattr(L, f).argtypes = [vp]
         for f in ("ct_host_scene_triangles", "ct_host_scene_materials", "ct_host_scene_lights", "ct_host_scene_tri_indexes"):
@@ -156,6 +160,24 @@ class HostScene:
                 raise RuntimeError("ct_host_scene_set_bvh: " + _err(L))
         return s
 
+    def share(self, name: str) -> None:
+        """Scene + BVH as built into the POSIX shared-memory object `name` (ct_host_scene_share): the other processes of a
+        multi-GPU job attach() instead of parsing and building again."""
+        if self.L.ct_host_scene_share(self.h, name.encode()) < 0:
+            raise RuntimeError("ct_host_scene_share: " + _err(self.L))
+
+    @classmethod
+    def attach(cls, name: str) -> "HostScene":
+        L = load_library()
+        h = L.ct_host_scene_attach(name.encode())
+        if not h:
+            raise RuntimeError("ct_host_scene_attach: " + _err(L))
+        return cls(h)
+
+    @staticmethod
+    def unshare(name: str) -> None:
+        load_library().ct_host_scene_unshare(name.encode())
+
     def __del__(self):
         try:
             if self.h:
@@ -182,6 +204,16 @@ class HostScene:
         if self.L.ct_host_scene_render_flags(self.h, C.byref(f)) < 0:
             raise RuntimeError("ct_host_scene_render_flags: " + _err(self.L))
         return int(f.value)
+
+    @property
+    def n_lights(self) -> int:
+        return int(self.L.ct_host_scene_light_count(self.h))
+
+    def camera(self):
+        """(position[3], rotation[9]) as float64 arrays (ct_host_scene_camera)."""
+        pos, rot = np.zeros(3), np.zeros(9)
+        self.L.ct_host_scene_camera(self.h, pos.ctypes.data_as(C.c_void_p), rot.ctypes.data_as(C.c_void_p))
+        return pos, rot
 
     def set_reflection(self, reflection: float):
         self.L.ct_host_scene_set_reflection(self.h, reflection)

@@ -51,6 +51,14 @@ ct_host_scene *ct_host_scene_from_arrays(uint32_t n_tri, const double *tri, cons
                                          const double cam_pos[3], const double cam_rot[9]);
 void ct_host_scene_free(ct_host_scene *s);
 
+/* One parse and one BVH build per box.  In a job with one process per GPU the scene is replicated on every GPU but need
+ * not be parsed and built by every process: one of them calls ct_host_scene_share (scene + BVH as built go into the POSIX
+ * shared-memory object `name`), the others ct_host_scene_attach (a private copy of those arrays -- a memcpy instead of
+ * ParseSceneFile + BuildBVH), and the first one ct_host_scene_unshare once everybody has attached.  0 / non-NULL on success. */
+int ct_host_scene_share(const ct_host_scene *s, const char *name);
+ct_host_scene *ct_host_scene_attach(const char *name);
+int ct_host_scene_unshare(const char *name);
+
 uint32_t ct_host_scene_triangle_count(const ct_host_scene *s);
 uint32_t ct_host_scene_sphere_count(const ct_host_scene *s);      /* parsed but ignored by the tracer (raythread.cpp:208) */
 const double *ct_host_scene_triangles(const ct_host_scene *s);    /* n_tri x 9, GetSceneTriangles order */

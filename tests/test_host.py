@@ -322,3 +322,23 @@ def test_boss_refuses_subsampling_on_several_devices(golden):
         host.Boss(hs, 64, 64, devices=(0, 1), flags=api.CT_FLAG_SUBSAMPLING)
     with pytest.raises(RuntimeError, match="whole frame on one device"):
         host.Boss(hs, 64, 64, devices=(0,), flags=api.CT_FLAG_SUBSAMPLING, shared_counter="ct_test_subsample", rank=0, world_size=2)
+
+
+def test_scene_shared_through_posix_shm_is_the_same_scene(golden):
+    """ct_host_scene_share / _attach (one parse + one BVH build per box in a multi-GPU job): the attached copy has the
+    shared scene's triangles, materials, lights, camera and BVH, bit for bit."""
+    from cobbletrace_b200 import host
+    from conftest import load_golden_scene
+    fs = load_golden_scene("scene_import_bunny", golden).with_reflection(0.25)
+    a = host.HostScene.from_flat(fs)
+    name = f"ct_test_scene_{os.getpid()}"
+    a.share(name)
+    try:
+        b = host.HostScene.attach(name)
+    finally:
+        host.HostScene.unshare(name)
+    fa, fb = a.to_flat(with_bvh=True), b.to_flat(with_bvh=True)
+    assert fa.geometry_digest() == fb.geometry_digest() and fa.bvh_digest() == fb.bvh_digest() == golden["scenes"]["scene_import_bunny"]["bvh_sha256"]
+    assert np.array_equal(fa.mat_reflection, fb.mat_reflection) and np.array_equal(fa.cam_rot, fb.cam_rot) and np.array_equal(fa.light_pos, fb.light_pos)
+    with pytest.raises(RuntimeError, match="shm_open"):
+        host.HostScene.attach(name)                          # unshared: gone
