@@ -578,6 +578,11 @@ def main():
         tot = {k: sum(v) / n_frames for k, v in per.items()}
         n_launch = {k: len(v) // n_frames for k, v in per.items()}
         prof.shutdown()
+        # the GPU's OWN walk: box / triangle tests it actually performed for this frame (a counted frame, untimed)
+        cnt = api.GpuRenderer(dev).upload(fs, W, H, max_depth=depth, flags=api.CT_FLAG_COUNT_TESTS)
+        own = cnt.render_tile(counters=True)
+        own_exact = cnt.filter_stats()
+        cnt.shutdown()
         alg = {   # algorithmic bytes per frame of each kernel type: 32 B per node visit + 48 B per triangle test of the
                   # REFERENCE's DFS on this frame, + 4 B per stored pixel.  k_shadow owns the shadow rays
                   # (the rays it parks are finished by k_overflow, whose time is charged to it below)
@@ -602,6 +607,31 @@ def main():
         except Exception:
             pass
         frame_alg = sum(alg.values())
+        # two yardsticks that do not saturate (the section-8d figure charges an any-hit walk with the reference's full
+        # closest-hit DFS): (1) the same 32 B / 48 B per test, but for the tests THIS implementation performed;
+        own_bytes = 32 * own["box_tests"] + 48 * own["tri_tests"] + 4 * traced_px
+        own_walk = {"box_tests": own["box_tests"], "tri_tests": own["tri_tests"], "box_tests_fp64": own_exact[0], "tri_tests_fp64": own_exact[1],
+                    "bytes": own_bytes, "achieved_GBps": own_bytes / (ms_per_step * 1e-3) / 1e9, "frac": own_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                    "vs_reference_dfs": {"box": own["box_tests"] / max(counts["box_tests"], 1), "tri": own["tri_tests"] / max(counts["tri_tests"], 1)},
+                    "note": "32 B per box test + 48 B per triangle test the GPU itself performed (CT_FLAG_COUNT_TESTS frame) + 4 B per pixel, over the timed frame"}
+        # (2) issue-slot utilisation: warp instructions per frame (ncu capture of the same workload, profiles/issue.json) over
+        # the issue slots the kernels' measured time offers (SMs x 4 schedulers x SM clock)
+        issue = None
+        try:
+            prof_issue = json.load(open(os.path.join(ROOT, "profiles", "issue.json")))[args.workload]
+            sm_hz = (clocks.get("sm_mhz") or prof_issue.get("sm_mhz_at_capture") or 1965.0) * 1e6
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            per_k = {}
+            for k, v in prof_issue["warp_instructions_per_frame"].items():
+                t_ms = tot_k.get(k) if k in ("shadow", "bounce") else tot.get(k)
+                if t_ms:
+                    per_k[k] = {"warp_instructions": v, "ms": t_ms, "issue_utilisation": v / (n_sm * 4 * sm_hz * t_ms * 1e-3)}
+            all_inst = sum(prof_issue["warp_instructions_per_frame"].values())
+            issue = {"per_kernel": per_k, "frame": {"warp_instructions": all_inst, "issue_utilisation": all_inst / (n_sm * 4 * sm_hz * ms_per_step * 1e-3)},
+                     "lanes_per_instruction": prof_issue.get("lanes_per_instruction"), "source": prof_issue.get("source"),
+                     "note": "warp instructions from the ncu capture (static, same workload and build), times measured live: 1.0 = every scheduler issues every cycle"}
+        except Exception:
+            pass
         line["roofline"] = {
             "bound": "hbm", "kernel": f"k_{dominant}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
@@ -612,6 +642,8 @@ def main():
                             "frac": frame_alg / (ms_per_step * 1e-3) / 1e9 / peak,
                             "bytes_per_ray": frame_alg / (counts["rays_primary"] + counts["rays_shadow"] + counts["rays_reflection"])},
             "reference_dfs_counts": {k: counts[k] for k in counts if k.startswith(("box_tests", "tri_tests"))},
+            "own_walk": own_walk,
+            "issue": issue,
             "note": ("achieved = algorithmic bytes of the REFERENCE's walk (32 B per box test + 48 B per triangle test of its closest-hit DFS, "
                      "SURVEY 8d) / kernel time: a throughput normalisation, not traffic.  The hot set (fp32 child pairs + fp32 triangles, 76 MB) is "
                      "L2-resident and a shadow ray needs fewer tests than the reference's full closest-hit walk, so the figure can exceed the HBM peak; "

@@ -108,9 +108,55 @@ def source(rep, top=40):
             print(f"      {i:5d} {r[ix['Source']].strip()[:64]:64s} {int(r[ix['# Samples']]) / tot * 100:5.1f}% x{r[ix['Instructions Executed']]:>9s} thr={r[ix['Avg. Threads Executed']]:>3s} {st}")
 
 
+def frame_metrics(path, workload="dragon4k", out=None):
+    """gpurun_out/X_frame_metrics.csv (one frame's kernels, `ncu --metrics ... --csv`) -> per-kernel table on stdout and, with
+    `out`, the entry of profiles/issue.json that bench.py's roofline.issue reads."""
+    import json
+    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
+    ix = {h: i for i, h in enumerate(rows[0])}
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        k = (r[ix["ID"]], short(r[ix["Kernel Name"]]))
+        per.setdefault(k, {})[r[ix["Metric Name"]]] = (float(r[ix["Metric Value"]].replace(",", "")), r[ix["Metric Unit"]])
+    agg = collections.OrderedDict()
+    print(f"# {path}: one frame of {workload}, kernel by kernel (ncu, serialised)")
+    for (kid, name), m in per.items():
+        inst = m["smsp__inst_executed.sum"][0]
+        lanes = m["smsp__thread_inst_executed_per_inst_executed.ratio"][0]
+        t, unit = m["gpu__time_duration.sum"]
+        ms = t * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(unit, 1.0)
+        def val(key, scale=1.0):
+            return m[key][0] * scale if key in m else float("nan")
+        dram = (val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+        du = m.get("dram__bytes_read.sum", (0, "byte"))[1]
+        dram_mb = dram * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(du, 1e-6)
+        print(f"{name:28s} {ms:8.3f} ms  warp-instr {inst / 1e6:9.1f} M  lanes/instr {lanes:5.2f}  issue {val('smsp__issue_active.avg.pct_of_peak_sustained_active'):5.1f} %"
+              f"  L1 hit {val('l1tex__t_sector_hit_rate.pct'):5.1f} %  L2 hit {val('lts__t_sector_hit_rate.pct'):5.1f} %  DRAM {dram_mb:7.1f} MB")
+        key = name.split("<")[0].replace("k_", "")
+        if key.startswith("overflow"):
+            key = "overflow_shadow" if "<1" in name or "(TraverseMode)1" in name else "overflow_bounce"
+        a = agg.setdefault(key, {"inst": 0.0, "lane_inst": 0.0, "ms": 0.0})
+        a["inst"] += inst; a["lane_inst"] += inst * lanes; a["ms"] += ms
+    tot_i = sum(a["inst"] for a in agg.values()); tot_l = sum(a["lane_inst"] for a in agg.values())
+    print("# per kernel type: " + "  ".join(f"{k}: {a['inst'] / 1e6:.0f} M @ {a['lane_inst'] / a['inst']:.1f} lanes" for k, a in agg.items()))
+    print(f"# frame: {tot_i / 1e6:.0f} M warp instructions, {tot_l / tot_i:.2f} lanes per instruction")
+    if out:
+        try:
+            doc = json.load(open(out))
+        except Exception:
+            doc = {}
+        doc[workload] = {"warp_instructions_per_frame": {k: a["inst"] for k, a in agg.items()},
+                         "lanes_per_instruction": {k: a["lane_inst"] / a["inst"] for k, a in agg.items()},
+                         "source": os.path.basename(path) + " (ncu --metrics smsp__inst_executed.sum, one frame)"}
+        json.dump(doc, open(out, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
+    import os
     mode, path = sys.argv[1], sys.argv[2]
-    if mode == "launches":
+    if mode == "frame":
+        frame_metrics(path, *(sys.argv[3:5]))
+    elif mode == "launches":
         launches(path)
     elif mode == "raw":
         raw(path)
