@@ -184,55 +184,91 @@ CT_DEV bool next_chunk(const Params &P, uint32_t n_chunks, bool &dealt_left, uin
     return false;
 }
 
+// Lanes of `idle` in rank order: the r-th idle lane gets item r.
+CT_DEV uint32_t idle_rank(uint32_t idle) { return __popc(idle & ((1u << (threadIdx.x & 31u)) - 1u)); }
+
+// k_primary's job (traverse_closest_refill): the warp takes chunks from the tile's cursor (next_chunk) and hands the slots
+// of its current chunk to lanes as they fall idle.
+struct PrimaryJob {
+    uint32_t n_chunks, chunk;
+    bool dealt_left;                                        // lane 0's view of this device's dealt share
+    uint32_t pend_slot = 0, pend_q = 0, pend_left = 0;      // warp-uniform: what is left of the chunk being handed out
+    uint32_t slot = 0, q = 0; int fbi = -1;                 // this lane's ray
+    uint32_t n_rays = 0;
+
+    CT_DEV bool refill(const Params &P, uint32_t idle, bool &got, TRay &r, double *r64) {
+        const uint32_t lane = threadIdx.x & 31u;
+        if (pend_left == 0u) {
+            unsigned long long base = ~0ull;
+            uint32_t mine = 0;
+            if (lane == 0) {
+                uint32_t idx;
+                if (next_chunk(P, n_chunks, dealt_left, idx)) {
+                    base = (unsigned long long)idx << P.chunk_shift;
+                    mine = atomicAdd(&P.sched->own_count, 1u);
+                    CT_CHECK(mine <= (P.cap >> kChunkLocalShift));
+                    P.own_chunks[mine] = idx;
+                }
+            }
+            base = __shfl_sync(kFullMask, base, 0);
+            mine = __shfl_sync(kFullMask, mine, 0);
+            if (base == ~0ull) return false;
+            pend_slot = (uint32_t)base; pend_q = mine << P.chunk_shift; pend_left = chunk;
+        }
+        const uint32_t take = min((uint32_t)__popc(idle), pend_left), rank = idle_rank(idle);
+        if (((idle >> lane) & 1u) && rank < take) {
+            slot = pend_slot + rank; q = pend_q + rank;     // q: this path's depth-0 number on this device
+            int x, y;
+            if (slot < P.n_slots && slot_pixel(P, slot, x, y, fbi)) {
+                const Ray ray = primary_ray(P, slot, x, y);
+                tray_setup(r, ray, P.bound, r64);
+                got = true;
+            }
+        }
+        pend_slot += take; pend_q += take; pend_left -= take;
+        return true;
+    }
+    CT_DEV void finish(const Params &P, bool found, float tc, uint32_t pos) {
+        n_rays++;
+        CT_CHECK(slot < P.cap && q < P.cap);
+        P.hit0_t[slot] = tc;
+        P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
+        if (found) clear_occ(P, q);
+        if (P.dbg_found && fbi >= 0) {
+            P.dbg_found[fbi] = found ? 1u : 0u;
+            P.dbg_index[fbi] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
+            P.dbg_t[fbi] = tc;
+        }
+    }
+};
+
+// Primary rays.  Persistent warps take chunks of 32 (or 64) slots from the tile's cursor (next_chunk) and remember which
+// chunks they took: the later stages of this device work on exactly those.  By default a warp walks the 32 rays of a
+// chunk together (one 8x4 pixel block: neighbouring rays visit the same nodes); -DCT_REFILL_T=n (n = 1..32) selects
+// traverse_closest_refill instead, which refills idle lanes from the next chunk -- measured SLOWER at every threshold
+// (1.45 ms -> 1.86 / 2.12 / 2.29 ms for n = 16 / 8 / 4), the mixed warps lose the block's coherence.
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __grid_constant__ Params P) {
     LocalCount lc;
-    uint32_t n_rays = 0;
-    const uint32_t lane = threadIdx.x & 31u, chunk = 1u << P.chunk_shift;
-    const uint32_t n_chunks = (P.n_slots + chunk - 1u) >> P.chunk_shift;
-    bool dealt_left = P.part_count > 1u && P.static_eighths > 0u;     // lane 0's view of this device's dealt share
+    PrimaryJob job;
+    job.chunk = 1u << P.chunk_shift;
+    job.n_chunks = (P.n_slots + job.chunk - 1u) >> P.chunk_shift;
+    job.dealt_left = P.part_count > 1u && P.static_eighths > 0u;
+#if CT_REFILL_T > 0
+    traverse_closest_refill<COUNT>(P, job, lc);
+#else
+    const uint32_t all = kFullMask;
     while (true) {
-        unsigned long long base = ~0ull;
-        uint32_t mine = 0;
-        if (lane == 0) {
-            uint32_t idx;
-            if (next_chunk(P, n_chunks, dealt_left, idx)) {
-                base = (unsigned long long)idx << P.chunk_shift;
-                mine = atomicAdd(&P.sched->own_count, 1u);
-                CT_CHECK(mine <= (P.cap >> kChunkLocalShift));
-                P.own_chunks[mine] = idx;
-            }
-        }
-        base = __shfl_sync(kFullMask, base, 0);
-        mine = __shfl_sync(kFullMask, mine, 0);
-        if (base == ~0ull) break;
-        for (uint32_t sub = 0; sub < chunk; sub += 32u) {
-            const uint32_t slot = (uint32_t)base + sub + lane;
-            const uint32_t q = (mine << P.chunk_shift) + sub + lane;   // this path's depth-0 number on this device
-            int x, y, fbi;
-            const bool active = slot < P.n_slots && slot_pixel(P, slot, x, y, fbi);
-            double r64[kRay64];
-            TRay r;
-            if (active) {
-                Ray ray = primary_ray(P, slot, x, y);
-                tray_setup(r, ray, P.bound, r64);
-            }
-            float tc; uint32_t pos;
-            bool found = traverse_closest_any<COUNT>(P, r, active, tc, pos, lc) == kTravHit;   // warp-synchronous
-            if (!active) continue;
-            n_rays++;
-            CT_CHECK(slot < P.cap && q < P.cap);
-            P.hit0_t[slot] = tc;
-            P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
-            if (found) clear_occ(P, q);
-            if (P.dbg_found && fbi >= 0) {
-                P.dbg_found[fbi] = found ? 1u : 0u;
-                P.dbg_index[fbi] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
-                P.dbg_t[fbi] = tc;
-            }
-        }
+        bool got = false;
+        double r64[kRay64];
+        TRay r;
+        if (!job.refill(P, all, got, r, r64)) break;          // a whole chunk's worth of slots: one per lane
+        float tc; uint32_t pos;
+        const bool found = traverse_closest_any<COUNT>(P, r, got, tc, pos, lc) == kTravHit;   // warp-synchronous
+        if (got) job.finish(P, found, tc, pos);
     }
-    warp_add(&P.tot->rays_primary, n_rays);
+#endif
+    warp_add(&P.tot->rays_primary, job.n_rays);
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
 

@@ -247,6 +247,98 @@ CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclose
     return r.t != kRayTInit ? kTravHit : kTravMiss;
 }
 
+// The same walk with LANE REFILL (north_star: "__ballot_sync / __shfl_sync compaction for ray regrouping"): the warp
+// does not wait for the slowest ray of a group of 32.  A lane whose walk has ended hands its result to the job and falls
+// idle; as soon as kRefillLanes lanes are idle (one ballot per iteration) the job deals new rays to exactly those lanes --
+// ranked with a prefix popcount over the idle mask -- whose set-up then runs for that many lanes at once.  Per ray nothing
+// changes (same visits, same order, same arithmetic); what changes is which rays share a warp at any moment.  Besides the
+// fuller warps this removes the per-group barrier, so a kernel ends with its longest single WALK, not its slowest group.
+// A JOB supplies the rays and takes the results:
+//     bool refill(P, idle_mask, got, r, r64)   warp-uniform.  May hand a ray to any lane of idle_mask: sets got and fills
+//                                              r / r64 (tray_setup).  Returns false once the source is exhausted.
+//     void finish(P, found, tc, pos)           per lane, when its walk has ended.
+#ifndef CT_REFILL_T
+#define CT_REFILL_T 0                 // 0: off (k_primary walks whole chunks); 1..32: idle lanes that trigger a refill
+#endif
+constexpr int kRefillLanes = CT_REFILL_T > 0 ? CT_REFILL_T : 32;
+template <bool COUNT, class Job>
+CT_DEV void traverse_closest_refill(const Params &P, Job &job, LocalCount &lc) {
+    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax], stk_src[kStackMax];
+    float stk_lo[kStackMax], stk_hi[kStackMax];
+    int sp = 0;
+    float tclosest = kFinf;
+    uint32_t closest_pos = kNoPos, cur_ref = 0u, cur_cnt = 0u;
+    bool live = false;                                        // this lane holds a ray whose walk is not over
+    double r64[kRay64];
+    TRay r;
+    r.t = 0.0f; r.filt = r.tfilt = false; r.r64 = r64;
+    bool more = true;                                         // warp-uniform: the source may still hold rays
+    while (true) {
+        const uint32_t idle = __ballot_sync(kFullMask, !live);
+        if (more && __popc(idle) >= kRefillLanes) {
+            bool got = false;
+            more = job.refill(P, idle, got, r, r64);
+            if (got) {
+                sp = 0; tclosest = kFinf; closest_pos = kNoPos;                // raythread.cpp:204-205
+                cur_ref = P.root_ref; cur_cnt = P.root_cnt;
+                if (COUNT) lc.box++;
+                live = root_accept(P, r);
+                if (!live) job.finish(P, false, tclosest, closest_pos);      // missed the root box: found = false
+            }
+            continue;
+        }
+        if (idle == kFullMask) break;
+        if (live) {
+            bool need_pop = true;
+            if (cur_cnt > 0) {
+                for (uint32_t i = 0; i < cur_cnt; i++) {
+                    uint32_t pos = cur_ref + i;
+                    if (COUNT) lc.tri++;
+                    const TriHit th = leaf_triangle<false, COUNT>(P, r, pos, lc);
+                    if (th.hit) {
+                        if (th.t > kEps) r.t = macro_min(r.t, th.t);               // bvh.cpp:161
+                        if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
+                            closest_pos = pos; tclosest = r.t;
+                        }
+                    }
+                }
+            } else {
+                CT_CHECK(cur_ref < P.n_pairs);
+                DevPair32 pr;
+                load_pair32(P.pairs32, cur_ref, pr);
+                if (COUNT) lc.box += 2;
+                bool hit_l, hit_r; float r_lo, r_hi;
+                pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
+                if (hit_l & hit_r) {
+                    CT_CHECK(sp < kStackMax);
+                    stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt;
+                    stk_lo[sp] = r_lo; stk_hi[sp] = r_hi; stk_src[sp] = cur_ref;
+                    sp++;
+                }
+                if (hit_l | hit_r) {
+                    cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
+                    need_pop = false;
+                }
+            }
+            if (need_pop) {
+                live = false;
+                while (sp > 0) {
+                    --sp;
+                    if (stk_lo[sp] >= r.t) continue;                          // the deferred `tmin < ray.t` of bvh.cpp:178
+                    if (!(stk_hi[sp] < r.t)) {
+                        if (COUNT) lc.box_exact++;
+                        BoxTimes e = exact_child(P.pairs64, stk_src[sp], 1u, r.r64);
+                        if (!(e.tmin < r.t)) continue;
+                    }
+                    cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; live = true;
+                    break;
+                }
+                if (!live) job.finish(P, r.t != kRayTInit, tclosest, closest_pos);      // raythread.cpp:227
+            }
+        }
+    }
+}
+
 // The two early-exit walks.
 //   kAnyHit    shadow rays (ray.t = 1e30f): only `found` is used (raythread.cpp:306), i.e. whether SOME triangle
 //              reachable through accepted boxes has a barycentric pass with 1e-4 < t < 1e30;
