@@ -623,7 +623,7 @@ def main():
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
             per_k = {}
             for k, v in prof_issue["warp_instructions_per_frame"].items():
-                t_ms = tot_k.get(k) if k in ("shadow", "bounce") else tot.get(k)
+                t_ms = tot.get(k)
                 if t_ms:
                     per_k[k] = {"warp_instructions": v, "ms": t_ms, "issue_utilisation": v / (n_sm * 4 * sm_hz * t_ms * 1e-3)}
             all_inst = sum(prof_issue["warp_instructions_per_frame"].values())
