@@ -118,6 +118,10 @@ struct DeviceState {
 
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mutex;
+// One host thread drives a device at a time (the boss uses one thread per GPU): every entry point that touches a device's
+// state holds that device's lock, so a second thread calling in for the same device waits instead of corrupting the state.
+std::recursive_mutex g_dev_mutex[kMaxDevices];
+#define DEVICE_GUARD(device) std::lock_guard<std::recursive_mutex> dev_lock_(g_dev_mutex[((device) >= 0 && (device) < kMaxDevices) ? (device) : 0])
 long long g_budget_option = 0;       // ct_gpu_set_option("traversal_budget"); 0 = default
 long long g_warp_budget_option = 0;  // ct_gpu_set_option("overflow_warp_budget"); 0 = default
 long long g_static_eighths = 7;      // ct_gpu_set_option("shared_static_eighths"), see next_chunk
@@ -293,6 +297,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     if (!ok) return fail(CT_ERR_INVALID, "BVH is malformed (child or triangle range out of bounds, overlapping leaves, a cycle or a shared child)");
     if (depth > kStackMax) return fail(CT_ERR_LIMIT, "BVH depth %d exceeds the device traversal stack (%d)", depth, kStackMax);
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     std::lock_guard<std::mutex> lock(g_mutex);
     DeviceState &s = g_dev[device];
     free_device(s);
@@ -536,6 +541,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
 int ct_gpu_set_camera(int device, const double position[3], const double rotation[9]) {
     if (!position || !rotation) return fail(CT_ERR_INVALID, "NULL camera");
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     memcpy(s.p.cam, position, sizeof s.p.cam);
@@ -545,6 +551,7 @@ int ct_gpu_set_camera(int device, const double position[3], const double rotatio
 
 int ct_gpu_set_stream(int device, void *cuda_stream) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     CU(cudaStreamSynchronize(s.stream));
@@ -560,6 +567,7 @@ int ct_gpu_set_stream(int device, void *cuda_stream) {
 
 static int render_impl(int device, int y_start, int y_end, ct_ray_counters *counters, bool shared) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     int half = s.p.H / 2;
@@ -728,6 +736,7 @@ int ct_gpu_render_shared(int device, int y_start, int y_end, ct_ray_counters *co
 int ct_gpu_share_export(int device, ct_gpu_share *out) {
     if (!out || out->struct_size != sizeof(ct_gpu_share)) return fail(CT_ERR_INVALID, "ct_gpu_share missing or struct_size != %zu", sizeof(ct_gpu_share));
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ct_gpu_share reserves 64 bytes per IPC handle");
@@ -747,6 +756,7 @@ int ct_gpu_share_export(int device, ct_gpu_share *out) {
 
 int ct_gpu_share_attach(int device, const ct_gpu_share *root) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     for (void *&q : s.ipc_opened) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
@@ -790,6 +800,7 @@ int ct_gpu_share_attach(int device, const ct_gpu_share *root) {
 
 int ct_gpu_share_partition(int device, int index, int count) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     if (count < 0 || count > 64 || (count > 0 && (index < 0 || index >= count))) return fail(CT_ERR_INVALID, "bad partition %d of %d", index, count);
@@ -800,6 +811,7 @@ int ct_gpu_share_partition(int device, int index, int count) {
 
 int ct_gpu_share_reset(int device) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     CU(cudaMemsetAsync(s.cursor_own, 0, 2 * kCursorStride * sizeof(unsigned long long), s.stream));
@@ -849,6 +861,7 @@ int ct_gpu_set_option(const char *name, long long value) {
 
 int ct_gpu_overflow_stats(int device, uint64_t *parked, uint64_t *finished_in_place) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     ct_ray_counters tmp;
@@ -860,6 +873,7 @@ int ct_gpu_overflow_stats(int device, uint64_t *parked, uint64_t *finished_in_pl
 
 int ct_gpu_filter_stats(int device, uint64_t *box_exact, uint64_t *tri_exact) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     ct_ray_counters tmp;
@@ -871,6 +885,7 @@ int ct_gpu_filter_stats(int device, uint64_t *box_exact, uint64_t *tri_exact) {
 
 int ct_gpu_sync(int device) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     CU(cudaStreamSynchronize(s.stream));
@@ -880,6 +895,7 @@ int ct_gpu_sync(int device) {
 int ct_gpu_kernel_launches(int device, uint64_t *out, int reset) {
     if (!out) return fail(CT_ERR_INVALID, "NULL out");
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     *out = s.launches;
@@ -889,6 +905,7 @@ int ct_gpu_kernel_launches(int device, uint64_t *out, int reset) {
 
 int ct_gpu_last_tile_stages(int device, int max, float *ms, const char **names, int *depth) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     if (!(s.flags & CT_FLAG_STAGE_TIMING)) return fail(CT_ERR_INVALID, "scene was uploaded without CT_FLAG_STAGE_TIMING");
@@ -903,6 +920,7 @@ int ct_gpu_last_tile_stages(int device, int max, float *ms, const char **names, 
 
 int ct_gpu_throttle(int device, int max_in_flight) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     if (max_in_flight <= 0) { CU(cudaStreamSynchronize(s.stream)); return CT_OK; }
@@ -914,6 +932,7 @@ int ct_gpu_throttle(int device, int max_in_flight) {
 int ct_gpu_last_tile_ms(int device, float *ms) {
     if (!ms) return fail(CT_ERR_INVALID, "NULL ms");
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded || !s.timed) return fail(CT_ERR_NO_SCENE, "no tile rendered on device %d", device);
     CU(cudaEventSynchronize(s.ev1));
@@ -924,6 +943,7 @@ int ct_gpu_last_tile_ms(int device, float *ms) {
 int ct_gpu_get_counters(int device, ct_ray_counters *out, int reset) {
     if (!out) return fail(CT_ERR_INVALID, "NULL out");
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     TRY(read_totals(s, out));
@@ -937,6 +957,7 @@ int ct_gpu_get_counters(int device, ct_ray_counters *out, int reset) {
 int ct_gpu_readback(int device, uint32_t *dst, int dst_stride_pixels, int row_start, int row_end) {
     if (!dst) return fail(CT_ERR_INVALID, "NULL dst");
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     const Params &p = s.p;
@@ -958,6 +979,7 @@ int ct_gpu_readback(int device, uint32_t *dst, int dst_stride_pixels, int row_st
 int ct_gpu_readback_async(int device, uint32_t *dst, int dst_stride_pixels, int row_start, int row_end) {
     if (!dst) return fail(CT_ERR_INVALID, "NULL dst");
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     const Params &p = s.p;
@@ -990,6 +1012,7 @@ int ct_gpu_readback_async(int device, uint32_t *dst, int dst_stride_pixels, int 
 
 int ct_gpu_readback_wait(int device) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     if (s.copy_pending) CU(cudaEventSynchronize(s.ev_copied));
@@ -999,6 +1022,7 @@ int ct_gpu_readback_wait(int device) {
 
 int ct_gpu_readback_hits(int device, uint32_t *found, uint32_t *index, float *t, int stride_pixels, int row_start, int row_end) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     const Params &p = s.p;
@@ -1016,6 +1040,7 @@ int ct_gpu_readback_hits(int device, uint32_t *found, uint32_t *index, float *t,
 
 int ct_gpu_framebuffer(int device, void **device_ptr, int *width, int *height) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     if (device_ptr) *device_ptr = s.p.fb;
@@ -1040,6 +1065,7 @@ int ct_gpu_gather_rows(int src_device, int dst_device, int row_start, int row_en
 
 int ct_gpu_mark_rows(int device, int row_start, int row_end) {
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     int r0 = std::max(row_start, 0), r1 = std::min(row_end, s.p.H);
@@ -1051,6 +1077,7 @@ int ct_gpu_debug_closest(int device, uint32_t n, const double *origins, const do
                          uint32_t *found, uint32_t *index, float *tclosest) {
     if (!origins || !directions || !t0) return fail(CT_ERR_INVALID, "NULL ray arrays");
     TRY(check_device(device));
+    DEVICE_GUARD(device);
     DeviceState &s = g_dev[device];
     if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
     if (n == 0) return CT_OK;
@@ -1121,6 +1148,7 @@ int ct_gpu_debug_filter(int device, uint32_t n, const double *origins, const dou
 
 int ct_gpu_shutdown(int device) {
     if (device < 0 || device >= kMaxDevices) return fail(CT_ERR_NO_DEVICE, "device %d out of range", device);
+    DEVICE_GUARD(device);
     std::lock_guard<std::mutex> lock(g_mutex);
     DeviceState &s = g_dev[device];
     if (s.loaded || !s.allocs.empty()) {
