@@ -493,17 +493,27 @@ def main():
         dist.barrier()
     pipe_ms = (time.perf_counter() - t0) * 1e3 / n_pipe
     frame(True)                                              # leaves the last frame in `bitmap` for the pixel check below
+    # the same frames with every shadow ray traced (option shadow_reuse = 0): what the reuse of identical shadow rays is worth
+    api.set_option("shadow_reuse", 0)
+    for _ in range(2):
+        frame(False)
+    if N > 1:
+        dist.barrier()
+    noreuse_ms, _, _ = timed(False, max(5, steps // 4))
+    api.set_option("shadow_reuse", 1)
 
     # ---- reduce over ranks: per-step max of the device time; sum of rays
     rays_vec = torch.tensor([st["rays_primary"], st["rays_shadow"], st["rays_reflection"], launches], dtype=torch.float64, device=f"cuda:{dev}")
     t_dev = torch.tensor(dev_ms, dtype=torch.float64, device=f"cuda:{dev}")
     t_e2e = torch.tensor(e2e_wall, dtype=torch.float64, device=f"cuda:{dev}")
+    t_noreuse = torch.tensor(noreuse_ms, dtype=torch.float64, device=f"cuda:{dev}")
     t_once = torch.tensor([attach_ms + upload_ms if rank != 0 else 0.0], dtype=torch.float64, device=f"cuda:{dev}")
     if N > 1:
         dist.all_reduce(t_once, op=dist.ReduceOp.MAX)
         dist.all_reduce(rays_vec, op=dist.ReduceOp.SUM)
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_noreuse, op=dist.ReduceOp.MAX)
     rays_primary, rays_shadow, rays_refl, total_launches = (int(x) for x in rays_vec.tolist())
     rays_total = rays_primary + rays_shadow + rays_refl
     ms_per_step = float(t_dev.mean())
@@ -529,6 +539,13 @@ def main():
                                    else "1 GPU; persistent warps steal 32-pixel chunks from a device-side cursor")},
         "ms_per_frame": ms_per_step,
         "rays_per_frame": {"primary": rays_primary, "shadow": rays_shadow, "reflection": rays_refl},
+        "shadow_rays": {"counted": rays_shadow, "reused": None, "traced": None,
+                        "note": ("rays are counted as the reference casts them (one shadow ray per light per shading point, raythread.cpp:304).  The reference's "
+                                 "reflection rays have t = 0, so a reflection hit (tclosest = 0) puts the next shading point exactly on the previous one and "
+                                 "ComputeLighting casts the same shadow rays again; this implementation answers those from the parent's verdicts ('reused') and "
+                                 "traces the rest.  `without_shadow_reuse` is the same frame with option shadow_reuse = 0 (every ray traced)."),
+                        "without_shadow_reuse": {"ms_per_step": float(t_noreuse.mean()), "value": rays_total / float(t_noreuse.mean()) / 1e3, "unit": "Mrays/s",
+                                                 "steps": int(len(noreuse_ms))}},
         "mrays_per_s_by_kind": {"primary": rays_primary / ms_per_step / 1e3, "shadow": rays_shadow / ms_per_step / 1e3,
                                 "reflection": rays_refl / ms_per_step / 1e3},
         "ms_per_step_min": float(t_dev.min()), "ms_per_step_max": float(t_dev.max()),
@@ -582,6 +599,8 @@ def main():
         cnt = api.GpuRenderer(dev).upload(fs, W, H, max_depth=depth, flags=api.CT_FLAG_COUNT_TESTS)
         own = cnt.render_tile(counters=True)
         own_exact = cnt.filter_stats()
+        line["shadow_rays"]["reused"] = cnt.reuse_stats()
+        line["shadow_rays"]["traced"] = rays_shadow - line["shadow_rays"]["reused"]
         cnt.shutdown()
         alg = {   # algorithmic bytes per frame of each kernel type: 32 B per node visit + 48 B per triangle test of the
                   # REFERENCE's DFS on this frame, + 4 B per stored pixel.  k_shadow owns the shadow rays

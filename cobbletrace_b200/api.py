@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "ct_gpu_abi_version", "ct_gpu_device_count", "ct_gpu_last_error", "ct_gpu_upload_scene", "ct_gpu_set_camera",
     "ct_gpu_set_stream", "ct_gpu_render_tile", "ct_gpu_readback", "ct_gpu_readback_async", "ct_gpu_readback_wait", "ct_gpu_readback_hits", "ct_gpu_get_counters",
     "ct_gpu_last_tile_ms", "ct_gpu_sync", "ct_gpu_throttle", "ct_gpu_kernel_launches", "ct_gpu_last_tile_stages", "ct_gpu_framebuffer", "ct_gpu_gather_rows", "ct_gpu_debug_closest",
-    "ct_gpu_debug_primitives", "ct_gpu_debug_filter", "ct_gpu_filter_stats", "ct_gpu_shutdown", "ct_gpu_share_export", "ct_gpu_share_attach", "ct_gpu_share_reset", "ct_gpu_share_partition", "ct_gpu_mark_rows", "ct_gpu_render_shared", "ct_gpu_set_option", "ct_gpu_overflow_stats",
+    "ct_gpu_debug_primitives", "ct_gpu_debug_filter", "ct_gpu_filter_stats", "ct_gpu_reuse_stats", "ct_gpu_shutdown", "ct_gpu_share_export", "ct_gpu_share_attach", "ct_gpu_share_reset", "ct_gpu_share_partition", "ct_gpu_mark_rows", "ct_gpu_render_shared", "ct_gpu_set_option", "ct_gpu_overflow_stats",
 ]
 
 
@@ -112,6 +112,7 @@ def load_library(path: Optional[str] = None):
     L.ct_gpu_debug_primitives.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ct_gpu_debug_filter.argtypes = [C.c_int, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_double, vp]
     L.ct_gpu_filter_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.ct_gpu_reuse_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64)]
     L.ct_gpu_share_export.argtypes = [C.c_int, C.POINTER(Share)]
     L.ct_gpu_share_attach.argtypes = [C.c_int, C.POINTER(Share)]
     L.ct_gpu_share_reset.argtypes = [C.c_int]
@@ -332,6 +333,12 @@ class GpuRenderer:
         a = C.c_uint64(); b = C.c_uint64()
         _check(self.L, self.L.ct_gpu_filter_stats(self.device, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+    def reuse_stats(self) -> int:
+        """Shadow rays (counted in rays_shadow) answered from an ancestor's identical ray instead of being traced."""
+        a = C.c_uint64()
+        _check(self.L, self.L.ct_gpu_reuse_stats(self.device, C.byref(a)))
+        return int(a.value)
 
     def overflow_stats(self):
         """(rays parked for the breadth-first overflow kernel, rays finished in place because the buffer was full)."""

@@ -88,6 +88,9 @@ struct DeviceState {
     float *hitb_t_all = nullptr; uint32_t *hitb_pos_all = nullptr;      // [depth][cap]
     double *rays_all = nullptr; uint32_t *path_slot_all = nullptr;      // [depth][cap * 6], [depth][cap]
     uint32_t *occ_all = nullptr;                                        // [depth][cap * occ_words]
+    uint32_t *parent_q_all = nullptr;                                   // [depth][cap]: parent path of a reflection path (k_emit)
+    cudaEvent_t ev_lit[16] = {};                                        // shadow verdicts of depth d complete (k_shade of deeper levels may read them)
+    unsigned long long rays_shadow_reused = 0;
     OvfRay *ovf_all = nullptr; uint32_t *ovf_huge_all = nullptr;        // [2 * depth + kind][ovf_cap]
     int levels = 1;
     cudaStream_t aux[4] = {};
@@ -127,6 +130,7 @@ long long g_warp_budget_option = 0;  // ct_gpu_set_option("overflow_warp_budget"
 long long g_static_eighths = 7;      // ct_gpu_set_option("shared_static_eighths"), see next_chunk
 long long g_shared_chunk_shift = 0;  // ct_gpu_set_option("shared_chunk_shift"): 0 = kChunkSharedShift
 long long g_emulate_ranks = 0;       // ct_gpu_set_option("emulate_ranks"): profiling aid, see ct_gpu.h
+long long g_shadow_reuse = 1;        // ct_gpu_set_option("shadow_reuse"): a shading point that repeats its parent's takes the parent's shadow verdicts
 long long g_hold_frame = 0;          // ct_gpu_set_option("shared_hold_frame"): test aid, see ct_gpu.h
 long long g_l2_persist = 1;          // ct_gpu_set_option("l2_persist"): pin the walk's fp32 records in L2 (apply_l2_policy)
 
@@ -157,6 +161,7 @@ void free_device(DeviceState &s) {
     for (cudaEvent_t e : s.stage_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s.ev_hit) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s.ev_done) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s.ev_lit) if (e) cudaEventDestroy(e);
     for (cudaStream_t a : s.aux) if (a) cudaStreamDestroy(a);
     if (s.copy_stream) { cudaStreamSynchronize(s.copy_stream); cudaStreamDestroy(s.copy_stream); }
     if (s.ev_snap) cudaEventDestroy(s.ev_snap);
@@ -262,6 +267,7 @@ int read_totals(DeviceState &s, ct_ray_counters *out) {   // synchronises the st
     out->box_tests = h.box_tests; out->tri_tests = h.tri_tests;
     s.rays_overflow = h.rays_overflow; s.rays_in_place = h.rays_in_place;
     s.box_exact = h.box_exact; s.tri_exact = h.tri_exact;
+    s.rays_shadow_reused = h.rays_shadow_reused;
     return CT_OK;
 }
 
@@ -311,6 +317,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     for (cudaEvent_t &e : s.tile_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (cudaEvent_t &e : s.ev_hit) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (cudaEvent_t &e : s.ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t &e : s.ev_lit) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (cudaStream_t &a : s.aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
     if (d->flags & CT_FLAG_STAGE_TIMING) for (cudaEvent_t &e : s.stage_ev) CU(cudaEventCreate(&e));
     s.p.budget = g_budget_option > 0 ? (uint32_t)std::min<long long>(g_budget_option, 1ll << 30) : kDefaultBudget;
@@ -515,6 +522,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
         TRY(dev_alloc(s, &s.hitb_t_all, (size_t)p.cap * levels)); TRY(dev_alloc(s, &s.hitb_pos_all, (size_t)p.cap * levels));
         TRY(dev_alloc(s, &p.stack_refl, (size_t)p.cap * levels));
         TRY(dev_alloc(s, &s.rays_all, (size_t)p.cap * 6 * (levels + 1))); TRY(dev_alloc(s, &s.path_slot_all, (size_t)p.cap * (levels + 1)));
+        TRY(dev_alloc(s, &s.parent_q_all, (size_t)p.cap * (levels + 1)));
     }
     TRY(dev_alloc(s, &p.fb, (size_t)d->width * d->height, true));       // calloc'd like cobbletrace.cpp:57
     p.subsample = (d->flags & CT_FLAG_SUBSAMPLING) ? 1 : 0;
@@ -609,6 +617,8 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     }
     p.fb_out = shared ? s.share_fb : p.fb;
     Params pk = p; pk.max_depth = depth_max;   // with no reflective material the recursion never goes past depth 0 (:369)
+    pk.parent_q_all = s.parent_q_all; pk.hitb_t_all = s.hitb_t_all; pk.occ_all = s.occ_all;
+    pk.reuse_shadow = (g_shadow_reuse && s.parent_q_all) ? 1u : 0u;
     cudaStream_t st = s.stream;
     if (shared && !same_frame) {
         if (s.share_cursor == s.cursor_own) CU(cudaMemsetAsync(s.cursor_own + kCursorStride * ((s.shared_frames + 1ull) & 1ull), 0, sizeof(unsigned long long), st));
@@ -637,6 +647,7 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
         if (s.rays_all) {
             v.ray_buf[d & 1] = s.rays_all + cap * 6 * d;            v.path_slot[d & 1] = s.path_slot_all + cap * d;
             v.ray_buf[(d & 1) ^ 1] = s.rays_all + cap * 6 * (d + 1); v.path_slot[(d & 1) ^ 1] = s.path_slot_all + cap * (d + 1);
+            v.parent_q[d & 1] = s.parent_q_all + cap * d; v.parent_q[(d & 1) ^ 1] = s.parent_q_all + cap * (d + 1);
         }
         v.occ = s.occ_all + cap * pk.occ_words * d;
         return v;
@@ -693,6 +704,11 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
                 else { k_overflow<kAnyHit, false><<<s.n_sm * 2, kOvfThreads, 0, side>>>(vo, ovf_s); k_overflow_huge<kAnyHit, false><<<s.n_sm * 4, 256, 0, side>>>(vo, ovf_s); }
                 s.launches += 2;
             }
+        }
+        if (!stages) {
+            // k_shade(d) may read the shadow verdicts of shallower depths (occlusion_source): they are complete at ev_lit
+            CU(cudaEventRecord(s.ev_lit[d], side));
+            for (int dd = 0; dd < d; dd++) CU(cudaStreamWaitEvent(side, s.ev_lit[dd], 0));
         }
         k_shade<<<grid, kBlockThreads, 0, side>>>(v, d, work++);
         if (stages) TRY(mark("shade", d)); else s.launches++;
@@ -841,6 +857,11 @@ int ct_gpu_set_option(const char *name, long long value) {
         g_shared_chunk_shift = value;
         return CT_OK;
     }
+    if (!strcmp(name, "shadow_reuse")) {
+        if (value != 0 && value != 1) return fail(CT_ERR_INVALID, "shadow_reuse must be 0 or 1");
+        g_shadow_reuse = value;
+        return CT_OK;
+    }
     if (!strcmp(name, "shared_hold_frame")) {
         if (value != 0 && value != 1) return fail(CT_ERR_INVALID, "shared_hold_frame must be 0 or 1");
         g_hold_frame = value;
@@ -868,6 +889,17 @@ int ct_gpu_overflow_stats(int device, uint64_t *parked, uint64_t *finished_in_pl
     TRY(read_totals(s, &tmp));
     if (parked) *parked = s.rays_overflow;
     if (finished_in_place) *finished_in_place = s.rays_in_place;
+    return CT_OK;
+}
+
+int ct_gpu_reuse_stats(int device, uint64_t *shadow_rays_reused) {
+    TRY(check_device(device));
+    DEVICE_GUARD(device);
+    DeviceState &s = g_dev[device];
+    if (!s.loaded) return fail(CT_ERR_NO_SCENE, "no scene uploaded on device %d", device);
+    ct_ray_counters tmp;
+    TRY(read_totals(s, &tmp));
+    if (shadow_rays_reused) *shadow_rays_reused = s.rays_shadow_reused;
     return CT_OK;
 }
 

@@ -131,6 +131,27 @@ CT_DEV bool load_path(const Params &P, int depth, uint32_t q, uint32_t &slot, in
     return true;
 }
 
+// IDENTICAL SHADOW RAYS ARE TRACED ONCE.  The reference's reflection rays are built with t = 0 (raythread.cpp:373): a
+// reflection "hit" -- the first triangle in DFS order whose line passes -- has tclosest = 0, so the next shading point is
+// position = origin + 0 * direction = the ray's origin = the PREVIOUS shading point, bit for bit (raythread.cpp:360; the direction
+// must be finite for 0 * direction to be 0).  ComputeLighting then casts, for every light, exactly the shadow ray the previous
+// level already cast from that point (raythread.cpp:288-304: same origin, same light, t = 1e30f): same ray, same verdict
+// (k_emit checks the "bit for bit" when it builds the reflection ray and flags the exceptions: kNoReuse).  So
+// a path whose hit has tclosest == 0 takes its occlusion mask from its parent (and so on up the chain) instead of tracing
+// the rays again; only normal, material and view direction differ between the levels.  The rays still count as shadow rays
+// (rays_shadow keeps the reference's definition); rays_shadow_reused says how many of them were answered this way.
+// Is the shading point of path q at `depth` (>= 1) a copy of its parent's?
+CT_DEV bool shading_point_repeats(const Params &P, int depth, uint32_t q) {
+    if (!P.reuse_shadow || depth <= 0) return false;
+    const size_t i = (size_t)depth * P.cap + q;
+    return __ldg(P.hitb_t_all + i) == 0.0f && !(__ldg(P.parent_q_all + i) & kNoReuse);
+}
+// The occlusion mask path q of `depth` is lit with: its own, or that of the nearest ancestor whose shading point it repeats.
+CT_DEV const uint32_t *occlusion_source(const Params &P, int depth, uint32_t q) {
+    while (shading_point_repeats(P, depth, q)) { q = __ldg(P.parent_q_all + (size_t)depth * P.cap + q) & ~kNoReuse; depth--; }
+    return P.occ_all + ((size_t)depth * P.cap + q) * P.occ_words;
+}
+
 CT_DEV void clear_occ(const Params &P, uint32_t q) {
     for (uint32_t w = 0; w < P.occ_words; w++) P.occ[(size_t)q * P.occ_words + w] = 0u;
 }
@@ -278,7 +299,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
     LocalCount lc;
-    uint32_t n_shadow = 0, n_parked = 0;
+    uint32_t n_shadow = 0, n_parked = 0, n_reused = 0;
     __shared__ __align__(128) DevWide top_nodes[kTopSmem > 0u ? kTopSmem : 1u];
     __shared__ unsigned long long top_bar;
     const uint32_t n_top = (kTopSmem > 0u && P.wide) ? stage_top_nodes(P, top_nodes, &top_bar, P.n_wide) : 0u;
@@ -291,7 +312,12 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
         uint32_t j = (uint32_t)(base / n_pad);
         uint32_t q = (uint32_t)(base - (unsigned long long)j * n_pad) + (threadIdx.x & 31u);
         uint32_t slot, pos = kNoPos; int fbi; Ray r; float tc = 0.0f;
-        bool active = q < n && load_path(P, depth, q, slot, fbi, r, tc, pos) && pos != kNoPos;
+        bool active = q < n;
+        if (active && shading_point_repeats(P, depth, q)) {           // the parent cast this very ray: k_shade reads its verdict there
+            n_shadow++; n_reused++;                                   // (every reflection path is a hit: 0 != 1e30f, raythread.cpp:227)
+            active = false;
+        }
+        active = active && load_path(P, depth, q, slot, fbi, r, tc, pos) && pos != kNoPos;
         double r64[kRay64];
         TRay tr;
         uint32_t word = 0, bit = 0;
@@ -323,6 +349,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
         }
     }
     warp_add(&P.tot->rays_shadow, n_shadow);
+    warp_add(&P.tot->rays_shadow_reused, n_reused);
     warp_add(&P.tot->rays_overflow, n_parked);
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
@@ -376,6 +403,13 @@ __global__ void __launch_bounds__(kBlockThreads) k_emit(const __grid_constant__ 
                 rb[1] = make_double2(position.z, rdir.x);
                 rb[2] = make_double2(rdir.y, rdir.z);
                 P.path_slot[nxt][nq] = slot;
+                // would a hit with tclosest = 0 put the next shading point exactly here?  (not with a non-finite direction:
+                // 0 * inf = NaN; and -0.0 + 0.0 = +0.0 changes a bit that a light at -0.0 could tell apart)
+                const V3 again = vadd(position, vscale(0.0, rdir));
+                const bool same = __double_as_longlong(again.x) == __double_as_longlong(position.x) &&
+                                  __double_as_longlong(again.y) == __double_as_longlong(position.y) &&
+                                  __double_as_longlong(again.z) == __double_as_longlong(position.z);
+                P.parent_q[nxt][nq] = q | (same ? 0u : kNoReuse);
                 n_refl++;
             }
         }
@@ -410,7 +444,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
         V3 view = vneg(r.d);
         // ---- ComputeLighting :275-327, lights in file order, fp32 accumulator
         float intensity = 0.0f;
-        const uint32_t *occ = P.occ + (size_t)q * P.occ_words;
+        const uint32_t *occ = occlusion_source(P, depth, q);
         uint32_t occ_word = 0;
         for (uint32_t i = 0; i < P.n_lights; i++) {
             const DevLight &L = P.lights[i];

@@ -21,6 +21,7 @@ constexpr int kMinBlocks = CT_MIN_BLOCKS;   // traversal kernels: resident CTAs 
 constexpr int kOvfThreads = 256;     // k_overflow CTA
 constexpr int kMaxLaunches = 80;     // launches of one tile (work cursors / stage events)
 constexpr uint32_t kNoPos = 0xffffffffu;
+constexpr uint32_t kNoReuse = 0x80000000u;      // parent_q flag: the reflection ray's direction is not finite (0 * direction would not be 0)
 constexpr int kCursorStride = 16;    // unsigned long longs between the two chunk cursors of a shared frame (128 bytes)
 // Slots a warp takes from the tile's cursor at a time: 32 = one 8x4 pixel block, one ray per lane.  When the cursor is
 // another GPU's memory, 64 would halve the NVLink round trips, but a kernel ends with its slowest warp and a warp's
@@ -88,6 +89,7 @@ struct DevTotals {                   // running ray / test counters (never reset
     unsigned long long rays_overflow;    // rays whose DFS ran past the budget
     unsigned long long rays_in_place;    // ... of which the parking buffer was full: finished by their own thread
     unsigned long long box_exact, tri_exact;   // tests the fp32 filters left to the fp64 arithmetic (CT_FLAG_COUNT_TESTS)
+    unsigned long long rays_shadow_reused;     // shadow rays (counted in rays_shadow) that were not traced: an ancestor's identical ray had been
 };
 
 struct Params {
@@ -127,6 +129,10 @@ struct Params {
     float *hitb_t; uint32_t *hitb_pos;           // depth>=1 hits, by queue slot
     double *ray_buf[2];                          // depth>=1 rays: 6 doubles per queue slot, ping-pong
     uint32_t *path_slot[2];                      // queue slot -> depth-0 slot, ping-pong
+    uint32_t *parent_q[2];                       // queue slot -> the parent path's queue slot one depth up (kNoReuse bit: its shading point is its own)
+    // every depth's arrays, for k_shade's walk up the chain of shading points that coincide (see occlusion_source)
+    const uint32_t *parent_q_all; const float *hitb_t_all; const uint32_t *occ_all;
+    uint32_t reuse_shadow;                       // option "shadow_reuse"
     uint32_t *occ;                               // [path][occ_words] shadow-ray verdicts of the current depth, bit i = light i occluded
     uint32_t *stack_color; float *stack_refl;    // [depth][slot]
     uint8_t *term_level;                         // [slot] level at which the chain ended

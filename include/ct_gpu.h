@@ -227,6 +227,9 @@ int ct_gpu_sync(int device);
  *                       the next render, 0 / 1 = off.
  *   "shared_static_eighths"  see ct_gpu_share_partition.
  *   "shared_chunk_shift"  log2 of the pixels a warp steals at a time in a shared frame: 5 (default, also 0) or 6.
+ *   "shadow_reuse"      1 (default): a reflection path whose shading point repeats its parent's (tclosest = 0, see
+ *                       ct_gpu_reuse_stats) takes the parent's shadow verdicts instead of tracing the same rays again; 0: trace all.
+ *                       Applies to the next render.
  *   "shared_hold_frame" 1: the next ct_gpu_render_shared calls belong to the SAME shared frame as the previous one (same
  *                       cursor, not advanced) -- for tests in which one device plays several participants in turn; 0 = off.
  *   "l2_persist"        1 (default): set aside L2 for persisting lines and open an access-policy window over the walk's
@@ -237,6 +240,13 @@ int ct_gpu_set_option(const char *name, long long value);
  * shadow rays of a shading point 2^32 ray lengths away after a reflection miss), and how many
  * of them found the parking buffer full and were finished by their own thread.  Synchronises. */
 int ct_gpu_overflow_stats(int device, uint64_t *parked, uint64_t *finished_in_place);
+
+/* Shadow rays, of those counted in rays_shadow since upload / the last counter reset, that were NOT traced because an
+ * ancestor's identical ray had been: the reference builds its reflection rays with t = 0 (raythread.cpp:373), so a reflection
+ * "hit" has tclosest = 0 and the next shading point IS the previous one (raythread.cpp:360) -- ComputeLighting casts the
+ * same shadow rays again (raythread.cpp:288-304).  Such a path takes its parent's verdicts (option "shadow_reuse", default
+ * 1; 0 traces every ray).  Synchronises. */
+int ct_gpu_reuse_stats(int device, uint64_t *shadow_rays_reused);
 
 /* With CT_FLAG_COUNT_TESTS: how many of the counted box / triangle tests the certified fp32 filters could not
  * decide and handed to the reference's fp64 arithmetic (since upload / last counter reset).  Synchronises. */

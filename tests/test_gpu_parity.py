@@ -730,3 +730,33 @@ def test_tree_that_is_not_nested_takes_the_exact_walks(golden, scene_loader, gpu
     gpu.render_tile()
     assert_same(gpu, oframe, ohits, "shrunk inner boxes")
     assert not np.array_equal(oframe, load_frames("bunny_refl_d2_160")["frame"])
+
+
+@pytest.mark.gpu
+def test_identical_shadow_rays_are_traced_once(golden, scene_loader, gpu):
+    """The reference's reflection rays have t = 0, so a reflection "hit" puts the next shading point exactly on the previous
+    one and ComputeLighting casts the same shadow rays again (raythread.cpp:360,373,288-304).  Option shadow_reuse (default on)
+    answers them from the parent's verdicts: same frames, same ray counts (rays_shadow keeps the reference's definition),
+    fewer box tests -- on the mirror scene of configs[0], the bunny with forced mirrors at depth 2 and 10, and a generated scene."""
+    # (in scene_file_cube.json no reflection ray finds a pass -- the mirror shows triangle 0's colour, SURVEY 0.4 -- so every
+    # reflection "hit" is 2^32 ray lengths away and nothing repeats: the option must not change anything there either)
+    cases = [("cube_160", False), ("bunny_refl_d2_160", True), ("bunny_refl_d10_128", True)]
+    for case, repeats in cases:
+        fs, meta = case_scene(case, golden, scene_loader)
+        want = load_frames(case)["frame"]
+        res = {}
+        for reuse in (0, 1):
+            ct.api.set_option("shadow_reuse", reuse)
+            try:
+                gpu.upload(fs, meta["width"], meta["height"], max_depth=meta["depth"], flags=ct.CT_FLAG_COUNT_TESTS)
+                c = gpu.render_tile(counters=True)
+                assert np.array_equal(gpu.readback(), want), (case, reuse)
+                res[reuse] = (c, gpu.reuse_stats())
+            finally:
+                ct.api.set_option("shadow_reuse", 1)
+        (c0, r0), (c1, r1) = res[0], res[1]
+        assert r0 == 0 and (r1 > 0) == repeats, (case, r0, r1)
+        for k in ("rays_primary", "rays_shadow", "rays_reflection"):
+            assert c0[k] == c1[k], (case, k)
+        assert (c1["box_tests"] < c0["box_tests"]) == repeats, case
+        assert r1 <= c1["rays_shadow"]
