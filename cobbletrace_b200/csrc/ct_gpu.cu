@@ -89,6 +89,7 @@ struct DeviceState {
     double *rays_all = nullptr; uint32_t *path_slot_all = nullptr;      // [depth][cap * 6], [depth][cap]
     uint32_t *occ_all = nullptr;                                        // [depth][cap * occ_words]
     uint32_t *parent_q_all = nullptr;                                   // [depth][cap]: parent path of a reflection path (k_emit)
+    uint32_t *far_all = nullptr;                                        // [depth][cap]: k_bounce's far lists
     cudaEvent_t ev_lit[16] = {};                                        // shadow verdicts of depth d complete (k_shade of deeper levels may read them)
     unsigned long long rays_shadow_reused = 0;
     OvfRay *ovf_all = nullptr; uint32_t *ovf_huge_all = nullptr;        // [2 * depth + kind][ovf_cap]
@@ -523,6 +524,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
         TRY(dev_alloc(s, &p.stack_refl, (size_t)p.cap * levels));
         TRY(dev_alloc(s, &s.rays_all, (size_t)p.cap * 6 * (levels + 1))); TRY(dev_alloc(s, &s.path_slot_all, (size_t)p.cap * (levels + 1)));
         TRY(dev_alloc(s, &s.parent_q_all, (size_t)p.cap * (levels + 1)));
+        TRY(dev_alloc(s, &s.far_all, (size_t)p.cap * levels));
     }
     TRY(dev_alloc(s, &p.fb, (size_t)d->width * d->height, true));       // calloc'd like cobbletrace.cpp:57
     p.subsample = (d->flags & CT_FLAG_SUBSAMPLING) ? 1 : 0;
@@ -650,6 +652,7 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
             v.parent_q[d & 1] = s.parent_q_all + cap * d; v.parent_q[(d & 1) ^ 1] = s.parent_q_all + cap * (d + 1);
         }
         v.occ = s.occ_all + cap * pk.occ_words * d;
+        if (s.far_all) v.far_list = s.far_all + cap * d;
         return v;
     };
     auto overflow = [&](const Params &v0, cudaStream_t q, int mode_anyhit, int ovf_idx, int depth) -> int {   // parked rays of the launch just made

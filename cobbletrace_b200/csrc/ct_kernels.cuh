@@ -303,7 +303,14 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
     __shared__ __align__(128) DevWide top_nodes[kTopSmem > 0u ? kTopSmem : 1u];
     __shared__ unsigned long long top_bar;
     const uint32_t n_top = (kTopSmem > 0u && P.wide) ? stage_top_nodes(P, top_nodes, &top_bar, P.n_wide) : 0u;
-    const uint32_t n = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
+    // depth >= 1 with shadow reuse: only the paths of the far list cast rays of their own; the others are counted here
+    const bool use_far = depth > 0 && P.reuse_shadow != 0u;
+    const uint32_t n_paths = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
+    const uint32_t n = use_far ? P.sched->far_count[depth] : n_paths;
+    if (use_far && blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long rest = (unsigned long long)(n_paths - n) * P.n_slights;
+        atomicAdd(&P.tot->rays_shadow, rest); atomicAdd(&P.tot->rays_shadow_reused, rest);
+    }
     const unsigned long long n_pad = ((unsigned long long)n + 31ull) & ~31ull;
     const unsigned long long total = n_pad * P.n_slights;
     while (true) {
@@ -313,6 +320,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
         uint32_t q = (uint32_t)(base - (unsigned long long)j * n_pad) + (threadIdx.x & 31u);
         uint32_t slot, pos = kNoPos; int fbi; Ray r; float tc = 0.0f;
         bool active = q < n;
+        if (active && use_far) q = P.far_list[q];
         if (active && shading_point_repeats(P, depth, q)) {           // the parent cast this very ray: k_shade reads its verdict there
             n_shadow++; n_reused++;                                   // (every reflection path is a hit: 0 != 1e30f, raythread.cpp:227)
             active = false;
@@ -331,6 +339,9 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
             word = q * P.occ_words + (L.index >> 5); bit = L.index & 31u;
         }
         uint32_t budget = P.budget;
+        // an origin this far outside the scene (a shading point 2^32 ray lengths away) makes every box pass: no point
+        // in walking up to the budget first -- park the ray at its first visit, k_overflow hands it straight to k_overflow_huge
+        if (active && (double)tr.om > 0x1p20 * fmax(fmax(P.bound[0], P.bound[1]), P.bound[2])) budget = 0u;
         while (true) {                                                  // warp-uniform: traverse_early is warp-synchronous
             float stc; uint32_t spos;
             int res = traverse_early_any<kAnyHit, COUNT>(P, tr, active, budget, stc, spos, lc, top_nodes, n_top);
@@ -488,6 +499,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
         if (base >= n) break;
         uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
         bool active = q < n;
+        bool far = false;            // this path needs shadow rays of its own (its shading point is not, or may not be, its parent's)
         double r64[kRay64];
         TRay r;
         if (active) {
@@ -508,13 +520,26 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
                     n_parked++;
                     again = !park_ray(P, ovf_idx, r64, q, 0u);          // parking buffer full: finish in place, no budget
                     budget = 0xffffffffu;
+                    far = true;                                         // k_overflow answers later: let k_shadow look at the path
                 } else {                                                // found is always true: 0 != 1e30f (:227)
                     P.hitb_t[q] = tc;
                     P.hitb_pos[q] = (pos == kNoPos) ? P.pos_of_tri0 : pos;
+                    far = tc != 0.0f || (P.parent_q[cur][q] & kNoReuse);
                 }
             }
             active = again;
             if (!__any_sync(kFullMask, again)) break;
+        }
+        // warp-aggregated append to the depth's far list (see shading_point_repeats: the others repeat their parent's shading point)
+        if (P.reuse_shadow) {
+            const uint32_t mask = __ballot_sync(kFullMask, far);
+            if (mask) {
+                const uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1;
+                uint32_t fbase = 0;
+                if (lane == leader) fbase = atomicAdd(&P.sched->far_count[depth], (uint32_t)__popc(mask));
+                fbase = __shfl_sync(kFullMask, fbase, leader);
+                if (far) P.far_list[fbase + __popc(mask & ((1u << lane) - 1u))] = q;
+            }
         }
     }
     warp_add(&P.tot->rays_overflow, n_parked);

@@ -83,6 +83,7 @@ struct DevSched {                    // zeroed at the start of every tile render
     uint32_t ovf_count[40];          // rays parked for the k_overflow launch 2*depth + {0: bounce, 1: shadow}
     uint32_t ovf_cursor[40];         // k_overflow's warp-cooperative pass: next parked ray to take
     uint32_t huge_count[40];         // ... rays it handed on to k_overflow_huge
+    uint32_t far_count[16];          // reflection paths of depth d whose shading point may differ from their parent's (far_list)
 };
 struct DevTotals {                   // running ray / test counters (never reset by a tile)
     unsigned long long rays_primary, rays_shadow, rays_reflection, box_tests, tri_tests;
@@ -133,6 +134,7 @@ struct Params {
     // every depth's arrays, for k_shade's walk up the chain of shading points that coincide (see occlusion_source)
     const uint32_t *parent_q_all; const float *hitb_t_all; const uint32_t *occ_all;
     uint32_t reuse_shadow;                       // option "shadow_reuse"
+    uint32_t *far_list;                          // this depth's reflection paths that need shadow rays of their own (k_bounce appends, k_shadow reads)
     uint32_t *occ;                               // [path][occ_words] shadow-ray verdicts of the current depth, bit i = light i occluded
     uint32_t *stack_color; float *stack_refl;    // [depth][slot]
     uint8_t *term_level;                         // [slot] level at which the chain ended
