@@ -116,8 +116,9 @@ CT_DEV bool load_path(const Params &P, int depth, uint32_t q, uint32_t &slot, in
         int x, y;
         slot = own_slot(P, q);
         if (!slot_pixel(P, slot, x, y, fbi)) return false;
-        r = primary_ray(P, slot, x, y);
         tc = P.hit0_t[slot]; pos = P.hit0_pos[slot];
+        if (pos == kNoPos) return true;                         // a miss: nobody needs its ray again (background pixel)
+        r = primary_ray(P, slot, x, y);
     } else {
         const int cur = depth & 1;
         slot = P.path_slot[cur][q];
