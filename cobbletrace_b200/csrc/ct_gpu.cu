@@ -676,8 +676,11 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     // so the lighting of depth d overlaps the hit chain of depth d+1 and the lighting of the other depths; the
     // persistent CTAs of a later kernel move into an SM as those of an earlier one run out of work, which fills
     // the kernels' tails.  With CT_FLAG_STAGE_TIMING everything is serialised on the main stream instead.
-    if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(pk);
-    else k_primary<false><<<grid, kBlockThreads, 0, st>>>(pk);
+    {
+        const Params v0 = view(0);        // (k_primary also runs the recursion step of depth 0: it needs the depth's queues)
+        if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(v0);
+        else k_primary<false><<<grid, kBlockThreads, 0, st>>>(v0);
+    }
     TRY(mark("primary", 0));
     for (int d = 0; d <= depth_max; d++) {
         const Params v = view(d);
@@ -692,7 +695,15 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
         }
         cudaStream_t side = stages ? st : s.aux[d % 4];
         if (!stages) { CU(cudaEventRecord(s.ev_hit[d], st)); CU(cudaStreamWaitEvent(side, s.ev_hit[d], 0)); }
-        if (depth_max > 0) { k_emit<<<grid, kBlockThreads, 0, st>>>(v, d, work++); TRY(mark("emit", d)); }
+        if (depth_max > 0) {
+            // TraceRay's recursion step runs inside the hit kernels (emit_paths); what is left for a kernel of its own are the
+            // reflection paths k_bounce had parked, whose hit k_overflow has just delivered
+            if (!kFusedEmit) { k_emit<<<grid, kBlockThreads, 0, st>>>(v, d, work++, nullptr, 0); TRY(mark("emit", d)); }
+            else if (d > 0 && s.can_overflow) {
+                k_emit<<<s.n_sm * 2, kBlockThreads, 0, st>>>(v, d, work++, s.ovf_all + (size_t)pk.ovf_cap * ovf_b, ovf_b);
+                TRY(mark("emit_late", d));
+            }
+        }
         if (pk.n_slights > 0) {
             Params vs = v;
             if (s.can_overflow) { vs.ovf = s.ovf_all + (size_t)pk.ovf_cap * ovf_s; vs.ovf_huge = s.ovf_huge_all + (size_t)pk.ovf_cap * ovf_s; }

@@ -206,6 +206,9 @@ CT_DEV bool next_chunk(const Params &P, uint32_t n_chunks, bool &dealt_left, uin
     return false;
 }
 
+constexpr bool kFusedEmit = CT_REFILL_T == 0;      // the hit kernels run TraceRay's recursion step themselves (emit_paths)
+CT_DEV void emit_paths(const Params &P, int depth, bool active, uint32_t q, uint32_t slot, V3 o, V3 d, float tc, uint32_t pos, uint32_t &n_refl);
+
 // Lanes of `idle` in rank order: the r-th idle lane gets item r.
 CT_DEV uint32_t idle_rank(uint32_t idle) { return __popc(idle & ((1u << (threadIdx.x & 31u)) - 1u)); }
 
@@ -272,6 +275,7 @@ struct PrimaryJob {
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __grid_constant__ Params P) {
     LocalCount lc;
+    uint32_t n_refl = 0;
     PrimaryJob job;
     job.chunk = 1u << P.chunk_shift;
     job.n_chunks = (P.n_slots + job.chunk - 1u) >> P.chunk_shift;
@@ -288,8 +292,12 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
         float tc; uint32_t pos;
         const bool found = traverse_closest_any<COUNT>(P, r, got, tc, pos, lc) == kTravHit;   // warp-synchronous
         if (got) job.finish(P, found, tc, pos);
+        if (P.max_depth > 0)          // the recursion step at once, while ray and hit are at hand (no k_emit pass over the tile)
+            emit_paths(P, 0, got, job.q, job.slot, {r64[0], r64[1], r64[2]}, {r64[3], r64[4], r64[5]}, tc,
+                       found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos, n_refl);
     }
 #endif
+    warp_add(&P.tot->rays_reflection, n_refl);
     warp_add(&P.tot->rays_primary, job.n_rays);
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
@@ -366,65 +374,75 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
 
-// TraceRay's recursion step (raythread.cpp:369-373) for the paths alive at `depth`: does the path end here, or does
-// it continue with the reflection ray {position, ReflectRay(-dir, normal), t = 0}?  Needs only the hit records --
-// not the shadow verdicts -- so it runs ahead of k_shadow / k_shade of the same depth (separate streams) and feeds
-// k_bounce of the next one.
-__global__ void __launch_bounds__(kBlockThreads) k_emit(const __grid_constant__ Params P, int depth, int work_idx) {
-    uint32_t n_refl = 0;
-    const uint32_t n = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
+// TraceRay's recursion step (raythread.cpp:369-373) for a path of `depth` whose hit record is final: does the path end here, or
+// does it continue with the reflection ray {position, ReflectRay(-dir, normal), t = 0}?  Needs only the hit -- not the shadow
+// verdicts -- so it runs in the hit kernel itself, in the warp that has just finished the walk (ray and hit are still in
+// registers), and feeds k_bounce of the next depth.  WARP-LEVEL: every lane calls it, `active` = this lane holds such a path.
+CT_DEV void emit_paths(const Params &P, int depth, bool active, uint32_t q, uint32_t slot, V3 o, V3 d, float tc, uint32_t pos, uint32_t &n_refl) {
     const int nxt = (depth & 1) ^ 1;
+    bool emit = false;
+    V3 position = {0, 0, 0}, rdir = {0, 0, 0};
+    if (active) {
+        float reflection = 0.0f;
+        if (pos != kNoPos) reflection = P.materials[P.tris[pos].orig].reflection;
+        const int remaining = P.max_depth - depth;                      // recursionDepth of this TraceRay call
+        if (pos == kNoPos || remaining <= 0 || !(reflection > 0.0f)) {  // miss :385 / :369 (reflection <= 0, NaN-safe)
+            P.term_level[slot] = (uint8_t)depth;
+        } else {
+            V3 p1, e1, e2;
+            load_tri(P.tris, pos, p1, e1, e2);
+            position = vadd(o, vscale((double)tc, d));                  // :360
+            V3 nn = vcross(e1, e2);                                     // NormalOfSceneObject :337-339
+            float dd = vdot(nn, d);
+            V3 normal = (dd < 0.0f) ? nn : vneg(nn);                    // :341-345
+            P.stack_refl[(size_t)depth * P.cap + slot] = reflection;
+            rdir = reflect_ray(vneg(d), normal);                        // :372
+            emit = true;
+        }
+    }
+    // warp-aggregated append of the reflection rays to the next queue
+    uint32_t mask = __ballot_sync(0xffffffffu, emit);
+    if (mask) {
+        uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1, qbase = 0;
+        if (lane == leader) qbase = atomicAdd(&P.sched->queue_count[depth + 1], (uint32_t)__popc(mask));
+        qbase = __shfl_sync(0xffffffffu, qbase, leader);
+        if (emit) {
+            uint32_t nq = qbase + __popc(mask & ((1u << lane) - 1u));
+            CT_CHECK(nq < P.cap && slot < P.cap);
+            double2 *rb = reinterpret_cast<double2 *>(P.ray_buf[nxt] + 6ull * nq);
+            rb[0] = make_double2(position.x, position.y);
+            rb[1] = make_double2(position.z, rdir.x);
+            rb[2] = make_double2(rdir.y, rdir.z);
+            P.path_slot[nxt][nq] = slot;
+            // would a hit with tclosest = 0 put the next shading point exactly here?  (not with a non-finite direction:
+            // 0 * inf = NaN; and -0.0 + 0.0 = +0.0 changes a bit that a light at -0.0 could tell apart)
+            const V3 again = vadd(position, vscale(0.0, rdir));
+            const bool same = __double_as_longlong(again.x) == __double_as_longlong(position.x) &&
+                              __double_as_longlong(again.y) == __double_as_longlong(position.y) &&
+                              __double_as_longlong(again.z) == __double_as_longlong(position.z);
+            P.parent_q[nxt][nq] = q | (same ? 0u : kNoReuse);
+            n_refl++;
+        }
+    }
+}
+
+// The same step as a kernel of its own, for the paths whose hit record a hit kernel could not finish itself: all paths of
+// `depth` (late_list == nullptr: builds in which the hit kernels do not emit, CT_REFILL_T), or the reflection paths k_bounce
+// had parked (their hit came from k_overflow).
+__global__ void __launch_bounds__(kBlockThreads) k_emit(const __grid_constant__ Params P, int depth, int work_idx, const OvfRay *late_list, int ovf_bounce) {
+    uint32_t n_refl = 0;
+    const uint32_t n = late_list ? min(P.sched->ovf_count[ovf_bounce], P.ovf_cap) : (depth == 0 ? depth0_count(P) : P.sched->queue_count[depth]);
     while (true) {
         unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
         if (base >= n) break;
         uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
+        bool active = q < n;
+        if (active && late_list) q = late_list[q].target;
         uint32_t slot = q, pos = kNoPos; int fbi = 0;
         Ray r; float tc = 0.0f;
-        bool active = q < n && load_path(P, depth, q, slot, fbi, r, tc, pos);
-        bool emit = false;
-        V3 position = {0, 0, 0}, rdir = {0, 0, 0};
-        if (active) {
-            float reflection = 0.0f;
-            if (pos != kNoPos) reflection = P.materials[P.tris[pos].orig].reflection;
-            const int remaining = P.max_depth - depth;                      // recursionDepth of this TraceRay call
-            if (pos == kNoPos || remaining <= 0 || !(reflection > 0.0f)) {  // miss :385 / :369 (reflection <= 0, NaN-safe)
-                P.term_level[slot] = (uint8_t)depth;
-            } else {
-                V3 p1, e1, e2;
-                load_tri(P.tris, pos, p1, e1, e2);
-                position = vadd(r.o, vscale((double)tc, r.d));              // :360
-                V3 nn = vcross(e1, e2);                                     // NormalOfSceneObject :337-339
-                float dd = vdot(nn, r.d);
-                V3 normal = (dd < 0.0f) ? nn : vneg(nn);                    // :341-345
-                P.stack_refl[(size_t)depth * P.cap + slot] = reflection;
-                rdir = reflect_ray(vneg(r.d), normal);                      // :372
-                emit = true;
-            }
-        }
-        // warp-aggregated append of the reflection rays to the next queue
-        uint32_t mask = __ballot_sync(0xffffffffu, emit);
-        if (mask) {
-            uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1, qbase = 0;
-            if (lane == leader) qbase = atomicAdd(&P.sched->queue_count[depth + 1], (uint32_t)__popc(mask));
-            qbase = __shfl_sync(0xffffffffu, qbase, leader);
-            if (emit) {
-                uint32_t nq = qbase + __popc(mask & ((1u << lane) - 1u));
-                CT_CHECK(nq < P.cap && slot < P.cap);
-                double2 *rb = reinterpret_cast<double2 *>(P.ray_buf[nxt] + 6ull * nq);
-                rb[0] = make_double2(position.x, position.y);
-                rb[1] = make_double2(position.z, rdir.x);
-                rb[2] = make_double2(rdir.y, rdir.z);
-                P.path_slot[nxt][nq] = slot;
-                // would a hit with tclosest = 0 put the next shading point exactly here?  (not with a non-finite direction:
-                // 0 * inf = NaN; and -0.0 + 0.0 = +0.0 changes a bit that a light at -0.0 could tell apart)
-                const V3 again = vadd(position, vscale(0.0, rdir));
-                const bool same = __double_as_longlong(again.x) == __double_as_longlong(position.x) &&
-                                  __double_as_longlong(again.y) == __double_as_longlong(position.y) &&
-                                  __double_as_longlong(again.z) == __double_as_longlong(position.z);
-                P.parent_q[nxt][nq] = q | (same ? 0u : kNoReuse);
-                n_refl++;
-            }
-        }
+        r.o = {0, 0, 0}; r.d = {0, 0, 0};
+        active = active && load_path(P, depth, q, slot, fbi, r, tc, pos);
+        emit_paths(P, depth, active, q, slot, r.o, r.d, tc, pos, n_refl);
     }
     warp_add(&P.tot->rays_reflection, n_refl);
 }
@@ -489,7 +507,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_shade(const __grid_constant__
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
     LocalCount lc;
-    uint32_t n_parked = 0;
+    uint32_t n_parked = 0, n_refl = 0;
     __shared__ __align__(128) DevWide top_nodes[kTopSmem > 0u ? kTopSmem : 1u];
     __shared__ unsigned long long top_bar;
     const uint32_t n_top = (kTopSmem > 0u && P.wide) ? stage_top_nodes(P, top_nodes, &top_bar, P.n_wide) : 0u;
@@ -501,6 +519,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
         uint32_t q = (uint32_t)base + (threadIdx.x & 31u);
         bool active = q < n;
         bool far = false;            // this path needs shadow rays of its own (its shading point is not, or may not be, its parent's)
+        bool parked = false;
         double r64[kRay64];
         TRay r;
         if (active) {
@@ -522,6 +541,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
                     again = !park_ray(P, ovf_idx, r64, q, 0u);          // parking buffer full: finish in place, no budget
                     budget = 0xffffffffu;
                     far = true;                                         // k_overflow answers later: let k_shadow look at the path
+                    parked = !again;
                 } else {                                                // found is always true: 0 != 1e30f (:227)
                     P.hitb_t[q] = tc;
                     P.hitb_pos[q] = (pos == kNoPos) ? P.pos_of_tri0 : pos;
@@ -530,6 +550,12 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
             }
             active = again;
             if (!__any_sync(kFullMask, again)) break;
+        }
+        if (kFusedEmit) {             // the recursion step of the paths whose hit is final (parked ones: k_emit after k_overflow)
+            const bool fin = q < n && !parked;
+            uint32_t pslot = 0, ppos = kNoPos; float ptc = 0.0f;
+            if (fin) { pslot = P.path_slot[cur][q]; ptc = P.hitb_t[q]; ppos = P.hitb_pos[q]; }
+            emit_paths(P, depth, fin, q, pslot, {r64[0], r64[1], r64[2]}, {r64[3], r64[4], r64[5]}, ptc, ppos, n_refl);
         }
         // warp-aggregated append to the depth's far list (see shading_point_repeats: the others repeat their parent's shading point)
         if (P.reuse_shadow) {
@@ -544,6 +570,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
         }
     }
     warp_add(&P.tot->rays_overflow, n_parked);
+    warp_add(&P.tot->rays_reflection, n_refl);
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
 
