@@ -11,7 +11,7 @@ echo "launch list rc=$?"
 FRAME="python tools/prof_frame.py --frames 2"
 $FRAME > gpurun_out/${TAG}_frame_plain.log 2>&1 &&
 ncu --metrics smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,lts__t_sector_hit_rate.pct,l1tex__t_sector_hit_rate.pct,dram__bytes_read.sum,dram__bytes_write.sum \
-    --clock-control none -k regex:"k_primary|k_emit|k_shadow|k_shade|k_bounce|k_overflow|k_resolve" -s 23 -c 23 --csv --log-file gpurun_out/${TAG}_frame_metrics.csv $FRAME > gpurun_out/${TAG}_ncu_frame.log 2>&1
+    --clock-control none -k regex:"k_primary|k_emit|k_shadow|k_shade|k_bounce|k_overflow|k_resolve|k_subsample|k_supersample" -c 80 --csv --log-file gpurun_out/${TAG}_frame_metrics.csv $FRAME > gpurun_out/${TAG}_ncu_frame.log 2>&1
 echo "frame metrics rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"k_shadow|k_primary|k_bounce" -s 6 -c 6 -f -o gpurun_out/${TAG}_trav $FRAME > gpurun_out/${TAG}_ncu_trav.log 2>&1
 echo "full capture rc=$?"

@@ -118,6 +118,11 @@ def frame_metrics(path, workload="dragon4k", out=None):
     for r in rows[1:]:
         k = (r[ix["ID"]], short(r[ix["Kernel Name"]]))
         per.setdefault(k, {})[r[ix["Metric Name"]]] = (float(r[ix["Metric Value"]].replace(",", "")), r[ix["Metric Unit"]])
+    # the capture may hold several frames: keep the last one (from its k_primary launch on)
+    keys = list(per.keys())
+    starts = [i for i, k in enumerate(keys) if k[1].startswith("k_primary")]
+    if starts:
+        per = collections.OrderedDict((k, per[k]) for k in keys[starts[-1]:])
     agg = collections.OrderedDict()
     print(f"# {path}: one frame of {workload}, kernel by kernel (ncu, serialised)")
     for (kid, name), m in per.items():
