@@ -65,6 +65,7 @@ struct TRay {
     float om;       // max|o_i|, rounded up
     bool filt;      // false: some axis cannot be bounded (d == 0, non-finite, absurd magnitudes) -> exact slab tests only
     bool tfilt;     // false: magnitudes outside the range the triangle filter's error analysis covers
+    float sg;       // tray_nearest_setup: the slop bound sigma of the order-free closest-hit walk, 0 = the ray may not take it
     double *r64;
 };
 
@@ -112,7 +113,40 @@ CT_DEV void tray_setup(TRay &r, const Ray &ray, const double bound[3], double *r
     r.cd = __double2float_ru(__dmul_ru(dm, 0x1p-17));
     r.om = __double2float_ru(om);
     r.t = ray.t;
+    r.sg = 0.0f;
     r.r64 = r64;
+}
+
+// Per-ray set-up of the ORDER-FREE closest-hit walk (traverse_wide_nearest, ct_traverse.cuh): sigma, a bound on
+//     tmin_ref(leaf box of Z) - t_ref(Z)
+// over every triangle Z of the scene that passes the reference's barycentric test for this ray -- how much EARLIER than
+// its own leaf's box a triangle can seem to be hit.  In real arithmetic that is <= 0 (a triangle lies inside the box of
+// its leaf, UpdateNodeBounds bvh.cpp:30-49); what is left is rounding.  With eps = 2^-24, u = 2^-53, B = max bound[k]
+// (>= every vertex coordinate), O = max|o_k|, D = max|d_k| and M = max_k (bound[k] + |o_k|) / |d_k| (>= every slab
+// quotient of the ray and >= the t of any point inside the scene's box):
+//   * IntersectTriangle (bvh.cpp:147-163) evaluates the determinants A, S, Q, T in fp64 from exact inputs -- six triple
+//     products each, <= 6 roundings per term: |dA| <= 144 u D B^2, |dS|, |dQ| <= 72 u (O + B) D B, |dT| <= 144 u B^2 (O + B)
+//     -- rounds each to float and multiplies by float(1 / a), |a| >= 1e-4 (1 - eps) (bvh.cpp:152).  Under the magnitude
+//     limits below every |d.| / |A| <= 2^-20 (dT: relative to M), so the computed u, v, t are the true u*, v*, t* of the
+//     plane intersection up to relative errors < 20 eps and absolute errors < 2^-20:
+//         t_ref >= t* - 20 eps |t*| - 100 eps M ,   u* >= -17 eps, v* >= -17 eps, u* + v* <= 1 + 73 eps  (passes only);
+//   * the point o + t* d = (1 - u* - v*) p1 + u* p2 + v* p3 therefore leaves the leaf's box by at most 107 eps times the
+//     box's extent on any axis, i.e. t* >= (near quotient of axis k) - 107 eps * ext_k / |d_k| >= ... - 214 eps M;
+//   * the reference's float tmin of the box exceeds the true entry distance by at most 1.01 eps M (tray_setup).
+// Sum: < 340 eps M.  sigma = 512 eps M = 2^-15 M, rounded up; the slack also covers the float additions the walk does
+// with it.  Rays outside the magnitude limits (or without a usable slab filter) get sigma = 0: they take the ordered walk.
+CT_DEV void tray_nearest_setup(TRay &r, const double bound[3]) {
+    r.sg = 0.0f;
+    if (!r.filt) return;
+    const double *o = r.r64, *d = r.r64 + 3;
+    const double B = fmax(fmax(bound[0], bound[1]), bound[2]);
+    const double O = fmax(fmax(fabs(o[0]), fabs(o[1])), fabs(o[2])), D = fmax(fmax(fabs(d[0]), fabs(d[1])), fabs(d[2]));
+    double M = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) M = fmax(M, (bound[k] + fabs(o[k])) * fabs((double)r.rdf[k]));      // rdf = (1/d)(1 + 2.01 eps)
+    // 144 u D B^2 / 1e-4 <= 2^-20  <=>  D B^2 <= 2^12.7; the same for (O + B) D B; dT / |A| <= 100 eps M holds with M >= (B + O) / (2 D)
+    const bool ok = (D * B * B <= 4096.0) && ((O + B) * D * B <= 4096.0) && (M > 0x1p-60) && (M < 0x1p60);
+    if (ok) r.sg = __double2float_ru(M * (0x1p-15 * 1.000001));
 }
 
 // r64[6..8] = correctly rounded 1/d, r64[9] = 1 when some 1/d leaves the normal range (then box_times divides).

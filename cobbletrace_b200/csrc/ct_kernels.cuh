@@ -247,6 +247,7 @@ struct PrimaryJob {
             if (slot < P.n_slots && slot_pixel(P, slot, x, y, fbi)) {
                 const Ray ray = primary_ray(P, slot, x, y);
                 tray_setup(r, ray, P.bound, r64);
+                tray_nearest_setup(r, P.bound);
                 got = true;
             }
         }
@@ -817,6 +818,7 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
     if (active) {
         r.o = ld3(org + 3ull * i); r.d = ld3(dir + 3ull * i); r.t = t0[i];
         tray_setup(tr, r, P.bound, r64);
+        tray_nearest_setup(tr, P.bound);
     }
     LocalCount lc; float tc, tc2; uint32_t pos, pos2;
     const bool first_line = r.t == 0.0f;

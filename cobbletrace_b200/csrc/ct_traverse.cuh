@@ -30,10 +30,30 @@ CT_DEV void prefetch_children(const Params &P, const DevPair32 &pr) {
 #endif
 }
 
+// 32 bytes per lane in ONE load instruction (ld.global.nc.v8 -> LDG.E.256, new with sm_100): a whole child of a wide
+// node, half a child pair.  The lanes of a walking warp read 32 different records, so every load instruction costs the
+// L1 one tag look-up per lane whatever its width -- the walks are bound by exactly that (l1tex throughput 79 % of peak in
+// k_shadow) -- and a 256-bit load halves the look-ups per record.  -DCT_LDG256=0: two 128-bit loads.  p: 32-byte aligned.
+#ifndef CT_LDG256
+#define CT_LDG256 1
+#endif
+CT_DEV void ldg256(const void *p, float4 &a, uint4 &b) {
+#if CT_LDG256
+    uint32_t x0, x1, x2, x3;
+    asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+    a = make_float4(__uint_as_float(x0), __uint_as_float(x1), __uint_as_float(x2), __uint_as_float(x3));
+#else
+    a = __ldg(reinterpret_cast<const float4 *>(p));
+    b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+#endif
+}
+
 CT_DEV void load_pair32(const DevPair32 *pairs, uint32_t pid, DevPair32 &p) {
-    const float4 *q = reinterpret_cast<const float4 *>(pairs + pid);
-    float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    uint4 m = __ldg(reinterpret_cast<const uint4 *>(q + 3));
+    float4 a, c; uint4 bu, m;
+    ldg256(pairs + pid, a, bu);
+    ldg256(reinterpret_cast<const char *>(pairs + pid) + 32, c, m);
+    const float4 b = make_float4(__uint_as_float(bu.x), __uint_as_float(bu.y), __uint_as_float(bu.z), __uint_as_float(bu.w));
     p.lmin[0] = a.x; p.lmin[1] = a.y; p.lmin[2] = a.z; p.lmax[0] = a.w; p.lmax[1] = b.x; p.lmax[2] = b.y;
     p.rmin[0] = b.z; p.rmin[1] = b.w; p.rmin[2] = c.x; p.rmax[0] = c.y; p.rmax[1] = c.z; p.rmax[2] = c.w;
     p.l_ref = m.x; p.l_cnt = m.y; p.r_ref = m.z; p.r_cnt = m.w;
@@ -512,8 +532,9 @@ CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint
                     else {
 #pragma unroll
                         for (int e = kWide - 1; e >= 0; e--) {             // reverse: the first accepted child is popped first
-                            const float4 a = kTopSmem > 0u ? q[2 * e] : __ldg(q + 2 * e);
-                            const uint4 b = kTopSmem > 0u ? *reinterpret_cast<const uint4 *>(q + 2 * e + 1) : __ldg(reinterpret_cast<const uint4 *>(q + 2 * e + 1));
+                            float4 a; uint4 b;
+                            if (kTopSmem > 0u) { a = q[2 * e]; b = *reinterpret_cast<const uint4 *>(q + 2 * e + 1); }
+                            else ldg256(q + 2 * e, a, b);
                             const float bmin[3] = {a.x, a.y, a.z}, bmax[3] = {a.w, __uint_as_float(b.x), __uint_as_float(b.y)};
                             const bool hit = box_maybe<MODE == kAnyHit>(r, bmin, bmax);
                             if (MODE == kAnyHit) {
@@ -607,8 +628,8 @@ CT_DEV int traverse_wide_closest(const Params &P, TRay &r, bool active, float &t
                     if (COUNT) lc.box += kWide;
 #pragma unroll
                     for (int e = kWide - 1; e >= 0; e--) {                 // reverse: the first accepted child is popped first
-                        const float4 a = __ldg(q + 2 * e);
-                        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(q + 2 * e + 1));
+                        float4 a; uint4 b;
+                        ldg256(q + 2 * e, a, b);
                         const float bmin[3] = {a.x, a.y, a.z}, bmax[3] = {a.w, __uint_as_float(b.x), __uint_as_float(b.y)};
                         if (box_maybe<false>(r, bmin, bmax)) { stk[sp] = make_uint2(b.z, b.w); sp++; }
                     }
@@ -670,6 +691,159 @@ CT_DEV int traverse_wide_closest(const Params &P, TRay &r, bool active, float &t
     return r.t != kRayTInit ? kTravHit : kTravMiss;
 }
 
+// IntersectBVHClosest as an ORDER-FREE search (primary rays, ray.t = 1e30f).  On a nested tree the reference tests a triangle
+// iff its LEAF's own box passes IntersectAABB against the ray.t of that moment (see traverse_wide_closest).  Let G be the
+// triangles with a barycentric pass and 1e-4 < t < 1e30 whose leaf box passes the two conditions that do not involve ray.t,
+// m = min t over G, and sigma the ray's slop bound (tray_nearest_setup:  tmin(leaf of Z) <= t_Z + sigma  for every Z).  Then
+//   * ray.t never drops below m; the first triangle with t = m is tested unless ray.t <= tmin(its leaf) <= m + sigma by
+//     then -- either way the walk ends with ray.t <= m + sigma;
+//   * a triangle with t > tau changes the fate of one with t <= tau only by lowering ray.t to a value that blocks the
+//     latter's leaf, i.e. only if  tmin(that leaf) >= t > tau.
+// So with S = { Z in G : t_Z <= m + sigma }:  if every member of S has tmin(leaf) <= m + sigma, nothing outside S can block
+// a member of S, a tested member of S lowers ray.t below anything outside S, and replaying the reference's update rules
+// (bvh.cpp:161, 178, 212) over S alone, in leaf-position order (= the reference's test order), gives the reference's
+// ray.t, tclosest and closestIndex bit for bit.  Finding S needs no particular order: the walk keeps best = min t so far
+// and prunes a box only when the LOWER end of its near bracket is >= best + 2 sigma: every triangle Z below it has
+// t_Z >= tmin(leaf of Z) - sigma >= tmin(box) - sigma >= best + sigma >= m + sigma (boxes are nested, best >= m; sigma
+// carries slack, so the inequality is strict) and is not in S.  Each barycentric pass within best + sigma becomes a candidate once the exact fp64 test of its own leaf box confirms membership in G (that test also
+// yields the reference's tmin for the replay).  The rare leftovers -- more than kNearCand candidates, a member of S whose
+// leaf starts beyond m + sigma, t >= FINF (raythread.cpp:204's tclosest quirk), a full stack -- return kTravOverBudget
+// and take traverse_closest.  oracle/ct_oracle.c holds the CPU prototype (tests/test_free_closest_prototype.py).
+// What the freedom buys: conservative one-sided box tests over the wide tree (half the FMAs of the certified brackets, half
+// the dependent fetches, no fp64 fallback), leaves tested by the warp together, and a walk that may be cut short.
+// WARP-SYNCHRONOUS, same contract as traverse_closest for the rays it decides.
+#ifndef CT_NEAR_LEAVES
+#define CT_NEAR_LEAVES 1
+#endif
+#ifndef CT_NEAR_LANES
+#define CT_NEAR_LANES 24
+#endif
+constexpr int kNearLeaves = CT_NEAR_LEAVES, kNearLanes = CT_NEAR_LANES, kNearCand = 4;      // kNearLeaves = 0: leaves are tested on the spot
+constexpr int kNearLeavesCap = kNearLeaves > 0 ? kNearLeaves : 1;
+template <bool COUNT>
+CT_DEV int traverse_wide_nearest(const Params &P, const TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    uint2 stk[kWideStack];
+    float stk_near[kWideStack];                           // lower end of the pushed child's near bracket
+    uint2 leaf[kNearLeavesCap];
+    float cand_t[kNearCand], cand_tmin[kNearCand];
+    uint32_t cand_pos[kNearCand], cand_code[kNearCand];
+    int sp = 0, nleaf = 0, ncand = 0;
+    float best = kRayTInit, band = kRayTInit, thr = kRayTInit;     // band >= best + sigma, thr >= best + 2 sigma
+    uint32_t cur_ref = 0u, cur_cnt = P.root_cnt;
+    if (P.root_cnt > 0u) cur_ref = P.root_ref;
+    int state = 0;
+    bool undecided = false;
+    tclosest = kFinf;          // raythread.cpp:204
+    closest_pos = kNoPos;
+    if (active) {
+        if (COUNT) lc.box++;
+        state = root_accept(P, r) ? 1 : 0;
+    }
+    auto test_triangle = [&](uint32_t pos) {
+        if (COUNT) lc.tri++;
+        const TriHit th = leaf_triangle<false, COUNT>(P, r, pos, lc);
+        if (th.hit & (th.t > kEps) & (th.t < kRayTInit)) {                     // would lower a ray.t of 1e30f (bvh.cpp:161)
+            if (!(th.t < kFinf)) undecided = true;
+            else if (th.t <= band) {
+                const uint32_t code = __ldg(P.tri_parent + pos);               // the triangle's leaf: 2 * pair + side
+                if (COUNT) lc.box_exact++;
+                const BoxTimes e = code == kNoPos ? box_times(r.r64, P.root_min, P.root_max) : exact_child(P.pairs64, code >> 1, code & 1u, r.r64);
+                if ((e.tmax >= e.tmin) & (e.tmax > 0.0f)) {                    // the leaf is one the reference can reach: Z is in G
+                    if (th.t < best) { best = th.t; band = __fadd_ru(best, r.sg); thr = __fadd_ru(band, r.sg); }
+                    if (ncand == kNearCand) {                                  // drop what has fallen out of the band
+                        int k = 0;
+                        for (int j = 0; j < kNearCand; j++)
+                            if (cand_t[j] <= band) { cand_t[k] = cand_t[j]; cand_tmin[k] = cand_tmin[j]; cand_pos[k] = cand_pos[j]; cand_code[k] = cand_code[j]; k++; }
+                        ncand = k;
+                    }
+                    if (ncand == kNearCand) undecided = true;
+                    else { cand_t[ncand] = th.t; cand_tmin[ncand] = e.tmin; cand_pos[ncand] = pos; cand_code[ncand] = code; ncand++; }
+                }
+            }
+        }
+    };
+    while (true) {
+        // ---- walk phase: one wide-node visit per walking lane and iteration
+        while (__any_sync(kFullMask, (state == 1) & (nleaf < kNearLeavesCap)) && __popc(__ballot_sync(kFullMask, nleaf > 0)) < kNearLanes) {
+            if ((state == 1) & (nleaf < kNearLeavesCap)) {
+                if (cur_cnt > 0u) {
+                    if (kNearLeaves == 0) {                                 // on the spot
+                        for (uint32_t i = 0; i < cur_cnt; i++) test_triangle(cur_ref + i);
+                        if (undecided) { state = 0; sp = 0; }
+                    }
+                    else { leaf[nleaf] = make_uint2(cur_ref, cur_cnt); nleaf++; }
+                } else if (sp > kWideStack - kWide) {
+                    undecided = true; state = 0; nleaf = 0; sp = 0;
+                } else {
+                    const float4 *q = reinterpret_cast<const float4 *>(P.wide + cur_ref);
+                    if (COUNT) lc.box += kWide;
+#pragma unroll
+                    for (int e = kWide - 1; e >= 0; e--) {                 // reverse: the first accepted child is popped first
+                        float4 a; uint4 b;
+                        ldg256(q + 2 * e, a, b);
+                        const float bmax1 = __uint_as_float(b.x), bmax2 = __uint_as_float(b.y);
+                        const bool px = r.rdf[0] > 0.0f, py = r.rdf[1] > 0.0f, pz = r.rdf[2] > 0.0f;
+                        const float n0 = __fmaf_rd(px ? a.x : a.w, r.rdf[0], r.cl[0]), f0 = __fmaf_ru(px ? a.w : a.x, r.rdf[0], r.cu[0]);
+                        const float n1 = __fmaf_rd(py ? a.y : bmax1, r.rdf[1], r.cl[1]), f1 = __fmaf_ru(py ? bmax1 : a.y, r.rdf[1], r.cu[1]);
+                        const float n2 = __fmaf_rd(pz ? a.z : bmax2, r.rdf[2], r.cl[2]), f2 = __fmaf_ru(pz ? bmax2 : a.z, r.rdf[2], r.cu[2]);
+                        const float near_lo = fmaxf(fmaxf(n0, n1), n2), far_hi = fminf(fminf(f0, f1), f2);      // box_maybe's brackets
+                        const bool no = (far_hi < near_lo) | (far_hi <= 0.0f) | (near_lo >= thr);
+                        if (!no) { stk[sp] = make_uint2(b.z, b.w); stk_near[sp] = near_lo; sp++; }
+                    }
+                }
+                if (state == 1) {
+                    state = 0;
+                    while (sp > 0) {                                       // best may have dropped since the child was pushed
+                        --sp;
+                        if (stk_near[sp] >= thr) continue;
+                        const uint2 t = stk[sp]; cur_ref = t.x; cur_cnt = t.y; state = 1;
+                        break;
+                    }
+                }
+            }
+        }
+        // ---- leaf phase: one triangle per lane and iteration
+        int li = 0;
+        uint32_t tri = 0;
+        while (__any_sync(kFullMask, li < nleaf)) {
+            if (li < nleaf) {
+                const uint2 lf = leaf[li];
+                const uint32_t pos = lf.x + tri;
+                test_triangle(pos);
+                if (++tri == lf.y) { tri = 0; li++; }
+            }
+        }
+        nleaf = 0;
+        if (undecided) { state = 0; sp = 0; }
+        if (!__any_sync(kFullMask, state == 1)) break;
+    }
+    if (!active) return kTravMiss;
+    if (undecided) return kTravOverBudget;
+    if (best == kRayTInit) return kTravMiss;                                           // ray.t never changes
+    // ---- S, its precondition, and the replay in leaf-position order
+    int n = 0;
+    for (int j = 0; j < ncand; j++)
+        if (cand_t[j] <= band) { cand_t[n] = cand_t[j]; cand_tmin[n] = cand_tmin[j]; cand_pos[n] = cand_pos[j]; cand_code[n] = cand_code[j]; n++; }
+    for (int j = 0; j < n; j++) if (!(cand_tmin[j] <= band)) return kTravOverBudget;
+    for (int j = 1; j < n; j++) {
+        const float zt = cand_t[j], zm = cand_tmin[j]; const uint32_t zp = cand_pos[j], zc = cand_code[j];
+        int k = j;
+        while (k > 0 && cand_pos[k - 1] > zp) { cand_t[k] = cand_t[k - 1]; cand_tmin[k] = cand_tmin[k - 1]; cand_pos[k] = cand_pos[k - 1]; cand_code[k] = cand_code[k - 1]; k--; }
+        cand_t[k] = zt; cand_tmin[k] = zm; cand_pos[k] = zp; cand_code[k] = zc;
+    }
+    float rt = kRayTInit;
+    uint32_t entered = 0xfffffffeu;                                                    // (no leaf has this code)
+    for (int j = 0; j < n; j++) {
+        if (cand_code[j] != entered) {                                                 // the box is tested once per leaf visit
+            if (!(cand_tmin[j] < rt)) continue;                                        // bvh.cpp:178, the leaf's own box
+            entered = cand_code[j];
+        }
+        rt = macro_min(rt, cand_t[j]);                                                 // bvh.cpp:161
+        if (rt != kRayTInit && rt < tclosest) { closest_pos = cand_pos[j]; tclosest = rt; }   // bvh.cpp:212
+    }
+    return rt != kRayTInit ? kTravHit : kTravMiss;
+}
+
 // The closest-hit walk for every lane's ray: over the wide tree where the ray allows conservative box tests, the binary
 // walk with the reference's verdict at every box otherwise.
 // Measured: the wide closest-hit walk is 7 % faster than the binary one on the dragon-class frame, 8 % slower
@@ -678,8 +852,23 @@ CT_DEV int traverse_wide_closest(const Params &P, TRay &r, bool active, float &t
 #ifndef CT_WIDE_CLOSEST
 #define CT_WIDE_CLOSEST 0
 #endif
+#ifndef CT_NEAREST
+#define CT_NEAREST 0                 // 1: primary rays take the order-free walk (traverse_wide_nearest) where the ray allows it -- measured slower, DESIGN.md 5
+#endif
 template <bool COUNT>
 CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    if (CT_NEAREST) {
+        // r.sg > 0: tray_nearest_setup found the ray within the limits of the slop analysis (and r.filt); ray.t must be 1e30f
+        const bool fr = active & (r.sg > 0.0f) & (r.t == kRayTInit) & (P.nested != 0u) & (P.wide != nullptr);
+        int res = traverse_wide_nearest<COUNT>(P, r, fr, tclosest, closest_pos, lc);
+        const bool ordered = active & (!fr | (res == kTravOverBudget));
+        if (__any_sync(kFullMask, ordered)) {                          // the ordered walk decides the rest
+            float tc2; uint32_t pos2;
+            const int res2 = traverse_closest<COUNT>(P, r, ordered, tc2, pos2, lc);
+            if (ordered) { res = res2; tclosest = tc2; closest_pos = pos2; }
+        }
+        return res;
+    }
     if (!CT_WIDE_CLOSEST) return traverse_closest<COUNT>(P, r, active, tclosest, closest_pos, lc);
     const bool cons = r.filt & (P.nested != 0u) & (P.wide != nullptr);
     const float t0 = r.t;

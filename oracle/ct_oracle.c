@@ -618,3 +618,137 @@ uint64_t ct_oracle_prehit_check(const ct_oracle_scene *s, uint64_t n, const doub
     if (n_found) *n_found = found;
     return bad;
 }
+
+/* ---- prototype: the WHOLE closest-hit walk as an order-free search + a replay of the near-minimum candidates ----------
+ * (what cobbletrace_b200's traverse_wide_nearest does on the device; checked here, on the CPU, against bvh_closest.)
+ * On a nested tree the reference tests triangle Z iff its LEAF's box passes IntersectAABB against the ray.t of that moment
+ * (DESIGN.md 2).  With G = the triangles with a barycentric pass and 1e-4 < t < 1e30 in leaves whose box passes the two
+ * conditions that do not depend on ray.t, and m = min t over G:
+ *   * ray.t never drops below m, and ends at <= m + sigma, where sigma bounds  tmin(leaf box of Z) - t_Z  over all Z
+ *     (a triangle lies inside its leaf's box, so only rounding can make its t smaller than the box's entry distance);
+ *   * a triangle with t > tau can change the fate of one with t <= tau only by blocking its leaf, i.e. only if that
+ *     leaf's tmin >= t > tau.
+ * So: find, in ANY order and pruning boxes whose tmin > best + 2 sigma, every member of G with t <= m + sigma (= S); if
+ * every member of S has tmin(leaf) <= m + sigma, replaying the reference's update rules over S alone, in leaf-position
+ * order, yields the reference's ray.t / tclosest / closestIndex.  Otherwise (and for m >= FINF) the caller falls back to
+ * the ordered walk.  order: 0 = left child first, 1 = nearer child first.
+ * stats[0] += box tests, stats[1] += triangle tests, stats[2] += fallbacks, stats[3] = max |S| seen. */
+typedef struct { float t, tmin; uint32_t pos, leaf; } free_cand;
+typedef struct {
+    const ct_oracle_scene *s; const ray *r; double sigma; double best;
+    free_cand cand[64]; int n_cand, overflow; uint64_t *stats;
+} free_ctx;
+
+static int box_times_ref(const ray *r, const double *bmin, const double *bmax, float *tmin_out) {
+    float tx1 = (float)((bmin[0] - r->org.x) / r->dir.x), tx2 = (float)((bmax[0] - r->org.x) / r->dir.x);
+    float tmin = MACRO_MIN(tx1, tx2), tmax = MACRO_MAX(tx1, tx2);
+    float ty1 = (float)((bmin[1] - r->org.y) / r->dir.y), ty2 = (float)((bmax[1] - r->org.y) / r->dir.y);
+    tmin = MACRO_MAX(tmin, MACRO_MIN(ty1, ty2)); tmax = MACRO_MIN(tmax, MACRO_MAX(ty1, ty2));
+    float tz1 = (float)((bmin[2] - r->org.z) / r->dir.z), tz2 = (float)((bmax[2] - r->org.z) / r->dir.z);
+    tmin = MACRO_MAX(tmin, MACRO_MIN(tz1, tz2)); tmax = MACRO_MIN(tmax, MACRO_MAX(tz1, tz2));
+    *tmin_out = tmin;
+    return tmax >= tmin && tmax > 0;
+}
+
+static void free_leaf(free_ctx *c, uint32_t node, float leaf_tmin) {
+    const ct_oracle_scene *s = c->s;
+    uint32_t first = s->node_first[node];
+    for (uint32_t i = 0; i < s->node_count[node]; i++) {
+        ray tmp = *c->r; tmp.t = RAY_T_INIT;
+        c->stats[1]++;
+        if (!intersect_triangle(&tmp, s->tri + 9 * (size_t)s->tri_index[first + i]) || tmp.t == RAY_T_INIT) continue;
+        if ((double)tmp.t > c->best + c->sigma) continue;
+        if ((double)tmp.t < c->best) c->best = (double)tmp.t;
+        if (c->n_cand == 64) {                                   /* drop what has fallen out of the band */
+            int k = 0;
+            for (int j = 0; j < c->n_cand; j++) if ((double)c->cand[j].t <= c->best + c->sigma) c->cand[k++] = c->cand[j];
+            c->n_cand = k;
+            if (k == 64) { c->overflow = 1; continue; }
+        }
+        free_cand z = {tmp.t, leaf_tmin, first + i, node};
+        c->cand[c->n_cand++] = z;
+    }
+}
+
+static void free_walk(free_ctx *c, uint32_t node, float node_tmin, int order) {
+    const ct_oracle_scene *s = c->s;
+    if ((double)node_tmin > c->best + 2.0 * c->sigma) return;                     /* the deferred distance test */
+    if (s->node_count[node] > 0) { free_leaf(c, node, node_tmin); return; }
+    uint32_t l = s->node_left[node], rgt = l + 1;
+    float tl, tr;
+    c->stats[0] += 2;
+    int hl = box_times_ref(c->r, s->node_min + 3 * (size_t)l, s->node_max + 3 * (size_t)l, &tl);
+    int hr = box_times_ref(c->r, s->node_min + 3 * (size_t)rgt, s->node_max + 3 * (size_t)rgt, &tr);
+    if (order == 1 && hl && hr && tr < tl) {
+        free_walk(c, rgt, tr, order); free_walk(c, l, tl, order);
+    } else {
+        if (hl) free_walk(c, l, tl, order);
+        if (hr) free_walk(c, rgt, tr, order);
+    }
+}
+
+/* Returns found (0 / 1), or -1 when the ordered walk must decide (*index / *tclosest untouched then). */
+int ct_oracle_closest_free(const ct_oracle_scene *s, const double org[3], const double dir[3], int order,
+                           uint32_t *index, float *tclosest, uint64_t *stats) {
+    ray r = {v_load(org), v_load(dir), RAY_T_INIT};
+    free_ctx c; memset(&c, 0, sizeof c);
+    c.s = s; c.r = &r; c.stats = stats; c.best = (double)RAY_T_INIT;
+    double m = 0;
+    for (int a = 0; a < 3; a++) {
+        double bound = 0;
+        bound = fmax(fabs(s->node_min[a]), fabs(s->node_max[a]));                  /* node 0 holds every triangle */
+        double mk = (bound + fabs(org[a])) / fabs(dir[a]);
+        if (!(mk < 1e30)) { stats[2]++; return -1; }                               /* zero / non-finite direction component */
+        m = fmax(m, mk);
+    }
+    c.sigma = m * 0x1p-16;
+    float t0;
+    stats[0]++;
+    if (!box_times_ref(&r, s->node_min, s->node_max, &t0)) { *index = 0; *tclosest = FINF; return 0; }
+    free_walk(&c, 0, t0, order);
+    if (c.overflow) { stats[2]++; return -1; }
+    if (c.best == (double)RAY_T_INIT) { *index = 0; *tclosest = FINF; return 0; }
+    if (c.best >= (double)FINF) { stats[2]++; return -1; }
+    const double tau = c.best + c.sigma;
+    int n = 0;
+    for (int j = 0; j < c.n_cand; j++) if ((double)c.cand[j].t <= tau) c.cand[n++] = c.cand[j];
+    if ((uint64_t)n > stats[3]) stats[3] = (uint64_t)n;
+    for (int j = 0; j < n; j++) if (!((double)c.cand[j].tmin <= tau)) { stats[2]++; return -1; }
+    for (int j = 1; j < n; j++) {                                                  /* leaf-position order = the reference's test order */
+        free_cand z = c.cand[j]; int k = j;
+        while (k > 0 && c.cand[k - 1].pos > z.pos) { c.cand[k] = c.cand[k - 1]; k--; }
+        c.cand[k] = z;
+    }
+    float rt = RAY_T_INIT, tc = FINF; uint32_t idx = 0;
+    uint32_t entered = 0xffffffffu;                                                /* the box is tested once per leaf visit, not per triangle */
+    for (int j = 0; j < n; j++) {
+        if (c.cand[j].leaf != entered) {
+            if (!(c.cand[j].tmin < rt)) continue;                                  /* bvh.cpp:178 for the leaf's own box */
+            entered = c.cand[j].leaf;
+        }
+        rt = MACRO_MIN(rt, c.cand[j].t);                                           /* bvh.cpp:161 (t > 1e-4 by construction) */
+        if (rt != RAY_T_INIT && rt < tc) { idx = s->tri_index[c.cand[j].pos]; tc = rt; }   /* bvh.cpp:212 */
+    }
+    *index = idx; *tclosest = tc;
+    return rt != RAY_T_INIT;
+}
+
+/* Both walks over n rays; returns how many rays the free walk answered differently (fallbacks excluded, counted in stats[2]).
+ * ref_stats[0] / [1] += the reference walk's box / triangle tests. */
+uint64_t ct_oracle_free_check(const ct_oracle_scene *s, uint64_t n, const double *org, const double *dir, int order,
+                              uint64_t *stats, uint64_t *ref_stats) {
+    uint64_t bad = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t ia = 0, ib = 0; float ta = 0, tb = 0;
+        ctx cx; memset(&cx, 0, sizeof cx); cx.s = s;
+        ray r = {v_load(org + 3 * i), v_load(dir + 3 * i), RAY_T_INIT};
+        ta = FINF; ia = 0;
+        bvh_closest(&cx, &r, 0, &ta, &ia);
+        int fa = r.t != RAY_T_INIT;
+        ref_stats[0] += cx.c.box_tests; ref_stats[1] += cx.c.tri_tests;
+        int fb = ct_oracle_closest_free(s, org + 3 * i, dir + 3 * i, order, &ib, &tb, stats);
+        if (fb < 0) continue;
+        if (fa != fb || ia != ib || memcmp(&ta, &tb, sizeof ta) != 0) bad++;
+    }
+    return bad;
+}

@@ -91,6 +91,13 @@ int ct_oracle_closest_prehit(const ct_oracle_scene *s, const uint32_t *node_pare
 /* Both walks over n rays; returns how many differ in found / index / tclosest (bitwise). */
 uint64_t ct_oracle_prehit_check(const ct_oracle_scene *s, uint64_t n, const double *org, const double *dir, uint64_t *n_found);
 
+/* Prototype of the order-free closest-hit walk (see the comment in ct_oracle.c).  order: 0 left child first, 1 nearer child first.
+ * Returns found, or -1 where the ordered walk must decide.  stats[4]: box tests, triangle tests, fallbacks, max candidates. */
+int ct_oracle_closest_free(const ct_oracle_scene *s, const double org[3], const double dir[3], int order,
+                           uint32_t *index, float *tclosest, uint64_t *stats);
+uint64_t ct_oracle_free_check(const ct_oracle_scene *s, uint64_t n, const double *org, const double *dir, int order,
+                              uint64_t *stats, uint64_t *ref_stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,8 @@ def lib():
         L.ct_oracle_intersect_aabb.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.ct_oracle_prehit_check.restype = C.c_uint64
         L.ct_oracle_prehit_check.argtypes = [C.POINTER(_Scene), C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.ct_oracle_free_check.restype = C.c_uint64
+        L.ct_oracle_free_check.argtypes = [C.POINTER(_Scene), C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ct_oracle_closest.restype = C.c_int
         L.ct_oracle_closest.argtypes = [C.POINTER(_Scene), C.c_void_p, C.c_void_p, C.c_float, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         L.ct_oracle_shade_color.restype = C.c_uint32
@@ -151,6 +153,16 @@ def prehit_check(scene: "OracleScene", org, direction):
     found = C.c_uint64()
     bad = lib().ct_oracle_prehit_check(C.byref(scene.c), org.shape[0], _ptr(org), _ptr(direction), C.byref(found))
     return int(bad), int(found.value)
+
+
+def free_check(scene: "OracleScene", org, direction, order=1):
+    """Prototype check (ct_oracle.c): reference-order closest-hit walk vs the order-free walk + candidate replay.
+    Returns (rays that differ, stats dict)."""
+    org = np.ascontiguousarray(org, np.float64); direction = np.ascontiguousarray(direction, np.float64)
+    st = np.zeros(4, np.uint64); ref = np.zeros(2, np.uint64)
+    bad = lib().ct_oracle_free_check(C.byref(scene.c), org.shape[0], _ptr(org), _ptr(direction), order, _ptr(st), _ptr(ref))
+    return int(bad), {"box": int(st[0]), "tri": int(st[1]), "fallback": int(st[2]), "max_cand": int(st[3]),
+                      "ref_box": int(ref[0]), "ref_tri": int(ref[1]), "rays": int(org.shape[0])}
 
 
 def camera_rotation(yaw=0.0, pitch=0.0, roll=0.0):

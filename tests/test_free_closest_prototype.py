@@ -1,0 +1,40 @@
+"""The closest-hit walk as an order-free search, checked on the CPU before the kernel (traverse_wide_nearest) relies on it.
+oracle/ct_oracle.c holds a prototype: any visit order, boxes pruned with a margin against the best t so far, the candidates
+within a rounding slop of the minimum replayed in leaf order with the reference's update rules -- or "undecided", where the
+caller falls back to the ordered walk.  Every ray the prototype decides must equal the reference-order walk bit for bit
+(found, triangle index, tclosest), for both visit orders."""
+import numpy as np
+import pytest
+
+from oracle import ct_oracle_py as O
+from conftest import load_fuzz_case
+from test_prehit_prototype import camera_rays
+
+
+@pytest.mark.parametrize("name,H", [("scene_file_cube", 96), ("scene_import", 96), ("scene_import_bunny", 128), ("pc_big", 96)])
+def test_free_walk_equals_reference_walk_on_bundled_scenes(name, H, scene_loader):
+    fs = scene_loader(name)
+    sc = O.OracleScene(fs)
+    rng = np.random.default_rng(7)
+    for order in (0, 1):
+        for jitter in (0.0, 0.003):
+            org, d = camera_rays(fs, H, H, rng, jitter)
+            bad, st = O.free_check(sc, org, d, order)
+            assert bad == 0, (name, order, jitter, bad, st)
+            # the axis-aligned scenes are where a triangle's t and its leaf box's entry distance tie: still decided
+            assert st["fallback"] <= 0.02 * st["rays"] + 2 * H, (name, order, jitter, st)    # (x = 0 / y = 0 lines: zero direction component)
+        c = fs.tri.reshape(-1, 3).mean(0)
+        ext = np.ptp(fs.tri.reshape(-1, 3), axis=0).max()
+        org = c + rng.normal(size=(4000, 3)) * ext * 0.7
+        bad, st = O.free_check(sc, org, rng.normal(size=(4000, 3)), order)
+        assert bad == 0, (name, order, "random", bad, st)
+
+
+def test_free_walk_equals_reference_walk_on_generated_scenes(golden):
+    rng = np.random.default_rng(8)
+    for k in golden["fuzz"]:
+        fs, _ = load_fuzz_case(k)
+        org, d = camera_rays(fs, 48, 48, rng, 0.002)
+        for order in (0, 1):
+            bad, st = O.free_check(O.OracleScene(fs), org, d, order)
+            assert bad == 0, (k, order, bad, st)
