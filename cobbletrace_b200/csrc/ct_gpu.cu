@@ -1137,7 +1137,7 @@ int ct_gpu_debug_closest(int device, uint32_t n, const double *origins, const do
     CUX(cudaMemcpy(d_d, directions, 24ull * n, cudaMemcpyHostToDevice));
     CUX(cudaMemcpy(d_t0, t0, 4ull * n, cudaMemcpyHostToDevice));
     CUX(cudaStreamSynchronize(s.stream));
-    k_debug_closest<<<(n + 127) / 128, 128, 0, s.stream>>>(s.p, n, d_o, d_d, d_t0, d_f, d_i, d_tc);
+    k_debug_closest<<<(n + kBlockThreads - 1) / kBlockThreads, kBlockThreads, 0, s.stream>>>(s.p, n, d_o, d_d, d_t0, d_f, d_i, d_tc);
     CUX(cudaGetLastError());
     CUX(cudaStreamSynchronize(s.stream));
     if (found) CUX(cudaMemcpy(found, d_f, 4ull * n, cudaMemcpyDeviceToHost));

@@ -313,6 +313,8 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
     __shared__ __align__(128) DevWide top_nodes[kTopSmem > 0u ? kTopSmem : 1u];
     __shared__ unsigned long long top_bar;
     const uint32_t n_top = (kTopSmem > 0u && P.wide) ? stage_top_nodes(P, top_nodes, &top_bar, P.n_wide) : 0u;
+    __shared__ uint32_t walk_sm[kWalkWords * kBlockThreads];          // the any-hit walk's per-lane stack and leaf list (traverse_wide)
+    uint32_t *const sm = walk_sm + threadIdx.x;
     // depth >= 1 with shadow reuse: only the paths of the far list cast rays of their own; the others are counted here
     const bool use_far = depth > 0 && P.reuse_shadow != 0u;
     const uint32_t n_paths = depth == 0 ? depth0_count(P) : P.sched->queue_count[depth];
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __gr
         if (active && (double)tr.om > 0x1p20 * fmax(fmax(P.bound[0], P.bound[1]), P.bound[2])) budget = 0u;
         while (true) {                                                  // warp-uniform: traverse_early is warp-synchronous
             float stc; uint32_t spos;
-            int res = traverse_early_any<kAnyHit, COUNT>(P, tr, active, budget, stc, spos, lc, top_nodes, n_top);
+            int res = traverse_early_any<kAnyHit, COUNT>(P, tr, active, budget, stc, spos, lc, sm, top_nodes, n_top);
             bool again = false;
             if (active) {
                 if (res == kTravOverBudget) {
@@ -512,6 +514,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
     __shared__ __align__(128) DevWide top_nodes[kTopSmem > 0u ? kTopSmem : 1u];
     __shared__ unsigned long long top_bar;
     const uint32_t n_top = (kTopSmem > 0u && P.wide) ? stage_top_nodes(P, top_nodes, &top_bar, P.n_wide) : 0u;
+    uint32_t *const sm = nullptr;                                     // (a first-line walk keeps its lists in local memory, traverse_wide)
     const uint32_t n = P.sched->queue_count[depth];
     const int cur = depth & 1;
     while (true) {
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_bounce(const __gr
         uint32_t budget = P.budget;
         while (true) {                                                  // warp-uniform: traverse is warp-synchronous
             float tc; uint32_t pos;
-            int res = traverse_early_any<kFirstLine, COUNT>(P, r, active, budget, tc, pos, lc, top_nodes, n_top);
+            int res = traverse_early_any<kFirstLine, COUNT>(P, r, active, budget, tc, pos, lc, sm, top_nodes, n_top);
             bool again = false;
             if (active) {
                 if (res == kTravOverBudget) {
@@ -822,7 +825,7 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
     }
     LocalCount lc; float tc, tc2; uint32_t pos, pos2;
     const bool first_line = r.t == 0.0f;
-    bool f = traverse_early_any<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc) == kTravHit;
+    bool f = traverse_early_any<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc, nullptr) == kTravHit;
     bool f2 = traverse_closest_any<false>(P, tr, active && !first_line, tc2, pos2, lc) == kTravHit;
     if (!active) return;
     if (!first_line) { f = f2; tc = tc2; pos = pos2; }

@@ -493,14 +493,60 @@ CT_DEV uint32_t stage_top_nodes(const Params &P, DevWide *top, unsigned long lon
     return n_top;
 }
 
+// THE ANY-HIT WALK'S PER-LANE LISTS LIVE IN SHARED MEMORY (-DCT_SM_WALK=0: in local memory, as in round 1).  As local arrays
+// the pending-children stack and the deferred-leaf list were more than half of the L1's sector traffic in every walk kernel
+// (ncu, k_shadow: 137 M local sectors against 95 M global ones per launch; the lanes of a walking warp sit at different
+// depths, so one STL / LDL touches up to 32 lines), every store went through to L2 (70 M write sectors = 2.2 GB per launch,
+// 0.37 GB of it on to DRAM) and the lines shared the L1 with the tree.  In shared memory an access is one conflict-free
+// wavefront whatever the lanes' indices (word w of thread t lives at sm[w * 128 + t]: bank = t mod 32), never leaves the SM
+// and costs no tag look-up.  A lane keeps kSmStackWords stack entries there (one word each: an any-hit walk only pushes
+// interior nodes) and its whole leaf list; deeper stack entries spill to a local array.  Shared memory is carved out of
+// the L1, so less is more: measured on one box (dragon4k k_shadow / 66-light scene, ms): local lists 1.160 / 7.99;
+// shared, stack 16 + 16 leaves (24 KB per CTA) 1.104 / 7.75; stack 8 + 12 leaves (16 KB) 1.112 / 7.14; stack 8 + 8 leaves
+// 1.153 / 6.75 (a shorter leaf list also means earlier leaf phases: occluded rays leave sooner, lit ones pay more phases).
+// The first-line walk (k_bounce) pushes leaves as well (two words per entry) and lost 2-6 % with its lists in shared
+// memory at every size tried -- its rays are less coherent and want the L1 -- so it keeps local arrays.
+#ifndef CT_SM_WALK
+#define CT_SM_WALK 1
+#endif
+#ifndef CT_SM_STACK
+#define CT_SM_STACK 8
+#endif
+#ifndef CT_ANY_LEAVES
+#define CT_ANY_LEAVES 12
+#endif
 constexpr int kWideStack = 64;                 // pending children per lane: (kWide - 1) per level of the wide tree
-constexpr int kWideLeaves = 2 * kWide + 8;     // deferred leaves per lane; a visit may add kWide
+constexpr int kWideLeaves = 2 * kWide + 8;     // deferred leaves per lane of a first-line walk; a visit may add kWide
+constexpr int kAnyLeaves = CT_ANY_LEAVES;      // ... of an any-hit walk
+constexpr int kSmStackWords = CT_SM_WALK ? CT_SM_STACK : 0;                 // shared-memory words per lane: stack ...
+constexpr int kSmLeafWords = CT_SM_WALK ? 2 * kAnyLeaves : 0;               // ... and leaf list
+constexpr int kWalkWords = CT_SM_WALK ? kSmStackWords + kSmLeafWords : 1;   // k_shadow declares walk_sm[kWalkWords * kBlockThreads]
 template <TraverseMode MODE, bool COUNT>
 CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc,
-                         const DevWide *top = nullptr, uint32_t n_top = 0u) {
+                         uint32_t *sm, const DevWide *top = nullptr, uint32_t n_top = 0u) {
     static_assert(MODE != kClosest, "closest-hit rays use traverse_closest");
-    uint2 stk[kWideStack];                                // pushed children (ref, cnt)
-    uint2 leaf[kWideLeaves];                              // deferred leaves (ref, cnt), DFS order
+    constexpr bool kUseSm = CT_SM_WALK && MODE == kAnyHit;                  // sm: this thread's column of walk_sm (any-hit walks only)
+    constexpr int kLeaves = MODE == kAnyHit ? kAnyLeaves : kWideLeaves;
+    constexpr int kSmEntries = kUseSm ? kSmStackWords : 0, kSmLeaves = kUseSm ? kAnyLeaves : 0;
+    uint2 stk_spill[kWideStack - kSmEntries];             // pushed children (ref, cnt) beyond the shared-memory part
+    uint2 leaf_spill[kLeaves - kSmLeaves + 1];            // deferred leaves (ref, cnt), DFS order
+    uint32_t *const sm_leaf = sm + kSmStackWords * kBlockThreads;
+    auto push = [&](int i, uint32_t ref, uint32_t cnt) {
+        if (i < kSmEntries) sm[i * kBlockThreads] = ref;                    // (cnt = 0: interior nodes only)
+        else stk_spill[i - kSmEntries] = make_uint2(ref, cnt);
+    };
+    auto pop = [&](int i) -> uint2 {
+        if (i < kSmEntries) return make_uint2(sm[i * kBlockThreads], 0u);
+        return stk_spill[i - kSmEntries];
+    };
+    auto leaf_put = [&](int i, uint32_t ref, uint32_t cnt) {
+        if (i < kSmLeaves) { sm_leaf[(2 * i) * kBlockThreads] = ref; sm_leaf[(2 * i + 1) * kBlockThreads] = cnt; }
+        else leaf_spill[i - kSmLeaves] = make_uint2(ref, cnt);
+    };
+    auto leaf_get = [&](int i) -> uint2 {
+        if (i < kSmLeaves) return make_uint2(sm_leaf[(2 * i) * kBlockThreads], sm_leaf[(2 * i + 1) * kBlockThreads]);
+        return leaf_spill[i - kSmLeaves];
+    };
     int sp = 0, nleaf = 0;
     uint32_t spent = 1u;
     uint32_t cur_ref = 0u, cur_cnt = P.root_cnt;          // wide node 0 = the root's descendants; a leaf root has no wide tree
@@ -517,10 +563,10 @@ CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint
     }
     while (true) {
         // ---- walk phase: one wide-node visit per walking lane and iteration; leaves go to the list
-        while (__any_sync(kFullMask, (state == 1) & (nleaf <= kWideLeaves - kWide))) {
-            if ((state == 1) & (nleaf <= kWideLeaves - kWide)) {
+        while (__any_sync(kFullMask, (state == 1) & (nleaf <= kLeaves - kWide))) {
+            if ((state == 1) & (nleaf <= kLeaves - kWide)) {
                 if (cur_cnt > 0u) {                       // a leaf that came off the stack (or a leaf root)
-                    leaf[nleaf] = make_uint2(cur_ref, cur_cnt); nleaf++;
+                    leaf_put(nleaf, cur_ref, cur_cnt); nleaf++;
                     spent += cur_cnt;
                 } else {
                     const float4 *q = reinterpret_cast<const float4 *>(P.wide + cur_ref);
@@ -539,17 +585,17 @@ CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint
                             const bool hit = box_maybe<MODE == kAnyHit>(r, bmin, bmax);
                             if (MODE == kAnyHit) {
                                 const bool is_leaf = b.w > 0u;
-                                if (hit & is_leaf) { leaf[nleaf] = make_uint2(b.z, b.w); nleaf++; spent += b.w; }
-                                if (hit & !is_leaf) { stk[sp] = make_uint2(b.z, 0u); sp++; }
+                                if (hit & is_leaf) { leaf_put(nleaf, b.z, b.w); nleaf++; spent += b.w; }
+                                if (hit & !is_leaf) { push(sp, b.z, 0u); sp++; }
                             } else {
-                                if (hit) { stk[sp] = make_uint2(b.z, b.w); sp++; }
+                                if (hit) { push(sp, b.z, b.w); sp++; }
                             }
                         }
                     }
                 }
                 if (state == 1) {
                     if (sp == 0) state = 0;
-                    else { --sp; const uint2 t = stk[sp]; cur_ref = t.x; cur_cnt = t.y; }
+                    else { --sp; const uint2 t = pop(sp); cur_ref = t.x; cur_cnt = t.y; }
                 }
                 if (spent > budget) { result = kTravOverBudget; state = 0; nleaf = 0; }
             }
@@ -559,7 +605,7 @@ CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint
         uint32_t tri = 0;                                 // next triangle inside leaf li
         while (__any_sync(kFullMask, li < nleaf)) {
             if (li < nleaf) {
-                const uint2 lf = leaf[li];
+                const uint2 lf = leaf_get(li);
                 const uint32_t pos = lf.x + tri;
                 if (COUNT) lc.tri++;
                 const TriHit th = leaf_triangle<MODE == kAnyHit, COUNT>(P, r, pos, lc);
@@ -887,9 +933,9 @@ CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tc
 // reference's exact verdicts at every box of the binary tree otherwise (zero direction components, non-nested trees).
 template <TraverseMode MODE, bool COUNT>
 CT_DEV int traverse_early_any(const Params &P, const TRay &r, bool active, const uint32_t budget, float &tclosest, uint32_t &closest_pos, LocalCount &lc,
-                              const DevWide *top = nullptr, uint32_t n_top = 0u) {
+                              uint32_t *sm, const DevWide *top = nullptr, uint32_t n_top = 0u) {
     const bool cons = r.filt & (P.nested != 0u) & (P.wide != nullptr);
-    int res = traverse_wide<MODE, COUNT>(P, r, active & cons, budget, tclosest, closest_pos, lc, top, n_top);
+    int res = traverse_wide<MODE, COUNT>(P, r, active & cons, budget, tclosest, closest_pos, lc, sm, top, n_top);
     // the binary walk for the other rays, and for rays that may not be parked (no budget) whose wide stack overflowed
     const bool binary = active & (!cons | ((res == kTravOverBudget) & (budget == 0xffffffffu)));
     if (__any_sync(kFullMask, binary)) {
