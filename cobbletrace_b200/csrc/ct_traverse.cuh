@@ -267,6 +267,110 @@ CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclose
     return r.t != kRayTInit ? kTravHit : kTravMiss;
 }
 
+// The same walk with CONSERVATIVE tests at the interior boxes (nested tree, r.filt: see box_maybe above).  The reference
+// reaches a leaf iff the leaf's OWN box passes IntersectAABB against the ray.t of that moment, whatever happened on the way
+// down -- so the boxes on the way only have to be accepted whenever the reference accepts them (box_maybe: the lower end of
+// the near bracket, the upper end of the far bracket: half the FMAs of pair_accept, no undecided case, no fp64 fallback),
+// and the exact verdict (certified bracket, fp64 when it cannot decide) is needed once per leaf the walk OPENS, against
+// the ray.t of that moment, from the leaf's own bounds in its parent's pair record.  The visit order stays the reference's
+// (left subtree first; a right child is pushed with the lower end of its near bracket and dropped when popped if ray.t
+// has fallen to it), so the leaves are scanned in DFS order with the reference's ray.t: same triangles tested in the same
+// order, same ray.t / tclosest / closestIndex.  Box-test COUNTS are this walk's own (a superset of the reference's boxes).
+// WARP-SYNCHRONOUS; lanes whose ray does not allow conservative tests pass active = false and take traverse_closest.
+template <bool T_FAR>
+CT_DEV bool box_maybe_lo(const TRay &r, const float bmin[3], const float bmax[3], float &near_lo) {
+    float nl[3], fh[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const bool pos = r.rdf[k] > 0.0f;
+        nl[k] = __fmaf_rd(pos ? bmin[k] : bmax[k], r.rdf[k], r.cl[k]);
+        fh[k] = __fmaf_ru(pos ? bmax[k] : bmin[k], r.rdf[k], r.cu[k]);
+    }
+    near_lo = fmaxf(fmaxf(nl[0], nl[1]), nl[2]);
+    const float far_hi = fminf(fminf(fh[0], fh[1]), fh[2]);
+    const bool no = T_FAR ? ((far_hi < near_lo) | (far_hi <= 0.0f)) : ((far_hi < near_lo) | (far_hi <= 0.0f) | (near_lo >= r.t));
+    return !no;
+}
+
+template <bool COUNT>
+CT_DEV int traverse_closest_cons(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax], stk_src[kStackMax];      // a pushed right child: (ref, cnt), its parent pair
+    float stk_lo[kStackMax];                                                  // ... and the lower end of its near bracket
+    int sp = 0;
+    tclosest = kFinf;          // raythread.cpp:204
+    closest_pos = kNoPos;
+    uint32_t cur_ref = P.root_ref, cur_cnt = P.root_cnt, cur_code = kNoPos;   // code = 2 * pair + side of the node's own box (kNoPos: the root)
+    bool live = false;
+    if (active) {
+        if (COUNT) lc.box++;
+        live = root_accept(P, r);
+    }
+    while (__any_sync(kFullMask, live)) {
+        if (live) {
+            bool need_pop = true;
+            if (cur_cnt > 0) {
+                bool acc = true;                                              // (the root itself: accepted above)
+                if (cur_code != kNoPos) {                                     // IntersectAABB for the leaf's own box, now
+                    const uint32_t pid = cur_code >> 1, side = cur_code & 1u;
+                    const float4 *q = reinterpret_cast<const float4 *>(P.pairs32 + pid);
+                    const float4 x = __ldg(q + side), y = __ldg(q + 1 + side);      // left: floats 0..5, right: floats 6..11
+                    float bmin[3], bmax[3];
+                    if (side == 0u) { bmin[0] = x.x; bmin[1] = x.y; bmin[2] = x.z; bmax[0] = x.w; bmax[1] = y.x; bmax[2] = y.y; }
+                    else { bmin[0] = x.z; bmin[1] = x.w; bmin[2] = y.x; bmax[0] = y.y; bmax[1] = y.z; bmax[2] = y.w; }
+                    const BoxBracket bb = box_filter(r, bmin, bmax);
+                    const bool no = bracket_geom_no(bb) | bracket_t_no(bb, r.t), yes = bracket_geom_yes(bb) & bracket_t_yes(bb, r.t);
+                    acc = yes;
+                    if (!(no | yes)) {
+                        if (COUNT) lc.box_exact++;
+                        acc = box_accept(exact_child(P.pairs64, pid, side, r.r64), r.t);
+                    }
+                }
+                if (acc) {
+                    for (uint32_t i = 0; i < cur_cnt; i++) {
+                        uint32_t pos = cur_ref + i;
+                        if (COUNT) lc.tri++;
+                        const TriHit th = leaf_triangle<false, COUNT>(P, r, pos, lc);
+                        if (th.hit) {
+                            if (th.t > kEps) r.t = macro_min(r.t, th.t);               // bvh.cpp:161
+                            if (r.t != kRayTInit && r.t < tclosest) {                  // bvh.cpp:212
+                                closest_pos = pos; tclosest = r.t;
+                            }
+                        }
+                    }
+                }
+            } else {
+                CT_CHECK(cur_ref < P.n_pairs);
+                DevPair32 pr;
+                load_pair32(P.pairs32, cur_ref, pr);
+                if (COUNT) lc.box += 2;
+                float l_lo, r_lo;
+                const bool hit_l = box_maybe_lo<false>(r, pr.lmin, pr.lmax, l_lo), hit_r = box_maybe_lo<false>(r, pr.rmin, pr.rmax, r_lo);
+                if (hit_l & hit_r) {
+                    CT_CHECK(sp < kStackMax);
+                    stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt; stk_lo[sp] = r_lo; stk_src[sp] = cur_ref;
+                    sp++;
+                }
+                if (hit_l | hit_r) {
+                    cur_code = 2u * cur_ref + (hit_l ? 0u : 1u);
+                    cur_ref = hit_l ? pr.l_ref : pr.r_ref; cur_cnt = hit_l ? pr.l_cnt : pr.r_cnt;
+                    need_pop = false;
+                }
+            }
+            if (need_pop) {
+                live = false;
+                while (sp > 0) {
+                    --sp;
+                    if (stk_lo[sp] >= r.t) continue;                          // tmin >= its lower bracket end >= ray.t: bvh.cpp:178 rejects it now
+                    cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; cur_code = 2u * stk_src[sp] + 1u; live = true;
+                    break;
+                }
+            }
+        }
+    }
+    if (!active) return kTravMiss;
+    return r.t != kRayTInit ? kTravHit : kTravMiss;
+}
+
 // The same walk with LANE REFILL (north_star: "__ballot_sync / __shfl_sync compaction for ray regrouping"): the warp
 // does not wait for the slowest ray of a group of 32.  A lane whose walk has ended hands its result to the job and falls
 // idle; as soon as kRefillLanes lanes are idle (one ballot per iteration) the job deals new rays to exactly those lanes --
@@ -898,6 +1002,9 @@ CT_DEV int traverse_wide_nearest(const Params &P, const TRay &r, bool active, fl
 #ifndef CT_WIDE_CLOSEST
 #define CT_WIDE_CLOSEST 0
 #endif
+#ifndef CT_CONS_CLOSEST
+#define CT_CONS_CLOSEST 0            // 1: the ordered closest-hit walk tests interior boxes conservatively and opens leaves exactly (traverse_closest_cons) -- measured slower, DESIGN.md 5
+#endif
 #ifndef CT_NEAREST
 #define CT_NEAREST 0                 // 1: primary rays take the order-free walk (traverse_wide_nearest) where the ray allows it -- measured slower, DESIGN.md 5
 #endif
@@ -912,6 +1019,17 @@ CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tc
             float tc2; uint32_t pos2;
             const int res2 = traverse_closest<COUNT>(P, r, ordered, tc2, pos2, lc);
             if (ordered) { res = res2; tclosest = tc2; closest_pos = pos2; }
+        }
+        return res;
+    }
+    if (CT_CONS_CLOSEST) {
+        const bool cons = active & r.filt & (P.nested != 0u);
+        int res = traverse_closest_cons<COUNT>(P, r, cons, tclosest, closest_pos, lc);
+        const bool rest = active & !cons;
+        if (__any_sync(kFullMask, rest)) {                             // zero direction components, trees that are not nested
+            float tc2; uint32_t pos2;
+            const int res2 = traverse_closest<COUNT>(P, r, rest, tc2, pos2, lc);
+            if (rest) { res = res2; tclosest = tc2; closest_pos = pos2; }
         }
         return res;
     }
