@@ -858,7 +858,7 @@ CT_DEV int traverse_wide_closest(const Params &P, TRay &r, bool active, float &t
 // carries slack, so the inequality is strict) and is not in S.  Each barycentric pass within best + sigma becomes a candidate once the exact fp64 test of its own leaf box confirms membership in G (that test also
 // yields the reference's tmin for the replay).  The rare leftovers -- more than kNearCand candidates, a member of S whose
 // leaf starts beyond m + sigma, t >= FINF (raythread.cpp:204's tclosest quirk), a full stack -- return kTravOverBudget
-// and take traverse_closest.  oracle/ct_oracle.c holds the CPU prototype (tests/test_free_closest_prototype.py).
+// and take traverse_closest.  The argument is checked on the CPU by tests/test_free_closest_prototype.py.
 // What the freedom buys: conservative one-sided box tests over the wide tree (half the FMAs of the certified brackets, half
 // the dependent fetches, no fp64 fallback), leaves tested by the warp together, and a walk that may be cut short.
 // WARP-SYNCHRONOUS, same contract as traverse_closest for the rays it decides.
