@@ -281,6 +281,8 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
     job.chunk = 1u << P.chunk_shift;
     job.n_chunks = (P.n_slots + job.chunk - 1u) >> P.chunk_shift;
     job.dealt_left = P.part_count > 1u && P.static_eighths > 0u;
+    __shared__ uint32_t closest_sm[kClosestWords * kBlockThreads];     // the top of the closest-hit walk's per-lane stack (traverse_closest)
+    uint32_t *const sm = kSmClosest > 0 ? closest_sm + threadIdx.x : nullptr;
 #if CT_REFILL_T > 0
     traverse_closest_refill<COUNT>(P, job, lc);
 #else
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
         TRay r;
         if (!job.refill(P, all, got, r, r64)) break;          // a whole chunk's worth of slots: one per lane
         float tc; uint32_t pos;
-        const bool found = traverse_closest_any<COUNT>(P, r, got, tc, pos, lc) == kTravHit;   // warp-synchronous
+        const bool found = traverse_closest_any<COUNT>(P, r, got, tc, pos, lc, sm) == kTravHit;   // warp-synchronous
         if (got) job.finish(P, found, tc, pos);
         if (P.max_depth > 0)          // the recursion step at once, while ray and hit are at hand (no k_emit pass over the tile)
             emit_paths(P, 0, got, job.q, job.slot, {r64[0], r64[1], r64[2]}, {r64[3], r64[4], r64[5]}, tc,
@@ -306,8 +308,11 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
 // ComputeLighting's shadow rays (raythread.cpp:288-306) for the paths alive at `depth`.  Work item =
 // (shadow light j, path q), j-major, so the 32 lanes of a warp trace 32 neighbouring shading points towards
 // the same light.  Verdicts go to the per-path occlusion mask read by k_shade.
+#ifndef CT_SHADOW_BLOCKS
+#define CT_SHADOW_BLOCKS CT_MIN_BLOCKS
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_shadow(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
+__global__ void __launch_bounds__(kBlockThreads, CT_SHADOW_BLOCKS) k_shadow(const __grid_constant__ Params P, int depth, int work_idx, int ovf_idx) {
     LocalCount lc;
     uint32_t n_shadow = 0, n_parked = 0, n_reused = 0;
     __shared__ __align__(128) DevWide top_nodes[kTopSmem > 0u ? kTopSmem : 1u];
@@ -826,7 +831,8 @@ __global__ void k_debug_closest(const __grid_constant__ Params P, uint32_t n, co
     LocalCount lc; float tc, tc2; uint32_t pos, pos2;
     const bool first_line = r.t == 0.0f;
     bool f = traverse_early_any<kFirstLine, false>(P, tr, active && first_line, 0xffffffffu, tc, pos, lc, nullptr) == kTravHit;
-    bool f2 = traverse_closest_any<false>(P, tr, active && !first_line, tc2, pos2, lc) == kTravHit;
+    __shared__ uint32_t closest_sm[kClosestWords * kBlockThreads];     // launched with kBlockThreads threads per block
+    bool f2 = traverse_closest_any<false>(P, tr, active && !first_line, tc2, pos2, lc, kSmClosest > 0 ? closest_sm + threadIdx.x : nullptr) == kTravHit;
     if (!active) return;
     if (!first_line) { f = f2; tc = tc2; pos = pos2; }
     if (found) found[i] = f ? 1u : 0u;

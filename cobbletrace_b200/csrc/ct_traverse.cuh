@@ -198,12 +198,24 @@ constexpr uint32_t kFullMask = 0xffffffffu;
 // visit per live lane, and the lanes re-converge at the vote that ends it (left to itself the compiler lets the
 // lanes of a warp drift apart for the whole walk: measured 8 of 32 lanes active).
 // Returns kTravHit/kTravMiss = ray.t != 1e30f ("found").
+#ifndef CT_SM_CLOSEST
+#define CT_SM_CLOSEST 0
+#endif
+constexpr int kSmClosest = CT_SM_CLOSEST;                         // stack entries of the closest-hit walk kept in shared memory
+constexpr int kClosestWords = kSmClosest > 0 ? 5 * kSmClosest : 1;   // k_primary declares closest_sm[kClosestWords * kBlockThreads]
+#ifndef CT_LEAF_HOLD
+#define CT_LEAF_HOLD 0
+#endif
+constexpr int kLeafHold = CT_LEAF_HOLD;
 template <bool COUNT>
-CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc, uint32_t *sm = nullptr) {
     // stack entry = a pushed right child: (ref, cnt), the bracket of its tmin and its parent pair (to find its fp64
-    // bounds again when the bracket cannot decide)
-    uint32_t stk_ref[kStackMax], stk_cnt[kStackMax], stk_src[kStackMax];
-    float stk_lo[kStackMax], stk_hi[kStackMax];
+    // bounds again when the bracket cannot decide).  The first kSmClosest entries live in shared memory (sm = this thread's
+    // column of the kernel's closest_sm array, five words per entry; see traverse_wide for the why), the rest in local memory.
+    constexpr int kSm = kSmClosest;
+    uint32_t stk_ref[kStackMax - kSm], stk_cnt[kStackMax - kSm], stk_src[kStackMax - kSm];
+    float stk_lo[kStackMax - kSm], stk_hi[kStackMax - kSm];
+    auto sm_at = [&](int i, int w) -> uint32_t & { return sm[(5 * i + w) * kBlockThreads]; };
     int sp = 0;
     tclosest = kFinf;          // raythread.cpp:204
     closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
@@ -214,10 +226,18 @@ CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclose
         live = root_accept(P, r);
     }
     while (__any_sync(kFullMask, live)) {
+        // -DCT_LEAF_HOLD=K (experiment): a lane that has reached a leaf waits until K lanes hold one (or nobody is left to
+        // walk), so that the triangle tests -- which otherwise run in most iterations for a handful of lanes -- are shared
+        bool hold = false;
+        if (kLeafHold > 0) {
+            const uint32_t at_leaf = __ballot_sync(kFullMask, live & (cur_cnt > 0)), walking = __ballot_sync(kFullMask, live & (cur_cnt == 0));
+            hold = walking != 0u && __popc(at_leaf) < kLeafHold;
+        }
         if (live) {
             bool need_pop = true;
             if (cur_cnt > 0) {
-                for (uint32_t i = 0; i < cur_cnt; i++) {
+                if (hold) need_pop = false;
+                else for (uint32_t i = 0; i < cur_cnt; i++) {
                     uint32_t pos = cur_ref + i;
                     if (COUNT) lc.tri++;
                     const TriHit th = leaf_triangle<false, COUNT>(P, r, pos, lc);
@@ -238,8 +258,13 @@ CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclose
                 pair_accept<COUNT>(P, r, cur_ref, pr, hit_l, hit_r, r_lo, r_hi, lc);
                 if (hit_l & hit_r) {
                     CT_CHECK(sp < kStackMax);
-                    stk_ref[sp] = pr.r_ref; stk_cnt[sp] = pr.r_cnt;
-                    stk_lo[sp] = r_lo; stk_hi[sp] = r_hi; stk_src[sp] = cur_ref;
+                    if (sp < kSm) {
+                        sm_at(sp, 0) = pr.r_ref; sm_at(sp, 1) = pr.r_cnt; sm_at(sp, 2) = cur_ref;
+                        sm_at(sp, 3) = __float_as_uint(r_lo); sm_at(sp, 4) = __float_as_uint(r_hi);
+                    } else {
+                        const int k = sp - kSm;
+                        stk_ref[k] = pr.r_ref; stk_cnt[k] = pr.r_cnt; stk_lo[k] = r_lo; stk_hi[k] = r_hi; stk_src[k] = cur_ref;
+                    }
                     sp++;
                 }
                 if (hit_l | hit_r) {
@@ -251,13 +276,17 @@ CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclose
                 live = false;
                 while (sp > 0) {
                     --sp;
-                    if (stk_lo[sp] >= r.t) continue;                          // the deferred `tmin < ray.t` of bvh.cpp:178
-                    if (!(stk_hi[sp] < r.t)) {
+                    const bool in_sm = sp < kSm;
+                    const int k = sp - kSm;
+                    const float lo = in_sm ? __uint_as_float(sm_at(sp, 3)) : stk_lo[k];
+                    if (lo >= r.t) continue;                                  // the deferred `tmin < ray.t` of bvh.cpp:178
+                    const float hi = in_sm ? __uint_as_float(sm_at(sp, 4)) : stk_hi[k];
+                    if (!(hi < r.t)) {
                         if (COUNT) lc.box_exact++;
-                        BoxTimes e = exact_child(P.pairs64, stk_src[sp], 1u, r.r64);
+                        BoxTimes e = exact_child(P.pairs64, in_sm ? sm_at(sp, 2) : stk_src[k], 1u, r.r64);
                         if (!(e.tmin < r.t)) continue;
                     }
-                    cur_ref = stk_ref[sp]; cur_cnt = stk_cnt[sp]; live = true;
+                    cur_ref = in_sm ? sm_at(sp, 0) : stk_ref[k]; cur_cnt = in_sm ? sm_at(sp, 1) : stk_cnt[k]; live = true;
                     break;
                 }
             }
@@ -620,7 +649,10 @@ CT_DEV uint32_t stage_top_nodes(const Params &P, DevWide *top, unsigned long lon
 #define CT_ANY_LEAVES 12
 #endif
 constexpr int kWideStack = 64;                 // pending children per lane: (kWide - 1) per level of the wide tree
-constexpr int kWideLeaves = 2 * kWide + 8;     // deferred leaves per lane of a first-line walk; a visit may add kWide
+#ifndef CT_LINE_LEAVES
+#define CT_LINE_LEAVES (2 * kWide + 8)
+#endif
+constexpr int kWideLeaves = CT_LINE_LEAVES;     // deferred leaves per lane of a first-line walk; a visit may add kWide
 constexpr int kAnyLeaves = CT_ANY_LEAVES;      // ... of an any-hit walk
 constexpr int kSmStackWords = CT_SM_WALK ? CT_SM_STACK : 0;                 // shared-memory words per lane: stack ...
 constexpr int kSmLeafWords = CT_SM_WALK ? 2 * kAnyLeaves : 0;               // ... and leaf list
@@ -1009,7 +1041,7 @@ CT_DEV int traverse_wide_nearest(const Params &P, const TRay &r, bool active, fl
 #define CT_NEAREST 0                 // 1: primary rays take the order-free walk (traverse_wide_nearest) where the ray allows it -- measured slower, DESIGN.md 5
 #endif
 template <bool COUNT>
-CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc) {
+CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc, uint32_t *sm = nullptr) {
     if (CT_NEAREST) {
         // r.sg > 0: tray_nearest_setup found the ray within the limits of the slop analysis (and r.filt); ray.t must be 1e30f
         const bool fr = active & (r.sg > 0.0f) & (r.t == kRayTInit) & (P.nested != 0u) & (P.wide != nullptr);
@@ -1033,7 +1065,7 @@ CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tc
         }
         return res;
     }
-    if (!CT_WIDE_CLOSEST) return traverse_closest<COUNT>(P, r, active, tclosest, closest_pos, lc);
+    if (!CT_WIDE_CLOSEST) return traverse_closest<COUNT>(P, r, active, tclosest, closest_pos, lc, sm);
     const bool cons = r.filt & (P.nested != 0u) & (P.wide != nullptr);
     const float t0 = r.t;
     int res = traverse_wide_closest<COUNT>(P, r, active & cons, tclosest, closest_pos, lc);
