@@ -130,6 +130,7 @@ long long g_budget_option = 0;       // ct_gpu_set_option("traversal_budget"); 0
 long long g_warp_budget_option = 0;  // ct_gpu_set_option("overflow_warp_budget"); 0 = default
 long long g_static_eighths = 7;      // ct_gpu_set_option("shared_static_eighths"), see next_chunk
 long long g_shared_chunk_shift = 0;  // ct_gpu_set_option("shared_chunk_shift"): 0 = kChunkSharedShift
+long long g_run_shift = 0;           // ct_gpu_set_option("shared_run_shift")
 long long g_emulate_ranks = 0;       // ct_gpu_set_option("emulate_ranks"): profiling aid, see ct_gpu.h
 long long g_shadow_reuse = 1;        // ct_gpu_set_option("shadow_reuse"): a shading point that repeats its parent's takes the parent's shadow verdicts
 long long g_hold_frame = 0;          // ct_gpu_set_option("shared_hold_frame"): test aid, see ct_gpu.h
@@ -612,6 +613,7 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     p.part_index = dealt ? (uint32_t)s.part_index : 0u;
     p.part_count = dealt ? (uint32_t)s.part_count : 0u;
     p.static_eighths = (uint32_t)g_static_eighths;
+    p.run_shift = (shared || p.steal_stride > 1) ? (uint32_t)g_run_shift : 0u;
     if (shared && !s.remote_cursor_ok) {
         // no native atomics to the root's cursor: stealing from it would hand chunks out twice or not at all
         if (!dealt) return fail(CT_ERR_CUDA, "device %d has no native atomics to the shared frame's cursor: declare the participants (ct_gpu_share_partition), then every chunk is dealt", device);
@@ -869,6 +871,11 @@ int ct_gpu_set_option(const char *name, long long value) {
     if (!strcmp(name, "shared_chunk_shift")) {
         if (value != 0 && (value < kChunkLocalShift || value > kChunkMaxShift)) return fail(CT_ERR_INVALID, "shared_chunk_shift must be 0 (default), 5 or 6");
         g_shared_chunk_shift = value;
+        return CT_OK;
+    }
+    if (!strcmp(name, "shared_run_shift")) {
+        if (value < 0 || value > 10) return fail(CT_ERR_INVALID, "shared_run_shift must be 0..10");
+        g_run_shift = value;
         return CT_OK;
     }
     if (!strcmp(name, "shadow_reuse")) {

@@ -181,26 +181,41 @@ CT_DEV bool park_ray(const Params &P, int ovf_idx, const double *r64, uint32_t t
 //     slower or busier GPU).  Stealing everything balances only this kernel: the GPU that holds the cursor steals
 //     cheaper and ends up with more paths to light (measured at 8 GPUs: 1.75 ms on the root against 1.41 ms elsewhere).
 CT_DEV bool next_chunk(const Params &P, uint32_t n_chunks, bool &dealt_left, uint32_t &idx) {
-    const uint32_t R = P.part_count, E = P.static_eighths;
+    // Chunks are handed out in RUNS of L = 2^run_shift consecutive chunks (horizontally adjacent 8x4 blocks): the formulas
+    // below deal / steal run numbers, `off` walks through a run.  L = 1 is the finest interleave; a longer run keeps the warps
+    // of one GPU on neighbouring pixels (option "shared_run_shift").
+    const uint32_t R = P.part_count, E = P.static_eighths, rs = P.run_shift, L = 1u << rs;
     if (R <= 1u) {
-        const unsigned long long d = atomicAdd(P.steal, (unsigned long long)P.steal_stride);
-        idx = (uint32_t)d;
-        return d < n_chunks;
+        if (P.steal_stride <= 1u) {
+            const unsigned long long d = atomicAdd(P.steal, 1ull);
+            idx = (uint32_t)d;
+            return d < n_chunks;
+        }
+        while (true) {                                       // (option "emulate_ranks": the runs rank 0 of steal_stride GPUs would own)
+            const unsigned long long c = atomicAdd(P.steal, 1ull);
+            const unsigned long long run = (c >> rs) * P.steal_stride;
+            if ((run << rs) >= n_chunks) return false;
+            idx = (uint32_t)((run << rs) + (c & (L - 1u)));
+            if (idx < n_chunks) return true;
+        }
     }
-    const uint32_t G = 8u * R, n_groups = (n_chunks + G - 1u) / G;
+    const uint32_t n_runs = (n_chunks + L - 1u) >> rs;
+    const uint32_t G = 8u * R, n_groups = (n_runs + G - 1u) / G;
     while (dealt_left) {
         const uint32_t c = atomicAdd(&P.sched->static_next, 1u);
-        const uint32_t g = c / E;
+        const uint32_t cr = c >> rs, off = c & (L - 1u);
+        const uint32_t g = cr / E;
         if (g >= n_groups) { dealt_left = false; break; }
-        idx = g * G + (c - g * E) * R + P.part_index;
+        idx = ((g * G + (cr - g * E) * R + P.part_index) << rs) + off;
         if (idx < n_chunks) return true;
     }
     const uint32_t per = (8u - E) * R;
     while (per) {
         const unsigned long long d = atomicAdd(P.steal, 1ull);
-        const unsigned long long g = d / per;
+        const unsigned long long dr = d >> rs, off = d & (L - 1u);
+        const unsigned long long g = dr / per;
         if (g >= n_groups) break;
-        idx = (uint32_t)(g * G + E * R + (d - g * per));
+        idx = (uint32_t)(((g * G + E * R + (dr - g * per)) << rs) + off);
         if (idx < n_chunks) return true;
     }
     return false;

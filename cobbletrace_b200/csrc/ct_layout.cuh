@@ -145,6 +145,7 @@ struct Params {
     uint32_t steal_stride;                       // 1; R > 1 (option "emulate_ranks") takes every R-th chunk only: the share of one of R GPUs
     uint32_t part_index, part_count;             // shared frame: this device is participant part_index of part_count (0: not declared)
     uint32_t static_eighths;                     // ... of every 8 * part_count chunks, static_eighths * part_count are dealt, the rest stolen
+    uint32_t run_shift;                          // log2 of the run of consecutive chunks that is dealt / stolen as one unit (option "shared_run_shift")
     uint32_t *own_chunks;                        // chunk numbers this device took, in the order it took them
     uint32_t *dbg_found, *dbg_index; float *dbg_t;   // optional (CT_FLAG_KEEP_HITS), framebuffer layout
     // parked rays

@@ -238,11 +238,12 @@ def test_shared_frame_mode_on_one_gpu(golden, scene_loader, gpu):
     assert np.array_equal(gpu.readback(), want)
 
 
-@pytest.mark.parametrize("count,eighths", [(2, 7), (3, 7), (8, 7), (4, 8), (4, 0), (5, 3)])
-def test_shared_frame_partition_covers_the_frame_once(count, eighths, golden, scene_loader, gpu):
-    """ct_gpu_share_partition: of every 8*count chunks `eighths`*count are dealt round-robin, the rest stolen from the
-    cursor.  One GPU plays all `count` participants in turn (the first one to run steals every stolen chunk): together
-    they must trace every pixel exactly once -- the ray counts add up to the one-GPU frame's and the frame is identical."""
+@pytest.mark.parametrize("count,eighths,run_shift", [(2, 7, 0), (3, 7, 0), (8, 7, 0), (4, 8, 0), (4, 0, 0), (5, 3, 0), (8, 7, 2), (3, 7, 4), (4, 8, 1), (2, 0, 3)])
+def test_shared_frame_partition_covers_the_frame_once(count, eighths, run_shift, golden, scene_loader, gpu):
+    """ct_gpu_share_partition: of every 8*count chunks (or runs of 2^run_shift chunks, option "shared_run_shift") `eighths`*count
+    are dealt round-robin, the rest stolen from the cursor.  One GPU plays all `count` participants in turn (the first one to run
+    steals every stolen chunk): together they must trace every pixel exactly once -- the ray counts add up to the one-GPU frame's
+    and the frame is identical."""
     fs, meta = case_scene("bunny_refl_d2_160", golden, scene_loader)
     want = load_frames("bunny_refl_d2_160")["frame"]
     gpu.upload(fs, meta["width"], meta["height"], max_depth=meta["depth"])
@@ -251,6 +252,7 @@ def test_shared_frame_partition_covers_the_frame_once(count, eighths, golden, sc
     gpu.upload(fs, meta["width"], meta["height"], max_depth=meta["depth"])      # fresh framebuffer
     gpu.share_attach(gpu.share_export())
     ct.api.set_option("shared_static_eighths", eighths)
+    ct.api.set_option("shared_run_shift", run_shift)
     try:
         parts = []
         for k in range(count):
@@ -263,9 +265,10 @@ def test_shared_frame_partition_covers_the_frame_once(count, eighths, golden, sc
         for key in ("rays_primary", "rays_shadow", "rays_reflection"):
             assert sum(p[key] for p in parts) == whole[key], key
         if eighths == 8:
-            assert max(p["rays_primary"] for p in parts) <= min(p["rays_primary"] for p in parts) + 64 * 2
+            assert max(p["rays_primary"] for p in parts) <= min(p["rays_primary"] for p in parts) + (64 * 2 << run_shift)
     finally:
         ct.api.set_option("shared_static_eighths", 7)
+        ct.api.set_option("shared_run_shift", 0)
         ct.api.set_option("shared_hold_frame", 0)
         gpu.share_partition(0, 0)
         gpu.share_attach(None)

@@ -11,8 +11,10 @@ fs = mk()
 shifts = [int(v) for v in os.environ.get("CT_SHARED_SHIFTS", "0").split(",")]
 budgets = [int(v) for v in os.environ.get("CT_BUDGETS", "0").split(",")]
 ranks = [int(v) for v in os.environ.get("CT_RANKS", "1,2,4,8").split(",")]
-for R, shift, budget in [(R, sh, b) for R in ranks for sh in shifts for b in budgets]:
+runs = [int(v) for v in os.environ.get("CT_RUN_SHIFTS", "0").split(",")]
+for R, shift, budget, run in [(R, sh, b, rn) for R in ranks for sh in shifts for b in budgets for rn in runs]:
     api.set_option("emulate_ranks", R)
+    api.set_option("shared_run_shift", run)
     api.set_option("shared_chunk_shift", shift)
     api.set_option("traversal_budget", budget)
     for flags, what in ((api.CT_FLAG_STAGE_TIMING, "serialised"), (0, "concurrent")):
@@ -21,11 +23,12 @@ for R, shift, budget in [(R, sh, b) for R in ranks for sh in shifts for b in bud
         for i in range(6):
             r.render_tile(); r.sync()
             if i >= 2: best = min(best, r.last_tile_ms())
-        line = f"ranks={R} shift={shift} budget={budget} {what}: {best:.3f} ms"
+        line = f"ranks={R} shift={shift} budget={budget} run_shift={run} {what}: {best:.3f} ms"
         if flags:
             line += "  " + " ".join(f"{nm}[{d}]={ms:.3f}" for nm, d, ms in r.last_tile_stages())
         print(line, flush=True)
         r.shutdown()
 api.set_option("emulate_ranks", 0)
+api.set_option("shared_run_shift", 0)
 api.set_option("shared_chunk_shift", 0)
 api.set_option("traversal_budget", 0)
