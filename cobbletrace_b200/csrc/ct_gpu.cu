@@ -128,6 +128,7 @@ std::recursive_mutex g_dev_mutex[kMaxDevices];
 #define DEVICE_GUARD(device) std::lock_guard<std::recursive_mutex> dev_lock_(g_dev_mutex[((device) >= 0 && (device) < kMaxDevices) ? (device) : 0])
 long long g_budget_option = 0;       // ct_gpu_set_option("traversal_budget"); 0 = default
 long long g_warp_budget_option = 0;  // ct_gpu_set_option("overflow_warp_budget"); 0 = default
+long long g_primary_budget_option = 0;   // ct_gpu_set_option("primary_budget"); 0 = default (kDefaultPrimaryBudget: never), < 0 = never
 long long g_static_eighths = 7;      // ct_gpu_set_option("shared_static_eighths"), see next_chunk
 long long g_shared_chunk_shift = 0;  // ct_gpu_set_option("shared_chunk_shift"): 0 = kChunkSharedShift
 long long g_run_shift = 0;           // ct_gpu_set_option("shared_run_shift")
@@ -324,6 +325,7 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     if (d->flags & CT_FLAG_STAGE_TIMING) for (cudaEvent_t &e : s.stage_ev) CU(cudaEventCreate(&e));
     s.p.budget = g_budget_option > 0 ? (uint32_t)std::min<long long>(g_budget_option, 1ll << 30) : kDefaultBudget;
     s.p.warp_budget = g_warp_budget_option > 0 ? (uint32_t)std::min<long long>(g_warp_budget_option, 1ll << 30) : kWarpBudget;
+    s.p.primary_budget = g_primary_budget_option < 0 ? 0u : g_primary_budget_option > 0 ? (uint32_t)std::min<long long>(g_primary_budget_option, 1ll << 30) : kDefaultPrimaryBudget;
     s.flags = d->flags;
 
     const bool timing = getenv("CT_GPU_TIMING") != nullptr;
@@ -515,7 +517,9 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     TRY(dev_alloc(s, &s.occ_all, (size_t)p.cap * p.occ_words * levels, true));
     p.occ = s.occ_all;
     if (s.can_overflow) {
-        p.ovf_cap = 1u << 18;          // parked rays per launch (16 MB); a full buffer means finishing rays in place, which must stay hypothetical
+        // parked rays per launch: 2^18 (16 MB), or 1/16 of the frame's paths where that is more (k_primary parks 2-3 % of a dragon-class
+        // frame's primary rays); a full buffer means finishing rays in place, which must stay hypothetical
+        p.ovf_cap = std::max<uint32_t>(1u << 18, p.cap / 16u);
         TRY(dev_alloc(s, &s.ovf_all, (size_t)p.ovf_cap * 2 * levels));
         TRY(dev_alloc(s, &s.ovf_huge_all, (size_t)p.ovf_cap * 2 * levels));
         p.ovf = s.ovf_all; p.ovf_huge = s.ovf_huge_all;
@@ -679,11 +683,20 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
     // persistent CTAs of a later kernel move into an SM as those of an earlier one run out of work, which fills
     // the kernels' tails.  With CT_FLAG_STAGE_TIMING everything is serialised on the main stream instead.
     {
-        const Params v0 = view(0);        // (k_primary also runs the recursion step of depth 0: it needs the depth's queues)
+        Params v0 = view(0);              // (k_primary also runs the recursion step of depth 0: it needs the depth's queues)
+        // walks longer than primary_budget pair visits are parked (slot 0 of the parking buffers: depth 0 has no bounce launch)
+        // and walked again by k_primary_long, in warps made of long walks only
+        const bool park_primary = s.can_overflow && pk.primary_budget > 0u;
+        v0.ovf = park_primary ? s.ovf_all : nullptr;
         if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(v0);
         else k_primary<false><<<grid, kBlockThreads, 0, st>>>(v0);
+        TRY(mark("primary", 0));
+        if (park_primary) {
+            if (count) k_primary_long<true><<<grid, kBlockThreads, 0, st>>>(v0, work++);
+            else k_primary_long<false><<<grid, kBlockThreads, 0, st>>>(v0, work++);
+            TRY(mark("primary_long", 0));
+        }
     }
-    TRY(mark("primary", 0));
     for (int d = 0; d <= depth_max; d++) {
         const Params v = view(d);
         const int ovf_b = 2 * d, ovf_s = 2 * d + 1;
@@ -891,6 +904,10 @@ int ct_gpu_set_option(const char *name, long long value) {
     if (!strcmp(name, "l2_persist")) {
         if (value != 0 && value != 1) return fail(CT_ERR_INVALID, "l2_persist must be 0 or 1");
         g_l2_persist = value;
+        return CT_OK;
+    }
+    if (!strcmp(name, "primary_budget")) {
+        g_primary_budget_option = value;
         return CT_OK;
     }
     if (!strcmp(name, "overflow_warp_budget")) {

@@ -227,6 +227,19 @@ CT_DEV void emit_paths(const Params &P, int depth, bool active, uint32_t q, uint
 // Lanes of `idle` in rank order: the r-th idle lane gets item r.
 CT_DEV uint32_t idle_rank(uint32_t idle) { return __popc(idle & ((1u << (threadIdx.x & 31u)) - 1u)); }
 
+// The closest-hit record of the depth-0 path (slot, q): ClosestIntersection's results as TraceRay sees them (raythread.cpp:227, :205).
+CT_DEV void store_primary_hit(const Params &P, uint32_t slot, uint32_t q, int fbi, bool found, float tc, uint32_t pos) {
+    CT_CHECK(slot < P.cap && q < P.cap);
+    P.hit0_t[slot] = tc;
+    P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
+    if (found) clear_occ(P, q);
+    if (P.dbg_found && fbi >= 0) {
+        P.dbg_found[fbi] = found ? 1u : 0u;
+        P.dbg_index[fbi] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
+        P.dbg_t[fbi] = tc;
+    }
+}
+
 // k_primary's job (traverse_closest_refill): the warp takes chunks from the tile's cursor (next_chunk) and hands the slots
 // of its current chunk to lanes as they fall idle.
 struct PrimaryJob {
@@ -271,15 +284,7 @@ struct PrimaryJob {
     }
     CT_DEV void finish(const Params &P, bool found, float tc, uint32_t pos) {
         n_rays++;
-        CT_CHECK(slot < P.cap && q < P.cap);
-        P.hit0_t[slot] = tc;
-        P.hit0_pos[slot] = found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos;
-        if (found) clear_occ(P, q);
-        if (P.dbg_found && fbi >= 0) {
-            P.dbg_found[fbi] = found ? 1u : 0u;
-            P.dbg_index[fbi] = (pos == kNoPos) ? 0u : P.tris[pos].orig;
-            P.dbg_t[fbi] = tc;
-        }
+        store_primary_hit(P, slot, q, fbi, found, tc, pos);
     }
 };
 
@@ -298,25 +303,83 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
     job.dealt_left = P.part_count > 1u && P.static_eighths > 0u;
     __shared__ uint32_t closest_sm[kClosestWords * kBlockThreads];     // the top of the closest-hit walk's per-lane stack (traverse_closest)
     uint32_t *const sm = kSmClosest > 0 ? closest_sm + threadIdx.x : nullptr;
+    uint32_t n_parked = 0;
 #if CT_REFILL_T > 0
     traverse_closest_refill<COUNT>(P, job, lc);
 #else
     const uint32_t all = kFullMask;
+    const uint32_t budget = (P.primary_budget > 0u && P.ovf != nullptr) ? P.primary_budget : 0xffffffffu;
     while (true) {
         bool got = false;
         double r64[kRay64];
         TRay r;
         if (!job.refill(P, all, got, r, r64)) break;          // a whole chunk's worth of slots: one per lane
         float tc; uint32_t pos;
-        const bool found = traverse_closest_any<COUNT>(P, r, got, tc, pos, lc, sm) == kTravHit;   // warp-synchronous
-        if (got) job.finish(P, found, tc, pos);
+        int res = traverse_closest_any<COUNT>(P, r, got, tc, pos, lc, sm, budget);   // warp-synchronous
+        // a walk given up at the budget: the ray is parked and walked again by k_primary_long, among long walks only
+        bool parked = false;
+        const bool over = got && res == kTravOverBudget;
+        if (__any_sync(all, over)) {
+            bool redo = false;
+            if (over) { parked = park_ray(P, 0, r64, job.q, job.slot); redo = !parked; n_parked++; }
+            if (__any_sync(all, redo)) {                          // parking buffer full: walk again right here, without a budget
+                if (redo) r.t = kRayTInit;
+                float tc2; uint32_t pos2;
+                const int res2 = traverse_closest_any<COUNT>(P, r, redo, tc2, pos2, lc, sm);
+                if (redo) { res = res2; tc = tc2; pos = pos2; }
+            }
+        }
+        const bool done = got && !parked, found = res == kTravHit;
+        if (done) job.finish(P, found, tc, pos);
         if (P.max_depth > 0)          // the recursion step at once, while ray and hit are at hand (no k_emit pass over the tile)
-            emit_paths(P, 0, got, job.q, job.slot, {r64[0], r64[1], r64[2]}, {r64[3], r64[4], r64[5]}, tc,
+            emit_paths(P, 0, done, job.q, job.slot, {r64[0], r64[1], r64[2]}, {r64[3], r64[4], r64[5]}, tc,
                        found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos, n_refl);
     }
 #endif
     warp_add(&P.tot->rays_reflection, n_refl);
     warp_add(&P.tot->rays_primary, job.n_rays);
+    warp_add(&P.tot->rays_overflow, n_parked);
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
+}
+
+// The primary rays k_primary parked (walks longer than P.primary_budget pair visits), 32 to a warp: the same closest-hit walk from
+// the start, without a budget, then the hit record and the recursion step exactly as k_primary does them.  A long walk in
+// k_primary has the other 31 lanes of its 8x4 block waiting; here its neighbours are long walks too.
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary_long(const __grid_constant__ Params P, int work_idx) {
+    const uint32_t n = min(P.sched->ovf_count[0], P.ovf_cap);
+    if (n == 0) return;
+    LocalCount lc;
+    uint32_t n_refl = 0, n_rays = 0;
+    while (true) {
+        const unsigned long long base = warp_fetch(&P.sched->work[work_idx]);
+        if (base >= n) break;
+        const uint32_t i = (uint32_t)base + (threadIdx.x & 31u);
+        const bool active = i < n;
+        double r64[kRay64];
+        TRay r;
+        uint32_t q = 0, slot = 0;
+        if (active) {
+            const OvfRay &o = P.ovf[i];
+            Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = kRayTInit;
+            q = o.target; slot = o.bit;
+            tray_setup(r, ray, P.bound, r64);
+            tray_nearest_setup(r, P.bound);
+        }
+        float tc; uint32_t pos;
+        const bool found = traverse_closest_any<COUNT>(P, r, active, tc, pos, lc) == kTravHit;
+        if (active) {
+            int x, y, fbi = -1;
+            if (!slot_pixel(P, slot, x, y, fbi)) fbi = -1;
+            n_rays++;
+            store_primary_hit(P, slot, q, fbi, found, tc, pos);
+        }
+        if (P.max_depth > 0)
+            emit_paths(P, 0, active, q, slot, {r64[0], r64[1], r64[2]}, {r64[3], r64[4], r64[5]}, tc,
+                       found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos, n_refl);
+    }
+    warp_add(&P.tot->rays_reflection, n_refl);
+    warp_add(&P.tot->rays_primary, n_rays);
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
 

@@ -32,6 +32,14 @@ constexpr uint32_t kChunkSharedShift = 5;
 constexpr uint32_t kChunkMaxShift = 6;
 constexpr uint32_t kChunkMax = 1u << kChunkMaxShift;
 constexpr uint32_t kDefaultBudget = 384;    // node visits + triangle tests before a ray is parked for k_overflow
+// Pair visits after which a primary ray's walk is given up and the ray parked: k_primary_long walks the parked rays again, from
+// the start, in warps that hold long walks only (option "primary_budget").  The mean primary walk of the dragon-class frame is 26
+// pair visits, 2.7 % of the rays need more than 64 and the longest ~300 -- and while one lane finishes such a walk the other 31
+// idle: cutting every walk at 64 visits (timing experiment, wrong pixels) took 21 % off k_primary.  But a lone walk advances at
+// ~1 us per DEPENDENT pair visit whoever its neighbours are, so the second kernel cannot end before its longest walk has:
+// measured k_primary 1.64 -> 1.31 ms + k_primary_long 0.55 ms at a budget of 64 (0.41 -> 0.24 + 0.31 ms for one rank's 1/8 share).
+// OFF by default (0); only splitting a long walk across lanes can shorten it.
+constexpr uint32_t kDefaultPrimaryBudget = 0;
 
 // ---- device-side scene layout (SoA arrays in HBM, uploaded once) -----------------------------------
 // The BVH is stored per INTERIOR node as the pair of its two children (bvh.cpp:89-97 allocates them adjacently
@@ -113,6 +121,7 @@ struct Params {
     uint32_t pos_of_tri0;            // leaf position of original triangle 0 (closestIndex default, raythread.cpp:205)
     uint32_t budget;                 // see kDefaultBudget
     uint32_t warp_budget;            // see kWarpBudget
+    uint32_t primary_budget;         // pair visits after which k_primary parks a closest-hit walk for k_primary_long (0: never), see kDefaultPrimaryBudget
     double cam[3], rot[9];
     float vp_w, vp_h, vp_d;
     int W, H, max_depth;

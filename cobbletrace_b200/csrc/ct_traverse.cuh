@@ -197,7 +197,8 @@ constexpr uint32_t kFullMask = 0xffffffffu;
 // WARP-SYNCHRONOUS: all 32 lanes call it (lanes without a ray pass active = false); every iteration = one node
 // visit per live lane, and the lanes re-converge at the vote that ends it (left to itself the compiler lets the
 // lanes of a warp drift apart for the whole walk: measured 8 of 32 lanes active).
-// Returns kTravHit/kTravMiss = ray.t != 1e30f ("found").
+// Returns kTravHit/kTravMiss = ray.t != 1e30f ("found"), or kTravOverBudget when the walk was given up after `budget` pair visits
+// (k_primary then parks the ray for k_primary_long: warps made of long walks only).
 #ifndef CT_SM_CLOSEST
 #define CT_SM_CLOSEST 0
 #endif
@@ -208,7 +209,8 @@ constexpr int kClosestWords = kSmClosest > 0 ? 5 * kSmClosest : 1;   // k_primar
 #endif
 constexpr int kLeafHold = CT_LEAF_HOLD;
 template <bool COUNT>
-CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc, uint32_t *sm = nullptr) {
+CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc, uint32_t *sm = nullptr,
+                            const uint32_t budget = 0xffffffffu) {
     // stack entry = a pushed right child: (ref, cnt), the bracket of its tmin and its parent pair (to find its fp64
     // bounds again when the bracket cannot decide).  The first kSmClosest entries live in shared memory (sm = this thread's
     // column of the kernel's closest_sm array, five words per entry; see traverse_wide for the why), the rest in local memory.
@@ -217,6 +219,8 @@ CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclose
     float stk_lo[kStackMax - kSm], stk_hi[kStackMax - kSm];
     auto sm_at = [&](int i, int w) -> uint32_t & { return sm[(5 * i + w) * kBlockThreads]; };
     int sp = 0;
+    uint32_t visits = 0;       // pair visits so far
+    bool over = false;
     tclosest = kFinf;          // raythread.cpp:204
     closest_pos = kNoPos;      // "closestIndex = 0" default, resolved by the caller via pos_of_tri0
     uint32_t cur_ref = P.root_ref, cur_cnt = P.root_cnt;   // current (already accepted) node
@@ -250,6 +254,7 @@ CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclose
                 }
             } else {
                 CT_CHECK(cur_ref < P.n_pairs);
+                if (++visits > budget) { over = true; live = false; continue; }      // a long walk: the caller parks the ray (k_primary)
                 DevPair32 pr;
                 load_pair32(P.pairs32, cur_ref, pr);
                 prefetch_children(P, pr);
@@ -293,6 +298,7 @@ CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclose
         }
     }
     if (!active) return kTravMiss;
+    if (over) return kTravOverBudget;          // given up after `budget` pair visits: ray.t, tclosest, closest_pos are those of a walk half done
     return r.t != kRayTInit ? kTravHit : kTravMiss;
 }
 
@@ -1041,7 +1047,8 @@ CT_DEV int traverse_wide_nearest(const Params &P, const TRay &r, bool active, fl
 #define CT_NEAREST 0                 // 1: primary rays take the order-free walk (traverse_wide_nearest) where the ray allows it -- measured slower, DESIGN.md 5
 #endif
 template <bool COUNT>
-CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc, uint32_t *sm = nullptr) {
+CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc, uint32_t *sm = nullptr,
+                                const uint32_t budget = 0xffffffffu) {
     if (CT_NEAREST) {
         // r.sg > 0: tray_nearest_setup found the ray within the limits of the slop analysis (and r.filt); ray.t must be 1e30f
         const bool fr = active & (r.sg > 0.0f) & (r.t == kRayTInit) & (P.nested != 0u) & (P.wide != nullptr);
@@ -1065,7 +1072,7 @@ CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tc
         }
         return res;
     }
-    if (!CT_WIDE_CLOSEST) return traverse_closest<COUNT>(P, r, active, tclosest, closest_pos, lc, sm);
+    if (!CT_WIDE_CLOSEST) return traverse_closest<COUNT>(P, r, active, tclosest, closest_pos, lc, sm, budget);
     const bool cons = r.filt & (P.nested != 0u) & (P.wide != nullptr);
     const float t0 = r.t;
     int res = traverse_wide_closest<COUNT>(P, r, active & cons, tclosest, closest_pos, lc);

@@ -227,6 +227,9 @@ int ct_gpu_sync(int device);
  *                       the next render, 0 / 1 = off.
  *   "shared_static_eighths"  see ct_gpu_share_partition.
  *   "shared_chunk_shift"  log2 of the pixels a warp steals at a time in a shared frame: 5 (default, also 0) or 6.
+ *   "primary_budget"    pair visits after which a primary ray's closest-hit walk is given up and the ray parked for a second
+ *                       kernel that walks the long rays together (same result; measured slower): 0 = default (never), < 0 = never.
+ *                       Read at upload.
  *   "shared_run_shift"  log2 of the run of consecutive 32-pixel chunks (horizontally adjacent 8x4 blocks) that is dealt to /
  *                       stolen by a GPU as one unit in a shared frame: 0 (default) = chunk by chunk.  Every participant of a
  *                       frame must use the same value.
