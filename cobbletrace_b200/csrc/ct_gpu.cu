@@ -688,8 +688,13 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
         // and walked again by k_primary_long, in warps made of long walks only
         const bool park_primary = s.can_overflow && pk.primary_budget > 0u;
         v0.ovf = park_primary ? s.ovf_all : nullptr;
-        if (count) k_primary<true><<<grid, kBlockThreads, 0, st>>>(v0);
-        else k_primary<false><<<grid, kBlockThreads, 0, st>>>(v0);
+        if (park_primary) {
+            if (count) k_primary<true, true><<<grid, kBlockThreads, 0, st>>>(v0);
+            else k_primary<false, true><<<grid, kBlockThreads, 0, st>>>(v0);
+        } else {
+            if (count) k_primary<true, false><<<grid, kBlockThreads, 0, st>>>(v0);
+            else k_primary<false, false><<<grid, kBlockThreads, 0, st>>>(v0);
+        }
         TRY(mark("primary", 0));
         if (park_primary) {
             if (count) k_primary_long<true><<<grid, kBlockThreads, 0, st>>>(v0, work++);

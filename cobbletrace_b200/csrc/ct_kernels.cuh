@@ -293,7 +293,8 @@ struct PrimaryJob {
 // chunk together (one 8x4 pixel block: neighbouring rays visit the same nodes); -DCT_REFILL_T=n (n = 1..32) selects
 // traverse_closest_refill instead, which refills idle lanes from the next chunk -- measured SLOWER at every threshold
 // (1.45 ms -> 1.86 / 2.12 / 2.29 ms for n = 16 / 8 / 4), the mixed warps lose the block's coherence.
-template <bool COUNT>
+// PARK: walks longer than P.primary_budget pair visits are given up and parked for k_primary_long (option "primary_budget").
+template <bool COUNT, bool PARK>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __grid_constant__ Params P) {
     LocalCount lc;
     uint32_t n_refl = 0;
@@ -308,18 +309,18 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary(const __g
     traverse_closest_refill<COUNT>(P, job, lc);
 #else
     const uint32_t all = kFullMask;
-    const uint32_t budget = (P.primary_budget > 0u && P.ovf != nullptr) ? P.primary_budget : 0xffffffffu;
+    const uint32_t budget = (PARK && P.primary_budget > 0u && P.ovf != nullptr) ? P.primary_budget : 0xffffffffu;
     while (true) {
         bool got = false;
         double r64[kRay64];
         TRay r;
         if (!job.refill(P, all, got, r, r64)) break;          // a whole chunk's worth of slots: one per lane
         float tc; uint32_t pos;
-        int res = traverse_closest_any<COUNT>(P, r, got, tc, pos, lc, sm, budget);   // warp-synchronous
+        int res = traverse_closest_any<COUNT, PARK>(P, r, got, tc, pos, lc, sm, budget);   // warp-synchronous
         // a walk given up at the budget: the ray is parked and walked again by k_primary_long, among long walks only
         bool parked = false;
-        const bool over = got && res == kTravOverBudget;
-        if (__any_sync(all, over)) {
+        const bool over = PARK && got && res == kTravOverBudget;
+        if (PARK && __any_sync(all, over)) {
             bool redo = false;
             if (over) { parked = park_ray(P, 0, r64, job.q, job.slot); redo = !parked; n_parked++; }
             if (__any_sync(all, redo)) {                          // parking buffer full: walk again right here, without a budget

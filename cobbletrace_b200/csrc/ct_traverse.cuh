@@ -208,7 +208,7 @@ constexpr int kClosestWords = kSmClosest > 0 ? 5 * kSmClosest : 1;   // k_primar
 #define CT_LEAF_HOLD 0
 #endif
 constexpr int kLeafHold = CT_LEAF_HOLD;
-template <bool COUNT>
+template <bool COUNT, bool BUDGETED = false>
 CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc, uint32_t *sm = nullptr,
                             const uint32_t budget = 0xffffffffu) {
     // stack entry = a pushed right child: (ref, cnt), the bracket of its tmin and its parent pair (to find its fp64
@@ -254,7 +254,7 @@ CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclose
                 }
             } else {
                 CT_CHECK(cur_ref < P.n_pairs);
-                if (++visits > budget) { over = true; live = false; continue; }      // a long walk: the caller parks the ray (k_primary)
+                if (BUDGETED && ++visits > budget) { over = true; live = false; continue; }      // a long walk: the caller parks the ray (k_primary<COUNT, true>)
                 DevPair32 pr;
                 load_pair32(P.pairs32, cur_ref, pr);
                 prefetch_children(P, pr);
@@ -298,7 +298,7 @@ CT_DEV int traverse_closest(const Params &P, TRay &r, bool active, float &tclose
         }
     }
     if (!active) return kTravMiss;
-    if (over) return kTravOverBudget;          // given up after `budget` pair visits: ray.t, tclosest, closest_pos are those of a walk half done
+    if (BUDGETED && over) return kTravOverBudget;          // given up after `budget` pair visits: ray.t, tclosest, closest_pos are those of a walk half done
     return r.t != kRayTInit ? kTravHit : kTravMiss;
 }
 
@@ -1046,7 +1046,7 @@ CT_DEV int traverse_wide_nearest(const Params &P, const TRay &r, bool active, fl
 #ifndef CT_NEAREST
 #define CT_NEAREST 0                 // 1: primary rays take the order-free walk (traverse_wide_nearest) where the ray allows it -- measured slower, DESIGN.md 5
 #endif
-template <bool COUNT>
+template <bool COUNT, bool BUDGETED = false>
 CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tclosest, uint32_t &closest_pos, LocalCount &lc, uint32_t *sm = nullptr,
                                 const uint32_t budget = 0xffffffffu) {
     if (CT_NEAREST) {
@@ -1072,7 +1072,7 @@ CT_DEV int traverse_closest_any(const Params &P, TRay &r, bool active, float &tc
         }
         return res;
     }
-    if (!CT_WIDE_CLOSEST) return traverse_closest<COUNT>(P, r, active, tclosest, closest_pos, lc, sm, budget);
+    if (!CT_WIDE_CLOSEST) return traverse_closest<COUNT, BUDGETED>(P, r, active, tclosest, closest_pos, lc, sm, budget);
     const bool cons = r.filt & (P.nested != 0u) & (P.wide != nullptr);
     const float t0 = r.t;
     int res = traverse_wide_closest<COUNT>(P, r, active & cons, tclosest, closest_pos, lc);
