@@ -517,9 +517,11 @@ int ct_gpu_upload_scene(int device, const ct_scene_desc *d) {
     TRY(dev_alloc(s, &s.occ_all, (size_t)p.cap * p.occ_words * levels, true));
     p.occ = s.occ_all;
     if (s.can_overflow) {
-        // parked rays per launch: 2^18 (16 MB), or 1/16 of the frame's paths where that is more (k_primary parks 2-3 % of a dragon-class
-        // frame's primary rays); a full buffer means finishing rays in place, which must stay hypothetical
-        p.ovf_cap = std::max<uint32_t>(1u << 18, p.cap / 16u);
+        // parked rays per launch: 2^18 (16 MB) -- with primary walks parked as well (option "primary_budget": 2-3 % of a dragon-class
+        // frame's primary rays) 1/16 of the frame's paths where that is more; a full buffer means finishing rays in place, which
+        // must stay hypothetical
+        p.ovf_cap = 1u << 18;
+        if (p.primary_budget > 0u) p.ovf_cap = std::max<uint32_t>(p.ovf_cap, p.cap / 16u);
         TRY(dev_alloc(s, &s.ovf_all, (size_t)p.ovf_cap * 2 * levels));
         TRY(dev_alloc(s, &s.ovf_huge_all, (size_t)p.ovf_cap * 2 * levels));
         p.ovf = s.ovf_all; p.ovf_huge = s.ovf_huge_all;
