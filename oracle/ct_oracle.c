@@ -752,3 +752,108 @@ uint64_t ct_oracle_free_check(const ct_oracle_scene *s, uint64_t n, const double
     }
     return bad;
 }
+
+/* ---- prototype: ONE long closest-hit walk split across the 32 lanes of a warp ("long walks split across a warp") --------
+ * The order-free formulation above lets a walk be processed as a frontier: per ROUND up to 32 pending nodes are taken off a shared
+ * stack (one per lane), their children tested against best + 2 sigma, accepted leaves tested on the spot (candidates as above),
+ * accepted interior children pushed back; the warp-wide minimum of t is taken once per round.  A round costs about what one visit of
+ * the ordered walk costs (~1 us on the device), so `rounds` against the ordered walk's pair visits is the floor such a kernel would
+ * have against today's.  Returns found / -1 like ct_oracle_closest_free; *rounds and *pair_visits are set either way. */
+int ct_oracle_closest_rounds(const ct_oracle_scene *s, const double org[3], const double dir[3], uint32_t *index, float *tclosest,
+                             uint32_t *rounds, uint32_t *pair_visits) {
+    ray r = {v_load(org), v_load(dir), RAY_T_INIT};
+    uint64_t stats[4] = {0, 0, 0, 0};
+    free_ctx c; memset(&c, 0, sizeof c);
+    c.s = s; c.r = &r; c.stats = stats; c.best = (double)RAY_T_INIT;
+    *rounds = 0; *pair_visits = 0;
+    double m = 0;
+    for (int a = 0; a < 3; a++) {
+        double bound = fmax(fabs(s->node_min[a]), fabs(s->node_max[a]));
+        double mk = (bound + fabs(org[a])) / fabs(dir[a]);
+        if (!(mk < 1e30)) return -1;
+        m = fmax(m, mk);
+    }
+    c.sigma = m * 0x1p-16;
+    float t0;
+    if (!box_times_ref(&r, s->node_min, s->node_max, &t0)) { *index = 0; *tclosest = FINF; return 0; }
+    enum { CAP = 4096 };
+    static __thread uint32_t stk[CAP];
+    static __thread float stk_t[CAP];
+    uint32_t sp = 0;
+    if (s->node_count[0] > 0) free_leaf(&c, 0, t0); else { stk[sp] = 0; stk_t[sp] = t0; sp++; }
+    while (sp > 0) {
+        uint32_t take = sp < 32 ? sp : 32;
+        sp -= take;
+        uint32_t out[64]; float out_t[64]; uint32_t n_out = 0;
+        const double thr = c.best + 2.0 * c.sigma;                      /* the warp-wide minimum: once per round */
+        double best_round = c.best;
+        (*rounds)++;
+        for (uint32_t l = 0; l < take; l++) {                           /* "lanes" */
+            uint32_t node = stk[sp + l];
+            if ((double)stk_t[sp + l] > thr) continue;
+            (*pair_visits)++;
+            for (uint32_t ch = s->node_left[node]; ch <= s->node_left[node] + 1; ch++) {
+                float tc;
+                if (!box_times_ref(&r, s->node_min + 3 * (size_t)ch, s->node_max + 3 * (size_t)ch, &tc)) continue;
+                if ((double)tc > thr) continue;
+                if (s->node_count[ch] > 0) {
+                    double keep = c.best;                               /* lanes see each other's hits at the round's end only */
+                    c.best = best_round;
+                    free_leaf(&c, ch, tc);
+                    if (c.best < keep) keep = c.best;
+                    best_round = c.best < best_round ? c.best : best_round;
+                    c.best = keep < best_round ? keep : best_round;
+                } else { out[n_out] = ch; out_t[n_out] = tc; n_out++; }
+            }
+        }
+        if (sp + n_out > CAP) return -1;
+        for (uint32_t k = 0; k < n_out; k++) { stk[sp] = out[k]; stk_t[sp] = out_t[k]; sp++; }
+    }
+    if (c.overflow) return -1;
+    if (c.best == (double)RAY_T_INIT) { *index = 0; *tclosest = FINF; return 0; }
+    if (c.best >= (double)FINF) return -1;
+    const double tau = c.best + c.sigma;
+    int n = 0;
+    for (int j = 0; j < c.n_cand; j++) if ((double)c.cand[j].t <= tau) c.cand[n++] = c.cand[j];
+    for (int j = 0; j < n; j++) if (!((double)c.cand[j].tmin <= tau)) return -1;
+    for (int j = 1; j < n; j++) {
+        free_cand z = c.cand[j]; int k = j;
+        while (k > 0 && c.cand[k - 1].pos > z.pos) { c.cand[k] = c.cand[k - 1]; k--; }
+        c.cand[k] = z;
+    }
+    float rt = RAY_T_INIT, tc = FINF; uint32_t idx = 0, entered = 0xffffffffu;
+    for (int j = 0; j < n; j++) {
+        if (c.cand[j].leaf != entered) {
+            if (!(c.cand[j].tmin < rt)) continue;
+            entered = c.cand[j].leaf;
+        }
+        rt = MACRO_MIN(rt, c.cand[j].t);
+        if (rt != RAY_T_INIT && rt < tc) { idx = s->tri_index[c.cand[j].pos]; tc = rt; }
+    }
+    *index = idx; *tclosest = tc;
+    return rt != RAY_T_INIT;
+}
+
+/* Over n rays: the ordered walk's pair visits (= box tests / 2) against the frontier walk's rounds, for the rays whose ordered walk
+ * needs at least min_visits pair visits.  out[0] rays considered, out[1] differing answers (must be 0), out[2] undecided, out[3] sum of
+ * ordered pair visits, out[4] sum of rounds, out[5] max ordered pair visits, out[6] max rounds, out[7] rounds of the longest ordered walk. */
+void ct_oracle_rounds_check(const ct_oracle_scene *s, uint64_t n, const double *org, const double *dir, uint32_t min_visits, uint64_t out[8]) {
+    memset(out, 0, 8 * sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; i++) {
+        ctx cx; memset(&cx, 0, sizeof cx); cx.s = s;
+        ray r = {v_load(org + 3 * i), v_load(dir + 3 * i), RAY_T_INIT};
+        float ta = FINF; uint32_t ia = 0;
+        bvh_closest(&cx, &r, 0, &ta, &ia);
+        int fa = r.t != RAY_T_INIT;
+        uint64_t visits = cx.c.box_tests / 2;
+        if (visits < min_visits) continue;
+        uint32_t ib = 0, rounds = 0, pv = 0; float tb = 0;
+        int fb = ct_oracle_closest_rounds(s, org + 3 * i, dir + 3 * i, &ib, &tb, &rounds, &pv);
+        out[0]++;
+        if (fb < 0) { out[2]++; continue; }
+        if (fa != fb || ia != ib || memcmp(&ta, &tb, sizeof ta) != 0) out[1]++;
+        out[3] += visits; out[4] += rounds;
+        if (visits > out[5]) { out[5] = visits; out[7] = rounds; }
+        if (rounds > out[6]) out[6] = rounds;
+    }
+}

@@ -98,6 +98,11 @@ int ct_oracle_closest_free(const ct_oracle_scene *s, const double org[3], const 
 uint64_t ct_oracle_free_check(const ct_oracle_scene *s, uint64_t n, const double *org, const double *dir, int order,
                               uint64_t *stats, uint64_t *ref_stats);
 
+/* Prototype of ONE walk split across a warp: the order-free search as a frontier of up to 32 nodes per round (ct_oracle.c). */
+int ct_oracle_closest_rounds(const ct_oracle_scene *s, const double org[3], const double dir[3], uint32_t *index, float *tclosest,
+                             uint32_t *rounds, uint32_t *pair_visits);
+void ct_oracle_rounds_check(const ct_oracle_scene *s, uint64_t n, const double *org, const double *dir, uint32_t min_visits, uint64_t out[8]);
+
 #ifdef __cplusplus
 }
 #endif

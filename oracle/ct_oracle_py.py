@@ -165,6 +165,19 @@ def free_check(scene: "OracleScene", org, direction, order=1):
                       "ref_box": int(ref[0]), "ref_tri": int(ref[1]), "rays": int(org.shape[0])}
 
 
+def rounds_check(scene: "OracleScene", org, direction, min_visits=0):
+    """Prototype (ct_oracle.c): the order-free closest-hit search as a 32-wide frontier against the reference-order walk, for the rays
+    whose ordered walk needs >= min_visits pair visits."""
+    org = np.ascontiguousarray(org, np.float64); direction = np.ascontiguousarray(direction, np.float64)
+    out = np.zeros(8, np.uint64)
+    L = lib()
+    L.ct_oracle_rounds_check.restype = None
+    L.ct_oracle_rounds_check.argtypes = [C.POINTER(_Scene), C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.ct_oracle_rounds_check(C.byref(scene.c), org.shape[0], _ptr(org), _ptr(direction), min_visits, _ptr(out))
+    keys = ("rays", "differ", "undecided", "ordered_pair_visits", "rounds", "max_ordered_pair_visits", "max_rounds", "rounds_of_longest")
+    return {k: int(v) for k, v in zip(keys, out)}
+
+
 def camera_rotation(yaw=0.0, pitch=0.0, roll=0.0):
     out = np.zeros(9)
     lib().ct_oracle_camera_rotation(yaw, pitch, roll, _ptr(out))

@@ -38,3 +38,22 @@ def test_free_walk_equals_reference_walk_on_generated_scenes(golden):
         for order in (0, 1):
             bad, st = O.free_check(O.OracleScene(fs), org, d, order)
             assert bad == 0, (k, order, bad, st)
+
+
+@pytest.mark.parametrize("name,H", [("scene_file_cube", 96), ("scene_import", 96), ("scene_import_bunny", 128), ("pc_big", 96)])
+def test_frontier_walk_equals_reference_walk(name, H, scene_loader):
+    """The same search as a FRONTIER -- up to 32 pending nodes per round, the minimum of t exchanged once per round: what one
+    warp finishing one long walk together would do.  Every decided ray equals the reference-order walk; the rounds a
+    walk needs are bounded by the tree's depth, not by the number of boxes the ray grazes."""
+    fs = scene_loader(name)
+    sc = O.OracleScene(fs)
+    rng = np.random.default_rng(9)
+    org, d = camera_rays(fs, H, H, rng, 0.002)
+    st = O.rounds_check(sc, org, d, 0)
+    assert st["differ"] == 0 and st["rays"] == org.shape[0], (name, st)
+    assert st["undecided"] <= 0.02 * st["rays"], (name, st)
+    c = fs.tri.reshape(-1, 3).mean(0)
+    ext = np.ptp(fs.tri.reshape(-1, 3), axis=0).max()
+    org = c + rng.normal(size=(3000, 3)) * ext * 0.7
+    st = O.rounds_check(sc, org, rng.normal(size=(3000, 3)), 0)
+    assert st["differ"] == 0, (name, "random", st)
