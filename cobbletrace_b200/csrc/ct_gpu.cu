@@ -128,6 +128,7 @@ std::recursive_mutex g_dev_mutex[kMaxDevices];
 #define DEVICE_GUARD(device) std::lock_guard<std::recursive_mutex> dev_lock_(g_dev_mutex[((device) >= 0 && (device) < kMaxDevices) ? (device) : 0])
 long long g_budget_option = 0;       // ct_gpu_set_option("traversal_budget"); 0 = default
 long long g_warp_budget_option = 0;  // ct_gpu_set_option("overflow_warp_budget"); 0 = default
+long long g_primary_split = 0;            // ct_gpu_set_option("primary_split"): parked primary rays are finished one ray per warp (k_primary_split)
 long long g_primary_budget_option = 0;   // ct_gpu_set_option("primary_budget"); 0 = default (kDefaultPrimaryBudget: never), < 0 = never
 long long g_static_eighths = 7;      // ct_gpu_set_option("shared_static_eighths"), see next_chunk
 long long g_shared_chunk_shift = 0;  // ct_gpu_set_option("shared_chunk_shift"): 0 = kChunkSharedShift
@@ -699,9 +700,15 @@ static int render_impl(int device, int y_start, int y_end, ct_ray_counters *coun
         }
         TRY(mark("primary", 0));
         if (park_primary) {
-            if (count) k_primary_long<true><<<grid, kBlockThreads, 0, st>>>(v0, work++);
-            else k_primary_long<false><<<grid, kBlockThreads, 0, st>>>(v0, work++);
-            TRY(mark("primary_long", 0));
+            if (g_primary_split) {
+                if (count) k_primary_split<true><<<s.n_sm * 4, kOvfThreads, 0, st>>>(v0);
+                else k_primary_split<false><<<s.n_sm * 4, kOvfThreads, 0, st>>>(v0);
+                TRY(mark("primary_split", 0));
+            } else {
+                if (count) k_primary_long<true><<<grid, kBlockThreads, 0, st>>>(v0, work++);
+                else k_primary_long<false><<<grid, kBlockThreads, 0, st>>>(v0, work++);
+                TRY(mark("primary_long", 0));
+            }
         }
     }
     for (int d = 0; d <= depth_max; d++) {
@@ -911,6 +918,11 @@ int ct_gpu_set_option(const char *name, long long value) {
     if (!strcmp(name, "l2_persist")) {
         if (value != 0 && value != 1) return fail(CT_ERR_INVALID, "l2_persist must be 0 or 1");
         g_l2_persist = value;
+        return CT_OK;
+    }
+    if (!strcmp(name, "primary_split")) {
+        if (value != 0 && value != 1) return fail(CT_ERR_INVALID, "primary_split must be 0 or 1");
+        g_primary_split = value;
         return CT_OK;
     }
     if (!strcmp(name, "primary_budget")) {

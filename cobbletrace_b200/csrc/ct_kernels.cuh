@@ -384,6 +384,180 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocks) k_primary_long(cons
     if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
 }
 
+// The parked primary rays, ONE RAY PER WARP (option "primary_split"): the order-free closest-hit search of traverse_wide_nearest
+// run as a frontier.  Per round every lane takes one pending node of the wide tree off a stack the warp shares, tests its
+// four children conservatively against best + 2 sigma, tests accepted leaves on the spot (a barycentric pass within best + sigma
+// becomes a candidate once the exact test of its leaf's own box confirms that the reference can reach it) and hands accepted interior
+// children back; the warp-wide minimum of t is exchanged once per round.  Afterwards the lanes' candidates within sigma of the
+// minimum are gathered and lane 0 replays the reference's update rules over them in leaf order -- the argument is
+// traverse_wide_nearest's, the CPU prototype tests/test_free_closest_prototype.py::test_frontier_walk_equals_reference_walk.
+// A walk of ~300 DEPENDENT pair visits (the floor under k_primary) becomes ~12 rounds: a round descends two levels of
+// the reference's tree whatever the number of boxes the ray grazes.  Undecided rays (more than 32 candidates, a candidate whose leaf
+// starts beyond the minimum + sigma, t >= FINF, a full stack, rays outside the slop analysis) are walked by lane 0 in the
+// reference's order.
+constexpr int kSplitStack = 512;         // pending wide nodes per warp: (node, lower end of its near bracket)
+template <bool COUNT>
+__global__ void __launch_bounds__(kOvfThreads) k_primary_split(const __grid_constant__ Params P) {
+    const uint32_t n = min(P.sched->ovf_count[0], P.ovf_cap);
+    if (n == 0) return;
+    LocalCount lc;
+    uint32_t n_refl = 0, n_rays = 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    __shared__ uint32_t wnode[kOvfThreads / 32][kSplitStack];
+    __shared__ float wnear[kOvfThreads / 32][kSplitStack];
+    uint32_t *const stk = wnode[threadIdx.x >> 5];
+    float *const stk_near = wnear[threadIdx.x >> 5];
+    while (true) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(&P.sched->ovf_cursor[0], 1u);
+        idx = __shfl_sync(kFullMask, idx, 0);
+        if (idx >= n) break;
+        const OvfRay &o = P.ovf[idx];
+        Ray ray; ray.o = ld3(o.o); ray.d = ld3(o.d); ray.t = kRayTInit;
+        const uint32_t q = o.target, slot = o.bit;
+        double r64[kRay64];
+        TRay r;
+        tray_setup(r, ray, P.bound, r64);                 // every lane holds the same ray
+        tray_nearest_setup(r, P.bound);
+        bool ordered = !(r.sg > 0.0f) || P.nested == 0u || P.wide == nullptr;      // warp-uniform: lane 0 walks in the reference's order
+        bool found = false;
+        float tc = kFinf;                                 // raythread.cpp:204
+        uint32_t pos = kNoPos;
+        if (!ordered) {
+            if (COUNT && lane == 0) lc.box++;
+            if (root_accept(P, r)) {
+                float cand_t[kNearCand], cand_tmin[kNearCand];
+                uint32_t cand_pos[kNearCand], cand_code[kNearCand];
+                int ncand = 0;
+                bool undecided = false;
+                float best = kRayTInit, band = kRayTInit, thr = kRayTInit;          // this lane's view; made warp-wide once per round
+                if (lane == 0) { stk[0] = 0u; stk_near[0] = -kRayTInit; }
+                __syncwarp();
+                uint32_t sp = 1;
+                while (sp > 0) {
+                    const uint32_t take = min(sp, 32u);
+                    sp -= take;
+                    uint32_t n_out = 0, out_ref[kWide];
+                    float out_near[kWide];
+                    if (lane < take && stk_near[sp + lane] < thr) {
+                        const float4 *qn = reinterpret_cast<const float4 *>(P.wide + stk[sp + lane]);
+                        if (COUNT) lc.box += kWide;
+#pragma unroll
+                        for (int e = 0; e < kWide; e++) {
+                            float4 a; uint4 b;
+                            ldg256(qn + 2 * e, a, b);
+                            const float bmax1 = __uint_as_float(b.x), bmax2 = __uint_as_float(b.y);
+                            const bool px = r.rdf[0] > 0.0f, py = r.rdf[1] > 0.0f, pz = r.rdf[2] > 0.0f;
+                            const float n0 = __fmaf_rd(px ? a.x : a.w, r.rdf[0], r.cl[0]), f0 = __fmaf_ru(px ? a.w : a.x, r.rdf[0], r.cu[0]);
+                            const float n1 = __fmaf_rd(py ? a.y : bmax1, r.rdf[1], r.cl[1]), f1 = __fmaf_ru(py ? bmax1 : a.y, r.rdf[1], r.cu[1]);
+                            const float n2 = __fmaf_rd(pz ? a.z : bmax2, r.rdf[2], r.cl[2]), f2 = __fmaf_ru(pz ? bmax2 : a.z, r.rdf[2], r.cu[2]);
+                            const float near_lo = fmaxf(fmaxf(n0, n1), n2), far_hi = fminf(fminf(f0, f1), f2);      // box_maybe's brackets
+                            if ((far_hi < near_lo) | (far_hi <= 0.0f) | (near_lo >= thr)) continue;
+                            if (b.w == 0u) { out_ref[n_out] = b.z; out_near[n_out] = near_lo; n_out++; continue; }
+                            for (uint32_t k = 0; k < b.w; k++) {                       // a leaf: its triangles on the spot
+                                const uint32_t tp = b.z + k;
+                                if (COUNT) lc.tri++;
+                                const TriHit th = leaf_triangle<false, COUNT>(P, r, tp, lc);
+                                if (!(th.hit & (th.t > kEps) & (th.t < kRayTInit))) continue;      // would not lower a ray.t of 1e30f (bvh.cpp:161)
+                                if (!(th.t < kFinf)) { undecided = true; continue; }
+                                if (!(th.t <= band)) continue;
+                                const uint32_t code = __ldg(P.tri_parent + tp);        // the triangle's leaf: 2 * pair + side
+                                if (COUNT) lc.box_exact++;
+                                const BoxTimes bt = code == kNoPos ? box_times(r.r64, P.root_min, P.root_max) : exact_child(P.pairs64, code >> 1, code & 1u, r.r64);
+                                if (!((bt.tmax >= bt.tmin) & (bt.tmax > 0.0f))) continue;          // a leaf the reference cannot reach
+                                if (th.t < best) { best = th.t; band = __fadd_ru(best, r.sg); thr = __fadd_ru(band, r.sg); }
+                                if (ncand == kNearCand) {                              // drop what has fallen out of the band
+                                    int m = 0;
+                                    for (int j = 0; j < kNearCand; j++)
+                                        if (cand_t[j] <= band) { cand_t[m] = cand_t[j]; cand_tmin[m] = cand_tmin[j]; cand_pos[m] = cand_pos[j]; cand_code[m] = cand_code[j]; m++; }
+                                    ncand = m;
+                                }
+                                if (ncand == kNearCand) undecided = true;
+                                else { cand_t[ncand] = th.t; cand_tmin[ncand] = bt.tmin; cand_pos[ncand] = tp; cand_code[ncand] = code; ncand++; }
+                            }
+                        }
+                    }
+                    __syncwarp();                                     // every lane has read its entry before the pushes below
+                    // the round's exchange: the minimum of t, "some lane cannot decide", where the accepted children go
+                    float bw = best;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) bw = fminf(bw, __shfl_xor_sync(kFullMask, bw, d));
+                    if (bw < best) { best = bw; band = __fadd_ru(best, r.sg); thr = __fadd_ru(band, r.sg); }
+                    uint32_t incl = n_out;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(kFullMask, incl, d); if ((int)lane >= d) incl += v; }
+                    const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+                    if (__any_sync(kFullMask, undecided) || sp + total > (uint32_t)kSplitStack) { ordered = true; break; }
+                    const uint32_t at = sp + incl - n_out;
+                    for (uint32_t k = 0; k < n_out; k++) { stk[at + k] = out_ref[k]; stk_near[at + k] = out_near[k]; }
+                    sp += total;
+                    __syncwarp();
+                }
+                if (!ordered && best != kRayTInit) {
+                    // ---- S = the candidates within sigma of the minimum, gathered into the (now empty) stack, replayed by lane 0
+                    int m = 0;
+                    bool late = false;                                // a member of S whose leaf starts beyond the minimum + sigma
+                    for (int j = 0; j < ncand; j++)
+                        if (cand_t[j] <= band) {
+                            late |= !(cand_tmin[j] <= band);
+                            cand_t[m] = cand_t[j]; cand_tmin[m] = cand_tmin[j]; cand_pos[m] = cand_pos[j]; cand_code[m] = cand_code[j]; m++;
+                        }
+                    uint32_t incl = (uint32_t)m;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(kFullMask, incl, d); if ((int)lane >= d) incl += v; }
+                    const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+                    if (__any_sync(kFullMask, late) || total > 32u) ordered = true;
+                    else {
+                        uint32_t *const g_pos = stk, *const g_code = stk + 32;
+                        float *const g_t = stk_near, *const g_tmin = stk_near + 32;
+                        const uint32_t at = incl - (uint32_t)m;
+                        for (int j = 0; j < m; j++) { g_t[at + j] = cand_t[j]; g_tmin[at + j] = cand_tmin[j]; g_pos[at + j] = cand_pos[j]; g_code[at + j] = cand_code[j]; }
+                        __syncwarp();
+                        if (lane == 0) {
+                            for (uint32_t j = 1; j < total; j++) {                    // leaf-position order = the reference's test order
+                                const float zt = g_t[j], zm = g_tmin[j]; const uint32_t zp = g_pos[j], zc = g_code[j];
+                                uint32_t k = j;
+                                while (k > 0 && g_pos[k - 1] > zp) { g_t[k] = g_t[k - 1]; g_tmin[k] = g_tmin[k - 1]; g_pos[k] = g_pos[k - 1]; g_code[k] = g_code[k - 1]; k--; }
+                                g_t[k] = zt; g_tmin[k] = zm; g_pos[k] = zp; g_code[k] = zc;
+                            }
+                            float rt = kRayTInit;
+                            uint32_t entered = 0xfffffffeu;                               // (no leaf has this code)
+                            for (uint32_t j = 0; j < total; j++) {
+                                if (g_code[j] != entered) {                                // the box is tested once per leaf visit
+                                    if (!(g_tmin[j] < rt)) continue;                       // bvh.cpp:178, the leaf's own box
+                                    entered = g_code[j];
+                                }
+                                rt = macro_min(rt, g_t[j]);                                // bvh.cpp:161
+                                if (rt != kRayTInit && rt < tc) { pos = g_pos[j]; tc = rt; }   // bvh.cpp:212
+                            }
+                            found = rt != kRayTInit;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (ordered) {                                        // warp-uniform
+            float tc2; uint32_t pos2;
+            const int res = traverse_closest<COUNT>(P, r, lane == 0, tc2, pos2, lc);
+            found = res == kTravHit; tc = tc2; pos = pos2;
+        }
+        if (lane == 0) {                                      // lane 0 holds the answer
+            int x, y, fbi = -1;
+            if (!slot_pixel(P, slot, x, y, fbi)) fbi = -1;
+            n_rays++;
+            store_primary_hit(P, slot, q, fbi, found, tc, pos);
+        }
+        if (P.max_depth > 0)
+            emit_paths(P, 0, lane == 0, q, slot, {r64[0], r64[1], r64[2]}, {r64[3], r64[4], r64[5]}, tc,
+                       found ? (pos == kNoPos ? P.pos_of_tri0 : pos) : kNoPos, n_refl);
+        __syncwarp();
+    }
+    warp_add(&P.tot->rays_reflection, n_refl);
+    warp_add(&P.tot->rays_primary, n_rays);
+    if (COUNT) { warp_add(&P.tot->box_tests, lc.box); warp_add(&P.tot->tri_tests, lc.tri); warp_add(&P.tot->box_exact, lc.box_exact); warp_add(&P.tot->tri_exact, lc.tri_exact); }
+}
+
 // ComputeLighting's shadow rays (raythread.cpp:288-306) for the paths alive at `depth`.  Work item =
 // (shadow light j, path q), j-major, so the 32 lanes of a warp trace 32 neighbouring shading points towards
 // the same light.  Verdicts go to the per-path occlusion mask read by k_shade.

@@ -230,6 +230,9 @@ int ct_gpu_sync(int device);
  *   "primary_budget"    pair visits after which a primary ray's closest-hit walk is given up and the ray parked for a second
  *                       kernel that walks the long rays together (same result; measured slower): 0 = default (never), < 0 = never.
  *                       Read at upload.
+ *   "primary_split"     1: the parked primary rays are finished ONE RAY PER WARP (k_primary_split: the order-free closest-hit search as
+ *                       a 32-wide frontier, ~12 rounds instead of up to ~300 dependent visits) instead of 32 rays to a warp; 0 (default).
+ *                       Applies to the next render.
  *   "shared_run_shift"  log2 of the run of consecutive 32-pixel chunks (horizontally adjacent 8x4 blocks) that is dealt to /
  *                       stolen by a GPU as one unit in a shared frame: 0 (default) = chunk by chunk.  Every participant of a
  *                       frame must use the same value.

@@ -189,24 +189,33 @@ def test_frames_against_oracle(name, W, H, depth, refl, golden, scene_loader, gp
     assert 0 < ctr["box_tests"] <= 2 * octr["box_tests"] and 0 < ctr["tri_tests"] <= octr["tri_tests"]
 
 
-@pytest.mark.parametrize("budget,warp_budget,primary_budget", [(16, 0, 0), (16, 4, 1), (200, 64, 6), (0, 0, 1), (0, 0, -1)])
-def test_parked_rays_give_the_same_frames(budget, warp_budget, primary_budget, golden, scene_loader):
+@pytest.mark.parametrize("budget,warp_budget,primary_budget,split", [(16, 0, 0, 0), (16, 4, 1, 0), (200, 64, 6, 0), (0, 0, 1, 0), (0, 0, -1, 0),
+                                                                     (0, 0, 1, 1), (200, 64, 6, 1), (0, 0, 40, 1)])
+def test_parked_rays_give_the_same_frames(budget, warp_budget, primary_budget, split, golden, scene_loader):
     """Shadow / reflection rays whose walk exceeds the budget are parked and finished by a warp (pass 1) or by the
     whole grid (pass 2) in k_overflow; with tiny budgets nearly every ray takes those paths (and the parking
     buffer overflows, so some are finished in place).  Primary rays whose walk exceeds "primary_budget" pair visits are
-    parked and walked again by k_primary_long (1: every ray that gets past the root; -1: none).  Frames must not change."""
+    parked and walked again by k_primary_long (1: every ray that gets past the root; -1: none) -- or, with "primary_split", finished
+    one ray per warp by the order-free frontier search of k_primary_split.  Frames (and hit records) must not change."""
+    ct.api.set_option("primary_split", split)
     ct.api.set_option("traversal_budget", budget)
     ct.api.set_option("overflow_warp_budget", warp_budget)
     ct.api.set_option("primary_budget", primary_budget)
     try:
         for case in ("bunny_refl_d2_160", "cube_160", "pc_big_96", "import_160"):
             fs, meta = case_scene(case, golden, scene_loader)
-            r = ct.GpuRenderer(0).upload(fs, meta["width"], meta["height"], max_depth=meta["depth"])
+            r = ct.GpuRenderer(0).upload(fs, meta["width"], meta["height"], max_depth=meta["depth"], flags=ct.CT_FLAG_KEEP_HITS)
             r.render_tile()
             frame = r.readback()
+            found, index, t = r.readback_hits()
             parked, in_place = r.overflow_stats()
             r.shutdown()
-            assert np.array_equal(frame, load_frames(case)["frame"]), case
+            gold = load_frames(case)
+            assert np.array_equal(frame, gold["frame"]), case
+            if "found" in gold:                                             # the primary hit records of the compiled reference
+                traced = gold["found"] != 0xFFFFFFFF
+                assert np.array_equal(found[traced], gold["found"][traced]) and np.array_equal(index[traced], gold["index"][traced]), case
+                assert np.array_equal(t[traced].view(np.uint32), gold["t"][traced].view(np.uint32)), case
             if budget == 16 and case != "cube_160":
                 assert parked > 1000, (case, parked)
             if primary_budget == 1 and budget == 0 and case != "cube_160":
@@ -215,6 +224,7 @@ def test_parked_rays_give_the_same_frames(budget, warp_budget, primary_budget, g
         ct.api.set_option("traversal_budget", 0)
         ct.api.set_option("overflow_warp_budget", 0)
         ct.api.set_option("primary_budget", 0)
+        ct.api.set_option("primary_split", 0)
 
 
 def test_shared_frame_mode_on_one_gpu(golden, scene_loader, gpu):

@@ -12,6 +12,8 @@ shifts = [int(v) for v in os.environ.get("CT_SHARED_SHIFTS", "0").split(",")]
 budgets = [int(v) for v in os.environ.get("CT_BUDGETS", "0").split(",")]
 ranks = [int(v) for v in os.environ.get("CT_RANKS", "1,2,4,8").split(",")]
 runs = [int(v) for v in os.environ.get("CT_RUN_SHIFTS", "0").split(",")]
+if os.environ.get("CT_PRIMARY_SPLIT"):
+    api.set_option("primary_split", int(os.environ["CT_PRIMARY_SPLIT"]))
 if os.environ.get("CT_PRIMARY_BUDGET"):
     api.set_option("primary_budget", int(os.environ["CT_PRIMARY_BUDGET"]))
 for R, shift, budget, run in [(R, sh, b, rn) for R in ranks for sh in shifts for b in budgets for rn in runs]:

@@ -47,6 +47,8 @@ CASES = {
     "import640": (lambda: golden_scene("scene_import"), 640, 640, 10),
 }
 
+if os.environ.get("CT_PRIMARY_SPLIT"):
+    api.set_option("primary_split", int(os.environ["CT_PRIMARY_SPLIT"]))
 if os.environ.get("CT_PRIMARY_BUDGET"):
     api.set_option("primary_budget", int(os.environ["CT_PRIMARY_BUDGET"]))      # experiments: -1 = never park a primary walk
 names = sys.argv[1:] or ["dragon4k", "bunny1080", "pcbig1080", "cube640", "import640"]
