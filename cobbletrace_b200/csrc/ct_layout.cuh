@@ -121,6 +121,7 @@ struct Params {
     uint32_t pos_of_tri0;            // leaf position of original triangle 0 (closestIndex default, raythread.cpp:205)
     uint32_t budget;                 // see kDefaultBudget
     uint32_t warp_budget;            // see kWarpBudget
+    uint32_t any_leaves;             // leaf-list entries an any-hit walk uses (<= kAnyLeaves): 12, or 8 for scenes with 16 or more shadow-casting lights
     uint32_t primary_budget;         // pair visits after which k_primary parks a closest-hit walk for k_primary_long (0: never), see kDefaultPrimaryBudget
     double cam[3], rot[9];
     float vp_w, vp_h, vp_d;

@@ -690,6 +690,9 @@ CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint
         return leaf_spill[i - kSmLeaves];
     };
     int sp = 0, nleaf = 0;
+    // a lane walks on while its list has room for a visit's worth of leaves; an any-hit walk may be told to use less of the list
+    // (P.any_leaves: many-light scenes, where most rays are occluded and want their leaves tested early)
+    const int leaf_room = (MODE == kAnyHit ? min(kLeaves, (int)P.any_leaves) : kLeaves) - kWide;
     uint32_t spent = 1u;
     uint32_t cur_ref = 0u, cur_cnt = P.root_cnt;          // wide node 0 = the root's descendants; a leaf root has no wide tree
     if (P.root_cnt > 0u) cur_ref = P.root_ref;
@@ -705,8 +708,8 @@ CT_DEV int traverse_wide(const Params &P, const TRay &r, bool active, const uint
     }
     while (true) {
         // ---- walk phase: one wide-node visit per walking lane and iteration; leaves go to the list
-        while (__any_sync(kFullMask, (state == 1) & (nleaf <= kLeaves - kWide))) {
-            if ((state == 1) & (nleaf <= kLeaves - kWide)) {
+        while (__any_sync(kFullMask, (state == 1) & (nleaf <= leaf_room))) {
+            if ((state == 1) & (nleaf <= leaf_room)) {
                 if (cur_cnt > 0u) {                       // a leaf that came off the stack (or a leaf root)
                     leaf_put(nleaf, cur_ref, cur_cnt); nleaf++;
                     spent += cur_cnt;

@@ -230,6 +230,8 @@ int ct_gpu_sync(int device);
  *   "primary_budget"    pair visits after which a primary ray's closest-hit walk is given up and the ray parked for a second
  *                       kernel that walks the long rays together (same result; measured slower): 0 = default (never), < 0 = never.
  *                       Read at upload.
+ *   "any_leaves"        leaf-list entries a shadow ray's walk fills before its warp tests the deferred leaves (5..12; larger values mean 12):
+ *                       0 = default (12; 8 for scenes with 16 or more shadow-casting lights).  Read at upload.  Never changes a result.
  *   "primary_split"     1: the parked primary rays are finished ONE RAY PER WARP (k_primary_split: the order-free closest-hit search as
  *                       a 32-wide frontier, ~12 rounds instead of up to ~300 dependent visits) instead of 32 rays to a warp; 0 (default).
  *                       Applies to the next render.
