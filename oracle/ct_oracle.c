@@ -701,7 +701,7 @@ int ct_oracle_closest_free(const ct_oracle_scene *s, const double org[3], const 
         if (!(mk < 1e30)) { stats[2]++; return -1; }                               /* zero / non-finite direction component */
         m = fmax(m, mk);
     }
-    c.sigma = m * 0x1p-16;
+    c.sigma = m * 0x1p-15;                                 /* as tray_nearest_setup (ct_exact.cuh) */
     float t0;
     stats[0]++;
     if (!box_times_ref(&r, s->node_min, s->node_max, &t0)) { *index = 0; *tclosest = FINF; return 0; }
@@ -773,7 +773,7 @@ int ct_oracle_closest_rounds(const ct_oracle_scene *s, const double org[3], cons
         if (!(mk < 1e30)) return -1;
         m = fmax(m, mk);
     }
-    c.sigma = m * 0x1p-16;
+    c.sigma = m * 0x1p-15;                                 /* as tray_nearest_setup (ct_exact.cuh) */
     float t0;
     if (!box_times_ref(&r, s->node_min, s->node_max, &t0)) { *index = 0; *tclosest = FINF; return 0; }
     enum { CAP = 4096 };
@@ -856,4 +856,35 @@ void ct_oracle_rounds_check(const ct_oracle_scene *s, uint64_t n, const double *
         if (visits > out[5]) { out[5] = visits; out[7] = rounds; }
         if (rounds > out[6]) out[6] = rounds;
     }
+}
+
+/* ---- the slop bound of the order-free walk, measured: for n (ray, triangle) cases the box of the triangle alone (the tightest leaf box the
+ * builder can produce, bvh.cpp:30-49) against the triangle's own t, both in the reference's arithmetic.  out[0] = barycentric passes with
+ * 1e-4 < t < 1e30, out[1] = max over them of (tmin(box) - t) / M with M = max_k (bound_k + |o_k|) / |d_k| as tray_nearest_setup defines it
+ * (bound_k = the largest |coordinate| of the triangle on axis k), out[2] = cases skipped for being outside the analysis' magnitude limits. */
+void ct_oracle_slop_check(uint64_t n, const double *org, const double *dir, const double *tri, double out[3]) {
+    out[0] = out[1] = out[2] = 0;
+    double worst = -1e300;
+    for (uint64_t i = 0; i < n; i++) {
+        const double *o = org + 3 * i, *d = dir + 3 * i, *t = tri + 9 * i;
+        double bmin[3], bmax[3], bound[3], M = 0, B = 0, O = 0, D = 0;
+        int ok = 1;
+        for (int a = 0; a < 3; a++) {
+            bmin[a] = fmin(fmin(t[a], t[3 + a]), t[6 + a]); bmax[a] = fmax(fmax(t[a], t[3 + a]), t[6 + a]);
+            bound[a] = fmax(fabs(bmin[a]), fabs(bmax[a]));
+            if (!(fabs(d[a]) > 0)) ok = 0;
+            M = fmax(M, (bound[a] + fabs(o[a])) / fabs(d[a]));
+            B = fmax(B, bound[a]); O = fmax(O, fabs(o[a])); D = fmax(D, fabs(d[a]));
+        }
+        if (!ok || !(D * B * B <= 4096.0) || !((O + B) * D * B <= 4096.0) || !(M < 0x1p60)) { out[2]++; continue; }
+        ray r = {v_load(o), v_load(d), RAY_T_INIT};
+        if (!intersect_triangle(&r, t) || r.t == RAY_T_INIT) continue;
+        float tmin;
+        ray r0 = {v_load(o), v_load(d), RAY_T_INIT};
+        box_times_ref(&r0, bmin, bmax, &tmin);
+        out[0]++;
+        double ratio = ((double)tmin - (double)r.t) / M;
+        if (ratio > worst) worst = ratio;
+    }
+    out[1] = worst;
 }

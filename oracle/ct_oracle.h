@@ -103,6 +103,9 @@ int ct_oracle_closest_rounds(const ct_oracle_scene *s, const double org[3], cons
                              uint32_t *rounds, uint32_t *pair_visits);
 void ct_oracle_rounds_check(const ct_oracle_scene *s, uint64_t n, const double *org, const double *dir, uint32_t min_visits, uint64_t out[8]);
 
+/* The slop bound of the order-free walk, measured on (ray, triangle) cases: out[0] passes, out[1] max (tmin(box) - t) / M, out[2] skipped. */
+void ct_oracle_slop_check(uint64_t n, const double *org, const double *dir, const double *tri, double out[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -178,6 +178,18 @@ def rounds_check(scene: "OracleScene", org, direction, min_visits=0):
     return {k: int(v) for k, v in zip(keys, out)}
 
 
+def slop_check(org, direction, tri):
+    """(passes, max (tmin(box of the triangle) - t) / M, skipped) over (ray, triangle) cases, all in the reference's arithmetic."""
+    org = np.ascontiguousarray(org, np.float64); direction = np.ascontiguousarray(direction, np.float64)
+    tri = np.ascontiguousarray(tri, np.float64).reshape(-1, 9)
+    out = np.zeros(3)
+    L = lib()
+    L.ct_oracle_slop_check.restype = None
+    L.ct_oracle_slop_check.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ct_oracle_slop_check(org.shape[0], _ptr(org), _ptr(direction), _ptr(tri), _ptr(out))
+    return int(out[0]), float(out[1]), int(out[2])
+
+
 def camera_rotation(yaw=0.0, pitch=0.0, roll=0.0):
     out = np.zeros(9)
     lib().ct_oracle_camera_rotation(yaw, pitch, roll, _ptr(out))
