@@ -610,6 +610,7 @@ def main():
             "bounce": 32 * counts["box_tests_reflection"] + 48 * counts["tri_tests_reflection"],
         }
         tot_k = dict(tot)
+        tot_k["primary"] = tot.get("primary", 0.0) + tot.get("primary_long", 0.0) + tot.get("primary_split", 0.0)   # (options primary_budget / primary_split)
         tot_k["shadow"] = tot.get("shadow", 0.0) + tot.get("overflow_shadow", 0.0)
         tot_k["bounce"] = tot.get("bounce", 0.0) + tot.get("overflow_bounce", 0.0)
         dominant = max(("primary", "shadow", "bounce"), key=lambda k: tot_k.get(k, 0.0))
